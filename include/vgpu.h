@@ -1,0 +1,265 @@
+/*
+ * vgpu.h — C ABI of libvgpu.so: the B200-native (sm_100a) replacement for ViyaDB's
+ * JIT-compiled columnar scan -> filter -> hash group-by-aggregate hot loop.
+ *
+ * This is the drop-in boundary. Everything above it (query JSON parsing, query::AggregateQuery,
+ * FilterArgsPacker, post-aggregation formatting/sorting) stays in the host language of the
+ * reference (C++); everything below it is hand-written CUDA. Plain C types only: no C++ types,
+ * no exceptions, no torch types. All entry points return VGPU_OK (0) or a negative vgpu_status
+ * and record a message retrievable with vgpu_last_error().
+ *
+ * What each entry point replaces in the reference (paths relative to the viyadb/viyadb tree):
+ *
+ *   vgpu_table_create / vgpu_segment_put / vgpu_table_invalidate
+ *       the physical column store the generated scan loop reads: the JIT-emitted
+ *       `class Segment : db::SegmentBase { Dimensions d; Metrics m; SegmentStats stats; }`
+ *       (src/codegen/db/store.cc:203-356), db::SegmentStore::segments_copy()
+ *       (src/db/store.h:40-44) and SegmentBase::size() (src/db/segment.h:34-39).
+ *       Host column memory is never owned by the library: put() copies into HBM.
+ *
+ *   vgpu_query_agg
+ *       the generated `extern "C" viya_query_agg(db::Table&, query::RowOutput&, query::QueryStats&,
+ *       std::vector<db::AnyNum> fargs, size_t skip, size_t limit, std::vector<db::AnyNum> hargs)`
+ *       (src/codegen/query/agg_query.cc:26-75; fn-pointer type query::AggQueryFn,
+ *       src/query/runner.h:33-35; call site src/query/runner.cc:61-62) up to and including
+ *       `stats.aggregated_recs = agg_map.size()` (src/codegen/query/scan.cc:168-247), i.e.
+ *         - segment loop + segment skip       scan.cc:40-51, filter.cc:263-349
+ *         - row predicate                      scan.cc:56-65, filter.cc:206-261
+ *         - group key build + time rollup      scan.cc:193-224, codegen/db/rollup.cc:25-95, util/time.h
+ *         - agg_map[key].Update(metrics)       scan.cc:228-242, codegen/db/store.cc:31-169
+ *         - count-distinct (util::Bitset |=)   util/bitset.h:26-67 over CRoaring
+ *       The plan is DATA (predicate program + raw AnyNum argument bytes exactly as the reference's
+ *       own FilterArgsPacker produces them, src/codegen/query/filter.cc:100-124) — nothing is
+ *       compiled per query.
+ *
+ *   vgpu_result_*
+ *       the `agg_map` the generated post-aggregation code iterates
+ *       (src/codegen/query/post_agg.cc:26-147) and the four QueryStats counters
+ *       (src/query/stats.h:35-58). HAVING / dict decode / formatting / sort / skip / limit remain
+ *       host code.
+ *
+ *   vgpu_comm_* / vgpu_query_agg_partial / vgpu_partial_*
+ *       multi-GPU: segments shard across the GPUs of one box, one process per GPU; the per-GPU
+ *       partial group tables are merged with one NCCL exchange. The reference's only counterpart
+ *       is the cluster controller's HTTP fan-out + TSV re-aggregation
+ *       (src/cluster/query/agg_runner.cc:93-140), whose *semantics* (merge = the same
+ *       commutative Update) are kept, not its transport.
+ */
+#ifndef VGPU_H_
+#define VGPU_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VGPU_ABI_VERSION 1
+
+typedef enum vgpu_status {
+  VGPU_OK = 0,
+  VGPU_ERR_INVALID = -1,     /* bad argument / malformed plan or schema            */
+  VGPU_ERR_UNSUPPORTED = -2, /* outside the reference's own domain */
+  VGPU_ERR_CUDA = -3,        /* CUDA runtime / driver failure                      */
+  VGPU_ERR_NOMEM = -4,       /* device or host allocation failed                   */
+  VGPU_ERR_NCCL = -5,        /* NCCL failure                                       */
+  VGPU_ERR_STATE = -6        /* call order / missing segment / shut down           */
+} vgpu_status;
+
+/* Element types: db::NumericType::Type (src/db/column.h:67-78) + the UIntType code widths. */
+typedef enum vgpu_type {
+  VGPU_U8 = 0, VGPU_U16 = 1, VGPU_U32 = 2, VGPU_U64 = 3,
+  VGPU_I8 = 4, VGPU_I16 = 5, VGPU_I32 = 6, VGPU_I64 = 7,
+  VGPU_F32 = 8, VGPU_F64 = 9
+} vgpu_type;
+
+/* Column kinds: db::Dimension::DimType (column.h:153) and the two Metric classes. */
+typedef enum vgpu_col_kind {
+  VGPU_DIM_STRING = 0,    /* dict code, width from cardinality (column.cc:54-62)      */
+  VGPU_DIM_NUMERIC = 1,
+  VGPU_DIM_TIME = 2,      /* uint32 seconds                                           */
+  VGPU_DIM_MICROTIME = 3, /* uint64 microseconds                                      */
+  VGPU_DIM_BOOLEAN = 4,
+  VGPU_METRIC_VALUE = 5,
+  VGPU_METRIC_BITSET = 6,
+  VGPU_METRIC_HIDDEN_COUNT = 7 /* the `uint64_t _count[]` of store.cc:286-289 */
+} vgpu_col_kind;
+
+/* Same order as db::Metric::AggregationType (column.h:246). */
+typedef enum vgpu_agg {
+  VGPU_AGG_MAX = 0, VGPU_AGG_MIN = 1, VGPU_AGG_SUM = 2, VGPU_AGG_AVG = 3,
+  VGPU_AGG_COUNT = 4, VGPU_AGG_BITSET = 5, VGPU_AGG_NONE = 255
+} vgpu_agg;
+
+/* Same order as util::TimeUnit (src/util/time.h:31). WEEK has no Truncator specialisation in
+ * the reference (time.h:52-89) and is rejected with VGPU_ERR_UNSUPPORTED. */
+typedef enum vgpu_time_unit {
+  VGPU_TU_YEAR = 0, VGPU_TU_MONTH = 1, VGPU_TU_WEEK = 2, VGPU_TU_DAY = 3,
+  VGPU_TU_HOUR = 4, VGPU_TU_MINUTE = 5, VGPU_TU_SECOND = 6, VGPU_TU_NONE = 7
+} vgpu_time_unit;
+
+typedef struct vgpu_column {
+  uint32_t kind; /* vgpu_col_kind */
+  uint32_t type; /* vgpu_type; for BITSET the id width (U32 or U64; U8/U16 ids are widened to U32) */
+  uint32_t agg;  /* vgpu_agg for metrics, VGPU_AGG_NONE for dimensions */
+  uint32_t reserved;
+} vgpu_column;
+
+/* Columns are listed as the reference indexes them: all dimensions in Table::dimensions() order,
+ * then all metrics in Table::metrics() order, then (optionally) the hidden count column. */
+typedef struct vgpu_schema {
+  uint32_t ncols;
+  uint32_t ndims;
+  uint64_t segment_size; /* Table::segment_size(), src/db/table.cc:48 */
+  const vgpu_column *cols;
+} vgpu_schema;
+
+/* A BITSET metric column of one segment, flattened to CSR: row r holds
+ * values[offsets[r] .. offsets[r+1]). offsets == NULL means exactly one id per row.
+ * values are uint32_t or uint64_t according to the column's `type`. */
+typedef struct vgpu_bitset_csr {
+  const uint64_t *offsets;
+  const void *values;
+  uint64_t nvalues;
+} vgpu_bitset_csr;
+
+/* ---- predicate program ------------------------------------------------------------------
+ * Post-order encoding of the reference's filter tree AFTER FilterFactory has pushed NOT down and
+ * sorted composite children by precedence (src/query/filter.cc:36-108). Leaves consume `args`
+ * in exactly the order FilterArgsPacker emits them (filter.cc:100-124). */
+typedef enum vgpu_node_kind {
+  VGPU_NODE_RELOP = 0, /* col OP args[arg]                      (query::RelOpFilter)           */
+  VGPU_NODE_IN = 1,    /* col IN / NOT IN args[arg .. arg+n)    (query::InFilter; op: 1 = IN, 0 = NOT IN) */
+  VGPU_NODE_AND = 2,   /* AND of the previous n sub-expressions (query::CompositeFilter)       */
+  VGPU_NODE_OR = 3,
+  VGPU_NODE_EMPTY = 4  /* constant true                         (query::EmptyFilter)           */
+} vgpu_node_kind;
+
+/* Same order as query::RelOpFilter::Operator (src/query/filter.h:40-47). */
+typedef enum vgpu_relop {
+  VGPU_OP_EQ = 0, VGPU_OP_NE = 1, VGPU_OP_LT = 2, VGPU_OP_LE = 3, VGPU_OP_GT = 4, VGPU_OP_GE = 5
+} vgpu_relop;
+
+typedef struct vgpu_pred_node {
+  uint32_t kind; /* vgpu_node_kind */
+  uint32_t op;   /* vgpu_relop for RELOP; 1/0 for IN/NOT IN */
+  uint32_t col;  /* schema column index */
+  uint32_t arg;  /* first index into args */
+  uint32_t n;    /* IN: number of values; AND/OR: number of children */
+  uint32_t reserved;
+} vgpu_pred_node;
+
+#define VGPU_MAX_ROLLUP_RULES 8
+
+/* One group-by key = one query::DimOutputColumn (src/query/query.h:119-137). */
+typedef struct vgpu_key {
+  uint32_t col;
+  /* Time rollup, mirroring scan.cc:198-219: active when the TIME dimension has rollup rules or the
+   * query column has a granularity. rule_boundary[i] is `now - after_i` in the column's unit
+   * (seconds, or microseconds for microtime), computed on the host with util::Duration::add_to
+   * (src/util/time.cc:49-83, codegen/db/rollup.cc:44-75); rules in TimeDimension order
+   * (descending `after`, src/db/column.cc:346-349). First rule with value < boundary truncates. */
+  uint32_t nrules;
+  uint32_t query_granularity; /* vgpu_time_unit, VGPU_TU_NONE if absent */
+  uint32_t reserved;
+  uint64_t rule_boundary[VGPU_MAX_ROLLUP_RULES];
+  uint32_t rule_granularity[VGPU_MAX_ROLLUP_RULES];
+} vgpu_key;
+
+typedef struct vgpu_plan {
+  uint32_t nnodes;
+  uint32_t nargs;
+  const vgpu_pred_node *nodes;
+  const uint64_t *args; /* raw 8-byte db::AnyNum images (src/db/column.h:98-121) */
+  uint32_t nkeys;
+  uint32_t nmetrics;
+  const vgpu_key *keys;
+  const uint32_t *metric_cols; /* schema column indices of the selected metrics, query order */
+  uint32_t need_hidden_count;  /* AVG selected without a COUNT metric selected (scan.cc:239-241) */
+  uint32_t flags;              /* VGPU_PLAN_* */
+} vgpu_plan;
+
+#define VGPU_PLAN_FORCE_HASH 1u  /* testing: never pick the dense group table */
+#define VGPU_PLAN_FORCE_DENSE 2u /* testing: fail instead of falling back to hashing */
+
+typedef struct vgpu_ctx vgpu_ctx;
+typedef struct vgpu_table vgpu_table;
+typedef struct vgpu_result vgpu_result;
+
+/* The group table of one query (library-owned host memory, valid until vgpu_result_free). */
+typedef struct vgpu_result_view {
+  uint64_t ngroups;
+  uint32_t nkeys;
+  uint32_t nmetrics;
+  const void *const *keys;      /* keys[k]: array[ngroups] of the key column's element type */
+  const void *const *accs;      /* accs[m]: array[ngroups]; SUM/AVG/COUNT/MIN/MAX in the metric
+                                   column's own type (wrap-around like the reference, Q4);
+                                   BITSET: cardinality as uint64_t                              */
+  const uint64_t *hidden_count; /* array[ngroups] or NULL */
+  uint64_t scanned_recs;        /* QueryStats, scan.cc:44 — all segments, pruned or not */
+  uint64_t scanned_segments;    /* scan.cc:51 — processed segments only                 */
+  uint64_t aggregated_recs;     /* scan.cc:246 == ngroups                               */
+  uint64_t passed_rows;         /* rows whose predicate was true (for selectivity/B_alg) */
+  double gpu_ms;                /* device time of all kernels of this query (CUDA events) */
+  double scan_ms;               /* device time of the fused scan kernel alone             */
+  uint32_t launches;            /* kernels launched for this query                        */
+  uint32_t table_mode;          /* 0 dense, 1 hash64 */
+  uint64_t table_cells;         /* dense cells or hash capacity */
+} vgpu_result_view;
+
+/* ---- lifecycle ---- */
+int vgpu_abi_version(void);
+int vgpu_init(int device, vgpu_ctx **out);
+/* Use an existing CUDA stream (cudaStream_t as void*) instead of the context's own. */
+int vgpu_set_stream(vgpu_ctx *ctx, void *cuda_stream);
+void vgpu_shutdown(vgpu_ctx *ctx);
+const char *vgpu_last_error(void);
+
+/* ---- column store ---- */
+int vgpu_table_create(vgpu_ctx *ctx, const vgpu_schema *schema, vgpu_table **out);
+void vgpu_table_free(vgpu_table *table);
+/* Copy rows [0,nrows) of every column of segment seg_idx into HBM. col_ptrs[c] is the host base
+ * address of the column array (any alignment; may be pageable or pinned), or a vgpu_bitset_csr*
+ * for BITSET columns. Replaces any previous content of that segment. */
+int vgpu_segment_put(vgpu_table *table, uint32_t seg_idx, uint64_t nrows,
+                     const void *const *col_ptrs);
+int vgpu_table_invalidate(vgpu_table *table, uint32_t seg_idx);
+uint32_t vgpu_table_segments(const vgpu_table *table);
+uint64_t vgpu_table_rows(const vgpu_table *table);
+uint64_t vgpu_table_bytes(const vgpu_table *table);
+
+/* Synthetic segment written directly in HBM (bench / parity at sizes no host buffer should
+ * carry): value(row, c) = lo + (mode ? (row / div) : splitmix64(seed*0x100000001B3 + row*16 + c)) % range,
+ * with row = row_offset + r. One entry per schema column; BITSET columns get one id per row. */
+typedef struct vgpu_gen_col {
+  int64_t lo;
+  uint64_t range;
+  uint32_t mode; /* 0 = hash, 1 = div */
+  uint32_t reserved;
+  uint64_t div;
+} vgpu_gen_col;
+int vgpu_segment_generate(vgpu_table *table, uint32_t seg_idx, uint64_t nrows,
+                          const vgpu_gen_col *gens, uint64_t seed, uint64_t row_offset);
+/* Copy a device-resident column back (tests): out must hold nrows * elem bytes. */
+int vgpu_segment_read(vgpu_table *table, uint32_t seg_idx, uint32_t col, void *out);
+
+/* ---- the hot path ---- */
+int vgpu_query_agg(vgpu_table *table, const vgpu_plan *plan, vgpu_result **out);
+int vgpu_result_get(const vgpu_result *res, vgpu_result_view *view);
+void vgpu_result_free(vgpu_result *res);
+
+/* ---- multi-GPU (one process per GPU) ----
+ * unique_id is the 128-byte ncclUniqueId produced by rank 0 (vgpu_comm_unique_id) and distributed
+ * by the host's own plumbing (torch.distributed, MPI, a file...). After vgpu_comm_init,
+ * vgpu_query_agg merges the per-GPU partial group tables over NCCL and every rank returns the
+ * full result. */
+int vgpu_comm_unique_id(void *unique_id_128);
+int vgpu_comm_init(vgpu_ctx *ctx, int rank, int nranks, const void *unique_id_128);
+int vgpu_comm_destroy(vgpu_ctx *ctx);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif /* VGPU_H_ */
