@@ -182,6 +182,7 @@ static void dump_table(db::Table &table, const std::string &path) {
   out.write(blob.data(), blob.size());
 }
 
+#ifndef VGPU_DUMP_ONLY
 int main(int argc, char **argv) {
   if (argc < 2) {
     std::cerr << "usage: oracle_cli <job.json>\n";
@@ -335,3 +336,4 @@ int main(int argc, char **argv) {
   std::cout << out.dump() << std::endl;
   return 0;
 }
+#endif  // VGPU_DUMP_ONLY

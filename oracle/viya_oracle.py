@@ -1,0 +1,697 @@
+"""oracle/viya_oracle.py — TEST INFRASTRUCTURE, not product code.
+
+A CPU restatement (numpy + pure-Python loops) of the reference's JIT-generated aggregate query
+function, `viya_query_agg` (src/codegen/query/agg_query.cc:26-75). It is the *checker* for the CUDA
+path: only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline leg may import it. Nothing
+under viyadb_b200/ imports it, and it imports nothing from viyadb_b200/.
+
+Parity status: PINNED. This restatement is itself checked (tests/test_oracle_golden.py) against
+  * the golden vectors of the reference's own gtest files (test/aggregation.cc, filter.cc,
+    metrics.cc, bitset.cc, boolean.cc, time.cc, index.cc, sort.cc, limits.cc), re-run through the
+    REAL reference (oracle/_ref/oracle_cli, built by oracle/Makefile from the unmodified sources)
+    and committed under tests/golden/ by tests/golden/make_golden.py, and
+  * small-N twins of the benchmark configs C0-C4 produced the same way.
+
+What each function follows (paths relative to the viyadb/viyadb tree):
+  parse_schema         src/db/table.cc:47-96, src/db/column.cc:54-62,275-402
+  make_filter          src/query/filter.cc:36-108        (NOT push-down, precedence sort)
+  decode_literal       src/codegen/query/filter.cc:154-204, src/db/dictionary.cc:46-75
+  eval_filter          src/codegen/query/filter.cc:206-261 (branch-free &,| ; IN = OR chain)
+  process_segment      src/codegen/query/filter.cc:263-335 (incl. the NOT IN pruning quirk)
+  rollup_boundaries    src/codegen/db/rollup.cc:44-75, src/util/time.cc:49-83
+  rollup_key           src/codegen/query/scan.cc:198-219, src/codegen/db/rollup.cc:77-95, src/util/time.h:52-137
+  aggregate            src/codegen/query/scan.cc:168-247, src/codegen/db/store.cc:31-169
+  post_aggregate       src/codegen/query/post_agg.cc:26-147, sort.cc:24-73, src/util/format.h, util/string.h
+"""
+import calendar
+import functools
+import re
+import struct
+import time as _time
+
+import numpy as np
+
+NP = {"u8": "<u1", "u16": "<u2", "u32": "<u4", "u64": "<u8", "i8": "<i1", "i16": "<i2", "i32": "<i4",
+      "i64": "<i8", "f32": "<f4", "f64": "<f8"}
+_NUM = {"byte": "i8", "ubyte": "u8", "short": "i16", "ushort": "u16", "int": "i32", "uint": "u32",
+        "long": "i64", "ulong": "u64", "float": "f32", "double": "f64"}
+UNITS = ["year", "month", "week", "day", "hour", "minute", "second"]
+
+
+def _uint_type(max_value):
+    m = (int(max_value) - 1) & 0xFFFFFFFFFFFFFFFF          # column.cc:54-62
+    return "u8" if m < 0xFF else "u16" if m < 0xFFFF else "u32" if m < 0xFFFFFFFF else "u64"
+
+
+# ------------------------------------------------------------------------------------------------
+# durations / calendar (util::Duration::add_to, gmtime_r + field add + timegm)
+# ------------------------------------------------------------------------------------------------
+def _timegm_norm(y, mon0, mday, hh, mm, ss):
+    y += mon0 // 12
+    mon0 %= 12
+    return calendar.timegm((y, mon0 + 1, 1, 0, 0, 0)) + (mday - 1) * 86400 + hh * 3600 + mm * 60 + ss
+
+
+def duration_parse(desc):
+    n, unit = desc.split()[:2]
+    n = int(n)
+    if n <= 0:
+        raise ValueError("Wrong duration description: " + desc)
+    return UNITS.index(unit[:-1]), n
+
+
+def duration_add(dur, ts, sign):
+    unit, count = dur
+    tm = _time.gmtime(ts & 0xFFFFFFFF)
+    f = [tm.tm_year, tm.tm_mon - 1, tm.tm_mday, tm.tm_hour, tm.tm_min, tm.tm_sec]
+    d = sign * count
+    if unit == 0:
+        f[0] += d
+    elif unit == 1:
+        f[1] += d
+    elif unit == 2:
+        f[2] += 7 * d
+    elif unit == 3:
+        f[2] += d
+    elif unit == 4:
+        f[3] += d
+    elif unit == 5:
+        f[4] += d
+    else:
+        f[5] += d
+    return _timegm_norm(*f) & 0xFFFFFFFF
+
+
+# ------------------------------------------------------------------------------------------------
+# schema
+# ------------------------------------------------------------------------------------------------
+class Col:
+    pass
+
+
+def parse_schema(conf):
+    dims, mets = [], []
+    for i, c in enumerate(conf.get("dimensions", [])):
+        d = Col()
+        d.name, d.index, d.is_dim = c["name"], i, True
+        t = c.get("type", "string")
+        d.rules, d.fmt, d.micro = [], c.get("format", ""), False
+        if t == "string":
+            d.kind, d.type, d.sort = "string", _uint_type(c.get("cardinality", 0xFFFFFFFF)), "string"
+        elif t == "boolean":
+            d.kind, d.type, d.sort = "boolean", "u8", "integer"
+        elif t in ("time", "microtime"):
+            d.kind, d.micro = "time", t == "microtime"
+            d.type, d.sort = ("u64" if d.micro else "u32"), "string"
+            if "granularity" not in c and "rollup_rules" in c:
+                rules = [(UNITS.index(r["granularity"]), duration_parse(r["after"])) for r in c["rollup_rules"]]
+                d.rules = sorted(rules, key=lambda r: -duration_add(r[1], 0, 1))     # column.cc:346-349
+        else:
+            d.kind = "numeric"
+            if t == "numeric":
+                d.type = "u64" if _uint_type(c.get("max", 0xFFFFFFFF)) == "u64" else "u32"
+            else:
+                d.type = _NUM[t]
+            d.sort = "float" if d.type in ("f32", "f64") else "integer"
+        dims.append(d)
+    for i, c in enumerate(conf.get("metrics", [])):
+        m = Col()
+        m.name, m.index, m.is_dim = c["name"], i, False
+        t = c["type"]
+        if t == "bitset":
+            m.agg, m.type, m.sort = "bitset", _uint_type(c.get("max", 0xFFFFFFFF)), "integer"
+        elif t == "count":
+            m.agg = "count"
+            m.type = "u64" if _uint_type(c.get("max", 0xFFFFFFFF)) == "u64" else "u32"
+            m.sort = "integer"
+        else:
+            base, _, agg = t.partition("_")
+            m.agg, m.type = agg, _NUM[base]
+            m.sort = "float" if m.type in ("f32", "f64") else "integer"
+        mets.append(m)
+    return dims, mets
+
+
+# ------------------------------------------------------------------------------------------------
+# filters
+# ------------------------------------------------------------------------------------------------
+_NEG = {"eq": "ne", "ne": "eq", "lt": "ge", "le": "gt", "gt": "le", "ge": "lt"}
+_PREC = {"rel": 1, "and": 2, "or": 3, "in": 4, "empty": 0}
+
+
+def make_filter(conf, negate=False):
+    """-> ('rel', op, column, value) | ('in', column, values, equal) | ('and'|'or', [children]) | ('empty',)"""
+    if not conf or "op" not in conf:
+        return ("empty",)
+    op = conf["op"]
+    if op in ("and", "or"):
+        kids = [make_filter(f, negate) for f in conf["filters"]]
+        kids = sorted(kids, key=lambda f: _PREC[f[0]])
+        if negate:
+            op = "or" if op == "and" else "and"
+        return (op, kids)
+    if op == "not":
+        return make_filter(conf["filter"], not negate)
+    if op == "in":
+        return ("in", conf["column"], [str(v) for v in conf["values"]], not negate)
+    if op in _NEG:
+        return ("rel", _NEG[op] if negate else op, conf["column"], str(conf["value"]))
+    raise ValueError("Unsupported filter operataor: " + op)
+
+
+def _stox(s):
+    m = re.match(r"^\s*([+-]?\d+)", s)
+    if not m:
+        raise ValueError("stoul")
+    return int(m.group(1))
+
+
+def decode_literal(col, value, dicts):
+    """ValueDecoder: returns a numpy scalar of the column's type."""
+    dt = np.dtype(NP[col.type])
+    if col.is_dim and col.kind == "string":
+        c2v = dicts[col.name]
+        try:
+            code = c2v.index(value)
+        except ValueError:
+            code = int(np.iinfo(dt).max)                       # dictionary.cc:46-75
+        return dt.type(code)
+    if col.is_dim and col.kind == "boolean":
+        return dt.type(1 if value == "true" else 0)
+    if col.is_dim and col.kind == "time" and not (value != "" and all(ch.isdigit() for ch in value)):
+        mult = 1000000 if col.micro else 1
+        ts = 0
+        m = re.match(r"^\s*(\d{1,4})-(\d{1,2})-(\d{1,2})\s+(\d{1,2}):(\d{1,2}):(\d{1,2})(.*)$", value)
+        if m:
+            base = _timegm_norm(int(m[1]), int(m[2]) - 1, int(m[3]), int(m[4]), int(m[5]), int(m[6]))
+            if m[7] == "":
+                ts = base * mult
+            elif col.micro and m[7].startswith("."):
+                raise ValueError("stoul")                      # filter.cc:178: stoul(".xxx") throws
+        else:
+            m = re.match(r"^\s*(\d{1,4})-(\d{1,2})-(\d{1,2})$", value)
+            if m:
+                ts = _timegm_norm(int(m[1]), int(m[2]) - 1, int(m[3]), 0, 0, 0) * mult
+        if ts <= 0:
+            raise ValueError("Unrecognized time format: " + value)
+        return dt.type(ts & int(np.iinfo(dt).max))
+    if dt.kind == "f":
+        return dt.type(float(value))
+    v = _stox(value)
+    bits = dt.itemsize * 8
+    v &= (1 << bits) - 1
+    if dt.kind == "i" and v >= 1 << (bits - 1):
+        v -= 1 << bits
+    return dt.type(v)
+
+
+_CMP = {"eq": np.equal, "ne": np.not_equal, "lt": np.less, "le": np.less_equal, "gt": np.greater,
+        "ge": np.greater_equal}
+
+
+def _col_values(col, seg):
+    v = seg[col.name]
+    if not col.is_dim and col.agg == "bitset":
+        offsets = v[0]
+        return (offsets[1:] - offsets[:-1]).astype(NP["u64"])   # .cardinality()  (filter.cc:215-217)
+    return v
+
+
+def eval_filter(f, seg, n, cols, dicts):
+    """Row predicate over one segment, exactly the &,| tree of ComparisonBuilder."""
+    kind = f[0]
+    if kind == "empty":
+        return np.ones(n, dtype=bool)
+    if kind == "rel":
+        col = cols[f[2]]
+        a = decode_literal(col, f[3], dicts)
+        return _CMP[f[1]](_col_values(col, seg), a)
+    if kind == "in":
+        col = cols[f[1]]
+        vals = _col_values(col, seg)
+        r = None
+        for s in f[2]:
+            a = decode_literal(col, s, dicts)
+            x = (vals == a) if f[3] else (vals != a)
+            r = x if r is None else ((r | x) if f[3] else (r & x))
+        return r
+    r = None
+    for c in f[1]:
+        x = eval_filter(c, seg, n, cols, dicts)
+        r = x if r is None else ((r & x) if kind == "and" else (r | x))
+    return r
+
+
+def _type_min(t):
+    dt = np.dtype(NP[t])
+    if dt.kind == "f":
+        return dt.type(np.finfo(dt).tiny)                      # FLT_MIN / DBL_MIN (column.cc:214-219)
+    return dt.type(np.iinfo(dt).min)
+
+
+def _type_max(t):
+    dt = np.dtype(NP[t])
+    return dt.type(np.finfo(dt).max) if dt.kind == "f" else dt.type(np.iinfo(dt).max)
+
+
+def segment_stats(col, seg, n):
+    """SegmentStats (store.cc:171-201): dmax starts at cpp_min_value, dmin at cpp_max_value."""
+    dmax, dmin = _type_min(col.type), _type_max(col.type)
+    if n:
+        v = seg[col.name][:n]
+        dmax, dmin = max(dmax, v.max()), min(dmin, v.min())
+    return dmin, dmax
+
+
+def process_segment(f, seg, n, cols, dicts):
+    kind = f[0]
+    if kind == "empty":
+        return True
+    if kind == "rel":
+        col = cols[f[2]]
+        if not (col.is_dim and col.kind in ("numeric", "time")):
+            return True
+        a = decode_literal(col, f[3], dicts)
+        dmin, dmax = segment_stats(col, seg, n)
+        op = f[1]
+        if op == "eq":
+            return bool(dmin <= a) and bool(dmax >= a)
+        if op in ("lt", "le"):
+            return bool(dmin <= a)
+        if op in ("gt", "ge"):
+            return bool(dmax >= a)
+        return True
+    if kind == "in":
+        col = cols[f[1]]
+        if not (col.is_dim and col.kind in ("numeric", "time")):
+            return True
+        dmin, dmax = segment_stats(col, seg, n)
+        r = False
+        for s in f[2]:                                         # equal() is ignored: filter.cc:303-327
+            a = decode_literal(col, s, dicts)
+            r = r or (bool(dmin <= a) and bool(dmax >= a))
+        return r
+    rs = [process_segment(c, seg, n, cols, dicts) for c in f[1]]
+    return all(rs) if kind == "and" else any(rs)
+
+
+# ------------------------------------------------------------------------------------------------
+# time rollup
+# ------------------------------------------------------------------------------------------------
+def _trunc_seconds(t, unit):
+    """Truncator::trunc<U> on gmtime_r fields, then timegm (time.h:52-89)."""
+    tm = _time.gmtime(int(t))
+    y, mo, d, hh, mm, ss = tm.tm_year, tm.tm_mon, tm.tm_mday, tm.tm_hour, tm.tm_min, tm.tm_sec
+    if unit <= 5:
+        ss = 0
+    if unit <= 4:
+        mm = 0
+    if unit <= 3:
+        hh = 0
+    if unit <= 1:
+        d = 1
+    if unit == 0:
+        mo = 1
+    if unit == 2:
+        raise RuntimeError("Truncator::trunc<WEEK> has no specialisation in the reference")
+    return calendar.timegm((y, mo, d, hh, mm, ss))
+
+
+def rollup_boundaries(dim, now):
+    out = []
+    for gran, after in dim.rules:
+        b = duration_add(after, now & 0xFFFFFFFF, -1)
+        out.append((b * 1000000 if dim.micro else b, gran))
+    return out
+
+
+def rollup_key(values, dim, boundaries, query_gran):
+    """scan.cc:198-219 per distinct value (memoised: pure function of the value)."""
+    uniq, inv = np.unique(values, return_inverse=True)
+    res = np.empty_like(uniq)
+    for i, v in enumerate(uniq.tolist()):
+        micros = v % 1000000 if dim.micro else 0
+        secs = v // 1000000 if dim.micro else v
+        truncated = False
+        for b, gran in boundaries:
+            if v < b:
+                secs = _trunc_seconds(secs, gran)
+                truncated = True
+                break
+        if query_gran is not None:
+            secs = _trunc_seconds(secs, query_gran)
+            truncated = True
+        if dim.micro:
+            res[i] = secs * 1000000 + (0 if truncated else micros)   # Time64::trunc zeroes micros_
+        else:
+            res[i] = secs & 0xFFFFFFFF
+    return res[inv]
+
+
+# ------------------------------------------------------------------------------------------------
+# the query
+# ------------------------------------------------------------------------------------------------
+def _fmt_num(v, t):
+    if t == "f64":
+        return "%.15g" % v
+    if t == "f32":
+        return "%g" % v
+    return str(int(v))
+
+
+def _smaller_int(a, b):
+    return len(a) < len(b) if len(a) != len(b) else a < b
+
+
+def run_query(table_conf, segments, dicts, query, now=None, hidden_counts=None):
+    """segments: list of {column name -> numpy array | (offsets, values) for bitset}; rows [0,len).
+    Returns {"rows": [[str]], "stats": {...}} with rows in an unspecified group order unless sorted."""
+    dims, mets = parse_schema(table_conf)
+    cols = {c.name: c for c in dims + mets}
+    if query.get("type") != "aggregate":
+        raise ValueError("unsupported query type: " + str(query.get("type")))
+    flt = make_filter(query.get("filter"))
+    # ---- select list (query.cc:48-83) ----
+    sel_dims, sel_mets = [], []
+    idx = 0
+    if "select" in query:
+        for s in query["select"]:
+            names = [c.name for c in dims + mets] if s["column"] == "*" else [s["column"]]
+            for nme in names:
+                if nme not in cols:
+                    raise ValueError("No such column: " + nme)
+                c = cols[nme]
+                if c.is_dim:
+                    gran = UNITS.index(s["granularity"]) if (c.kind == "time" and "granularity" in s) else None
+                    fmt = s.get("format", c.fmt) if c.kind == "time" else ""
+                    sel_dims.append((c, idx, gran, fmt))
+                else:
+                    sel_mets.append((c, idx))
+                idx += 1
+    else:
+        for nme in query.get("dimensions", []):
+            c = cols.get(nme)
+            if c is None or not c.is_dim:
+                raise ValueError("No such dimension: " + nme)
+            sel_dims.append((c, idx, None, ""))     # DimOutputColumn(dim, index): no format (query.h:121-122)
+            idx += 1
+        for nme in query.get("metrics", []):
+            c = cols.get(nme)
+            if c is None or c.is_dim:
+                raise ValueError("No such metric: " + nme)
+            sel_mets.append((c, idx))
+            idx += 1
+    ncols = idx
+    sort_cols = []
+    for sc in query.get("sort", []) or []:
+        if sc["column"] not in cols:
+            raise ValueError("No such column: " + sc["column"])
+        c = cols[sc["column"]]
+        pos = next((i for d, i, _, _ in sel_dims if d is c), None)
+        if pos is None:
+            pos = next((i for m, i in sel_mets if m is c), None)
+        if pos is None:
+            raise ValueError("Sort column '" + sc["column"] + "' is not selected")
+        sort_cols.append((c, pos, bool(sc.get("ascending", False))))
+    having = None
+    if "having" in query:
+        having = make_filter(query["having"])
+        names = [d.name for d, _, _, _ in sel_dims] + [m.name for m, _ in sel_mets]
+
+        def collect(f, out):
+            if f[0] == "rel":
+                out.add(f[2])
+            elif f[0] == "in":
+                out.add(f[1])
+            elif f[0] in ("and", "or"):
+                for k in f[1]:
+                    collect(k, out)
+            return out
+        for c in collect(having, set()):
+            if c not in names:
+                raise ValueError("Column '" + c + " is not selected")
+
+    if now is None:
+        now = int(_time.time())
+    has_avg = any(m.agg == "avg" for m, _ in sel_mets)
+    has_count = any(m.agg == "count" for m, _ in sel_mets)
+    need_hidden = has_avg and not has_count
+    if need_hidden and any(m.agg == "count" for m in mets):
+        # the generated code reads tuple_metrics._count (scan.cc:239-241), a member that only exists
+        # when the TABLE has an AVG metric and no COUNT metric (store.cc:286-289): g++ rejects it
+        raise RuntimeError("reference JIT compile error: 'struct Metrics' has no member named '_count'")
+
+    stats = {"scanned_segments": 0, "scanned_recs": 0, "aggregated_recs": 0, "output_recs": 0}
+    # ---- scan (scan.cc:40-73,168-247) ----
+    key_parts = [[] for _ in sel_dims]
+    met_parts = [[] for _ in sel_mets]
+    hid_parts = []
+    for si, seg in enumerate(segments):
+        n = _seg_rows(seg, dims + mets)
+        stats["scanned_recs"] += n
+        if not process_segment(flt, seg, n, cols, dicts):
+            continue
+        stats["scanned_segments"] += 1
+        if n == 0:
+            continue
+        r = eval_filter(flt, seg, n, cols, dicts)
+        sel = np.nonzero(r)[0]
+        if len(sel) == 0:
+            continue
+        for k, (d, _, gran, _) in enumerate(sel_dims):
+            v = seg[d.name][sel]
+            if d.kind == "time" and (d.rules or gran is not None):
+                v = rollup_key(v, d, rollup_boundaries(d, now), gran)
+            key_parts[k].append(v)
+        for k, (m, _) in enumerate(sel_mets):
+            if m.agg == "bitset":
+                offsets, values = seg[m.name]
+                met_parts[k].append([values[offsets[i]:offsets[i + 1]] for i in sel])
+            else:
+                met_parts[k].append(seg[m.name][sel])
+        if need_hidden:
+            hid_parts.append(hidden_counts[si][sel])
+
+    # ---- group (unordered_map<Dimensions, Metrics>) ----
+    keys = [np.concatenate(p) if p else np.zeros(0, NP[d.type]) for p, (d, _, _, _) in zip(key_parts, sel_dims)]
+    nrows = len(keys[0]) if keys else sum(len(p) for p in (met_parts[0] if met_parts else hid_parts)) if (met_parts or hid_parts) else 0
+    if not keys:
+        # no dimensions: one group if any row passed (scan.cc: agg_map[{}])
+        nrows = _count_passed(met_parts, hid_parts, segments, flt, cols, dicts, dims + mets)
+        gid = np.zeros(nrows, dtype=np.int64)
+        ngroups = 1 if nrows else 0
+        gkeys = []
+    else:
+        if nrows:
+            # float keys compare with ==: -0.0 == 0.0 (KeyEqual, store.cc:46-63); view raw bits otherwise
+            stacked = np.stack([_key_bits(k) for k in keys], axis=1)
+            uniq, gid = np.unique(stacked, axis=0, return_inverse=True)
+            gid = gid.reshape(-1)
+            ngroups = len(uniq)
+            first = np.full(ngroups, nrows, dtype=np.int64)
+            np.minimum.at(first, gid, np.arange(nrows))
+            gkeys = [k[first] for k in keys]
+        else:
+            gid, ngroups, gkeys = np.zeros(0, dtype=np.int64), 0, [k for k in keys]
+    stats["aggregated_recs"] = ngroups
+
+    gaccs = []
+    for (m, _), parts in zip(sel_mets, met_parts):
+        if m.agg == "bitset":
+            sets = [set() for _ in range(ngroups)]
+            flat = [cell for part in parts for cell in part]
+            for g, cell in zip(gid.tolist(), flat):
+                sets[g].update(cell.tolist())
+            gaccs.append(np.array([len(s) for s in sets], dtype="<u8"))
+            continue
+        dt = np.dtype(NP[m.type])
+        v = np.concatenate(parts) if parts else np.zeros(0, dt)
+        if m.agg in ("sum", "avg", "count"):
+            acc = np.zeros(ngroups, dtype=dt)                   # accumulator has the column's own type
+            if dt.kind == "f":
+                # the reference adds in row order; do the same so that float sums are reproducible
+                for g, x in zip(gid.tolist(), v):
+                    acc[g] = acc[g] + x
+            else:
+                with np.errstate(over="ignore"):
+                    np.add.at(acc, gid, v)                      # wraps modulo 2^bits like the C++ +=
+        elif m.agg == "max":
+            acc = np.full(ngroups, _type_min(m.type), dtype=dt)
+            np.maximum.at(acc, gid, v)
+        elif m.agg == "min":
+            acc = np.full(ngroups, _type_max(m.type), dtype=dt)
+            np.minimum.at(acc, gid, v)
+        else:
+            raise RuntimeError("Unsupported metric aggregation type!")
+        gaccs.append(acc)
+    ghidden = None
+    if need_hidden:
+        ghidden = np.zeros(ngroups, dtype="<u8")
+        if hid_parts:
+            np.add.at(ghidden, gid, np.concatenate(hid_parts))
+
+    # ---- post aggregation (post_agg.cc:26-147) ----
+    rows_out = []
+    skip = min(ngroups, int(query.get("skip", 0)))
+    limit = min(int(query.get("limit", 0)), ngroups - skip)
+    lo, hi = 0, ngroups
+    if not sort_cols:
+        lo = skip
+        if limit > 0:
+            hi = lo + limit
+    if query.get("header"):
+        row = [None] * ncols
+        for d, i, _, _ in sel_dims:
+            row[i] = d.name
+        for m, i in sel_mets:
+            row[i] = m.name
+        rows_out.append(row)
+    count_acc = ghidden
+    for k, (m, _) in enumerate(sel_mets):
+        if m.agg == "count":
+            count_acc = gaccs[k]
+            break
+    body = []
+    for g in range(lo, hi):
+        if having is not None and not _having(having, g, sel_dims, sel_mets, gkeys, gaccs, cols, dicts):
+            continue
+        row = [None] * ncols
+        for k, (d, i, _, fmt) in enumerate(sel_dims):
+            v = gkeys[k][g]
+            if d.kind == "string":
+                row[i] = dicts[d.name][int(v)]
+            elif d.kind == "time" and fmt:
+                row[i] = _time.strftime(fmt, _time.gmtime(int(v) & 0xFFFFFFFF))
+            elif d.kind == "boolean":
+                row[i] = "true" if v else "false"
+            else:
+                row[i] = _fmt_num(v, d.type)
+        for k, (m, i) in enumerate(sel_mets):
+            v = gaccs[k][g]
+            if m.agg == "avg":
+                c = float(count_acc[g])
+                with np.errstate(divide="ignore", invalid="ignore"):
+                    row[i] = "%.15g" % (np.float64(v) / np.float64(c))
+            elif m.agg == "bitset":
+                row[i] = str(int(v))
+            else:
+                row[i] = _fmt_num(v, m.type)
+        body.append(row)
+    if not sort_cols:
+        rows_out += body
+        stats["output_recs"] = len(body)
+    else:
+        def less(a, b):
+            nsc = len(sort_cols)
+            for j, (c, pos, asc) in enumerate(sort_cols):
+                x, y = a[pos], b[pos]
+                if c.sort == "string":
+                    lt = (x < y) if asc else (x > y)
+                    gt = (y < x) if asc else (y > x)
+                elif c.sort == "integer":
+                    lt = _smaller_int(x, y) if asc else _smaller_int(y, x)
+                    gt = _smaller_int(y, x) if asc else _smaller_int(x, y)
+                else:
+                    lt = (float(x) < float(y)) if asc else (float(x) > float(y))
+                    gt = (float(y) < float(x)) if asc else (float(y) > float(x))
+                if lt:
+                    return True
+                if j < nsc - 1 and gt:
+                    return False
+            return False
+        body.sort(key=functools.cmp_to_key(lambda a, b: -1 if less(a, b) else (1 if less(b, a) else 0)))
+        end = min(len(body), skip + limit) if limit > 0 else len(body)
+        out = body[min(skip, len(body)):end]
+        rows_out += out
+        stats["output_recs"] = len(out)
+    return {"rows": rows_out, "stats": stats,
+            "groups": {"keys": gkeys, "accs": gaccs, "hidden_count": ghidden}}
+
+
+def _seg_rows(seg, columns):
+    for c in columns:
+        v = seg[c.name]
+        if isinstance(v, tuple):
+            return len(v[0]) - 1
+        return len(v)
+    return 0
+
+
+def _count_passed(met_parts, hid_parts, segments, flt, cols, dicts, columns):
+    n = 0
+    for seg in segments:
+        rows = _seg_rows(seg, columns)
+        if rows and process_segment(flt, seg, rows, cols, dicts):
+            n += int(eval_filter(flt, seg, rows, cols, dicts).sum())
+    return n
+
+
+def _key_bits(k):
+    if k.dtype.kind == "f":
+        k = k + k.dtype.type(0)                                 # -0.0 -> +0.0 so that == groups them
+        return k.view("<u4" if k.dtype.itemsize == 4 else "<u8").astype("<u8")
+    if k.dtype.kind == "i":
+        return k.astype("<i8").view("<u8")
+    return k.astype("<u8")
+
+
+def _having(f, g, sel_dims, sel_mets, gkeys, gaccs, cols, dicts):
+    def value(name):
+        for k, (d, _, _, _) in enumerate(sel_dims):
+            if d.name == name:
+                return gkeys[k][g], d
+        for k, (m, _) in enumerate(sel_mets):
+            if m.name == name:
+                return gaccs[k][g], m
+        raise ValueError("Column '" + name + " is not selected")
+    kind = f[0]
+    if kind == "empty":
+        return True
+    if kind == "rel":
+        v, c = value(f[2])
+        a = decode_literal(c, f[3], dicts)
+        if not c.is_dim and c.agg == "bitset":
+            a = np.uint64(a)
+        return bool(_CMP[f[1]](v, a))
+    if kind == "in":
+        v, c = value(f[1])
+        r = None
+        for s in f[2]:
+            a = decode_literal(c, s, dicts)
+            if not c.is_dim and c.agg == "bitset":
+                a = np.uint64(a)
+            x = bool(v == a) if f[3] else bool(v != a)
+            r = x if r is None else ((r or x) if f[3] else (r and x))
+        return r
+    rs = [_having(c, g, sel_dims, sel_mets, gkeys, gaccs, cols, dicts) for c in f[1]]
+    return all(rs) if kind == "and" else any(rs)
+
+
+# ------------------------------------------------------------------------------------------------
+# reading the reference's dumped segments (oracle_cli "dump")
+# ------------------------------------------------------------------------------------------------
+def read_dump(path):
+    """VGPUSEG1 container -> (header, segments, dicts, hidden_counts) in run_query's input form."""
+    import json
+    with open(path, "rb") as f:
+        data = f.read()
+    assert data[:8] == b"VGPUSEG1"
+    (hl,) = struct.unpack("<Q", data[8:16])
+    hdr = json.loads(data[16:16 + hl].decode())
+    start = 16 + hl
+    start += (8 - start % 8) % 8
+    blob = memoryview(data)[start:]
+    segments, hidden = [], []
+    for seg in hdr["segments"]:
+        n = seg["size"]
+        cols = {}
+        for cj, meta in zip(seg["cols"], hdr["dims"] + hdr["metrics"]):
+            if meta.get("agg") == "bitset":
+                offsets = np.frombuffer(blob, "<u8", n + 1, cj["off"])
+                values = np.frombuffer(blob, "<u8", cj["values"], cj["values_off"])
+                cols[meta["name"]] = (offsets, values)
+            else:
+                cols[meta["name"]] = np.frombuffer(blob, NP[meta["type"]], n, cj["off"])
+        segments.append(cols)
+        hidden.append(np.frombuffer(blob, "<u8", n, seg["hidden_count"]["off"]) if "hidden_count" in seg else None)
+    return hdr, segments, hdr["dicts"], hidden

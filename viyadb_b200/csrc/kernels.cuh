@@ -1,0 +1,707 @@
+// kernels.cuh — hand-written sm_100a kernels of the scan -> filter -> group-by-aggregate path.
+//
+// Reference semantics each piece reproduces (paths relative to the viyadb/viyadb tree):
+//   predicate        src/codegen/query/filter.cc:206-261 (branch-free &,| over typed compares)
+//   key build        src/codegen/query/scan.cc:193-224
+//   time rollup      src/codegen/db/rollup.cc:77-95, src/util/time.h:52-137 (gmtime_r/timegm, UTC)
+//   Update()         src/codegen/db/store.cc:131-161 (+=, std::min, std::max, |=)
+//   count-distinct   src/util/bitset.h:26-67 (set union, cardinality)
+//
+// Design: one persistent launch over all active segments; a CTA processes tiles of
+// 4096 rows; each thread owns 4 sub-tiles x 4 consecutive rows so that every filter-column load is
+// one fully coalesced 128-bit (u32), 64-bit (u16) or 32-bit (u8) request per thread. The predicate
+// program is interpreted per 16-row register vector (uniform control flow, no divergence); key and
+// metric columns are touched only for passing rows, so their HBM traffic is sector-granular in the
+// selectivity. Group accumulators live in L2/HBM (dense mixed-radix cells, or an open-addressing
+// table keyed by the packed 64-bit key) and are updated with native RED/ATOM operations.
+#ifndef VGPU_KERNELS_CUH_
+#define VGPU_KERNELS_CUH_
+
+#include "scan_params.h"
+#include <cuda_runtime.h>
+
+namespace vgpu {
+
+constexpr uint64_t kEmptyKey = ~0ull;
+
+// ---------------------------------------------------------------------------------------------
+// streaming loads (filter columns are read exactly once: keep them out of L1)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint4 ldg_stream128(const void *p) {
+  uint4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+               : "l"(p));
+  return r;
+}
+__device__ __forceinline__ uint2 ldg_stream64(const void *p) {
+  uint2 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ uint32_t ldg_stream32(const void *p) {
+  uint32_t r;
+  asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(r) : "l"(p));
+  return r;
+}
+
+// Scalar load of one element, widened to 64 bit (zero- or sign-extended). Goes through L1 so the
+// 2-8 rows sharing a 32-byte sector are served from one HBM sector.
+__device__ __forceinline__ uint64_t load_elem(const uint8_t *p, uint32_t width, uint32_t sext) {
+  switch (width) {
+    case 1: {
+      uint8_t v = __ldg(p);
+      return sext ? (uint64_t)(int64_t)(int8_t)v : (uint64_t)v;
+    }
+    case 2: {
+      uint16_t v = __ldg(reinterpret_cast<const uint16_t *>(p));
+      return sext ? (uint64_t)(int64_t)(int16_t)v : (uint64_t)v;
+    }
+    case 4: {
+      uint32_t v = __ldg(reinterpret_cast<const uint32_t *>(p));
+      return sext ? (uint64_t)(int64_t)(int32_t)v : (uint64_t)v;
+    }
+    default:
+      return __ldg(reinterpret_cast<const unsigned long long *>(p));
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// UTC calendar arithmetic (proleptic Gregorian, no leap seconds) == glibc gmtime_r / timegm for
+// non-negative time_t, which is all util::Time32/Time64 ever see (unsigned inputs).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t trunc_days_to(uint64_t days, bool to_year) {
+  // civil_from_days / days_from_civil (H. Hinnant's public-domain algorithms), days since 1970-01-01
+  uint64_t z = days + 719468;
+  uint64_t era = z / 146097;
+  uint64_t doe = z - era * 146097;
+  uint64_t yoe = (doe - doe / 1460 + doe / 36524 - doe / 146096) / 365;
+  uint64_t doy = doe - (365 * yoe + yoe / 4 - yoe / 100);  // March-based day of year
+  uint64_t mp = (5 * doy + 2) / 153;
+  uint64_t d = doy - (153 * mp + 2) / 5 + 1;
+  if (!to_year) return days - (d - 1);
+  // first of January of the civil year: March-based months 10,11 (Jan, Feb) belong to year yoe+1
+  uint64_t y = yoe + era * 400 + (mp >= 10 ? 1 : 0);
+  // days_from_civil(y, 1, 1)
+  uint64_t yy = y - 1;
+  uint64_t era2 = yy / 400;
+  uint64_t yoe2 = yy - era2 * 400;
+  uint64_t doy2 = (153 * 10 + 2) / 5;  // January 1st, March-based
+  uint64_t doe2 = yoe2 * 365 + yoe2 / 4 - yoe2 / 100 + doy2;
+  return era2 * 146097 + doe2 - 719468;
+}
+
+__device__ __forceinline__ uint64_t trunc_seconds(uint64_t t, uint32_t unit) {
+  switch (unit) {
+    case 0: return trunc_days_to(t / 86400, true) * 86400;   // YEAR
+    case 1: return trunc_days_to(t / 86400, false) * 86400;  // MONTH
+    case 3: return t - t % 86400;                            // DAY
+    case 4: return t - t % 3600;                             // HOUR
+    case 5: return t - t % 60;                               // MINUTE
+    default: return t;                                       // SECOND / NONE
+  }
+}
+
+__device__ __forceinline__ uint64_t rollup_value(uint64_t v, const KeySpec &k) {
+  uint32_t unit = 7;  // VGPU_TU_NONE
+  for (uint32_t r = 0; r < k.nrules; ++r) {
+    if (v < k.rule_boundary[r]) {  // first matching rule wins (rollup.cc:77-95)
+      unit = k.rule_unit[r];
+      break;
+    }
+  }
+  // the query granularity truncates the same std::tm again (scan.cc:212-216): nested units, so the
+  // result is the coarser of the two
+  unit = min(unit, (uint32_t)k.query_unit);
+  if (k.micro) {
+    uint64_t secs = v / 1000000ull;
+    uint64_t micros = v - secs * 1000000ull;
+    if (unit != 7) micros = 0;  // Time64::trunc zeroes micros_ for every unit (time.h:129-132)
+    return trunc_seconds(secs, unit) * 1000000ull + micros;
+  }
+  return (uint64_t)(uint32_t)trunc_seconds(v, unit);
+}
+
+// ---------------------------------------------------------------------------------------------
+// accumulator update == Metrics::Update (store.cc:131-161), on native atomics
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void acc_update(void *acc, uint64_t cell, uint32_t op, uint64_t v) {
+  switch (op) {
+    case A_ADD32: atomicAdd(reinterpret_cast<unsigned int *>(acc) + cell, (unsigned int)v); break;
+    case A_ADD64: atomicAdd(reinterpret_cast<unsigned long long *>(acc) + cell, (unsigned long long)v); break;
+    case A_ADDF32: atomicAdd(reinterpret_cast<float *>(acc) + cell, __uint_as_float((uint32_t)v)); break;
+    case A_ADDF64: atomicAdd(reinterpret_cast<double *>(acc) + cell, __longlong_as_double((long long)v)); break;
+    case A_MINS32: atomicMin(reinterpret_cast<int *>(acc) + cell, (int)(uint32_t)v); break;
+    case A_MAXS32: atomicMax(reinterpret_cast<int *>(acc) + cell, (int)(uint32_t)v); break;
+    case A_MINU32: atomicMin(reinterpret_cast<unsigned int *>(acc) + cell, (unsigned int)v); break;
+    case A_MAXU32: atomicMax(reinterpret_cast<unsigned int *>(acc) + cell, (unsigned int)v); break;
+    case A_MINS64: atomicMin(reinterpret_cast<long long *>(acc) + cell, (long long)v); break;
+    case A_MAXS64: atomicMax(reinterpret_cast<long long *>(acc) + cell, (long long)v); break;
+    case A_MINU64: atomicMin(reinterpret_cast<unsigned long long *>(acc) + cell, (unsigned long long)v); break;
+    case A_MAXU64: atomicMax(reinterpret_cast<unsigned long long *>(acc) + cell, (unsigned long long)v); break;
+    // IEEE order on raw bits: non-negative floats order like signed ints, negative floats in
+    // reverse like unsigned ints. (NaN metrics are outside the reference's tested domain.)
+    case A_MAXF32: {
+      uint32_t b = (uint32_t)v;
+      if (!(b >> 31)) atomicMax(reinterpret_cast<int *>(acc) + cell, (int)b);
+      else atomicMin(reinterpret_cast<unsigned int *>(acc) + cell, b);
+    } break;
+    case A_MINF32: {
+      uint32_t b = (uint32_t)v;
+      if (!(b >> 31)) atomicMin(reinterpret_cast<int *>(acc) + cell, (int)b);
+      else atomicMax(reinterpret_cast<unsigned int *>(acc) + cell, b);
+    } break;
+    case A_MAXF64: {
+      if (!(v >> 63)) atomicMax(reinterpret_cast<long long *>(acc) + cell, (long long)v);
+      else atomicMin(reinterpret_cast<unsigned long long *>(acc) + cell, (unsigned long long)v);
+    } break;
+    case A_MINF64: {
+      if (!(v >> 63)) atomicMin(reinterpret_cast<long long *>(acc) + cell, (long long)v);
+      else atomicMax(reinterpret_cast<unsigned long long *>(acc) + cell, (unsigned long long)v);
+    } break;
+    default: break;
+  }
+}
+
+__device__ __forceinline__ uint64_t mix64(uint64_t x) {
+  x ^= x >> 33;
+  x *= 0xff51afd7ed558ccdULL;
+  x ^= x >> 33;
+  x *= 0xc4ceb9fe1a85ec53ULL;
+  x ^= x >> 33;
+  return x;
+}
+
+// Find-or-claim the cell of `key` in the open-addressing table. The all-ones key (== the EMPTY
+// marker) gets the dedicated cell `cap`. Returns ~0 on probe-limit overflow.
+__device__ __forceinline__ uint64_t hash_cell(const ScanParams &P, uint64_t key) {
+  if (key == kEmptyKey) {
+    P.present[0] = 1;
+    return P.hmask + 1;
+  }
+  uint64_t slot = mix64(key) & P.hmask;
+  for (uint32_t probe = 0; probe < P.max_probe; ++probe) {
+    uint64_t k = *reinterpret_cast<volatile uint64_t *>(P.hkeys + slot);
+    if (k == key) return slot;
+    if (k == kEmptyKey) {
+      unsigned long long old = atomicCAS(reinterpret_cast<unsigned long long *>(P.hkeys + slot),
+                                         (unsigned long long)kEmptyKey, (unsigned long long)key);
+      if (old == kEmptyKey || old == key) return slot;
+    }
+    slot = (slot + 1) & P.hmask;
+  }
+  return kEmptyKey;
+}
+
+// ---------------------------------------------------------------------------------------------
+// predicate interpreter: 16 rows per thread, bit (s*4+j) of the result = row s*1024 + tid*4 + j
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void load_vec16(const uint8_t *col, uint32_t width, uint64_t row0,
+                                           uint32_t (&v)[kRowsPerThread]) {
+  if (width == 4) {
+    uint4 q[kSub];
+#pragma unroll
+    for (int s = 0; s < kSub; ++s) q[s] = ldg_stream128(col + (row0 + (uint64_t)s * kSubRows) * 4);
+#pragma unroll
+    for (int s = 0; s < kSub; ++s) {
+      v[s * 4 + 0] = q[s].x; v[s * 4 + 1] = q[s].y; v[s * 4 + 2] = q[s].z; v[s * 4 + 3] = q[s].w;
+    }
+  } else if (width == 2) {
+    uint2 q[kSub];
+#pragma unroll
+    for (int s = 0; s < kSub; ++s) q[s] = ldg_stream64(col + (row0 + (uint64_t)s * kSubRows) * 2);
+#pragma unroll
+    for (int s = 0; s < kSub; ++s) {
+      v[s * 4 + 0] = q[s].x & 0xffffu; v[s * 4 + 1] = q[s].x >> 16;
+      v[s * 4 + 2] = q[s].y & 0xffffu; v[s * 4 + 3] = q[s].y >> 16;
+    }
+  } else {
+    uint32_t q[kSub];
+#pragma unroll
+    for (int s = 0; s < kSub; ++s) q[s] = ldg_stream32(col + (row0 + (uint64_t)s * kSubRows));
+#pragma unroll
+    for (int s = 0; s < kSub; ++s) {
+      v[s * 4 + 0] = q[s] & 0xffu; v[s * 4 + 1] = (q[s] >> 8) & 0xffu;
+      v[s * 4 + 2] = (q[s] >> 16) & 0xffu; v[s * 4 + 3] = q[s] >> 24;
+    }
+  }
+}
+
+__device__ __forceinline__ bool gen_compare(uint32_t gcls, uint32_t gop, uint64_t v, uint64_t a) {
+  switch (gcls) {
+    case G_I64: {
+      long long x = (long long)v, y = (long long)a;
+      switch (gop) { case 0: return x == y; case 1: return x != y; case 2: return x < y;
+                     case 3: return x <= y; case 4: return x > y; default: return x >= y; }
+    }
+    case G_F32: {
+      float x = __uint_as_float((uint32_t)v), y = __uint_as_float((uint32_t)a);
+      switch (gop) { case 0: return x == y; case 1: return x != y; case 2: return x < y;
+                     case 3: return x <= y; case 4: return x > y; default: return x >= y; }
+    }
+    case G_F64: {
+      double x = __longlong_as_double((long long)v), y = __longlong_as_double((long long)a);
+      switch (gop) { case 0: return x == y; case 1: return x != y; case 2: return x < y;
+                     case 3: return x <= y; case 4: return x > y; default: return x >= y; }
+    }
+    default: {  // G_U64, G_CARD
+      switch (gop) { case 0: return v == a; case 1: return v != a; case 2: return v < a;
+                     case 3: return v <= a; case 4: return v > a; default: return v >= a; }
+    }
+  }
+}
+
+__device__ __forceinline__ uint64_t bitset_card(const SegDesc &seg, uint32_t bidx, uint64_t row) {
+  const uint32_t *off = seg.bs_offsets[bidx];
+  if (off == nullptr) return 1;
+  return (uint64_t)(__ldg(off + row + 1) - __ldg(off + row));
+}
+
+__device__ __forceinline__ uint32_t eval_predicate(const ScanParams &P, const SegDesc &seg,
+                                                   uint64_t row0) {
+  uint32_t stk[kStackDepth];
+#pragma unroll
+  for (int i = 0; i < kStackDepth; ++i) stk[i] = 0;
+  uint32_t v[kRowsPerThread];
+  int cached = -1;
+  for (uint32_t pc = 0; pc < P.nprog; ++pc) {
+    const PInstr &in = P.prog[pc];
+    const uint32_t kind = in.kind;
+    if (kind <= P_OR_LEAF) {
+      uint32_t m = 0;
+      const uint32_t cls = in.cls;
+      if (cls == C_TRUE) {
+        m = 0xffffu;
+      } else if (cls == C_FALSE) {
+        m = 0;
+      } else if (cls == C_GEN) {
+        const Slot &sl = P.slots[in.slot];
+#pragma unroll
+        for (int s = 0; s < kSub; ++s) {
+#pragma unroll
+          for (int j = 0; j < kVec; ++j) {
+            uint64_t row = row0 + (uint64_t)s * kSubRows + j;
+            uint64_t val = 0;
+            if (row < seg.nrows) {  // scalar path must not read past the logical end of CSR tables
+              val = sl.bitset ? bitset_card(seg, sl.bitset_idx, row)
+                              : load_elem(seg.slab + sl.off * seg.cap + row * sl.width, sl.width, sl.sext);
+            }
+            if (gen_compare(in.gcls, in.gop, val, in.arg)) m |= 1u << (s * 4 + j);
+          }
+        }
+      } else {
+        if ((int)in.slot != cached) {
+          const Slot &sl = P.slots[in.slot];
+          load_vec16(seg.slab + sl.off * seg.cap, sl.width, row0, v);
+          cached = in.slot;
+        }
+        const uint32_t a = (uint32_t)in.arg;
+        if (cls == C_EQ32) {
+#pragma unroll
+          for (int i = 0; i < kRowsPerThread; ++i) m |= (v[i] == a) ? (1u << i) : 0u;
+        } else if (cls == C_LT32) {
+          const uint32_t bias = in.bias;
+#pragma unroll
+          for (int i = 0; i < kRowsPerThread; ++i) m |= ((v[i] ^ bias) < a) ? (1u << i) : 0u;
+        } else {  // C_RNG32
+          const uint32_t bias = in.bias, len = in.arg2;
+#pragma unroll
+          for (int i = 0; i < kRowsPerThread; ++i) m |= (((v[i] ^ bias) - a) < len) ? (1u << i) : 0u;
+        }
+      }
+      if (in.neg) m ^= 0xffffu;
+      if (kind == P_PUSH) {
+#pragma unroll
+        for (int i = kStackDepth - 1; i > 0; --i) stk[i] = stk[i - 1];
+        stk[0] = m;
+      } else if (kind == P_AND_LEAF) {
+        stk[0] &= m;
+      } else {
+        stk[0] |= m;
+      }
+    } else {
+      uint32_t r = (kind == P_AND) ? (stk[1] & stk[0]) : (stk[1] | stk[0]);
+      stk[0] = r;
+#pragma unroll
+      for (int i = 1; i < kStackDepth - 1; ++i) stk[i] = stk[i + 1];
+    }
+  }
+  return stk[0];
+}
+
+// ---------------------------------------------------------------------------------------------
+// the fused scan kernel
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads, 4)
+scan_filter_groupby_kernel(const __grid_constant__ ScanParams P) {
+  __shared__ unsigned long long s_pair_base[kMaxDistinct];
+  __shared__ uint32_t s_warp_tot[kMaxDistinct][kThreads / 32];
+  __shared__ unsigned long long s_passed;
+
+  const uint32_t tid = threadIdx.x;
+  const uint32_t lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) s_passed = 0;
+  unsigned long long my_passed = 0;
+
+  for (uint64_t tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
+    const uint32_t si = (uint32_t)(tile / P.tiles_per_seg);
+    const uint32_t ti = (uint32_t)(tile - (uint64_t)si * P.tiles_per_seg);
+    const SegDesc &seg = P.segs[P.active[si]];
+    const uint64_t nrows = seg.nrows;
+    const uint64_t tile_row = (uint64_t)ti * kTileRows;
+    if (tile_row >= nrows) continue;  // uniform per CTA
+    const uint64_t row0 = tile_row + (uint64_t)tid * kVec;
+    // a full group table / pair buffer makes the host grow it and run again: stop wasting time
+    if (P.hash_mode || P.ndistinct) {
+      if (__syncthreads_or(*reinterpret_cast<volatile unsigned long long *>(&P.counters[1]) != 0ull)) break;
+    }
+
+    uint32_t mask = eval_predicate(P, seg, row0);
+    // rows past the end of a partially filled segment never count
+    if (tile_row + kTileRows > nrows) {
+#pragma unroll
+      for (int s = 0; s < kSub; ++s) {
+#pragma unroll
+        for (int j = 0; j < kVec; ++j) {
+          if (row0 + (uint64_t)s * kSubRows + j >= nrows) mask &= ~(1u << (s * 4 + j));
+        }
+      }
+    }
+    my_passed += __popc(mask);
+
+    // ---- count-distinct: reserve space in the pair buffers for this tile (one atomic per CTA) ----
+    unsigned long long pair_pos[kMaxDistinct];
+    if (P.ndistinct > 0) {
+      for (uint32_t d = 0; d < P.ndistinct; ++d) {
+        const Slot &sl = P.slots[P.mets[P.distinct_met[d]].slot];
+        uint32_t cnt = 0;
+        if (seg.bs_offsets[sl.bitset_idx] == nullptr) {
+          cnt = __popc(mask);
+        } else {
+          uint32_t m = mask;
+          while (m) {
+            int b = __ffs(m) - 1;
+            m &= m - 1;
+            uint64_t row = row0 + (uint64_t)(b >> 2) * kSubRows + (b & 3);
+            cnt += (uint32_t)bitset_card(seg, sl.bitset_idx, row);
+          }
+        }
+        uint32_t incl = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+          if (lane >= o) incl += t;
+        }
+        if (lane == 31) s_warp_tot[d][warp] = incl;
+        pair_pos[d] = incl - cnt;  // exclusive within the warp
+      }
+      __syncthreads();
+      if (tid < P.ndistinct) {
+        uint32_t tot = 0;
+        for (int w = 0; w < kThreads / 32; ++w) {
+          uint32_t t = s_warp_tot[tid][w];
+          s_warp_tot[tid][w] = tot;
+          tot += t;
+        }
+        unsigned long long base = 0;
+        if (tot) base = atomicAdd(&P.counters[2 + tid], (unsigned long long)tot);
+        if (base + tot > P.pairs_cap[tid]) {
+          atomicExch(&P.counters[1], 1ull);
+          base = ~0ull;
+        }
+        s_pair_base[tid] = base;
+      }
+      __syncthreads();
+      for (uint32_t d = 0; d < P.ndistinct; ++d) {
+        unsigned long long base = s_pair_base[d];
+        pair_pos[d] = (base == ~0ull) ? ~0ull : base + s_warp_tot[d][warp] + pair_pos[d];
+      }
+      __syncthreads();  // s_warp_tot / s_pair_base are reused by the next tile
+    }
+
+    // ---- aggregate the passing rows ----
+    while (mask) {
+      const int b = __ffs(mask) - 1;
+      mask &= mask - 1;
+      const uint64_t row = row0 + (uint64_t)(b >> 2) * kSubRows + (b & 3);
+
+      uint64_t packed = 0;
+      for (uint32_t k = 0; k < P.nkeys; ++k) {
+        const KeySpec &ks = P.keys[k];
+        const Slot &sl = P.slots[ks.slot];
+        uint64_t val = load_elem(seg.slab + sl.off * seg.cap + row * sl.width, sl.width, sl.sext);
+        if (ks.rollup) val = rollup_value(val, ks);
+        packed += (val - ks.lo) * ks.mul;
+      }
+      uint64_t cell;
+      if (P.hash_mode) {
+        cell = hash_cell(P, packed);
+        if (cell == kEmptyKey) {
+          atomicExch(&P.counters[1], 1ull);
+          continue;
+        }
+      } else {
+        cell = packed;
+        P.present[cell] = 1;
+      }
+      for (uint32_t m = 0; m < P.nmetrics; ++m) {
+        const MetSpec &ms = P.mets[m];
+        if (ms.op == A_DISTINCT) continue;
+        const Slot &sl = P.slots[ms.slot];
+        uint64_t val = load_elem(seg.slab + sl.off * seg.cap + row * sl.width, sl.width, sl.sext);
+        acc_update(ms.acc, cell, ms.op, val);
+      }
+      for (uint32_t d = 0; d < P.ndistinct; ++d) {
+        if (pair_pos[d] == ~0ull) continue;
+        const Slot &sl = P.slots[P.mets[P.distinct_met[d]].slot];
+        const uint32_t *vals = seg.bs_values[sl.bitset_idx];
+        const uint32_t *off = seg.bs_offsets[sl.bitset_idx];
+        uint64_t lo = row, hi = row + 1;
+        if (off != nullptr) { lo = __ldg(off + row); hi = __ldg(off + row + 1); }
+        for (uint64_t i = lo; i < hi; ++i) {
+          P.pairs[d][pair_pos[d]++] = (cell << 32) | (uint64_t)__ldg(vals + i);
+        }
+      }
+    }
+  }
+
+  // passed-row counter: one atomic per CTA
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) my_passed += __shfl_down_sync(0xffffffffu, my_passed, o);
+  __syncthreads();
+  if (lane == 0 && my_passed) atomicAdd(&s_passed, my_passed);
+  __syncthreads();
+  if (tid == 0 && s_passed) atomicAdd(&P.counters[0], s_passed);
+}
+
+// ---------------------------------------------------------------------------------------------
+// count-distinct: dedupe (cell,id) pairs in an open-addressing set, count new ones per cell
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+distinct_insert_kernel(const uint64_t *__restrict__ pairs, uint64_t npairs, uint64_t *set,
+                       uint64_t set_mask, uint32_t *distinct, unsigned long long *sentinel_seen) {
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < npairs;
+       i += (uint64_t)gridDim.x * blockDim.x) {
+    uint64_t key = pairs[i];
+    if (key == kEmptyKey) {  // (cell 0xffffffff, id 0xffffffff): cannot live in the set
+      if (atomicExch(sentinel_seen, 1ull) == 0ull) atomicAdd(distinct + (key >> 32), 1u);
+      continue;
+    }
+    uint64_t slot = mix64(key) & set_mask;
+    while (true) {
+      uint64_t k = *reinterpret_cast<volatile uint64_t *>(set + slot);
+      if (k == key) break;
+      if (k == kEmptyKey) {
+        unsigned long long old = atomicCAS(reinterpret_cast<unsigned long long *>(set + slot),
+                                           (unsigned long long)kEmptyKey, (unsigned long long)key);
+        if (old == kEmptyKey) {
+          atomicAdd(distinct + (key >> 32), 1u);
+          break;
+        }
+        if (old == key) break;
+      }
+      slot = (slot + 1) & set_mask;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// group extraction: present cells -> dense SoA result
+// ---------------------------------------------------------------------------------------------
+struct ExtractKey {
+  uint64_t lo, div, mod;  // value = lo + (packed / div) % mod   (mod == 0: no modulo)
+  uint32_t width;
+  uint32_t pad;
+  void *out;
+};
+struct ExtractMet {
+  const void *acc;
+  uint32_t acc_width;  // 4 or 8
+  uint32_t out_width;  // 1,2,4,8 (truncation == the reference's own-type wrap-around, Q4)
+  void *out;
+};
+struct ExtractParams {
+  uint64_t ncells;  // dense cells, or hash capacity + 1 (last = sentinel-key cell)
+  uint32_t hash_mode;
+  uint32_t nkeys, nmets;
+  const uint64_t *hkeys;
+  const uint8_t *present;
+  ExtractKey keys[kMaxKeys];
+  ExtractMet mets[kMaxMetrics + 1];
+  unsigned long long *counter;  // number of groups
+  uint32_t count_only;
+};
+
+__device__ __forceinline__ bool cell_present(const ExtractParams &E, uint64_t c, uint64_t &packed) {
+  if (!E.hash_mode) {
+    packed = c;
+    return E.present[c] != 0;
+  }
+  if (c == E.ncells - 1) {
+    packed = kEmptyKey;
+    return E.present[0] != 0;
+  }
+  packed = E.hkeys[c];
+  return packed != kEmptyKey;
+}
+
+__global__ void __launch_bounds__(256)
+extract_groups_kernel(const __grid_constant__ ExtractParams E) {
+  const uint32_t lane = threadIdx.x & 31;
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  const uint64_t limit = (E.ncells + 31) & ~31ull;  // whole warps iterate together
+  for (uint64_t c = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; c < limit; c += stride) {
+    uint64_t packed = 0;
+    bool pres = (c < E.ncells) && cell_present(E, c, packed);
+    uint32_t ballot = __ballot_sync(0xffffffffu, pres);
+    if (ballot == 0) continue;
+    unsigned long long base = 0;
+    if (lane == 0) base = atomicAdd(E.counter, (unsigned long long)__popc(ballot));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (!pres || E.count_only) continue;
+    uint64_t pos = base + __popc(ballot & ((1u << lane) - 1));
+    for (uint32_t k = 0; k < E.nkeys; ++k) {
+      const ExtractKey &ek = E.keys[k];
+      uint64_t q = packed / ek.div;
+      if (ek.mod) q %= ek.mod;
+      uint64_t v = ek.lo + q;
+      switch (ek.width) {
+        case 1: reinterpret_cast<uint8_t *>(ek.out)[pos] = (uint8_t)v; break;
+        case 2: reinterpret_cast<uint16_t *>(ek.out)[pos] = (uint16_t)v; break;
+        case 4: reinterpret_cast<uint32_t *>(ek.out)[pos] = (uint32_t)v; break;
+        default: reinterpret_cast<uint64_t *>(ek.out)[pos] = v; break;
+      }
+    }
+    for (uint32_t m = 0; m < E.nmets; ++m) {
+      const ExtractMet &em = E.mets[m];
+      uint64_t v = em.acc_width == 4 ? (uint64_t)reinterpret_cast<const uint32_t *>(em.acc)[c]
+                                     : reinterpret_cast<const uint64_t *>(em.acc)[c];
+      switch (em.out_width) {
+        case 1: reinterpret_cast<uint8_t *>(em.out)[pos] = (uint8_t)v; break;
+        case 2: reinterpret_cast<uint16_t *>(em.out)[pos] = (uint16_t)v; break;
+        case 4: reinterpret_cast<uint32_t *>(em.out)[pos] = (uint32_t)v; break;
+        default: reinterpret_cast<uint64_t *>(em.out)[pos] = v; break;
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// helpers: fills, per-column min/max (segment stats), synthetic generator
+// ---------------------------------------------------------------------------------------------
+__global__ void fill32_kernel(uint32_t *p, uint64_t n, uint32_t v) {
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (uint64_t)gridDim.x * blockDim.x)
+    p[i] = v;
+}
+__global__ void fill64_kernel(uint64_t *p, uint64_t n, uint64_t v) {
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (uint64_t)gridDim.x * blockDim.x)
+    p[i] = v;
+}
+
+// Order-preserving map of an element to uint64 (so one atomicMin/Max pair serves every type).
+__device__ __forceinline__ uint64_t to_ordered(uint64_t raw, uint32_t type) {
+  switch (type) {
+    case 4: case 5: case 6: case 7:  // signed ints (already sign-extended)
+      return raw ^ 0x8000000000000000ull;
+    case 8: {                        // f32
+      uint32_t b = (uint32_t)raw;
+      if (b == 0x80000000u) b = 0;   // -0.0 == +0.0
+      b = (b >> 31) ? ~b : (b | 0x80000000u);
+      return b;
+    }
+    case 9: {                        // f64
+      uint64_t b = raw;
+      if (b == 0x8000000000000000ull) b = 0;
+      return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
+    }
+    default:
+      return raw;
+  }
+}
+
+struct StatCol {
+  uint64_t off;
+  uint32_t width, sext, type, pad;
+};
+struct StatParams {
+  const uint8_t *slab;
+  uint64_t nrows;
+  uint32_t ncols;
+  StatCol cols[32];
+  unsigned long long *out;  // [ncols][2] ordered min, ordered max
+};
+
+__global__ void __launch_bounds__(256) column_minmax_kernel(const __grid_constant__ StatParams S) {
+  const uint32_t c = blockIdx.y;
+  const StatCol &sc = S.cols[c];
+  uint64_t mn = ~0ull, mx = 0;
+  for (uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; r < S.nrows;
+       r += (uint64_t)gridDim.x * blockDim.x) {
+    uint64_t o = to_ordered(load_elem(S.slab + sc.off + r * sc.width, sc.width, sc.sext), sc.type);
+    mn = min(mn, o);
+    mx = max(mx, o);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    mn = min(mn, __shfl_down_sync(0xffffffffu, mn, o));
+    mx = max(mx, __shfl_down_sync(0xffffffffu, mx, o));
+  }
+  if ((threadIdx.x & 31) == 0 && mn <= mx) {
+    atomicMin(&S.out[2 * c], (unsigned long long)mn);
+    atomicMax(&S.out[2 * c + 1], (unsigned long long)mx);
+  }
+}
+
+__device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
+  x += 0x9E3779B97F4A7C15ULL;
+  uint64_t z = x;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+  return z ^ (z >> 31);
+}
+
+struct GenCol {
+  uint64_t off;     // slab offset, or unused for bitset
+  uint32_t width;
+  uint32_t mode;
+  int64_t lo;
+  uint64_t range;
+  uint64_t div;
+  uint32_t *bitset_out;  // non-null: write uint32 ids here instead of the slab
+  uint32_t gen_index;    // column index used in the hash
+  uint32_t is_f32, is_f64, pad;
+};
+struct GenParams {
+  uint8_t *slab;
+  uint64_t nrows, seed, row_offset;
+  uint32_t ncols;
+  GenCol cols[32];
+};
+
+__global__ void __launch_bounds__(256) generate_kernel(const __grid_constant__ GenParams G) {
+  for (uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; r < G.nrows;
+       r += (uint64_t)gridDim.x * blockDim.x) {
+    const uint64_t row = G.row_offset + r;
+    for (uint32_t c = 0; c < G.ncols; ++c) {
+      const GenCol &gc = G.cols[c];
+      uint64_t u = gc.mode ? (row / gc.div) : splitmix64(G.seed * 0x100000001B3ULL + row * 16 + gc.gen_index);
+      int64_t v = gc.lo + (int64_t)(u % gc.range);
+      if (gc.bitset_out) { gc.bitset_out[r] = (uint32_t)v; continue; }
+      uint8_t *p = G.slab + gc.off + r * gc.width;
+      if (gc.is_f32) { *reinterpret_cast<float *>(p) = (float)v; continue; }
+      if (gc.is_f64) { *reinterpret_cast<double *>(p) = (double)v; continue; }
+      switch (gc.width) {
+        case 1: *p = (uint8_t)v; break;
+        case 2: *reinterpret_cast<uint16_t *>(p) = (uint16_t)v; break;
+        case 4: *reinterpret_cast<uint32_t *>(p) = (uint32_t)v; break;
+        default: *reinterpret_cast<uint64_t *>(p) = (uint64_t)v; break;
+      }
+    }
+  }
+}
+
+}  // namespace vgpu
+
+#endif  // VGPU_KERNELS_CUH_

@@ -1,0 +1,139 @@
+// scan_params.h — the device-side "plan": everything the fused scan kernel needs, as one POD that
+// is passed by value (__grid_constant__) so every field is a uniform constant-bank read.
+// Built on the host by planner code in vgpu.cu from a vgpu_plan (include/vgpu.h).
+#ifndef VGPU_SCAN_PARAMS_H_
+#define VGPU_SCAN_PARAMS_H_
+
+#include <stdint.h>
+
+namespace vgpu {
+
+constexpr int kThreads = 256;       // threads per CTA
+constexpr int kVec = 4;             // consecutive rows owned by a thread inside a sub-tile
+constexpr int kSub = 4;             // sub-tiles per tile
+constexpr int kRowsPerThread = kVec * kSub;
+constexpr int kSubRows = kThreads * kVec;       // 1024
+constexpr int kTileRows = kSubRows * kSub;      // 4096 rows per CTA iteration
+
+constexpr int kMaxSlots = 16;   // distinct columns one query may touch
+constexpr int kMaxProg = 64;    // predicate program length (leaves + combinators)
+constexpr int kMaxKeys = 8;
+constexpr int kMaxMetrics = 8;
+constexpr int kMaxRules = 8;
+constexpr int kStackDepth = 6;
+constexpr int kMaxDistinct = 2;
+constexpr int kMaxBitsetCols = 4;
+
+// A column as the kernel sees it.
+struct Slot {
+  uint64_t off;      // bytes per row of all preceding fixed-width columns: the column starts at
+                     // slab + off * SegDesc::cap (fixed-width columns)
+  uint32_t width;    // 1,2,4,8
+  uint32_t sext;     // 1: sign-extend narrow values (i8/i16/i32) when widening to 64 bit
+  uint32_t bitset;   // 1: BITSET column (values/offsets come from per-segment side tables)
+  uint32_t bitset_idx;  // which bitset column of the table (index into SegDesc::bs_*)
+};
+
+enum PKind : uint8_t { P_PUSH = 0, P_AND_LEAF = 1, P_OR_LEAF = 2, P_AND = 3, P_OR = 4 };
+enum PCls : uint8_t {
+  C_TRUE = 0,   // constant true
+  C_FALSE = 1,  // constant false
+  C_EQ32 = 2,   // zero-extended raw value == arg (1/2/4-byte columns)
+  C_LT32 = 3,   // (zero-extended raw value ^ bias) <u arg (1/2/4-byte columns; bias maps signed types
+                // to the order-preserving unsigned domain)
+  C_RNG32 = 4,  // ((raw ^ bias) - arg) <u arg2  (fused lo <= x < hi, peephole)
+  C_GEN = 5     // generic per-row path: 8-byte ints, float, double, bitset cardinality
+};
+// generic compare element classes
+enum GCls : uint8_t { G_I64 = 0, G_U64 = 1, G_F32 = 2, G_F64 = 3, G_CARD = 4 };
+
+struct PInstr {
+  uint8_t kind;   // PKind
+  uint8_t cls;    // PCls
+  uint8_t slot;
+  uint8_t neg;    // invert the leaf mask
+  uint8_t gcls;   // GCls for C_GEN
+  uint8_t gop;    // vgpu_relop for C_GEN
+  uint16_t pad;
+  uint32_t bias;  // C_LT32/C_RNG32
+  uint32_t arg2;  // C_RNG32: hi - lo
+  uint64_t arg;   // prepared argument (raw bits)
+};
+
+struct KeySpec {
+  uint8_t slot;
+  uint8_t rollup;      // 1: apply time rollup (scan.cc:198-219)
+  uint8_t micro;       // 1: value is microseconds (util::Time64), else seconds (util::Time32)
+  uint8_t nrules;
+  uint8_t rule_unit[kMaxRules];  // vgpu_time_unit
+  uint8_t query_unit;            // vgpu_time_unit or VGPU_TU_NONE
+  uint8_t pad[3];
+  uint64_t rule_boundary[kMaxRules];
+  uint64_t lo;    // subtracted from the (rolled-up) value
+  uint64_t mul;   // cell index / packed key = sum (v - lo) * mul
+};
+
+enum AccOp : uint8_t {
+  A_ADD32 = 0, A_ADD64 = 1, A_ADDF32 = 2, A_ADDF64 = 3,
+  A_MINS32 = 4, A_MAXS32 = 5, A_MINU32 = 6, A_MAXU32 = 7,
+  A_MINS64 = 8, A_MAXS64 = 9, A_MINU64 = 10, A_MAXU64 = 11,
+  A_MINF32 = 12, A_MAXF32 = 13, A_MINF64 = 14, A_MAXF64 = 15,
+  A_DISTINCT = 16
+};
+
+struct MetSpec {
+  uint8_t slot;
+  uint8_t op;      // AccOp
+  uint8_t pad[6];
+  void *acc;       // device accumulator array, one cell (4 or 8 bytes) per group cell
+};
+
+// Per-segment descriptor (device array, one per table segment).
+struct SegDesc {
+  const uint8_t *slab;        // fixed-width columns
+  uint64_t nrows;
+  uint64_t cap;               // row capacity of the slab (multiple of kTileRows)
+  const uint32_t *bs_values[kMaxBitsetCols];   // per bitset column: ids (uint32)
+  const uint32_t *bs_offsets[kMaxBitsetCols];  // per bitset column: CSR offsets (nrows+1) or nullptr = 1 id/row
+};
+
+struct ScanParams {
+  // work list
+  const SegDesc *segs;
+  const uint32_t *active;   // indices of segments to scan
+  uint32_t nactive;
+  uint32_t tiles_per_seg;
+  uint64_t total_tiles;
+
+  // columns
+  Slot slots[kMaxSlots];
+  uint32_t nslots;
+
+  // predicate
+  uint32_t nprog;
+  PInstr prog[kMaxProg];
+
+  // group keys
+  uint32_t nkeys;
+  uint32_t hash_mode;      // 0: dense cells, 1: open-addressing hash on the packed 64-bit key
+  KeySpec keys[kMaxKeys];
+  uint64_t *hkeys;         // hash_mode: capacity cells, EMPTY = ~0
+  uint64_t hmask;          // capacity - 1
+  uint8_t *present;        // dense: 1 byte per cell; hash: present[0] flags the sentinel key
+  uint32_t max_probe;
+
+  // metrics
+  uint32_t nmetrics;
+  MetSpec mets[kMaxMetrics];
+  uint32_t ndistinct;                 // BITSET metrics selected (count-distinct)
+  uint8_t distinct_met[kMaxDistinct]; // their indices into mets
+  uint64_t *pairs[kMaxDistinct];      // per distinct metric: (cell << 32 | id) append buffer
+  uint64_t pairs_cap[kMaxDistinct];
+
+  // counters: [0] passed rows, [1] overflow flag (hash probe limit / pair buffer), [2+d] pairs appended
+  unsigned long long *counters;
+};
+
+}  // namespace vgpu
+
+#endif  // VGPU_SCAN_PARAMS_H_

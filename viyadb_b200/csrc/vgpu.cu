@@ -1,0 +1,1593 @@
+// vgpu.cu — implementation of the C ABI declared in include/vgpu.h (libvgpu.so).
+//
+// Host side of the B200-native scan -> filter -> group-by-aggregate path: the HBM column store,
+// the planner that lowers a vgpu_plan (data, not code) to ScanParams, segment pruning with the
+// reference's exact rule (src/codegen/query/filter.cc:263-335), kernel launches, the optional
+// NCCL merge of per-GPU partial group tables and the extraction of the group table.
+// There is NO CPU implementation of the scan in this library: without a CUDA device every entry
+// point fails with VGPU_ERR_CUDA.
+#include "../../include/vgpu.h"
+#include "kernels.cuh"
+
+#include <algorithm>
+#include <cfloat>
+#include <climits>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <dlfcn.h>
+#include <memory>
+#include <mutex>
+#include <nccl.h>
+#include <string>
+#include <vector>
+
+using namespace vgpu;
+
+namespace {
+
+thread_local std::string g_err;
+
+struct Err {
+  int code;
+  std::string msg;
+};
+[[noreturn]] void fail(int code, const std::string &m) { throw Err{code, m}; }
+
+#define CUDA_CK(x)                                                                          \
+  do {                                                                                      \
+    cudaError_t e_ = (x);                                                                   \
+    if (e_ != cudaSuccess)                                                                  \
+      fail(e_ == cudaErrorMemoryAllocation ? VGPU_ERR_NOMEM : VGPU_ERR_CUDA,                \
+           std::string(#x) + ": " + cudaGetErrorString(e_));                                \
+  } while (0)
+
+template <class F> int guard(F &&f) {
+  try {
+    f();
+    return VGPU_OK;
+  } catch (const Err &e) {
+    g_err = e.msg;
+    return e.code;
+  } catch (const std::bad_alloc &) {
+    g_err = "host allocation failed";
+    return VGPU_ERR_NOMEM;
+  } catch (const std::exception &e) {
+    g_err = e.what();
+    return VGPU_ERR_INVALID;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// element types
+// ---------------------------------------------------------------------------------------------
+uint32_t type_width(uint32_t t) {
+  switch (t) {
+    case VGPU_U8: case VGPU_I8: return 1;
+    case VGPU_U16: case VGPU_I16: return 2;
+    case VGPU_U32: case VGPU_I32: case VGPU_F32: return 4;
+    case VGPU_U64: case VGPU_I64: case VGPU_F64: return 8;
+  }
+  fail(VGPU_ERR_INVALID, "unknown element type " + std::to_string(t));
+}
+bool type_signed(uint32_t t) { return t >= VGPU_I8 && t <= VGPU_I64; }
+bool type_float(uint32_t t) { return t == VGPU_F32 || t == VGPU_F64; }
+
+// raw 8-byte AnyNum image -> value widened the way the kernel widens a cell (low `width` bytes,
+// sign-extended for signed ints). The upper bytes of an AnyNum are uninitialised in the reference
+// (src/db/column.h:98-121), so they are never looked at.
+uint64_t widen_arg(uint64_t raw, uint32_t type) {
+  switch (type) {
+    case VGPU_U8: return raw & 0xffull;
+    case VGPU_U16: return raw & 0xffffull;
+    case VGPU_U32: case VGPU_F32: return raw & 0xffffffffull;
+    case VGPU_I8: return (uint64_t)(int64_t)(int8_t)(raw & 0xff);
+    case VGPU_I16: return (uint64_t)(int64_t)(int16_t)(raw & 0xffff);
+    case VGPU_I32: return (uint64_t)(int64_t)(int32_t)(raw & 0xffffffffull);
+    default: return raw;
+  }
+}
+
+// Same mapping as the device-side to_ordered(): order-preserving image in uint64.
+uint64_t to_ordered_host(uint64_t v, uint32_t type) {
+  switch (type) {
+    case VGPU_I8: case VGPU_I16: case VGPU_I32: case VGPU_I64:
+      return v ^ 0x8000000000000000ull;
+    case VGPU_F32: {
+      uint32_t b = (uint32_t)v;
+      if (b == 0x80000000u) b = 0;
+      b = (b >> 31) ? ~b : (b | 0x80000000u);
+      return b;
+    }
+    case VGPU_F64: {
+      uint64_t b = v;
+      if (b == 0x8000000000000000ull) b = 0;
+      return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
+    }
+    default: return v;
+  }
+}
+uint64_t from_ordered_int(uint64_t o, uint32_t type) {
+  return type_signed(type) ? (o ^ 0x8000000000000000ull) : o;
+}
+
+// NumericType::cpp_min_value / cpp_max_value (src/db/column.cc:187-219): the initial values of MAX /
+// MIN accumulators (store.cc:106-117) and of SegmentStats dmax / dmin (store.cc:171-184). Note
+// FLT_MIN / DBL_MIN (smallest positive) for floating point — reproduced on purpose.
+uint64_t type_min_value(uint32_t t) {
+  switch (t) {
+    case VGPU_I8: return (uint64_t)(int64_t)INT8_MIN;
+    case VGPU_I16: return (uint64_t)(int64_t)INT16_MIN;
+    case VGPU_I32: return (uint64_t)(int64_t)INT32_MIN;
+    case VGPU_I64: return (uint64_t)INT64_MIN;
+    case VGPU_F32: { float f = FLT_MIN; uint32_t b; memcpy(&b, &f, 4); return b; }
+    case VGPU_F64: { double d = DBL_MIN; uint64_t b; memcpy(&b, &d, 8); return b; }
+    default: return 0;
+  }
+}
+uint64_t type_max_value(uint32_t t) {
+  switch (t) {
+    case VGPU_U8: return UINT8_MAX;
+    case VGPU_U16: return UINT16_MAX;
+    case VGPU_U32: return UINT32_MAX;
+    case VGPU_U64: return UINT64_MAX;
+    case VGPU_I8: return INT8_MAX;
+    case VGPU_I16: return INT16_MAX;
+    case VGPU_I32: return INT32_MAX;
+    case VGPU_I64: return INT64_MAX;
+    case VGPU_F32: { float f = FLT_MAX; uint32_t b; memcpy(&b, &f, 4); return b; }
+    default: { double d = DBL_MAX; uint64_t b; memcpy(&b, &d, 8); return b; }
+  }
+}
+
+uint64_t round_up(uint64_t v, uint64_t m) { return (v + m - 1) / m * m; }
+uint64_t pow2_ceil(uint64_t v) {
+  uint64_t p = 1;
+  while (p < v) p <<= 1;
+  return p;
+}
+
+// ---------------------------------------------------------------------------------------------
+// NCCL through dlopen: single-GPU users never need the library
+// ---------------------------------------------------------------------------------------------
+struct NcclApi {
+  void *lib = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t,
+                            cudaStream_t) = nullptr;
+  ncclResult_t (*Broadcast)(const void *, void *, size_t, ncclDataType_t, int, ncclComm_t,
+                            cudaStream_t) = nullptr;
+  ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t,
+                            cudaStream_t) = nullptr;
+  ncclResult_t (*GroupStart)() = nullptr;
+  ncclResult_t (*GroupEnd)() = nullptr;
+  const char *(*GetErrorString)(ncclResult_t) = nullptr;
+};
+NcclApi g_nccl;
+std::mutex g_nccl_mu;
+
+void nccl_load() {
+  std::lock_guard<std::mutex> lk(g_nccl_mu);
+  if (g_nccl.lib) return;
+  // RTLD_NOLOAD first: reuse the copy torch already mapped (same soname), else load the system one.
+  void *lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD | RTLD_GLOBAL);
+  if (!lib) lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+  if (!lib) lib = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+  if (!lib) fail(VGPU_ERR_NCCL, std::string("cannot load libnccl.so.2: ") + dlerror());
+#define NSYM(field, name)                                                  \
+  g_nccl.field = reinterpret_cast<decltype(g_nccl.field)>(dlsym(lib, name)); \
+  if (!g_nccl.field) fail(VGPU_ERR_NCCL, std::string("missing NCCL symbol ") + name);
+  NSYM(GetUniqueId, "ncclGetUniqueId");
+  NSYM(CommInitRank, "ncclCommInitRank");
+  NSYM(CommDestroy, "ncclCommDestroy");
+  NSYM(AllReduce, "ncclAllReduce");
+  NSYM(Broadcast, "ncclBroadcast");
+  NSYM(AllGather, "ncclAllGather");
+  NSYM(GroupStart, "ncclGroupStart");
+  NSYM(GroupEnd, "ncclGroupEnd");
+  NSYM(GetErrorString, "ncclGetErrorString");
+#undef NSYM
+  g_nccl.lib = lib;
+}
+#define NCCL_CK(x)                                                                           \
+  do {                                                                                       \
+    ncclResult_t r_ = (x);                                                                   \
+    if (r_ != ncclSuccess)                                                                   \
+      fail(VGPU_ERR_NCCL, std::string(#x) + ": " + g_nccl.GetErrorString(r_));               \
+  } while (0)
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------
+// objects behind the opaque handles
+// ---------------------------------------------------------------------------------------------
+struct vgpu_ctx {
+  int device = 0;
+  int sm_count = 148;
+  cudaStream_t stream = nullptr;
+  bool own_stream = true;
+  cudaEvent_t ev_begin = nullptr, ev_scan0 = nullptr, ev_scan1 = nullptr, ev_end = nullptr;
+  unsigned long long *d_counters = nullptr;  // 16 x u64
+  unsigned long long *h_counters = nullptr;  // pinned
+  std::mutex mu;                             // one query / put at a time per context
+  // multi-GPU
+  ncclComm_t comm = nullptr;
+  int rank = 0, nranks = 1;
+  // pinned staging for results (grown on demand)
+  void *h_stage = nullptr;
+  size_t h_stage_bytes = 0;
+};
+
+namespace {
+
+struct ColInfo {
+  uint32_t kind, type, agg;
+  uint32_t width;
+  bool sext;
+  bool bitset;
+  uint32_t bitset_idx;
+  uint64_t off_per_row;  // bytes per row of the preceding fixed-width columns
+};
+
+struct SegmentData {
+  uint8_t *slab = nullptr;
+  uint64_t cap = 0;
+  uint64_t nrows = 0;
+  bool valid = false;
+  uint32_t *bs_values[kMaxBitsetCols] = {nullptr, nullptr, nullptr, nullptr};
+  uint32_t *bs_offsets[kMaxBitsetCols] = {nullptr, nullptr, nullptr, nullptr};
+  uint64_t bs_n[kMaxBitsetCols] = {0, 0, 0, 0};
+  // ordered (to_ordered) min / max of the stored values per column; only fixed-width dimensions
+  std::vector<uint64_t> omin, omax;
+};
+
+}  // namespace
+
+struct vgpu_table {
+  vgpu_ctx *ctx = nullptr;
+  std::vector<ColInfo> cols;
+  uint32_t ndims = 0;
+  uint32_t nbitsets = 0;
+  uint64_t segment_size = 0;
+  uint64_t row_bytes = 0;
+  std::vector<SegmentData> segs;
+  SegDesc *d_segs = nullptr;
+  size_t d_segs_cap = 0;
+  bool descs_dirty = true;
+  // scratch high-water marks so that a repeated query shape never re-runs on overflow
+  uint64_t hash_cap_hint = 0;
+  uint64_t pairs_cap_hint = 0;
+};
+
+struct vgpu_result {
+  std::vector<std::vector<uint8_t>> key_data, acc_data;
+  std::vector<uint64_t> hidden;
+  std::vector<const void *> key_ptrs, acc_ptrs;
+  vgpu_result_view view{};
+};
+
+namespace {
+
+// ---------------------------------------------------------------------------------------------
+// device scratch: stream-ordered pool allocations, released when the query ends
+// ---------------------------------------------------------------------------------------------
+struct Scratch {
+  cudaStream_t stream;
+  std::vector<void *> ptrs;
+  explicit Scratch(cudaStream_t s) : stream(s) {}
+  ~Scratch() {
+    for (void *p : ptrs) cudaFreeAsync(p, stream);
+  }
+  template <class T> T *alloc(uint64_t n) {
+    void *p = nullptr;
+    CUDA_CK(cudaMallocAsync(&p, std::max<uint64_t>(n, 1) * sizeof(T), stream));
+    ptrs.push_back(p);
+    return static_cast<T *>(p);
+  }
+};
+
+int grid_for(uint64_t n, int threads, int sm_count, int per_sm = 8) {
+  uint64_t blocks = (n + threads - 1) / threads;
+  uint64_t cap = (uint64_t)sm_count * per_sm;
+  return (int)std::max<uint64_t>(1, std::min(blocks, cap));
+}
+
+// return the number of kernels launched (memsets are driver operations, not our kernels)
+uint32_t fill32(cudaStream_t s, int sms, void *p, uint64_t n, uint32_t v) {
+  if (n == 0) return 0;
+  if (v == 0) { CUDA_CK(cudaMemsetAsync(p, 0, n * 4, s)); return 0; }
+  fill32_kernel<<<grid_for(n, 256, sms), 256, 0, s>>>(static_cast<uint32_t *>(p), n, v);
+  CUDA_CK(cudaGetLastError());
+  return 1;
+}
+uint32_t fill64(cudaStream_t s, int sms, void *p, uint64_t n, uint64_t v) {
+  if (n == 0) return 0;
+  if (v == 0) { CUDA_CK(cudaMemsetAsync(p, 0, n * 8, s)); return 0; }
+  if (v == ~0ull) { CUDA_CK(cudaMemsetAsync(p, 0xff, n * 8, s)); return 0; }
+  fill64_kernel<<<grid_for(n, 256, sms), 256, 0, s>>>(static_cast<uint64_t *>(p), n, v);
+  CUDA_CK(cudaGetLastError());
+  return 1;
+}
+
+// ---------------------------------------------------------------------------------------------
+// column store
+// ---------------------------------------------------------------------------------------------
+void free_segment(SegmentData &sd) {
+  if (sd.slab) cudaFree(sd.slab);
+  for (int b = 0; b < kMaxBitsetCols; ++b) {
+    if (sd.bs_values[b]) cudaFree(sd.bs_values[b]);
+    if (sd.bs_offsets[b]) cudaFree(sd.bs_offsets[b]);
+  }
+  sd = SegmentData();
+}
+
+void ensure_segment(vgpu_table *t, uint32_t seg_idx, uint64_t nrows) {
+  if (nrows > t->segment_size)
+    fail(VGPU_ERR_INVALID, "segment rows " + std::to_string(nrows) + " exceed segment_size " +
+                               std::to_string(t->segment_size));
+  if (seg_idx >= t->segs.size()) t->segs.resize(seg_idx + 1);
+  SegmentData &sd = t->segs[seg_idx];
+  uint64_t cap = round_up(std::max<uint64_t>(nrows, 1), kTileRows);
+  if (sd.slab == nullptr || sd.cap < cap) {
+    free_segment(sd);
+    if (t->row_bytes > 0) {
+      CUDA_CK(cudaMalloc(&sd.slab, t->row_bytes * cap));
+    }
+    sd.cap = cap;
+  } else {
+    for (int b = 0; b < kMaxBitsetCols; ++b) {
+      if (sd.bs_values[b]) { cudaFree(sd.bs_values[b]); sd.bs_values[b] = nullptr; }
+      if (sd.bs_offsets[b]) { cudaFree(sd.bs_offsets[b]); sd.bs_offsets[b] = nullptr; }
+      sd.bs_n[b] = 0;
+    }
+  }
+  sd.nrows = nrows;
+  sd.valid = false;
+  t->descs_dirty = true;
+}
+
+// per-column min/max of the stored cells (device reduction), kept in the ordered domain
+void compute_stats(vgpu_table *t, SegmentData &sd) {
+  vgpu_ctx *ctx = t->ctx;
+  size_t ncols = t->cols.size();
+  sd.omin.assign(ncols, ~0ull);
+  sd.omax.assign(ncols, 0ull);
+  std::vector<uint32_t> want;
+  for (uint32_t c = 0; c < t->ndims; ++c)
+    if (!t->cols[c].bitset) want.push_back(c);
+  if (sd.nrows == 0 || want.empty()) return;
+  Scratch scratch(ctx->stream);
+  for (size_t base = 0; base < want.size(); base += 32) {
+    uint32_t n = (uint32_t)std::min<size_t>(32, want.size() - base);
+    StatParams S{};
+    S.slab = sd.slab;
+    S.nrows = sd.nrows;
+    S.ncols = n;
+    std::vector<unsigned long long> init(2 * n);
+    for (uint32_t i = 0; i < n; ++i) {
+      const ColInfo &ci = t->cols[want[base + i]];
+      S.cols[i].off = ci.off_per_row * sd.cap;
+      S.cols[i].width = ci.width;
+      S.cols[i].sext = ci.sext;
+      S.cols[i].type = ci.type;
+      init[2 * i] = ~0ull;
+      init[2 * i + 1] = 0;
+    }
+    unsigned long long *d_out = scratch.alloc<unsigned long long>(2 * n);
+    CUDA_CK(cudaMemcpyAsync(d_out, init.data(), init.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
+    S.out = d_out;
+    dim3 grid(grid_for(sd.nrows, 256, ctx->sm_count, 4), n);
+    column_minmax_kernel<<<grid, 256, 0, ctx->stream>>>(S);
+    CUDA_CK(cudaGetLastError());
+    CUDA_CK(cudaMemcpyAsync(init.data(), d_out, init.size() * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_CK(cudaStreamSynchronize(ctx->stream));
+    for (uint32_t i = 0; i < n; ++i) {
+      sd.omin[want[base + i]] = init[2 * i];
+      sd.omax[want[base + i]] = init[2 * i + 1];
+    }
+  }
+}
+
+void upload_descs(vgpu_table *t) {
+  if (!t->descs_dirty) return;
+  size_t n = t->segs.size();
+  if (n > t->d_segs_cap) {
+    if (t->d_segs) cudaFree(t->d_segs);
+    t->d_segs = nullptr;
+    size_t cap = std::max<size_t>(16, n * 2);
+    CUDA_CK(cudaMalloc(&t->d_segs, cap * sizeof(SegDesc)));
+    t->d_segs_cap = cap;
+  }
+  std::vector<SegDesc> h(n);
+  for (size_t i = 0; i < n; ++i) {
+    const SegmentData &sd = t->segs[i];
+    h[i].slab = sd.slab;
+    h[i].nrows = sd.valid ? sd.nrows : 0;
+    h[i].cap = sd.cap;
+    for (int b = 0; b < kMaxBitsetCols; ++b) {
+      h[i].bs_values[b] = sd.bs_values[b];
+      h[i].bs_offsets[b] = sd.bs_offsets[b];
+    }
+  }
+  if (n) {
+    CUDA_CK(cudaMemcpyAsync(t->d_segs, h.data(), n * sizeof(SegDesc), cudaMemcpyHostToDevice,
+                            t->ctx->stream));
+    CUDA_CK(cudaStreamSynchronize(t->ctx->stream));  // h goes out of scope
+  }
+  t->descs_dirty = false;
+}
+
+// ---------------------------------------------------------------------------------------------
+// planner: vgpu_plan -> ScanParams
+// ---------------------------------------------------------------------------------------------
+struct TreeNode {
+  uint32_t kind, op, col, arg, n;
+  std::vector<int> kids;
+};
+
+struct Planner {
+  const vgpu_table *t;
+  const vgpu_plan *plan;
+  ScanParams P{};
+  std::vector<TreeNode> tree;
+  int root = -1;
+  int depth = 0, max_depth = 0;
+
+  Planner(const vgpu_table *table, const vgpu_plan *p) : t(table), plan(p) {}
+
+  uint32_t slot_of(uint32_t col) {
+    if (col >= t->cols.size()) fail(VGPU_ERR_INVALID, "column index out of range");
+    const ColInfo &ci = t->cols[col];
+    for (uint32_t s = 0; s < P.nslots; ++s)
+      if (slot_cols[s] == col) return s;
+    if (P.nslots >= kMaxSlots) fail(VGPU_ERR_UNSUPPORTED, "query touches too many columns");
+    Slot &sl = P.slots[P.nslots];
+    sl.off = ci.off_per_row;
+    sl.width = ci.width;
+    sl.sext = ci.sext;
+    sl.bitset = ci.bitset;
+    sl.bitset_idx = ci.bitset_idx;
+    slot_cols[P.nslots] = col;
+    return P.nslots++;
+  }
+  uint32_t slot_cols[kMaxSlots];
+
+  void build_tree() {
+    if (plan->nnodes == 0) {  // no filter at all == EmptyFilter
+      TreeNode e{};
+      e.kind = VGPU_NODE_EMPTY;
+      tree.push_back(e);
+      root = 0;
+      return;
+    }
+    std::vector<int> stack;
+    for (uint32_t i = 0; i < plan->nnodes; ++i) {
+      const vgpu_pred_node &pn = plan->nodes[i];
+      TreeNode tn{};
+      tn.kind = pn.kind; tn.op = pn.op; tn.col = pn.col; tn.arg = pn.arg; tn.n = pn.n;
+      switch (pn.kind) {
+        case VGPU_NODE_RELOP:
+          if (pn.op > VGPU_OP_GE) fail(VGPU_ERR_INVALID, "bad relational operator");
+          if (pn.arg >= plan->nargs) fail(VGPU_ERR_INVALID, "predicate argument out of range");
+          if (pn.col >= t->cols.size()) fail(VGPU_ERR_INVALID, "predicate column out of range");
+          break;
+        case VGPU_NODE_IN:
+          if (pn.n == 0) fail(VGPU_ERR_INVALID, "IN filter without values");
+          if ((uint64_t)pn.arg + pn.n > plan->nargs) fail(VGPU_ERR_INVALID, "predicate argument out of range");
+          if (pn.col >= t->cols.size()) fail(VGPU_ERR_INVALID, "predicate column out of range");
+          break;
+        case VGPU_NODE_AND:
+        case VGPU_NODE_OR:
+          if (pn.n == 0) fail(VGPU_ERR_INVALID, "composite filter without children");
+          if (pn.n > stack.size()) fail(VGPU_ERR_INVALID, "malformed predicate program");
+          tn.kids.assign(stack.end() - pn.n, stack.end());
+          stack.resize(stack.size() - pn.n);
+          break;
+        case VGPU_NODE_EMPTY:
+          break;
+        default:
+          fail(VGPU_ERR_INVALID, "unknown predicate node kind");
+      }
+      tree.push_back(tn);
+      stack.push_back((int)tree.size() - 1);
+    }
+    if (stack.size() != 1) fail(VGPU_ERR_INVALID, "predicate program does not reduce to one expression");
+    root = stack[0];
+  }
+
+  // ---- leaf classification ----
+  static uint32_t ord32(uint64_t widened, uint32_t type) {
+    switch (type) {
+      case VGPU_I8: return (uint32_t)(widened & 0xff) ^ 0x80u;
+      case VGPU_I16: return (uint32_t)(widened & 0xffff) ^ 0x8000u;
+      case VGPU_I32: return (uint32_t)widened ^ 0x80000000u;
+      default: return (uint32_t)widened;
+    }
+  }
+  static uint32_t bias32(uint32_t type) {
+    switch (type) {
+      case VGPU_I8: return 0x80u;
+      case VGPU_I16: return 0x8000u;
+      case VGPU_I32: return 0x80000000u;
+      default: return 0;
+    }
+  }
+  static uint32_t ordmax32(uint32_t type) {
+    switch (type_width(type)) {
+      case 1: return 0xffu;
+      case 2: return 0xffffu;
+      default: return 0xffffffffu;
+    }
+  }
+
+  void emit(PInstr in) {
+    if (P.nprog >= kMaxProg) fail(VGPU_ERR_UNSUPPORTED, "predicate too long for the device program");
+    P.prog[P.nprog++] = in;
+  }
+  void push_depth() { max_depth = std::max(max_depth, ++depth); }
+
+  static uint8_t leaf_kind(int mode) { return mode == 0 ? P_PUSH : (mode == 1 ? P_AND_LEAF : P_OR_LEAF); }
+
+  // one comparison `col OP arg`; mode 0 push, 1 and-into-top, 2 or-into-top
+  void emit_compare(uint32_t col, uint32_t op, uint64_t raw_arg, int mode) {
+    const ColInfo &ci = t->cols[col];
+    PInstr in{};
+    in.kind = leaf_kind(mode);
+    in.slot = (uint8_t)slot_of(col);
+    if (mode == 0) push_depth();
+    if (ci.bitset) {  // compares cardinality() (filter.cc:215-217)
+      in.cls = C_GEN; in.gcls = G_CARD; in.gop = (uint8_t)op;
+      in.arg = widen_arg(raw_arg, ci.type) & (ci.width == 8 ? ~0ull : ((1ull << (8 * ci.width)) - 1));
+      emit(in);
+      return;
+    }
+    uint64_t a = widen_arg(raw_arg, ci.type);
+    if (ci.width == 8 || type_float(ci.type)) {
+      in.cls = C_GEN;
+      in.gcls = ci.type == VGPU_F32 ? G_F32 : ci.type == VGPU_F64 ? G_F64 : ci.type == VGPU_I64 ? G_I64 : G_U64;
+      in.gop = (uint8_t)op;
+      in.arg = a;
+      emit(in);
+      return;
+    }
+    const uint32_t ao = ord32(a, ci.type), omax = ordmax32(ci.type);
+    in.bias = bias32(ci.type);
+    switch (op) {
+      case VGPU_OP_EQ: case VGPU_OP_NE:
+        in.cls = C_EQ32;
+        in.arg = (uint32_t)(a & (ci.width == 4 ? 0xffffffffull : ((1ull << (8 * ci.width)) - 1)));
+        in.neg = op == VGPU_OP_NE;
+        break;
+      case VGPU_OP_LT: case VGPU_OP_GE:
+        in.cls = C_LT32; in.arg = ao; in.neg = op == VGPU_OP_GE;
+        break;
+      default:  // LE / GT:  x <= a  <=>  x < a+1 unless a is the largest value of the type
+        if (ao == omax) { in.cls = C_TRUE; } else { in.cls = C_LT32; in.arg = ao + 1; }
+        in.neg = op == VGPU_OP_GT;
+        break;
+    }
+    emit(in);
+  }
+
+  bool is_small_int_col(uint32_t col) const {
+    const ColInfo &ci = t->cols[col];
+    return !ci.bitset && ci.width <= 4 && !type_float(ci.type);
+  }
+
+  // mode: 0 push, 1 and-into-top, 2 or-into-top
+  void emit_node(int idx, int mode) {
+    const TreeNode &n = tree[idx];
+    switch (n.kind) {
+      case VGPU_NODE_EMPTY: {
+        PInstr in{};
+        in.kind = leaf_kind(mode);
+        in.cls = C_TRUE;
+        if (mode == 0) push_depth();
+        emit(in);
+      } break;
+      case VGPU_NODE_RELOP:
+        emit_compare(n.col, n.op, plan->args[n.arg], mode);
+        break;
+      case VGPU_NODE_IN: {
+        // IN = OR chain of ==, NOT IN = AND chain of != (filter.cc:222-241)
+        const bool eq = n.op != 0;
+        const int chain = eq ? 2 : 1;
+        const uint32_t op = eq ? VGPU_OP_EQ : VGPU_OP_NE;
+        if (mode == chain) {
+          for (uint32_t i = 0; i < n.n; ++i) emit_compare(n.col, op, plan->args[n.arg + i], chain);
+        } else {
+          emit_compare(n.col, op, plan->args[n.arg], 0);
+          for (uint32_t i = 1; i < n.n; ++i) emit_compare(n.col, op, plan->args[n.arg + i], chain);
+          if (mode != 0) combine(mode);
+        }
+      } break;
+      default: {  // AND / OR
+        const int chain = n.kind == VGPU_NODE_AND ? 1 : 2;
+        std::vector<int> kids = n.kids;
+        std::vector<char> done(kids.size(), 0);
+        bool first = mode != chain;  // the first emitted child must PUSH unless we chain into the top
+        auto child_mode = [&]() { int m = first ? 0 : chain; first = false; return m; };
+        if (chain == 1) {
+          // peephole: lo <= x < hi on one small integer column -> one subtract-and-compare
+          for (size_t i = 0; i < kids.size(); ++i) {
+            if (done[i]) continue;
+            const TreeNode &a = tree[kids[i]];
+            if (a.kind != VGPU_NODE_RELOP || !is_small_int_col(a.col)) continue;
+            const bool a_lo = a.op == VGPU_OP_GE || a.op == VGPU_OP_GT;
+            const bool a_hi = a.op == VGPU_OP_LT || a.op == VGPU_OP_LE;
+            if (!a_lo && !a_hi) continue;
+            for (size_t j = i + 1; j < kids.size(); ++j) {
+              if (done[j]) continue;
+              const TreeNode &b = tree[kids[j]];
+              if (b.kind != VGPU_NODE_RELOP || b.col != a.col) continue;
+              const bool b_lo = b.op == VGPU_OP_GE || b.op == VGPU_OP_GT;
+              const bool b_hi = b.op == VGPU_OP_LT || b.op == VGPU_OP_LE;
+              if (!((a_lo && b_hi) || (a_hi && b_lo))) continue;
+              const TreeNode &lo = a_lo ? a : b, &hi = a_lo ? b : a;
+              const ColInfo &ci = t->cols[a.col];
+              uint64_t lo_o = ord32(widen_arg(plan->args[lo.arg], ci.type), ci.type);
+              uint64_t hi_o = ord32(widen_arg(plan->args[hi.arg], ci.type), ci.type);
+              if (lo.op == VGPU_OP_GT) lo_o += 1;
+              if (hi.op == VGPU_OP_LE) hi_o += 1;  // exclusive upper bound, may be ordmax+1
+              PInstr in{};
+              in.kind = leaf_kind(child_mode());
+              if (in.kind == P_PUSH) push_depth();
+              in.slot = (uint8_t)slot_of(a.col);
+              if (hi_o <= lo_o || lo_o > ordmax32(ci.type)) {
+                in.cls = C_FALSE;
+              } else {
+                in.cls = C_RNG32;
+                in.bias = bias32(ci.type);
+                in.arg = (uint32_t)lo_o;
+                uint64_t len = hi_o - lo_o;  // <= 2^32
+                if (len > 0xffffffffull) { in.cls = C_TRUE; } else in.arg2 = (uint32_t)len;
+              }
+              emit(in);
+              done[i] = done[j] = 1;
+              break;
+            }
+          }
+        }
+        for (size_t i = 0; i < kids.size(); ++i) {
+          if (done[i]) continue;
+          emit_node(kids[i], child_mode());
+        }
+        if (mode != 0 && mode != chain) combine(mode);
+      } break;
+    }
+  }
+  void combine(int mode) {
+    PInstr in{};
+    in.kind = mode == 1 ? P_AND : P_OR;
+    emit(in);
+    --depth;
+  }
+
+  void build_predicate() {
+    build_tree();
+    emit_node(root, 0);
+    if (max_depth > kStackDepth) fail(VGPU_ERR_UNSUPPORTED, "predicate nesting too deep");
+  }
+
+  // ---- segment pruning: SegmentSkipBuilder (filter.cc:263-335), evaluated on the host ----
+  bool skip_leaf(const SegmentData &sd, uint32_t col, uint32_t op, uint64_t raw_arg) const {
+    const ColInfo &ci = t->cols[col];
+    if (!(ci.kind == VGPU_DIM_NUMERIC || ci.kind == VGPU_DIM_TIME || ci.kind == VGPU_DIM_MICROTIME))
+      return true;
+    // SegmentStats: dmax starts at cpp_min_value, dmin at cpp_max_value (store.cc:171-184)
+    uint64_t dmax = to_ordered_host(type_min_value(ci.type), ci.type);
+    uint64_t dmin = to_ordered_host(type_max_value(ci.type), ci.type);
+    if (sd.nrows > 0) {
+      dmax = std::max(dmax, sd.omax[col]);
+      dmin = std::min(dmin, sd.omin[col]);
+    }
+    uint64_t v = to_ordered_host(widen_arg(raw_arg, ci.type), ci.type);
+    switch (op) {
+      case VGPU_OP_EQ: return dmin <= v && dmax >= v;
+      case VGPU_OP_LT: case VGPU_OP_LE: return dmin <= v;
+      case VGPU_OP_GT: case VGPU_OP_GE: return dmax >= v;
+      default: return true;
+    }
+  }
+  bool process_segment(const SegmentData &sd, int idx) const {
+    const TreeNode &n = tree[idx];
+    switch (n.kind) {
+      case VGPU_NODE_EMPTY: return true;
+      case VGPU_NODE_RELOP: return skip_leaf(sd, n.col, n.op, plan->args[n.arg]);
+      case VGPU_NODE_IN: {
+        const ColInfo &ci = t->cols[n.col];
+        if (!(ci.kind == VGPU_DIM_NUMERIC || ci.kind == VGPU_DIM_TIME || ci.kind == VGPU_DIM_MICROTIME))
+          return true;
+        // NOT IN is pruned with the same "some value inside [min,max]" test (filter.cc:303-327
+        // ignores equal()) — reproduced as is
+        bool r = false;
+        for (uint32_t i = 0; i < n.n; ++i) r = r || skip_leaf(sd, n.col, VGPU_OP_EQ, plan->args[n.arg + i]);
+        return r;
+      }
+      case VGPU_NODE_AND: {
+        bool r = true;
+        for (int k : n.kids) r = process_segment(sd, k) && r;
+        return r;
+      }
+      default: {
+        bool r = false;
+        for (int k : n.kids) r = process_segment(sd, k) || r;
+        return r;
+      }
+    }
+  }
+};
+
+struct AccInfo {
+  uint32_t op;         // AccOp
+  uint32_t acc_width;  // 4 or 8
+  uint32_t out_width;  // metric column width (8 for BITSET cardinality)
+  uint64_t init;
+  ncclDataType_t nccl_type;
+  ncclRedOp_t nccl_op;
+};
+
+AccInfo acc_for(const ColInfo &ci) {
+  AccInfo a{};
+  a.out_width = ci.width;
+  const uint32_t t = ci.type;
+  if (ci.bitset) {
+    a.op = A_DISTINCT; a.acc_width = 4; a.out_width = 8; a.init = 0;
+    a.nccl_type = ncclUint32; a.nccl_op = ncclSum;
+    return a;
+  }
+  switch (ci.agg) {
+    case VGPU_AGG_SUM: case VGPU_AGG_AVG: case VGPU_AGG_COUNT:
+      a.init = 0; a.nccl_op = ncclSum;
+      if (t == VGPU_F32) { a.op = A_ADDF32; a.acc_width = 4; a.nccl_type = ncclFloat32; }
+      else if (t == VGPU_F64) { a.op = A_ADDF64; a.acc_width = 8; a.nccl_type = ncclFloat64; }
+      else if (ci.width == 8) { a.op = A_ADD64; a.acc_width = 8; a.nccl_type = ncclUint64; }
+      else { a.op = A_ADD32; a.acc_width = 4; a.nccl_type = ncclUint32; }
+      break;
+    case VGPU_AGG_MAX: case VGPU_AGG_MIN: {
+      const bool mx = ci.agg == VGPU_AGG_MAX;
+      a.init = mx ? type_min_value(t) : type_max_value(t);
+      a.nccl_op = mx ? ncclMax : ncclMin;
+      if (t == VGPU_F32) { a.op = mx ? A_MAXF32 : A_MINF32; a.acc_width = 4; a.nccl_type = ncclFloat32; }
+      else if (t == VGPU_F64) { a.op = mx ? A_MAXF64 : A_MINF64; a.acc_width = 8; a.nccl_type = ncclFloat64; }
+      else if (ci.width == 8) {
+        if (type_signed(t)) { a.op = mx ? A_MAXS64 : A_MINS64; a.nccl_type = ncclInt64; }
+        else { a.op = mx ? A_MAXU64 : A_MINU64; a.nccl_type = ncclUint64; }
+        a.acc_width = 8;
+      } else {
+        if (type_signed(t)) { a.op = mx ? A_MAXS32 : A_MINS32; a.nccl_type = ncclInt32; }
+        else { a.op = mx ? A_MAXU32 : A_MINU32; a.nccl_type = ncclUint32; }
+        a.acc_width = 4;
+      }
+    } break;
+    default:
+      fail(VGPU_ERR_INVALID, "metric column without an aggregation type");
+  }
+  return a;
+}
+
+struct KeyRange {
+  uint64_t lo;     // widened representation (two's complement for signed)
+  uint64_t range;  // number of distinct representable values, 0 means 2^64
+};
+
+unsigned __int128 range128(const KeyRange &r) {
+  return r.range == 0 ? ((unsigned __int128)1 << 64) : (unsigned __int128)r.range;
+}
+
+// host copy of the device trunc for the lower bound of a rolled-up time key
+uint64_t host_trunc_year_seconds(uint64_t t) {
+  time_t tt = (time_t)t;
+  struct tm tm;
+  gmtime_r(&tt, &tm);
+  tm.tm_sec = 0; tm.tm_min = 0; tm.tm_hour = 0; tm.tm_mday = 1; tm.tm_mon = 0;
+  return (uint64_t)timegm(&tm);
+}
+
+}  // namespace
+
+// =============================================================================================
+// C ABI
+// =============================================================================================
+extern "C" {
+
+int vgpu_abi_version(void) { return VGPU_ABI_VERSION; }
+
+const char *vgpu_last_error(void) { return g_err.c_str(); }
+
+int vgpu_init(int device, vgpu_ctx **out) {
+  return guard([&] {
+    if (!out) fail(VGPU_ERR_INVALID, "null output pointer");
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+      fail(VGPU_ERR_CUDA, std::string("no CUDA device: this library has no CPU path (") +
+                              cudaGetErrorString(e) + ")");
+    if (device < 0 || device >= ndev) fail(VGPU_ERR_INVALID, "device index out of range");
+    CUDA_CK(cudaSetDevice(device));
+    std::unique_ptr<vgpu_ctx> ctx(new vgpu_ctx());
+    ctx->device = device;
+    cudaDeviceProp prop;
+    CUDA_CK(cudaGetDeviceProperties(&prop, device));
+    ctx->sm_count = prop.multiProcessorCount;
+    CUDA_CK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    CUDA_CK(cudaEventCreate(&ctx->ev_begin));
+    CUDA_CK(cudaEventCreate(&ctx->ev_scan0));
+    CUDA_CK(cudaEventCreate(&ctx->ev_scan1));
+    CUDA_CK(cudaEventCreate(&ctx->ev_end));
+    CUDA_CK(cudaMalloc(&ctx->d_counters, 16 * sizeof(unsigned long long)));
+    CUDA_CK(cudaMallocHost(&ctx->h_counters, 16 * sizeof(unsigned long long)));
+    // keep freed scratch in the pool: repeated queries never go back to the driver
+    cudaMemPool_t pool;
+    CUDA_CK(cudaDeviceGetDefaultMemPool(&pool, device));
+    uint64_t threshold = UINT64_MAX;
+    CUDA_CK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &threshold));
+    // gathers of key/metric cells for passing rows want 32-byte sectors, not 64/128-byte fetches
+    cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, 32);
+    *out = ctx.release();
+  });
+}
+
+int vgpu_set_stream(vgpu_ctx *ctx, void *cuda_stream) {
+  return guard([&] {
+    if (!ctx) fail(VGPU_ERR_INVALID, "null context");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CUDA_CK(cudaSetDevice(ctx->device));
+    if (ctx->own_stream && ctx->stream) {
+      CUDA_CK(cudaStreamSynchronize(ctx->stream));
+      CUDA_CK(cudaStreamDestroy(ctx->stream));
+    }
+    ctx->stream = static_cast<cudaStream_t>(cuda_stream);
+    ctx->own_stream = false;
+  });
+}
+
+void vgpu_shutdown(vgpu_ctx *ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+  if (ctx->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(ctx->comm);
+  if (ctx->d_counters) cudaFree(ctx->d_counters);
+  if (ctx->h_counters) cudaFreeHost(ctx->h_counters);
+  if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
+  if (ctx->ev_begin) cudaEventDestroy(ctx->ev_begin);
+  if (ctx->ev_scan0) cudaEventDestroy(ctx->ev_scan0);
+  if (ctx->ev_scan1) cudaEventDestroy(ctx->ev_scan1);
+  if (ctx->ev_end) cudaEventDestroy(ctx->ev_end);
+  if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+// ---------------------------------------------------------------------------------------------
+// column store
+// ---------------------------------------------------------------------------------------------
+int vgpu_table_create(vgpu_ctx *ctx, const vgpu_schema *schema, vgpu_table **out) {
+  return guard([&] {
+    if (!ctx || !schema || !out) fail(VGPU_ERR_INVALID, "null argument");
+    *out = nullptr;
+    if (schema->ncols == 0 || schema->ndims > schema->ncols || !schema->cols)
+      fail(VGPU_ERR_INVALID, "malformed schema");
+    if (schema->segment_size == 0) fail(VGPU_ERR_INVALID, "segment_size must be positive");
+    std::unique_ptr<vgpu_table> t(new vgpu_table());
+    t->ctx = ctx;
+    t->ndims = schema->ndims;
+    t->segment_size = schema->segment_size;
+    uint64_t off = 0;
+    for (uint32_t c = 0; c < schema->ncols; ++c) {
+      const vgpu_column &sc = schema->cols[c];
+      ColInfo ci{};
+      ci.kind = sc.kind; ci.type = sc.type; ci.agg = sc.agg;
+      const bool is_dim = c < schema->ndims;
+      if (is_dim != (sc.kind <= VGPU_DIM_BOOLEAN))
+        fail(VGPU_ERR_INVALID, "dimensions must precede metrics in the schema");
+      switch (sc.kind) {
+        case VGPU_DIM_STRING:
+          if (!(sc.type <= VGPU_U64)) fail(VGPU_ERR_INVALID, "string dimension codes are unsigned");
+          break;
+        case VGPU_DIM_TIME:
+          if (sc.type != VGPU_U32) fail(VGPU_ERR_INVALID, "time dimension is uint32 seconds");
+          break;
+        case VGPU_DIM_MICROTIME:
+          if (sc.type != VGPU_U64) fail(VGPU_ERR_INVALID, "microtime dimension is uint64 microseconds");
+          break;
+        case VGPU_DIM_BOOLEAN:
+          if (sc.type != VGPU_U8) fail(VGPU_ERR_INVALID, "boolean dimension is uint8");
+          break;
+        case VGPU_DIM_NUMERIC:
+        case VGPU_METRIC_VALUE:
+          break;
+        case VGPU_METRIC_HIDDEN_COUNT:
+          if (sc.type != VGPU_U64) fail(VGPU_ERR_INVALID, "hidden count column is uint64");
+          ci.agg = VGPU_AGG_COUNT;
+          break;
+        case VGPU_METRIC_BITSET:
+          if (sc.type == VGPU_U64)
+            fail(VGPU_ERR_UNSUPPORTED, "64-bit bitset ids (Roaring64Map) are not supported yet");
+          if (sc.type > VGPU_U32) fail(VGPU_ERR_INVALID, "bitset ids are unsigned");
+          break;
+        default:
+          fail(VGPU_ERR_INVALID, "unknown column kind");
+      }
+      ci.width = type_width(sc.type);
+      ci.sext = type_signed(sc.type);
+      if (sc.kind == VGPU_METRIC_BITSET) {
+        if (t->nbitsets >= kMaxBitsetCols) fail(VGPU_ERR_UNSUPPORTED, "too many bitset metrics");
+        ci.bitset = true;
+        ci.bitset_idx = t->nbitsets++;
+        ci.agg = VGPU_AGG_BITSET;
+        ci.off_per_row = 0;
+      } else {
+        if (sc.kind == VGPU_METRIC_VALUE && sc.agg > VGPU_AGG_COUNT)
+          fail(VGPU_ERR_INVALID, "value metric needs max/min/sum/avg/count");
+        // natural alignment inside the slab: widest columns need 8-byte aligned bases; cap is a
+        // multiple of 4096 rows, so off_per_row * cap is always 4096-byte aligned
+        ci.off_per_row = off;
+        off += ci.width;
+      }
+      t->cols.push_back(ci);
+    }
+    t->row_bytes = off;
+    *out = t.release();
+  });
+}
+
+void vgpu_table_free(vgpu_table *table) {
+  if (!table) return;
+  cudaSetDevice(table->ctx->device);
+  cudaStreamSynchronize(table->ctx->stream);
+  for (auto &sd : table->segs) free_segment(sd);
+  if (table->d_segs) cudaFree(table->d_segs);
+  delete table;
+}
+
+int vgpu_segment_put(vgpu_table *t, uint32_t seg_idx, uint64_t nrows, const void *const *col_ptrs) {
+  return guard([&] {
+    if (!t || (!col_ptrs && nrows)) fail(VGPU_ERR_INVALID, "null argument");
+    vgpu_ctx *ctx = t->ctx;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CUDA_CK(cudaSetDevice(ctx->device));
+    if (seg_idx > t->segs.size() + (1u << 20)) fail(VGPU_ERR_INVALID, "segment index too sparse");
+    ensure_segment(t, seg_idx, nrows);
+    SegmentData &sd = t->segs[seg_idx];
+    std::vector<std::vector<uint32_t>> keep;  // converted CSR offsets must outlive the async copies
+    for (size_t c = 0; c < t->cols.size(); ++c) {
+      const ColInfo &ci = t->cols[c];
+      if (ci.bitset) {
+        if (nrows == 0) continue;
+        const vgpu_bitset_csr *csr = static_cast<const vgpu_bitset_csr *>(col_ptrs[c]);
+        if (!csr || !csr->values) fail(VGPU_ERR_INVALID, "bitset column needs a vgpu_bitset_csr");
+        uint64_t nvalues = csr->offsets ? csr->offsets[nrows] : nrows;
+        if (csr->offsets && csr->nvalues != nvalues) fail(VGPU_ERR_INVALID, "bitset CSR: nvalues != offsets[nrows]");
+        if (!csr->offsets && csr->nvalues != nrows) fail(VGPU_ERR_INVALID, "bitset without offsets needs one id per row");
+        if (nvalues >= (1ull << 32)) fail(VGPU_ERR_UNSUPPORTED, "more than 2^32 bitset ids in one segment");
+        bool one_per_row = true;
+        if (csr->offsets) {
+          if (csr->offsets[0] != 0) fail(VGPU_ERR_INVALID, "bitset CSR: offsets[0] != 0");
+          for (uint64_t r = 0; r < nrows; ++r) {
+            if (csr->offsets[r + 1] < csr->offsets[r]) fail(VGPU_ERR_INVALID, "bitset CSR: offsets not monotone");
+            if (csr->offsets[r + 1] - csr->offsets[r] != 1) one_per_row = false;
+          }
+        }
+        // values padded to a whole tile so that speculative reads stay in bounds
+        uint64_t vcap = round_up(std::max<uint64_t>(nvalues, 1), kTileRows);
+        CUDA_CK(cudaMalloc(&sd.bs_values[ci.bitset_idx], vcap * 4));
+        CUDA_CK(cudaMemsetAsync(sd.bs_values[ci.bitset_idx], 0, vcap * 4, ctx->stream));
+        if (nvalues)
+          CUDA_CK(cudaMemcpyAsync(sd.bs_values[ci.bitset_idx], csr->values, nvalues * 4,
+                                  cudaMemcpyHostToDevice, ctx->stream));
+        sd.bs_n[ci.bitset_idx] = nvalues;
+        if (!one_per_row) {
+          keep.emplace_back(nrows + 1);
+          auto &o32 = keep.back();
+          for (uint64_t r = 0; r <= nrows; ++r) o32[r] = (uint32_t)csr->offsets[r];
+          CUDA_CK(cudaMalloc(&sd.bs_offsets[ci.bitset_idx], (nrows + 1) * 4));
+          CUDA_CK(cudaMemcpyAsync(sd.bs_offsets[ci.bitset_idx], o32.data(), (nrows + 1) * 4,
+                                  cudaMemcpyHostToDevice, ctx->stream));
+        }
+        continue;
+      }
+      uint8_t *dst = sd.slab + ci.off_per_row * sd.cap;
+      if (nrows) {
+        if (!col_ptrs[c]) fail(VGPU_ERR_INVALID, "null column pointer");
+        CUDA_CK(cudaMemcpyAsync(dst, col_ptrs[c], nrows * ci.width, cudaMemcpyHostToDevice, ctx->stream));
+      }
+      if (sd.cap > nrows)
+        CUDA_CK(cudaMemsetAsync(dst + nrows * ci.width, 0, (sd.cap - nrows) * ci.width, ctx->stream));
+    }
+    CUDA_CK(cudaStreamSynchronize(ctx->stream));
+    compute_stats(t, sd);
+    sd.valid = true;
+  });
+}
+
+int vgpu_segment_generate(vgpu_table *t, uint32_t seg_idx, uint64_t nrows, const vgpu_gen_col *gens,
+                          uint64_t seed, uint64_t row_offset) {
+  return guard([&] {
+    if (!t || !gens) fail(VGPU_ERR_INVALID, "null argument");
+    vgpu_ctx *ctx = t->ctx;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CUDA_CK(cudaSetDevice(ctx->device));
+    if (t->cols.size() > 32) fail(VGPU_ERR_UNSUPPORTED, "generator supports at most 32 columns");
+    ensure_segment(t, seg_idx, nrows);
+    SegmentData &sd = t->segs[seg_idx];
+    if (sd.slab) CUDA_CK(cudaMemsetAsync(sd.slab, 0, t->row_bytes * sd.cap, ctx->stream));
+    GenParams G{};
+    G.slab = sd.slab;
+    G.nrows = nrows;
+    G.seed = seed;
+    G.row_offset = row_offset;
+    G.ncols = (uint32_t)t->cols.size();
+    for (size_t c = 0; c < t->cols.size(); ++c) {
+      const ColInfo &ci = t->cols[c];
+      GenCol &gc = G.cols[c];
+      if (gens[c].range == 0) fail(VGPU_ERR_INVALID, "generator range must be positive");
+      if (gens[c].mode == 1 && gens[c].div == 0) fail(VGPU_ERR_INVALID, "generator div must be positive");
+      gc.off = ci.off_per_row * sd.cap;
+      gc.width = ci.width;
+      gc.mode = gens[c].mode;
+      gc.lo = gens[c].lo;
+      gc.range = gens[c].range;
+      gc.div = gens[c].div ? gens[c].div : 1;
+      gc.gen_index = (uint32_t)c;
+      gc.is_f32 = ci.type == VGPU_F32;
+      gc.is_f64 = ci.type == VGPU_F64;
+      gc.bitset_out = nullptr;
+      if (ci.bitset) {
+        uint64_t vcap = round_up(std::max<uint64_t>(nrows, 1), kTileRows);
+        CUDA_CK(cudaMalloc(&sd.bs_values[ci.bitset_idx], vcap * 4));
+        CUDA_CK(cudaMemsetAsync(sd.bs_values[ci.bitset_idx], 0, vcap * 4, ctx->stream));
+        sd.bs_n[ci.bitset_idx] = nrows;
+        gc.bitset_out = sd.bs_values[ci.bitset_idx];
+      }
+    }
+    if (nrows) {
+      generate_kernel<<<grid_for(nrows, 256, ctx->sm_count), 256, 0, ctx->stream>>>(G);
+      CUDA_CK(cudaGetLastError());
+    }
+    CUDA_CK(cudaStreamSynchronize(ctx->stream));
+    compute_stats(t, sd);
+    sd.valid = true;
+  });
+}
+
+int vgpu_segment_read(vgpu_table *t, uint32_t seg_idx, uint32_t col, void *out) {
+  return guard([&] {
+    if (!t || !out) fail(VGPU_ERR_INVALID, "null argument");
+    vgpu_ctx *ctx = t->ctx;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CUDA_CK(cudaSetDevice(ctx->device));
+    if (seg_idx >= t->segs.size() || !t->segs[seg_idx].valid) fail(VGPU_ERR_STATE, "no such segment");
+    if (col >= t->cols.size()) fail(VGPU_ERR_INVALID, "column index out of range");
+    const SegmentData &sd = t->segs[seg_idx];
+    const ColInfo &ci = t->cols[col];
+    if (ci.bitset) {
+      if (sd.bs_n[ci.bitset_idx])
+        CUDA_CK(cudaMemcpyAsync(out, sd.bs_values[ci.bitset_idx], sd.bs_n[ci.bitset_idx] * 4,
+                                cudaMemcpyDeviceToHost, ctx->stream));
+    } else if (sd.nrows) {
+      CUDA_CK(cudaMemcpyAsync(out, sd.slab + ci.off_per_row * sd.cap, sd.nrows * ci.width,
+                              cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    CUDA_CK(cudaStreamSynchronize(ctx->stream));
+  });
+}
+
+int vgpu_table_invalidate(vgpu_table *t, uint32_t seg_idx) {
+  return guard([&] {
+    if (!t) fail(VGPU_ERR_INVALID, "null table");
+    std::lock_guard<std::mutex> lk(t->ctx->mu);
+    if (seg_idx >= t->segs.size()) fail(VGPU_ERR_STATE, "no such segment");
+    CUDA_CK(cudaSetDevice(t->ctx->device));
+    CUDA_CK(cudaStreamSynchronize(t->ctx->stream));
+    free_segment(t->segs[seg_idx]);
+    t->descs_dirty = true;
+  });
+}
+
+uint32_t vgpu_table_segments(const vgpu_table *t) {
+  if (!t) return 0;
+  uint32_t n = 0;
+  for (auto &sd : t->segs) n += sd.valid ? 1 : 0;
+  return n;
+}
+uint64_t vgpu_table_rows(const vgpu_table *t) {
+  if (!t) return 0;
+  uint64_t n = 0;
+  for (auto &sd : t->segs) n += sd.valid ? sd.nrows : 0;
+  return n;
+}
+uint64_t vgpu_table_bytes(const vgpu_table *t) {
+  if (!t) return 0;
+  uint64_t n = 0;
+  for (auto &sd : t->segs) {
+    if (!sd.valid) continue;
+    n += sd.cap * t->row_bytes;
+    for (int b = 0; b < kMaxBitsetCols; ++b) {
+      n += sd.bs_n[b] * 4;
+      if (sd.bs_offsets[b]) n += (sd.nrows + 1) * 4;
+    }
+  }
+  return n;
+}
+
+// ---------------------------------------------------------------------------------------------
+// the hot path
+// ---------------------------------------------------------------------------------------------
+namespace {
+
+struct QueryRun {
+  // inputs
+  vgpu_table *t;
+  const vgpu_plan *plan;
+  // planned
+  Planner planner;
+  std::vector<AccInfo> accs;       // per selected metric (+ hidden count last)
+  std::vector<uint32_t> acc_cols;  // schema column per accumulator
+  std::vector<KeyRange> ranges;
+  std::vector<uint32_t> active;
+  uint64_t active_rows = 0;
+  uint64_t scanned_recs = 0;
+  bool hash_mode = false;
+  uint64_t ncells = 0;  // dense cells, or hash capacity (power of two)
+
+  QueryRun(vgpu_table *table, const vgpu_plan *p) : t(table), plan(p), planner(table, p) {}
+};
+
+void validate_plan(const vgpu_table *t, const vgpu_plan *plan) {
+  if (plan->nnodes && !plan->nodes) fail(VGPU_ERR_INVALID, "null predicate nodes");
+  if (plan->nargs && !plan->args) fail(VGPU_ERR_INVALID, "null predicate args");
+  if (plan->nkeys && !plan->keys) fail(VGPU_ERR_INVALID, "null keys");
+  if (plan->nmetrics && !plan->metric_cols) fail(VGPU_ERR_INVALID, "null metric list");
+  if (plan->nkeys > kMaxKeys) fail(VGPU_ERR_UNSUPPORTED, "too many group-by keys");
+  if (plan->nmetrics + (plan->need_hidden_count ? 1 : 0) > kMaxMetrics)
+    fail(VGPU_ERR_UNSUPPORTED, "too many metrics");
+  for (uint32_t k = 0; k < plan->nkeys; ++k) {
+    const vgpu_key &key = plan->keys[k];
+    if (key.col >= t->ndims) fail(VGPU_ERR_INVALID, "group-by key must be a dimension");
+    if (key.nrules > VGPU_MAX_ROLLUP_RULES) fail(VGPU_ERR_INVALID, "too many rollup rules");
+    const ColInfo &ci = t->cols[key.col];
+    const bool rollup = key.nrules > 0 || key.query_granularity != VGPU_TU_NONE;
+    if (rollup && !(ci.kind == VGPU_DIM_TIME || ci.kind == VGPU_DIM_MICROTIME))
+      fail(VGPU_ERR_INVALID, "time rollup on a non-time dimension");
+    if (key.query_granularity > VGPU_TU_NONE) fail(VGPU_ERR_INVALID, "bad query granularity");
+    // util::Truncator has no WEEK specialisation (src/util/time.h:52-89): the reference fails to link
+    if (key.query_granularity == VGPU_TU_WEEK) fail(VGPU_ERR_UNSUPPORTED, "week granularity is not supported by the reference");
+    for (uint32_t r = 0; r < key.nrules; ++r) {
+      if (key.rule_granularity[r] >= VGPU_TU_NONE) fail(VGPU_ERR_INVALID, "bad rollup granularity");
+      if (key.rule_granularity[r] == VGPU_TU_WEEK) fail(VGPU_ERR_UNSUPPORTED, "week granularity is not supported by the reference");
+    }
+  }
+  for (uint32_t m = 0; m < plan->nmetrics; ++m) {
+    uint32_t c = plan->metric_cols[m];
+    if (c < t->ndims || c >= t->cols.size()) fail(VGPU_ERR_INVALID, "metric index out of range");
+    if (t->cols[c].kind == VGPU_METRIC_HIDDEN_COUNT) fail(VGPU_ERR_INVALID, "the hidden count column cannot be selected");
+  }
+}
+
+int find_hidden_count(const vgpu_table *t) {
+  for (size_t c = t->ndims; c < t->cols.size(); ++c)
+    if (t->cols[c].kind == VGPU_METRIC_HIDDEN_COUNT) return (int)c;
+  return -1;
+}
+
+// ---- multi-GPU merge of partial group tables (dense mode) ----
+void nccl_merge_dense(vgpu_ctx *ctx, QueryRun &q, ScanParams &P, std::vector<void *> &acc_ptrs) {
+  NCCL_CK(g_nccl.GroupStart());
+  for (size_t m = 0; m < q.accs.size(); ++m) {
+    if (q.accs[m].op == A_DISTINCT) continue;
+    NCCL_CK(g_nccl.AllReduce(acc_ptrs[m], acc_ptrs[m], q.ncells, q.accs[m].nccl_type, q.accs[m].nccl_op,
+                             ctx->comm, ctx->stream));
+  }
+  NCCL_CK(g_nccl.AllReduce(P.present, P.present, q.ncells, ncclUint8, ncclMax, ctx->comm, ctx->stream));
+  NCCL_CK(g_nccl.GroupEnd());
+}
+
+}  // namespace
+
+int vgpu_query_agg(vgpu_table *t, const vgpu_plan *plan, vgpu_result **out) {
+  return guard([&] {
+    if (!t || !plan || !out) fail(VGPU_ERR_INVALID, "null argument");
+    *out = nullptr;
+    vgpu_ctx *ctx = t->ctx;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CUDA_CK(cudaSetDevice(ctx->device));
+    cudaStream_t stream = ctx->stream;
+    validate_plan(t, plan);
+
+    QueryRun q(t, plan);
+    Planner &pl = q.planner;
+    ScanParams &P = pl.P;
+    pl.build_predicate();
+
+    // ---- segment loop bookkeeping + pruning (scan.cc:42-51) ----
+    for (uint32_t s = 0; s < t->segs.size(); ++s) {
+      const SegmentData &sd = t->segs[s];
+      if (!sd.valid) continue;
+      q.scanned_recs += sd.nrows;
+      if (!pl.process_segment(sd, pl.root)) continue;
+      q.active.push_back(s);
+      q.active_rows += sd.nrows;
+    }
+
+    // ---- keys ----
+    P.nkeys = plan->nkeys;
+    q.ranges.resize(plan->nkeys);
+    for (uint32_t k = 0; k < plan->nkeys; ++k) {
+      const vgpu_key &key = plan->keys[k];
+      const ColInfo &ci = t->cols[key.col];
+      if (ci.bitset) fail(VGPU_ERR_INVALID, "bitset column as a key");
+      KeySpec &ks = P.keys[k];
+      ks.slot = (uint8_t)pl.slot_of(key.col);
+      ks.rollup = key.nrules > 0 || key.query_granularity != VGPU_TU_NONE;
+      ks.micro = ci.kind == VGPU_DIM_MICROTIME;
+      ks.nrules = (uint8_t)key.nrules;
+      ks.query_unit = (uint8_t)key.query_granularity;
+      for (uint32_t r = 0; r < key.nrules; ++r) {
+        ks.rule_unit[r] = (uint8_t)key.rule_granularity[r];
+        ks.rule_boundary[r] = key.rule_boundary[r];
+      }
+      // value range over the active segments
+      KeyRange kr{0, 1};
+      if (type_float(ci.type) || (ci.width == 8 && false)) {
+        kr.lo = 0;
+        kr.range = ci.width == 4 ? (1ull << 32) : 0;  // keyed by raw bits
+      } else {
+        uint64_t omin = ~0ull, omax = 0;
+        bool any = false;
+        for (uint32_t s : q.active) {
+          const SegmentData &sd = t->segs[s];
+          if (sd.nrows == 0) continue;
+          omin = std::min(omin, sd.omin[key.col]);
+          omax = std::max(omax, sd.omax[key.col]);
+          any = true;
+        }
+        if (any) {
+          uint64_t lo = from_ordered_int(omin, ci.type), hi = from_ordered_int(omax, ci.type);
+          if (ks.rollup) {  // truncation only moves values down, at most to the start of their year
+            if (ks.micro) lo = host_trunc_year_seconds(lo / 1000000ull) * 1000000ull;
+            else lo = host_trunc_year_seconds(lo);
+          }
+          kr.lo = lo;
+          kr.range = hi - lo + 1;  // wraps to 0 for the full 64-bit domain
+        }
+      }
+      q.ranges[k] = kr;
+    }
+
+    // ---- metrics ----
+    const int hidden_col = find_hidden_count(t);
+    if (plan->need_hidden_count && hidden_col < 0)
+      fail(VGPU_ERR_INVALID, "plan needs the hidden count column but the table has none");
+    for (uint32_t m = 0; m < plan->nmetrics; ++m) {
+      q.acc_cols.push_back(plan->metric_cols[m]);
+      q.accs.push_back(acc_for(t->cols[plan->metric_cols[m]]));
+    }
+    if (plan->need_hidden_count) {
+      q.acc_cols.push_back((uint32_t)hidden_col);
+      q.accs.push_back(acc_for(t->cols[hidden_col]));
+    }
+    P.nmetrics = (uint32_t)q.accs.size();
+    P.ndistinct = 0;
+    for (uint32_t m = 0; m < P.nmetrics; ++m) {
+      P.mets[m].slot = (uint8_t)pl.slot_of(q.acc_cols[m]);
+      P.mets[m].op = (uint8_t)q.accs[m].op;
+      if (q.accs[m].op == A_DISTINCT) {
+        if (P.ndistinct >= kMaxDistinct) fail(VGPU_ERR_UNSUPPORTED, "too many count-distinct metrics in one query");
+        P.distinct_met[P.ndistinct++] = (uint8_t)m;
+      }
+    }
+
+    // ---- dense or hash ----
+    unsigned __int128 cells128 = 1;
+    bool fits64 = true;
+    for (auto &r : q.ranges) {
+      cells128 *= range128(r);
+      if (cells128 > ((unsigned __int128)1 << 64) - 2) { fits64 = false; break; }
+    }
+    if (!fits64) fail(VGPU_ERR_UNSUPPORTED, "group key does not pack into 64 bits");
+    const uint64_t cells = (uint64_t)cells128;
+    uint64_t dense_limit = std::min<uint64_t>(std::max<uint64_t>(4 * q.active_rows, 1ull << 22), 1ull << 28);
+    if (P.ndistinct) dense_limit = std::min<uint64_t>(dense_limit, 0xffffffffull);
+    bool dense = cells <= dense_limit;
+    if (plan->flags & VGPU_PLAN_FORCE_HASH) dense = false;
+    if (plan->flags & VGPU_PLAN_FORCE_DENSE) {
+      if (cells > (1ull << 30)) fail(VGPU_ERR_UNSUPPORTED, "key domain too large for a dense group table");
+      dense = true;
+    }
+    q.hash_mode = !dense;
+    {
+      uint64_t mul = 1;
+      for (uint32_t k = 0; k < plan->nkeys; ++k) {
+        P.keys[k].lo = q.ranges[k].lo;
+        P.keys[k].mul = mul;
+        mul *= q.ranges[k].range;  // the last multiplication may wrap only if it is never used
+      }
+    }
+
+    // ---- work list ----
+    uint64_t max_rows = 0;
+    for (uint32_t s : q.active) max_rows = std::max(max_rows, t->segs[s].nrows);
+    P.tiles_per_seg = (uint32_t)std::max<uint64_t>(1, (max_rows + kTileRows - 1) / kTileRows);
+    P.nactive = (uint32_t)q.active.size();
+    P.total_tiles = (uint64_t)P.nactive * P.tiles_per_seg;
+    upload_descs(t);
+    P.segs = t->d_segs;
+
+    std::unique_ptr<vgpu_result> res(new vgpu_result());
+    vgpu_result_view &view = res->view;
+    view.nkeys = plan->nkeys;
+    view.nmetrics = plan->nmetrics;
+    view.scanned_recs = q.scanned_recs;
+    view.scanned_segments = q.active.size();
+
+    CUDA_CK(cudaEventRecord(ctx->ev_begin, stream));
+    uint32_t launches = 0;
+    float scan_ms_total = 0;
+
+    uint64_t hash_cap = 0;
+    if (q.hash_mode) {
+      uint64_t est = std::min<uint64_t>(cells, std::max<uint64_t>(q.active_rows, 1));
+      uint64_t want = pow2_ceil(std::max<uint64_t>(2 * est, 1024));
+      hash_cap = std::min<uint64_t>(want, 1ull << 24);
+      hash_cap = std::max(hash_cap, std::min(t->hash_cap_hint, want));
+      if (hash_cap > 0xfffffffeull && P.ndistinct) fail(VGPU_ERR_UNSUPPORTED, "count-distinct over more than 2^32 groups");
+    }
+    uint64_t pairs_cap = 0;
+    if (P.ndistinct) {
+      pairs_cap = std::max<uint64_t>(1ull << 16, q.active_rows / 16);
+      pairs_cap = std::max(pairs_cap, t->pairs_cap_hint);
+    }
+
+    for (int attempt = 0;; ++attempt) {
+      if (attempt > 12) fail(VGPU_ERR_NOMEM, "group table keeps overflowing");
+      Scratch scratch(stream);
+      q.ncells = q.hash_mode ? hash_cap : cells;
+      const uint64_t acc_cells = q.hash_mode ? hash_cap + 1 : cells;  // + the all-ones-key cell
+      P.hash_mode = q.hash_mode;
+      P.max_probe = 512;
+      if (q.hash_mode) {
+        P.hkeys = scratch.alloc<uint64_t>(hash_cap);
+        P.hmask = hash_cap - 1;
+        fill64(stream, ctx->sm_count, P.hkeys, hash_cap, kEmptyKey);
+        P.present = scratch.alloc<uint8_t>(16);
+        CUDA_CK(cudaMemsetAsync(P.present, 0, 16, stream));
+      } else {
+        P.hkeys = nullptr;
+        P.hmask = 0;
+        P.present = scratch.alloc<uint8_t>(acc_cells);
+        CUDA_CK(cudaMemsetAsync(P.present, 0, acc_cells, stream));
+      }
+      std::vector<void *> acc_ptrs(q.accs.size());
+      for (size_t m = 0; m < q.accs.size(); ++m) {
+        const AccInfo &a = q.accs[m];
+        if (a.acc_width == 4) {
+          acc_ptrs[m] = scratch.alloc<uint32_t>(acc_cells);
+          launches += fill32(stream, ctx->sm_count, acc_ptrs[m], acc_cells, (uint32_t)a.init);
+        } else {
+          acc_ptrs[m] = scratch.alloc<uint64_t>(acc_cells);
+          launches += fill64(stream, ctx->sm_count, acc_ptrs[m], acc_cells, a.init);
+        }
+        P.mets[m].acc = acc_ptrs[m];
+      }
+      for (uint32_t d = 0; d < P.ndistinct; ++d) {
+        P.pairs[d] = scratch.alloc<uint64_t>(pairs_cap);
+        P.pairs_cap[d] = pairs_cap;
+      }
+      CUDA_CK(cudaMemsetAsync(ctx->d_counters, 0, 16 * sizeof(unsigned long long), stream));
+      P.counters = ctx->d_counters;
+      uint32_t *d_active = scratch.alloc<uint32_t>(q.active.size());
+      if (!q.active.empty())
+        CUDA_CK(cudaMemcpyAsync(d_active, q.active.data(), q.active.size() * 4, cudaMemcpyHostToDevice, stream));
+      P.active = d_active;
+
+      // ---- the fused scan ----
+      CUDA_CK(cudaEventRecord(ctx->ev_scan0, stream));
+      if (P.total_tiles > 0) {
+        int grid = (int)std::min<uint64_t>(P.total_tiles, (uint64_t)ctx->sm_count * 4);
+        scan_filter_groupby_kernel<<<grid, kThreads, 0, stream>>>(P);
+        CUDA_CK(cudaGetLastError());
+        ++launches;
+      }
+      CUDA_CK(cudaEventRecord(ctx->ev_scan1, stream));
+      CUDA_CK(cudaMemcpyAsync(ctx->h_counters, ctx->d_counters, 16 * sizeof(unsigned long long),
+                              cudaMemcpyDeviceToHost, stream));
+      CUDA_CK(cudaStreamSynchronize(stream));
+      {
+        float ms = 0;
+        CUDA_CK(cudaEventElapsedTime(&ms, ctx->ev_scan0, ctx->ev_scan1));
+        scan_ms_total += ms;
+      }
+      const uint64_t passed = ctx->h_counters[0];
+      if (ctx->h_counters[1] != 0) {  // overflow: grow and run again
+        bool grew = false;
+        for (uint32_t d = 0; d < P.ndistinct; ++d) {
+          if (ctx->h_counters[2 + d] > pairs_cap) {
+            pairs_cap = round_up(ctx->h_counters[2 + d] + ctx->h_counters[2 + d] / 8, 1024);
+            grew = true;
+          }
+        }
+        if (!grew) {
+          if (!q.hash_mode) fail(VGPU_ERR_CUDA, "unexpected overflow flag in dense mode");
+          hash_cap *= 4;
+        }
+        continue;
+      }
+      if (q.hash_mode) t->hash_cap_hint = std::max(t->hash_cap_hint, hash_cap);
+      if (P.ndistinct) t->pairs_cap_hint = std::max(t->pairs_cap_hint, pairs_cap);
+      view.passed_rows = passed;
+
+      // ---- count-distinct: dedupe the (cell,id) pairs ----
+      for (uint32_t d = 0; d < P.ndistinct; ++d) {
+        const uint64_t npairs = ctx->h_counters[2 + d];
+        uint32_t *distinct = static_cast<uint32_t *>(acc_ptrs[P.distinct_met[d]]);
+        if (npairs == 0) continue;
+        const uint64_t set_cap = pow2_ceil(std::max<uint64_t>(2 * npairs, 1024));
+        uint64_t *set = scratch.alloc<uint64_t>(set_cap);
+        fill64(stream, ctx->sm_count, set, set_cap, kEmptyKey);
+        unsigned long long *sentinel = ctx->d_counters + 8 + d;
+        distinct_insert_kernel<<<grid_for(npairs, 256, ctx->sm_count), 256, 0, stream>>>(
+            P.pairs[d], npairs, set, set_cap - 1, distinct, sentinel);
+        CUDA_CK(cudaGetLastError());
+        launches += 1;
+        if (ctx->nranks > 1) fail(VGPU_ERR_UNSUPPORTED, "multi-GPU count-distinct merge is not implemented yet");
+      }
+
+      // ---- multi-GPU: merge the partial group tables ----
+      if (ctx->nranks > 1) {
+        if (q.hash_mode) fail(VGPU_ERR_UNSUPPORTED, "multi-GPU merge of hashed group tables is not implemented yet");
+        nccl_merge_dense(ctx, q, P, acc_ptrs);
+      }
+
+      // ---- extract the groups ----
+      ExtractParams E{};
+      E.ncells = acc_cells;
+      E.hash_mode = q.hash_mode;
+      E.nkeys = plan->nkeys;
+      E.nmets = (uint32_t)q.accs.size();
+      E.hkeys = P.hkeys;
+      E.present = P.present;
+      unsigned long long *d_ngroups = ctx->d_counters + 12;
+      E.counter = d_ngroups;
+      uint64_t bound = std::min<uint64_t>(acc_cells, passed);
+      if (ctx->nranks > 1) {  // merged tables: `passed` is only this rank's share, count first
+        E.count_only = 1;
+        extract_groups_kernel<<<grid_for(acc_cells, 256, ctx->sm_count), 256, 0, stream>>>(E);
+        CUDA_CK(cudaGetLastError());
+        ++launches;
+        CUDA_CK(cudaMemcpyAsync(ctx->h_counters, ctx->d_counters, 16 * sizeof(unsigned long long),
+                                cudaMemcpyDeviceToHost, stream));
+        CUDA_CK(cudaStreamSynchronize(stream));
+        bound = ctx->h_counters[12];
+        CUDA_CK(cudaMemsetAsync(d_ngroups, 0, sizeof(unsigned long long), stream));
+      }
+      E.count_only = 0;
+      std::vector<void *> d_keys(plan->nkeys), d_accs(q.accs.size());
+      for (uint32_t k = 0; k < plan->nkeys; ++k) {
+        const ColInfo &ci = t->cols[plan->keys[k].col];
+        d_keys[k] = scratch.alloc<uint8_t>(bound * ci.width);
+        E.keys[k].lo = q.ranges[k].lo;
+        E.keys[k].div = P.keys[k].mul;
+        E.keys[k].mod = (k + 1 < plan->nkeys) ? q.ranges[k].range : 0;
+        E.keys[k].width = ci.width;
+        E.keys[k].out = d_keys[k];
+      }
+      for (size_t m = 0; m < q.accs.size(); ++m) {
+        d_accs[m] = scratch.alloc<uint8_t>(bound * q.accs[m].out_width);
+        E.mets[m].acc = acc_ptrs[m];
+        E.mets[m].acc_width = q.accs[m].acc_width;
+        E.mets[m].out_width = q.accs[m].out_width;
+        E.mets[m].out = d_accs[m];
+      }
+      if (bound > 0) {
+        extract_groups_kernel<<<grid_for(acc_cells, 256, ctx->sm_count), 256, 0, stream>>>(E);
+        CUDA_CK(cudaGetLastError());
+        ++launches;
+      }
+      CUDA_CK(cudaMemcpyAsync(ctx->h_counters, ctx->d_counters, 16 * sizeof(unsigned long long),
+                              cudaMemcpyDeviceToHost, stream));
+      CUDA_CK(cudaStreamSynchronize(stream));
+      const uint64_t ngroups = bound > 0 ? ctx->h_counters[12] : 0;
+      if (ngroups > bound) fail(VGPU_ERR_CUDA, "group extraction overflow");
+
+      // ---- results to the host ----
+      res->key_data.resize(plan->nkeys);
+      res->acc_data.resize(plan->nmetrics);
+      for (uint32_t k = 0; k < plan->nkeys; ++k) {
+        const ColInfo &ci = t->cols[plan->keys[k].col];
+        res->key_data[k].resize(std::max<uint64_t>(ngroups * ci.width, 1));
+        if (ngroups)
+          CUDA_CK(cudaMemcpyAsync(res->key_data[k].data(), d_keys[k], ngroups * ci.width, cudaMemcpyDeviceToHost, stream));
+      }
+      for (uint32_t m = 0; m < plan->nmetrics; ++m) {
+        res->acc_data[m].resize(std::max<uint64_t>(ngroups * q.accs[m].out_width, 1));
+        if (ngroups)
+          CUDA_CK(cudaMemcpyAsync(res->acc_data[m].data(), d_accs[m], ngroups * q.accs[m].out_width,
+                                  cudaMemcpyDeviceToHost, stream));
+      }
+      if (plan->need_hidden_count) {
+        res->hidden.resize(std::max<uint64_t>(ngroups, 1));
+        if (ngroups)
+          CUDA_CK(cudaMemcpyAsync(res->hidden.data(), d_accs[plan->nmetrics], ngroups * 8, cudaMemcpyDeviceToHost, stream));
+      }
+      CUDA_CK(cudaEventRecord(ctx->ev_end, stream));
+      CUDA_CK(cudaStreamSynchronize(stream));
+      float total_ms = 0;
+      CUDA_CK(cudaEventElapsedTime(&total_ms, ctx->ev_begin, ctx->ev_end));
+      view.ngroups = ngroups;
+      view.aggregated_recs = ngroups;
+      view.gpu_ms = total_ms;
+      view.scan_ms = scan_ms_total;
+      view.launches = launches;
+      view.table_mode = q.hash_mode ? 1 : 0;
+      view.table_cells = q.ncells;
+      break;
+    }
+
+    for (auto &v : res->key_data) res->key_ptrs.push_back(v.data());
+    for (auto &v : res->acc_data) res->acc_ptrs.push_back(v.data());
+    view.keys = res->key_ptrs.empty() ? nullptr : res->key_ptrs.data();
+    view.accs = res->acc_ptrs.empty() ? nullptr : res->acc_ptrs.data();
+    view.hidden_count = plan->need_hidden_count ? res->hidden.data() : nullptr;
+    *out = res.release();
+  });
+}
+
+int vgpu_result_get(const vgpu_result *res, vgpu_result_view *view) {
+  return guard([&] {
+    if (!res || !view) fail(VGPU_ERR_INVALID, "null argument");
+    *view = res->view;
+  });
+}
+
+void vgpu_result_free(vgpu_result *res) { delete res; }
+
+// ---------------------------------------------------------------------------------------------
+// multi-GPU
+// ---------------------------------------------------------------------------------------------
+int vgpu_comm_unique_id(void *unique_id_128) {
+  return guard([&] {
+    if (!unique_id_128) fail(VGPU_ERR_INVALID, "null argument");
+    nccl_load();
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+    ncclUniqueId id;
+    NCCL_CK(g_nccl.GetUniqueId(&id));
+    memcpy(unique_id_128, &id, sizeof(id));
+  });
+}
+
+int vgpu_comm_init(vgpu_ctx *ctx, int rank, int nranks, const void *unique_id_128) {
+  return guard([&] {
+    if (!ctx || !unique_id_128) fail(VGPU_ERR_INVALID, "null argument");
+    if (nranks < 1 || rank < 0 || rank >= nranks) fail(VGPU_ERR_INVALID, "bad rank / nranks");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    if (ctx->comm) fail(VGPU_ERR_STATE, "communicator already initialised");
+    nccl_load();
+    CUDA_CK(cudaSetDevice(ctx->device));
+    ncclUniqueId id;
+    memcpy(&id, unique_id_128, sizeof(id));
+    NCCL_CK(g_nccl.CommInitRank(&ctx->comm, nranks, id, rank));
+    ctx->rank = rank;
+    ctx->nranks = nranks;
+  });
+}
+
+int vgpu_comm_destroy(vgpu_ctx *ctx) {
+  return guard([&] {
+    if (!ctx) fail(VGPU_ERR_INVALID, "null context");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    if (ctx->comm) {
+      CUDA_CK(cudaSetDevice(ctx->device));
+      CUDA_CK(cudaStreamSynchronize(ctx->stream));
+      NCCL_CK(g_nccl.CommDestroy(ctx->comm));
+      ctx->comm = nullptr;
+    }
+    ctx->rank = 0;
+    ctx->nranks = 1;
+  });
+}
+
+}  // extern "C"
