@@ -1,0 +1,463 @@
+#!/usr/bin/env python
+"""bench.py — scanned rows/s of the scan -> filter -> group-by-aggregate hot path on B200.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c2] [--impl reference]
+
+A step = one pass of the hot path (vgpu_query_agg through the C ABI: prune, fused scan kernel,
+count-distinct dedupe, NCCL merge when N > 1, group extraction, groups copied to the host) over the
+whole resident table. One process per GPU (torchrun for N > 1); segments are sharded round-robin
+across ranks (weak scaling: the per-GPU table is fixed), the only data-path collective is the merge
+of the per-GPU partial group tables.
+
+Workloads (synthetic, splitmix64(seed=42), written directly in HBM):
+  c2 (default) 1e9 rows/GPU: d0 IN(5) AND n4 in [250,750) AND t5 in [T+2.5e6,T+7.5e6); group (d0,d1,d2,d3);
+               min, max, count-distinct            -> the 60 %-of-roofline target config of BASELINE.json
+  c1           1e8 rows/GPU: d0 == code; group (d1,d2); sum, count
+  c3           1e9 rows/GPU: time range; group (d0,d1,d2); sum
+  c4           1e9 rows/GPU: no filter; group (d0, hour/day/month rollup of t1); sum, count (1e7 groups)
+
+`--impl reference` times the reference's own CPU implementation (oracle/_ref/oracle_cli = the
+unmodified ViyaDB sources, JIT .so cache pre-warmed in the authoring container) on the box's host
+cores, as P shared-nothing single-threaded shards (the reference's own scale-out model).
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+T0 = 1490000000
+NOW = 1496570140
+SEG = 1_000_000
+
+# per workload: table config, generator (lo, range[, mode, div]) per schema column, query, per-row bytes
+WORKLOADS = {
+    "c1": {
+        "rows": 100_000_000,
+        "table": {"name": "events", "segment_size": SEG,
+                  "dimensions": [{"name": "d0"}, {"name": "d1"}, {"name": "d2"}, {"name": "d3"}],
+                  "metrics": [{"name": "count", "type": "count"}, {"name": "m1", "type": "long_sum"},
+                              {"name": "m2", "type": "int_sum"}]},
+        "gens": [(1, 16), (1, 1000), (1, 100), (1, 1_000_000), (1, 1), (0, 1000), (-50, 100)],
+        "prefix": ["a", "b", "c", "d", "", "", ""],
+        "query": {"type": "aggregate", "table": "events", "dimensions": ["d1", "d2"], "metrics": ["m1", "count"],
+                  "filter": {"op": "eq", "column": "d0", "value": "a7"}},
+        "filter_bytes": 4, "payload_bytes": 4 + 4 + 8 + 4, "full_bytes": 32, "dtype": "int64",
+    },
+    "c2": {
+        "rows": 1_000_000_000,
+        "table": {"name": "events", "segment_size": SEG,
+                  "dimensions": [{"name": "d0"}, {"name": "d1"}, {"name": "d2"}, {"name": "d3"},
+                                 {"name": "n4", "type": "ushort"}, {"name": "t5", "type": "time"}],
+                  "metrics": [{"name": "mn", "type": "int_min"}, {"name": "mx", "type": "int_max"},
+                              {"name": "uid", "type": "bitset"}]},
+        "gens": [(1, 50), (1, 20), (1, 50), (1, 100), (0, 1000), (T0, 10_000_000),
+                 (-2**31, 2**32), (-2**31, 2**32), (0, 1_000_000)],
+        "prefix": ["a", "b", "c", "d", "", "", "", "", ""],
+        "query": {"type": "aggregate", "table": "events", "dimensions": ["d0", "d1", "d2", "d3"],
+                  "metrics": ["mn", "mx", "uid"],
+                  "filter": {"op": "and", "filters": [
+                      {"op": "in", "column": "d0", "values": ["a3", "a11", "a19", "a27", "a42"]},
+                      {"op": "ge", "column": "n4", "value": "250"}, {"op": "lt", "column": "n4", "value": "750"},
+                      {"op": "ge", "column": "t5", "value": str(T0 + 2_500_000)},
+                      {"op": "lt", "column": "t5", "value": str(T0 + 7_500_000)}]}},
+        "filter_bytes": 4 + 2 + 4, "payload_bytes": 12 + 4 + 4 + 4, "full_bytes": 34, "dtype": "int32",
+    },
+    "c3": {
+        "rows": 1_000_000_000,
+        "table": {"name": "events", "segment_size": SEG,
+                  "dimensions": [{"name": "d0"}, {"name": "d1"}, {"name": "d2"}, {"name": "t3", "type": "time"}],
+                  "metrics": [{"name": "m1", "type": "long_sum"}]},
+        "gens": [(1, 100), (1, 100), (1, 100), (T0, 4_000_000), (0, 1000)],
+        "prefix": ["a", "b", "c", "", ""],
+        "query": {"type": "aggregate", "table": "events", "dimensions": ["d0", "d1", "d2"], "metrics": ["m1"],
+                  "filter": {"op": "and", "filters": [{"op": "ge", "column": "t3", "value": str(T0 + 1_000_000)},
+                                                      {"op": "lt", "column": "t3", "value": str(T0 + 2_000_000)}]}},
+        "filter_bytes": 4, "payload_bytes": 12 + 8, "full_bytes": 24, "dtype": "int64",
+    },
+    "c4": {
+        "rows": 1_000_000_000,
+        "table": {"name": "events", "segment_size": SEG,
+                  "dimensions": [{"name": "d0"},
+                                 {"name": "t1", "type": "time",
+                                  "rollup_rules": [{"granularity": "hour", "after": "1 days"},
+                                                   {"granularity": "day", "after": "1 weeks"},
+                                                   {"granularity": "month", "after": "1 years"}]}],
+                  "metrics": [{"name": "m1", "type": "long_sum"}, {"name": "count", "type": "count"}]},
+        "gens": [(1, 20000), (NOW - 730 * 86400, 730 * 86400), (0, 1000), (1, 1)],
+        "prefix": ["a", "", "", ""],
+        "query": {"type": "aggregate", "table": "events",
+                  "select": [{"column": "d0"}, {"column": "t1", "granularity": "hour"}, {"column": "m1"},
+                             {"column": "count"}]},
+        "filter_bytes": 0, "payload_bytes": 4 + 4 + 8 + 4, "full_bytes": 20, "dtype": "int64",
+    },
+}
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.gpu)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append((time.time(), line.strip()))
+
+    def stop(self, t_begin, t_end):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        for ts, line in self.lines:
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                clk = float(f[1])
+                mx = float(f[2])
+            except ValueError:
+                continue
+            if t_begin - 0.05 <= ts <= t_end + 0.05 or not sm:
+                sm.append(clk)
+                for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                    if val.lower().startswith("active"):
+                        reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+# the reference CPU arm
+# ------------------------------------------------------------------------------------------------
+def oracle_cli_path():
+    return os.path.join(ROOT, "oracle", "_ref", "oracle_cli")
+
+
+def reference_job(wname, rows, row_offset, repeat):
+    w = WORKLOADS[wname]
+    cols = []
+    table = w["table"]
+    names = [d["name"] for d in table["dimensions"]] + [m["name"] for m in table["metrics"]]
+    for (name, g, prefix) in zip(names, w["gens"], w["prefix"]):
+        mt = next((m for m in table["metrics"] if m["name"] == name), None)
+        if mt is not None and mt["type"] == "count":
+            continue  # count is not an input column
+        cols.append({"prefix": prefix, "lo": g[0], "range": g[1]})
+    return {"state_dir": os.path.join(ROOT, "oracle", "_ref", "state"), "rollup_ts": NOW, "table": table,
+            "generate": {"n": rows, "seed": 42, "row_offset": row_offset, "columns": cols},
+            "queries": [w["query"]], "repeat": repeat}
+
+
+def run_reference(wname, rows_per_proc, procs, warmup, steps):
+    """P shared-nothing single-threaded reference processes, each owning rows_per_proc rows, all
+    running the same query concurrently. Returns (rows/s, ms_per_step, total_rows, detail)."""
+    cli = oracle_cli_path()
+    if not os.path.exists(cli):
+        return None
+    tmp = tempfile.mkdtemp(prefix="vgpu_ref_")
+    ps = []
+    for p in range(procs):
+        job = reference_job(wname, rows_per_proc, p * rows_per_proc, warmup + steps)
+        jp = os.path.join(tmp, f"job{p}.json")
+        json.dump(job, open(jp, "w"))
+        ps.append(subprocess.Popen([cli, jp], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True))
+    per_proc, scanned = [], 0
+    for p in ps:
+        out, err = p.communicate()
+        lines = out.strip().splitlines()
+        if p.returncode != 0 or not lines:
+            return {"error": (lines[-1] if lines else err)[-300:]}
+        res = json.loads(lines[-1])
+        r = res["results"][0]
+        if "error" in r:
+            return {"error": r["error"][-300:]}
+        per_proc.append([t["whole_ms"] - t["compile_ms"] for t in r["timings"]][warmup:])
+        scanned += r["stats"]["scanned_recs"]
+    step_ms = [max(pp[i] for pp in per_proc) for i in range(steps)]
+    ms = sum(step_ms) / len(step_ms)
+    return {"value": scanned / (ms / 1e3), "ms_per_step": ms, "rows": scanned, "best_ms": min(step_ms)}
+
+
+def main_reference(args):
+    if int(os.environ.get("RANK", "0")) != 0:
+        return 0
+    procs = os.cpu_count() or 1
+    rows_per_proc = args.ref_rows // procs
+    r = run_reference(args.workload, rows_per_proc, procs, args.warmup, args.steps)
+    w = WORKLOADS[args.workload]
+    line = {"impl": "reference", "metric": "scanned rows/sec", "unit": "rows/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": w["dtype"], "data": "synthetic",
+            "config": {"workload": f"{args.workload} ({describe(args.workload)})", "rows": None}}
+    if r is None or "error" in (r or {}):
+        line["unavailable"] = "oracle/_ref/oracle_cli missing" if r is None else "reference run failed: " + r["error"]
+        print(json.dumps(line))
+        return 0
+    sample = f"{r['rows']} rows of {args.workload} as {procs} shared-nothing single-threaded reference shards"
+    line.update({"value": r["value"], "ms_per_step": r["ms_per_step"],
+                 "cpu_baseline": {"value": r["value"], "unit": "rows/s", "cores": procs, "kind": "reference", "sample": sample},
+                 "e2e": {"value": r["value"], "unit": "rows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
+    line["config"]["rows"] = r["rows"]
+    print(json.dumps(line))
+    return 0
+
+
+def describe(wname):
+    return {"c1": "1e8 rows/GPU, eq filter, 2-key group-by, sum+count",
+            "c2": "1e9 rows/GPU, IN + 2 range predicates over 3 dims, 4-key group-by, min/max + count-distinct",
+            "c3": "1e9 rows/GPU, time-range filter, 3-key group-by, sum",
+            "c4": "1e9 rows/GPU, no filter, (dim, rolled-up time) group-by ~1e7 groups, sum+count"}[wname]
+
+
+# ------------------------------------------------------------------------------------------------
+# the CUDA arm
+# ------------------------------------------------------------------------------------------------
+def main_ours(args):
+    import torch
+    import viyadb_b200 as v
+    from viyadb_b200 import _native as N
+    from viyadb_b200.query import GpuQueryRunner, QueryFactory
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: viyadb_b200 has no CPU path")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    w = WORKLOADS[args.workload]
+    rows = args.rows or w["rows"]
+    table_conf = dict(w["table"])
+    db = v.Database({"tables": [table_conf]}, device=local)
+    lib = N.load()
+    stream = torch.cuda.current_stream()
+    N.check(lib.vgpu_set_stream(db.ctx, stream.cuda_stream))
+    if world > 1:
+        uid = [v.Database.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        db.init_comm(rank, world, uid[0])
+    t = db.get_table("events")
+    # dictionaries: code k <-> "<prefix>k" (code 0 stays "__exceeded")
+    for d, g, prefix in zip(t.dimensions, w["gens"], w["prefix"]):
+        if d.dict is not None:
+            for k in range(1, g[0] + g[1]):
+                d.dict.encode(f"{prefix}{k}")
+    # segments: global segment s lives on rank s % world
+    nseg = (rows + SEG - 1) // SEG
+    t_gen = time.time()
+    for ls in range(nseg):
+        gs = ls * world + rank
+        n = min(SEG, rows - ls * SEG)
+        t.generate_segment(ls, n, w["gens"], seed=42, row_offset=gs * SEG)
+    torch.cuda.synchronize()
+    t_gen = time.time() - t_gen
+
+    query = QueryFactory.create(w["query"], db)
+    runner = GpuQueryRunner(db, v.MemoryRowOutput(), now=NOW)
+    plan = runner.build_plan(query)
+
+    def step():
+        return runner.run_plan(query, plan)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        groups = step()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.25)
+    scan_ms, gpu_ms, launches = [], [], 0
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    wall0 = time.time()
+    ev0.record(stream)
+    for _ in range(args.steps):
+        groups = step()
+        scan_ms.append(runner.stats.kernel_scan_ms)
+        gpu_ms.append(runner.stats.gpu_ms)
+        launches += runner.stats.launches
+    ev1.record(stream)
+    barrier()
+    wall1 = time.time()
+    elapsed_ms = ev0.elapsed_time(ev1)
+    if dist is not None:
+        tt = torch.tensor([elapsed_ms, sum(scan_ms) / len(scan_ms)], device="cuda", dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        elapsed_ms, scan_avg = tt.tolist()
+    else:
+        scan_avg = sum(scan_ms) / len(scan_ms)
+    clocks = sampler.stop(wall0, wall1) if rank == 0 else None
+    total_rows = rows * world
+    passed = runner.stats.passed_rows
+    ngroups = groups["ngroups"]
+    selectivity = passed / max(1, runner.stats.scanned_recs)   # this rank's share
+    b_alg = w["filter_bytes"] + selectivity * w["payload_bytes"]
+    peak, peak_src = load_peaks()
+    achieved = rows * b_alg / (scan_avg / 1e3) / 1e9
+    value = total_rows * args.steps / (elapsed_ms / 1e3)
+
+    # ---- e2e: host buffers -> put_segment (H2D from pinned memory) -> query -> groups on host ----
+    e2e = None
+    if not args.no_e2e:
+        e2e = measure_e2e(torch, v, db, t, query, runner, plan, rows, nseg, world, dist, stream, args)
+
+    # ---- CPU baseline (rank 0, N=1 only) ----
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        procs = os.cpu_count() or 1
+        r = run_reference(args.workload, args.ref_rows // procs, procs, 1, 3)
+        if r and "error" not in r:
+            cpu = {"value": r["value"], "unit": "rows/s", "cores": procs, "kind": "reference",
+                   "sample": f"{r['rows']} rows of {args.workload} as {procs} shared-nothing single-threaded shards of "
+                             f"the unmodified reference (oracle/_ref/oracle_cli), query time only, mean of 3"}
+        else:
+            cpu = {"value": None, "unit": "rows/s", "cores": procs, "kind": "reference",
+                   "sample": "unavailable: " + ("oracle_cli missing" if r is None else r["error"])}
+
+    if rank == 0:
+        line = {
+            "metric": "scanned rows/sec", "value": value, "unit": "rows/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": w["dtype"], "data": "synthetic",
+            "config": {"workload": f"{args.workload} ({describe(args.workload)})", "rows_per_gpu": rows,
+                       "segments_per_gpu": nseg, "segment_size": SEG, "groups": ngroups,
+                       "selectivity": selectivity, "resident_bytes_per_gpu": t.device_bytes,
+                       "l2_policy": "inputs larger than L2 (table >> 126 MB), no flush needed",
+                       "group_table": "dense" if runner.stats.table_mode == 0 else "hash",
+                       "parallelism": f"segment-sharded x{world}, one NCCL merge of partial group tables" if world > 1 else "single GPU"},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "kernel": "scan_filter_groupby_kernel", "kernel_ms": scan_avg,
+                         "algorithmic_bytes_per_row": b_alg, "algorithmic_bytes_per_launch": rows * b_alg,
+                         "peak_source": peak_src},
+            "gpu_launches": launches, "gpu_ms_per_step": sum(gpu_ms) / len(gpu_ms),
+            "clocks": clocks, "e2e": e2e, "cpu_baseline": cpu, "generate_s": t_gen,
+        }
+        print(json.dumps(line))
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+    db.close()
+    return 0
+
+
+def measure_e2e(torch, v, db, t, query, runner, plan, rows, nseg, world, dist, stream, args):
+    """Same metric through the public API with HOST buffers: every step copies every column of every
+    segment from pinned host memory into HBM (Table.put_segment -> vgpu_segment_put), runs the query
+    and reads the groups back. PCIe-bound by construction."""
+    import ctypes as C
+    from viyadb_b200 import _native as N
+    lib = N.load()
+    e_rows = min(rows, args.e2e_rows) if args.e2e_rows else rows
+    e_nseg = (e_rows + SEG - 1) // SEG
+    cols = t.dimensions + t.metrics
+    pinned, views = {}, {}
+    h2d = 0
+    for c in cols:
+        width = 4 if c.kind == N.METRIC_BITSET else N.TYPE_WIDTH[c.type]
+        buf = torch.empty(e_rows * width, dtype=torch.uint8, pin_memory=True)
+        pinned[c.name] = buf
+        views[c.name] = buf.numpy().view("<u4" if c.kind == N.METRIC_BITSET else N.NP_DTYPES[c.type])
+        h2d += e_rows * width
+        for s in range(e_nseg):   # fill the host buffers from the generated table (device -> pinned host)
+            n = min(SEG, e_rows - s * SEG)
+            N.check(lib.vgpu_segment_read(t.handle, s, t.schema_index(c), C.c_void_p(buf.data_ptr() + s * SEG * width)))
+    host = []
+    for s in range(e_nseg):
+        n = min(SEG, e_rows - s * SEG)
+        host.append({c.name: views[c.name][s * SEG:s * SEG + n] for c in cols})
+
+    def step():
+        for s, seg in enumerate(host):
+            t.put_segment(s, seg)
+        return runner.run_plan(query, runner.build_plan(query))
+
+    for _ in range(2):
+        g = step()
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    k = 3
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(stream)
+    for _ in range(k):
+        g = step()
+    ev1.record(stream)
+    torch.cuda.synchronize()
+    ms = ev0.elapsed_time(ev1) / k
+    if dist is not None:
+        tt = torch.tensor([ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms = tt.item()
+    d2h = sum(a.nbytes for a in g["keys"]) + sum(a.nbytes for a in g["accs"])
+    # the query scans the whole table: segments beyond e_nseg stay resident from the first leg
+    scanned = runner.stats.scanned_recs
+    return {"value": scanned * world / (ms / 1e3), "unit": "rows/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+            "rows_uploaded_per_gpu_per_step": e_rows, "rows_scanned_per_gpu_per_step": scanned, "ms_per_step": ms, "steps": k,
+            "note": "every step re-uploads all columns from pinned host memory (vgpu_segment_put), then runs the query "
+                    "and copies the groups back; PCIe-bound"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--rows", type=int, default=0, help="rows per GPU (default: the workload's)")
+    ap.add_argument("--e2e-rows", type=int, default=0, help="rows per GPU re-uploaded per e2e step (0 = the whole table)")
+    ap.add_argument("--ref-rows", type=int, default=16_000_000, help="total rows of the bounded CPU sample")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return main_reference(args)
+    return main_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

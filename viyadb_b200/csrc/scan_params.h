@@ -15,10 +15,10 @@ constexpr int kRowsPerThread = kVec * kSub;
 constexpr int kSubRows = kThreads * kVec;       // 1024
 constexpr int kTileRows = kSubRows * kSub;      // 4096 rows per CTA iteration
 
-constexpr int kMaxSlots = 16;   // distinct columns one query may touch
+constexpr int kMaxSlots = 32;   // distinct columns one query may touch
 constexpr int kMaxProg = 64;    // predicate program length (leaves + combinators)
-constexpr int kMaxKeys = 8;
-constexpr int kMaxMetrics = 8;
+constexpr int kMaxKeys = 12;
+constexpr int kMaxMetrics = 16;
 constexpr int kMaxRules = 8;
 constexpr int kStackDepth = 6;
 constexpr int kMaxDistinct = 2;
