@@ -27,21 +27,30 @@ constexpr uint64_t kEmptyKey = ~0ull;
 // ---------------------------------------------------------------------------------------------
 // streaming loads (filter columns are read exactly once: keep them out of L1)
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint4 ldg_stream128(const void *p) {
+// An L2 evict-first policy: column data is read exactly once, it must not push the group table
+// (pinned with an access-policy window) or anything else out of L2.
+__device__ __forceinline__ uint64_t make_stream_policy(bool evict_first) {
+  uint64_t pol;
+  if (evict_first) asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  else asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ uint4 ldg_stream128(const void *p, uint64_t pol) {
   uint4 r;
-  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;"
                : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
-               : "l"(p));
+               : "l"(p), "l"(pol));
   return r;
 }
-__device__ __forceinline__ uint2 ldg_stream64(const void *p) {
+__device__ __forceinline__ uint2 ldg_stream64(const void *p, uint64_t pol) {
   uint2 r;
-  asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));
+  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v2.u32 {%0,%1}, [%2], %3;"
+               : "=r"(r.x), "=r"(r.y) : "l"(p), "l"(pol));
   return r;
 }
-__device__ __forceinline__ uint32_t ldg_stream32(const void *p) {
+__device__ __forceinline__ uint32_t ldg_stream32(const void *p, uint64_t pol) {
   uint32_t r;
-  asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(r) : "l"(p));
+  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(r) : "l"(p), "l"(pol));
   return r;
 }
 
@@ -64,6 +73,61 @@ __device__ __forceinline__ uint64_t load_elem(const uint8_t *p, uint32_t width, 
     default:
       return __ldg(reinterpret_cast<const unsigned long long *>(p));
   }
+}
+
+// Gather flavour of load_elem for the cells of passing rows. Measured on B200 (tools/gather_probe.cu):
+// a plain ld.global(.nc) miss makes L1 request the whole 128-byte line (4 sectors, ~125 B of DRAM
+// traffic per 4-byte gather, whatever cudaLimitMaxL2FetchGranularity says); the .L2::64B qualifier
+// halves that to one 64-byte DRAM atom. PTX offers no smaller prefetch size.
+__device__ __forceinline__ uint64_t gather_elem(const uint8_t *p, uint32_t width, uint32_t sext) {
+  switch (width) {
+    case 1: {
+      uint32_t v;
+      asm volatile("ld.global.nc.L2::64B.u8 %0, [%1];" : "=r"(v) : "l"(p));
+      return sext ? (uint64_t)(int64_t)(int8_t)v : (uint64_t)(v & 0xffu);
+    }
+    case 2: {
+      uint32_t v;
+      asm volatile("ld.global.nc.L2::64B.u16 %0, [%1];" : "=r"(v) : "l"(p));
+      return sext ? (uint64_t)(int64_t)(int16_t)v : (uint64_t)(v & 0xffffu);
+    }
+    case 4: {
+      uint32_t v;
+      asm volatile("ld.global.nc.L2::64B.u32 %0, [%1];" : "=r"(v) : "l"(p));
+      return sext ? (uint64_t)(int64_t)(int32_t)v : (uint64_t)v;
+    }
+    default: {
+      unsigned long long v;
+      asm volatile("ld.global.nc.L2::64B.u64 %0, [%1];" : "=l"(v) : "l"(p));
+      return v;
+    }
+  }
+}
+// Branch-free gather of one cell of any width: load the aligned 8-byte word that contains it and
+// shift / mask / sign-extend with per-slot constants. No control flow, so the loads of all key and
+// metric cells of a row issue back to back (a switch on the width would put every load in its own
+// basic block and serialise the DRAM round trips — measured: 8 equal stall shares, ncu r1 v3).
+// Column bases are 4096-byte aligned and slab capacities whole tiles, so the aligned word is always
+// inside the column.
+__device__ __forceinline__ uint64_t gather_raw64(const uint8_t *p) {
+  unsigned long long v;
+  asm("ld.global.nc.L2::64B.u64 %0, [%1];" : "=l"(v) : "l"(reinterpret_cast<uintptr_t>(p) & ~7ull));
+  return v;
+}
+__device__ __forceinline__ uint64_t gather_finish(uint64_t raw, const uint8_t *p, uint64_t vmask, uint64_t signbit) {
+  uint64_t v = (raw >> ((reinterpret_cast<uintptr_t>(p) & 7u) * 8u)) & vmask;
+  return (v ^ signbit) - signbit;
+}
+// 32-bit flavour for cells of at most 4 bytes (dictionary codes, time, int metrics): half the registers.
+__device__ __forceinline__ uint32_t gather_raw32(const uint8_t *p) {
+  uint32_t v;
+  asm("ld.global.nc.L2::64B.u32 %0, [%1];" : "=r"(v) : "l"(reinterpret_cast<uintptr_t>(p) & ~3ull));
+  return v;
+}
+__device__ __forceinline__ uint32_t gather_u32(const uint32_t *p) {
+  uint32_t v;
+  asm volatile("ld.global.nc.L2::64B.u32 %0, [%1];" : "=r"(v) : "l"(p));
+  return v;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -102,7 +166,7 @@ __device__ __forceinline__ uint64_t trunc_seconds(uint64_t t, uint32_t unit) {
   }
 }
 
-__device__ __forceinline__ uint64_t rollup_value(uint64_t v, const KeySpec &k) {
+__device__ __noinline__ uint64_t rollup_value(uint64_t v, const KeySpec &k) {
   uint32_t unit = 7;  // VGPU_TU_NONE
   for (uint32_t r = 0; r < k.nrules; ++r) {
     if (v < k.rule_boundary[r]) {  // first matching rule wins (rollup.cc:77-95)
@@ -125,39 +189,68 @@ __device__ __forceinline__ uint64_t rollup_value(uint64_t v, const KeySpec &k) {
 // ---------------------------------------------------------------------------------------------
 // accumulator update == Metrics::Update (store.cc:131-161), on native atomics
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ void acc_update(void *acc, uint64_t cell, uint32_t op, uint64_t v) {
+// All accumulator traffic carries an L2 cache-policy operand (evict_last when the table fits L2): the
+// columns stream through L2 and, with default priorities, evict the accumulator lines so that almost
+// every RED goes to DRAM (ncu r1: 87 % of RED sectors missed L2 at 5e5 groups).
+__device__ __forceinline__ uint64_t make_table_policy(bool evict_last) {
+  uint64_t pol;
+  if (evict_last) asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+  else asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+#define VGPU_RED(op_type, cst, addr, val, pol) \
+  asm volatile("red.global." op_type ".L2::cache_hint [%0], %1, %2;" ::"l"(addr), cst(val), "l"(pol) : "memory")
+// PTX wants the type last: red.global.add.L2::cache_hint.u32
+#define VGPU_RED2(op, type, cst, addr, val, pol) \
+  asm volatile("red.global." op ".L2::cache_hint." type " [%0], %1, %2;" ::"l"(addr), cst(val), "l"(pol) : "memory")
+
+__device__ __forceinline__ void red_min_s32(void *a, int v, uint64_t pol) { VGPU_RED2("min", "s32", "r", a, v, pol); }
+__device__ __forceinline__ void red_max_s32(void *a, int v, uint64_t pol) { VGPU_RED2("max", "s32", "r", a, v, pol); }
+__device__ __forceinline__ void red_min_u32(void *a, uint32_t v, uint64_t pol) { VGPU_RED2("min", "u32", "r", a, v, pol); }
+__device__ __forceinline__ void red_max_u32(void *a, uint32_t v, uint64_t pol) { VGPU_RED2("max", "u32", "r", a, v, pol); }
+__device__ __forceinline__ void red_min_s64(void *a, long long v, uint64_t pol) { VGPU_RED2("min", "s64", "l", a, v, pol); }
+__device__ __forceinline__ void red_max_s64(void *a, long long v, uint64_t pol) { VGPU_RED2("max", "s64", "l", a, v, pol); }
+__device__ __forceinline__ void red_min_u64(void *a, unsigned long long v, uint64_t pol) { VGPU_RED2("min", "u64", "l", a, v, pol); }
+__device__ __forceinline__ void red_max_u64(void *a, unsigned long long v, uint64_t pol) { VGPU_RED2("max", "u64", "l", a, v, pol); }
+__device__ __forceinline__ void red_add_u32(void *a, uint32_t v, uint64_t pol) { VGPU_RED2("add", "u32", "r", a, v, pol); }
+__device__ __forceinline__ void red_add_u64(void *a, unsigned long long v, uint64_t pol) { VGPU_RED2("add", "u64", "l", a, v, pol); }
+__device__ __forceinline__ void red_add_f32(void *a, float v, uint64_t pol) { VGPU_RED2("add", "f32", "f", a, v, pol); }
+__device__ __forceinline__ void red_add_f64(void *a, double v, uint64_t pol) { VGPU_RED2("add", "f64", "d", a, v, pol); }
+__device__ __forceinline__ void st_u8_hint(uint8_t *a, uint32_t v, uint64_t pol) {
+  asm volatile("st.global.L2::cache_hint.u8 [%0], %1, %2;" ::"l"(a), "r"(v), "l"(pol) : "memory");
+}
+
+__device__ __forceinline__ void acc_update(void *acc, uint64_t cell, uint32_t op, uint64_t v, uint64_t pol) {
+  uint32_t *a32 = reinterpret_cast<uint32_t *>(acc) + cell;
+  uint64_t *a64 = reinterpret_cast<uint64_t *>(acc) + cell;
   switch (op) {
-    case A_ADD32: atomicAdd(reinterpret_cast<unsigned int *>(acc) + cell, (unsigned int)v); break;
-    case A_ADD64: atomicAdd(reinterpret_cast<unsigned long long *>(acc) + cell, (unsigned long long)v); break;
-    case A_ADDF32: atomicAdd(reinterpret_cast<float *>(acc) + cell, __uint_as_float((uint32_t)v)); break;
-    case A_ADDF64: atomicAdd(reinterpret_cast<double *>(acc) + cell, __longlong_as_double((long long)v)); break;
-    case A_MINS32: atomicMin(reinterpret_cast<int *>(acc) + cell, (int)(uint32_t)v); break;
-    case A_MAXS32: atomicMax(reinterpret_cast<int *>(acc) + cell, (int)(uint32_t)v); break;
-    case A_MINU32: atomicMin(reinterpret_cast<unsigned int *>(acc) + cell, (unsigned int)v); break;
-    case A_MAXU32: atomicMax(reinterpret_cast<unsigned int *>(acc) + cell, (unsigned int)v); break;
-    case A_MINS64: atomicMin(reinterpret_cast<long long *>(acc) + cell, (long long)v); break;
-    case A_MAXS64: atomicMax(reinterpret_cast<long long *>(acc) + cell, (long long)v); break;
-    case A_MINU64: atomicMin(reinterpret_cast<unsigned long long *>(acc) + cell, (unsigned long long)v); break;
-    case A_MAXU64: atomicMax(reinterpret_cast<unsigned long long *>(acc) + cell, (unsigned long long)v); break;
+    case A_ADD32: red_add_u32(a32, (uint32_t)v, pol); break;
+    case A_ADD64: red_add_u64(a64, v, pol); break;
+    case A_ADDF32: red_add_f32(a32, __uint_as_float((uint32_t)v), pol); break;
+    case A_ADDF64: red_add_f64(a64, __longlong_as_double((long long)v), pol); break;
+    case A_MINS32: red_min_s32(a32, (int)(uint32_t)v, pol); break;
+    case A_MAXS32: red_max_s32(a32, (int)(uint32_t)v, pol); break;
+    case A_MINU32: red_min_u32(a32, (uint32_t)v, pol); break;
+    case A_MAXU32: red_max_u32(a32, (uint32_t)v, pol); break;
+    case A_MINS64: red_min_s64(a64, (long long)v, pol); break;
+    case A_MAXS64: red_max_s64(a64, (long long)v, pol); break;
+    case A_MINU64: red_min_u64(a64, v, pol); break;
+    case A_MAXU64: red_max_u64(a64, v, pol); break;
     // IEEE order on raw bits: non-negative floats order like signed ints, negative floats in
     // reverse like unsigned ints. (NaN metrics are outside the reference's tested domain.)
     case A_MAXF32: {
       uint32_t b = (uint32_t)v;
-      if (!(b >> 31)) atomicMax(reinterpret_cast<int *>(acc) + cell, (int)b);
-      else atomicMin(reinterpret_cast<unsigned int *>(acc) + cell, b);
+      if (!(b >> 31)) red_max_s32(a32, (int)b, pol); else red_min_u32(a32, b, pol);
     } break;
     case A_MINF32: {
       uint32_t b = (uint32_t)v;
-      if (!(b >> 31)) atomicMin(reinterpret_cast<int *>(acc) + cell, (int)b);
-      else atomicMax(reinterpret_cast<unsigned int *>(acc) + cell, b);
+      if (!(b >> 31)) red_min_s32(a32, (int)b, pol); else red_max_u32(a32, b, pol);
     } break;
     case A_MAXF64: {
-      if (!(v >> 63)) atomicMax(reinterpret_cast<long long *>(acc) + cell, (long long)v);
-      else atomicMin(reinterpret_cast<unsigned long long *>(acc) + cell, (unsigned long long)v);
+      if (!(v >> 63)) red_max_s64(a64, (long long)v, pol); else red_min_u64(a64, v, pol);
     } break;
     case A_MINF64: {
-      if (!(v >> 63)) atomicMin(reinterpret_cast<long long *>(acc) + cell, (long long)v);
-      else atomicMax(reinterpret_cast<unsigned long long *>(acc) + cell, (unsigned long long)v);
+      if (!(v >> 63)) red_min_s64(a64, (long long)v, pol); else red_max_u64(a64, v, pol);
     } break;
     default: break;
   }
@@ -191,287 +284,6 @@ __device__ __forceinline__ uint64_t hash_cell(const ScanParams &P, uint64_t key)
     slot = (slot + 1) & P.hmask;
   }
   return kEmptyKey;
-}
-
-// ---------------------------------------------------------------------------------------------
-// predicate interpreter: 16 rows per thread, bit (s*4+j) of the result = row s*1024 + tid*4 + j
-// ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ void load_vec16(const uint8_t *col, uint32_t width, uint64_t row0,
-                                           uint32_t (&v)[kRowsPerThread]) {
-  if (width == 4) {
-    uint4 q[kSub];
-#pragma unroll
-    for (int s = 0; s < kSub; ++s) q[s] = ldg_stream128(col + (row0 + (uint64_t)s * kSubRows) * 4);
-#pragma unroll
-    for (int s = 0; s < kSub; ++s) {
-      v[s * 4 + 0] = q[s].x; v[s * 4 + 1] = q[s].y; v[s * 4 + 2] = q[s].z; v[s * 4 + 3] = q[s].w;
-    }
-  } else if (width == 2) {
-    uint2 q[kSub];
-#pragma unroll
-    for (int s = 0; s < kSub; ++s) q[s] = ldg_stream64(col + (row0 + (uint64_t)s * kSubRows) * 2);
-#pragma unroll
-    for (int s = 0; s < kSub; ++s) {
-      v[s * 4 + 0] = q[s].x & 0xffffu; v[s * 4 + 1] = q[s].x >> 16;
-      v[s * 4 + 2] = q[s].y & 0xffffu; v[s * 4 + 3] = q[s].y >> 16;
-    }
-  } else {
-    uint32_t q[kSub];
-#pragma unroll
-    for (int s = 0; s < kSub; ++s) q[s] = ldg_stream32(col + (row0 + (uint64_t)s * kSubRows));
-#pragma unroll
-    for (int s = 0; s < kSub; ++s) {
-      v[s * 4 + 0] = q[s] & 0xffu; v[s * 4 + 1] = (q[s] >> 8) & 0xffu;
-      v[s * 4 + 2] = (q[s] >> 16) & 0xffu; v[s * 4 + 3] = q[s] >> 24;
-    }
-  }
-}
-
-__device__ __forceinline__ bool gen_compare(uint32_t gcls, uint32_t gop, uint64_t v, uint64_t a) {
-  switch (gcls) {
-    case G_I64: {
-      long long x = (long long)v, y = (long long)a;
-      switch (gop) { case 0: return x == y; case 1: return x != y; case 2: return x < y;
-                     case 3: return x <= y; case 4: return x > y; default: return x >= y; }
-    }
-    case G_F32: {
-      float x = __uint_as_float((uint32_t)v), y = __uint_as_float((uint32_t)a);
-      switch (gop) { case 0: return x == y; case 1: return x != y; case 2: return x < y;
-                     case 3: return x <= y; case 4: return x > y; default: return x >= y; }
-    }
-    case G_F64: {
-      double x = __longlong_as_double((long long)v), y = __longlong_as_double((long long)a);
-      switch (gop) { case 0: return x == y; case 1: return x != y; case 2: return x < y;
-                     case 3: return x <= y; case 4: return x > y; default: return x >= y; }
-    }
-    default: {  // G_U64, G_CARD
-      switch (gop) { case 0: return v == a; case 1: return v != a; case 2: return v < a;
-                     case 3: return v <= a; case 4: return v > a; default: return v >= a; }
-    }
-  }
-}
-
-__device__ __forceinline__ uint64_t bitset_card(const SegDesc &seg, uint32_t bidx, uint64_t row) {
-  const uint32_t *off = seg.bs_offsets[bidx];
-  if (off == nullptr) return 1;
-  return (uint64_t)(__ldg(off + row + 1) - __ldg(off + row));
-}
-
-__device__ __forceinline__ uint32_t eval_predicate(const ScanParams &P, const SegDesc &seg,
-                                                   uint64_t row0) {
-  uint32_t stk[kStackDepth];
-#pragma unroll
-  for (int i = 0; i < kStackDepth; ++i) stk[i] = 0;
-  uint32_t v[kRowsPerThread];
-  int cached = -1;
-  for (uint32_t pc = 0; pc < P.nprog; ++pc) {
-    const PInstr &in = P.prog[pc];
-    const uint32_t kind = in.kind;
-    if (kind <= P_OR_LEAF) {
-      uint32_t m = 0;
-      const uint32_t cls = in.cls;
-      if (cls == C_TRUE) {
-        m = 0xffffu;
-      } else if (cls == C_FALSE) {
-        m = 0;
-      } else if (cls == C_GEN) {
-        const Slot &sl = P.slots[in.slot];
-#pragma unroll
-        for (int s = 0; s < kSub; ++s) {
-#pragma unroll
-          for (int j = 0; j < kVec; ++j) {
-            uint64_t row = row0 + (uint64_t)s * kSubRows + j;
-            uint64_t val = 0;
-            if (row < seg.nrows) {  // scalar path must not read past the logical end of CSR tables
-              val = sl.bitset ? bitset_card(seg, sl.bitset_idx, row)
-                              : load_elem(seg.slab + sl.off * seg.cap + row * sl.width, sl.width, sl.sext);
-            }
-            if (gen_compare(in.gcls, in.gop, val, in.arg)) m |= 1u << (s * 4 + j);
-          }
-        }
-      } else {
-        if ((int)in.slot != cached) {
-          const Slot &sl = P.slots[in.slot];
-          load_vec16(seg.slab + sl.off * seg.cap, sl.width, row0, v);
-          cached = in.slot;
-        }
-        const uint32_t a = (uint32_t)in.arg;
-        if (cls == C_EQ32) {
-#pragma unroll
-          for (int i = 0; i < kRowsPerThread; ++i) m |= (v[i] == a) ? (1u << i) : 0u;
-        } else if (cls == C_LT32) {
-          const uint32_t bias = in.bias;
-#pragma unroll
-          for (int i = 0; i < kRowsPerThread; ++i) m |= ((v[i] ^ bias) < a) ? (1u << i) : 0u;
-        } else {  // C_RNG32
-          const uint32_t bias = in.bias, len = in.arg2;
-#pragma unroll
-          for (int i = 0; i < kRowsPerThread; ++i) m |= (((v[i] ^ bias) - a) < len) ? (1u << i) : 0u;
-        }
-      }
-      if (in.neg) m ^= 0xffffu;
-      if (kind == P_PUSH) {
-#pragma unroll
-        for (int i = kStackDepth - 1; i > 0; --i) stk[i] = stk[i - 1];
-        stk[0] = m;
-      } else if (kind == P_AND_LEAF) {
-        stk[0] &= m;
-      } else {
-        stk[0] |= m;
-      }
-    } else {
-      uint32_t r = (kind == P_AND) ? (stk[1] & stk[0]) : (stk[1] | stk[0]);
-      stk[0] = r;
-#pragma unroll
-      for (int i = 1; i < kStackDepth - 1; ++i) stk[i] = stk[i + 1];
-    }
-  }
-  return stk[0];
-}
-
-// ---------------------------------------------------------------------------------------------
-// the fused scan kernel
-// ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kThreads, 4)
-scan_filter_groupby_kernel(const __grid_constant__ ScanParams P) {
-  __shared__ unsigned long long s_pair_base[kMaxDistinct];
-  __shared__ uint32_t s_warp_tot[kMaxDistinct][kThreads / 32];
-  __shared__ unsigned long long s_passed;
-
-  const uint32_t tid = threadIdx.x;
-  const uint32_t lane = tid & 31, warp = tid >> 5;
-  if (tid == 0) s_passed = 0;
-  unsigned long long my_passed = 0;
-
-  for (uint64_t tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
-    const uint32_t si = (uint32_t)(tile / P.tiles_per_seg);
-    const uint32_t ti = (uint32_t)(tile - (uint64_t)si * P.tiles_per_seg);
-    const SegDesc &seg = P.segs[P.active[si]];
-    const uint64_t nrows = seg.nrows;
-    const uint64_t tile_row = (uint64_t)ti * kTileRows;
-    if (tile_row >= nrows) continue;  // uniform per CTA
-    const uint64_t row0 = tile_row + (uint64_t)tid * kVec;
-    // a full group table / pair buffer makes the host grow it and run again: stop wasting time
-    if (P.hash_mode || P.ndistinct) {
-      if (__syncthreads_or(*reinterpret_cast<volatile unsigned long long *>(&P.counters[1]) != 0ull)) break;
-    }
-
-    uint32_t mask = eval_predicate(P, seg, row0);
-    // rows past the end of a partially filled segment never count
-    if (tile_row + kTileRows > nrows) {
-#pragma unroll
-      for (int s = 0; s < kSub; ++s) {
-#pragma unroll
-        for (int j = 0; j < kVec; ++j) {
-          if (row0 + (uint64_t)s * kSubRows + j >= nrows) mask &= ~(1u << (s * 4 + j));
-        }
-      }
-    }
-    my_passed += __popc(mask);
-
-    // ---- count-distinct: reserve space in the pair buffers for this tile (one atomic per CTA) ----
-    unsigned long long pair_pos[kMaxDistinct];
-    if (P.ndistinct > 0) {
-      for (uint32_t d = 0; d < P.ndistinct; ++d) {
-        const Slot &sl = P.slots[P.mets[P.distinct_met[d]].slot];
-        uint32_t cnt = 0;
-        if (seg.bs_offsets[sl.bitset_idx] == nullptr) {
-          cnt = __popc(mask);
-        } else {
-          uint32_t m = mask;
-          while (m) {
-            int b = __ffs(m) - 1;
-            m &= m - 1;
-            uint64_t row = row0 + (uint64_t)(b >> 2) * kSubRows + (b & 3);
-            cnt += (uint32_t)bitset_card(seg, sl.bitset_idx, row);
-          }
-        }
-        uint32_t incl = cnt;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-          uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
-          if (lane >= o) incl += t;
-        }
-        if (lane == 31) s_warp_tot[d][warp] = incl;
-        pair_pos[d] = incl - cnt;  // exclusive within the warp
-      }
-      __syncthreads();
-      if (tid < P.ndistinct) {
-        uint32_t tot = 0;
-        for (int w = 0; w < kThreads / 32; ++w) {
-          uint32_t t = s_warp_tot[tid][w];
-          s_warp_tot[tid][w] = tot;
-          tot += t;
-        }
-        unsigned long long base = 0;
-        if (tot) base = atomicAdd(&P.counters[2 + tid], (unsigned long long)tot);
-        if (base + tot > P.pairs_cap[tid]) {
-          atomicExch(&P.counters[1], 1ull);
-          base = ~0ull;
-        }
-        s_pair_base[tid] = base;
-      }
-      __syncthreads();
-      for (uint32_t d = 0; d < P.ndistinct; ++d) {
-        unsigned long long base = s_pair_base[d];
-        pair_pos[d] = (base == ~0ull) ? ~0ull : base + s_warp_tot[d][warp] + pair_pos[d];
-      }
-      __syncthreads();  // s_warp_tot / s_pair_base are reused by the next tile
-    }
-
-    // ---- aggregate the passing rows ----
-    while (mask) {
-      const int b = __ffs(mask) - 1;
-      mask &= mask - 1;
-      const uint64_t row = row0 + (uint64_t)(b >> 2) * kSubRows + (b & 3);
-
-      uint64_t packed = 0;
-      for (uint32_t k = 0; k < P.nkeys; ++k) {
-        const KeySpec &ks = P.keys[k];
-        const Slot &sl = P.slots[ks.slot];
-        uint64_t val = load_elem(seg.slab + sl.off * seg.cap + row * sl.width, sl.width, sl.sext);
-        if (ks.rollup) val = rollup_value(val, ks);
-        packed += (val - ks.lo) * ks.mul;
-      }
-      uint64_t cell;
-      if (P.hash_mode) {
-        cell = hash_cell(P, packed);
-        if (cell == kEmptyKey) {
-          atomicExch(&P.counters[1], 1ull);
-          continue;
-        }
-      } else {
-        cell = packed;
-        P.present[cell] = 1;
-      }
-      for (uint32_t m = 0; m < P.nmetrics; ++m) {
-        const MetSpec &ms = P.mets[m];
-        if (ms.op == A_DISTINCT) continue;
-        const Slot &sl = P.slots[ms.slot];
-        uint64_t val = load_elem(seg.slab + sl.off * seg.cap + row * sl.width, sl.width, sl.sext);
-        acc_update(ms.acc, cell, ms.op, val);
-      }
-      for (uint32_t d = 0; d < P.ndistinct; ++d) {
-        if (pair_pos[d] == ~0ull) continue;
-        const Slot &sl = P.slots[P.mets[P.distinct_met[d]].slot];
-        const uint32_t *vals = seg.bs_values[sl.bitset_idx];
-        const uint32_t *off = seg.bs_offsets[sl.bitset_idx];
-        uint64_t lo = row, hi = row + 1;
-        if (off != nullptr) { lo = __ldg(off + row); hi = __ldg(off + row + 1); }
-        for (uint64_t i = lo; i < hi; ++i) {
-          P.pairs[d][pair_pos[d]++] = (cell << 32) | (uint64_t)__ldg(vals + i);
-        }
-      }
-    }
-  }
-
-  // passed-row counter: one atomic per CTA
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) my_passed += __shfl_down_sync(0xffffffffu, my_passed, o);
-  __syncthreads();
-  if (lane == 0 && my_passed) atomicAdd(&s_passed, my_passed);
-  __syncthreads();
-  if (tid == 0 && s_passed) atomicAdd(&P.counters[0], s_passed);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -1,0 +1,405 @@
+// scan_kernel.cuh — the fused scan -> filter -> group-by-aggregate kernel (sm_100a).
+//
+// Reference semantics reproduced (paths relative to the viyadb/viyadb tree):
+//   segment / tuple loops   src/codegen/query/scan.cc:40-73
+//   predicate               src/codegen/query/filter.cc:206-261 (branch-free &,| over typed compares)
+//   key build + rollup      src/codegen/query/scan.cc:193-224, src/codegen/db/rollup.cc:77-95
+//   agg_map[key].Update(m)  src/codegen/query/scan.cc:228-242, src/codegen/db/store.cc:131-161
+//   count-distinct          src/util/bitset.h:26-67 (set union; cardinality at output)
+//
+// Execution model: warps are fully independent (no CTA barrier anywhere). A warp owns a chunk of
+// 512 consecutive rows of one segment: 4 sub-chunks of 128 rows, lane l holding rows l*4..l*4+3 of
+// each, so that every filter-column load is one 128-bit (u32), 64-bit (u16) or 32-bit (u8) request
+// per lane and 512/256/128 contiguous bytes per warp instruction — all 4 sub-chunk loads of a
+// column are issued back to back (MLP 4 per lane). The predicate program is interpreted once per
+// 16-row register vector with uniform control flow. Passing rows are compacted with a packed warp
+// prefix sum into a per-warp shared-memory list, then handled one row per lane: all key and metric
+// cells of a row are loaded before anything depends on them (one DRAM round trip), the group cell
+// is found (mixed-radix index, or open-addressing probe on the packed 64-bit key) and the
+// accumulators are updated with native RED/ATOM operations; count-distinct ids go straight into a
+// global (cell,id) hash set. Key/metric HBM traffic is therefore sector-granular in the
+// selectivity, filter columns are read exactly once, nothing is written but accumulators.
+#ifndef VGPU_SCAN_KERNEL_CUH_
+#define VGPU_SCAN_KERNEL_CUH_
+
+#include "kernels.cuh"
+
+namespace vgpu {
+
+constexpr int kChunkRows = 512;                 // rows per warp iteration
+constexpr int kSubChunk = kChunkRows / kSub;    // 128
+constexpr int kWarps = kThreads / 32;
+static_assert(kVec * 32 == kSubChunk, "a lane owns kVec consecutive rows of every sub-chunk");
+static_assert(kTileRows % kChunkRows == 0, "slab capacity is a whole number of chunks");
+
+// ---------------------------------------------------------------------------------------------
+// predicate interpreter: 16 rows per lane, bit (s*4+j) of the result = row s*128 + lane*4 + j
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void load_vec16(const uint8_t *col, uint32_t width, uint64_t row0,
+                                           uint32_t (&v)[kRowsPerThread], uint64_t pol) {
+  if (width == 4) {
+    uint4 q[kSub];
+#pragma unroll
+    for (int s = 0; s < kSub; ++s) q[s] = ldg_stream128(col + (row0 + (uint64_t)s * kSubChunk) * 4, pol);
+#pragma unroll
+    for (int s = 0; s < kSub; ++s) {
+      v[s * 4 + 0] = q[s].x; v[s * 4 + 1] = q[s].y; v[s * 4 + 2] = q[s].z; v[s * 4 + 3] = q[s].w;
+    }
+  } else if (width == 2) {
+    uint2 q[kSub];
+#pragma unroll
+    for (int s = 0; s < kSub; ++s) q[s] = ldg_stream64(col + (row0 + (uint64_t)s * kSubChunk) * 2, pol);
+#pragma unroll
+    for (int s = 0; s < kSub; ++s) {
+      v[s * 4 + 0] = q[s].x & 0xffffu; v[s * 4 + 1] = q[s].x >> 16;
+      v[s * 4 + 2] = q[s].y & 0xffffu; v[s * 4 + 3] = q[s].y >> 16;
+    }
+  } else {
+    uint32_t q[kSub];
+#pragma unroll
+    for (int s = 0; s < kSub; ++s) q[s] = ldg_stream32(col + (row0 + (uint64_t)s * kSubChunk), pol);
+#pragma unroll
+    for (int s = 0; s < kSub; ++s) {
+      v[s * 4 + 0] = q[s] & 0xffu; v[s * 4 + 1] = (q[s] >> 8) & 0xffu;
+      v[s * 4 + 2] = (q[s] >> 16) & 0xffu; v[s * 4 + 3] = q[s] >> 24;
+    }
+  }
+}
+
+__device__ __noinline__ bool gen_compare(uint32_t gcls, uint32_t gop, uint64_t v, uint64_t a) {
+  switch (gcls) {
+    case G_I64: {
+      long long x = (long long)v, y = (long long)a;
+      switch (gop) { case 0: return x == y; case 1: return x != y; case 2: return x < y;
+                     case 3: return x <= y; case 4: return x > y; default: return x >= y; }
+    }
+    case G_F32: {
+      float x = __uint_as_float((uint32_t)v), y = __uint_as_float((uint32_t)a);
+      switch (gop) { case 0: return x == y; case 1: return x != y; case 2: return x < y;
+                     case 3: return x <= y; case 4: return x > y; default: return x >= y; }
+    }
+    case G_F64: {
+      double x = __longlong_as_double((long long)v), y = __longlong_as_double((long long)a);
+      switch (gop) { case 0: return x == y; case 1: return x != y; case 2: return x < y;
+                     case 3: return x <= y; case 4: return x > y; default: return x >= y; }
+    }
+    default: {  // G_U64, G_CARD
+      switch (gop) { case 0: return v == a; case 1: return v != a; case 2: return v < a;
+                     case 3: return v <= a; case 4: return v > a; default: return v >= a; }
+    }
+  }
+}
+
+__device__ __forceinline__ uint64_t bitset_card(const SegDesc &seg, uint32_t bidx, uint64_t row) {
+  const uint32_t *off = seg.bs_offsets[bidx];
+  if (off == nullptr) return 1;
+  return (uint64_t)(__ldg(off + row + 1) - __ldg(off + row));
+}
+
+// row0 = first row of the lane inside the segment (chunk_row0 + lane*4)
+__device__ __forceinline__ uint32_t eval_predicate(const ScanParams &P, const SegDesc &seg,
+                                                   uint64_t row0, uint64_t pol) {
+  uint32_t stk[kStackDepth];
+#pragma unroll
+  for (int i = 0; i < kStackDepth; ++i) stk[i] = 0;
+  uint32_t v[kRowsPerThread];
+  int cached = -1;
+  for (uint32_t pc = 0; pc < P.nprog; ++pc) {
+    const PInstr &in = P.prog[pc];
+    const uint32_t kind = in.kind;
+    if (kind <= P_OR_LEAF) {
+      uint32_t m = 0;
+      const uint32_t cls = in.cls;
+      if (cls == C_TRUE) {
+        m = 0xffffu;
+      } else if (cls == C_FALSE) {
+        m = 0;
+      } else if (cls == C_GEN) {
+        const Slot &sl = P.slots[in.slot];
+#pragma unroll 1
+        for (int s = 0; s < kSub; ++s) {
+#pragma unroll 1
+          for (int j = 0; j < kVec; ++j) {
+            uint64_t row = row0 + (uint64_t)s * kSubChunk + j;
+            uint64_t val = 0;
+            if (row < seg.nrows) {  // scalar path must not read past the logical end of CSR tables
+              val = sl.bitset ? bitset_card(seg, sl.bitset_idx, row)
+                              : load_elem(seg.slab + sl.off * seg.cap + row * sl.width, sl.width, sl.sext);
+            }
+            if (gen_compare(in.gcls, in.gop, val, in.arg)) m |= 1u << (s * 4 + j);
+          }
+        }
+      } else {
+        if ((int)in.slot != cached) {
+          const Slot &sl = P.slots[in.slot];
+          load_vec16(seg.slab + sl.off * seg.cap, sl.width, row0, v, pol);
+          cached = in.slot;
+        }
+        const uint32_t a = (uint32_t)in.arg;
+        if (cls == C_EQ32) {
+#pragma unroll
+          for (int i = 0; i < kRowsPerThread; ++i) m |= (v[i] == a) ? (1u << i) : 0u;
+        } else if (cls == C_LT32) {
+          const uint32_t bias = in.bias;
+#pragma unroll
+          for (int i = 0; i < kRowsPerThread; ++i) m |= ((v[i] ^ bias) < a) ? (1u << i) : 0u;
+        } else {  // C_RNG32
+          const uint32_t bias = in.bias, len = in.arg2;
+#pragma unroll
+          for (int i = 0; i < kRowsPerThread; ++i) m |= (((v[i] ^ bias) - a) < len) ? (1u << i) : 0u;
+        }
+      }
+      if (in.neg) m ^= 0xffffu;
+      if (kind == P_PUSH) {
+#pragma unroll
+        for (int i = kStackDepth - 1; i > 0; --i) stk[i] = stk[i - 1];
+        stk[0] = m;
+      } else if (kind == P_AND_LEAF) {
+        stk[0] &= m;
+      } else {
+        stk[0] |= m;
+      }
+    } else {
+      uint32_t r = (kind == P_AND) ? (stk[1] & stk[0]) : (stk[1] | stk[0]);
+      stk[0] = r;
+#pragma unroll
+      for (int i = 1; i < kStackDepth - 1; ++i) stk[i] = stk[i + 1];
+    }
+  }
+  return stk[0];
+}
+
+// ---------------------------------------------------------------------------------------------
+// (cell,id) hash set for count-distinct: 0 = already there, 1 = inserted, 2 = probe limit hit
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ int dset_insert(uint64_t *set, uint64_t mask, uint32_t max_probe, uint64_t key) {
+  uint64_t slot = mix64(key) & mask;
+  for (uint32_t probe = 0; probe < max_probe; ++probe) {
+    // the set is kept at most half full: claim first, look second (one L2 operation per insert)
+    unsigned long long old = atomicCAS(reinterpret_cast<unsigned long long *>(set + slot),
+                                       (unsigned long long)kEmptyKey, (unsigned long long)key);
+    if (old == kEmptyKey) return 1;
+    if (old == key) return 0;
+    slot = (slot + 1) & mask;
+  }
+  return 2;
+}
+
+// ---------------------------------------------------------------------------------------------
+// the fused scan kernel
+// ---------------------------------------------------------------------------------------------
+#ifndef VGPU_MIN_CTAS
+#define VGPU_MIN_CTAS 4
+#endif
+__global__ void __launch_bounds__(kThreads, VGPU_MIN_CTAS)
+scan_filter_groupby_kernel(const __grid_constant__ ScanParams P) {
+  __shared__ uint16_t s_list[kWarps][kChunkRows];
+
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint16_t *list = s_list[warp];
+  unsigned long long my_passed = 0;
+  uint32_t ins0 = 0, ins1 = 0;  // pairs this lane added to the count-distinct sets
+  static_assert(kMaxDistinct == 2, "two insert counters");
+  const bool can_overflow = P.hash_mode || P.ndistinct;
+  const uint64_t pol = make_stream_policy((P.tune & 2u) != 0);
+  const uint64_t tpol = make_table_policy((P.tune & 4u) != 0);
+
+  const uint64_t nwarps = (uint64_t)gridDim.x * kWarps;
+  for (uint64_t chunk = (uint64_t)blockIdx.x * kWarps + warp; chunk < P.total_tiles; chunk += nwarps) {
+    const uint32_t si = (uint32_t)(chunk / P.tiles_per_seg);
+    const uint32_t ci = (uint32_t)(chunk - (uint64_t)si * P.tiles_per_seg);
+    const SegDesc &seg = P.segs[P.active[si]];
+    const uint64_t nrows = seg.nrows;
+    const uint64_t chunk_row = (uint64_t)ci * kChunkRows;
+    if (chunk_row >= nrows) continue;  // uniform per warp
+    // a full group table / distinct set makes the host grow it and run again: stop wasting time
+    if (can_overflow) {
+      unsigned long long f = 0;
+      if (lane == 0) f = *reinterpret_cast<volatile unsigned long long *>(&P.counters[1]);
+      if (__shfl_sync(0xffffffffu, f, 0) != 0ull) break;
+    }
+    const uint64_t row0 = chunk_row + (uint64_t)lane * kVec;
+
+    // software pipeline: pull the filter columns of this warp's NEXT chunk into L2 now, so that its
+    // vector loads find them there instead of paying a DRAM round trip per column
+    {
+      const uint64_t next = chunk + nwarps;
+      if (next < P.total_tiles) {
+        const uint32_t nsi = (uint32_t)(next / P.tiles_per_seg);
+        const uint32_t nci = (uint32_t)(next - (uint64_t)nsi * P.tiles_per_seg);
+        const SegDesc &nseg = P.segs[P.active[nsi]];
+        const uint64_t nrow = (uint64_t)nci * kChunkRows;
+        if (nrow < nseg.nrows) {
+          for (uint32_t f = 0; f < P.nfilter_slots; ++f) {
+            const Slot &sl = P.slots[P.filter_slots[f]];
+            if (lane * 128u < (uint32_t)kChunkRows * sl.width)
+              asm volatile("prefetch.global.L2 [%0];" ::"l"(nseg.slab + sl.off * nseg.cap + nrow * sl.width + lane * 128u));
+          }
+        }
+      }
+    }
+
+    uint32_t mask = eval_predicate(P, seg, row0, pol);
+    // rows past the end of a partially filled segment never count
+    if (chunk_row + kChunkRows > nrows) {
+#pragma unroll
+      for (int s = 0; s < kSub; ++s) {
+#pragma unroll
+        for (int j = 0; j < kVec; ++j) {
+          if (row0 + (uint64_t)s * kSubChunk + j >= nrows) mask &= ~(1u << (s * 4 + j));
+        }
+      }
+    }
+    if (__ballot_sync(0xffffffffu, mask != 0) == 0) continue;
+    my_passed += __popc(mask);
+
+    // ---- compaction: packed prefix sum of the four per-sub-chunk counts (8 bits each, <= 128) ----
+    uint32_t cnt = __popc(mask & 0xfu) | (__popc(mask & 0xf0u) << 8) | (__popc(mask & 0xf00u) << 16) |
+                   (__popc(mask & 0xf000u) << 24);
+    uint32_t incl = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += t;
+    }
+    const uint32_t tot = __shfl_sync(0xffffffffu, incl, 31);
+    // a sub-chunk total of 128 would need 8 bits + the packed adds never carry (max field 128)
+    const uint32_t excl = incl - cnt;
+    const uint32_t t0 = tot & 0xffu, t1 = (tot >> 8) & 0xffu, t2 = (tot >> 16) & 0xffu, t3 = tot >> 24;
+    const uint32_t total = t0 + t1 + t2 + t3;
+    {
+      uint32_t base = 0;
+#pragma unroll
+      for (int s = 0; s < kSub; ++s) {
+        uint32_t pos = base + ((excl >> (8 * s)) & 0xffu);
+        uint32_t nib = (mask >> (4 * s)) & 0xfu;
+#pragma unroll
+        for (int j = 0; j < kVec; ++j) {
+          if (nib & (1u << j)) list[pos++] = (uint16_t)(s * kSubChunk + lane * kVec + j);
+        }
+        base += (s == 0) ? t0 : (s == 1) ? t1 : (s == 2) ? t2 : t3;
+      }
+    }
+    __syncwarp();
+
+    // ---- aggregate: one passing row per lane ----
+    // fast path: up to 4 keys of at most 4 bytes and up to 4 metrics, staged in 12 registers
+    const bool small_plan = P.small_plan != 0;  // uniform
+    for (uint32_t i = lane; i < total; i += 32) {
+      const uint64_t row = chunk_row + list[i];
+      uint32_t kv[4];
+      uint64_t mv[4];
+      if (small_plan) {
+        // one DRAM round trip per row: every key and metric cell (or the first word a bitset cell
+        // needs) is requested before anything depends on it; branch-free and fully unrolled, so the
+        // loads issue back to back and the values stay in registers. Slab and side-table bases are
+        // 8-byte aligned, so the position of a cell inside its aligned word depends on the row only.
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          if (k < P.nkeys) {
+            const Slot &sl = P.slots[P.keys[k].slot];
+            kv[k] = gather_raw32(seg.slab + sl.off * seg.cap + row * sl.width);
+          }
+        }
+#pragma unroll
+        for (int m = 0; m < 4; ++m) {
+          if (m < P.nmetrics) {
+            const Slot &sl = P.slots[P.mets[m].slot];
+            const uint32_t *off = seg.bs_offsets[sl.bitset_idx];
+            const uint32_t *vals = seg.bs_values[sl.bitset_idx];
+            const uint8_t *fixed = seg.slab + sl.off * seg.cap + row * sl.width;
+            const uint8_t *bits = reinterpret_cast<const uint8_t *>((off == nullptr ? vals : off) + row);
+            mv[m] = gather_raw64(sl.bitset ? bits : fixed);
+          }
+        }
+      }
+      uint64_t packed = 0;
+      if (small_plan) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          if (k < P.nkeys) {
+            const KeySpec &ks = P.keys[k];
+            const Slot &sl = P.slots[ks.slot];
+            uint64_t val = ((uint64_t)(kv[k] >> ((((uint32_t)row * sl.width) & 3u) * 8u))) & sl.vmask;
+            val = (val ^ sl.signbit) - sl.signbit;
+            if (ks.rollup) val = rollup_value(val, ks);
+            packed += (val - ks.lo) * ks.mul;
+          }
+        }
+      } else {
+        for (uint32_t k = 0; k < P.nkeys; ++k) {
+          const KeySpec &ks = P.keys[k];
+          const Slot &sl = P.slots[ks.slot];
+          const uint8_t *a = seg.slab + sl.off * seg.cap + row * sl.width;
+          uint64_t val = gather_finish(gather_raw64(a), a, sl.vmask, sl.signbit);
+          if (ks.rollup) val = rollup_value(val, ks);
+          packed += (val - ks.lo) * ks.mul;
+        }
+      }
+      uint64_t cell;
+      if (P.hash_mode) {
+        cell = hash_cell(P, packed);
+        if (cell == kEmptyKey) {
+          atomicOr(&P.counters[1], 1ull);
+          continue;
+        }
+      } else {
+        cell = packed;
+        st_u8_hint(P.present + cell, 1u, tpol);
+      }
+      uint32_t dn = 0;
+      for (uint32_t m = 0; m < P.nmetrics; ++m) {
+        const MetSpec &ms = P.mets[m];
+        const Slot &sl = P.slots[ms.slot];
+        uint64_t pre;
+        if (small_plan) {
+          const uint64_t raw = m == 0 ? mv[0] : m == 1 ? mv[1] : m == 2 ? mv[2] : mv[3];
+          pre = (raw >> ((((uint32_t)row * sl.width) & 7u) * 8u)) & sl.vmask;
+          pre = (pre ^ sl.signbit) - sl.signbit;
+        } else {
+          const uint32_t *off = seg.bs_offsets[sl.bitset_idx];
+          const uint8_t *a = sl.bitset ? reinterpret_cast<const uint8_t *>((off == nullptr ? seg.bs_values[sl.bitset_idx] : off) + row)
+                                       : seg.slab + sl.off * seg.cap + row * sl.width;
+          pre = gather_finish(gather_raw64(a), a, sl.vmask, sl.signbit);
+        }
+        if (ms.op != A_DISTINCT) {
+          acc_update(ms.acc, cell, ms.op, pre, tpol);
+          continue;
+        }
+        const uint32_t *off = seg.bs_offsets[sl.bitset_idx];
+        const uint32_t *vals = seg.bs_values[sl.bitset_idx];
+        uint32_t *distinct = reinterpret_cast<uint32_t *>(ms.acc);
+        if (off == nullptr) {  // one id per row: `pre` is the id
+          int r = dset_insert(P.dset[dn], P.dset_mask[dn], P.max_probe, (cell << 32) | pre);
+          if (r == 1) { red_add_u32(distinct + cell, 1u, tpol); if (dn == 0) ++ins0; else ++ins1; }
+          else if (r == 2) atomicOr(&P.counters[1], 2ull);
+        } else {               // CSR cell: `pre` is offsets[row]
+          const uint32_t lo = (uint32_t)pre, hi = gather_u32(off + row + 1);
+          for (uint32_t q = lo; q < hi; ++q) {
+            int r = dset_insert(P.dset[dn], P.dset_mask[dn], P.max_probe, (cell << 32) | (uint64_t)gather_u32(vals + q));
+            if (r == 1) { red_add_u32(distinct + cell, 1u, tpol); if (dn == 0) ++ins0; else ++ins1; }
+            else if (r == 2) { atomicOr(&P.counters[1], 2ull); break; }
+          }
+        }
+        ++dn;
+      }
+    }
+    __syncwarp();  // the list is reused by the next chunk
+  }
+
+  // counters: one atomic per warp
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) my_passed += __shfl_down_sync(0xffffffffu, my_passed, o);
+  if (lane == 0 && my_passed) atomicAdd(&P.counters[0], my_passed);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    ins0 += __shfl_down_sync(0xffffffffu, ins0, o);
+    ins1 += __shfl_down_sync(0xffffffffu, ins1, o);
+  }
+  if (lane == 0 && ins0) atomicAdd(&P.counters[2], (unsigned long long)ins0);
+  if (lane == 0 && ins1) atomicAdd(&P.counters[3], (unsigned long long)ins1);
+}
+
+}  // namespace vgpu
+
+#endif  // VGPU_SCAN_KERNEL_CUH_

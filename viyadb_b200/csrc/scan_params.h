@@ -32,6 +32,8 @@ struct Slot {
   uint32_t sext;     // 1: sign-extend narrow values (i8/i16/i32) when widening to 64 bit
   uint32_t bitset;   // 1: BITSET column (values/offsets come from per-segment side tables)
   uint32_t bitset_idx;  // which bitset column of the table (index into SegDesc::bs_*)
+  uint64_t vmask;    // value mask of the element (0xff, 0xffff, 0xffffffff, ~0)
+  uint64_t signbit;  // sign bit of the element when sext, else 0:  (x ^ signbit) - signbit sign-extends
 };
 
 enum PKind : uint8_t { P_PUSH = 0, P_AND_LEAF = 1, P_OR_LEAF = 2, P_AND = 3, P_OR = 4 };
@@ -102,12 +104,19 @@ struct ScanParams {
   const SegDesc *segs;
   const uint32_t *active;   // indices of segments to scan
   uint32_t nactive;
-  uint32_t tiles_per_seg;
-  uint64_t total_tiles;
+  uint32_t tiles_per_seg;   // 512-row warp chunks per segment
+  uint64_t total_tiles;     // nactive * tiles_per_seg
 
   // columns
   Slot slots[kMaxSlots];
   uint32_t nslots;
+
+  uint32_t small_plan;  // <= 4 keys of <= 4 bytes and <= 4 metrics: register-staged gather path
+  uint32_t tune;  // bit 1: stream the columns with an L2 evict_first policy; bit 2: group table evict_last
+
+  // fixed-width columns the predicate reads with vector loads (prefetched one chunk ahead)
+  uint32_t nfilter_slots;
+  uint8_t filter_slots[kMaxSlots];
 
   // predicate
   uint32_t nprog;
@@ -127,10 +136,11 @@ struct ScanParams {
   MetSpec mets[kMaxMetrics];
   uint32_t ndistinct;                 // BITSET metrics selected (count-distinct)
   uint8_t distinct_met[kMaxDistinct]; // their indices into mets
-  uint64_t *pairs[kMaxDistinct];      // per distinct metric: (cell << 32 | id) append buffer
-  uint64_t pairs_cap[kMaxDistinct];
+  uint64_t *dset[kMaxDistinct];       // per distinct metric: open-addressing set of (cell << 32 | id)
+  uint64_t dset_mask[kMaxDistinct];   // capacity - 1
 
-  // counters: [0] passed rows, [1] overflow flag (hash probe limit / pair buffer), [2+d] pairs appended
+  // counters: [0] passed rows, [1] overflow flag (probe limit of the group table or of a distinct set),
+  // [2+d] pairs inserted into distinct set d
   unsigned long long *counters;
 };
 

@@ -7,7 +7,7 @@
 // There is NO CPU implementation of the scan in this library: without a CUDA device every entry
 // point fails with VGPU_ERR_CUDA.
 #include "../../include/vgpu.h"
-#include "kernels.cuh"
+#include "scan_kernel.cuh"
 
 #include <algorithm>
 #include <cfloat>
@@ -216,6 +216,9 @@ struct vgpu_ctx {
   // multi-GPU
   ncclComm_t comm = nullptr;
   int rank = 0, nranks = 1;
+  // L2 persistence (group tables are pinned in L2 while the columns stream through it)
+  uint64_t l2_persist_bytes = 0, l2_window_max = 0;
+  uint32_t tune = 0;  // VGPU_TUNE: bit 0 pin the group table in L2, bit 1 evict_first column streams
   // pinned staging for results (grown on demand)
   void *h_stage = nullptr;
   size_t h_stage_bytes = 0;
@@ -450,6 +453,12 @@ struct Planner {
     sl.sext = ci.sext;
     sl.bitset = ci.bitset;
     sl.bitset_idx = ci.bitset_idx;
+    if (ci.bitset) {  // ids / CSR offsets are uint32
+      sl.width = 4;
+      sl.sext = 0;
+    }
+    sl.vmask = sl.width == 8 ? ~0ull : ((1ull << (8 * sl.width)) - 1);
+    sl.signbit = sl.sext ? (1ull << (8 * sl.width - 1)) : 0;
     slot_cols[P.nslots] = col;
     return P.nslots++;
   }
@@ -826,8 +835,19 @@ int vgpu_init(int device, vgpu_ctx **out) {
     CUDA_CK(cudaDeviceGetDefaultMemPool(&pool, device));
     uint64_t threshold = UINT64_MAX;
     CUDA_CK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &threshold));
-    // gathers of key/metric cells for passing rows want 32-byte sectors, not 64/128-byte fetches
-    cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, 32);
+    if (const char *e = getenv("VGPU_TUNE")) ctx->tune = (uint32_t)strtoul(e, nullptr, 0);
+    // carve out the persisting part of L2 for group tables
+    if (ctx->tune & 1u) {
+      int max_persist = 0, max_window = 0;
+      cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, device);
+      cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, device);
+      if (max_persist > 0 && max_window > 0 &&
+          cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)max_persist) == cudaSuccess) {
+        ctx->l2_persist_bytes = (uint64_t)max_persist;
+        ctx->l2_window_max = (uint64_t)max_window;
+      }
+      cudaGetLastError();
+    }
     *out = ctx.release();
   });
 }
@@ -1202,6 +1222,13 @@ int vgpu_query_agg(vgpu_table *t, const vgpu_plan *plan, vgpu_result **out) {
     Planner &pl = q.planner;
     ScanParams &P = pl.P;
     pl.build_predicate();
+    for (uint32_t i = 0; i < P.nprog; ++i) {
+      const PInstr &in = P.prog[i];
+      if (in.kind > P_OR_LEAF || !(in.cls == C_EQ32 || in.cls == C_LT32 || in.cls == C_RNG32)) continue;
+      bool seen = false;
+      for (uint32_t f = 0; f < P.nfilter_slots; ++f) seen = seen || P.filter_slots[f] == in.slot;
+      if (!seen) P.filter_slots[P.nfilter_slots++] = in.slot;
+    }
 
     // ---- segment loop bookkeeping + pruning (scan.cc:42-51) ----
     for (uint32_t s = 0; s < t->segs.size(); ++s) {
@@ -1281,6 +1308,10 @@ int vgpu_query_agg(vgpu_table *t, const vgpu_plan *plan, vgpu_result **out) {
       }
     }
 
+    P.small_plan = P.nkeys <= 4 && P.nmetrics <= 4;
+    for (uint32_t k = 0; k < P.nkeys; ++k)
+      if (P.slots[P.keys[k].slot].width > 4) P.small_plan = 0;
+
     // ---- dense or hash ----
     unsigned __int128 cells128 = 1;
     bool fits64 = true;
@@ -1311,11 +1342,12 @@ int vgpu_query_agg(vgpu_table *t, const vgpu_plan *plan, vgpu_result **out) {
     // ---- work list ----
     uint64_t max_rows = 0;
     for (uint32_t s : q.active) max_rows = std::max(max_rows, t->segs[s].nrows);
-    P.tiles_per_seg = (uint32_t)std::max<uint64_t>(1, (max_rows + kTileRows - 1) / kTileRows);
+    P.tiles_per_seg = (uint32_t)std::max<uint64_t>(1, (max_rows + kChunkRows - 1) / kChunkRows);
     P.nactive = (uint32_t)q.active.size();
     P.total_tiles = (uint64_t)P.nactive * P.tiles_per_seg;
     upload_descs(t);
     P.segs = t->d_segs;
+    P.tune = ctx->tune;
 
     std::unique_ptr<vgpu_result> res(new vgpu_result());
     vgpu_result_view &view = res->view;
@@ -1336,10 +1368,12 @@ int vgpu_query_agg(vgpu_table *t, const vgpu_plan *plan, vgpu_result **out) {
       hash_cap = std::max(hash_cap, std::min(t->hash_cap_hint, want));
       if (hash_cap > 0xfffffffeull && P.ndistinct) fail(VGPU_ERR_UNSUPPORTED, "count-distinct over more than 2^32 groups");
     }
-    uint64_t pairs_cap = 0;
+    // count-distinct: (cell,id) pairs go straight into an open-addressing set; its capacity follows the
+    // high-water mark of earlier queries on this table, and grows (re-running the scan) on overflow
+    uint64_t dset_cap = 0;
     if (P.ndistinct) {
-      pairs_cap = std::max<uint64_t>(1ull << 16, q.active_rows / 16);
-      pairs_cap = std::max(pairs_cap, t->pairs_cap_hint);
+      dset_cap = pow2_ceil(std::max<uint64_t>(1ull << 16, q.active_rows / 16));
+      dset_cap = std::max(dset_cap, t->pairs_cap_hint);
     }
 
     for (int attempt = 0;; ++attempt) {
@@ -1349,33 +1383,41 @@ int vgpu_query_agg(vgpu_table *t, const vgpu_plan *plan, vgpu_result **out) {
       const uint64_t acc_cells = q.hash_mode ? hash_cap + 1 : cells;  // + the all-ones-key cell
       P.hash_mode = q.hash_mode;
       P.max_probe = 512;
+      // The group table (keys / present flags / accumulators) is ONE contiguous block so that one L2
+      // access-policy window can pin it: the column stream flowing through L2 otherwise evicts the
+      // accumulator lines and every RED/ATOM becomes a DRAM round trip (measured: +10 B/row of DRAM
+      // traffic at 5e5 groups, profiles/r1_explore_c2.txt).
+      uint64_t block_bytes = 0;
+      auto carve = [&](uint64_t bytes) { uint64_t o = block_bytes; block_bytes += round_up(bytes, 256); return o; };
+      const uint64_t o_hkeys = q.hash_mode ? carve(hash_cap * 8) : 0;
+      const uint64_t o_present = carve(q.hash_mode ? 16 : acc_cells);
+      std::vector<uint64_t> o_acc(q.accs.size());
+      for (size_t m = 0; m < q.accs.size(); ++m) o_acc[m] = carve(acc_cells * q.accs[m].acc_width);
+      uint8_t *block = scratch.alloc<uint8_t>(block_bytes);
       if (q.hash_mode) {
-        P.hkeys = scratch.alloc<uint64_t>(hash_cap);
+        P.hkeys = reinterpret_cast<uint64_t *>(block + o_hkeys);
         P.hmask = hash_cap - 1;
         fill64(stream, ctx->sm_count, P.hkeys, hash_cap, kEmptyKey);
-        P.present = scratch.alloc<uint8_t>(16);
+        P.present = block + o_present;
         CUDA_CK(cudaMemsetAsync(P.present, 0, 16, stream));
       } else {
         P.hkeys = nullptr;
         P.hmask = 0;
-        P.present = scratch.alloc<uint8_t>(acc_cells);
+        P.present = block + o_present;
         CUDA_CK(cudaMemsetAsync(P.present, 0, acc_cells, stream));
       }
       std::vector<void *> acc_ptrs(q.accs.size());
       for (size_t m = 0; m < q.accs.size(); ++m) {
         const AccInfo &a = q.accs[m];
-        if (a.acc_width == 4) {
-          acc_ptrs[m] = scratch.alloc<uint32_t>(acc_cells);
-          launches += fill32(stream, ctx->sm_count, acc_ptrs[m], acc_cells, (uint32_t)a.init);
-        } else {
-          acc_ptrs[m] = scratch.alloc<uint64_t>(acc_cells);
-          launches += fill64(stream, ctx->sm_count, acc_ptrs[m], acc_cells, a.init);
-        }
+        acc_ptrs[m] = block + o_acc[m];
+        if (a.acc_width == 4) launches += fill32(stream, ctx->sm_count, acc_ptrs[m], acc_cells, (uint32_t)a.init);
+        else launches += fill64(stream, ctx->sm_count, acc_ptrs[m], acc_cells, a.init);
         P.mets[m].acc = acc_ptrs[m];
       }
       for (uint32_t d = 0; d < P.ndistinct; ++d) {
-        P.pairs[d] = scratch.alloc<uint64_t>(pairs_cap);
-        P.pairs_cap[d] = pairs_cap;
+        P.dset[d] = scratch.alloc<uint64_t>(dset_cap);
+        P.dset_mask[d] = dset_cap - 1;
+        fill64(stream, ctx->sm_count, P.dset[d], dset_cap, kEmptyKey);
       }
       CUDA_CK(cudaMemsetAsync(ctx->d_counters, 0, 16 * sizeof(unsigned long long), stream));
       P.counters = ctx->d_counters;
@@ -1387,9 +1429,27 @@ int vgpu_query_agg(vgpu_table *t, const vgpu_plan *plan, vgpu_result **out) {
       // ---- the fused scan ----
       CUDA_CK(cudaEventRecord(ctx->ev_scan0, stream));
       if (P.total_tiles > 0) {
-        int grid = (int)std::min<uint64_t>(P.total_tiles, (uint64_t)ctx->sm_count * 4);
-        scan_filter_groupby_kernel<<<grid, kThreads, 0, stream>>>(P);
-        CUDA_CK(cudaGetLastError());
+        int grid = (int)std::min<uint64_t>((P.total_tiles + kWarps - 1) / kWarps, (uint64_t)ctx->sm_count * VGPU_MIN_CTAS);
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3(grid);
+        cfg.blockDim = dim3(kThreads);
+        cfg.stream = stream;
+        cudaLaunchAttribute attr[1];
+        cfg.attrs = attr;
+        cfg.numAttrs = 0;
+        if ((ctx->tune & 1u) && ctx->l2_persist_bytes > 0 && block_bytes > 0) {
+          // pin as much of the group table as the persisting carve-out holds
+          const uint64_t win = std::min<uint64_t>(block_bytes, ctx->l2_window_max);
+          attr[0].id = cudaLaunchAttributeAccessPolicyWindow;
+          attr[0].val.accessPolicyWindow.base_ptr = block;
+          attr[0].val.accessPolicyWindow.num_bytes = win;
+          attr[0].val.accessPolicyWindow.hitRatio =
+              (float)std::min(1.0, (double)ctx->l2_persist_bytes / (double)win);
+          attr[0].val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+          attr[0].val.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+          cfg.numAttrs = 1;
+        }
+        CUDA_CK(cudaLaunchKernelEx(&cfg, scan_filter_groupby_kernel, P));
         ++launches;
       }
       CUDA_CK(cudaEventRecord(ctx->ev_scan1, stream));
@@ -1402,39 +1462,23 @@ int vgpu_query_agg(vgpu_table *t, const vgpu_plan *plan, vgpu_result **out) {
         scan_ms_total += ms;
       }
       const uint64_t passed = ctx->h_counters[0];
-      if (ctx->h_counters[1] != 0) {  // overflow: grow and run again
-        bool grew = false;
-        for (uint32_t d = 0; d < P.ndistinct; ++d) {
-          if (ctx->h_counters[2 + d] > pairs_cap) {
-            pairs_cap = round_up(ctx->h_counters[2 + d] + ctx->h_counters[2 + d] / 8, 1024);
-            grew = true;
-          }
-        }
-        if (!grew) {
+      if (ctx->h_counters[1] != 0) {  // overflow (bit 0: group table, bit 1: a distinct set): grow, run again
+        if (ctx->h_counters[1] & 1ull) {
           if (!q.hash_mode) fail(VGPU_ERR_CUDA, "unexpected overflow flag in dense mode");
           hash_cap *= 4;
         }
+        if (ctx->h_counters[1] & 2ull) dset_cap *= 4;
         continue;
       }
       if (q.hash_mode) t->hash_cap_hint = std::max(t->hash_cap_hint, hash_cap);
-      if (P.ndistinct) t->pairs_cap_hint = std::max(t->pairs_cap_hint, pairs_cap);
-      view.passed_rows = passed;
-
-      // ---- count-distinct: dedupe the (cell,id) pairs ----
-      for (uint32_t d = 0; d < P.ndistinct; ++d) {
-        const uint64_t npairs = ctx->h_counters[2 + d];
-        uint32_t *distinct = static_cast<uint32_t *>(acc_ptrs[P.distinct_met[d]]);
-        if (npairs == 0) continue;
-        const uint64_t set_cap = pow2_ceil(std::max<uint64_t>(2 * npairs, 1024));
-        uint64_t *set = scratch.alloc<uint64_t>(set_cap);
-        fill64(stream, ctx->sm_count, set, set_cap, kEmptyKey);
-        unsigned long long *sentinel = ctx->d_counters + 8 + d;
-        distinct_insert_kernel<<<grid_for(npairs, 256, ctx->sm_count), 256, 0, stream>>>(
-            P.pairs[d], npairs, set, set_cap - 1, distinct, sentinel);
-        CUDA_CK(cudaGetLastError());
-        launches += 1;
+      if (P.ndistinct) {
+        // keep the load factor of the next run below 1/2
+        uint64_t most = 0;
+        for (uint32_t d = 0; d < P.ndistinct; ++d) most = std::max<uint64_t>(most, ctx->h_counters[2 + d]);
+        t->pairs_cap_hint = std::max(t->pairs_cap_hint, pow2_ceil(std::max<uint64_t>(2 * most, 1ull << 16)));
         if (ctx->nranks > 1) fail(VGPU_ERR_UNSUPPORTED, "multi-GPU count-distinct merge is not implemented yet");
       }
+      view.passed_rows = passed;
 
       // ---- multi-GPU: merge the partial group tables ----
       if (ctx->nranks > 1) {
