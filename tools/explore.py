@@ -27,7 +27,10 @@ if wname == "c2":
         "d0 | mn": dict(base, dimensions=["d0"], metrics=["mn"]),
         "d0 | mn,mx": dict(base, dimensions=["d0"], metrics=["mn", "mx"]),
         "d0,d1 | mn,mx": dict(base, dimensions=["d0", "d1"], metrics=["mn", "mx"]),
+        "d0,d1,d2 | mn,mx": dict(base, dimensions=["d0", "d1", "d2"], metrics=["mn", "mx"]),
+        "d1,d2,d3 | mn,mx": dict(base, dimensions=["d1", "d2", "d3"], metrics=["mn", "mx"]),
         "d0..d3 | mn,mx": dict(base, metrics=["mn", "mx"]),
+        "d0..d3 | mn": dict(base, metrics=["mn"]),
         "d0..d3 | uid": dict(base, metrics=["uid"]),
         "d0 | mn  [filter d0 only]": dict(base, dimensions=["d0"], metrics=["mn"], filter=f["filters"][0]),
         "d0 | mn  [filter n4 only]": dict(base, dimensions=["d0"], metrics=["mn"], filter={"op": "and", "filters": f["filters"][1:3]}),

@@ -35,12 +35,12 @@ static_assert(kTileRows % kChunkRows == 0, "slab capacity is a whole number of c
 // ---------------------------------------------------------------------------------------------
 // predicate interpreter: 16 rows per lane, bit (s*4+j) of the result = row s*128 + lane*4 + j
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ void load_vec16(const uint8_t *col, uint32_t width, uint64_t row0,
+__device__ __forceinline__ void load_vec16(const uint8_t *col, uint32_t width, uint32_t row0,
                                            uint32_t (&v)[kRowsPerThread], uint64_t pol) {
   if (width == 4) {
     uint4 q[kSub];
 #pragma unroll
-    for (int s = 0; s < kSub; ++s) q[s] = ldg_stream128(col + (row0 + (uint64_t)s * kSubChunk) * 4, pol);
+    for (int s = 0; s < kSub; ++s) q[s] = ldg_stream128(col + (uint64_t)(row0 + s * kSubChunk) * 4, pol);
 #pragma unroll
     for (int s = 0; s < kSub; ++s) {
       v[s * 4 + 0] = q[s].x; v[s * 4 + 1] = q[s].y; v[s * 4 + 2] = q[s].z; v[s * 4 + 3] = q[s].w;
@@ -48,7 +48,7 @@ __device__ __forceinline__ void load_vec16(const uint8_t *col, uint32_t width, u
   } else if (width == 2) {
     uint2 q[kSub];
 #pragma unroll
-    for (int s = 0; s < kSub; ++s) q[s] = ldg_stream64(col + (row0 + (uint64_t)s * kSubChunk) * 2, pol);
+    for (int s = 0; s < kSub; ++s) q[s] = ldg_stream64(col + (uint64_t)(row0 + s * kSubChunk) * 2, pol);
 #pragma unroll
     for (int s = 0; s < kSub; ++s) {
       v[s * 4 + 0] = q[s].x & 0xffffu; v[s * 4 + 1] = q[s].x >> 16;
@@ -57,7 +57,7 @@ __device__ __forceinline__ void load_vec16(const uint8_t *col, uint32_t width, u
   } else {
     uint32_t q[kSub];
 #pragma unroll
-    for (int s = 0; s < kSub; ++s) q[s] = ldg_stream32(col + (row0 + (uint64_t)s * kSubChunk), pol);
+    for (int s = 0; s < kSub; ++s) q[s] = ldg_stream32(col + (uint64_t)(row0 + s * kSubChunk), pol);
 #pragma unroll
     for (int s = 0; s < kSub; ++s) {
       v[s * 4 + 0] = q[s] & 0xffu; v[s * 4 + 1] = (q[s] >> 8) & 0xffu;
@@ -98,7 +98,7 @@ __device__ __forceinline__ uint64_t bitset_card(const SegDesc &seg, uint32_t bid
 
 // row0 = first row of the lane inside the segment (chunk_row0 + lane*4)
 __device__ __forceinline__ uint32_t eval_predicate(const ScanParams &P, const SegDesc &seg,
-                                                   uint64_t row0, uint64_t pol) {
+                                                   uint32_t row0, uint64_t pol) {
   uint32_t stk[kStackDepth];
 #pragma unroll
   for (int i = 0; i < kStackDepth; ++i) stk[i] = 0;
@@ -120,11 +120,11 @@ __device__ __forceinline__ uint32_t eval_predicate(const ScanParams &P, const Se
         for (int s = 0; s < kSub; ++s) {
 #pragma unroll 1
           for (int j = 0; j < kVec; ++j) {
-            uint64_t row = row0 + (uint64_t)s * kSubChunk + j;
+            uint32_t row = row0 + s * kSubChunk + j;
             uint64_t val = 0;
             if (row < seg.nrows) {  // scalar path must not read past the logical end of CSR tables
               val = sl.bitset ? bitset_card(seg, sl.bitset_idx, row)
-                              : load_elem(seg.slab + sl.off * seg.cap + row * sl.width, sl.width, sl.sext);
+                              : load_elem(seg.slab + sl.off * seg.cap + (uint64_t)row * sl.width, sl.width, sl.sext);
             }
             if (gen_compare(in.gcls, in.gop, val, in.arg)) m |= 1u << (s * 4 + j);
           }
@@ -138,15 +138,23 @@ __device__ __forceinline__ uint32_t eval_predicate(const ScanParams &P, const Se
         const uint32_t a = (uint32_t)in.arg;
         if (cls == C_EQ32) {
 #pragma unroll
-          for (int i = 0; i < kRowsPerThread; ++i) m |= (v[i] == a) ? (1u << i) : 0u;
+          for (int i = 0; i < kRowsPerThread; ++i) if (v[i] == a) m |= 1u << i;
         } else if (cls == C_LT32) {
           const uint32_t bias = in.bias;
 #pragma unroll
-          for (int i = 0; i < kRowsPerThread; ++i) m |= ((v[i] ^ bias) < a) ? (1u << i) : 0u;
-        } else {  // C_RNG32
+          for (int i = 0; i < kRowsPerThread; ++i) if ((v[i] ^ bias) < a) m |= 1u << i;
+        } else if (cls == C_RNG32) {
           const uint32_t bias = in.bias, len = in.arg2;
 #pragma unroll
-          for (int i = 0; i < kRowsPerThread; ++i) m |= (((v[i] ^ bias) - a) < len) ? (1u << i) : 0u;
+          for (int i = 0; i < kRowsPerThread; ++i) if (((v[i] ^ bias) - a) < len) m |= 1u << i;
+        } else {  // C_LUT64: membership in a set of codes < 64 — one shift per row whatever the list length
+          const uint64_t lut = in.arg;
+#pragma unroll
+          for (int i = 0; i < kRowsPerThread; ++i) {
+            uint64_t t;
+            asm("shr.b64 %0, %1, %2;" : "=l"(t) : "l"(lut), "r"(v[i]));  // shift amounts >= 64 give 0
+            if (t & 1ull) m |= 1u << i;
+          }
         }
       }
       if (in.neg) m ^= 0xffffu;
@@ -189,7 +197,7 @@ __device__ __forceinline__ int dset_insert(uint64_t *set, uint64_t mask, uint32_
 // the fused scan kernel
 // ---------------------------------------------------------------------------------------------
 #ifndef VGPU_MIN_CTAS
-#define VGPU_MIN_CTAS 4
+#define VGPU_MIN_CTAS 3
 #endif
 __global__ void __launch_bounds__(kThreads, VGPU_MIN_CTAS)
 scan_filter_groupby_kernel(const __grid_constant__ ScanParams P) {
@@ -197,20 +205,32 @@ scan_filter_groupby_kernel(const __grid_constant__ ScanParams P) {
 
   const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   uint16_t *list = s_list[warp];
-  unsigned long long my_passed = 0;
+  uint32_t my_passed = 0;
   uint32_t ins0 = 0, ins1 = 0;  // pairs this lane added to the count-distinct sets
   static_assert(kMaxDistinct == 2, "two insert counters");
   const bool can_overflow = P.hash_mode || P.ndistinct;
   const uint64_t pol = make_stream_policy((P.tune & 2u) != 0);
   const uint64_t tpol = make_table_policy((P.tune & 4u) != 0);
 
-  const uint64_t nwarps = (uint64_t)gridDim.x * kWarps;
-  for (uint64_t chunk = (uint64_t)blockIdx.x * kWarps + warp; chunk < P.total_tiles; chunk += nwarps) {
-    const uint32_t si = (uint32_t)(chunk / P.tiles_per_seg);
-    const uint32_t ci = (uint32_t)(chunk - (uint64_t)si * P.tiles_per_seg);
+  // chunk -> (active segment, chunk inside it), advanced incrementally: no 64-bit division per chunk
+  const uint32_t cps = P.tiles_per_seg;
+  const uint32_t nwarps = gridDim.x * kWarps;
+  const uint32_t step_seg = nwarps / cps, step_chunk = nwarps - step_seg * cps;
+  uint32_t si, ci;
+  {
+    const uint32_t first = blockIdx.x * kWarps + warp;
+    si = first / cps;
+    ci = first - si * cps;
+  }
+  while (si < P.nactive) {
+    // this warp's next chunk (also the prefetch target)
+    uint32_t nsi = si + step_seg, nci = ci + step_chunk;
+    if (nci >= cps) { nci -= cps; ++nsi; }
     const SegDesc &seg = P.segs[P.active[si]];
-    const uint64_t nrows = seg.nrows;
-    const uint64_t chunk_row = (uint64_t)ci * kChunkRows;
+    const uint32_t nrows = (uint32_t)seg.nrows;
+    const uint32_t chunk_row = ci * kChunkRows;
+    si = nsi;
+    ci = nci;
     if (chunk_row >= nrows) continue;  // uniform per warp
     // a full group table / distinct set makes the host grow it and run again: stop wasting time
     if (can_overflow) {
@@ -218,23 +238,18 @@ scan_filter_groupby_kernel(const __grid_constant__ ScanParams P) {
       if (lane == 0) f = *reinterpret_cast<volatile unsigned long long *>(&P.counters[1]);
       if (__shfl_sync(0xffffffffu, f, 0) != 0ull) break;
     }
-    const uint64_t row0 = chunk_row + (uint64_t)lane * kVec;
+    const uint32_t row0 = chunk_row + lane * kVec;
 
     // software pipeline: pull the filter columns of this warp's NEXT chunk into L2 now, so that its
     // vector loads find them there instead of paying a DRAM round trip per column
-    {
-      const uint64_t next = chunk + nwarps;
-      if (next < P.total_tiles) {
-        const uint32_t nsi = (uint32_t)(next / P.tiles_per_seg);
-        const uint32_t nci = (uint32_t)(next - (uint64_t)nsi * P.tiles_per_seg);
-        const SegDesc &nseg = P.segs[P.active[nsi]];
-        const uint64_t nrow = (uint64_t)nci * kChunkRows;
-        if (nrow < nseg.nrows) {
-          for (uint32_t f = 0; f < P.nfilter_slots; ++f) {
-            const Slot &sl = P.slots[P.filter_slots[f]];
-            if (lane * 128u < (uint32_t)kChunkRows * sl.width)
-              asm volatile("prefetch.global.L2 [%0];" ::"l"(nseg.slab + sl.off * nseg.cap + nrow * sl.width + lane * 128u));
-          }
+    if (nsi < P.nactive && !(P.tune & 32u)) {
+      const SegDesc &nseg = P.segs[P.active[nsi]];
+      const uint32_t nrow = nci * kChunkRows;
+      if (nrow < (uint32_t)nseg.nrows) {
+        for (uint32_t f = 0; f < P.nfilter_slots; ++f) {
+          const Slot &sl = P.slots[P.filter_slots[f]];
+          if (lane * 128u < (uint32_t)kChunkRows * sl.width)
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(nseg.slab + sl.off * nseg.cap + (uint64_t)nrow * sl.width + lane * 128u));
         }
       }
     }
@@ -246,7 +261,7 @@ scan_filter_groupby_kernel(const __grid_constant__ ScanParams P) {
       for (int s = 0; s < kSub; ++s) {
 #pragma unroll
         for (int j = 0; j < kVec; ++j) {
-          if (row0 + (uint64_t)s * kSubChunk + j >= nrows) mask &= ~(1u << (s * 4 + j));
+          if (row0 + s * kSubChunk + j >= nrows) mask &= ~(1u << (s * 4 + j));
         }
       }
     }
@@ -286,7 +301,7 @@ scan_filter_groupby_kernel(const __grid_constant__ ScanParams P) {
     // fast path: up to 4 keys of at most 4 bytes and up to 4 metrics, staged in 12 registers
     const bool small_plan = P.small_plan != 0;  // uniform
     for (uint32_t i = lane; i < total; i += 32) {
-      const uint64_t row = chunk_row + list[i];
+      const uint32_t row = chunk_row + list[i];
       uint32_t kv[4];
       uint64_t mv[4];
       if (small_plan) {
@@ -298,7 +313,7 @@ scan_filter_groupby_kernel(const __grid_constant__ ScanParams P) {
         for (int k = 0; k < 4; ++k) {
           if (k < P.nkeys) {
             const Slot &sl = P.slots[P.keys[k].slot];
-            kv[k] = gather_raw32(seg.slab + sl.off * seg.cap + row * sl.width);
+            kv[k] = gather_raw32(seg.slab + sl.off * seg.cap + (uint64_t)row * sl.width);
           }
         }
 #pragma unroll
@@ -307,7 +322,7 @@ scan_filter_groupby_kernel(const __grid_constant__ ScanParams P) {
             const Slot &sl = P.slots[P.mets[m].slot];
             const uint32_t *off = seg.bs_offsets[sl.bitset_idx];
             const uint32_t *vals = seg.bs_values[sl.bitset_idx];
-            const uint8_t *fixed = seg.slab + sl.off * seg.cap + row * sl.width;
+            const uint8_t *fixed = seg.slab + sl.off * seg.cap + (uint64_t)row * sl.width;
             const uint8_t *bits = reinterpret_cast<const uint8_t *>((off == nullptr ? vals : off) + row);
             mv[m] = gather_raw64(sl.bitset ? bits : fixed);
           }
@@ -330,7 +345,7 @@ scan_filter_groupby_kernel(const __grid_constant__ ScanParams P) {
         for (uint32_t k = 0; k < P.nkeys; ++k) {
           const KeySpec &ks = P.keys[k];
           const Slot &sl = P.slots[ks.slot];
-          const uint8_t *a = seg.slab + sl.off * seg.cap + row * sl.width;
+          const uint8_t *a = seg.slab + sl.off * seg.cap + (uint64_t)row * sl.width;
           uint64_t val = gather_finish(gather_raw64(a), a, sl.vmask, sl.signbit);
           if (ks.rollup) val = rollup_value(val, ks);
           packed += (val - ks.lo) * ks.mul;
@@ -345,7 +360,7 @@ scan_filter_groupby_kernel(const __grid_constant__ ScanParams P) {
         }
       } else {
         cell = packed;
-        st_u8_hint(P.present + cell, 1u, tpol);
+        if (!(P.tune & 8u)) st_u8_hint(P.present + cell, 1u, tpol);
       }
       uint32_t dn = 0;
       for (uint32_t m = 0; m < P.nmetrics; ++m) {
@@ -359,11 +374,12 @@ scan_filter_groupby_kernel(const __grid_constant__ ScanParams P) {
         } else {
           const uint32_t *off = seg.bs_offsets[sl.bitset_idx];
           const uint8_t *a = sl.bitset ? reinterpret_cast<const uint8_t *>((off == nullptr ? seg.bs_values[sl.bitset_idx] : off) + row)
-                                       : seg.slab + sl.off * seg.cap + row * sl.width;
+                                       : seg.slab + sl.off * seg.cap + (uint64_t)row * sl.width;
           pre = gather_finish(gather_raw64(a), a, sl.vmask, sl.signbit);
         }
         if (ms.op != A_DISTINCT) {
-          acc_update(ms.acc, cell, ms.op, pre, tpol);
+          if (P.tune & 16u) { if (ms.op == A_MINS32) atomicMin(reinterpret_cast<int *>(ms.acc) + cell, (int)pre); else if (ms.op == A_MAXS32) atomicMax(reinterpret_cast<int *>(ms.acc) + cell, (int)pre); }
+          else acc_update(ms.acc, cell, ms.op, pre, tpol);
           continue;
         }
         const uint32_t *off = seg.bs_offsets[sl.bitset_idx];
@@ -390,7 +406,7 @@ scan_filter_groupby_kernel(const __grid_constant__ ScanParams P) {
   // counters: one atomic per warp
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) my_passed += __shfl_down_sync(0xffffffffu, my_passed, o);
-  if (lane == 0 && my_passed) atomicAdd(&P.counters[0], my_passed);
+  if (lane == 0 && my_passed) atomicAdd(&P.counters[0], (unsigned long long)my_passed);
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
     ins0 += __shfl_down_sync(0xffffffffu, ins0, o);

@@ -20,7 +20,7 @@ constexpr int kMaxProg = 64;    // predicate program length (leaves + combinator
 constexpr int kMaxKeys = 12;
 constexpr int kMaxMetrics = 16;
 constexpr int kMaxRules = 8;
-constexpr int kStackDepth = 6;
+constexpr int kStackDepth = 5;
 constexpr int kMaxDistinct = 2;
 constexpr int kMaxBitsetCols = 4;
 
@@ -44,7 +44,8 @@ enum PCls : uint8_t {
   C_LT32 = 3,   // (zero-extended raw value ^ bias) <u arg (1/2/4-byte columns; bias maps signed types
                 // to the order-preserving unsigned domain)
   C_RNG32 = 4,  // ((raw ^ bias) - arg) <u arg2  (fused lo <= x < hi, peephole)
-  C_GEN = 5     // generic per-row path: 8-byte ints, float, double, bitset cardinality
+  C_GEN = 5,    // generic per-row path: 8-byte ints, float, double, bitset cardinality
+  C_LUT64 = 6   // bit `raw` of the 64-bit mask in arg (IN / NOT IN lists whose values are all < 64)
 };
 // generic compare element classes
 enum GCls : uint8_t { G_I64 = 0, G_U64 = 1, G_F32 = 2, G_F64 = 3, G_CARD = 4 };

@@ -204,6 +204,47 @@ void nccl_load() {
 // ---------------------------------------------------------------------------------------------
 // objects behind the opaque handles
 // ---------------------------------------------------------------------------------------------
+// Pinned host blocks behind vgpu_result. Reference-counted: a result may be freed after
+// vgpu_shutdown() of its context.
+struct PinnedPool {
+  std::mutex mu;
+  std::vector<std::pair<void *, size_t>> free_blocks;
+  ~PinnedPool() {
+    for (auto &b : free_blocks) cudaFreeHost(b.first);
+  }
+  std::pair<void *, size_t> acquire(size_t bytes) {
+    {
+      std::lock_guard<std::mutex> lk(mu);
+      size_t best = free_blocks.size();
+      for (size_t i = 0; i < free_blocks.size(); ++i)
+        if (free_blocks[i].second >= bytes && (best == free_blocks.size() || free_blocks[i].second < free_blocks[best].second))
+          best = i;
+      if (best != free_blocks.size()) {
+        auto blk = free_blocks[best];
+        free_blocks.erase(free_blocks.begin() + best);
+        return blk;
+      }
+    }
+    size_t cap = 1 << 16;
+    while (cap < bytes) cap <<= 1;
+    void *p = nullptr;
+    if (cudaMallocHost(&p, cap) != cudaSuccess) throw std::bad_alloc();
+    return {p, cap};
+  }
+  void release(std::pair<void *, size_t> blk) {
+    std::lock_guard<std::mutex> lk(mu);
+    if (free_blocks.size() >= 8) {  // keep the pool small: drop the smallest block
+      size_t worst = 0;
+      for (size_t i = 1; i < free_blocks.size(); ++i)
+        if (free_blocks[i].second < free_blocks[worst].second) worst = i;
+      if (free_blocks[worst].second < blk.second) std::swap(free_blocks[worst], blk);
+      cudaFreeHost(blk.first);
+      return;
+    }
+    free_blocks.push_back(blk);
+  }
+};
+
 struct vgpu_ctx {
   int device = 0;
   int sm_count = 148;
@@ -219,9 +260,10 @@ struct vgpu_ctx {
   // L2 persistence (group tables are pinned in L2 while the columns stream through it)
   uint64_t l2_persist_bytes = 0, l2_window_max = 0;
   uint32_t tune = 0;  // VGPU_TUNE: bit 0 pin the group table in L2, bit 1 evict_first column streams
-  // pinned staging for results (grown on demand)
-  void *h_stage = nullptr;
-  size_t h_stage_bytes = 0;
+  // pool of pinned host blocks that back vgpu_result (D2H at full PCIe speed, no per-query
+  // cudaMallocHost); shared with the results so that they may outlive the context
+  std::shared_ptr<PinnedPool> pool = std::make_shared<PinnedPool>();
+  bool trace = false;
 };
 
 namespace {
@@ -266,10 +308,13 @@ struct vgpu_table {
 };
 
 struct vgpu_result {
-  std::vector<std::vector<uint8_t>> key_data, acc_data;
-  std::vector<uint64_t> hidden;
+  std::shared_ptr<PinnedPool> pool;
+  std::pair<void *, size_t> block{nullptr, 0};  // pinned host memory holding every array of the view
   std::vector<const void *> key_ptrs, acc_ptrs;
   vgpu_result_view view{};
+  ~vgpu_result() {
+    if (block.first && pool) pool->release(block);
+  }
 };
 
 namespace {
@@ -603,6 +648,30 @@ struct Planner {
       case VGPU_NODE_IN: {
         // IN = OR chain of ==, NOT IN = AND chain of != (filter.cc:222-241)
         const bool eq = n.op != 0;
+        // small dictionary / numeric domains: one 64-bit lookup mask instead of a compare chain
+        if (n.n >= 2 && is_small_int_col(n.col) && !type_signed(t->cols[n.col].type)) {
+          const ColInfo &ci = t->cols[n.col];
+          uint64_t lut = 0;
+          bool ok = true;
+          for (uint32_t i = 0; i < n.n && ok; ++i) {
+            uint64_t a = widen_arg(plan->args[n.arg + i], ci.type);
+            // a literal that is missing from the dictionary decodes to UINTn_MAX: it matches no stored
+            // code (dictionary.cc:46-75 hands out codes from 0 upwards), so it adds nothing to the mask
+            if (ci.kind == VGPU_DIM_STRING && a == type_max_value(ci.type)) continue;
+            if (a >= 64) ok = false; else lut |= 1ull << a;
+          }
+          if (ok) {
+            PInstr in{};
+            in.kind = leaf_kind(mode);
+            if (mode == 0) push_depth();
+            in.cls = C_LUT64;
+            in.slot = (uint8_t)slot_of(n.col);
+            in.arg = lut;
+            in.neg = !eq;
+            emit(in);
+            break;
+          }
+        }
         const int chain = eq ? 2 : 1;
         const uint32_t op = eq ? VGPU_OP_EQ : VGPU_OP_NE;
         if (mode == chain) {
@@ -836,6 +905,7 @@ int vgpu_init(int device, vgpu_ctx **out) {
     uint64_t threshold = UINT64_MAX;
     CUDA_CK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &threshold));
     if (const char *e = getenv("VGPU_TUNE")) ctx->tune = (uint32_t)strtoul(e, nullptr, 0);
+    ctx->trace = getenv("VGPU_TRACE") != nullptr;
     // carve out the persisting part of L2 for group tables
     if (ctx->tune & 1u) {
       int max_persist = 0, max_window = 0;
@@ -873,7 +943,6 @@ void vgpu_shutdown(vgpu_ctx *ctx) {
   if (ctx->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(ctx->comm);
   if (ctx->d_counters) cudaFree(ctx->d_counters);
   if (ctx->h_counters) cudaFreeHost(ctx->h_counters);
-  if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
   if (ctx->ev_begin) cudaEventDestroy(ctx->ev_begin);
   if (ctx->ev_scan0) cudaEventDestroy(ctx->ev_scan0);
   if (ctx->ev_scan1) cudaEventDestroy(ctx->ev_scan1);
@@ -892,6 +961,7 @@ int vgpu_table_create(vgpu_ctx *ctx, const vgpu_schema *schema, vgpu_table **out
     if (schema->ncols == 0 || schema->ndims > schema->ncols || !schema->cols)
       fail(VGPU_ERR_INVALID, "malformed schema");
     if (schema->segment_size == 0) fail(VGPU_ERR_INVALID, "segment_size must be positive");
+    if (schema->segment_size > (1ull << 31)) fail(VGPU_ERR_UNSUPPORTED, "segment_size above 2^31 rows");
     std::unique_ptr<vgpu_table> t(new vgpu_table());
     t->ctx = ctx;
     t->ndims = schema->ndims;
@@ -1224,7 +1294,7 @@ int vgpu_query_agg(vgpu_table *t, const vgpu_plan *plan, vgpu_result **out) {
     pl.build_predicate();
     for (uint32_t i = 0; i < P.nprog; ++i) {
       const PInstr &in = P.prog[i];
-      if (in.kind > P_OR_LEAF || !(in.cls == C_EQ32 || in.cls == C_LT32 || in.cls == C_RNG32)) continue;
+      if (in.kind > P_OR_LEAF || !(in.cls == C_EQ32 || in.cls == C_LT32 || in.cls == C_RNG32 || in.cls == C_LUT64)) continue;
       bool seen = false;
       for (uint32_t f = 0; f < P.nfilter_slots; ++f) seen = seen || P.filter_slots[f] == in.slot;
       if (!seen) P.filter_slots[P.nfilter_slots++] = in.slot;
@@ -1537,25 +1607,32 @@ int vgpu_query_agg(vgpu_table *t, const vgpu_plan *plan, vgpu_result **out) {
       const uint64_t ngroups = bound > 0 ? ctx->h_counters[12] : 0;
       if (ngroups > bound) fail(VGPU_ERR_CUDA, "group extraction overflow");
 
-      // ---- results to the host ----
-      res->key_data.resize(plan->nkeys);
-      res->acc_data.resize(plan->nmetrics);
-      for (uint32_t k = 0; k < plan->nkeys; ++k) {
-        const ColInfo &ci = t->cols[plan->keys[k].col];
-        res->key_data[k].resize(std::max<uint64_t>(ngroups * ci.width, 1));
-        if (ngroups)
-          CUDA_CK(cudaMemcpyAsync(res->key_data[k].data(), d_keys[k], ngroups * ci.width, cudaMemcpyDeviceToHost, stream));
-      }
-      for (uint32_t m = 0; m < plan->nmetrics; ++m) {
-        res->acc_data[m].resize(std::max<uint64_t>(ngroups * q.accs[m].out_width, 1));
-        if (ngroups)
-          CUDA_CK(cudaMemcpyAsync(res->acc_data[m].data(), d_accs[m], ngroups * q.accs[m].out_width,
-                                  cudaMemcpyDeviceToHost, stream));
-      }
-      if (plan->need_hidden_count) {
-        res->hidden.resize(std::max<uint64_t>(ngroups, 1));
-        if (ngroups)
-          CUDA_CK(cudaMemcpyAsync(res->hidden.data(), d_accs[plan->nmetrics], ngroups * 8, cudaMemcpyDeviceToHost, stream));
+      // ---- results to the host: one pinned block, arrays 64-byte aligned ----
+      {
+        uint64_t bytes = 0;
+        std::vector<uint64_t> off_k(plan->nkeys), off_m(plan->nmetrics);
+        uint64_t off_h = 0;
+        auto place = [&](uint64_t n) { uint64_t o = bytes; bytes += round_up(std::max<uint64_t>(n, 1), 64); return o; };
+        for (uint32_t k = 0; k < plan->nkeys; ++k) off_k[k] = place(ngroups * t->cols[plan->keys[k].col].width);
+        for (uint32_t m = 0; m < plan->nmetrics; ++m) off_m[m] = place(ngroups * q.accs[m].out_width);
+        if (plan->need_hidden_count) off_h = place(ngroups * 8);
+        res->pool = ctx->pool;
+        res->block = ctx->pool->acquire(bytes);
+        uint8_t *hb = static_cast<uint8_t *>(res->block.first);
+        for (uint32_t k = 0; k < plan->nkeys; ++k) {
+          const uint64_t n = ngroups * t->cols[plan->keys[k].col].width;
+          if (n) CUDA_CK(cudaMemcpyAsync(hb + off_k[k], d_keys[k], n, cudaMemcpyDeviceToHost, stream));
+          res->key_ptrs.push_back(hb + off_k[k]);
+        }
+        for (uint32_t m = 0; m < plan->nmetrics; ++m) {
+          const uint64_t n = ngroups * q.accs[m].out_width;
+          if (n) CUDA_CK(cudaMemcpyAsync(hb + off_m[m], d_accs[m], n, cudaMemcpyDeviceToHost, stream));
+          res->acc_ptrs.push_back(hb + off_m[m]);
+        }
+        if (plan->need_hidden_count) {
+          if (ngroups) CUDA_CK(cudaMemcpyAsync(hb + off_h, d_accs[plan->nmetrics], ngroups * 8, cudaMemcpyDeviceToHost, stream));
+          view.hidden_count = reinterpret_cast<const uint64_t *>(hb + off_h);
+        }
       }
       CUDA_CK(cudaEventRecord(ctx->ev_end, stream));
       CUDA_CK(cudaStreamSynchronize(stream));
@@ -1571,11 +1648,8 @@ int vgpu_query_agg(vgpu_table *t, const vgpu_plan *plan, vgpu_result **out) {
       break;
     }
 
-    for (auto &v : res->key_data) res->key_ptrs.push_back(v.data());
-    for (auto &v : res->acc_data) res->acc_ptrs.push_back(v.data());
     view.keys = res->key_ptrs.empty() ? nullptr : res->key_ptrs.data();
     view.accs = res->acc_ptrs.empty() ? nullptr : res->acc_ptrs.data();
-    view.hidden_count = plan->need_hidden_count ? res->hidden.data() : nullptr;
     *out = res.release();
   });
 }

@@ -374,6 +374,18 @@ def _cmp_rows(sort_cols):
 # ------------------------------------------------------------------------------------------------
 # the runner
 # ------------------------------------------------------------------------------------------------
+class _ResultOwner:
+    """Keeps a vgpu_result alive while numpy views of its (library-owned, pinned) arrays exist."""
+
+    def __init__(self, lib, handle):
+        self._lib, self._handle = lib, handle
+
+    def __del__(self):
+        if self._handle is not None:
+            self._lib.vgpu_result_free(self._handle)
+            self._handle = None
+
+
 class GpuQueryRunner:
     """Counterpart of query::QueryRunner (src/query/runner.cc:45-64): visit_aggregate packs the
     filter arguments exactly like the reference, lowers the query to a vgpu_plan, calls
@@ -449,30 +461,34 @@ class GpuQueryRunner:
         t0 = _time.perf_counter()
         N.check(lib.vgpu_query_agg(t.handle, C.byref(plan), C.byref(res)))
         self.stats.scan_time = _time.perf_counter() - t0
-        try:
-            view = N.ResultView()
-            N.check(lib.vgpu_result_get(res, C.byref(view)))
-            n = view.ngroups
-            keys, accs = [], []
-            for i, dc in enumerate(query.dimension_cols):
-                dt = np.dtype(N.NP_DTYPES[dc.dim.type])
-                buf = (C.c_char * (n * dt.itemsize)).from_address(view.keys[i]) if n else b""
-                keys.append(np.frombuffer(buf, dtype=dt, count=n).copy())
-            for i, mc in enumerate(query.metric_cols):
-                dt = np.dtype("<u8") if mc.metric.agg == N.AGG_BITSET else np.dtype(N.NP_DTYPES[mc.metric.type])
-                buf = (C.c_char * (n * dt.itemsize)).from_address(view.accs[i]) if n else b""
-                accs.append(np.frombuffer(buf, dtype=dt, count=n).copy())
-            hidden = None
-            if plan.need_hidden_count:
-                hidden = np.ctypeslib.as_array(view.hidden_count, shape=(n,)).copy() if n else np.zeros(0, "<u8")
-            s = self.stats
-            s.scanned_recs, s.scanned_segments = view.scanned_recs, view.scanned_segments
-            s.aggregated_recs, s.passed_rows = view.aggregated_recs, view.passed_rows
-            s.gpu_ms, s.kernel_scan_ms, s.launches = view.gpu_ms, view.scan_ms, view.launches
-            s.table_mode, s.table_cells = view.table_mode, view.table_cells
-        finally:
-            lib.vgpu_result_free(res)
-        return {"ngroups": n, "keys": keys, "accs": accs, "hidden_count": hidden}
+        owner = _ResultOwner(lib, res)   # the arrays below are zero-copy views of library-owned pinned memory
+        view = N.ResultView()
+        N.check(lib.vgpu_result_get(res, C.byref(view)))
+        n = view.ngroups
+        keys, accs = [], []
+
+        def wrap(addr, dt):
+            if not n:
+                return np.zeros(0, dt)
+            buf = (C.c_char * (n * dt.itemsize)).from_address(addr)
+            arr = np.frombuffer(buf, dtype=dt, count=n)
+            arr.flags.writeable = False
+            return arr
+
+        for i, dc in enumerate(query.dimension_cols):
+            keys.append(wrap(view.keys[i], np.dtype(N.NP_DTYPES[dc.dim.type])))
+        for i, mc in enumerate(query.metric_cols):
+            dt = np.dtype("<u8") if mc.metric.agg == N.AGG_BITSET else np.dtype(N.NP_DTYPES[mc.metric.type])
+            accs.append(wrap(view.accs[i], dt))
+        hidden = None
+        if plan.need_hidden_count:
+            hidden = wrap(C.cast(view.hidden_count, C.c_void_p).value, np.dtype("<u8"))
+        s = self.stats
+        s.scanned_recs, s.scanned_segments = view.scanned_recs, view.scanned_segments
+        s.aggregated_recs, s.passed_rows = view.aggregated_recs, view.passed_rows
+        s.gpu_ms, s.kernel_scan_ms, s.launches = view.gpu_ms, view.scan_ms, view.launches
+        s.table_mode, s.table_cells = view.table_mode, view.table_cells
+        return {"ngroups": n, "keys": keys, "accs": accs, "hidden_count": hidden, "_owner": owner}
 
     def visit_aggregate(self, query):
         t_begin = _time.perf_counter()
