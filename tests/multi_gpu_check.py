@@ -1,0 +1,77 @@
+#!/usr/bin/env python
+"""Run under torchrun on N GPUs: every workload's N-GPU result (segments sharded round-robin, NCCL
+merge) must equal the single-GPU result over the union of all segments, bit for bit, on every rank.
+Prints MULTI_GPU_OK on rank 0."""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import numpy as np
+import torch
+import torch.distributed as dist
+
+import bench
+import viyadb_b200 as v
+from viyadb_b200 import dist as vdist
+from viyadb_b200.query import GpuQueryRunner, QueryFactory
+
+SEG = 50_000
+
+
+def run(db, w, q, flags=0):
+    query = QueryFactory.create(q, db)
+    r = GpuQueryRunner(db, v.MemoryRowOutput(), now=bench.NOW, flags=flags)
+    g = r.run_plan(query, r.build_plan(query))
+    keys = [np.array(k) for k in g["keys"]]
+    accs = [np.array(a) for a in g["accs"]]
+    order = np.lexsort(tuple(reversed(keys))) if keys else np.arange(g["ngroups"])
+    return [k[order] for k in keys], [a[order] for a in accs], r.stats
+
+
+def main():
+    rank, world, local = vdist.world()
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    nseg_global = 3 * world + 1          # ragged on purpose: ranks own different numbers of segments
+    for wname, flags in (("c1", 0), ("c2", 2), ("c3", 0), ("c4", 0), ("c1", 1), ("c3", 1)):
+        w = bench.WORKLOADS[wname]
+        conf = dict(w["table"], segment_size=SEG)
+        # sharded database, attached to the communicator
+        db = v.Database({"tables": [conf]}, device=local)
+        vdist.init_database_comm(db, dist)
+        t = db.get_table("events")
+        for ls, gs in enumerate(vdist.segments_for_rank(nseg_global, rank, world)):
+            n = SEG if gs < nseg_global - 1 else SEG // 3
+            t.generate_segment(ls, n, w["gens"], seed=42, row_offset=gs * SEG)
+        for d, g, prefix in zip(t.dimensions, w["gens"], w["prefix"]):
+            if d.dict is not None:
+                for k in range(1, min(g[0] + g[1], 1001)):
+                    d.dict.encode(f"{prefix}{k}")
+        # for the IN/eq literals to exist in the dictionaries of c1/c2 the prefixes above suffice
+        keys, accs, stats = run(db, w, w["query"], flags)
+        # reference: one GPU, all segments, no communicator
+        db1 = v.Database({"tables": [conf]}, device=local)
+        t1 = db1.get_table("events")
+        for gs in range(nseg_global):
+            n = SEG if gs < nseg_global - 1 else SEG // 3
+            t1.generate_segment(gs, n, w["gens"], seed=42, row_offset=gs * SEG)
+        for d, d1 in zip(t.dimensions, t1.dimensions):
+            d1.dict = d.dict
+        keys1, accs1, stats1 = run(db1, w, w["query"], flags)
+        assert len(keys) == len(keys1) and all(np.array_equal(a, b) for a, b in zip(keys, keys1)), (wname, "keys differ")
+        assert all(np.array_equal(a, b) for a, b in zip(accs, accs1)), (wname, "aggregates differ")
+        assert stats.aggregated_recs == stats1.aggregated_recs
+        if rank == 0:
+            print(f"{wname} flags={flags}: {stats.aggregated_recs} groups identical on {world} GPUs "
+                  f"(table mode {stats.table_mode})", flush=True)
+        db.close()
+        db1.close()
+    dist.barrier()
+    if rank == 0:
+        print("MULTI_GPU_OK", flush=True)
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -318,6 +318,129 @@ distinct_insert_kernel(const uint64_t *__restrict__ pairs, uint64_t npairs, uint
 }
 
 // ---------------------------------------------------------------------------------------------
+// multi-GPU exchange: scatter the live entries of an open-addressing u64 table (and the accumulator
+// cells that go with them) into one bucket per owner rank. owner = mix64(key >> owner_shift) % nparts
+// (count-distinct pairs: owner of the CELL, so that all ids of a group meet on one rank; group
+// records: owner of the packed key). Bucket o occupies [o * bucket_cap, (o+1) * bucket_cap).
+// CTA-level histogram in shared memory: one global atomic per owner per tile.
+// ---------------------------------------------------------------------------------------------
+constexpr int kMaxParts = 16;
+constexpr int kPartPerThread = 8;
+struct PartitionParams {
+  const uint64_t *keys;   // table keys, kEmptyKey = free slot
+  uint64_t nslots;
+  uint64_t sentinel_slot; // slot index that stands for the all-ones key when sentinel_present points at 1 (hash group tables), else ~0
+  const uint8_t *sentinel_present;
+  uint32_t nparts;
+  uint32_t owner_shift;
+  uint64_t bucket_cap;
+  unsigned long long *cursors;  // [nparts], zeroed; ends up holding the bucket sizes
+  uint64_t *out_keys;
+  uint32_t npay;
+  uint32_t pay_width[kMaxMetrics + 1];
+  const void *pay_src[kMaxMetrics + 1];  // indexed by slot
+  void *pay_dst[kMaxMetrics + 1];        // indexed by bucket position
+};
+
+__device__ __forceinline__ uint32_t owner_of(uint64_t key, uint32_t shift, uint32_t nparts) {
+  return (uint32_t)((mix64(key >> shift) >> 17) % nparts);
+}
+
+__global__ void __launch_bounds__(256) partition_table_kernel(const __grid_constant__ PartitionParams A) {
+  __shared__ uint32_t s_cnt[kMaxParts];
+  __shared__ unsigned long long s_base[kMaxParts];
+  const uint64_t tile = (uint64_t)blockDim.x * kPartPerThread;
+  const uint64_t total = A.nslots + (A.sentinel_slot != ~0ull ? 1 : 0);
+  const uint64_t ntiles = (total + tile - 1) / tile;
+  for (uint64_t ti = blockIdx.x; ti < ntiles; ti += gridDim.x) {
+    if (threadIdx.x < kMaxParts) s_cnt[threadIdx.x] = 0;
+    __syncthreads();
+    uint64_t key[kPartPerThread];
+    uint64_t slot[kPartPerThread];
+    uint32_t own[kPartPerThread], pos[kPartPerThread];
+#pragma unroll
+    for (int j = 0; j < kPartPerThread; ++j) {
+      const uint64_t i = ti * tile + (uint64_t)j * blockDim.x + threadIdx.x;
+      own[j] = 0xffffffffu;
+      if (i < A.nslots) {
+        key[j] = A.keys[i];
+        slot[j] = i;
+        if (key[j] != kEmptyKey) own[j] = owner_of(key[j], A.owner_shift, A.nparts);
+      } else if (i == A.nslots && A.sentinel_slot != ~0ull && A.sentinel_present[0]) {
+        key[j] = kEmptyKey;  // the all-ones key lives in its dedicated cell
+        slot[j] = A.sentinel_slot;
+        own[j] = owner_of(kEmptyKey, A.owner_shift, A.nparts);
+      }
+      if (own[j] != 0xffffffffu) pos[j] = atomicAdd(&s_cnt[own[j]], 1u);
+    }
+    __syncthreads();
+    if (threadIdx.x < A.nparts && s_cnt[threadIdx.x])
+      s_base[threadIdx.x] = atomicAdd(&A.cursors[threadIdx.x], (unsigned long long)s_cnt[threadIdx.x]);
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < kPartPerThread; ++j) {
+      if (own[j] == 0xffffffffu) continue;
+      const uint64_t p = (uint64_t)own[j] * A.bucket_cap + s_base[own[j]] + pos[j];
+      A.out_keys[p] = key[j];
+      for (uint32_t m = 0; m < A.npay; ++m) {
+        if (A.pay_width[m] == 4)
+          reinterpret_cast<uint32_t *>(A.pay_dst[m])[p] = reinterpret_cast<const uint32_t *>(A.pay_src[m])[slot[j]];
+        else
+          reinterpret_cast<uint64_t *>(A.pay_dst[m])[p] = reinterpret_cast<const uint64_t *>(A.pay_src[m])[slot[j]];
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// Merge exchanged group records (packed key + one partial accumulator per metric) into a hash group
+// table with the same commutative Update() the scan uses (store.cc:131-161).
+struct MergeParams {
+  const uint64_t *keys;
+  uint64_t n;
+  uint32_t nmets;
+  uint32_t ops[kMaxMetrics + 1];
+  uint32_t widths[kMaxMetrics + 1];
+  const void *src[kMaxMetrics + 1];
+  void *acc[kMaxMetrics + 1];
+  uint64_t *hkeys;
+  uint64_t hmask;
+  uint8_t *present;
+  uint32_t max_probe;
+  unsigned long long *overflow;
+};
+
+__global__ void __launch_bounds__(256) merge_records_kernel(const __grid_constant__ MergeParams M) {
+  const uint64_t pol = make_table_policy(false);
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < M.n;
+       i += (uint64_t)gridDim.x * blockDim.x) {
+    const uint64_t key = M.keys[i];
+    uint64_t cell;
+    if (key == kEmptyKey) {
+      M.present[0] = 1;
+      cell = M.hmask + 1;
+    } else {
+      uint64_t slot = mix64(key) & M.hmask;
+      cell = kEmptyKey;
+      for (uint32_t probe = 0; probe < M.max_probe; ++probe) {
+        unsigned long long old = atomicCAS(reinterpret_cast<unsigned long long *>(M.hkeys + slot),
+                                           (unsigned long long)kEmptyKey, (unsigned long long)key);
+        if (old == kEmptyKey || old == key) { cell = slot; break; }
+        slot = (slot + 1) & M.hmask;
+      }
+      if (cell == kEmptyKey) { atomicExch(M.overflow, 1ull); continue; }
+    }
+    for (uint32_t m = 0; m < M.nmets; ++m) {
+      uint64_t v = M.widths[m] == 4 ? (uint64_t)reinterpret_cast<const uint32_t *>(M.src[m])[i]
+                                    : reinterpret_cast<const uint64_t *>(M.src[m])[i];
+      if (M.ops[m] == A_ADD32 || M.ops[m] == A_MINS32 || M.ops[m] == A_MAXS32)
+        v = (uint64_t)(int64_t)(int32_t)(uint32_t)v;
+      acc_update(M.acc[m], cell, M.ops[m], v, pol);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // group extraction: present cells -> dense SoA result
 // ---------------------------------------------------------------------------------------------
 struct ExtractKey {

@@ -162,6 +162,8 @@ struct NcclApi {
                             cudaStream_t) = nullptr;
   ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t,
                             cudaStream_t) = nullptr;
+  ncclResult_t (*Send)(const void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*GroupStart)() = nullptr;
   ncclResult_t (*GroupEnd)() = nullptr;
   const char *(*GetErrorString)(ncclResult_t) = nullptr;
@@ -186,6 +188,8 @@ void nccl_load() {
   NSYM(AllReduce, "ncclAllReduce");
   NSYM(Broadcast, "ncclBroadcast");
   NSYM(AllGather, "ncclAllGather");
+  NSYM(Send, "ncclSend");
+  NSYM(Recv, "ncclRecv");
   NSYM(GroupStart, "ncclGroupStart");
   NSYM(GroupEnd, "ncclGroupEnd");
   NSYM(GetErrorString, "ncclGetErrorString");
@@ -253,6 +257,7 @@ struct vgpu_ctx {
   cudaEvent_t ev_begin = nullptr, ev_scan0 = nullptr, ev_scan1 = nullptr, ev_end = nullptr;
   unsigned long long *d_counters = nullptr;  // 16 x u64
   unsigned long long *h_counters = nullptr;  // pinned
+  uint64_t *d_plan = nullptr;                // 64 x u64: plan-time agreement between ranks
   std::mutex mu;                             // one query / put at a time per context
   // multi-GPU
   ncclComm_t comm = nullptr;
@@ -899,6 +904,7 @@ int vgpu_init(int device, vgpu_ctx **out) {
     CUDA_CK(cudaEventCreate(&ctx->ev_end));
     CUDA_CK(cudaMalloc(&ctx->d_counters, 16 * sizeof(unsigned long long)));
     CUDA_CK(cudaMallocHost(&ctx->h_counters, 16 * sizeof(unsigned long long)));
+    CUDA_CK(cudaMalloc(&ctx->d_plan, 64 * sizeof(uint64_t)));
     // keep freed scratch in the pool: repeated queries never go back to the driver
     cudaMemPool_t pool;
     CUDA_CK(cudaDeviceGetDefaultMemPool(&pool, device));
@@ -942,6 +948,7 @@ void vgpu_shutdown(vgpu_ctx *ctx) {
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   if (ctx->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(ctx->comm);
   if (ctx->d_counters) cudaFree(ctx->d_counters);
+  if (ctx->d_plan) cudaFree(ctx->d_plan);
   if (ctx->h_counters) cudaFreeHost(ctx->h_counters);
   if (ctx->ev_begin) cudaEventDestroy(ctx->ev_begin);
   if (ctx->ev_scan0) cudaEventDestroy(ctx->ev_scan0);
@@ -1276,6 +1283,262 @@ void nccl_merge_dense(vgpu_ctx *ctx, QueryRun &q, ScanParams &P, std::vector<voi
   NCCL_CK(g_nccl.GroupEnd());
 }
 
+// bucket sizes of every rank: matrix[r * G + o] = entries rank r holds for owner o
+std::vector<uint64_t> exchange_counts(vgpu_ctx *ctx, unsigned long long *d_cursors, Scratch &scratch) {
+  const int G = ctx->nranks;
+  uint64_t *d_matrix = scratch.alloc<uint64_t>((uint64_t)G * G);
+  NCCL_CK(g_nccl.AllGather(d_cursors, d_matrix, G, ncclUint64, ctx->comm, ctx->stream));
+  std::vector<uint64_t> matrix((size_t)G * G);
+  CUDA_CK(cudaMemcpyAsync(matrix.data(), d_matrix, matrix.size() * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_CK(cudaStreamSynchronize(ctx->stream));
+  return matrix;
+}
+
+// all-to-all of one bucketed array: rank `me` sends bucket o (matrix[me][o] elements) to rank o and
+// receives matrix[r][me] elements from every r into recv + recv_off[r]. Must be called inside a group.
+void exchange_array(vgpu_ctx *ctx, const void *send, uint64_t bucket_cap, uint32_t elem, void *recv,
+                    const std::vector<uint64_t> &matrix, const std::vector<uint64_t> &recv_off) {
+  const int G = ctx->nranks, me = ctx->rank;
+  const uint8_t *sb = static_cast<const uint8_t *>(send);
+  uint8_t *rb = static_cast<uint8_t *>(recv);
+  for (int r = 0; r < G; ++r) {
+    const uint64_t ns = matrix[(size_t)me * G + r], nr = matrix[(size_t)r * G + me];
+    if (r == me) {
+      if (ns) CUDA_CK(cudaMemcpyAsync(rb + recv_off[r] * elem, sb + (uint64_t)r * bucket_cap * elem, ns * elem,
+                                      cudaMemcpyDeviceToDevice, ctx->stream));
+      continue;
+    }
+    if (ns) NCCL_CK(g_nccl.Send(sb + (uint64_t)r * bucket_cap * elem, ns * elem, ncclUint8, r, ctx->comm, ctx->stream));
+    if (nr) NCCL_CK(g_nccl.Recv(rb + recv_off[r] * elem, nr * elem, ncclUint8, r, ctx->comm, ctx->stream));
+  }
+}
+
+// count-distinct across ranks (dense group table): the (cell,id) sets of all ranks are united. Every
+// pair travels to the rank that owns its cell, owners dedupe and count, one sum-allreduce of the
+// per-cell counts gives every rank the full answer. Per-rank work stays constant as ranks are added.
+void nccl_merge_distinct(vgpu_ctx *ctx, const uint64_t *dset, uint64_t dset_cap, uint64_t inserted,
+                         uint32_t *distinct, uint64_t acc_cells, Scratch &scratch, uint32_t &launches) {
+  const int G = ctx->nranks, me = ctx->rank;
+  cudaStream_t stream = ctx->stream;
+  const uint64_t bucket_cap = std::max<uint64_t>(inserted, 1);
+  unsigned long long *cursors = scratch.alloc<unsigned long long>(kMaxParts);
+  CUDA_CK(cudaMemsetAsync(cursors, 0, kMaxParts * sizeof(unsigned long long), stream));
+  uint64_t *send = scratch.alloc<uint64_t>(bucket_cap * G);
+  PartitionParams A{};
+  A.keys = dset;
+  A.nslots = dset_cap;
+  A.sentinel_slot = ~0ull;
+  A.sentinel_present = nullptr;
+  A.nparts = (uint32_t)G;
+  A.owner_shift = 32;  // owner of the cell
+  A.bucket_cap = bucket_cap;
+  A.cursors = cursors;
+  A.out_keys = send;
+  A.npay = 0;
+  partition_table_kernel<<<grid_for(dset_cap, 256 * kPartPerThread, ctx->sm_count, 8), 256, 0, stream>>>(A);
+  CUDA_CK(cudaGetLastError());
+  ++launches;
+  std::vector<uint64_t> matrix = exchange_counts(ctx, cursors, scratch);
+  std::vector<uint64_t> recv_off(G);
+  uint64_t total = 0;
+  for (int r = 0; r < G; ++r) { recv_off[r] = total; total += matrix[(size_t)r * G + me]; }
+  uint64_t *recv = scratch.alloc<uint64_t>(total);
+  NCCL_CK(g_nccl.GroupStart());
+  exchange_array(ctx, send, bucket_cap, 8, recv, matrix, recv_off);
+  NCCL_CK(g_nccl.GroupEnd());
+  // owners dedupe what they received and count per cell
+  CUDA_CK(cudaMemsetAsync(distinct, 0, acc_cells * 4, stream));
+  if (total) {
+    const uint64_t set_cap = pow2_ceil(std::max<uint64_t>(2 * total, 1024));
+    uint64_t *set = scratch.alloc<uint64_t>(set_cap);
+    fill64(stream, ctx->sm_count, set, set_cap, kEmptyKey);
+    unsigned long long *sentinel = scratch.alloc<unsigned long long>(1);
+    CUDA_CK(cudaMemsetAsync(sentinel, 0, 8, stream));
+    distinct_insert_kernel<<<grid_for(total, 256, ctx->sm_count), 256, 0, stream>>>(recv, total, set, set_cap - 1,
+                                                                                  distinct, sentinel);
+    CUDA_CK(cudaGetLastError());
+    ++launches;
+  }
+  NCCL_CK(g_nccl.AllReduce(distinct, distinct, acc_cells, ncclUint32, ncclSum, ctx->comm, stream));
+}
+
+// hashed group tables across ranks: every (packed key, partial accumulators) record travels to the
+// rank that owns the key, owners merge with the same Update() as the scan, then the owned groups are
+// all-gathered so that every rank returns the full result. On return P / acc_ptrs / acc_cells
+// describe a table that holds ALL groups of all ranks (rebuilt from the gathered records).
+void nccl_merge_hash(vgpu_ctx *ctx, QueryRun &q, ScanParams &P, std::vector<void *> &acc_ptrs, Scratch &scratch,
+                     uint64_t &acc_cells, uint32_t &launches) {
+  const int G = ctx->nranks, me = ctx->rank;
+  cudaStream_t stream = ctx->stream;
+  const size_t nm = q.accs.size();
+  // how many groups does this rank hold?
+  ExtractParams E{};
+  E.ncells = acc_cells;
+  E.hash_mode = 1;
+  E.hkeys = P.hkeys;
+  E.present = P.present;
+  E.count_only = 1;
+  unsigned long long *d_n = scratch.alloc<unsigned long long>(1);
+  CUDA_CK(cudaMemsetAsync(d_n, 0, 8, stream));
+  E.counter = d_n;
+  extract_groups_kernel<<<grid_for(acc_cells, 256, ctx->sm_count), 256, 0, stream>>>(E);
+  CUDA_CK(cudaGetLastError());
+  ++launches;
+  uint64_t n_local = 0;
+  CUDA_CK(cudaMemcpyAsync(&n_local, d_n, 8, cudaMemcpyDeviceToHost, stream));
+  CUDA_CK(cudaStreamSynchronize(stream));
+
+  auto run_exchange = [&](const uint64_t *keys, uint64_t nslots, uint64_t sentinel_slot, const uint8_t *sentinel_present,
+                          const std::vector<void *> &src, uint64_t n_hint, bool all_to_root_of_key,
+                          uint64_t *&out_keys, std::vector<void *> &out_acc) -> uint64_t {
+    (void)all_to_root_of_key;
+    const uint64_t bucket_cap = std::max<uint64_t>(n_hint, 1);
+    unsigned long long *cursors = scratch.alloc<unsigned long long>(kMaxParts);
+    CUDA_CK(cudaMemsetAsync(cursors, 0, kMaxParts * sizeof(unsigned long long), stream));
+    uint64_t *send_keys = scratch.alloc<uint64_t>(bucket_cap * G);
+    std::vector<void *> send_acc(nm);
+    PartitionParams A{};
+    A.keys = keys;
+    A.nslots = nslots;
+    A.sentinel_slot = sentinel_slot;
+    A.sentinel_present = sentinel_present;
+    A.nparts = (uint32_t)G;
+    A.owner_shift = 0;
+    A.bucket_cap = bucket_cap;
+    A.cursors = cursors;
+    A.out_keys = send_keys;
+    A.npay = (uint32_t)nm;
+    for (size_t m = 0; m < nm; ++m) {
+      send_acc[m] = scratch.alloc<uint8_t>(bucket_cap * G * q.accs[m].acc_width);
+      A.pay_width[m] = q.accs[m].acc_width;
+      A.pay_src[m] = src[m];
+      A.pay_dst[m] = send_acc[m];
+    }
+    partition_table_kernel<<<grid_for(nslots + 1, 256 * kPartPerThread, ctx->sm_count, 8), 256, 0, stream>>>(A);
+    CUDA_CK(cudaGetLastError());
+    ++launches;
+    std::vector<uint64_t> matrix = exchange_counts(ctx, cursors, scratch);
+    std::vector<uint64_t> recv_off(G);
+    uint64_t total = 0;
+    for (int r = 0; r < G; ++r) { recv_off[r] = total; total += matrix[(size_t)r * G + me]; }
+    out_keys = scratch.alloc<uint64_t>(total);
+    out_acc.resize(nm);
+    for (size_t m = 0; m < nm; ++m) out_acc[m] = scratch.alloc<uint8_t>(total * q.accs[m].acc_width);
+    NCCL_CK(g_nccl.GroupStart());
+    exchange_array(ctx, send_keys, bucket_cap, 8, out_keys, matrix, recv_off);
+    for (size_t m = 0; m < nm; ++m)
+      exchange_array(ctx, send_acc[m], bucket_cap, q.accs[m].acc_width, out_acc[m], matrix, recv_off);
+    NCCL_CK(g_nccl.GroupEnd());
+    return total;
+  };
+
+  // build a fresh table from records
+  auto build_table = [&](const uint64_t *keys, const std::vector<void *> &src, uint64_t n, uint64_t cap) {
+    uint64_t block_bytes = 0;
+    auto carve = [&](uint64_t bytes) { uint64_t o = block_bytes; block_bytes += round_up(bytes, 256); return o; };
+    const uint64_t o_h = carve(cap * 8), o_p = carve(16);
+    std::vector<uint64_t> o_a(nm);
+    for (size_t m = 0; m < nm; ++m) o_a[m] = carve((cap + 1) * q.accs[m].acc_width);
+    uint8_t *block = scratch.alloc<uint8_t>(block_bytes);
+    MergeParams M{};
+    M.keys = keys;
+    M.n = n;
+    M.nmets = (uint32_t)nm;
+    M.hkeys = reinterpret_cast<uint64_t *>(block + o_h);
+    M.hmask = cap - 1;
+    M.present = block + o_p;
+    M.max_probe = (uint32_t)std::min<uint64_t>(cap, 1u << 20);
+    M.overflow = scratch.alloc<unsigned long long>(1);
+    CUDA_CK(cudaMemsetAsync(M.overflow, 0, 8, stream));
+    fill64(stream, ctx->sm_count, M.hkeys, cap, kEmptyKey);
+    CUDA_CK(cudaMemsetAsync(M.present, 0, 16, stream));
+    for (size_t m = 0; m < nm; ++m) {
+      M.ops[m] = q.accs[m].op;
+      M.widths[m] = q.accs[m].acc_width;
+      M.src[m] = src[m];
+      M.acc[m] = block + o_a[m];
+      if (q.accs[m].acc_width == 4) launches += fill32(stream, ctx->sm_count, M.acc[m], cap + 1, (uint32_t)q.accs[m].init);
+      else launches += fill64(stream, ctx->sm_count, M.acc[m], cap + 1, q.accs[m].init);
+    }
+    if (n) {
+      merge_records_kernel<<<grid_for(n, 256, ctx->sm_count), 256, 0, stream>>>(M);
+      CUDA_CK(cudaGetLastError());
+      ++launches;
+    }
+    P.hkeys = M.hkeys;
+    P.hmask = M.hmask;
+    P.present = M.present;
+    for (size_t m = 0; m < nm; ++m) acc_ptrs[m] = M.acc[m];
+    acc_cells = cap + 1;
+  };
+
+  // 1. records to their owners, owners merge
+  uint64_t *own_keys = nullptr;
+  std::vector<void *> own_acc;
+  const uint64_t n_owned_in = run_exchange(P.hkeys, P.hmask + 1, P.hmask + 1, P.present, acc_ptrs, n_local, false, own_keys, own_acc);
+  build_table(own_keys, own_acc, n_owned_in, pow2_ceil(std::max<uint64_t>(2 * n_owned_in, 1024)));
+
+  // 2. all-gather the owned groups: every rank sends its whole (merged) table to every rank
+  //    (bucket routing with owner := destination is not needed: broadcast each table's live records)
+  //    live records of this rank, compacted:
+  uint64_t *send_keys = nullptr;
+  std::vector<void *> send_acc;
+  {
+    // reuse the partition kernel with ONE bucket to compact the merged table
+    const uint64_t cap = P.hmask + 1;
+    unsigned long long *cursor = scratch.alloc<unsigned long long>(kMaxParts);
+    CUDA_CK(cudaMemsetAsync(cursor, 0, kMaxParts * sizeof(unsigned long long), stream));
+    const uint64_t bucket_cap = std::max<uint64_t>(n_owned_in, 1);
+    send_keys = scratch.alloc<uint64_t>(bucket_cap);
+    send_acc.resize(nm);
+    PartitionParams A{};
+    A.keys = P.hkeys;
+    A.nslots = cap;
+    A.sentinel_slot = cap;
+    A.sentinel_present = P.present;
+    A.nparts = 1;
+    A.owner_shift = 0;
+    A.bucket_cap = bucket_cap;
+    A.cursors = cursor;
+    A.out_keys = send_keys;
+    A.npay = (uint32_t)nm;
+    for (size_t m = 0; m < nm; ++m) {
+      send_acc[m] = scratch.alloc<uint8_t>(bucket_cap * q.accs[m].acc_width);
+      A.pay_width[m] = q.accs[m].acc_width;
+      A.pay_src[m] = acc_ptrs[m];
+      A.pay_dst[m] = send_acc[m];
+    }
+    partition_table_kernel<<<grid_for(cap + 1, 256 * kPartPerThread, ctx->sm_count, 8), 256, 0, stream>>>(A);
+    CUDA_CK(cudaGetLastError());
+    ++launches;
+    // group counts of every rank
+    uint64_t *d_all = scratch.alloc<uint64_t>(G);
+    NCCL_CK(g_nccl.AllGather(cursor, d_all, 1, ncclUint64, ctx->comm, stream));
+    std::vector<uint64_t> counts(G);
+    CUDA_CK(cudaMemcpyAsync(counts.data(), d_all, G * 8, cudaMemcpyDeviceToHost, stream));
+    CUDA_CK(cudaStreamSynchronize(stream));
+    std::vector<uint64_t> off(G);
+    uint64_t total = 0;
+    for (int r = 0; r < G; ++r) { off[r] = total; total += counts[r]; }
+    uint64_t *all_keys = scratch.alloc<uint64_t>(total);
+    std::vector<void *> all_acc(nm);
+    for (size_t m = 0; m < nm; ++m) all_acc[m] = scratch.alloc<uint8_t>(total * q.accs[m].acc_width);
+    NCCL_CK(g_nccl.GroupStart());
+    for (int r = 0; r < G; ++r) {
+      if (counts[r] == 0) continue;
+      NCCL_CK(g_nccl.Broadcast(send_keys, all_keys + off[r], counts[r] * 8, ncclUint8, r, ctx->comm, stream));
+      for (size_t m = 0; m < nm; ++m) {
+        const uint32_t w = q.accs[m].acc_width;
+        NCCL_CK(g_nccl.Broadcast(send_acc[m], static_cast<uint8_t *>(all_acc[m]) + off[r] * w, counts[r] * w, ncclUint8, r,
+                                 ctx->comm, stream));
+      }
+    }
+    NCCL_CK(g_nccl.GroupEnd());
+    // 3. the full table, identical on every rank (keys are disjoint between owners: plain inserts)
+    build_table(all_keys, all_acc, total, pow2_ceil(std::max<uint64_t>(2 * total, 1024)));
+  }
+}
+
 }  // namespace
 
 int vgpu_query_agg(vgpu_table *t, const vgpu_plan *plan, vgpu_result **out) {
@@ -1327,30 +1590,47 @@ int vgpu_query_agg(vgpu_table *t, const vgpu_plan *plan, vgpu_result **out) {
         ks.rule_unit[r] = (uint8_t)key.rule_granularity[r];
         ks.rule_boundary[r] = key.rule_boundary[r];
       }
-      // value range over the active segments
+    }
+    // value range of every key over the active segments (ordered domain). With several ranks the
+    // ranges — hence the cell numbering / key packing — must be the same everywhere: min-reduce them.
+    std::vector<uint64_t> kmin(plan->nkeys, ~0ull), kmax(plan->nkeys, 0ull);
+    for (uint32_t k = 0; k < plan->nkeys; ++k) {
+      const uint32_t col = plan->keys[k].col;
+      for (uint32_t s : q.active) {
+        const SegmentData &sd = t->segs[s];
+        if (sd.nrows == 0) continue;
+        kmin[k] = std::min(kmin[k], sd.omin[col]);
+        kmax[k] = std::max(kmax[k], sd.omax[col]);
+      }
+    }
+    uint64_t global_active_rows = q.active_rows;
+    if (ctx->nranks > 1) {
+      std::vector<uint64_t> h(2 * plan->nkeys + 1);
+      for (uint32_t k = 0; k < plan->nkeys; ++k) { h[2 * k] = kmin[k]; h[2 * k + 1] = ~kmax[k]; }
+      h[2 * plan->nkeys] = ~q.active_rows;  // min of complements == complement of the max
+      uint64_t *d = ctx->d_plan;
+      CUDA_CK(cudaMemcpyAsync(d, h.data(), h.size() * 8, cudaMemcpyHostToDevice, stream));
+      NCCL_CK(g_nccl.AllReduce(d, d, h.size(), ncclUint64, ncclMin, ctx->comm, stream));
+      CUDA_CK(cudaMemcpyAsync(h.data(), d, h.size() * 8, cudaMemcpyDeviceToHost, stream));
+      CUDA_CK(cudaStreamSynchronize(stream));
+      for (uint32_t k = 0; k < plan->nkeys; ++k) { kmin[k] = h[2 * k]; kmax[k] = ~h[2 * k + 1]; }
+      global_active_rows = ~h[2 * plan->nkeys] * (uint64_t)ctx->nranks;  // upper bound, same on every rank
+    }
+    for (uint32_t k = 0; k < plan->nkeys; ++k) {
+      const ColInfo &ci = t->cols[plan->keys[k].col];
+      const KeySpec &ks = P.keys[k];
       KeyRange kr{0, 1};
-      if (type_float(ci.type) || (ci.width == 8 && false)) {
+      if (type_float(ci.type)) {
         kr.lo = 0;
         kr.range = ci.width == 4 ? (1ull << 32) : 0;  // keyed by raw bits
-      } else {
-        uint64_t omin = ~0ull, omax = 0;
-        bool any = false;
-        for (uint32_t s : q.active) {
-          const SegmentData &sd = t->segs[s];
-          if (sd.nrows == 0) continue;
-          omin = std::min(omin, sd.omin[key.col]);
-          omax = std::max(omax, sd.omax[key.col]);
-          any = true;
+      } else if (kmin[k] <= kmax[k]) {
+        uint64_t lo = from_ordered_int(kmin[k], ci.type), hi = from_ordered_int(kmax[k], ci.type);
+        if (ks.rollup) {  // truncation only moves values down, at most to the start of their year
+          if (ks.micro) lo = host_trunc_year_seconds(lo / 1000000ull) * 1000000ull;
+          else lo = host_trunc_year_seconds(lo);
         }
-        if (any) {
-          uint64_t lo = from_ordered_int(omin, ci.type), hi = from_ordered_int(omax, ci.type);
-          if (ks.rollup) {  // truncation only moves values down, at most to the start of their year
-            if (ks.micro) lo = host_trunc_year_seconds(lo / 1000000ull) * 1000000ull;
-            else lo = host_trunc_year_seconds(lo);
-          }
-          kr.lo = lo;
-          kr.range = hi - lo + 1;  // wraps to 0 for the full 64-bit domain
-        }
+        kr.lo = lo;
+        kr.range = hi - lo + 1;  // wraps to 0 for the full 64-bit domain
       }
       q.ranges[k] = kr;
     }
@@ -1391,7 +1671,7 @@ int vgpu_query_agg(vgpu_table *t, const vgpu_plan *plan, vgpu_result **out) {
     }
     if (!fits64) fail(VGPU_ERR_UNSUPPORTED, "group key does not pack into 64 bits");
     const uint64_t cells = (uint64_t)cells128;
-    uint64_t dense_limit = std::min<uint64_t>(std::max<uint64_t>(4 * q.active_rows, 1ull << 22), 1ull << 28);
+    uint64_t dense_limit = std::min<uint64_t>(std::max<uint64_t>(4 * global_active_rows, 1ull << 22), 1ull << 28);
     if (P.ndistinct) dense_limit = std::min<uint64_t>(dense_limit, 0xffffffffull);
     bool dense = cells <= dense_limit;
     if (plan->flags & VGPU_PLAN_FORCE_HASH) dense = false;
@@ -1400,6 +1680,10 @@ int vgpu_query_agg(vgpu_table *t, const vgpu_plan *plan, vgpu_result **out) {
       dense = true;
     }
     q.hash_mode = !dense;
+    if (ctx->trace) {
+      fprintf(stderr, "[vgpu r%d] cells=%llu dense_limit=%llu dense=%d active_rows=%llu global=%llu\n", ctx->rank, (unsigned long long)cells, (unsigned long long)dense_limit, (int)dense, (unsigned long long)q.active_rows, (unsigned long long)global_active_rows);
+      for (uint32_t k = 0; k < plan->nkeys; ++k) fprintf(stderr, "[vgpu r%d]   key %u lo=%llu range=%llu kmin=%llu kmax=%llu\n", ctx->rank, k, (unsigned long long)q.ranges[k].lo, (unsigned long long)q.ranges[k].range, (unsigned long long)kmin[k], (unsigned long long)kmax[k]);
+    }
     {
       uint64_t mul = 1;
       for (uint32_t k = 0; k < plan->nkeys; ++k) {
@@ -1432,7 +1716,7 @@ int vgpu_query_agg(vgpu_table *t, const vgpu_plan *plan, vgpu_result **out) {
 
     uint64_t hash_cap = 0;
     if (q.hash_mode) {
-      uint64_t est = std::min<uint64_t>(cells, std::max<uint64_t>(q.active_rows, 1));
+      uint64_t est = std::min<uint64_t>(cells, std::max<uint64_t>(global_active_rows, 1));
       uint64_t want = pow2_ceil(std::max<uint64_t>(2 * est, 1024));
       hash_cap = std::min<uint64_t>(want, 1ull << 24);
       hash_cap = std::max(hash_cap, std::min(t->hash_cap_hint, want));
@@ -1523,6 +1807,8 @@ int vgpu_query_agg(vgpu_table *t, const vgpu_plan *plan, vgpu_result **out) {
         ++launches;
       }
       CUDA_CK(cudaEventRecord(ctx->ev_scan1, stream));
+      if (ctx->nranks > 1)  // every rank must take the same grow-and-retry decision
+        NCCL_CK(g_nccl.AllReduce(ctx->d_counters + 1, ctx->d_counters + 1, 1, ncclUint64, ncclMax, ctx->comm, stream));
       CUDA_CK(cudaMemcpyAsync(ctx->h_counters, ctx->d_counters, 16 * sizeof(unsigned long long),
                               cudaMemcpyDeviceToHost, stream));
       CUDA_CK(cudaStreamSynchronize(stream));
@@ -1546,19 +1832,26 @@ int vgpu_query_agg(vgpu_table *t, const vgpu_plan *plan, vgpu_result **out) {
         uint64_t most = 0;
         for (uint32_t d = 0; d < P.ndistinct; ++d) most = std::max<uint64_t>(most, ctx->h_counters[2 + d]);
         t->pairs_cap_hint = std::max(t->pairs_cap_hint, pow2_ceil(std::max<uint64_t>(2 * most, 1ull << 16)));
-        if (ctx->nranks > 1) fail(VGPU_ERR_UNSUPPORTED, "multi-GPU count-distinct merge is not implemented yet");
       }
       view.passed_rows = passed;
 
       // ---- multi-GPU: merge the partial group tables ----
+      uint64_t acc_cells_x = acc_cells;  // group table the extraction reads (replaced by the merged one)
       if (ctx->nranks > 1) {
-        if (q.hash_mode) fail(VGPU_ERR_UNSUPPORTED, "multi-GPU merge of hashed group tables is not implemented yet");
-        nccl_merge_dense(ctx, q, P, acc_ptrs);
+        if (q.hash_mode) {
+          if (P.ndistinct) fail(VGPU_ERR_UNSUPPORTED, "multi-GPU count-distinct over a hashed group table is not implemented yet");
+          nccl_merge_hash(ctx, q, P, acc_ptrs, scratch, acc_cells_x, launches);
+        } else {
+          nccl_merge_dense(ctx, q, P, acc_ptrs);
+          for (uint32_t d = 0; d < P.ndistinct; ++d)
+            nccl_merge_distinct(ctx, P.dset[d], dset_cap, ctx->h_counters[2 + d],
+                                static_cast<uint32_t *>(acc_ptrs[P.distinct_met[d]]), acc_cells, scratch, launches);
+        }
       }
 
       // ---- extract the groups ----
       ExtractParams E{};
-      E.ncells = acc_cells;
+      E.ncells = acc_cells_x;
       E.hash_mode = q.hash_mode;
       E.nkeys = plan->nkeys;
       E.nmets = (uint32_t)q.accs.size();
@@ -1566,10 +1859,10 @@ int vgpu_query_agg(vgpu_table *t, const vgpu_plan *plan, vgpu_result **out) {
       E.present = P.present;
       unsigned long long *d_ngroups = ctx->d_counters + 12;
       E.counter = d_ngroups;
-      uint64_t bound = std::min<uint64_t>(acc_cells, passed);
+      uint64_t bound = std::min<uint64_t>(acc_cells_x, passed);
       if (ctx->nranks > 1) {  // merged tables: `passed` is only this rank's share, count first
         E.count_only = 1;
-        extract_groups_kernel<<<grid_for(acc_cells, 256, ctx->sm_count), 256, 0, stream>>>(E);
+        extract_groups_kernel<<<grid_for(acc_cells_x, 256, ctx->sm_count), 256, 0, stream>>>(E);
         CUDA_CK(cudaGetLastError());
         ++launches;
         CUDA_CK(cudaMemcpyAsync(ctx->h_counters, ctx->d_counters, 16 * sizeof(unsigned long long),
@@ -1597,7 +1890,7 @@ int vgpu_query_agg(vgpu_table *t, const vgpu_plan *plan, vgpu_result **out) {
         E.mets[m].out = d_accs[m];
       }
       if (bound > 0) {
-        extract_groups_kernel<<<grid_for(acc_cells, 256, ctx->sm_count), 256, 0, stream>>>(E);
+        extract_groups_kernel<<<grid_for(acc_cells_x, 256, ctx->sm_count), 256, 0, stream>>>(E);
         CUDA_CK(cudaGetLastError());
         ++launches;
       }
