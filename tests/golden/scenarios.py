@@ -1,0 +1,140 @@
+"""Scenario definitions shared by tests/golden/make_golden.py (-> oracle_cli, the real reference) and
+tests/test_dropin_cpp.py (-> vgpu_cli: stock runner vs GpuQueryRunner in one reference process).
+
+  * fixtures of the reference's own tests (test/db.h:33-289) with extra queries that the gtests do not
+    issue (edge cases: NOT IN pruning quirk, float MAX init, wrap-around sums, missing dict values),
+  * small-N twins of the benchmark configs C0-C4 (same generators as bench.py).
+"""
+NOW = 1496570140
+T0 = 1490000000
+
+
+def agg(**kw):
+    q = {"type": "aggregate", "table": "events"}
+    q.update(kw)
+    return q
+
+
+INAPP = {"name": "events",
+         "dimensions": [{"name": "country"}, {"name": "event_name", "length": 20}, {"name": "install_time", "type": "uint"}],
+         "metrics": [{"name": "count", "type": "count"}, {"name": "revenue", "type": "double_sum"}]}
+INAPP_ROWS = [["US", "purchase", "20141112", "0.1"], ["US", "purchase", "20141113", "1.1"], ["US", "donate", "20141112", "5.0"],
+              ["IL", "refund", "20141111", "1.01"], ["CH", "refund", "20141111", "1.1"], ["AZ", "refund", "20141111", "1.1"],
+              ["RU", "donate", "20141112", "1.0"], ["KZ", "review", "20141113", "5.0"]]
+
+SCENARIOS = [
+    {"name": "inapp", "table": INAPP, "rows": INAPP_ROWS, "queries": [
+        agg(dimensions=["event_name", "country"], metrics=["revenue"], filter={"op": "eq", "column": "country", "value": "US"}),
+        agg(dimensions=["country"], metrics=["count", "revenue"], header=True),
+        agg(dimensions=["country"], metrics=["count"], filter={"op": "eq", "column": "country", "value": "nowhere"}),
+        agg(dimensions=["country"], metrics=["count"], filter={"op": "ne", "column": "country", "value": "nowhere"}),
+        agg(dimensions=[], metrics=["count", "revenue"], filter={"op": "gt", "column": "install_time", "value": "20141111"}),
+        agg(dimensions=["event_name"], metrics=["count"],
+            filter={"op": "not", "filter": {"op": "or", "filters": [
+                {"op": "in", "column": "country", "values": ["US", "IL"]},
+                {"op": "lt", "column": "revenue", "value": "1.05"}]}}),
+        agg(dimensions=["country"], metrics=["revenue", "count"], having={"op": "ge", "column": "revenue", "value": "1.1"},
+            sort=[{"column": "revenue"}, {"column": "country", "ascending": True}], limit=4),
+        agg(select=[{"column": "install_time"}, {"column": "count"}], sort=[{"column": "install_time", "ascending": True}], skip=1, limit=2),
+    ]},
+    {"name": "prune_quirk", "table": {"name": "events", "segment_size": 2,
+                                      "dimensions": [{"name": "n", "type": "uint"}, {"name": "s"}],
+                                      "metrics": [{"name": "count", "type": "count"}]},
+     "rows": [["1", "a"], ["2", "b"], ["10", "a"], ["11", "c"], ["20", "a"]],
+     "queries": [
+         agg(dimensions=["n"], metrics=["count"], filter={"op": "not", "filter": {"op": "in", "column": "n", "values": ["1"]}}),
+         agg(dimensions=["n"], metrics=["count"], filter={"op": "in", "column": "n", "values": ["2", "11", "99"]}),
+         agg(dimensions=["s"], metrics=["count"], filter={"op": "ge", "column": "n", "value": "10"}),
+         agg(dimensions=["s"], metrics=["count"], filter={"op": "or", "filters": [
+             {"op": "lt", "column": "n", "value": "2"}, {"op": "eq", "column": "s", "value": "c"}]}),
+         agg(dimensions=["s"], metrics=["count"], filter={"op": "and", "filters": [
+             {"op": "le", "column": "n", "value": "0"}, {"op": "eq", "column": "s", "value": "a"}]}),
+     ]},
+    {"name": "metric_types", "table": {"name": "events", "dimensions": [{"name": "k"}],
+                                       "metrics": [{"name": "bs", "type": "byte_sum"}, {"name": "ubs", "type": "ubyte_sum"},
+                                                   {"name": "is", "type": "int_sum"}, {"name": "fmx", "type": "float_max"},
+                                                   {"name": "fmn", "type": "float_min"}, {"name": "dmx", "type": "double_max"},
+                                                   {"name": "lav", "type": "long_avg"}, {"name": "smn", "type": "short_min"},
+                                                   {"name": "umx", "type": "uint_max"}]},
+     "rows": [["a", "100", "200", "2000000000", "-1.5", "-1.5", "-7.25", "10", "-5", "7"],
+              ["a", "100", "100", "2000000000", "-2.5", "2.5", "-0.5", "21", "3", "4000000000"],
+              ["b", "-128", "255", "-5", "3.25", "0", "1e300", "-9", "-32768", "0"],
+              ["b", "-1", "1", "5", "1.0", "-0.0", "2.0", "0", "32767", "1"]],
+     "queries": [
+         agg(dimensions=["k"], metrics=["bs", "ubs", "is", "fmx", "fmn", "dmx", "lav", "smn", "umx"]),
+         agg(dimensions=[], metrics=["lav", "is"], filter={"op": "gt", "column": "lav", "value": "-100"}),
+         agg(dimensions=["k"], metrics=["lav"], having={"op": "gt", "column": "lav", "value": "0"}),
+     ]},
+    {"name": "users_bitset", "table": {"name": "events", "dimensions": [{"name": "country"}, {"name": "event_name"}, {"name": "time", "type": "uint"}],
+                                       "metrics": [{"name": "user_id", "type": "bitset"}]},
+     "rows": [["US", "purchase", "1495475514", "12345"], ["RU", "support", "1495475517", "12346"],
+              ["US", "openapp", "1495475632", "12347"], ["IL", "purchase", "1495475715", "12348"],
+              ["KZ", "closeapp", "1495475716", "12349"], ["US", "uninstall", "1495475809", "12350"],
+              ["KZ", "purchase", "1495475808", "12351"], ["US", "purchase", "1495476000", "12352"],
+              ["US", "purchase", "1495475514", "12352"], ["US", "purchase", "1495475514", "777"]],
+     "queries": [
+         agg(dimensions=["country"], metrics=["user_id"]),
+         agg(dimensions=["event_name"], metrics=["user_id"], filter={"op": "ge", "column": "user_id", "value": "1"}),
+         agg(dimensions=["country", "event_name"], metrics=["user_id"], filter={"op": "gt", "column": "user_id", "value": "1"}),
+         agg(dimensions=[], metrics=["user_id"], having={"op": "gt", "column": "user_id", "value": "3"}),
+     ]},
+    {"name": "time_rollup", "rollup_ts": NOW,
+     "table": {"name": "events", "dimensions": [{"name": "country"}, {"name": "install_time", "type": "time", "format": "millis",
+                                                 "rollup_rules": [{"granularity": "hour", "after": "1 days"},
+                                                                  {"granularity": "day", "after": "1 weeks"},
+                                                                  {"granularity": "month", "after": "1 years"}]},
+                                                {"name": "mt", "type": "microtime", "format": "micros"}],
+               "metrics": [{"name": "count", "type": "count"}]},
+     "rows": [["US", str((NOW - d * 3600 * 7 - 11) * 1000), str((NOW - d * 86400 * 5 - 3) * 1000000 + 123456)] for d in range(120)],
+     "queries": [
+         agg(select=[{"column": "install_time", "format": "%Y-%m-%d %H:%M:%S"}, {"column": "count"}]),
+         agg(select=[{"column": "install_time", "granularity": "day", "format": "%Y-%m-%d"}, {"column": "count"}]),
+         agg(select=[{"column": "install_time", "granularity": "year", "format": "%Y-%m-%d %H:%M:%S"}, {"column": "count"}]),
+         agg(select=[{"column": "mt", "granularity": "month", "format": "%Y-%m-%d %H:%M:%S"}, {"column": "count"}]),
+         agg(select=[{"column": "mt", "format": "%Y-%m-%d %H:%M:%S"}, {"column": "count"}], filter={"op": "ge", "column": "mt", "value": str((NOW - 86400 * 30) * 1000000)}),
+         agg(select=[{"column": "install_time", "granularity": "minute", "format": "%Y-%m-%d %H:%M:%S"}, {"column": "count"}],
+             filter={"op": "gt", "column": "install_time", "value": "2017-06-01 00:00:00"}),
+     ]},
+    # ---- small-N twins of the benchmark configs (bench.py WORKLOADS) ----
+    {"name": "c1_twin", "table": {"name": "events", "segment_size": 20000,
+                                  "dimensions": [{"name": "d0"}, {"name": "d1"}, {"name": "d2"}, {"name": "d3"}],
+                                  "metrics": [{"name": "count", "type": "count"}, {"name": "m1", "type": "long_sum"}, {"name": "m2", "type": "int_sum"}]},
+     "generate": {"n": 70000, "seed": 42, "columns": [{"prefix": "a", "lo": 1, "range": 16}, {"prefix": "b", "lo": 1, "range": 50},
+                                                       {"prefix": "c", "lo": 1, "range": 10}, {"prefix": "d", "lo": 1, "range": 1000000},
+                                                       {"lo": 0, "range": 1000}, {"lo": -50, "range": 100}]},
+     "queries": [agg(dimensions=["d1", "d2"], metrics=["m1", "count"], filter={"op": "eq", "column": "d0", "value": "a7"}),
+                 agg(dimensions=["d0"], metrics=["m1", "m2", "count"])]},
+    {"name": "c2_twin", "table": {"name": "events", "segment_size": 20000,
+                                  "dimensions": [{"name": "d0"}, {"name": "d1"}, {"name": "d2"}, {"name": "d3"},
+                                                 {"name": "n4", "type": "ushort"}, {"name": "t5", "type": "time", "format": "posix"}],
+                                  "metrics": [{"name": "mn", "type": "int_min"}, {"name": "mx", "type": "int_max"}, {"name": "uid", "type": "bitset"}]},
+     "generate": {"n": 70000, "seed": 42, "columns": [{"prefix": "a", "lo": 1, "range": 50}, {"prefix": "b", "lo": 1, "range": 20},
+                                                       {"prefix": "c", "lo": 1, "range": 50}, {"prefix": "d", "lo": 1, "range": 100},
+                                                       {"lo": 0, "range": 1000}, {"lo": T0, "range": 10000000},
+                                                       {"lo": -2**31, "range": 2**32}, {"lo": -2**31, "range": 2**32}, {"lo": 0, "range": 1000}]},
+     "queries": [agg(dimensions=["d0", "d1", "d2", "d3"], metrics=["mn", "mx", "uid"],
+                     filter={"op": "and", "filters": [
+                         {"op": "in", "column": "d0", "values": ["a3", "a11", "a19", "a27", "a42"]},
+                         {"op": "ge", "column": "n4", "value": "250"}, {"op": "lt", "column": "n4", "value": "750"},
+                         {"op": "ge", "column": "t5", "value": str(T0 + 2500000)}, {"op": "lt", "column": "t5", "value": str(T0 + 7500000)}]}),
+                 agg(dimensions=["d1"], metrics=["uid", "mn"], filter={"op": "in", "column": "d0", "values": ["a3", "a11"]})]},
+    {"name": "c3_twin", "table": {"name": "events", "segment_size": 20000,
+                                  "dimensions": [{"name": "d0"}, {"name": "d1"}, {"name": "d2"}, {"name": "t3", "type": "time", "format": "posix"}],
+                                  "metrics": [{"name": "m1", "type": "long_sum"}]},
+     "generate": {"n": 70000, "seed": 42, "columns": [{"prefix": "a", "lo": 1, "range": 100}, {"prefix": "b", "lo": 1, "range": 100},
+                                                       {"prefix": "c", "lo": 1, "range": 100}, {"lo": T0, "range": 4000000}, {"lo": 0, "range": 1000}]},
+     "queries": [agg(dimensions=["d0", "d1", "d2"], metrics=["m1"],
+                     filter={"op": "and", "filters": [{"op": "ge", "column": "t3", "value": str(T0 + 1000000)},
+                                                      {"op": "lt", "column": "t3", "value": str(T0 + 2000000)}]})]},
+    {"name": "c4_twin", "rollup_ts": NOW,
+     "table": {"name": "events", "segment_size": 20000,
+               "dimensions": [{"name": "d0"}, {"name": "t1", "type": "time", "format": "posix",
+                                               "rollup_rules": [{"granularity": "hour", "after": "1 days"},
+                                                                {"granularity": "day", "after": "1 weeks"},
+                                                                {"granularity": "month", "after": "1 years"}]}],
+               "metrics": [{"name": "m1", "type": "long_sum"}, {"name": "count", "type": "count"}]},
+     "generate": {"n": 70000, "seed": 42, "columns": [{"prefix": "a", "lo": 1, "range": 200},
+                                                       {"lo": NOW - 730 * 86400, "range": 730 * 86400}, {"lo": 0, "range": 1000}]},
+     "queries": [agg(select=[{"column": "d0"}, {"column": "t1", "granularity": "hour", "format": "%Y-%m-%d %H:%M:%S"}, {"column": "m1"}, {"column": "count"}]),
+                 agg(select=[{"column": "t1", "format": "%Y-%m-%d %H:%M:%S"}, {"column": "count"}])]},
+]
