@@ -1,0 +1,78 @@
+"""The C-ABI boundary: libvgpu.so loads on a CPU-only box and exports every symbol include/vgpu.h
+declares; without a GPU the entry points fail loudly (there is no CPU path). No compute calls here."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    hdr = open(os.path.join(ROOT, "include", "vgpu.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    return sorted(set(re.findall(r"\b(vgpu_[a-z_0-9]+)\s*\(", hdr)))
+
+
+def test_header_declares_the_boundary():
+    syms = declared_symbols()
+    for must in ("vgpu_init", "vgpu_table_create", "vgpu_segment_put", "vgpu_query_agg", "vgpu_result_get",
+                 "vgpu_result_free", "vgpu_comm_init", "vgpu_last_error", "vgpu_shutdown"):
+        assert must in syms
+
+
+def test_library_exports_every_declared_symbol(built_lib):
+    from viyadb_b200 import _native as N
+    lib = C.CDLL(N.LIB_PATH)
+    for name in declared_symbols():
+        assert hasattr(lib, name), f"{name} declared in include/vgpu.h but not exported"
+    bound = {s[0] for s in N.SYMBOLS}
+    assert bound == set(declared_symbols()), "viyadb_b200/_native.py must bind exactly the declared symbols"
+    assert lib.vgpu_abi_version() == N.VGPU_ABI_VERSION
+
+
+def test_struct_layouts_match_the_header(built_lib):
+    """sizeof of the ctypes mirrors == sizeof in C (compiled from the header with gcc)."""
+    import subprocess
+    import tempfile
+    from viyadb_b200 import _native as N
+    src = '#include "vgpu.h"\n#include <stdio.h>\nint main(){printf("%zu %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(vgpu_column), sizeof(vgpu_schema), sizeof(vgpu_bitset_csr), sizeof(vgpu_pred_node), sizeof(vgpu_key), sizeof(vgpu_plan), sizeof(vgpu_result_view), sizeof(vgpu_gen_col));return 0;}\n'
+    with tempfile.TemporaryDirectory() as d:
+        open(os.path.join(d, "t.c"), "w").write(src)
+        subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), "-o", os.path.join(d, "t"), os.path.join(d, "t.c")], check=True)
+        out = subprocess.run([os.path.join(d, "t")], capture_output=True, text=True, check=True).stdout.split()
+    want = [C.sizeof(x) for x in (N.Column, N.Schema, N.BitsetCsr, N.PredNode, N.Key, N.Plan, N.ResultView, N.GenCol)]
+    assert [int(x) for x in out] == want
+
+
+def test_no_cpu_fallback_without_a_device(built_lib):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    import viyadb_b200 as v
+    with pytest.raises(v.VgpuError) as e:
+        v.Database({"tables": []}, device=0)
+    assert e.value.code == -3 and "no CPU path" in str(e.value)
+    # plan-only databases have no device store: scanning must fail, not fall back
+    db = v.Database({"tables": [{"name": "t", "dimensions": [{"name": "a"}], "metrics": [{"name": "count", "type": "count"}]}]}, device=None)
+    with pytest.raises(RuntimeError):
+        db.query({"type": "aggregate", "table": "t", "dimensions": ["a"], "metrics": ["count"]})
+
+
+def test_product_never_imports_the_oracle():
+    """Nothing under viyadb_b200/ may import, call, link or execute anything under oracle/ (comments that
+    cite it are fine)."""
+    bad = ("import viya_oracle", "from viya_oracle", "viya_oracle.", "oracle/_ref", "\"oracle\"", "'oracle'",
+           "#include \"../../oracle", "#include \"oracle")
+    for base, _, files in os.walk(os.path.join(ROOT, "viyadb_b200")):
+        if "_build" in base or "__pycache__" in base:
+            continue
+        for f in files:
+            if not f.endswith((".py", ".cu", ".cuh", ".h", ".cc")):
+                continue
+            for line in open(os.path.join(base, f), errors="replace"):
+                code = line.split("#")[0] if f.endswith(".py") else line.split("//")[0]
+                if f.endswith(".py") is False and line.lstrip().startswith("#include"):
+                    code = line
+                assert not any(b in code for b in bad), (os.path.join(base, f), line.strip())
