@@ -584,8 +584,8 @@ __global__ void __launch_bounds__(256) column_minmax_kernel(const __grid_constan
     mx = max(mx, __shfl_down_sync(0xffffffffu, mx, o));
   }
   if ((threadIdx.x & 31) == 0 && mn <= mx) {
-    atomicMin(&S.out[2 * c], (unsigned long long)mn);
-    atomicMax(&S.out[2 * c + 1], (unsigned long long)mx);
+    atomicMin(&S.out[2 * sc.pad], (unsigned long long)mn);   // sc.pad = schema column (output slot)
+    atomicMax(&S.out[2 * sc.pad + 1], (unsigned long long)mx);
   }
 }
 

@@ -290,6 +290,10 @@ struct SegmentData {
   uint32_t *bs_values[kMaxBitsetCols] = {nullptr, nullptr, nullptr, nullptr};
   uint32_t *bs_offsets[kMaxBitsetCols] = {nullptr, nullptr, nullptr, nullptr};
   uint64_t bs_n[kMaxBitsetCols] = {0, 0, 0, 0};
+  uint64_t bs_vcap[kMaxBitsetCols] = {0, 0, 0, 0};  // allocated ids / offsets (elements)
+  uint64_t bs_ocap[kMaxBitsetCols] = {0, 0, 0, 0};
+  bool bs_has_offsets[kMaxBitsetCols] = {false, false, false, false};  // CSR offsets in use (else one id per row)
+  bool stats_pending = false;  // min/max computed on the device, not yet read back
   // ordered (to_ordered) min / max of the stored values per column; only fixed-width dimensions
   std::vector<uint64_t> omin, omax;
 };
@@ -306,6 +310,11 @@ struct vgpu_table {
   std::vector<SegmentData> segs;
   SegDesc *d_segs = nullptr;
   size_t d_segs_cap = 0;
+  // per segment, per column: ordered min / max, reduced on the device at put time and read back in
+  // one batch by the next query (a put never waits for its own statistics)
+  unsigned long long *d_stats = nullptr;
+  size_t d_stats_segs = 0;
+  unsigned long long *h_stats_init = nullptr;  // pinned pattern {~0, 0} x ncols
   bool descs_dirty = true;
   // scratch high-water marks so that a repeated query shape never re-runs on overflow
   uint64_t hash_cap_hint = 0;
@@ -391,56 +400,91 @@ void ensure_segment(vgpu_table *t, uint32_t seg_idx, uint64_t nrows) {
     }
     sd.cap = cap;
   } else {
-    for (int b = 0; b < kMaxBitsetCols; ++b) {
-      if (sd.bs_values[b]) { cudaFree(sd.bs_values[b]); sd.bs_values[b] = nullptr; }
-      if (sd.bs_offsets[b]) { cudaFree(sd.bs_offsets[b]); sd.bs_offsets[b] = nullptr; }
-      sd.bs_n[b] = 0;
-    }
+    for (int b = 0; b < kMaxBitsetCols; ++b) sd.bs_n[b] = 0;  // buffers are kept and reused
   }
   sd.nrows = nrows;
   sd.valid = false;
   t->descs_dirty = true;
 }
 
-// per-column min/max of the stored cells (device reduction), kept in the ordered domain
-void compute_stats(vgpu_table *t, SegmentData &sd) {
+// per-column min/max of the stored cells (device reduction), kept in the ordered domain. Launch only:
+// the values are fetched by fetch_stats() when a query needs them.
+void ensure_stats_capacity(vgpu_table *t, size_t nsegs) {
+  const size_t ncols = t->cols.size();
+  if (t->h_stats_init == nullptr) {
+    CUDA_CK(cudaMallocHost(&t->h_stats_init, 2 * ncols * sizeof(unsigned long long)));
+    for (size_t c = 0; c < ncols; ++c) { t->h_stats_init[2 * c] = ~0ull; t->h_stats_init[2 * c + 1] = 0; }
+  }
+  if (nsegs <= t->d_stats_segs) return;
+  size_t cap = std::max<size_t>(64, t->d_stats_segs * 2);
+  while (cap < nsegs) cap *= 2;
+  unsigned long long *n = nullptr;
+  CUDA_CK(cudaMalloc(&n, cap * 2 * ncols * sizeof(unsigned long long)));
+  if (t->d_stats) {
+    CUDA_CK(cudaMemcpyAsync(n, t->d_stats, t->d_stats_segs * 2 * ncols * sizeof(unsigned long long),
+                            cudaMemcpyDeviceToDevice, t->ctx->stream));
+    CUDA_CK(cudaStreamSynchronize(t->ctx->stream));
+    cudaFree(t->d_stats);
+  }
+  t->d_stats = n;
+  t->d_stats_segs = cap;
+}
+
+void compute_stats(vgpu_table *t, uint32_t seg_idx) {
   vgpu_ctx *ctx = t->ctx;
-  size_t ncols = t->cols.size();
+  SegmentData &sd = t->segs[seg_idx];
+  const size_t ncols = t->cols.size();
   sd.omin.assign(ncols, ~0ull);
   sd.omax.assign(ncols, 0ull);
+  sd.stats_pending = false;
   std::vector<uint32_t> want;
   for (uint32_t c = 0; c < t->ndims; ++c)
     if (!t->cols[c].bitset) want.push_back(c);
   if (sd.nrows == 0 || want.empty()) return;
-  Scratch scratch(ctx->stream);
+  ensure_stats_capacity(t, t->segs.size());
+  unsigned long long *d_out = t->d_stats + (size_t)seg_idx * 2 * ncols;
+  CUDA_CK(cudaMemcpyAsync(d_out, t->h_stats_init, 2 * ncols * sizeof(unsigned long long), cudaMemcpyHostToDevice, ctx->stream));
   for (size_t base = 0; base < want.size(); base += 32) {
     uint32_t n = (uint32_t)std::min<size_t>(32, want.size() - base);
     StatParams S{};
     S.slab = sd.slab;
     S.nrows = sd.nrows;
     S.ncols = n;
-    std::vector<unsigned long long> init(2 * n);
     for (uint32_t i = 0; i < n; ++i) {
       const ColInfo &ci = t->cols[want[base + i]];
       S.cols[i].off = ci.off_per_row * sd.cap;
       S.cols[i].width = ci.width;
       S.cols[i].sext = ci.sext;
       S.cols[i].type = ci.type;
-      init[2 * i] = ~0ull;
-      init[2 * i + 1] = 0;
+      S.cols[i].pad = want[base + i];  // output slot = schema column
     }
-    unsigned long long *d_out = scratch.alloc<unsigned long long>(2 * n);
-    CUDA_CK(cudaMemcpyAsync(d_out, init.data(), init.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
     S.out = d_out;
-    dim3 grid(grid_for(sd.nrows, 256, ctx->sm_count, 4), n);
+    dim3 grid(grid_for(sd.nrows, 256, ctx->sm_count, 2), n);
     column_minmax_kernel<<<grid, 256, 0, ctx->stream>>>(S);
     CUDA_CK(cudaGetLastError());
-    CUDA_CK(cudaMemcpyAsync(init.data(), d_out, init.size() * 8, cudaMemcpyDeviceToHost, ctx->stream));
-    CUDA_CK(cudaStreamSynchronize(ctx->stream));
-    for (uint32_t i = 0; i < n; ++i) {
-      sd.omin[want[base + i]] = init[2 * i];
-      sd.omax[want[base + i]] = init[2 * i + 1];
+  }
+  sd.stats_pending = true;
+}
+
+// one batched read-back for every segment whose statistics are still on the device
+void fetch_stats(vgpu_table *t) {
+  const size_t ncols = t->cols.size();
+  size_t lo = t->segs.size(), hi = 0;
+  for (size_t s = 0; s < t->segs.size(); ++s)
+    if (t->segs[s].stats_pending) { lo = std::min(lo, s); hi = std::max(hi, s + 1); }
+  if (lo >= hi) return;
+  std::vector<unsigned long long> h((hi - lo) * 2 * ncols);
+  CUDA_CK(cudaMemcpyAsync(h.data(), t->d_stats + lo * 2 * ncols, h.size() * sizeof(unsigned long long),
+                          cudaMemcpyDeviceToHost, t->ctx->stream));
+  CUDA_CK(cudaStreamSynchronize(t->ctx->stream));
+  for (size_t s = lo; s < hi; ++s) {
+    SegmentData &sd = t->segs[s];
+    if (!sd.stats_pending) continue;
+    for (size_t c = 0; c < ncols; ++c) {
+      sd.omin[c] = h[(s - lo) * 2 * ncols + 2 * c];
+      sd.omax[c] = h[(s - lo) * 2 * ncols + 2 * c + 1];
     }
+    sd.stats_pending = false;
   }
 }
 
@@ -462,7 +506,7 @@ void upload_descs(vgpu_table *t) {
     h[i].cap = sd.cap;
     for (int b = 0; b < kMaxBitsetCols; ++b) {
       h[i].bs_values[b] = sd.bs_values[b];
-      h[i].bs_offsets[b] = sd.bs_offsets[b];
+      h[i].bs_offsets[b] = sd.bs_has_offsets[b] ? sd.bs_offsets[b] : nullptr;
     }
   }
   if (n) {
@@ -1038,6 +1082,8 @@ void vgpu_table_free(vgpu_table *table) {
   cudaStreamSynchronize(table->ctx->stream);
   for (auto &sd : table->segs) free_segment(sd);
   if (table->d_segs) cudaFree(table->d_segs);
+  if (table->d_stats) cudaFree(table->d_stats);
+  if (table->h_stats_init) cudaFreeHost(table->h_stats_init);
   delete table;
 }
 
@@ -1071,8 +1117,14 @@ int vgpu_segment_put(vgpu_table *t, uint32_t seg_idx, uint64_t nrows, const void
         }
         // values padded to a whole tile so that speculative reads stay in bounds
         uint64_t vcap = round_up(std::max<uint64_t>(nvalues, 1), kTileRows);
-        CUDA_CK(cudaMalloc(&sd.bs_values[ci.bitset_idx], vcap * 4));
-        CUDA_CK(cudaMemsetAsync(sd.bs_values[ci.bitset_idx], 0, vcap * 4, ctx->stream));
+        if (sd.bs_vcap[ci.bitset_idx] < vcap) {
+          if (sd.bs_values[ci.bitset_idx]) cudaFree(sd.bs_values[ci.bitset_idx]);
+          sd.bs_values[ci.bitset_idx] = nullptr;
+          CUDA_CK(cudaMalloc(&sd.bs_values[ci.bitset_idx], vcap * 4));
+          sd.bs_vcap[ci.bitset_idx] = vcap;
+        }
+        if (sd.bs_vcap[ci.bitset_idx] > nvalues)
+          CUDA_CK(cudaMemsetAsync(sd.bs_values[ci.bitset_idx] + nvalues, 0, (sd.bs_vcap[ci.bitset_idx] - nvalues) * 4, ctx->stream));
         if (nvalues)
           CUDA_CK(cudaMemcpyAsync(sd.bs_values[ci.bitset_idx], csr->values, nvalues * 4,
                                   cudaMemcpyHostToDevice, ctx->stream));
@@ -1081,9 +1133,17 @@ int vgpu_segment_put(vgpu_table *t, uint32_t seg_idx, uint64_t nrows, const void
           keep.emplace_back(nrows + 1);
           auto &o32 = keep.back();
           for (uint64_t r = 0; r <= nrows; ++r) o32[r] = (uint32_t)csr->offsets[r];
-          CUDA_CK(cudaMalloc(&sd.bs_offsets[ci.bitset_idx], (nrows + 1) * 4));
+          if (sd.bs_ocap[ci.bitset_idx] < nrows + 1) {
+            if (sd.bs_offsets[ci.bitset_idx]) cudaFree(sd.bs_offsets[ci.bitset_idx]);
+            sd.bs_offsets[ci.bitset_idx] = nullptr;
+            CUDA_CK(cudaMalloc(&sd.bs_offsets[ci.bitset_idx], (nrows + 1) * 4));
+            sd.bs_ocap[ci.bitset_idx] = nrows + 1;
+          }
           CUDA_CK(cudaMemcpyAsync(sd.bs_offsets[ci.bitset_idx], o32.data(), (nrows + 1) * 4,
                                   cudaMemcpyHostToDevice, ctx->stream));
+          sd.bs_has_offsets[ci.bitset_idx] = true;
+        } else {
+          sd.bs_has_offsets[ci.bitset_idx] = false;
         }
         continue;
       }
@@ -1095,8 +1155,8 @@ int vgpu_segment_put(vgpu_table *t, uint32_t seg_idx, uint64_t nrows, const void
       if (sd.cap > nrows)
         CUDA_CK(cudaMemsetAsync(dst + nrows * ci.width, 0, (sd.cap - nrows) * ci.width, ctx->stream));
     }
-    CUDA_CK(cudaStreamSynchronize(ctx->stream));
-    compute_stats(t, sd);
+    compute_stats(t, seg_idx);
+    CUDA_CK(cudaStreamSynchronize(ctx->stream));  // host buffers may be reused by the caller now
     sd.valid = true;
   });
 }
@@ -1135,8 +1195,14 @@ int vgpu_segment_generate(vgpu_table *t, uint32_t seg_idx, uint64_t nrows, const
       gc.bitset_out = nullptr;
       if (ci.bitset) {
         uint64_t vcap = round_up(std::max<uint64_t>(nrows, 1), kTileRows);
-        CUDA_CK(cudaMalloc(&sd.bs_values[ci.bitset_idx], vcap * 4));
-        CUDA_CK(cudaMemsetAsync(sd.bs_values[ci.bitset_idx], 0, vcap * 4, ctx->stream));
+        if (sd.bs_vcap[ci.bitset_idx] < vcap) {
+          if (sd.bs_values[ci.bitset_idx]) cudaFree(sd.bs_values[ci.bitset_idx]);
+          sd.bs_values[ci.bitset_idx] = nullptr;
+          CUDA_CK(cudaMalloc(&sd.bs_values[ci.bitset_idx], vcap * 4));
+          sd.bs_vcap[ci.bitset_idx] = vcap;
+        }
+        CUDA_CK(cudaMemsetAsync(sd.bs_values[ci.bitset_idx], 0, sd.bs_vcap[ci.bitset_idx] * 4, ctx->stream));
+        sd.bs_has_offsets[ci.bitset_idx] = false;
         sd.bs_n[ci.bitset_idx] = nrows;
         gc.bitset_out = sd.bs_values[ci.bitset_idx];
       }
@@ -1145,8 +1211,7 @@ int vgpu_segment_generate(vgpu_table *t, uint32_t seg_idx, uint64_t nrows, const
       generate_kernel<<<grid_for(nrows, 256, ctx->sm_count), 256, 0, ctx->stream>>>(G);
       CUDA_CK(cudaGetLastError());
     }
-    CUDA_CK(cudaStreamSynchronize(ctx->stream));
-    compute_stats(t, sd);
+    compute_stats(t, seg_idx);
     sd.valid = true;
   });
 }
@@ -1205,7 +1270,7 @@ uint64_t vgpu_table_bytes(const vgpu_table *t) {
     n += sd.cap * t->row_bytes;
     for (int b = 0; b < kMaxBitsetCols; ++b) {
       n += sd.bs_n[b] * 4;
-      if (sd.bs_offsets[b]) n += (sd.nrows + 1) * 4;
+      if (sd.bs_has_offsets[b]) n += (sd.nrows + 1) * 4;
     }
   }
   return n;
@@ -1551,6 +1616,7 @@ int vgpu_query_agg(vgpu_table *t, const vgpu_plan *plan, vgpu_result **out) {
     cudaStream_t stream = ctx->stream;
     validate_plan(t, plan);
 
+    fetch_stats(t);
     QueryRun q(t, plan);
     Planner &pl = q.planner;
     ScanParams &P = pl.P;
