@@ -286,6 +286,38 @@ __device__ __forceinline__ uint64_t hash_cell(const ScanParams &P, uint64_t key)
   return kEmptyKey;
 }
 
+// Key tuples that do not pack into 64 bits (e.g. a float next to a double dimension,
+// test/aggregation.cc NumericDimensions): one word per key, slots claimed through a state word.
+// 0 free -> 1 being written -> 2 ready; readers of a slot in state 1 wait for the writer (Volta+
+// independent thread scheduling makes the intra-warp case safe).
+__device__ __noinline__ uint64_t wide_cell(const ScanParams &P, const uint64_t *kw) {
+  uint64_t h = 0x9e3779b97f4a7c15ull;
+  for (uint32_t k = 0; k < P.nkeys; ++k) h = mix64(h ^ kw[k]);
+  uint64_t slot = h & P.hmask;
+  for (uint32_t probe = 0; probe < P.max_probe; ++probe) {
+    while (true) {
+      uint32_t st = *reinterpret_cast<volatile uint32_t *>(P.wstate + slot);
+      if (st == 0) {
+        if (atomicCAS(P.wstate + slot, 0u, 1u) == 0u) {
+          for (uint32_t k = 0; k < P.nkeys; ++k) P.wkeys[slot * P.nkeys + k] = kw[k];
+          __threadfence();
+          atomicExch(P.wstate + slot, 2u);
+          return slot;
+        }
+        continue;  // somebody else claimed it: look again
+      }
+      if (st == 2) break;
+    }
+    __threadfence();
+    bool same = true;
+    for (uint32_t k = 0; k < P.nkeys; ++k)
+      same = same && (*reinterpret_cast<volatile uint64_t *>(P.wkeys + slot * P.nkeys + k) == kw[k]);
+    if (same) return slot;
+    slot = (slot + 1) & P.hmask;
+  }
+  return kEmptyKey;
+}
+
 // ---------------------------------------------------------------------------------------------
 // count-distinct: dedupe (cell,id) pairs in an open-addressing set, count new ones per cell
 // ---------------------------------------------------------------------------------------------
@@ -461,6 +493,8 @@ struct ExtractParams {
   uint32_t nkeys, nmets;
   const uint64_t *hkeys;
   const uint8_t *present;
+  const uint32_t *wstate;
+  const uint64_t *wkeys;
   ExtractKey keys[kMaxKeys];
   ExtractMet mets[kMaxMetrics + 1];
   unsigned long long *counter;  // number of groups
@@ -471,6 +505,10 @@ __device__ __forceinline__ bool cell_present(const ExtractParams &E, uint64_t c,
   if (!E.hash_mode) {
     packed = c;
     return E.present[c] != 0;
+  }
+  if (E.hash_mode == 2) {
+    packed = c;
+    return c + 1 < E.ncells && E.wstate[c] == 2u;
   }
   if (c == E.ncells - 1) {
     packed = kEmptyKey;
@@ -497,9 +535,14 @@ extract_groups_kernel(const __grid_constant__ ExtractParams E) {
     uint64_t pos = base + __popc(ballot & ((1u << lane) - 1));
     for (uint32_t k = 0; k < E.nkeys; ++k) {
       const ExtractKey &ek = E.keys[k];
-      uint64_t q = packed / ek.div;
-      if (ek.mod) q %= ek.mod;
-      uint64_t v = ek.lo + q;
+      uint64_t v;
+      if (E.hash_mode == 2) {
+        v = E.wkeys[c * E.nkeys + k];
+      } else {
+        uint64_t q = packed / ek.div;
+        if (ek.mod) q %= ek.mod;
+        v = ek.lo + q;
+      }
       switch (ek.width) {
         case 1: reinterpret_cast<uint8_t *>(ek.out)[pos] = (uint8_t)v; break;
         case 2: reinterpret_cast<uint16_t *>(ek.out)[pos] = (uint16_t)v; break;

@@ -193,6 +193,22 @@ __device__ __forceinline__ int dset_insert(uint64_t *set, uint64_t mask, uint32_
   return 2;
 }
 
+// Wide key tuples (hash_mode 2): gather the key words of one row and find / claim its slot. Out of line
+// so that its local array does not cost the common paths registers.
+__device__ __noinline__ uint64_t wide_row_cell(const ScanParams &P, const SegDesc &seg, uint32_t row) {
+  uint64_t kw[kMaxKeys];
+  for (uint32_t k = 0; k < P.nkeys; ++k) {
+    const KeySpec &ks = P.keys[k];
+    const Slot &sl = P.slots[ks.slot];
+    const uint8_t *a = seg.slab + sl.off * seg.cap + (uint64_t)row * sl.width;
+    uint64_t val = gather_finish(gather_raw64(a), a, sl.vmask, sl.signbit);
+    if (ks.rollup) val = rollup_value(val, ks);
+    if (ks.fzero && ((val << 1) == 0 || (sl.width == 4 && (uint32_t)(val << 1) == 0))) val = 0;  // -0.0 == +0.0
+    kw[k] = val;
+  }
+  return wide_cell(P, kw);
+}
+
 // ---------------------------------------------------------------------------------------------
 // the fused scan kernel
 // ---------------------------------------------------------------------------------------------
@@ -299,7 +315,7 @@ scan_filter_groupby_kernel(const __grid_constant__ ScanParams P) {
 
     // ---- aggregate: one passing row per lane ----
     // fast path: up to 4 keys of at most 4 bytes and up to 4 metrics, staged in 12 registers
-    const bool small_plan = P.small_plan != 0;  // uniform
+    const bool small_plan = P.small_plan != 0 && P.hash_mode != 2;  // uniform
     for (uint32_t i = lane; i < total; i += 32) {
       const uint32_t row = chunk_row + list[i];
       uint32_t kv[4];
@@ -329,7 +345,9 @@ scan_filter_groupby_kernel(const __grid_constant__ ScanParams P) {
         }
       }
       uint64_t packed = 0;
-      if (small_plan) {
+      if (P.hash_mode == 2) {
+        packed = wide_row_cell(P, seg, row);  // rare path, out of line
+      } else if (small_plan) {
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
           if (k < P.nkeys) {
@@ -352,7 +370,13 @@ scan_filter_groupby_kernel(const __grid_constant__ ScanParams P) {
         }
       }
       uint64_t cell;
-      if (P.hash_mode) {
+      if (P.hash_mode == 2) {
+        cell = packed;
+        if (cell == kEmptyKey) {
+          atomicOr(&P.counters[1], 1ull);
+          continue;
+        }
+      } else if (P.hash_mode) {
         cell = hash_cell(P, packed);
         if (cell == kEmptyKey) {
           atomicOr(&P.counters[1], 1ull);

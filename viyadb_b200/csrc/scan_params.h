@@ -70,7 +70,8 @@ struct KeySpec {
   uint8_t nrules;
   uint8_t rule_unit[kMaxRules];  // vgpu_time_unit
   uint8_t query_unit;            // vgpu_time_unit or VGPU_TU_NONE
-  uint8_t pad[3];
+  uint8_t fzero;                 // floating-point key: -0.0 groups with +0.0 (KeyEqual uses ==, store.cc:46-63)
+  uint8_t pad[2];
   uint64_t rule_boundary[kMaxRules];
   uint64_t lo;    // subtracted from the (rolled-up) value
   uint64_t mul;   // cell index / packed key = sum (v - lo) * mul
@@ -125,11 +126,14 @@ struct ScanParams {
 
   // group keys
   uint32_t nkeys;
-  uint32_t hash_mode;      // 0: dense cells, 1: open-addressing hash on the packed 64-bit key
+  uint32_t hash_mode;      // 0: dense cells, 1: open-addressing hash on the packed 64-bit key,
+                           // 2: open-addressing hash on the full key tuple (one 64-bit word per key)
   KeySpec keys[kMaxKeys];
   uint64_t *hkeys;         // hash_mode: capacity cells, EMPTY = ~0
   uint64_t hmask;          // capacity - 1
   uint8_t *present;        // dense: 1 byte per cell; hash: present[0] flags the sentinel key
+  uint32_t *wstate;        // wide mode: 0 free, 1 being written, 2 ready
+  uint64_t *wkeys;         // wide mode: capacity x nkeys words
   uint32_t max_probe;
 
   // metrics

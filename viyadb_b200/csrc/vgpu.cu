@@ -1294,6 +1294,7 @@ struct QueryRun {
   uint64_t active_rows = 0;
   uint64_t scanned_recs = 0;
   bool hash_mode = false;
+  bool wide = false;  // hash on the full key tuple
   uint64_t ncells = 0;  // dense cells, or hash capacity (power of two)
 
   QueryRun(vgpu_table *table, const vgpu_plan *p) : t(table), plan(p), planner(table, p) {}
@@ -1735,17 +1736,21 @@ int vgpu_query_agg(vgpu_table *t, const vgpu_plan *plan, vgpu_result **out) {
       cells128 *= range128(r);
       if (cells128 > ((unsigned __int128)1 << 64) - 2) { fits64 = false; break; }
     }
-    if (!fits64) fail(VGPU_ERR_UNSUPPORTED, "group key does not pack into 64 bits");
-    const uint64_t cells = (uint64_t)cells128;
+    const bool wide = !fits64;  // key tuple wider than 64 bits: hash on the full tuple
+    if (wide && ctx->nranks > 1) fail(VGPU_ERR_UNSUPPORTED, "multi-GPU merge of key tuples wider than 64 bits is not implemented yet");
+    if (wide && (plan->flags & VGPU_PLAN_FORCE_DENSE)) fail(VGPU_ERR_UNSUPPORTED, "key domain too large for a dense group table");
+    const uint64_t cells = wide ? ~0ull : (uint64_t)cells128;
     uint64_t dense_limit = std::min<uint64_t>(std::max<uint64_t>(4 * global_active_rows, 1ull << 22), 1ull << 28);
     if (P.ndistinct) dense_limit = std::min<uint64_t>(dense_limit, 0xffffffffull);
-    bool dense = cells <= dense_limit;
+    bool dense = !wide && cells <= dense_limit;
     if (plan->flags & VGPU_PLAN_FORCE_HASH) dense = false;
     if (plan->flags & VGPU_PLAN_FORCE_DENSE) {
       if (cells > (1ull << 30)) fail(VGPU_ERR_UNSUPPORTED, "key domain too large for a dense group table");
       dense = true;
     }
     q.hash_mode = !dense;
+    q.wide = wide;
+    for (uint32_t k = 0; k < plan->nkeys; ++k) P.keys[k].fzero = wide && type_float(t->cols[plan->keys[k].col].type);
     if (ctx->trace) {
       fprintf(stderr, "[vgpu r%d] cells=%llu dense_limit=%llu dense=%d active_rows=%llu global=%llu\n", ctx->rank, (unsigned long long)cells, (unsigned long long)dense_limit, (int)dense, (unsigned long long)q.active_rows, (unsigned long long)global_active_rows);
       for (uint32_t k = 0; k < plan->nkeys; ++k) fprintf(stderr, "[vgpu r%d]   key %u lo=%llu range=%llu kmin=%llu kmax=%llu\n", ctx->rank, k, (unsigned long long)q.ranges[k].lo, (unsigned long long)q.ranges[k].range, (unsigned long long)kmin[k], (unsigned long long)kmax[k]);
@@ -1801,7 +1806,7 @@ int vgpu_query_agg(vgpu_table *t, const vgpu_plan *plan, vgpu_result **out) {
       Scratch scratch(stream);
       q.ncells = q.hash_mode ? hash_cap : cells;
       const uint64_t acc_cells = q.hash_mode ? hash_cap + 1 : cells;  // + the all-ones-key cell
-      P.hash_mode = q.hash_mode;
+      P.hash_mode = q.wide ? 2u : (q.hash_mode ? 1u : 0u);
       P.max_probe = 512;
       // The group table (keys / present flags / accumulators) is ONE contiguous block so that one L2
       // access-policy window can pin it: the column stream flowing through L2 otherwise evicts the
@@ -1809,12 +1814,22 @@ int vgpu_query_agg(vgpu_table *t, const vgpu_plan *plan, vgpu_result **out) {
       // traffic at 5e5 groups, profiles/r1_explore_c2.txt).
       uint64_t block_bytes = 0;
       auto carve = [&](uint64_t bytes) { uint64_t o = block_bytes; block_bytes += round_up(bytes, 256); return o; };
-      const uint64_t o_hkeys = q.hash_mode ? carve(hash_cap * 8) : 0;
+      const uint64_t o_hkeys = (q.hash_mode && !q.wide) ? carve(hash_cap * 8) : 0;
+      const uint64_t o_wstate = q.wide ? carve(hash_cap * 4) : 0;
+      const uint64_t o_wkeys = q.wide ? carve(hash_cap * 8 * std::max<uint32_t>(plan->nkeys, 1)) : 0;
       const uint64_t o_present = carve(q.hash_mode ? 16 : acc_cells);
       std::vector<uint64_t> o_acc(q.accs.size());
       for (size_t m = 0; m < q.accs.size(); ++m) o_acc[m] = carve(acc_cells * q.accs[m].acc_width);
       uint8_t *block = scratch.alloc<uint8_t>(block_bytes);
-      if (q.hash_mode) {
+      if (q.wide) {
+        P.hkeys = nullptr;
+        P.hmask = hash_cap - 1;
+        P.wstate = reinterpret_cast<uint32_t *>(block + o_wstate);
+        P.wkeys = reinterpret_cast<uint64_t *>(block + o_wkeys);
+        CUDA_CK(cudaMemsetAsync(P.wstate, 0, hash_cap * 4, stream));
+        P.present = block + o_present;
+        CUDA_CK(cudaMemsetAsync(P.present, 0, 16, stream));
+      } else if (q.hash_mode) {
         P.hkeys = reinterpret_cast<uint64_t *>(block + o_hkeys);
         P.hmask = hash_cap - 1;
         fill64(stream, ctx->sm_count, P.hkeys, hash_cap, kEmptyKey);
@@ -1918,11 +1933,13 @@ int vgpu_query_agg(vgpu_table *t, const vgpu_plan *plan, vgpu_result **out) {
       // ---- extract the groups ----
       ExtractParams E{};
       E.ncells = acc_cells_x;
-      E.hash_mode = q.hash_mode;
+      E.hash_mode = q.wide ? 2u : (q.hash_mode ? 1u : 0u);
       E.nkeys = plan->nkeys;
       E.nmets = (uint32_t)q.accs.size();
       E.hkeys = P.hkeys;
       E.present = P.present;
+      E.wstate = P.wstate;
+      E.wkeys = P.wkeys;
       unsigned long long *d_ngroups = ctx->d_counters + 12;
       E.counter = d_ngroups;
       uint64_t bound = std::min<uint64_t>(acc_cells_x, passed);
@@ -2002,7 +2019,7 @@ int vgpu_query_agg(vgpu_table *t, const vgpu_plan *plan, vgpu_result **out) {
       view.gpu_ms = total_ms;
       view.scan_ms = scan_ms_total;
       view.launches = launches;
-      view.table_mode = q.hash_mode ? 1 : 0;
+      view.table_mode = q.wide ? 2 : (q.hash_mode ? 1 : 0);
       view.table_cells = q.ncells;
       break;
     }
