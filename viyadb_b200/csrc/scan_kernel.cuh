@@ -29,6 +29,7 @@ namespace vgpu {
 constexpr int kChunkRows = 512;                 // rows per warp iteration
 constexpr int kSubChunk = kChunkRows / kSub;    // 128
 constexpr int kWarps = kThreads / 32;
+constexpr int kListCap = kChunkRows + 32;       // a chunk's worth of rows plus one incomplete batch
 static_assert(kVec * 32 == kSubChunk, "a lane owns kVec consecutive rows of every sub-chunk");
 static_assert(kTileRows % kChunkRows == 0, "slab capacity is a whole number of chunks");
 
@@ -217,16 +218,128 @@ __device__ __noinline__ uint64_t wide_row_cell(const ScanParams &P, const SegDes
 #endif
 __global__ void __launch_bounds__(kThreads, VGPU_MIN_CTAS)
 scan_filter_groupby_kernel(const __grid_constant__ ScanParams P) {
-  __shared__ uint16_t s_list[kWarps][kChunkRows];
+  __shared__ uint2 s_list[kWarps][kListCap];  // (segment index, row) of passing rows waiting for aggregation
 
   const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  uint16_t *list = s_list[warp];
+  uint2 *list = s_list[warp];
+  uint32_t npend = 0;  // rows waiting in the list (warp-uniform)
   uint32_t my_passed = 0;
   uint32_t ins0 = 0, ins1 = 0;  // pairs this lane added to the count-distinct sets
   static_assert(kMaxDistinct == 2, "two insert counters");
   const bool can_overflow = P.hash_mode || P.ndistinct;
   const uint64_t pol = make_stream_policy((P.tune & 2u) != 0);
   const uint64_t tpol = make_table_policy((P.tune & 4u) != 0);
+
+  // ---- aggregate one passing row (one row per lane, rows may come from different segments) ----
+  // fast path: up to 4 keys of at most 4 bytes and up to 4 metrics, staged in 12 registers
+  const bool small_plan = P.small_plan != 0 && P.hash_mode != 2;  // uniform
+  auto process_row = [&](const SegDesc &seg, const uint32_t row) {
+    uint32_t kv[4];
+    uint64_t mv[4];
+    if (small_plan) {
+      // one DRAM round trip per row: every key and metric cell (or the first word a bitset cell
+      // needs) is requested before anything depends on it; branch-free and fully unrolled, so the
+      // loads issue back to back and the values stay in registers. Slab and side-table bases are
+      // 8-byte aligned, so the position of a cell inside its aligned word depends on the row only.
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        if (k < P.nkeys) {
+          const Slot &sl = P.slots[P.keys[k].slot];
+          kv[k] = gather_raw32(seg.slab + sl.off * seg.cap + (uint64_t)row * sl.width);
+        }
+      }
+#pragma unroll
+      for (int m = 0; m < 4; ++m) {
+        if (m < P.nmetrics) {
+          const Slot &sl = P.slots[P.mets[m].slot];
+          const uint32_t *off = seg.bs_offsets[sl.bitset_idx];
+          const uint32_t *vals = seg.bs_values[sl.bitset_idx];
+          const uint8_t *fixed = seg.slab + sl.off * seg.cap + (uint64_t)row * sl.width;
+          const uint8_t *bits = reinterpret_cast<const uint8_t *>((off == nullptr ? vals : off) + row);
+          mv[m] = gather_raw64(sl.bitset ? bits : fixed);
+        }
+      }
+    }
+    uint64_t packed = 0;
+    if (P.hash_mode == 2) {
+      packed = wide_row_cell(P, seg, row);  // rare path, out of line
+    } else if (small_plan) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        if (k < P.nkeys) {
+          const KeySpec &ks = P.keys[k];
+          const Slot &sl = P.slots[ks.slot];
+          uint64_t val = ((uint64_t)(kv[k] >> ((((uint32_t)row * sl.width) & 3u) * 8u))) & sl.vmask;
+          val = (val ^ sl.signbit) - sl.signbit;
+          if (ks.rollup) val = rollup_value(val, ks);
+          packed += (val - ks.lo) * ks.mul;
+        }
+      }
+    } else {
+      for (uint32_t k = 0; k < P.nkeys; ++k) {
+        const KeySpec &ks = P.keys[k];
+        const Slot &sl = P.slots[ks.slot];
+        const uint8_t *a = seg.slab + sl.off * seg.cap + (uint64_t)row * sl.width;
+        uint64_t val = gather_finish(gather_raw64(a), a, sl.vmask, sl.signbit);
+        if (ks.rollup) val = rollup_value(val, ks);
+        packed += (val - ks.lo) * ks.mul;
+      }
+    }
+    uint64_t cell;
+    if (P.hash_mode == 2) {
+      cell = packed;
+      if (cell == kEmptyKey) {
+        atomicOr(&P.counters[1], 1ull);
+        return;
+      }
+    } else if (P.hash_mode) {
+      cell = hash_cell(P, packed);
+      if (cell == kEmptyKey) {
+        atomicOr(&P.counters[1], 1ull);
+        return;
+      }
+    } else {
+      cell = packed;
+      if (!(P.tune & 8u)) st_u8_hint(P.present + cell, 1u, tpol);
+    }
+    uint32_t dn = 0;
+    for (uint32_t m = 0; m < P.nmetrics; ++m) {
+      const MetSpec &ms = P.mets[m];
+      const Slot &sl = P.slots[ms.slot];
+      uint64_t pre;
+      if (small_plan) {
+        const uint64_t raw = m == 0 ? mv[0] : m == 1 ? mv[1] : m == 2 ? mv[2] : mv[3];
+        pre = (raw >> ((((uint32_t)row * sl.width) & 7u) * 8u)) & sl.vmask;
+        pre = (pre ^ sl.signbit) - sl.signbit;
+      } else {
+        const uint32_t *off = seg.bs_offsets[sl.bitset_idx];
+        const uint8_t *a = sl.bitset ? reinterpret_cast<const uint8_t *>((off == nullptr ? seg.bs_values[sl.bitset_idx] : off) + row)
+                                     : seg.slab + sl.off * seg.cap + (uint64_t)row * sl.width;
+        pre = gather_finish(gather_raw64(a), a, sl.vmask, sl.signbit);
+      }
+      if (ms.op != A_DISTINCT) {
+        if (P.tune & 16u) { if (ms.op == A_MINS32) atomicMin(reinterpret_cast<int *>(ms.acc) + cell, (int)pre); else if (ms.op == A_MAXS32) atomicMax(reinterpret_cast<int *>(ms.acc) + cell, (int)pre); }
+        else acc_update(ms.acc, cell, ms.op, pre, tpol);
+        continue;
+      }
+      const uint32_t *off = seg.bs_offsets[sl.bitset_idx];
+      const uint32_t *vals = seg.bs_values[sl.bitset_idx];
+      uint32_t *distinct = reinterpret_cast<uint32_t *>(ms.acc);
+      if (off == nullptr) {  // one id per row: `pre` is the id
+        int r = dset_insert(P.dset[dn], P.dset_mask[dn], P.max_probe, (cell << 32) | pre);
+        if (r == 1) { red_add_u32(distinct + cell, 1u, tpol); if (dn == 0) ++ins0; else ++ins1; }
+        else if (r == 2) atomicOr(&P.counters[1], 2ull);
+      } else {               // CSR cell: `pre` is offsets[row]
+        const uint32_t lo = (uint32_t)pre, hi = gather_u32(off + row + 1);
+        for (uint32_t q = lo; q < hi; ++q) {
+          int r = dset_insert(P.dset[dn], P.dset_mask[dn], P.max_probe, (cell << 32) | (uint64_t)gather_u32(vals + q));
+          if (r == 1) { red_add_u32(distinct + cell, 1u, tpol); if (dn == 0) ++ins0; else ++ins1; }
+          else if (r == 2) { atomicOr(&P.counters[1], 2ull); break; }
+        }
+      }
+      ++dn;
+    }
+  };
 
   // chunk -> (active segment, chunk inside it), advanced incrementally: no 64-bit division per chunk
   const uint32_t cps = P.tiles_per_seg;
@@ -242,7 +355,8 @@ scan_filter_groupby_kernel(const __grid_constant__ ScanParams P) {
     // this warp's next chunk (also the prefetch target)
     uint32_t nsi = si + step_seg, nci = ci + step_chunk;
     if (nci >= cps) { nci -= cps; ++nsi; }
-    const SegDesc &seg = P.segs[P.active[si]];
+    const uint32_t seg_index = P.active[si];
+    const SegDesc &seg = P.segs[seg_index];
     const uint32_t nrows = (uint32_t)seg.nrows;
     const uint32_t chunk_row = ci * kChunkRows;
     si = nsi;
@@ -306,125 +420,38 @@ scan_filter_groupby_kernel(const __grid_constant__ ScanParams P) {
         uint32_t nib = (mask >> (4 * s)) & 0xfu;
 #pragma unroll
         for (int j = 0; j < kVec; ++j) {
-          if (nib & (1u << j)) list[pos++] = (uint16_t)(s * kSubChunk + lane * kVec + j);
+          if (nib & (1u << j)) list[npend + pos++] = make_uint2(seg_index, chunk_row + s * kSubChunk + lane * kVec + j);
         }
         base += (s == 0) ? t0 : (s == 1) ? t1 : (s == 2) ? t2 : t3;
       }
     }
     __syncwarp();
+    npend += total;
 
-    // ---- aggregate: one passing row per lane ----
-    // fast path: up to 4 keys of at most 4 bytes and up to 4 metrics, staged in 12 registers
-    const bool small_plan = P.small_plan != 0 && P.hash_mode != 2;  // uniform
-    for (uint32_t i = lane; i < total; i += 32) {
-      const uint32_t row = chunk_row + list[i];
-      uint32_t kv[4];
-      uint64_t mv[4];
-      if (small_plan) {
-        // one DRAM round trip per row: every key and metric cell (or the first word a bitset cell
-        // needs) is requested before anything depends on it; branch-free and fully unrolled, so the
-        // loads issue back to back and the values stay in registers. Slab and side-table bases are
-        // 8-byte aligned, so the position of a cell inside its aligned word depends on the row only.
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          if (k < P.nkeys) {
-            const Slot &sl = P.slots[P.keys[k].slot];
-            kv[k] = gather_raw32(seg.slab + sl.off * seg.cap + (uint64_t)row * sl.width);
-          }
-        }
-#pragma unroll
-        for (int m = 0; m < 4; ++m) {
-          if (m < P.nmetrics) {
-            const Slot &sl = P.slots[P.mets[m].slot];
-            const uint32_t *off = seg.bs_offsets[sl.bitset_idx];
-            const uint32_t *vals = seg.bs_values[sl.bitset_idx];
-            const uint8_t *fixed = seg.slab + sl.off * seg.cap + (uint64_t)row * sl.width;
-            const uint8_t *bits = reinterpret_cast<const uint8_t *>((off == nullptr ? vals : off) + row);
-            mv[m] = gather_raw64(sl.bitset ? bits : fixed);
-          }
-        }
-      }
-      uint64_t packed = 0;
-      if (P.hash_mode == 2) {
-        packed = wide_row_cell(P, seg, row);  // rare path, out of line
-      } else if (small_plan) {
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          if (k < P.nkeys) {
-            const KeySpec &ks = P.keys[k];
-            const Slot &sl = P.slots[ks.slot];
-            uint64_t val = ((uint64_t)(kv[k] >> ((((uint32_t)row * sl.width) & 3u) * 8u))) & sl.vmask;
-            val = (val ^ sl.signbit) - sl.signbit;
-            if (ks.rollup) val = rollup_value(val, ks);
-            packed += (val - ks.lo) * ks.mul;
-          }
-        }
-      } else {
-        for (uint32_t k = 0; k < P.nkeys; ++k) {
-          const KeySpec &ks = P.keys[k];
-          const Slot &sl = P.slots[ks.slot];
-          const uint8_t *a = seg.slab + sl.off * seg.cap + (uint64_t)row * sl.width;
-          uint64_t val = gather_finish(gather_raw64(a), a, sl.vmask, sl.signbit);
-          if (ks.rollup) val = rollup_value(val, ks);
-          packed += (val - ks.lo) * ks.mul;
-        }
-      }
-      uint64_t cell;
-      if (P.hash_mode == 2) {
-        cell = packed;
-        if (cell == kEmptyKey) {
-          atomicOr(&P.counters[1], 1ull);
-          continue;
-        }
-      } else if (P.hash_mode) {
-        cell = hash_cell(P, packed);
-        if (cell == kEmptyKey) {
-          atomicOr(&P.counters[1], 1ull);
-          continue;
-        }
-      } else {
-        cell = packed;
-        if (!(P.tune & 8u)) st_u8_hint(P.present + cell, 1u, tpol);
-      }
-      uint32_t dn = 0;
-      for (uint32_t m = 0; m < P.nmetrics; ++m) {
-        const MetSpec &ms = P.mets[m];
-        const Slot &sl = P.slots[ms.slot];
-        uint64_t pre;
-        if (small_plan) {
-          const uint64_t raw = m == 0 ? mv[0] : m == 1 ? mv[1] : m == 2 ? mv[2] : mv[3];
-          pre = (raw >> ((((uint32_t)row * sl.width) & 7u) * 8u)) & sl.vmask;
-          pre = (pre ^ sl.signbit) - sl.signbit;
-        } else {
-          const uint32_t *off = seg.bs_offsets[sl.bitset_idx];
-          const uint8_t *a = sl.bitset ? reinterpret_cast<const uint8_t *>((off == nullptr ? seg.bs_values[sl.bitset_idx] : off) + row)
-                                       : seg.slab + sl.off * seg.cap + (uint64_t)row * sl.width;
-          pre = gather_finish(gather_raw64(a), a, sl.vmask, sl.signbit);
-        }
-        if (ms.op != A_DISTINCT) {
-          if (P.tune & 16u) { if (ms.op == A_MINS32) atomicMin(reinterpret_cast<int *>(ms.acc) + cell, (int)pre); else if (ms.op == A_MAXS32) atomicMax(reinterpret_cast<int *>(ms.acc) + cell, (int)pre); }
-          else acc_update(ms.acc, cell, ms.op, pre, tpol);
-          continue;
-        }
-        const uint32_t *off = seg.bs_offsets[sl.bitset_idx];
-        const uint32_t *vals = seg.bs_values[sl.bitset_idx];
-        uint32_t *distinct = reinterpret_cast<uint32_t *>(ms.acc);
-        if (off == nullptr) {  // one id per row: `pre` is the id
-          int r = dset_insert(P.dset[dn], P.dset_mask[dn], P.max_probe, (cell << 32) | pre);
-          if (r == 1) { red_add_u32(distinct + cell, 1u, tpol); if (dn == 0) ++ins0; else ++ins1; }
-          else if (r == 2) atomicOr(&P.counters[1], 2ull);
-        } else {               // CSR cell: `pre` is offsets[row]
-          const uint32_t lo = (uint32_t)pre, hi = gather_u32(off + row + 1);
-          for (uint32_t q = lo; q < hi; ++q) {
-            int r = dset_insert(P.dset[dn], P.dset_mask[dn], P.max_probe, (cell << 32) | (uint64_t)gather_u32(vals + q));
-            if (r == 1) { red_add_u32(distinct + cell, 1u, tpol); if (dn == 0) ++ins0; else ++ins1; }
-            else if (r == 2) { atomicOr(&P.counters[1], 2ull); break; }
-          }
-        }
-        ++dn;
-      }
+    // ---- hand the passing rows to the aggregation stage in full batches of 32 ----
+    // The list is a small per-warp queue: rows wait (across chunks) until a whole warp of them is
+    // available, so that one DRAM round trip of gathers always serves 32 rows whatever the selectivity.
+    uint32_t head = 0;
+    while (npend - head >= 32) {
+      const uint2 e = list[head + lane];
+      process_row(P.segs[e.x], e.y);
+      head += 32;
     }
-    __syncwarp();  // the list is reused by the next chunk
+    if (head) {  // move the incomplete batch (< 32 rows) to the front
+      const uint32_t left = npend - head;
+      uint2 t = make_uint2(0, 0);
+      if (lane < left) t = list[head + lane];
+      __syncwarp();
+      if (lane < left) list[lane] = t;
+      __syncwarp();
+      npend = left;
+    }
+  }
+
+  // the last, incomplete batch
+  if (lane < npend) {
+    const uint2 e = list[lane];
+    process_row(P.segs[e.x], e.y);
   }
 
   // counters: one atomic per warp
