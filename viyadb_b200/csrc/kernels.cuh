@@ -220,9 +220,9 @@ __device__ __forceinline__ void st_u8_hint(uint8_t *a, uint32_t v, uint64_t pol)
   asm volatile("st.global.L2::cache_hint.u8 [%0], %1, %2;" ::"l"(a), "r"(v), "l"(pol) : "memory");
 }
 
-__device__ __forceinline__ void acc_update(void *acc, uint64_t cell, uint32_t op, uint64_t v, uint64_t pol) {
-  uint32_t *a32 = reinterpret_cast<uint32_t *>(acc) + cell;
-  uint64_t *a64 = reinterpret_cast<uint64_t *>(acc) + cell;
+__device__ __forceinline__ void acc_update(void *addr, uint32_t op, uint64_t v, uint64_t pol) {
+  uint32_t *a32 = reinterpret_cast<uint32_t *>(addr);
+  uint64_t *a64 = reinterpret_cast<uint64_t *>(addr);
   switch (op) {
     case A_ADD32: red_add_u32(a32, (uint32_t)v, pol); break;
     case A_ADD64: red_add_u64(a64, v, pol); break;
@@ -274,10 +274,11 @@ __device__ __forceinline__ uint64_t hash_cell(const ScanParams &P, uint64_t key)
   }
   uint64_t slot = mix64(key) & P.hmask;
   for (uint32_t probe = 0; probe < P.max_probe; ++probe) {
-    uint64_t k = *reinterpret_cast<volatile uint64_t *>(P.hkeys + slot);
+    uint64_t *kp = reinterpret_cast<uint64_t *>(reinterpret_cast<uint8_t *>(P.hkeys) + slot * P.hkey_stride);
+    uint64_t k = *reinterpret_cast<volatile uint64_t *>(kp);
     if (k == key) return slot;
     if (k == kEmptyKey) {
-      unsigned long long old = atomicCAS(reinterpret_cast<unsigned long long *>(P.hkeys + slot),
+      unsigned long long old = atomicCAS(reinterpret_cast<unsigned long long *>(kp),
                                          (unsigned long long)kEmptyKey, (unsigned long long)key);
       if (old == kEmptyKey || old == key) return slot;
     }
@@ -467,7 +468,7 @@ __global__ void __launch_bounds__(256) merge_records_kernel(const __grid_constan
                                     : reinterpret_cast<const uint64_t *>(M.src[m])[i];
       if (M.ops[m] == A_ADD32 || M.ops[m] == A_MINS32 || M.ops[m] == A_MAXS32)
         v = (uint64_t)(int64_t)(int32_t)(uint32_t)v;
-      acc_update(M.acc[m], cell, M.ops[m], v, pol);
+      acc_update(reinterpret_cast<uint8_t *>(M.acc[m]) + cell * M.widths[m], M.ops[m], v, pol);
     }
   }
 }
@@ -482,7 +483,8 @@ struct ExtractKey {
   void *out;
 };
 struct ExtractMet {
-  const void *acc;
+  const void *acc;     // accumulator of cell 0
+  uint32_t stride;     // bytes between cells
   uint32_t acc_width;  // 4 or 8
   uint32_t out_width;  // 1,2,4,8 (truncation == the reference's own-type wrap-around, Q4)
   void *out;
@@ -493,6 +495,7 @@ struct ExtractParams {
   uint32_t nkeys, nmets;
   const uint64_t *hkeys;
   const uint8_t *present;
+  uint32_t hkey_stride, present_stride;
   const uint32_t *wstate;
   const uint64_t *wkeys;
   ExtractKey keys[kMaxKeys];
@@ -504,7 +507,7 @@ struct ExtractParams {
 __device__ __forceinline__ bool cell_present(const ExtractParams &E, uint64_t c, uint64_t &packed) {
   if (!E.hash_mode) {
     packed = c;
-    return E.present[c] != 0;
+    return E.present[c * E.present_stride] != 0;
   }
   if (E.hash_mode == 2) {
     packed = c;
@@ -514,7 +517,7 @@ __device__ __forceinline__ bool cell_present(const ExtractParams &E, uint64_t c,
     packed = kEmptyKey;
     return E.present[0] != 0;
   }
-  packed = E.hkeys[c];
+  packed = *reinterpret_cast<const uint64_t *>(reinterpret_cast<const uint8_t *>(E.hkeys) + c * E.hkey_stride);
   return packed != kEmptyKey;
 }
 
@@ -552,8 +555,9 @@ extract_groups_kernel(const __grid_constant__ ExtractParams E) {
     }
     for (uint32_t m = 0; m < E.nmets; ++m) {
       const ExtractMet &em = E.mets[m];
-      uint64_t v = em.acc_width == 4 ? (uint64_t)reinterpret_cast<const uint32_t *>(em.acc)[c]
-                                     : reinterpret_cast<const uint64_t *>(em.acc)[c];
+      const uint8_t *ap = reinterpret_cast<const uint8_t *>(em.acc) + c * em.stride;
+      uint64_t v = em.acc_width == 4 ? (uint64_t)*reinterpret_cast<const uint32_t *>(ap)
+                                     : *reinterpret_cast<const uint64_t *>(ap);
       switch (em.out_width) {
         case 1: reinterpret_cast<uint8_t *>(em.out)[pos] = (uint8_t)v; break;
         case 2: reinterpret_cast<uint16_t *>(em.out)[pos] = (uint16_t)v; break;
@@ -567,6 +571,16 @@ extract_groups_kernel(const __grid_constant__ ExtractParams E) {
 // ---------------------------------------------------------------------------------------------
 // helpers: fills, per-column min/max (segment stats), synthetic generator
 // ---------------------------------------------------------------------------------------------
+// Interleaved group cells: every cell starts as the same pattern of `words` 32-bit words.
+struct CellPattern {
+  uint32_t words;
+  uint32_t w[48];
+};
+__global__ void __launch_bounds__(256) fill_cells_kernel(uint32_t *p, uint64_t total_words, const __grid_constant__ CellPattern C) {
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total_words;
+       i += (uint64_t)gridDim.x * blockDim.x)
+    p[i] = C.w[i % C.words];
+}
 __global__ void fill32_kernel(uint32_t *p, uint64_t n, uint32_t v) {
   for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
        i += (uint64_t)gridDim.x * blockDim.x)

@@ -300,7 +300,7 @@ scan_filter_groupby_kernel(const __grid_constant__ ScanParams P) {
       }
     } else {
       cell = packed;
-      if (!(P.tune & 8u)) st_u8_hint(P.present + cell, 1u, tpol);
+      st_u8_hint(P.present + cell * P.present_stride, 1u, tpol);
     }
     uint32_t dn = 0;
     for (uint32_t m = 0; m < P.nmetrics; ++m) {
@@ -318,22 +318,21 @@ scan_filter_groupby_kernel(const __grid_constant__ ScanParams P) {
         pre = gather_finish(gather_raw64(a), a, sl.vmask, sl.signbit);
       }
       if (ms.op != A_DISTINCT) {
-        if (P.tune & 16u) { if (ms.op == A_MINS32) atomicMin(reinterpret_cast<int *>(ms.acc) + cell, (int)pre); else if (ms.op == A_MAXS32) atomicMax(reinterpret_cast<int *>(ms.acc) + cell, (int)pre); }
-        else acc_update(ms.acc, cell, ms.op, pre, tpol);
+        acc_update(reinterpret_cast<uint8_t *>(ms.acc) + cell * ms.stride, ms.op, pre, tpol);
         continue;
       }
       const uint32_t *off = seg.bs_offsets[sl.bitset_idx];
       const uint32_t *vals = seg.bs_values[sl.bitset_idx];
-      uint32_t *distinct = reinterpret_cast<uint32_t *>(ms.acc);
+      uint32_t *distinct = reinterpret_cast<uint32_t *>(reinterpret_cast<uint8_t *>(ms.acc) + cell * ms.stride);
       if (off == nullptr) {  // one id per row: `pre` is the id
         int r = dset_insert(P.dset[dn], P.dset_mask[dn], P.max_probe, (cell << 32) | pre);
-        if (r == 1) { red_add_u32(distinct + cell, 1u, tpol); if (dn == 0) ++ins0; else ++ins1; }
+        if (r == 1) { red_add_u32(distinct, 1u, tpol); if (dn == 0) ++ins0; else ++ins1; }
         else if (r == 2) atomicOr(&P.counters[1], 2ull);
       } else {               // CSR cell: `pre` is offsets[row]
         const uint32_t lo = (uint32_t)pre, hi = gather_u32(off + row + 1);
         for (uint32_t q = lo; q < hi; ++q) {
           int r = dset_insert(P.dset[dn], P.dset_mask[dn], P.max_probe, (cell << 32) | (uint64_t)gather_u32(vals + q));
-          if (r == 1) { red_add_u32(distinct + cell, 1u, tpol); if (dn == 0) ++ins0; else ++ins1; }
+          if (r == 1) { red_add_u32(distinct, 1u, tpol); if (dn == 0) ++ins0; else ++ins1; }
           else if (r == 2) { atomicOr(&P.counters[1], 2ull); break; }
         }
       }

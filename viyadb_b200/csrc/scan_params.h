@@ -88,8 +88,10 @@ enum AccOp : uint8_t {
 struct MetSpec {
   uint8_t slot;
   uint8_t op;      // AccOp
-  uint8_t pad[6];
-  void *acc;       // device accumulator array, one cell (4 or 8 bytes) per group cell
+  uint8_t pad[2];
+  uint32_t stride; // bytes between the accumulators of consecutive cells (== width when the table is
+                   // one array per metric, == cell size when the fields of a cell are interleaved)
+  void *acc;       // accumulator of cell 0
 };
 
 // Per-segment descriptor (device array, one per table segment).
@@ -129,7 +131,9 @@ struct ScanParams {
   uint32_t hash_mode;      // 0: dense cells, 1: open-addressing hash on the packed 64-bit key,
                            // 2: open-addressing hash on the full key tuple (one 64-bit word per key)
   KeySpec keys[kMaxKeys];
-  uint64_t *hkeys;         // hash_mode: capacity cells, EMPTY = ~0
+  uint64_t *hkeys;         // hash_mode: key of slot 0, EMPTY = ~0
+  uint32_t hkey_stride;    // bytes between the keys of consecutive slots
+  uint32_t present_stride; // bytes between the presence flags of consecutive cells (dense)
   uint64_t hmask;          // capacity - 1
   uint8_t *present;        // dense: 1 byte per cell; hash: present[0] flags the sentinel key
   uint32_t *wstate;        // wide mode: 0 free, 1 being written, 2 ready

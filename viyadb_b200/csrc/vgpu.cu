@@ -1443,6 +1443,8 @@ void nccl_merge_hash(vgpu_ctx *ctx, QueryRun &q, ScanParams &P, std::vector<void
   E.hash_mode = 1;
   E.hkeys = P.hkeys;
   E.present = P.present;
+  E.hkey_stride = P.hkey_stride;
+  E.present_stride = P.present_stride;
   E.count_only = 1;
   unsigned long long *d_n = scratch.alloc<unsigned long long>(1);
   CUDA_CK(cudaMemsetAsync(d_n, 0, 8, stream));
@@ -1532,9 +1534,15 @@ void nccl_merge_hash(vgpu_ctx *ctx, QueryRun &q, ScanParams &P, std::vector<void
       ++launches;
     }
     P.hkeys = M.hkeys;
+    P.hkey_stride = 8;
     P.hmask = M.hmask;
     P.present = M.present;
-    for (size_t m = 0; m < nm; ++m) acc_ptrs[m] = M.acc[m];
+    P.present_stride = 1;
+    for (size_t m = 0; m < nm; ++m) {
+      acc_ptrs[m] = M.acc[m];
+      P.mets[m].acc = M.acc[m];
+      P.mets[m].stride = q.accs[m].acc_width;
+    }
     acc_cells = cap + 1;
   };
 
@@ -1808,46 +1816,89 @@ int vgpu_query_agg(vgpu_table *t, const vgpu_plan *plan, vgpu_result **out) {
       const uint64_t acc_cells = q.hash_mode ? hash_cap + 1 : cells;  // + the all-ones-key cell
       P.hash_mode = q.wide ? 2u : (q.hash_mode ? 1u : 0u);
       P.max_probe = 512;
-      // The group table (keys / present flags / accumulators) is ONE contiguous block so that one L2
-      // access-policy window can pin it: the column stream flowing through L2 otherwise evicts the
-      // accumulator lines and every RED/ATOM becomes a DRAM round trip (measured: +10 B/row of DRAM
-      // traffic at 5e5 groups, profiles/r1_explore_c2.txt).
+      // Group table layout. Single GPU: the fields of a cell (key, accumulators, presence flag) are
+      // INTERLEAVED, so that one passing row touches one line of the table instead of one line per
+      // metric array (tables beyond a few MB are DRAM-resident under the column stream: measured
+      // +3..10 B/row of traffic with separate arrays). Several GPUs: one array per field, because the
+      // NCCL merge reduces each array with its own type and operator.
+      const bool interleave = ctx->nranks == 1;
       uint64_t block_bytes = 0;
       auto carve = [&](uint64_t bytes) { uint64_t o = block_bytes; block_bytes += round_up(bytes, 256); return o; };
-      const uint64_t o_hkeys = (q.hash_mode && !q.wide) ? carve(hash_cap * 8) : 0;
       const uint64_t o_wstate = q.wide ? carve(hash_cap * 4) : 0;
       const uint64_t o_wkeys = q.wide ? carve(hash_cap * 8 * std::max<uint32_t>(plan->nkeys, 1)) : 0;
-      const uint64_t o_present = carve(q.hash_mode ? 16 : acc_cells);
-      std::vector<uint64_t> o_acc(q.accs.size());
-      for (size_t m = 0; m < q.accs.size(); ++m) o_acc[m] = carve(acc_cells * q.accs[m].acc_width);
-      uint8_t *block = scratch.alloc<uint8_t>(block_bytes);
+      std::vector<void *> acc_ptrs(q.accs.size());
+      std::vector<uint32_t> acc_stride(q.accs.size());
+      uint8_t *block = nullptr;
+      const bool key_in_cell = q.hash_mode && !q.wide;
+      if (interleave) {
+        // cell = [key u64]? [8-byte accumulators] [4-byte accumulators] [presence u32]?
+        uint32_t off = 0;
+        uint32_t o_key = 0, o_pres = 0;
+        std::vector<uint32_t> o_f(q.accs.size());
+        if (key_in_cell) { o_key = off; off += 8; }
+        for (size_t m = 0; m < q.accs.size(); ++m) if (q.accs[m].acc_width == 8) { o_f[m] = off; off += 8; }
+        for (size_t m = 0; m < q.accs.size(); ++m) if (q.accs[m].acc_width == 4) { o_f[m] = off; off += 4; }
+        const bool need_present = !q.hash_mode;
+        if (need_present) { o_pres = off; off += 4; }
+        uint32_t stride = off <= 4 ? 4 : off <= 8 ? 8 : off <= 16 ? 16 : off <= 32 ? 32 : (uint32_t)round_up(off, 8);
+        if (stride / 4 > 48) fail(VGPU_ERR_UNSUPPORTED, "group cell too wide");
+        const uint64_t o_cells = carve(acc_cells * (uint64_t)stride);
+        const uint64_t o_flag = carve(16);
+        block = scratch.alloc<uint8_t>(block_bytes);
+        CellPattern C{};
+        C.words = stride / 4;
+        if (key_in_cell) { C.w[o_key / 4] = 0xffffffffu; C.w[o_key / 4 + 1] = 0xffffffffu; }
+        for (size_t m = 0; m < q.accs.size(); ++m) {
+          C.w[o_f[m] / 4] = (uint32_t)q.accs[m].init;
+          if (q.accs[m].acc_width == 8) C.w[o_f[m] / 4 + 1] = (uint32_t)(q.accs[m].init >> 32);
+          acc_ptrs[m] = block + o_cells + o_f[m];
+          acc_stride[m] = stride;
+        }
+        const uint64_t total_words = acc_cells * (uint64_t)(stride / 4);
+        fill_cells_kernel<<<grid_for(total_words, 256, ctx->sm_count), 256, 0, stream>>>(
+            reinterpret_cast<uint32_t *>(block + o_cells), total_words, C);
+        CUDA_CK(cudaGetLastError());
+        ++launches;
+        P.hkeys = key_in_cell ? reinterpret_cast<uint64_t *>(block + o_cells + o_key) : nullptr;
+        P.hkey_stride = stride;
+        P.hmask = q.hash_mode ? hash_cap - 1 : 0;
+        if (need_present) {
+          P.present = block + o_cells + o_pres;
+          P.present_stride = stride;
+        } else {
+          P.present = block + o_flag;  // present[0] flags the all-ones key
+          P.present_stride = 1;
+          CUDA_CK(cudaMemsetAsync(P.present, 0, 16, stream));
+        }
+      } else {
+        const uint64_t o_hkeys = key_in_cell ? carve(hash_cap * 8) : 0;
+        const uint64_t o_present = carve(q.hash_mode ? 16 : acc_cells);
+        std::vector<uint64_t> o_acc(q.accs.size());
+        for (size_t m = 0; m < q.accs.size(); ++m) o_acc[m] = carve(acc_cells * q.accs[m].acc_width);
+        block = scratch.alloc<uint8_t>(block_bytes);
+        P.hkeys = key_in_cell ? reinterpret_cast<uint64_t *>(block + o_hkeys) : nullptr;
+        P.hkey_stride = 8;
+        P.hmask = q.hash_mode ? hash_cap - 1 : 0;
+        if (key_in_cell) fill64(stream, ctx->sm_count, P.hkeys, hash_cap, kEmptyKey);
+        P.present = block + o_present;
+        P.present_stride = 1;
+        CUDA_CK(cudaMemsetAsync(P.present, 0, q.hash_mode ? 16 : acc_cells, stream));
+        for (size_t m = 0; m < q.accs.size(); ++m) {
+          const AccInfo &a = q.accs[m];
+          acc_ptrs[m] = block + o_acc[m];
+          acc_stride[m] = a.acc_width;
+          if (a.acc_width == 4) launches += fill32(stream, ctx->sm_count, acc_ptrs[m], acc_cells, (uint32_t)a.init);
+          else launches += fill64(stream, ctx->sm_count, acc_ptrs[m], acc_cells, a.init);
+        }
+      }
       if (q.wide) {
-        P.hkeys = nullptr;
-        P.hmask = hash_cap - 1;
         P.wstate = reinterpret_cast<uint32_t *>(block + o_wstate);
         P.wkeys = reinterpret_cast<uint64_t *>(block + o_wkeys);
         CUDA_CK(cudaMemsetAsync(P.wstate, 0, hash_cap * 4, stream));
-        P.present = block + o_present;
-        CUDA_CK(cudaMemsetAsync(P.present, 0, 16, stream));
-      } else if (q.hash_mode) {
-        P.hkeys = reinterpret_cast<uint64_t *>(block + o_hkeys);
-        P.hmask = hash_cap - 1;
-        fill64(stream, ctx->sm_count, P.hkeys, hash_cap, kEmptyKey);
-        P.present = block + o_present;
-        CUDA_CK(cudaMemsetAsync(P.present, 0, 16, stream));
-      } else {
-        P.hkeys = nullptr;
-        P.hmask = 0;
-        P.present = block + o_present;
-        CUDA_CK(cudaMemsetAsync(P.present, 0, acc_cells, stream));
       }
-      std::vector<void *> acc_ptrs(q.accs.size());
       for (size_t m = 0; m < q.accs.size(); ++m) {
-        const AccInfo &a = q.accs[m];
-        acc_ptrs[m] = block + o_acc[m];
-        if (a.acc_width == 4) launches += fill32(stream, ctx->sm_count, acc_ptrs[m], acc_cells, (uint32_t)a.init);
-        else launches += fill64(stream, ctx->sm_count, acc_ptrs[m], acc_cells, a.init);
         P.mets[m].acc = acc_ptrs[m];
+        P.mets[m].stride = acc_stride[m];
       }
       for (uint32_t d = 0; d < P.ndistinct; ++d) {
         P.dset[d] = scratch.alloc<uint64_t>(dset_cap);
@@ -1938,6 +1989,8 @@ int vgpu_query_agg(vgpu_table *t, const vgpu_plan *plan, vgpu_result **out) {
       E.nmets = (uint32_t)q.accs.size();
       E.hkeys = P.hkeys;
       E.present = P.present;
+      E.hkey_stride = P.hkey_stride;
+      E.present_stride = P.present_stride;
       E.wstate = P.wstate;
       E.wkeys = P.wkeys;
       unsigned long long *d_ngroups = ctx->d_counters + 12;
@@ -1968,6 +2021,7 @@ int vgpu_query_agg(vgpu_table *t, const vgpu_plan *plan, vgpu_result **out) {
       for (size_t m = 0; m < q.accs.size(); ++m) {
         d_accs[m] = scratch.alloc<uint8_t>(bound * q.accs[m].out_width);
         E.mets[m].acc = acc_ptrs[m];
+        E.mets[m].stride = P.mets[m].stride;
         E.mets[m].acc_width = q.accs[m].acc_width;
         E.mets[m].out_width = q.accs[m].out_width;
         E.mets[m].out = d_accs[m];
