@@ -178,22 +178,6 @@ __device__ __forceinline__ uint32_t eval_predicate(const ScanParams &P, const Se
   return stk[0];
 }
 
-// ---------------------------------------------------------------------------------------------
-// (cell,id) hash set for count-distinct: 0 = already there, 1 = inserted, 2 = probe limit hit
-// ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ int dset_insert(uint64_t *set, uint64_t mask, uint32_t max_probe, uint64_t key) {
-  uint64_t slot = mix64(key) & mask;
-  for (uint32_t probe = 0; probe < max_probe; ++probe) {
-    // the set is kept at most half full: claim first, look second (one L2 operation per insert)
-    unsigned long long old = atomicCAS(reinterpret_cast<unsigned long long *>(set + slot),
-                                       (unsigned long long)kEmptyKey, (unsigned long long)key);
-    if (old == kEmptyKey) return 1;
-    if (old == key) return 0;
-    slot = (slot + 1) & mask;
-  }
-  return 2;
-}
-
 // Wide key tuples (hash_mode 2): gather the key words of one row and find / claim its slot. Out of line
 // so that its local array does not cost the common paths registers.
 __device__ __noinline__ uint64_t wide_row_cell(const ScanParams &P, const SegDesc &seg, uint32_t row) {
@@ -224,8 +208,9 @@ scan_filter_groupby_kernel(const __grid_constant__ ScanParams P) {
   uint2 *list = s_list[warp];
   uint32_t npend = 0;  // rows waiting in the list (warp-uniform)
   uint32_t my_passed = 0;
-  uint32_t ins0 = 0, ins1 = 0;  // pairs this lane added to the count-distinct sets
-  static_assert(kMaxDistinct == 2, "two insert counters");
+  __shared__ uint32_t s_cursor[kMaxDistinct];  // pairs this CTA appended per count-distinct metric
+  if (threadIdx.x < kMaxDistinct) s_cursor[threadIdx.x] = 0;
+  __syncthreads();
   const bool can_overflow = P.hash_mode || P.ndistinct;
   const uint64_t pol = make_stream_policy((P.tune & 2u) != 0);
   const uint64_t tpol = make_table_policy((P.tune & 4u) != 0);
@@ -321,19 +306,18 @@ scan_filter_groupby_kernel(const __grid_constant__ ScanParams P) {
         acc_update(reinterpret_cast<uint8_t *>(ms.acc) + cell * ms.stride, ms.op, pre, tpol);
         continue;
       }
+      // count-distinct: append (cell, id) to this CTA's region; deduplicated after the scan
       const uint32_t *off = seg.bs_offsets[sl.bitset_idx];
       const uint32_t *vals = seg.bs_values[sl.bitset_idx];
-      uint32_t *distinct = reinterpret_cast<uint32_t *>(reinterpret_cast<uint8_t *>(ms.acc) + cell * ms.stride);
+      uint64_t *region = P.dpairs[dn] + (uint64_t)blockIdx.x * P.dpair_cap;
       if (off == nullptr) {  // one id per row: `pre` is the id
-        int r = dset_insert(P.dset[dn], P.dset_mask[dn], P.max_probe, (cell << 32) | pre);
-        if (r == 1) { red_add_u32(distinct, 1u, tpol); if (dn == 0) ++ins0; else ++ins1; }
-        else if (r == 2) atomicOr(&P.counters[1], 2ull);
+        const uint32_t pos = atomicAdd(&s_cursor[dn], 1u);
+        if (pos < P.dpair_cap) region[pos] = (cell << 32) | pre;
       } else {               // CSR cell: `pre` is offsets[row]
         const uint32_t lo = (uint32_t)pre, hi = gather_u32(off + row + 1);
         for (uint32_t q = lo; q < hi; ++q) {
-          int r = dset_insert(P.dset[dn], P.dset_mask[dn], P.max_probe, (cell << 32) | (uint64_t)gather_u32(vals + q));
-          if (r == 1) { red_add_u32(distinct, 1u, tpol); if (dn == 0) ++ins0; else ++ins1; }
-          else if (r == 2) { atomicOr(&P.counters[1], 2ull); break; }
+          const uint32_t pos = atomicAdd(&s_cursor[dn], 1u);
+          if (pos < P.dpair_cap) region[pos] = (cell << 32) | (uint64_t)gather_u32(vals + q);
         }
       }
       ++dn;
@@ -457,13 +441,15 @@ scan_filter_groupby_kernel(const __grid_constant__ ScanParams P) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) my_passed += __shfl_down_sync(0xffffffffu, my_passed, o);
   if (lane == 0 && my_passed) atomicAdd(&P.counters[0], (unsigned long long)my_passed);
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    ins0 += __shfl_down_sync(0xffffffffu, ins0, o);
-    ins1 += __shfl_down_sync(0xffffffffu, ins1, o);
+  if (P.ndistinct) {  // the only CTA-wide barrier of the kernel: publish the per-CTA pair counts
+    __syncthreads();
+    if (threadIdx.x < P.ndistinct) {
+      const uint32_t n = s_cursor[threadIdx.x];
+      P.dpair_count[threadIdx.x][blockIdx.x] = n < P.dpair_cap ? n : P.dpair_cap;
+      if (n > P.dpair_cap) atomicOr(&P.counters[1], 2ull);  // region overflow: the host grows it and re-runs
+      atomicAdd(&P.counters[2 + threadIdx.x], (unsigned long long)n);
+    }
   }
-  if (lane == 0 && ins0) atomicAdd(&P.counters[2], (unsigned long long)ins0);
-  if (lane == 0 && ins1) atomicAdd(&P.counters[3], (unsigned long long)ins1);
 }
 
 }  // namespace vgpu

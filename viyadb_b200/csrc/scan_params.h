@@ -145,11 +145,14 @@ struct ScanParams {
   MetSpec mets[kMaxMetrics];
   uint32_t ndistinct;                 // BITSET metrics selected (count-distinct)
   uint8_t distinct_met[kMaxDistinct]; // their indices into mets
-  uint64_t *dset[kMaxDistinct];       // per distinct metric: open-addressing set of (cell << 32 | id)
-  uint64_t dset_mask[kMaxDistinct];   // capacity - 1
+  // count-distinct: (cell << 32 | id) pairs are appended to a private region per CTA (cursor in shared
+  // memory), deduplicated afterwards in L2-sized hash partitions (pairs_* kernels)
+  uint64_t *dpairs[kMaxDistinct];     // region of CTA b: [b * dpair_cap, (b + 1) * dpair_cap)
+  uint32_t *dpair_count[kMaxDistinct];  // [gridDim.x] pairs written by each CTA
+  uint32_t dpair_cap;
 
   // counters: [0] passed rows, [1] overflow flag (probe limit of the group table or of a distinct set),
-  // [2+d] pairs inserted into distinct set d
+  // [2+d] pairs appended for distinct metric d (all CTAs)
   unsigned long long *counters;
 };
 

@@ -1379,20 +1379,122 @@ void exchange_array(vgpu_ctx *ctx, const void *send, uint64_t bucket_cap, uint32
   }
 }
 
+// Deduplicate the (cell,id) pairs of one count-distinct metric and count them per cell.
+// Input: ragged per-CTA regions (d_counts != nullptr) or `total` contiguous pairs. The pairs are hash-
+// partitioned into buckets whose open-addressing sets fit L2, then each bucket is inserted; a pair seen
+// for the first time bumps distinct[cell] and, if asked, lands in `unique_out`.
+void dedupe_pairs(vgpu_ctx *ctx, Scratch &scratch, const uint64_t *pairs, const uint32_t *d_counts, uint32_t nregions,
+                  uint32_t region_cap, uint64_t total, uint8_t *distinct, uint32_t stride, uint64_t *unique_out,
+                  unsigned long long *d_unique_n, uint32_t &launches) {
+  if (total == 0) return;
+  cudaStream_t stream = ctx->stream;
+  const uint64_t kBucketPairs = 1ull << 21;  // 2^22-slot set = 32 MB: stays in the 126 MB L2
+  uint32_t B = (uint32_t)std::min<uint64_t>(pow2_ceil((total + kBucketPairs - 1) / kBucketPairs), kMaxBuckets);
+  PairsDedupeParams D{};
+  D.distinct = distinct;
+  D.stride = stride;
+  D.unique_out = unique_out;
+  D.unique_n = d_unique_n;
+  if (B <= 1) {
+    const uint64_t set_cap = pow2_ceil(std::max<uint64_t>(2 * total, 1024));
+    uint64_t *set = scratch.alloc<uint64_t>(set_cap);
+    CUDA_CK(cudaMemsetAsync(set, 0xff, set_cap * 8, stream));
+    D.pairs = pairs;
+    D.counts = d_counts;
+    D.nregions = nregions;
+    D.region_cap = region_cap;
+    D.n = total;
+    D.set = set;
+    D.set_mask = set_cap - 1;
+    const int grid = d_counts ? (int)std::min<uint32_t>(nregions, ctx->sm_count * 8) : grid_for(total, 256, ctx->sm_count);
+    pairs_dedupe_kernel<<<std::max(grid, 1), 256, 0, stream>>>(D);
+    CUDA_CK(cudaGetLastError());
+    ++launches;
+    return;
+  }
+  // 1. partition
+  uint64_t bucket_cap = total / B + total / B / 8 + 8192;
+  unsigned long long *cursors = scratch.alloc<unsigned long long>(kMaxBuckets + 1);
+  std::vector<unsigned long long> h_cursors(kMaxBuckets + 1);
+  uint64_t *buckets = nullptr;
+  for (int attempt = 0; attempt < 2; ++attempt) {
+    buckets = scratch.alloc<uint64_t>(bucket_cap * B);
+    CUDA_CK(cudaMemsetAsync(cursors, 0, (kMaxBuckets + 1) * sizeof(unsigned long long), stream));
+    PairsPartitionParams A{};
+    A.pairs = pairs;
+    A.counts = d_counts;
+    A.total = total;
+    if (d_counts) {
+      A.nregions = nregions;
+      A.region_cap = region_cap;
+    } else {
+      A.region_cap = 1u << 16;
+      A.nregions = (uint32_t)((total + A.region_cap - 1) / A.region_cap);
+    }
+    A.nbuckets = B;
+    A.shift = 40;
+    A.bucket_cap = bucket_cap;
+    A.cursors = cursors;
+    A.out = buckets;
+    A.overflow = cursors + kMaxBuckets;
+    pairs_partition_kernel<<<(int)std::min<uint32_t>(A.nregions, ctx->sm_count * 8), 256, 0, stream>>>(A);
+    CUDA_CK(cudaGetLastError());
+    ++launches;
+    CUDA_CK(cudaMemcpyAsync(h_cursors.data(), cursors, (kMaxBuckets + 1) * sizeof(unsigned long long),
+                            cudaMemcpyDeviceToHost, stream));
+    CUDA_CK(cudaStreamSynchronize(stream));
+    if (h_cursors[kMaxBuckets] == 0) break;
+    if (attempt == 1) fail(VGPU_ERR_CUDA, "count-distinct partitioning overflowed twice");
+    bucket_cap = 0;  // a skewed hash bucket: size every bucket for the largest one and scatter again
+    for (uint32_t b = 0; b < B; ++b) bucket_cap = std::max<uint64_t>(bucket_cap, h_cursors[b]);
+  }
+  // 2. one L2-resident set, reused bucket after bucket
+  uint64_t max_n = 0;
+  for (uint32_t b = 0; b < B; ++b) max_n = std::max<uint64_t>(max_n, h_cursors[b]);
+  const uint64_t set_cap_max = pow2_ceil(std::max<uint64_t>(2 * max_n, 1024));
+  uint64_t *set = scratch.alloc<uint64_t>(set_cap_max);
+  for (uint32_t b = 0; b < B; ++b) {
+    const uint64_t n = h_cursors[b];
+    if (n == 0) continue;
+    const uint64_t set_cap = pow2_ceil(std::max<uint64_t>(2 * n, 1024));
+    CUDA_CK(cudaMemsetAsync(set, 0xff, set_cap * 8, stream));
+    D.pairs = buckets + (uint64_t)b * bucket_cap;
+    D.counts = nullptr;
+    D.n = n;
+    D.set = set;
+    D.set_mask = set_cap - 1;
+    pairs_dedupe_kernel<<<grid_for(n, 256, ctx->sm_count), 256, 0, stream>>>(D);
+    CUDA_CK(cudaGetLastError());
+    ++launches;
+  }
+}
+
 // count-distinct across ranks (dense group table): the (cell,id) sets of all ranks are united. Every
-// pair travels to the rank that owns its cell, owners dedupe and count, one sum-allreduce of the
-// per-cell counts gives every rank the full answer. Per-rank work stays constant as ranks are added.
-void nccl_merge_distinct(vgpu_ctx *ctx, const uint64_t *dset, uint64_t dset_cap, uint64_t inserted,
-                         uint32_t *distinct, uint64_t acc_cells, Scratch &scratch, uint32_t &launches) {
+// rank dedupes its own pairs, each unique pair travels to the rank that owns its cell, owners dedupe
+// and count, one sum-allreduce of the per-cell counts gives every rank the full answer. Per-rank work
+// stays constant as ranks are added.
+void nccl_merge_distinct(vgpu_ctx *ctx, Scratch &scratch, const uint64_t *regions, const uint32_t *d_counts,
+                         uint32_t nregions, uint32_t region_cap, uint64_t total_pairs, uint32_t *distinct,
+                         uint64_t acc_cells, uint32_t &launches) {
   const int G = ctx->nranks, me = ctx->rank;
   cudaStream_t stream = ctx->stream;
-  const uint64_t bucket_cap = std::max<uint64_t>(inserted, 1);
+  // 1. local dedupe into a compact list
+  uint64_t *unique = scratch.alloc<uint64_t>(std::max<uint64_t>(total_pairs, 1));
+  unsigned long long *d_unique_n = scratch.alloc<unsigned long long>(1);
+  CUDA_CK(cudaMemsetAsync(d_unique_n, 0, 8, stream));
+  dedupe_pairs(ctx, scratch, regions, d_counts, nregions, region_cap, total_pairs, reinterpret_cast<uint8_t *>(distinct), 4,
+               unique, d_unique_n, launches);
+  unsigned long long n_unique = 0;
+  CUDA_CK(cudaMemcpyAsync(&n_unique, d_unique_n, 8, cudaMemcpyDeviceToHost, stream));
+  CUDA_CK(cudaStreamSynchronize(stream));
+  // 2. to the owners of the cells
+  const uint64_t bucket_cap = std::max<uint64_t>(n_unique, 1);
   unsigned long long *cursors = scratch.alloc<unsigned long long>(kMaxParts);
   CUDA_CK(cudaMemsetAsync(cursors, 0, kMaxParts * sizeof(unsigned long long), stream));
   uint64_t *send = scratch.alloc<uint64_t>(bucket_cap * G);
   PartitionParams A{};
-  A.keys = dset;
-  A.nslots = dset_cap;
+  A.keys = unique;
+  A.nslots = n_unique;
   A.sentinel_slot = ~0ull;
   A.sentinel_present = nullptr;
   A.nparts = (uint32_t)G;
@@ -1401,7 +1503,7 @@ void nccl_merge_distinct(vgpu_ctx *ctx, const uint64_t *dset, uint64_t dset_cap,
   A.cursors = cursors;
   A.out_keys = send;
   A.npay = 0;
-  partition_table_kernel<<<grid_for(dset_cap, 256 * kPartPerThread, ctx->sm_count, 8), 256, 0, stream>>>(A);
+  partition_table_kernel<<<grid_for(n_unique + 1, 256 * kPartPerThread, ctx->sm_count, 8), 256, 0, stream>>>(A);
   CUDA_CK(cudaGetLastError());
   ++launches;
   std::vector<uint64_t> matrix = exchange_counts(ctx, cursors, scratch);
@@ -1412,19 +1514,9 @@ void nccl_merge_distinct(vgpu_ctx *ctx, const uint64_t *dset, uint64_t dset_cap,
   NCCL_CK(g_nccl.GroupStart());
   exchange_array(ctx, send, bucket_cap, 8, recv, matrix, recv_off);
   NCCL_CK(g_nccl.GroupEnd());
-  // owners dedupe what they received and count per cell
+  // 3. owners dedupe what they received and count per cell; 4. everybody gets every count
   CUDA_CK(cudaMemsetAsync(distinct, 0, acc_cells * 4, stream));
-  if (total) {
-    const uint64_t set_cap = pow2_ceil(std::max<uint64_t>(2 * total, 1024));
-    uint64_t *set = scratch.alloc<uint64_t>(set_cap);
-    fill64(stream, ctx->sm_count, set, set_cap, kEmptyKey);
-    unsigned long long *sentinel = scratch.alloc<unsigned long long>(1);
-    CUDA_CK(cudaMemsetAsync(sentinel, 0, 8, stream));
-    distinct_insert_kernel<<<grid_for(total, 256, ctx->sm_count), 256, 0, stream>>>(recv, total, set, set_cap - 1,
-                                                                                  distinct, sentinel);
-    CUDA_CK(cudaGetLastError());
-    ++launches;
-  }
+  dedupe_pairs(ctx, scratch, recv, nullptr, 0, 0, total, reinterpret_cast<uint8_t *>(distinct), 4, nullptr, nullptr, launches);
   NCCL_CK(g_nccl.AllReduce(distinct, distinct, acc_cells, ncclUint32, ncclSum, ctx->comm, stream));
 }
 
@@ -1801,12 +1893,15 @@ int vgpu_query_agg(vgpu_table *t, const vgpu_plan *plan, vgpu_result **out) {
       hash_cap = std::max(hash_cap, std::min(t->hash_cap_hint, want));
       if (hash_cap > 0xfffffffeull && P.ndistinct) fail(VGPU_ERR_UNSUPPORTED, "count-distinct over more than 2^32 groups");
     }
-    // count-distinct: (cell,id) pairs go straight into an open-addressing set; its capacity follows the
-    // high-water mark of earlier queries on this table, and grows (re-running the scan) on overflow
-    uint64_t dset_cap = 0;
+    // the scan grid (also the number of count-distinct pair regions)
+    const int scan_grid = (int)std::max<uint64_t>(1, std::min<uint64_t>((P.total_tiles + kWarps - 1) / kWarps,
+                                                                       (uint64_t)ctx->sm_count * VGPU_MIN_CTAS));
+    // count-distinct: every CTA appends its (cell,id) pairs to a private region. The region capacity
+    // follows the high-water mark of earlier queries on this table; overflow => grow and re-run the scan
+    uint64_t dpair_total_cap = 0;
     if (P.ndistinct) {
-      dset_cap = pow2_ceil(std::max<uint64_t>(1ull << 16, q.active_rows / 16));
-      dset_cap = std::max(dset_cap, t->pairs_cap_hint);
+      dpair_total_cap = std::max<uint64_t>(1ull << 16, q.active_rows / 16);
+      dpair_total_cap = std::max(dpair_total_cap, t->pairs_cap_hint);
     }
 
     for (int attempt = 0;; ++attempt) {
@@ -1900,10 +1995,14 @@ int vgpu_query_agg(vgpu_table *t, const vgpu_plan *plan, vgpu_result **out) {
         P.mets[m].acc = acc_ptrs[m];
         P.mets[m].stride = acc_stride[m];
       }
+      // per-CTA pair regions: the even share plus 25 % and a constant for the unevenness between CTAs
+      const uint64_t region_cap64 = dpair_total_cap / scan_grid + dpair_total_cap / scan_grid / 4 + 1024;
+      if (P.ndistinct && region_cap64 > 0xffffffffull) fail(VGPU_ERR_NOMEM, "count-distinct pair regions too large");
+      P.dpair_cap = (uint32_t)region_cap64;
       for (uint32_t d = 0; d < P.ndistinct; ++d) {
-        P.dset[d] = scratch.alloc<uint64_t>(dset_cap);
-        P.dset_mask[d] = dset_cap - 1;
-        fill64(stream, ctx->sm_count, P.dset[d], dset_cap, kEmptyKey);
+        P.dpairs[d] = scratch.alloc<uint64_t>(region_cap64 * scan_grid);
+        P.dpair_count[d] = scratch.alloc<uint32_t>(scan_grid);
+        CUDA_CK(cudaMemsetAsync(P.dpair_count[d], 0, scan_grid * 4, stream));
       }
       CUDA_CK(cudaMemsetAsync(ctx->d_counters, 0, 16 * sizeof(unsigned long long), stream));
       P.counters = ctx->d_counters;
@@ -1915,7 +2014,7 @@ int vgpu_query_agg(vgpu_table *t, const vgpu_plan *plan, vgpu_result **out) {
       // ---- the fused scan ----
       CUDA_CK(cudaEventRecord(ctx->ev_scan0, stream));
       if (P.total_tiles > 0) {
-        int grid = (int)std::min<uint64_t>((P.total_tiles + kWarps - 1) / kWarps, (uint64_t)ctx->sm_count * VGPU_MIN_CTAS);
+        const int grid = scan_grid;
         cudaLaunchConfig_t cfg{};
         cfg.gridDim = dim3(grid);
         cfg.blockDim = dim3(kThreads);
@@ -1955,15 +2054,18 @@ int vgpu_query_agg(vgpu_table *t, const vgpu_plan *plan, vgpu_result **out) {
           if (!q.hash_mode) fail(VGPU_ERR_CUDA, "unexpected overflow flag in dense mode");
           hash_cap *= 4;
         }
-        if (ctx->h_counters[1] & 2ull) dset_cap *= 4;
+        if (ctx->h_counters[1] & 2ull) {  // a pair region overflowed: size for what was actually produced
+          uint64_t most = 0;
+          for (uint32_t d = 0; d < P.ndistinct; ++d) most = std::max<uint64_t>(most, ctx->h_counters[2 + d]);
+          dpair_total_cap = std::max<uint64_t>(2 * dpair_total_cap, most + most / 4);
+        }
         continue;
       }
       if (q.hash_mode) t->hash_cap_hint = std::max(t->hash_cap_hint, hash_cap);
       if (P.ndistinct) {
-        // keep the load factor of the next run below 1/2
         uint64_t most = 0;
         for (uint32_t d = 0; d < P.ndistinct; ++d) most = std::max<uint64_t>(most, ctx->h_counters[2 + d]);
-        t->pairs_cap_hint = std::max(t->pairs_cap_hint, pow2_ceil(std::max<uint64_t>(2 * most, 1ull << 16)));
+        t->pairs_cap_hint = std::max(t->pairs_cap_hint, most);
       }
       view.passed_rows = passed;
 
@@ -1976,9 +2078,15 @@ int vgpu_query_agg(vgpu_table *t, const vgpu_plan *plan, vgpu_result **out) {
         } else {
           nccl_merge_dense(ctx, q, P, acc_ptrs);
           for (uint32_t d = 0; d < P.ndistinct; ++d)
-            nccl_merge_distinct(ctx, P.dset[d], dset_cap, ctx->h_counters[2 + d],
-                                static_cast<uint32_t *>(acc_ptrs[P.distinct_met[d]]), acc_cells, scratch, launches);
+            nccl_merge_distinct(ctx, scratch, P.dpairs[d], P.dpair_count[d], (uint32_t)scan_grid, P.dpair_cap,
+                                ctx->h_counters[2 + d], static_cast<uint32_t *>(acc_ptrs[P.distinct_met[d]]), acc_cells, launches);
         }
+      } else {
+        // ---- count-distinct: dedupe the pairs in L2-sized partitions ----
+        for (uint32_t d = 0; d < P.ndistinct; ++d)
+          dedupe_pairs(ctx, scratch, P.dpairs[d], P.dpair_count[d], (uint32_t)scan_grid, P.dpair_cap, ctx->h_counters[2 + d],
+                       static_cast<uint8_t *>(acc_ptrs[P.distinct_met[d]]), P.mets[P.distinct_met[d]].stride, nullptr, nullptr,
+                       launches);
       }
 
       // ---- extract the groups ----
