@@ -90,11 +90,29 @@ QUERIES = {
 FLOAT_COLS = {"double_sum": (1,), "nested_or_and": ()}
 
 
-@pytest.fixture(scope="module")
-def env(built_lib):
+_TABLE = {}
+_WANT = {}
+
+
+# VGPU_TUNE (read by vgpu_init): "auto" lets the planner choose per chunk between gathering the cells of
+# passing rows from the columns or from the row-major mirror; the other two pin one of the two paths.
+@pytest.fixture(scope="module", params=[None, "130", "258"], ids=["auto", "columns_only", "mirror_only"])
+def env(built_lib, request):
+    import os
     import viyadb_b200 as v
-    segs, dicts, hidden = random_table(EVENTS, 4, 50000, 1234, SPEC, last_rows=12345)
-    db = v.Database({"tables": [EVENTS]}, device=0)
+    if not _TABLE:
+        _TABLE["t"] = random_table(EVENTS, 4, 50000, 1234, SPEC, last_rows=12345)
+    segs, dicts, hidden = _TABLE["t"]
+    old = os.environ.get("VGPU_TUNE")
+    if request.param is not None:
+        os.environ["VGPU_TUNE"] = request.param
+    try:
+        db = v.Database({"tables": [EVENTS]}, device=0)
+    finally:
+        if old is None:
+            os.environ.pop("VGPU_TUNE", None)
+        else:
+            os.environ["VGPU_TUNE"] = old
     upload(db.get_table("events"), segs, dicts, hidden)
     yield v, db, segs, dicts, hidden
     db.close()
@@ -112,7 +130,9 @@ def test_query_matches_oracle(env, name, flags):
         if flags == 1 and e.code == -2:
             pytest.skip("group key wider than 64 bits in forced hash mode")
         raise
-    want = viya_oracle.run_query(EVENTS, segs, dicts, q, now=NOW, hidden_counts=hidden)
+    if name not in _WANT:
+        _WANT[name] = viya_oracle.run_query(EVENTS, segs, dicts, q, now=NOW, hidden_counts=hidden)
+    want = _WANT[name]
     if q.get("limit") and q.get("sort"):
         assert len(out.rows) == len(want["rows"])
         # ties of the sort key are unordered in std::sort: compare the sort-key columns only

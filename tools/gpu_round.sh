@@ -20,4 +20,11 @@ timeout 900 ncu --set full --clock-control none --import-source on --profile-fro
 for w in ${WORKLOADS:-c1 c3 c4}; do
   timeout 600 python bench.py --workload $w --steps 10 --no-e2e --no-cpu > $out/bench_$w.json 2> $out/bench_$w.err; tail -c 1500 $out/bench_$w.json
 done
+for tune in $VARIANTS; do   # A/B of VGPU_TUNE bits on the headline workload (and $VARIANT_WORKLOADS)
+  for w in c2 $VARIANT_WORKLOADS; do
+    echo "VGPU_TUNE=$tune $w"; VGPU_TUNE=$tune timeout 600 python bench.py --workload $w --steps 10 --no-e2e --no-cpu 2>&1 | tail -1 | tee $out/bench_${w}_tune$tune.json | python -c "
+import sys,json
+r=json.loads(sys.stdin.read()); print('   rows/s %.3g'%r['value'], 'ms/step %.3f'%r['ms_per_step'], 'kernel_ms %.3f'%r['roofline']['kernel_ms'], 'frac %.3f'%r['roofline']['frac'])"
+  done
+done
 if [ -n "$EXPLORE" ]; then timeout 600 python tools/explore.py 200000000 c2 > $out/explore_c2.txt 2>&1; cat $out/explore_c2.txt; fi

@@ -753,6 +753,55 @@ __global__ void __launch_bounds__(256) column_minmax_kernel(const __grid_constan
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// row-major mirror (put time): columns -> rows. A CTA transposes tiles of kRowsTileBytes / stride rows
+// through shared memory: column cells are read coalesced along the rows, the finished rows leave as
+// one contiguous coalesced block. One pass over the segment: reads row_bytes, writes stride per row.
+// ---------------------------------------------------------------------------------------------
+constexpr uint32_t kRowsTileBytes = 32768;
+struct RowsCol {
+  const uint8_t *src;  // cell of row 0
+  uint32_t width;
+  uint32_t row_off;
+};
+struct RowsParams {
+  uint8_t *rows;
+  uint64_t nrows;
+  uint32_t stride;
+  uint32_t ncols;
+  RowsCol cols[32];
+};
+
+__global__ void __launch_bounds__(256) build_rows_kernel(const __grid_constant__ RowsParams R) {
+  __shared__ __align__(16) uint8_t s_tile[kRowsTileBytes];
+  const uint32_t tile_rows = kRowsTileBytes / R.stride;
+  const uint64_t ntiles = (R.nrows + tile_rows - 1) / tile_rows;
+  for (uint64_t ti = blockIdx.x; ti < ntiles; ti += gridDim.x) {
+    const uint64_t row0 = ti * tile_rows;
+    const uint32_t n = (uint32_t)min((uint64_t)tile_rows, R.nrows - row0);
+    // padding bytes of the rows are written too: zero them once
+    for (uint32_t i = threadIdx.x; i < n * R.stride / 4; i += blockDim.x) reinterpret_cast<uint32_t *>(s_tile)[i] = 0;
+    __syncthreads();
+    for (uint32_t c = 0; c < R.ncols; ++c) {
+      const RowsCol &rc = R.cols[c];
+      for (uint32_t r = threadIdx.x; r < n; r += blockDim.x) {
+        const uint8_t *src = rc.src + (row0 + r) * rc.width;
+        uint8_t *dst = s_tile + r * R.stride + rc.row_off;
+        switch (rc.width) {
+          case 1: *dst = *src; break;
+          case 2: *reinterpret_cast<uint16_t *>(dst) = *reinterpret_cast<const uint16_t *>(src); break;
+          case 4: *reinterpret_cast<uint32_t *>(dst) = *reinterpret_cast<const uint32_t *>(src); break;
+          default: *reinterpret_cast<uint64_t *>(dst) = *reinterpret_cast<const uint64_t *>(src); break;
+        }
+      }
+    }
+    __syncthreads();
+    uint32_t *out = reinterpret_cast<uint32_t *>(R.rows + row0 * R.stride);  // stride is a multiple of 4
+    for (uint32_t i = threadIdx.x; i < n * R.stride / 4; i += blockDim.x) out[i] = reinterpret_cast<uint32_t *>(s_tile)[i];
+    __syncthreads();
+  }
+}
+
 __device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
   x += 0x9E3779B97F4A7C15ULL;
   uint64_t z = x;

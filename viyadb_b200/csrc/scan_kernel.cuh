@@ -218,19 +218,25 @@ scan_filter_groupby_kernel(const __grid_constant__ ScanParams P) {
   // ---- aggregate one passing row (one row per lane, rows may come from different segments) ----
   // fast path: up to 4 keys of at most 4 bytes and up to 4 metrics, staged in 12 registers
   const bool small_plan = P.small_plan != 0 && P.hash_mode != 2;  // uniform
-  auto process_row = [&](const SegDesc &seg, const uint32_t row) {
+  auto process_row = [&](const SegDesc &seg, const uint32_t row, const bool rowpath) {
     uint32_t kv[4];
     uint64_t mv[4];
+    // position of a cell in bytes from an 8-byte aligned base: inside its column, or inside the mirror
+    const uint32_t rpos = row * P.row_stride;
     if (small_plan) {
       // one DRAM round trip per row: every key and metric cell (or the first word a bitset cell
       // needs) is requested before anything depends on it; branch-free and fully unrolled, so the
-      // loads issue back to back and the values stay in registers. Slab and side-table bases are
-      // 8-byte aligned, so the position of a cell inside its aligned word depends on the row only.
+      // loads issue back to back and the values stay in registers. Slab, mirror and side-table bases
+      // are 8-byte aligned, so the position of a cell inside its aligned word depends on the row only.
+      // rowpath (warp-uniform) only changes the addresses: the cells come from the row-major mirror,
+      // where they share one or two 64-byte DRAM atoms instead of costing one atom per column.
+      const uint8_t *rb = seg.rows + (uint64_t)row * P.row_stride;
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         if (k < P.nkeys) {
           const Slot &sl = P.slots[P.keys[k].slot];
-          kv[k] = gather_raw32(seg.slab + sl.off * seg.cap + (uint64_t)row * sl.width);
+          const uint8_t *col = seg.slab + sl.off * seg.cap + (uint64_t)row * sl.width;
+          kv[k] = gather_raw32(rowpath ? rb + sl.row_off : col);
         }
       }
 #pragma unroll
@@ -241,7 +247,7 @@ scan_filter_groupby_kernel(const __grid_constant__ ScanParams P) {
           const uint32_t *vals = seg.bs_values[sl.bitset_idx];
           const uint8_t *fixed = seg.slab + sl.off * seg.cap + (uint64_t)row * sl.width;
           const uint8_t *bits = reinterpret_cast<const uint8_t *>((off == nullptr ? vals : off) + row);
-          mv[m] = gather_raw64(sl.bitset ? bits : fixed);
+          mv[m] = gather_raw64(rowpath ? rb + sl.row_off : (sl.bitset ? bits : fixed));
         }
       }
     }
@@ -254,7 +260,8 @@ scan_filter_groupby_kernel(const __grid_constant__ ScanParams P) {
         if (k < P.nkeys) {
           const KeySpec &ks = P.keys[k];
           const Slot &sl = P.slots[ks.slot];
-          uint64_t val = ((uint64_t)(kv[k] >> ((((uint32_t)row * sl.width) & 3u) * 8u))) & sl.vmask;
+          const uint32_t pos = rowpath ? sl.row_off : row * sl.width;
+          uint64_t val = ((uint64_t)(kv[k] >> ((pos & 3u) * 8u))) & sl.vmask;
           val = (val ^ sl.signbit) - sl.signbit;
           if (ks.rollup) val = rollup_value(val, ks);
           packed += (val - ks.lo) * ks.mul;
@@ -294,7 +301,8 @@ scan_filter_groupby_kernel(const __grid_constant__ ScanParams P) {
       uint64_t pre;
       if (small_plan) {
         const uint64_t raw = m == 0 ? mv[0] : m == 1 ? mv[1] : m == 2 ? mv[2] : mv[3];
-        pre = (raw >> ((((uint32_t)row * sl.width) & 7u) * 8u)) & sl.vmask;
+        const uint32_t pos = rowpath ? rpos + sl.row_off : row * sl.width;
+        pre = (raw >> ((pos & 7u) * 8u)) & sl.vmask;
         pre = (pre ^ sl.signbit) - sl.signbit;
       } else {
         const uint32_t *off = seg.bs_offsets[sl.bitset_idx];
@@ -414,10 +422,11 @@ scan_filter_groupby_kernel(const __grid_constant__ ScanParams P) {
     // ---- hand the passing rows to the aggregation stage in full batches of 32 ----
     // The list is a small per-warp queue: rows wait (across chunks) until a whole warp of them is
     // available, so that one DRAM round trip of gathers always serves 32 rows whatever the selectivity.
+    const bool rowpath = total <= P.row_thresh;  // sparse chunk: gather from the row-major mirror
     uint32_t head = 0;
     while (npend - head >= 32) {
       const uint2 e = list[head + lane];
-      process_row(P.segs[e.x], e.y);
+      process_row(P.segs[e.x], e.y, rowpath);
       head += 32;
     }
     if (head) {  // move the incomplete batch (< 32 rows) to the front
@@ -434,7 +443,7 @@ scan_filter_groupby_kernel(const __grid_constant__ ScanParams P) {
   // the last, incomplete batch
   if (lane < npend) {
     const uint2 e = list[lane];
-    process_row(P.segs[e.x], e.y);
+    process_row(P.segs[e.x], e.y, P.row_thresh != 0);
   }
 
   // counters: one atomic per warp

@@ -32,6 +32,8 @@ struct Slot {
   uint32_t sext;     // 1: sign-extend narrow values (i8/i16/i32) when widening to 64 bit
   uint32_t bitset;   // 1: BITSET column (values/offsets come from per-segment side tables)
   uint32_t bitset_idx;  // which bitset column of the table (index into SegDesc::bs_*)
+  uint32_t row_off;  // byte offset of the cell inside a row of the row-major mirror (naturally aligned)
+  uint32_t pad;
   uint64_t vmask;    // value mask of the element (0xff, 0xffff, 0xffffffff, ~0)
   uint64_t signbit;  // sign bit of the element when sext, else 0:  (x ^ signbit) - signbit sign-extends
 };
@@ -101,6 +103,7 @@ struct SegDesc {
   uint64_t cap;               // row capacity of the slab (multiple of kTileRows)
   const uint32_t *bs_values[kMaxBitsetCols];   // per bitset column: ids (uint32)
   const uint32_t *bs_offsets[kMaxBitsetCols];  // per bitset column: CSR offsets (nrows+1) or nullptr = 1 id/row
+  const uint8_t *rows;        // row-major mirror: row r at rows + r * ScanParams::row_stride, or nullptr
 };
 
 struct ScanParams {
@@ -117,6 +120,13 @@ struct ScanParams {
 
   uint32_t small_plan;  // <= 4 keys of <= 4 bytes and <= 4 metrics: register-staged gather path
   uint32_t tune;  // bit 1: stream the columns with an L2 evict_first policy; bit 2: group table evict_last
+
+  // Row-major mirror: at low selectivity every key / metric cell of a passing row costs
+  // a whole 64-byte DRAM atom in its column, but all of them share one or two atoms of the mirror row.
+  // A batch of passing rows is gathered from the mirror when the chunk that filled it had at most
+  // row_thresh passing rows (0: never) — the break-even of the two byte counts, computed by the planner.
+  uint32_t row_stride;
+  uint32_t row_thresh;
 
   // fixed-width columns the predicate reads with vector loads (prefetched one chunk ahead)
   uint32_t nfilter_slots;

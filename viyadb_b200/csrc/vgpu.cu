@@ -264,7 +264,10 @@ struct vgpu_ctx {
   int rank = 0, nranks = 1;
   // L2 persistence (group tables are pinned in L2 while the columns stream through it)
   uint64_t l2_persist_bytes = 0, l2_window_max = 0;
-  uint32_t tune = 2;  // VGPU_TUNE: bit 0 pin the group table in L2 (off: measured slower), bit 1 evict_first column streams (on)
+  // VGPU_TUNE: bit 0 pin the group table in L2 (off: measured slower), bit 1 evict_first column streams (on),
+  // bit 2 evict_last group table, bit 5 no next-chunk L2 prefetch, bit 6 build no row-major mirror,
+  // bit 7 never gather from the mirror, bit 8 always gather from the mirror (tests)
+  uint32_t tune = 2;
   // pool of pinned host blocks that back vgpu_result (D2H at full PCIe speed, no per-query
   // cudaMallocHost); shared with the results so that they may outlive the context
   std::shared_ptr<PinnedPool> pool = std::make_shared<PinnedPool>();
@@ -280,6 +283,7 @@ struct ColInfo {
   bool bitset;
   uint32_t bitset_idx;
   uint64_t off_per_row;  // bytes per row of the preceding fixed-width columns
+  uint32_t row_off;      // byte offset inside a row of the row-major mirror
 };
 
 struct SegmentData {
@@ -293,6 +297,8 @@ struct SegmentData {
   uint64_t bs_vcap[kMaxBitsetCols] = {0, 0, 0, 0};  // allocated ids / offsets (elements)
   uint64_t bs_ocap[kMaxBitsetCols] = {0, 0, 0, 0};
   bool bs_has_offsets[kMaxBitsetCols] = {false, false, false, false};  // CSR offsets in use (else one id per row)
+  uint8_t *rows = nullptr;     // row-major mirror of every column, or nullptr
+  uint64_t rows_cap = 0;       // rows the mirror was allocated for
   bool stats_pending = false;  // min/max computed on the device, not yet read back
   // ordered (to_ordered) min / max of the stored values per column; only fixed-width dimensions
   std::vector<uint64_t> omin, omax;
@@ -307,6 +313,7 @@ struct vgpu_table {
   uint32_t nbitsets = 0;
   uint64_t segment_size = 0;
   uint64_t row_bytes = 0;
+  uint32_t row_stride = 0;     // bytes per row of the row-major mirror (0: no mirror)
   std::vector<SegmentData> segs;
   SegDesc *d_segs = nullptr;
   size_t d_segs_cap = 0;
@@ -379,6 +386,7 @@ uint32_t fill64(cudaStream_t s, int sms, void *p, uint64_t n, uint64_t v) {
 // ---------------------------------------------------------------------------------------------
 void free_segment(SegmentData &sd) {
   if (sd.slab) cudaFree(sd.slab);
+  if (sd.rows) cudaFree(sd.rows);
   for (int b = 0; b < kMaxBitsetCols; ++b) {
     if (sd.bs_values[b]) cudaFree(sd.bs_values[b]);
     if (sd.bs_offsets[b]) cudaFree(sd.bs_offsets[b]);
@@ -399,6 +407,11 @@ void ensure_segment(vgpu_table *t, uint32_t seg_idx, uint64_t nrows) {
       CUDA_CK(cudaMalloc(&sd.slab, t->row_bytes * cap));
     }
     sd.cap = cap;
+    if (t->row_stride) {
+      // the mirror is an optimisation: without memory for it the columnar gathers serve every query
+      if (cudaMalloc(&sd.rows, (uint64_t)t->row_stride * cap + 64) == cudaSuccess) sd.rows_cap = cap;
+      else { sd.rows = nullptr; cudaGetLastError(); }
+    }
   } else {
     for (int b = 0; b < kMaxBitsetCols; ++b) sd.bs_n[b] = 0;  // buffers are kept and reused
   }
@@ -466,6 +479,37 @@ void compute_stats(vgpu_table *t, uint32_t seg_idx) {
   sd.stats_pending = true;
 }
 
+// (re)build the row-major mirror of a segment from its columns; stream-ordered after the column copies
+void build_row_mirror(vgpu_table *t, uint32_t seg_idx) {
+  vgpu_ctx *ctx = t->ctx;
+  SegmentData &sd = t->segs[seg_idx];
+  if (sd.rows == nullptr || sd.nrows == 0) return;
+  if (t->cols.size() > 32) fail(VGPU_ERR_UNSUPPORTED, "row mirror supports at most 32 columns");
+  RowsParams R{};
+  R.rows = sd.rows;
+  R.nrows = sd.nrows;
+  R.stride = t->row_stride;
+  R.ncols = (uint32_t)t->cols.size();
+  for (size_t c = 0; c < t->cols.size(); ++c) {
+    const ColInfo &ci = t->cols[c];
+    RowsCol &rc = R.cols[c];
+    rc.row_off = ci.row_off;
+    if (ci.bitset) {  // the first word a count-distinct needs: the id, or the CSR offset of the cell
+      rc.width = 4;
+      rc.src = reinterpret_cast<const uint8_t *>(sd.bs_has_offsets[ci.bitset_idx] ? sd.bs_offsets[ci.bitset_idx]
+                                                                                    : sd.bs_values[ci.bitset_idx]);
+    } else {
+      rc.width = ci.width;
+      rc.src = sd.slab + ci.off_per_row * sd.cap;
+    }
+  }
+  const uint32_t tile_rows = kRowsTileBytes / R.stride;
+  const uint64_t ntiles = (sd.nrows + tile_rows - 1) / tile_rows;
+  const int grid = (int)std::min<uint64_t>(ntiles, (uint64_t)ctx->sm_count * 8);
+  build_rows_kernel<<<grid, 256, 0, ctx->stream>>>(R);
+  CUDA_CK(cudaGetLastError());
+}
+
 // one batched read-back for every segment whose statistics are still on the device
 void fetch_stats(vgpu_table *t) {
   const size_t ncols = t->cols.size();
@@ -504,6 +548,7 @@ void upload_descs(vgpu_table *t) {
     h[i].slab = sd.slab;
     h[i].nrows = sd.valid ? sd.nrows : 0;
     h[i].cap = sd.cap;
+    h[i].rows = sd.rows;
     for (int b = 0; b < kMaxBitsetCols; ++b) {
       h[i].bs_values[b] = sd.bs_values[b];
       h[i].bs_offsets[b] = sd.bs_has_offsets[b] ? sd.bs_offsets[b] : nullptr;
@@ -547,6 +592,7 @@ struct Planner {
     sl.sext = ci.sext;
     sl.bitset = ci.bitset;
     sl.bitset_idx = ci.bitset_idx;
+    sl.row_off = ci.row_off;
     if (ci.bitset) {  // ids / CSR offsets are uint32
       sl.width = 4;
       sl.sext = 0;
@@ -1072,6 +1118,21 @@ int vgpu_table_create(vgpu_ctx *ctx, const vgpu_schema *schema, vgpu_table **out
       t->cols.push_back(ci);
     }
     t->row_bytes = off;
+    // Row-major mirror: cells ordered by decreasing width so that each is naturally aligned, the row
+    // padded to the widest cell (8-byte cells need 8-byte aligned rows for the aligned-word gathers).
+    if (!(ctx->tune & 64u) && schema->ncols <= 32) {
+      uint32_t roff = 0, align = 4;
+      for (uint32_t w : {8u, 4u, 2u, 1u})
+        for (auto &ci : t->cols) {
+          const uint32_t cw = ci.bitset ? 4u : ci.width;
+          if (cw != w) continue;
+          ci.row_off = roff;
+          roff += cw;
+          align = std::max(align, cw);
+        }
+      t->row_stride = (uint32_t)round_up(roff, align);
+      if (t->row_stride > kRowsTileBytes / 32) t->row_stride = 0;  // very wide rows: no mirror
+    }
     *out = t.release();
   });
 }
@@ -1156,6 +1217,7 @@ int vgpu_segment_put(vgpu_table *t, uint32_t seg_idx, uint64_t nrows, const void
         CUDA_CK(cudaMemsetAsync(dst + nrows * ci.width, 0, (sd.cap - nrows) * ci.width, ctx->stream));
     }
     compute_stats(t, seg_idx);
+    build_row_mirror(t, seg_idx);
     CUDA_CK(cudaStreamSynchronize(ctx->stream));  // host buffers may be reused by the caller now
     sd.valid = true;
   });
@@ -1212,6 +1274,7 @@ int vgpu_segment_generate(vgpu_table *t, uint32_t seg_idx, uint64_t nrows, const
       CUDA_CK(cudaGetLastError());
     }
     compute_stats(t, seg_idx);
+    build_row_mirror(t, seg_idx);
     sd.valid = true;
   });
 }
@@ -1268,6 +1331,7 @@ uint64_t vgpu_table_bytes(const vgpu_table *t) {
   for (auto &sd : t->segs) {
     if (!sd.valid) continue;
     n += sd.cap * t->row_bytes;
+    if (sd.rows) n += sd.rows_cap * t->row_stride;
     for (int b = 0; b < kMaxBitsetCols; ++b) {
       n += sd.bs_n[b] * 4;
       if (sd.bs_has_offsets[b]) n += (sd.nrows + 1) * 4;
@@ -1829,6 +1893,40 @@ int vgpu_query_agg(vgpu_table *t, const vgpu_plan *plan, vgpu_result **out) {
     for (uint32_t k = 0; k < P.nkeys; ++k)
       if (P.slots[P.keys[k].slot].width > 4) P.small_plan = 0;
 
+    // ---- row-major mirror or columns for the cells of passing rows? (per chunk, in the kernel) ----
+    // Bytes of DRAM atoms (64 B) each way for a 512-row chunk with n passing rows: the mirror costs the
+    // atoms one row's cells span; a column costs every atom that holds at least one passing row. Columns
+    // the predicate has just streamed are in L2 either way.
+    P.row_stride = t->row_stride;
+    P.row_thresh = 0;
+    if (t->row_stride && P.small_plan && !(ctx->tune & 128u) && (plan->nnodes > 0 || (ctx->tune & 256u))) {
+      bool all_mirrored = true;
+      for (uint32_t s : q.active) all_mirrored = all_mirrored && t->segs[s].rows != nullptr;
+      uint32_t lo_off = ~0u, hi_off = 0;
+      std::vector<uint32_t> widths;
+      auto payload = [&](uint32_t slot) {
+        const Slot &sl = P.slots[slot];
+        lo_off = std::min(lo_off, sl.row_off);
+        hi_off = std::max(hi_off, sl.row_off + sl.width);
+        bool streamed = false;
+        for (uint32_t f = 0; f < P.nfilter_slots; ++f) streamed = streamed || P.filter_slots[f] == slot;
+        if (!streamed) widths.push_back(sl.width);
+      };
+      for (uint32_t k = 0; k < P.nkeys; ++k) payload(P.keys[k].slot);
+      for (uint32_t m = 0; m < P.nmetrics; ++m) payload(P.mets[m].slot);
+      if (all_mirrored && !widths.empty()) {
+        const double span = (double)(hi_off - lo_off);
+        const double row_cost = 64.0 * (1.0 + (span - 1.0) / 64.0);
+        for (uint32_t n = 1; n <= (uint32_t)kChunkRows; ++n) {
+          double col_cost = 0;
+          for (uint32_t w : widths)
+            col_cost += 8.0 * w * 64.0 * (1.0 - std::pow(1.0 - (double)n / kChunkRows, 64.0 / w));
+          if (n * row_cost < col_cost) P.row_thresh = n; else break;
+        }
+      }
+      if (all_mirrored && (ctx->tune & 256u)) P.row_thresh = kChunkRows;  // tests: every batch from the mirror
+    }
+
     // ---- dense or hash ----
     unsigned __int128 cells128 = 1;
     bool fits64 = true;
@@ -1850,6 +1948,7 @@ int vgpu_query_agg(vgpu_table *t, const vgpu_plan *plan, vgpu_result **out) {
     }
     q.hash_mode = !dense;
     q.wide = wide;
+    if (wide) P.row_thresh = 0;  // the wide-tuple path gathers from the columns
     for (uint32_t k = 0; k < plan->nkeys; ++k) P.keys[k].fzero = wide && type_float(t->cols[plan->keys[k].col].type);
     if (ctx->trace) {
       fprintf(stderr, "[vgpu r%d] cells=%llu dense_limit=%llu dense=%d active_rows=%llu global=%llu\n", ctx->rank, (unsigned long long)cells, (unsigned long long)dense_limit, (int)dense, (unsigned long long)q.active_rows, (unsigned long long)global_active_rows);
