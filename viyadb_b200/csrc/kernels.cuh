@@ -585,6 +585,7 @@ __global__ void __launch_bounds__(256) merge_records_kernel(const __grid_constan
 // ---------------------------------------------------------------------------------------------
 struct ExtractKey {
   uint64_t lo, div, mod;  // value = lo + (packed / div) % mod   (mod == 0: no modulo)
+  uint64_t lut;           // non-zero: the digit is the rank of the value among the set bits (KeySpec::lut)
   uint32_t width;
   uint32_t pad;
   void *out;
@@ -652,6 +653,11 @@ extract_groups_kernel(const __grid_constant__ ExtractParams E) {
         uint64_t q = packed / ek.div;
         if (ek.mod) q %= ek.mod;
         v = ek.lo + q;
+        if (ek.lut) {  // the q-th set bit
+          uint64_t x = ek.lut;
+          for (uint64_t i = 0; i < q; ++i) x &= x - 1;
+          v = (uint64_t)(__ffsll((long long)x) - 1);
+        }
       }
       switch (ek.width) {
         case 1: reinterpret_cast<uint8_t *>(ek.out)[pos] = (uint8_t)v; break;

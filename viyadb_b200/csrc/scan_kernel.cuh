@@ -97,13 +97,65 @@ __device__ __forceinline__ uint64_t bitset_card(const SegDesc &seg, uint32_t bid
   return (uint64_t)(__ldg(off + row + 1) - __ldg(off + row));
 }
 
+// mask of one vectorisable leaf over the 16 rows in v
+__device__ __forceinline__ uint32_t leaf_mask16(const PInstr &in, const uint32_t (&v)[kRowsPerThread]) {
+  uint32_t m = 0;
+  const uint32_t cls = in.cls;
+  const uint32_t a = (uint32_t)in.arg;
+  if (cls == C_EQ32) {
+#pragma unroll
+    for (int i = 0; i < kRowsPerThread; ++i) if (v[i] == a) m |= 1u << i;
+  } else if (cls == C_LT32) {
+    const uint32_t bias = in.bias;
+#pragma unroll
+    for (int i = 0; i < kRowsPerThread; ++i) if ((v[i] ^ bias) < a) m |= 1u << i;
+  } else if (cls == C_RNG32) {
+    const uint32_t bias = in.bias, len = in.arg2;
+    if (bias == 0) {
+#pragma unroll
+      for (int i = 0; i < kRowsPerThread; ++i) if ((v[i] - a) < len) m |= 1u << i;
+    } else {
+#pragma unroll
+      for (int i = 0; i < kRowsPerThread; ++i) if (((v[i] ^ bias) - a) < len) m |= 1u << i;
+    }
+  } else {  // C_LUT64: membership in a set of codes < 64 — one shift per row whatever the list length
+    const uint64_t lut = in.arg;
+#pragma unroll
+    for (int i = 0; i < kRowsPerThread; ++i) {
+      uint64_t t;
+      asm("shr.b64 %0, %1, %2;" : "=l"(t) : "l"(lut), "r"(v[i]));  // shift amounts >= 64 give 0
+      if (t & 1ull) m |= 1u << i;
+    }
+  }
+  return m;
+}
+
 // row0 = first row of the lane inside the segment (chunk_row0 + lane*4)
 __device__ __forceinline__ uint32_t eval_predicate(const ScanParams &P, const SegDesc &seg,
                                                    uint32_t row0, uint64_t pol) {
+  uint32_t v[kRowsPerThread];
+  if (P.conj) {
+    // The common shape — a conjunction of up to 4 vectorisable leaves — with the program counter
+    // unrolled: every operand of a leaf is a constant-bank operand, nothing is interpreted.
+    uint32_t m = 0xffffu;
+#pragma unroll
+    for (int pc = 0; pc < 4; ++pc) {
+      if (pc < P.nprog) {
+        const PInstr &in = P.prog[pc];
+        if (pc == 0 || in.slot != P.prog[pc > 0 ? pc - 1 : 0].slot) {
+          const Slot &sl = P.slots[in.slot];
+          load_vec16(seg.slab + sl.off * seg.cap, sl.width, row0, v, pol);
+        }
+        uint32_t lm = leaf_mask16(in, v);
+        if (in.neg) lm ^= 0xffffu;
+        m &= lm;
+      }
+    }
+    return m;
+  }
   uint32_t stk[kStackDepth];
 #pragma unroll
   for (int i = 0; i < kStackDepth; ++i) stk[i] = 0;
-  uint32_t v[kRowsPerThread];
   int cached = -1;
   for (uint32_t pc = 0; pc < P.nprog; ++pc) {
     const PInstr &in = P.prog[pc];
@@ -136,27 +188,7 @@ __device__ __forceinline__ uint32_t eval_predicate(const ScanParams &P, const Se
           load_vec16(seg.slab + sl.off * seg.cap, sl.width, row0, v, pol);
           cached = in.slot;
         }
-        const uint32_t a = (uint32_t)in.arg;
-        if (cls == C_EQ32) {
-#pragma unroll
-          for (int i = 0; i < kRowsPerThread; ++i) if (v[i] == a) m |= 1u << i;
-        } else if (cls == C_LT32) {
-          const uint32_t bias = in.bias;
-#pragma unroll
-          for (int i = 0; i < kRowsPerThread; ++i) if ((v[i] ^ bias) < a) m |= 1u << i;
-        } else if (cls == C_RNG32) {
-          const uint32_t bias = in.bias, len = in.arg2;
-#pragma unroll
-          for (int i = 0; i < kRowsPerThread; ++i) if (((v[i] ^ bias) - a) < len) m |= 1u << i;
-        } else {  // C_LUT64: membership in a set of codes < 64 — one shift per row whatever the list length
-          const uint64_t lut = in.arg;
-#pragma unroll
-          for (int i = 0; i < kRowsPerThread; ++i) {
-            uint64_t t;
-            asm("shr.b64 %0, %1, %2;" : "=l"(t) : "l"(lut), "r"(v[i]));  // shift amounts >= 64 give 0
-            if (t & 1ull) m |= 1u << i;
-          }
-        }
+        m = leaf_mask16(in, v);
       }
       if (in.neg) m ^= 0xffffu;
       if (kind == P_PUSH) {
@@ -230,24 +262,32 @@ scan_filter_groupby_kernel(const __grid_constant__ ScanParams P) {
       // are 8-byte aligned, so the position of a cell inside its aligned word depends on the row only.
       // rowpath (warp-uniform) only changes the addresses: the cells come from the row-major mirror,
       // where they share one or two 64-byte DRAM atoms instead of costing one atom per column.
-      const uint8_t *rb = seg.rows + (uint64_t)row * P.row_stride;
+      if (rowpath) {
+        const uint8_t *rb = seg.rows + (uint64_t)row * P.row_stride;
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        if (k < P.nkeys) {
-          const Slot &sl = P.slots[P.keys[k].slot];
-          const uint8_t *col = seg.slab + sl.off * seg.cap + (uint64_t)row * sl.width;
-          kv[k] = gather_raw32(rowpath ? rb + sl.row_off : col);
+        for (int k = 0; k < 4; ++k)
+          if (k < P.nkeys) kv[k] = gather_raw32(rb + P.slots[P.keys[k].slot].row_off);
+#pragma unroll
+        for (int m = 0; m < 4; ++m)
+          if (m < P.nmetrics) mv[m] = gather_raw64(rb + P.slots[P.mets[m].slot].row_off);
+      } else {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          if (k < P.nkeys) {
+            const Slot &sl = P.slots[P.keys[k].slot];
+            kv[k] = gather_raw32(seg.slab + sl.off * seg.cap + (uint64_t)row * sl.width);
+          }
         }
-      }
 #pragma unroll
-      for (int m = 0; m < 4; ++m) {
-        if (m < P.nmetrics) {
-          const Slot &sl = P.slots[P.mets[m].slot];
-          const uint32_t *off = seg.bs_offsets[sl.bitset_idx];
-          const uint32_t *vals = seg.bs_values[sl.bitset_idx];
-          const uint8_t *fixed = seg.slab + sl.off * seg.cap + (uint64_t)row * sl.width;
-          const uint8_t *bits = reinterpret_cast<const uint8_t *>((off == nullptr ? vals : off) + row);
-          mv[m] = gather_raw64(rowpath ? rb + sl.row_off : (sl.bitset ? bits : fixed));
+        for (int m = 0; m < 4; ++m) {
+          if (m < P.nmetrics) {
+            const Slot &sl = P.slots[P.mets[m].slot];
+            const uint32_t *off = seg.bs_offsets[sl.bitset_idx];
+            const uint32_t *vals = seg.bs_values[sl.bitset_idx];
+            const uint8_t *fixed = seg.slab + sl.off * seg.cap + (uint64_t)row * sl.width;
+            const uint8_t *bits = reinterpret_cast<const uint8_t *>((off == nullptr ? vals : off) + row);
+            mv[m] = gather_raw64(sl.bitset ? bits : fixed);
+          }
         }
       }
     }
@@ -264,7 +304,9 @@ scan_filter_groupby_kernel(const __grid_constant__ ScanParams P) {
           uint64_t val = ((uint64_t)(kv[k] >> ((pos & 3u) * 8u))) & sl.vmask;
           val = (val ^ sl.signbit) - sl.signbit;
           if (ks.rollup) val = rollup_value(val, ks);
-          packed += (val - ks.lo) * ks.mul;
+          if (ks.lut) val = (uint64_t)__popcll(ks.lut & ((1ull << val) - 1ull));  // rank inside the IN list
+          else val -= ks.lo;
+          packed += val * ks.mul;
         }
       }
     } else {
@@ -274,7 +316,9 @@ scan_filter_groupby_kernel(const __grid_constant__ ScanParams P) {
         const uint8_t *a = seg.slab + sl.off * seg.cap + (uint64_t)row * sl.width;
         uint64_t val = gather_finish(gather_raw64(a), a, sl.vmask, sl.signbit);
         if (ks.rollup) val = rollup_value(val, ks);
-        packed += (val - ks.lo) * ks.mul;
+        if (ks.lut) val = (uint64_t)__popcll(ks.lut & ((1ull << val) - 1ull));
+        else val -= ks.lo;
+        packed += val * ks.mul;
       }
     }
     uint64_t cell;
@@ -336,7 +380,7 @@ scan_filter_groupby_kernel(const __grid_constant__ ScanParams P) {
   const uint32_t cps = P.tiles_per_seg;
   const uint32_t nwarps = gridDim.x * kWarps;
   const uint32_t step_seg = nwarps / cps, step_chunk = nwarps - step_seg * cps;
-  uint32_t si, ci;
+  uint32_t si, ci, nchunk = 0;
   {
     const uint32_t first = blockIdx.x * kWarps + warp;
     si = first / cps;
@@ -354,7 +398,7 @@ scan_filter_groupby_kernel(const __grid_constant__ ScanParams P) {
     ci = nci;
     if (chunk_row >= nrows) continue;  // uniform per warp
     // a full group table / distinct set makes the host grow it and run again: stop wasting time
-    if (can_overflow) {
+    if (can_overflow && (++nchunk & 15u) == 0) {
       unsigned long long f = 0;
       if (lane == 0) f = *reinterpret_cast<volatile unsigned long long *>(&P.counters[1]);
       if (__shfl_sync(0xffffffffu, f, 0) != 0ull) break;
@@ -366,7 +410,13 @@ scan_filter_groupby_kernel(const __grid_constant__ ScanParams P) {
     if (nsi < P.nactive && !(P.tune & 32u)) {
       const SegDesc &nseg = P.segs[P.active[nsi]];
       const uint32_t nrow = nci * kChunkRows;
-      if (nrow < (uint32_t)nseg.nrows) {
+      if (nrow < (uint32_t)nseg.nrows && !(P.tune & 8192u)) {
+        // one bulk L2 prefetch (TMA unit) per predicate column, lane f taking column f
+        if (lane < P.nfilter_slots) {
+          const uint8_t *a = nseg.slab + P.pf_off[lane] * nseg.cap + (uint64_t)nrow * P.pf_width[lane];
+          asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a), "r"((uint32_t)kChunkRows * P.pf_width[lane]) : "memory");
+        }
+      } else if (nrow < (uint32_t)nseg.nrows) {
         for (uint32_t f = 0; f < P.nfilter_slots; ++f) {
           const Slot &sl = P.slots[P.filter_slots[f]];
           if (lane * 128u < (uint32_t)kChunkRows * sl.width)
@@ -389,40 +439,46 @@ scan_filter_groupby_kernel(const __grid_constant__ ScanParams P) {
     if (__ballot_sync(0xffffffffu, mask != 0) == 0) continue;
     my_passed += __popc(mask);
 
-    // ---- compaction: packed prefix sum of the four per-sub-chunk counts (8 bits each, <= 128) ----
-    uint32_t cnt = __popc(mask & 0xfu) | (__popc(mask & 0xf0u) << 8) | (__popc(mask & 0xf00u) << 16) |
-                   (__popc(mask & 0xf000u) << 24);
-    uint32_t incl = cnt;
+    // ---- compaction: one warp prefix sum of the per-lane counts, rows appended to the list ----
+    const uint32_t n = __popc(mask);
+    uint32_t incl = n;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
       uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
       if (lane >= o) incl += t;
     }
-    const uint32_t tot = __shfl_sync(0xffffffffu, incl, 31);
-    // a sub-chunk total of 128 would need 8 bits + the packed adds never carry (max field 128)
-    const uint32_t excl = incl - cnt;
-    const uint32_t t0 = tot & 0xffu, t1 = (tot >> 8) & 0xffu, t2 = (tot >> 16) & 0xffu, t3 = tot >> 24;
-    const uint32_t total = t0 + t1 + t2 + t3;
+    const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
     {
-      uint32_t base = 0;
-#pragma unroll
-      for (int s = 0; s < kSub; ++s) {
-        uint32_t pos = base + ((excl >> (8 * s)) & 0xffu);
-        uint32_t nib = (mask >> (4 * s)) & 0xfu;
-#pragma unroll
-        for (int j = 0; j < kVec; ++j) {
-          if (nib & (1u << j)) list[npend + pos++] = make_uint2(seg_index, chunk_row + s * kSubChunk + lane * kVec + j);
+      uint32_t pos = npend + incl - n;
+      const uint32_t base_row = chunk_row + lane * kVec;
+      if (total <= 96) {  // sparse: a lane holds few passing rows, visit the set bits only
+        while (mask) {
+          const uint32_t b = __ffs(mask) - 1;
+          mask &= mask - 1;
+          list[pos++] = make_uint2(seg_index, base_row + (b >> 2) * kSubChunk + (b & 3u));
         }
-        base += (s == 0) ? t0 : (s == 1) ? t1 : (s == 2) ? t2 : t3;
+      } else {
+#pragma unroll
+        for (int b = 0; b < kRowsPerThread; ++b)
+          if (mask & (1u << b)) list[pos++] = make_uint2(seg_index, base_row + (b >> 2) * kSubChunk + (b & 3));
       }
     }
     __syncwarp();
+    const bool rowpath = total <= P.row_thresh;  // sparse chunk: gather from the row-major mirror
+    if (rowpath && (P.tune & 2048u)) {  // start pulling the mirror rows into L2 now: they are gathered a batch later
+      const uint8_t *rows = seg.rows;
+#pragma unroll 1
+      for (uint32_t i = lane; i < total; i += 32) {
+        const uint8_t *a = rows + (uint64_t)list[npend + i].y * P.row_stride + P.row_lo;
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(a));
+        if (((uint32_t)(uintptr_t)a & 63u) + P.row_span > 64u) asm volatile("prefetch.global.L2 [%0];" ::"l"(a + P.row_span - 1));
+      }
+    }
     npend += total;
 
     // ---- hand the passing rows to the aggregation stage in full batches of 32 ----
     // The list is a small per-warp queue: rows wait (across chunks) until a whole warp of them is
     // available, so that one DRAM round trip of gathers always serves 32 rows whatever the selectivity.
-    const bool rowpath = total <= P.row_thresh;  // sparse chunk: gather from the row-major mirror
     uint32_t head = 0;
     while (npend - head >= 32) {
       const uint2 e = list[head + lane];

@@ -77,6 +77,9 @@ struct KeySpec {
   uint64_t rule_boundary[kMaxRules];
   uint64_t lo;    // subtracted from the (rolled-up) value
   uint64_t mul;   // cell index / packed key = sum (v - lo) * mul
+  uint64_t lut;   // non-zero: the predicate restricts this key to the codes whose bits are set (an IN list over
+                  // codes < 64 in a top-level conjunction); the key is numbered by its rank in the set instead
+                  // of v - lo, which shrinks the dense key domain to the values that can actually occur
 };
 
 enum AccOp : uint8_t {
@@ -127,10 +130,14 @@ struct ScanParams {
   // row_thresh passing rows (0: never) — the break-even of the two byte counts, computed by the planner.
   uint32_t row_stride;
   uint32_t row_thresh;
+  uint32_t row_lo, row_span;  // byte range of a mirror row the query's keys and metrics occupy (L2 prefetch at enqueue)
+  uint32_t conj;              // predicate is a conjunction of at most 4 vectorisable leaves (unrolled fast path)
 
   // fixed-width columns the predicate reads with vector loads (prefetched one chunk ahead)
   uint32_t nfilter_slots;
   uint8_t filter_slots[kMaxSlots];
+  uint8_t pf_width[kMaxSlots];   // per predicate column f: element width and bytes-per-row offset of the column
+  uint64_t pf_off[kMaxSlots];    // in the slab (bulk L2 prefetch of the next chunk, lane f takes column f)
 
   // predicate
   uint32_t nprog;

@@ -266,7 +266,10 @@ struct vgpu_ctx {
   uint64_t l2_persist_bytes = 0, l2_window_max = 0;
   // VGPU_TUNE: bit 0 pin the group table in L2 (off: measured slower), bit 1 evict_first column streams (on),
   // bit 2 evict_last group table, bit 5 no next-chunk L2 prefetch, bit 6 build no row-major mirror,
-  // bit 7 never gather from the mirror, bit 8 always gather from the mirror (tests)
+  // bit 7 never gather from the mirror, bit 8 always gather from the mirror (tests), bit 11 L2 prefetch of mirror
+  // rows at enqueue (off: measured slower, it fetches 128-byte lines), bit 12 no unrolled conjunction fast path
+  // (always the stack interpreter), bit 13 per-lane instead of bulk L2 prefetch of the next chunk, bit 14 no
+  // tightening of key domains from the predicate
   uint32_t tune = 2;
   // pool of pinned host blocks that back vgpu_result (D2H at full PCIe speed, no per-query
   // cudaMallocHost); shared with the results so that they may outlive the context
@@ -1793,6 +1796,17 @@ int vgpu_query_agg(vgpu_table *t, const vgpu_plan *plan, vgpu_result **out) {
       for (uint32_t f = 0; f < P.nfilter_slots; ++f) seen = seen || P.filter_slots[f] == in.slot;
       if (!seen) P.filter_slots[P.nfilter_slots++] = in.slot;
     }
+    for (uint32_t f = 0; f < P.nfilter_slots; ++f) {
+      P.pf_width[f] = (uint8_t)P.slots[P.filter_slots[f]].width;
+      P.pf_off[f] = P.slots[P.filter_slots[f]].off;
+    }
+    // conjunction of at most 4 vectorisable leaves: the kernel's unrolled fast path
+    P.conj = P.nprog >= 1 && P.nprog <= 4 && !(ctx->tune & 4096u);
+    for (uint32_t i = 0; i < P.nprog && P.conj; ++i) {
+      const PInstr &in = P.prog[i];
+      const bool vec = in.cls == C_EQ32 || in.cls == C_LT32 || in.cls == C_RNG32 || in.cls == C_LUT64;
+      if (!vec || in.kind != (i == 0 ? P_PUSH : P_AND_LEAF)) P.conj = 0;
+    }
 
     // ---- segment loop bookkeeping + pruning (scan.cc:42-51) ----
     for (uint32_t s = 0; s < t->segs.size(); ++s) {
@@ -1860,8 +1874,29 @@ int vgpu_query_agg(vgpu_table *t, const vgpu_plan *plan, vgpu_result **out) {
           if (ks.micro) lo = host_trunc_year_seconds(lo / 1000000ull) * 1000000ull;
           else lo = host_trunc_year_seconds(lo);
         }
+        // A top-level conjunction restricts what a key can be for passing rows: tighten the key domain
+        // (unsigned keys of at most 4 bytes, no rollup; leaf arguments are raw zero-extended values).
+        uint64_t lut = 0;
+        if (P.conj && !ks.rollup && !type_signed(ci.type) && ci.width <= 4 && !(ctx->tune & 16384u)) {
+          for (uint32_t i = 0; i < P.nprog; ++i) {
+            const PInstr &in = P.prog[i];
+            if (in.slot != ks.slot || in.neg) continue;
+            const uint64_t a = (uint32_t)in.arg;
+            if (in.cls == C_EQ32) { lo = std::max(lo, a); hi = std::min(hi, a); }
+            else if (in.cls == C_RNG32 && in.bias == 0) { lo = std::max(lo, a); hi = std::min(hi, a + in.arg2 - 1); }
+            else if (in.cls == C_LT32 && in.bias == 0 && a > 0) { hi = std::min(hi, a - 1); }
+            else if (in.cls == C_LUT64) lut = lut ? (lut & in.arg) : in.arg;
+          }
+          if (lo > hi) hi = lo;  // nothing can pass: any one-value domain will do
+          if (lut) {
+            for (uint32_t b = 0; b < 64; ++b)
+              if (b < lo || b > hi) lut &= ~(1ull << b);
+          }
+        }
         kr.lo = lo;
         kr.range = hi - lo + 1;  // wraps to 0 for the full 64-bit domain
+        if (lut) { kr.lo = 0; kr.range = (uint64_t)__builtin_popcountll(lut); }
+        P.keys[k].lut = lut;
       }
       q.ranges[k] = kr;
     }
@@ -1914,6 +1949,7 @@ int vgpu_query_agg(vgpu_table *t, const vgpu_plan *plan, vgpu_result **out) {
       };
       for (uint32_t k = 0; k < P.nkeys; ++k) payload(P.keys[k].slot);
       for (uint32_t m = 0; m < P.nmetrics; ++m) payload(P.mets[m].slot);
+      if (lo_off < hi_off) { P.row_lo = lo_off; P.row_span = hi_off - lo_off; }
       if (all_mirrored && !widths.empty()) {
         const double span = (double)(hi_off - lo_off);
         const double row_cost = 64.0 * (1.0 + (span - 1.0) / 64.0);
@@ -2220,6 +2256,7 @@ int vgpu_query_agg(vgpu_table *t, const vgpu_plan *plan, vgpu_result **out) {
         const ColInfo &ci = t->cols[plan->keys[k].col];
         d_keys[k] = scratch.alloc<uint8_t>(bound * ci.width);
         E.keys[k].lo = q.ranges[k].lo;
+        E.keys[k].lut = P.keys[k].lut;
         E.keys[k].div = P.keys[k].mul;
         E.keys[k].mod = (k + 1 < plan->nkeys) ? q.ranges[k].range : 0;
         E.keys[k].width = ci.width;
