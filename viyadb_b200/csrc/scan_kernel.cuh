@@ -97,6 +97,13 @@ __device__ __forceinline__ uint64_t bitset_card(const SegDesc &seg, uint32_t bid
   return (uint64_t)(__ldg(off + row + 1) - __ldg(off + row));
 }
 
+// the segment a warp is working in: a copy of its descriptor in registers (warp-uniform)
+struct CurSeg {
+  const uint8_t *slab;
+  const uint8_t *rows;
+  uint32_t cap, nrows, index;
+};
+
 // mask of one vectorisable leaf over the 16 rows in v
 __device__ __forceinline__ uint32_t leaf_mask16(const PInstr &in, const uint32_t (&v)[kRowsPerThread]) {
   uint32_t m = 0;
@@ -131,7 +138,7 @@ __device__ __forceinline__ uint32_t leaf_mask16(const PInstr &in, const uint32_t
 }
 
 // row0 = first row of the lane inside the segment (chunk_row0 + lane*4)
-__device__ __forceinline__ uint32_t eval_predicate(const ScanParams &P, const SegDesc &seg,
+__device__ __forceinline__ uint32_t eval_predicate(const ScanParams &P, const CurSeg &seg,
                                                    uint32_t row0, uint64_t pol) {
   uint32_t v[kRowsPerThread];
   if (P.conj) {
@@ -169,6 +176,7 @@ __device__ __forceinline__ uint32_t eval_predicate(const ScanParams &P, const Se
         m = 0;
       } else if (cls == C_GEN) {
         const Slot &sl = P.slots[in.slot];
+        const SegDesc &sd = P.segs[seg.index];
 #pragma unroll 1
         for (int s = 0; s < kSub; ++s) {
 #pragma unroll 1
@@ -176,7 +184,7 @@ __device__ __forceinline__ uint32_t eval_predicate(const ScanParams &P, const Se
             uint32_t row = row0 + s * kSubChunk + j;
             uint64_t val = 0;
             if (row < seg.nrows) {  // scalar path must not read past the logical end of CSR tables
-              val = sl.bitset ? bitset_card(seg, sl.bitset_idx, row)
+              val = sl.bitset ? bitset_card(sd, sl.bitset_idx, row)
                               : load_elem(seg.slab + sl.off * seg.cap + (uint64_t)row * sl.width, sl.width, sl.sext);
             }
             if (gen_compare(in.gcls, in.gop, val, in.arg)) m |= 1u << (s * 4 + j);
@@ -212,7 +220,7 @@ __device__ __forceinline__ uint32_t eval_predicate(const ScanParams &P, const Se
 
 // Wide key tuples (hash_mode 2): gather the key words of one row and find / claim its slot. Out of line
 // so that its local array does not cost the common paths registers.
-__device__ __noinline__ uint64_t wide_row_cell(const ScanParams &P, const SegDesc &seg, uint32_t row) {
+__device__ __noinline__ uint64_t wide_row_cell(const ScanParams &P, const CurSeg &seg, uint32_t row) {
   uint64_t kw[kMaxKeys];
   for (uint32_t k = 0; k < P.nkeys; ++k) {
     const KeySpec &ks = P.keys[k];
@@ -232,13 +240,16 @@ __device__ __noinline__ uint64_t wide_row_cell(const ScanParams &P, const SegDes
 #ifndef VGPU_MIN_CTAS
 #define VGPU_MIN_CTAS 3
 #endif
-__global__ void __launch_bounds__(kThreads, VGPU_MIN_CTAS)
+// kMinCtas CTAs per SM: caps the registers (3 -> 80, 4 -> 64); the host picks (VGPU_CTAS, default VGPU_MIN_CTAS)
+template <int kMinCtas>
+__global__ void __launch_bounds__(kThreads, kMinCtas)
 scan_filter_groupby_kernel(const __grid_constant__ ScanParams P) {
-  __shared__ uint2 s_list[kWarps][kListCap];  // (segment index, row) of passing rows waiting for aggregation
+  __shared__ uint32_t s_list[kWarps][kListCap];  // rows (of the warp's current segment) waiting for aggregation
 
   const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  uint2 *list = s_list[warp];
+  uint32_t *list = s_list[warp];
   uint32_t npend = 0;  // rows waiting in the list (warp-uniform)
+  CurSeg seg{};        // the segment of the warp's current work unit
   uint32_t my_passed = 0;
   __shared__ uint32_t s_cursor[kMaxDistinct];  // pairs this CTA appended per count-distinct metric
   if (threadIdx.x < kMaxDistinct) s_cursor[threadIdx.x] = 0;
@@ -247,46 +258,42 @@ scan_filter_groupby_kernel(const __grid_constant__ ScanParams P) {
   const uint64_t pol = make_stream_policy((P.tune & 2u) != 0);
   const uint64_t tpol = make_table_policy((P.tune & 4u) != 0);
 
-  // ---- aggregate one passing row (one row per lane, rows may come from different segments) ----
+  // ---- aggregate one passing row of the current segment (one row per lane) ----
   // fast path: up to 4 keys of at most 4 bytes and up to 4 metrics, staged in 12 registers
   const bool small_plan = P.small_plan != 0 && P.hash_mode != 2;  // uniform
-  auto process_row = [&](const SegDesc &seg, const uint32_t row, const bool rowpath) {
+  auto process_row = [&](const uint32_t row, const bool rowpath) {
     uint32_t kv[4];
     uint64_t mv[4];
+    const SegDesc &sd = P.segs[seg.index];  // side tables of bitset columns (uniform address)
     // position of a cell in bytes from an 8-byte aligned base: inside its column, or inside the mirror
     const uint32_t rpos = row * P.row_stride;
     if (small_plan) {
       // one DRAM round trip per row: every key and metric cell (or the first word a bitset cell
-      // needs) is requested before anything depends on it; branch-free and fully unrolled, so the
-      // loads issue back to back and the values stay in registers. Slab, mirror and side-table bases
-      // are 8-byte aligned, so the position of a cell inside its aligned word depends on the row only.
-      // rowpath (warp-uniform) only changes the addresses: the cells come from the row-major mirror,
-      // where they share one or two 64-byte DRAM atoms instead of costing one atom per column.
-      if (rowpath) {
+      // needs) is requested before anything depends on it; fully unrolled, so the loads issue back to
+      // back and the values stay in registers. Slab, mirror and side-table bases are 8-byte aligned, so the
+      // position of a cell inside its aligned word depends on the row only.
+      if (rowpath) {  // warp-uniform: the cells of a row share one or two 64-byte atoms of the mirror
         const uint8_t *rb = seg.rows + (uint64_t)row * P.row_stride;
 #pragma unroll
         for (int k = 0; k < 4; ++k)
-          if (k < P.nkeys) kv[k] = gather_raw32(rb + P.slots[P.keys[k].slot].row_off);
+          if (k < P.nkeys) kv[k] = gather_raw32(rb + P.keys[k].row_off);
 #pragma unroll
         for (int m = 0; m < 4; ++m)
-          if (m < P.nmetrics) mv[m] = gather_raw64(rb + P.slots[P.mets[m].slot].row_off);
+          if (m < P.nmetrics) mv[m] = gather_raw64(rb + P.mets[m].row_off);
       } else {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          if (k < P.nkeys) {
-            const Slot &sl = P.slots[P.keys[k].slot];
-            kv[k] = gather_raw32(seg.slab + sl.off * seg.cap + (uint64_t)row * sl.width);
-          }
-        }
+        for (int k = 0; k < 4; ++k)
+          if (k < P.nkeys) kv[k] = gather_raw32(seg.slab + P.keys[k].col_off * seg.cap + (uint64_t)row * P.keys[k].width);
 #pragma unroll
         for (int m = 0; m < 4; ++m) {
           if (m < P.nmetrics) {
-            const Slot &sl = P.slots[P.mets[m].slot];
-            const uint32_t *off = seg.bs_offsets[sl.bitset_idx];
-            const uint32_t *vals = seg.bs_values[sl.bitset_idx];
-            const uint8_t *fixed = seg.slab + sl.off * seg.cap + (uint64_t)row * sl.width;
-            const uint8_t *bits = reinterpret_cast<const uint8_t *>((off == nullptr ? vals : off) + row);
-            mv[m] = gather_raw64(sl.bitset ? bits : fixed);
+            const MetSpec &ms = P.mets[m];
+            const uint8_t *a = seg.slab + ms.col_off * seg.cap + (uint64_t)row * ms.width;
+            if (ms.bitset) {
+              const uint32_t *off = sd.bs_offsets[ms.bitset_idx];
+              a = reinterpret_cast<const uint8_t *>((off == nullptr ? sd.bs_values[ms.bitset_idx] : off) + row);
+            }
+            mv[m] = gather_raw64(a);
           }
         }
       }
@@ -299,10 +306,9 @@ scan_filter_groupby_kernel(const __grid_constant__ ScanParams P) {
       for (int k = 0; k < 4; ++k) {
         if (k < P.nkeys) {
           const KeySpec &ks = P.keys[k];
-          const Slot &sl = P.slots[ks.slot];
-          const uint32_t pos = rowpath ? sl.row_off : row * sl.width;
-          uint64_t val = ((uint64_t)(kv[k] >> ((pos & 3u) * 8u))) & sl.vmask;
-          val = (val ^ sl.signbit) - sl.signbit;
+          const uint32_t pos = rowpath ? ks.row_off : row * ks.width;
+          uint64_t val = ((uint64_t)(kv[k] >> ((pos & 3u) * 8u))) & ks.vmask;
+          val = (val ^ ks.signbit) - ks.signbit;
           if (ks.rollup) val = rollup_value(val, ks);
           if (ks.lut) val = (uint64_t)__popcll(ks.lut & ((1ull << val) - 1ull));  // rank inside the IN list
           else val -= ks.lo;
@@ -341,26 +347,25 @@ scan_filter_groupby_kernel(const __grid_constant__ ScanParams P) {
     uint32_t dn = 0;
     for (uint32_t m = 0; m < P.nmetrics; ++m) {
       const MetSpec &ms = P.mets[m];
-      const Slot &sl = P.slots[ms.slot];
       uint64_t pre;
       if (small_plan) {
         const uint64_t raw = m == 0 ? mv[0] : m == 1 ? mv[1] : m == 2 ? mv[2] : mv[3];
-        const uint32_t pos = rowpath ? rpos + sl.row_off : row * sl.width;
-        pre = (raw >> ((pos & 7u) * 8u)) & sl.vmask;
-        pre = (pre ^ sl.signbit) - sl.signbit;
+        const uint32_t pos = rowpath ? rpos + ms.row_off : row * ms.width;
+        pre = (raw >> ((pos & 7u) * 8u)) & ms.vmask;
+        pre = (pre ^ ms.signbit) - ms.signbit;
       } else {
-        const uint32_t *off = seg.bs_offsets[sl.bitset_idx];
-        const uint8_t *a = sl.bitset ? reinterpret_cast<const uint8_t *>((off == nullptr ? seg.bs_values[sl.bitset_idx] : off) + row)
-                                     : seg.slab + sl.off * seg.cap + (uint64_t)row * sl.width;
-        pre = gather_finish(gather_raw64(a), a, sl.vmask, sl.signbit);
+        const uint32_t *off = sd.bs_offsets[ms.bitset_idx];
+        const uint8_t *a = ms.bitset ? reinterpret_cast<const uint8_t *>((off == nullptr ? sd.bs_values[ms.bitset_idx] : off) + row)
+                                     : seg.slab + ms.col_off * seg.cap + (uint64_t)row * ms.width;
+        pre = gather_finish(gather_raw64(a), a, ms.vmask, ms.signbit);
       }
       if (ms.op != A_DISTINCT) {
         acc_update(reinterpret_cast<uint8_t *>(ms.acc) + cell * ms.stride, ms.op, pre, tpol);
         continue;
       }
       // count-distinct: append (cell, id) to this CTA's region; deduplicated after the scan
-      const uint32_t *off = seg.bs_offsets[sl.bitset_idx];
-      const uint32_t *vals = seg.bs_values[sl.bitset_idx];
+      const uint32_t *off = sd.bs_offsets[ms.bitset_idx];
+      const uint32_t *vals = sd.bs_values[ms.bitset_idx];
       uint64_t *region = P.dpairs[dn] + (uint64_t)blockIdx.x * P.dpair_cap;
       if (off == nullptr) {  // one id per row: `pre` is the id
         const uint32_t pos = atomicAdd(&s_cursor[dn], 1u);
@@ -376,53 +381,62 @@ scan_filter_groupby_kernel(const __grid_constant__ ScanParams P) {
     }
   };
 
-  // chunk -> (active segment, chunk inside it), advanced incrementally: no 64-bit division per chunk
-  const uint32_t cps = P.tiles_per_seg;
-  const uint32_t nwarps = gridDim.x * kWarps;
-  const uint32_t step_seg = nwarps / cps, step_chunk = nwarps - step_seg * cps;
-  uint32_t si, ci, nchunk = 0;
-  {
-    const uint32_t first = blockIdx.x * kWarps + warp;
-    si = first / cps;
-    ci = first - si * cps;
-  }
-  while (si < P.nactive) {
-    // this warp's next chunk (also the prefetch target)
-    uint32_t nsi = si + step_seg, nci = ci + step_chunk;
-    if (nci >= cps) { nci -= cps; ++nsi; }
-    const uint32_t seg_index = P.active[si];
-    const SegDesc &seg = P.segs[seg_index];
-    const uint32_t nrows = (uint32_t)seg.nrows;
-    const uint32_t chunk_row = ci * kChunkRows;
-    si = nsi;
-    ci = nci;
-    if (chunk_row >= nrows) continue;  // uniform per warp
+  // the one place process_row is instantiated: `count` rows of the list, one per lane and 32 per batch
+  auto batches = [&](const uint32_t count, const bool rowpath) {
+#pragma unroll 1
+    for (uint32_t head = 0; head < count; head += 32)
+      if (head + lane < count) process_row(list[head + lane], rowpath);
+  };
+
+  // ---- work units: runs of P.unit_chunks consecutive chunks of one segment, handed out dynamically ----
+  // A warp keeps its segment's descriptor in registers for a whole unit and the list holds bare row numbers;
+  // units are taken in table order, so all warps together sweep a window of a few dozen segments.
+  const uint32_t ups = P.units_per_seg, nunits = P.nactive * ups;
+  auto grab = [&]() {
+    uint32_t u = 0;
+    if (lane == 0) u = atomicAdd(reinterpret_cast<unsigned int *>(&P.counters[8]), 1u);
+    return __shfl_sync(0xffffffffu, u, 0);
+  };
+  uint32_t unit = grab();
+  while (unit < nunits) {
+    const uint32_t next_unit = grab();  // one ahead: its first chunk is prefetched from this unit's last one
     // a full group table / distinct set makes the host grow it and run again: stop wasting time
-    if (can_overflow && (++nchunk & 15u) == 0) {
+    if (can_overflow) {
       unsigned long long f = 0;
       if (lane == 0) f = *reinterpret_cast<volatile unsigned long long *>(&P.counters[1]);
       if (__shfl_sync(0xffffffffu, f, 0) != 0ull) break;
     }
+    const uint32_t si = unit / ups, part = unit - si * ups;
+    {
+      seg.index = P.active[si];
+      const SegDesc &sd = P.segs[seg.index];
+      seg.slab = sd.slab;
+      seg.rows = sd.rows;
+      seg.cap = (uint32_t)sd.cap;
+      seg.nrows = (uint32_t)sd.nrows;
+    }
+    const uint32_t nrows = seg.nrows;
+    const uint32_t c_begin = part * P.unit_chunks;
+    const uint32_t c_end = min(c_begin + P.unit_chunks, (nrows + kChunkRows - 1) / kChunkRows);
+    for (uint32_t ci = c_begin; ci < c_end; ++ci) {
+    const uint32_t chunk_row = ci * kChunkRows;
     const uint32_t row0 = chunk_row + lane * kVec;
 
-    // software pipeline: pull the filter columns of this warp's NEXT chunk into L2 now, so that its
-    // vector loads find them there instead of paying a DRAM round trip per column
-    if (nsi < P.nactive && !(P.tune & 32u)) {
-      const SegDesc &nseg = P.segs[P.active[nsi]];
-      const uint32_t nrow = nci * kChunkRows;
-      if (nrow < (uint32_t)nseg.nrows && !(P.tune & 8192u)) {
-        // one bulk L2 prefetch (TMA unit) per predicate column, lane f taking column f
-        if (lane < P.nfilter_slots) {
-          const uint8_t *a = nseg.slab + P.pf_off[lane] * nseg.cap + (uint64_t)nrow * P.pf_width[lane];
-          asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a), "r"((uint32_t)kChunkRows * P.pf_width[lane]) : "memory");
-        }
-      } else if (nrow < (uint32_t)nseg.nrows) {
-        for (uint32_t f = 0; f < P.nfilter_slots; ++f) {
-          const Slot &sl = P.slots[P.filter_slots[f]];
-          if (lane * 128u < (uint32_t)kChunkRows * sl.width)
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(nseg.slab + sl.off * nseg.cap + (uint64_t)nrow * sl.width + lane * 128u));
-        }
+    // software pipeline: pull the predicate columns of this warp's NEXT chunk into L2 now (one bulk prefetch,
+    // TMA unit, per column: lane f takes column f), so that its vector loads find them there instead of
+    // paying a DRAM round trip per column. The chunk after the last one of a unit opens the next unit.
+    if (!(P.tune & 32u) && lane < P.nfilter_slots) {
+      const uint8_t *a = nullptr;
+      if (ci + 1 < c_end) {
+        a = seg.slab + P.pf_off[lane] * seg.cap + (uint64_t)(chunk_row + kChunkRows) * P.pf_width[lane];
+      } else if (next_unit < nunits) {
+        const uint32_t nsi = next_unit / ups, npart = next_unit - nsi * ups;
+        const SegDesc &nsd = P.segs[P.active[nsi]];
+        const uint32_t nrow = npart * P.unit_chunks * kChunkRows;
+        if (nrow < (uint32_t)nsd.nrows) a = nsd.slab + P.pf_off[lane] * nsd.cap + (uint64_t)nrow * P.pf_width[lane];
       }
+      if (a != nullptr)
+        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a), "r"((uint32_t)kChunkRows * P.pf_width[lane]) : "memory");
     }
 
     uint32_t mask = eval_predicate(P, seg, row0, pol);
@@ -455,12 +469,12 @@ scan_filter_groupby_kernel(const __grid_constant__ ScanParams P) {
         while (mask) {
           const uint32_t b = __ffs(mask) - 1;
           mask &= mask - 1;
-          list[pos++] = make_uint2(seg_index, base_row + (b >> 2) * kSubChunk + (b & 3u));
+          list[pos++] = base_row + (b >> 2) * kSubChunk + (b & 3u);
         }
       } else {
 #pragma unroll
         for (int b = 0; b < kRowsPerThread; ++b)
-          if (mask & (1u << b)) list[pos++] = make_uint2(seg_index, base_row + (b >> 2) * kSubChunk + (b & 3));
+          if (mask & (1u << b)) list[pos++] = base_row + (b >> 2) * kSubChunk + (b & 3);
       }
     }
     __syncwarp();
@@ -469,7 +483,7 @@ scan_filter_groupby_kernel(const __grid_constant__ ScanParams P) {
       const uint8_t *rows = seg.rows;
 #pragma unroll 1
       for (uint32_t i = lane; i < total; i += 32) {
-        const uint8_t *a = rows + (uint64_t)list[npend + i].y * P.row_stride + P.row_lo;
+        const uint8_t *a = rows + (uint64_t)list[npend + i] * P.row_stride + P.row_lo;
         asm volatile("prefetch.global.L2 [%0];" ::"l"(a));
         if (((uint32_t)(uintptr_t)a & 63u) + P.row_span > 64u) asm volatile("prefetch.global.L2 [%0];" ::"l"(a + P.row_span - 1));
       }
@@ -477,29 +491,27 @@ scan_filter_groupby_kernel(const __grid_constant__ ScanParams P) {
     npend += total;
 
     // ---- hand the passing rows to the aggregation stage in full batches of 32 ----
-    // The list is a small per-warp queue: rows wait (across chunks) until a whole warp of them is
-    // available, so that one DRAM round trip of gathers always serves 32 rows whatever the selectivity.
-    uint32_t head = 0;
-    while (npend - head >= 32) {
-      const uint2 e = list[head + lane];
-      process_row(P.segs[e.x], e.y, rowpath);
-      head += 32;
-    }
-    if (head) {  // move the incomplete batch (< 32 rows) to the front
-      const uint32_t left = npend - head;
-      uint2 t = make_uint2(0, 0);
+    // The list is a small per-warp queue: rows wait (across the chunks of a unit) until a whole warp of
+    // them is available, so that one DRAM round trip of gathers always serves 32 rows whatever the selectivity.
+    const uint32_t head = npend & ~31u;
+    if (head) {
+      batches(head, rowpath);
+      const uint32_t left = npend - head;  // move the incomplete batch (< 32 rows) to the front
+      uint32_t t = 0;
       if (lane < left) t = list[head + lane];
       __syncwarp();
       if (lane < left) list[lane] = t;
       __syncwarp();
       npend = left;
     }
-  }
-
-  // the last, incomplete batch
-  if (lane < npend) {
-    const uint2 e = list[lane];
-    process_row(P.segs[e.x], e.y, P.row_thresh != 0);
+    }  // chunks of the unit
+    // the unit's last, incomplete batch (the next unit is in another segment)
+    if (npend) {
+      batches(npend, P.row_thresh != 0);
+      npend = 0;
+      __syncwarp();
+    }
+    unit = next_unit;
   }
 
   // counters: one atomic per warp

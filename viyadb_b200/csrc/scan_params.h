@@ -77,6 +77,9 @@ struct KeySpec {
   uint64_t rule_boundary[kMaxRules];
   uint64_t lo;    // subtracted from the (rolled-up) value
   uint64_t mul;   // cell index / packed key = sum (v - lo) * mul
+  // copy of the key column's Slot fields: direct constant operands under the unrolled key loop
+  uint64_t col_off, vmask, signbit;
+  uint32_t width, row_off;
   uint64_t lut;   // non-zero: the predicate restricts this key to the codes whose bits are set (an IN list over
                   // codes < 64 in a top-level conjunction); the key is numbered by its rank in the set instead
                   // of v - lo, which shrinks the dense key domain to the values that can actually occur
@@ -97,6 +100,9 @@ struct MetSpec {
   uint32_t stride; // bytes between the accumulators of consecutive cells (== width when the table is
                    // one array per metric, == cell size when the fields of a cell are interleaved)
   void *acc;       // accumulator of cell 0
+  // copy of the metric column's Slot fields (one constant load level instead of two)
+  uint64_t col_off, vmask, signbit;
+  uint32_t width, row_off, bitset, bitset_idx;
 };
 
 // Per-segment descriptor (device array, one per table segment).
@@ -116,6 +122,8 @@ struct ScanParams {
   uint32_t nactive;
   uint32_t tiles_per_seg;   // 512-row warp chunks per segment
   uint64_t total_tiles;     // nactive * tiles_per_seg
+  uint32_t unit_chunks;     // chunks per work unit (a run of consecutive chunks of one segment)
+  uint32_t units_per_seg;   // ceil(tiles_per_seg / unit_chunks); unit u = (active segment u / units_per_seg, part u % units_per_seg)
 
   // columns
   Slot slots[kMaxSlots];
@@ -169,7 +177,7 @@ struct ScanParams {
   uint32_t dpair_cap;
 
   // counters: [0] passed rows, [1] overflow flag (probe limit of the group table or of a distinct set),
-  // [2+d] pairs appended for distinct metric d (all CTAs)
+  // [2+d] pairs appended for distinct metric d (all CTAs), [8] next work unit (low 32 bits)
   unsigned long long *counters;
 };
 

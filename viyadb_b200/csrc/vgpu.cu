@@ -271,6 +271,8 @@ struct vgpu_ctx {
   // (always the stack interpreter), bit 13 per-lane instead of bulk L2 prefetch of the next chunk, bit 14 no
   // tightening of key domains from the predicate
   uint32_t tune = 2;
+  int ctas_per_sm = VGPU_MIN_CTAS;  // VGPU_CTAS: resident scan CTAs per SM (2, 3 or 4: picks the register cap)
+  uint32_t unit_chunks = 0;  // VGPU_UNIT_CHUNKS: 512-row chunks per dynamically scheduled work unit (0: adaptive)
   // pool of pinned host blocks that back vgpu_result (D2H at full PCIe speed, no per-query
   // cudaMallocHost); shared with the results so that they may outlive the context
   std::shared_ptr<PinnedPool> pool = std::make_shared<PinnedPool>();
@@ -1005,6 +1007,8 @@ int vgpu_init(int device, vgpu_ctx **out) {
     CUDA_CK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &threshold));
     if (const char *e = getenv("VGPU_TUNE")) ctx->tune = (uint32_t)strtoul(e, nullptr, 0);
     ctx->trace = getenv("VGPU_TRACE") != nullptr;
+    if (const char *e = getenv("VGPU_CTAS")) { int c = atoi(e); if (c >= 2 && c <= 4) ctx->ctas_per_sm = c; }
+    if (const char *e = getenv("VGPU_UNIT_CHUNKS")) ctx->unit_chunks = (uint32_t)strtoul(e, nullptr, 0);
     // carve out the persisting part of L2 for group tables
     if (ctx->tune & 1u) {
       int max_persist = 0, max_window = 0;
@@ -1924,6 +1928,17 @@ int vgpu_query_agg(vgpu_table *t, const vgpu_plan *plan, vgpu_result **out) {
       }
     }
 
+    for (uint32_t k = 0; k < P.nkeys; ++k) {
+      const Slot &sl = P.slots[P.keys[k].slot];
+      P.keys[k].col_off = sl.off; P.keys[k].vmask = sl.vmask; P.keys[k].signbit = sl.signbit;
+      P.keys[k].width = sl.width; P.keys[k].row_off = sl.row_off;
+    }
+    for (uint32_t m = 0; m < P.nmetrics; ++m) {
+      const Slot &sl = P.slots[P.mets[m].slot];
+      P.mets[m].col_off = sl.off; P.mets[m].vmask = sl.vmask; P.mets[m].signbit = sl.signbit;
+      P.mets[m].width = sl.width; P.mets[m].row_off = sl.row_off;
+      P.mets[m].bitset = sl.bitset; P.mets[m].bitset_idx = sl.bitset_idx;
+    }
     P.small_plan = P.nkeys <= 4 && P.nmetrics <= 4;
     for (uint32_t k = 0; k < P.nkeys; ++k)
       if (P.slots[P.keys[k].slot].width > 4) P.small_plan = 0;
@@ -2005,6 +2020,14 @@ int vgpu_query_agg(vgpu_table *t, const vgpu_plan *plan, vgpu_result **out) {
     P.tiles_per_seg = (uint32_t)std::max<uint64_t>(1, (max_rows + kChunkRows - 1) / kChunkRows);
     P.nactive = (uint32_t)q.active.size();
     P.total_tiles = (uint64_t)P.nactive * P.tiles_per_seg;
+    // work units: about 8 per resident warp so that dynamic scheduling evens out the tail, at most 64 chunks
+    P.unit_chunks = ctx->unit_chunks;
+    if (P.unit_chunks == 0) {
+      const uint64_t warps = (uint64_t)ctx->sm_count * ctx->ctas_per_sm * kWarps;
+      P.unit_chunks = (uint32_t)std::min<uint64_t>(64, std::max<uint64_t>(4, P.total_tiles / (8 * warps)));
+    }
+    P.units_per_seg = (P.tiles_per_seg + P.unit_chunks - 1) / P.unit_chunks;
+    if ((uint64_t)P.nactive * P.units_per_seg > 0x7fffffffull) fail(VGPU_ERR_UNSUPPORTED, "too many work units");
     upload_descs(t);
     P.segs = t->d_segs;
     P.tune = ctx->tune;
@@ -2030,7 +2053,7 @@ int vgpu_query_agg(vgpu_table *t, const vgpu_plan *plan, vgpu_result **out) {
     }
     // the scan grid (also the number of count-distinct pair regions)
     const int scan_grid = (int)std::max<uint64_t>(1, std::min<uint64_t>((P.total_tiles + kWarps - 1) / kWarps,
-                                                                       (uint64_t)ctx->sm_count * VGPU_MIN_CTAS));
+                                                                       (uint64_t)ctx->sm_count * ctx->ctas_per_sm));
     // count-distinct: every CTA appends its (cell,id) pairs to a private region. The region capacity
     // follows the high-water mark of earlier queries on this table; overflow => grow and re-run the scan
     uint64_t dpair_total_cap = 0;
@@ -2169,7 +2192,9 @@ int vgpu_query_agg(vgpu_table *t, const vgpu_plan *plan, vgpu_result **out) {
           attr[0].val.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
           cfg.numAttrs = 1;
         }
-        CUDA_CK(cudaLaunchKernelEx(&cfg, scan_filter_groupby_kernel, P));
+        if (ctx->ctas_per_sm == 2) CUDA_CK(cudaLaunchKernelEx(&cfg, scan_filter_groupby_kernel<2>, P));
+        else if (ctx->ctas_per_sm == 4) CUDA_CK(cudaLaunchKernelEx(&cfg, scan_filter_groupby_kernel<4>, P));
+        else CUDA_CK(cudaLaunchKernelEx(&cfg, scan_filter_groupby_kernel<3>, P));
         ++launches;
       }
       CUDA_CK(cudaEventRecord(ctx->ev_scan1, stream));
