@@ -101,6 +101,16 @@ WORKLOADS = {
 }
 
 
+def load_traffic(wname):
+    """DRAM bytes per launch of the scan kernel from the last `ncu --set full` capture of this workload
+    (profiles/traffic.json, written by tools/save_profile.sh; never measured inside a bench run)."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))[wname]
+        return float(t["bytes_per_launch"]), t.get("source")
+    except Exception:
+        return None, None
+
+
 def load_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -339,6 +349,7 @@ def main_ours(args):
     selectivity = passed / max(1, runner.stats.scanned_recs)   # this rank's share
     b_alg = w["filter_bytes"] + selectivity * w["payload_bytes"]
     peak, peak_src = load_peaks()
+    traffic, traffic_src = load_traffic(args.workload) if rows == w["rows"] else (None, None)
     achieved = rows * b_alg / (scan_avg / 1e3) / 1e9
     value = total_rows * args.steps / (elapsed_ms / 1e3)
 
@@ -372,7 +383,8 @@ def main_ours(args):
                        "group_table": "dense" if runner.stats.table_mode == 0 else "hash",
                        "parallelism": f"segment-sharded x{world}, one NCCL merge of partial group tables" if world > 1 else "single GPU"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "kernel": "scan_filter_groupby_kernel", "kernel_ms": scan_avg,
+                         "traffic": traffic, "traffic_unit": "bytes/launch (dram__bytes_read.sum + dram__bytes_write.sum)",
+                         "traffic_source": traffic_src, "kernel": "scan_filter_groupby_kernel", "kernel_ms": scan_avg,
                          "algorithmic_bytes_per_row": b_alg, "algorithmic_bytes_per_launch": rows * b_alg,
                          "peak_source": peak_src},
             "gpu_launches": launches, "gpu_ms_per_step": sum(gpu_ms) / len(gpu_ms),

@@ -367,7 +367,8 @@ struct PairsPartitionParams {
   uint64_t total;
   uint32_t nregions;
   uint32_t region_cap;
-  uint32_t nbuckets;           // power of two <= kMaxBuckets
+  uint32_t nbuckets;           // power of two <= kMaxBuckets (hash buckets), or the number of ranks (owner_parts)
+  uint32_t owner_parts;        // non-zero: bucket = rank that owns the pair's cell (multi-GPU exchange)
   uint32_t shift;              // bucket = mix64(pair) >> shift
   uint64_t bucket_cap;
   unsigned long long *cursors; // [nbuckets], zeroed
@@ -394,7 +395,8 @@ __global__ void __launch_bounds__(256) pairs_partition_kernel(const __grid_const
         bkt[j] = 0xffffffffu;
         if (i < n) {
           key[j] = src[i];
-          bkt[j] = (uint32_t)(mix64(key[j]) >> A.shift) & (A.nbuckets - 1);
+          bkt[j] = A.owner_parts ? (uint32_t)((mix64(key[j] >> 32) >> 17) % A.owner_parts)
+                                 : (uint32_t)(mix64(key[j]) >> A.shift) & (A.nbuckets - 1);
           pos[j] = atomicAdd(&s_cnt[bkt[j]], 1u);
         }
       }
@@ -446,6 +448,8 @@ __device__ __forceinline__ void pairs_insert(const PairsDedupeParams &D, uint64_
 __global__ void __launch_bounds__(256) pairs_dedupe_kernel(const __grid_constant__ PairsDedupeParams D) {
   const uint64_t pol = make_table_policy(false);
   if (D.counts == nullptr) {
+    // one insert in flight per thread: the kernel is bound by the L2's atomic throughput, not by latency
+    // (four CAS in flight per thread measured 5 % slower on C2)
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < D.n; i += (uint64_t)gridDim.x * blockDim.x)
       pairs_insert(D, D.pairs[i], pol);
   } else {

@@ -145,7 +145,8 @@ struct ScanParams {
   uint32_t nfilter_slots;
   uint8_t filter_slots[kMaxSlots];
   uint8_t pf_width[kMaxSlots];   // per predicate column f: element width and bytes-per-row offset of the column
-  uint64_t pf_off[kMaxSlots];    // in the slab (bulk L2 prefetch of the next chunk, lane f takes column f)
+  uint64_t pf_off[kMaxSlots];    // in the slab (bulk L2 prefetch of the next chunk, lane f takes column f);
+  uint32_t npf_payload;          // entries nfilter_slots.. : key / metric columns the predicate does not read
 
   // predicate
   uint32_t nprog;

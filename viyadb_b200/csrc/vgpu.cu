@@ -269,7 +269,8 @@ struct vgpu_ctx {
   // bit 7 never gather from the mirror, bit 8 always gather from the mirror (tests), bit 11 L2 prefetch of mirror
   // rows at enqueue (off: measured slower, it fetches 128-byte lines), bit 12 no unrolled conjunction fast path
   // (always the stack interpreter), bit 13 per-lane instead of bulk L2 prefetch of the next chunk, bit 14 no
-  // tightening of key domains from the predicate
+  // tightening of key domains from the predicate, bit 15 prefetch the key / metric columns too after dense chunks
+  // (off: measured slower)
   uint32_t tune = 2;
   int ctas_per_sm = VGPU_MIN_CTAS;  // VGPU_CTAS: resident scan CTAs per SM (2, 3 or 4: picks the register cap)
   uint32_t unit_chunks = 0;  // VGPU_UNIT_CHUNKS: 512-row chunks per dynamically scheduled work unit (0: adaptive)
@@ -1549,34 +1550,39 @@ void nccl_merge_distinct(vgpu_ctx *ctx, Scratch &scratch, const uint64_t *region
                          uint64_t acc_cells, uint32_t &launches) {
   const int G = ctx->nranks, me = ctx->rank;
   cudaStream_t stream = ctx->stream;
-  // 1. local dedupe into a compact list
-  uint64_t *unique = scratch.alloc<uint64_t>(std::max<uint64_t>(total_pairs, 1));
-  unsigned long long *d_unique_n = scratch.alloc<unsigned long long>(1);
-  CUDA_CK(cudaMemsetAsync(d_unique_n, 0, 8, stream));
-  dedupe_pairs(ctx, scratch, regions, d_counts, nregions, region_cap, total_pairs, reinterpret_cast<uint8_t *>(distinct), 4,
-               unique, d_unique_n, launches);
-  unsigned long long n_unique = 0;
-  CUDA_CK(cudaMemcpyAsync(&n_unique, d_unique_n, 8, cudaMemcpyDeviceToHost, stream));
-  CUDA_CK(cudaStreamSynchronize(stream));
-  // 2. to the owners of the cells
-  const uint64_t bucket_cap = std::max<uint64_t>(n_unique, 1);
-  unsigned long long *cursors = scratch.alloc<unsigned long long>(kMaxParts);
-  CUDA_CK(cudaMemsetAsync(cursors, 0, kMaxParts * sizeof(unsigned long long), stream));
-  uint64_t *send = scratch.alloc<uint64_t>(bucket_cap * G);
-  PartitionParams A{};
-  A.keys = unique;
-  A.nslots = n_unique;
-  A.sentinel_slot = ~0ull;
-  A.sentinel_present = nullptr;
-  A.nparts = (uint32_t)G;
-  A.owner_shift = 32;  // owner of the cell
-  A.bucket_cap = bucket_cap;
-  A.cursors = cursors;
-  A.out_keys = send;
-  A.npay = 0;
-  partition_table_kernel<<<grid_for(n_unique + 1, 256 * kPartPerThread, ctx->sm_count, 8), 256, 0, stream>>>(A);
-  CUDA_CK(cudaGetLastError());
-  ++launches;
+  // 1. straight from the scan's per-CTA regions to one bucket per owner rank (no local dedupe pass: the
+  //    owners dedupe anyway, and an extra pass over the pairs costs more than the duplicates it would save)
+  uint64_t bucket_cap = total_pairs / G + total_pairs / G / 4 + 65536;
+  unsigned long long *cursors = scratch.alloc<unsigned long long>(kMaxBuckets + 1);
+  std::vector<unsigned long long> h_cursors(kMaxBuckets + 1);
+  uint64_t *send = nullptr;
+  for (int attempt = 0; attempt < 2; ++attempt) {
+    send = scratch.alloc<uint64_t>(bucket_cap * G);
+    CUDA_CK(cudaMemsetAsync(cursors, 0, (kMaxBuckets + 1) * sizeof(unsigned long long), stream));
+    PairsPartitionParams A{};
+    A.pairs = regions;
+    A.counts = d_counts;
+    A.total = total_pairs;
+    A.nregions = nregions;
+    A.region_cap = region_cap;
+    A.nbuckets = (uint32_t)G;
+    A.owner_parts = (uint32_t)G;
+    A.bucket_cap = bucket_cap;
+    A.cursors = cursors;
+    A.out = send;
+    A.overflow = cursors + kMaxBuckets;
+    pairs_partition_kernel<<<(int)std::min<uint32_t>(std::max<uint32_t>(nregions, 1), ctx->sm_count * 8), 256, 0, stream>>>(A);
+    CUDA_CK(cudaGetLastError());
+    ++launches;
+    // every rank must take the same retry decision (the exchange below is collective)
+    NCCL_CK(g_nccl.AllReduce(cursors + kMaxBuckets, cursors + kMaxBuckets, 1, ncclUint64, ncclMax, ctx->comm, stream));
+    CUDA_CK(cudaMemcpyAsync(h_cursors.data(), cursors, (kMaxBuckets + 1) * sizeof(unsigned long long),
+                            cudaMemcpyDeviceToHost, stream));
+    CUDA_CK(cudaStreamSynchronize(stream));
+    if (h_cursors[kMaxBuckets] == 0) break;
+    if (attempt == 1) fail(VGPU_ERR_CUDA, "count-distinct owner partitioning overflowed twice");
+    bucket_cap = total_pairs + 1;  // skewed owners: room for everything in every bucket
+  }
   std::vector<uint64_t> matrix = exchange_counts(ctx, cursors, scratch);
   std::vector<uint64_t> recv_off(G);
   uint64_t total = 0;
@@ -1938,6 +1944,22 @@ int vgpu_query_agg(vgpu_table *t, const vgpu_plan *plan, vgpu_result **out) {
       P.mets[m].col_off = sl.off; P.mets[m].vmask = sl.vmask; P.mets[m].signbit = sl.signbit;
       P.mets[m].width = sl.width; P.mets[m].row_off = sl.row_off;
       P.mets[m].bitset = sl.bitset; P.mets[m].bitset_idx = sl.bitset_idx;
+    }
+    {  // key / metric columns after the predicate's in the prefetch table (dense chunks prefetch them too)
+      uint32_t n = P.nfilter_slots;
+      P.npf_payload = 0;
+      auto add = [&](uint32_t slot) {
+        const Slot &sl = P.slots[slot];
+        if (sl.bitset || n >= 31) return;
+        for (uint32_t f = 0; f < P.nfilter_slots; ++f) if (P.filter_slots[f] == slot) return;
+        for (uint32_t f = P.nfilter_slots; f < n; ++f) if (P.pf_off[f] == sl.off) return;
+        P.pf_width[n] = (uint8_t)sl.width;
+        P.pf_off[n] = sl.off;
+        ++n;
+      };
+      for (uint32_t k = 0; k < P.nkeys; ++k) add(P.keys[k].slot);
+      for (uint32_t m = 0; m < P.nmetrics; ++m) add(P.mets[m].slot);
+      if (ctx->tune & 32768u) P.npf_payload = n - P.nfilter_slots;  // off by default: measured slower on C3
     }
     P.small_plan = P.nkeys <= 4 && P.nmetrics <= 4;
     for (uint32_t k = 0; k < P.nkeys; ++k)
