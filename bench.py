@@ -12,6 +12,7 @@ of the per-GPU partial group tables.
 Workloads (synthetic, splitmix64(seed=42), written directly in HBM):
   c2 (default) 1e9 rows/GPU: d0 IN(5) AND n4 in [250,750) AND t5 in [T+2.5e6,T+7.5e6); group (d0,d1,d2,d3);
                min, max, count-distinct            -> the 60 %-of-roofline target config of BASELINE.json
+  c0           1e7 rows: dim2 == code; group (dim1); sum        -> the reference's own CPU-runnable config
   c1           1e8 rows/GPU: d0 == code; group (d1,d2); sum, count
   c3           1e9 rows/GPU: time range; group (d0,d1,d2); sum
   c4           1e9 rows/GPU: no filter; group (d0, hour/day/month rollup of t1); sum, count (1e7 groups)
@@ -39,6 +40,18 @@ SEG = 1_000_000
 
 # per workload: table config, generator (lo, range[, mode, div]) per schema column, query, per-row bytes
 WORKLOADS = {
+    # C0: the reference's own CPU-runnable config (BASELINE.json configs[0]): the whole table also runs on the CPU arm
+    "c0": {
+        "rows": 10_000_000,
+        "table": {"name": "events", "segment_size": SEG,
+                  "dimensions": [{"name": "dim1"}, {"name": "dim2"}, {"name": "dim3"}],
+                  "metrics": [{"name": "m1", "type": "long_sum"}, {"name": "m2", "type": "int_sum"}]},
+        "gens": [(1, 1000), (1, 100), (1, 100), (0, 977), (0, 13)],
+        "prefix": ["a", "b", "c", "", ""],
+        "query": {"type": "aggregate", "table": "events", "dimensions": ["dim1"], "metrics": ["m1"],
+                  "filter": {"op": "eq", "column": "dim2", "value": "b7"}},
+        "filter_bytes": 4, "payload_bytes": 4 + 8, "full_bytes": 24, "dtype": "int64",
+    },
     "c1": {
         "rows": 100_000_000,
         "table": {"name": "events", "segment_size": SEG,
@@ -246,7 +259,8 @@ def main_reference(args):
 
 
 def describe(wname):
-    return {"c1": "1e8 rows/GPU, eq filter, 2-key group-by, sum+count",
+    return {"c0": "1e7 rows, 3 string dims + 2 int metrics, SELECT dim1,SUM(m1) WHERE dim2='x' GROUP BY dim1",
+            "c1": "1e8 rows/GPU, eq filter, 2-key group-by, sum+count",
             "c2": "1e9 rows/GPU, IN + 2 range predicates over 3 dims, 4-key group-by, min/max + count-distinct",
             "c3": "1e9 rows/GPU, time-range filter, 3-key group-by, sum",
             "c4": "1e9 rows/GPU, no filter, (dim, rolled-up time) group-by ~1e7 groups, sum+count"}[wname]

@@ -95,8 +95,10 @@ _WANT = {}
 
 
 # VGPU_TUNE (read by vgpu_init): "auto" lets the planner choose per chunk between gathering the cells of
-# passing rows from the columns or from the row-major mirror; the other two pin one of the two paths.
-@pytest.fixture(scope="module", params=[None, "130", "258"], ids=["auto", "columns_only", "mirror_only"])
+# passing rows from the columns or from the row-major mirror and keeps small dense group tables CTA-private in
+# shared memory; the others pin one gather path / keep every group table in global memory.
+@pytest.fixture(scope="module", params=[None, "130", "258", "262146"],
+                ids=["auto", "columns_only", "mirror_only", "no_smem_tables"])
 def env(built_lib, request):
     import os
     import viyadb_b200 as v

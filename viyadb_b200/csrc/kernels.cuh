@@ -256,6 +256,42 @@ __device__ __forceinline__ void acc_update(void *addr, uint32_t op, uint64_t v, 
   }
 }
 
+// The same Update() on a CTA-private accumulator in shared memory (32-bit shared-window address).
+__device__ __forceinline__ void acc_update_shared(uint32_t a, uint32_t op, uint64_t v) {
+  const uint32_t v32 = (uint32_t)v;
+  switch (op) {
+    case A_ADD32: asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(a), "r"(v32) : "memory"); break;
+    case A_ADD64: asm volatile("red.shared.add.u64 [%0], %1;" ::"r"(a), "l"(v) : "memory"); break;
+    case A_ADDF32: asm volatile("red.shared.add.f32 [%0], %1;" ::"r"(a), "f"(__uint_as_float(v32)) : "memory"); break;
+    case A_ADDF64: asm volatile("red.shared.add.f64 [%0], %1;" ::"r"(a), "d"(__longlong_as_double((long long)v)) : "memory"); break;
+    case A_MINS32: asm volatile("red.shared.min.s32 [%0], %1;" ::"r"(a), "r"(v32) : "memory"); break;
+    case A_MAXS32: asm volatile("red.shared.max.s32 [%0], %1;" ::"r"(a), "r"(v32) : "memory"); break;
+    case A_MINU32: asm volatile("red.shared.min.u32 [%0], %1;" ::"r"(a), "r"(v32) : "memory"); break;
+    case A_MAXU32: asm volatile("red.shared.max.u32 [%0], %1;" ::"r"(a), "r"(v32) : "memory"); break;
+    case A_MINS64: asm volatile("red.shared.min.s64 [%0], %1;" ::"r"(a), "l"(v) : "memory"); break;
+    case A_MAXS64: asm volatile("red.shared.max.s64 [%0], %1;" ::"r"(a), "l"(v) : "memory"); break;
+    case A_MINU64: asm volatile("red.shared.min.u64 [%0], %1;" ::"r"(a), "l"(v) : "memory"); break;
+    case A_MAXU64: asm volatile("red.shared.max.u64 [%0], %1;" ::"r"(a), "l"(v) : "memory"); break;
+    case A_MAXF32:
+      if (!(v32 >> 31)) asm volatile("red.shared.max.s32 [%0], %1;" ::"r"(a), "r"(v32) : "memory");
+      else asm volatile("red.shared.min.u32 [%0], %1;" ::"r"(a), "r"(v32) : "memory");
+      break;
+    case A_MINF32:
+      if (!(v32 >> 31)) asm volatile("red.shared.min.s32 [%0], %1;" ::"r"(a), "r"(v32) : "memory");
+      else asm volatile("red.shared.max.u32 [%0], %1;" ::"r"(a), "r"(v32) : "memory");
+      break;
+    case A_MAXF64:
+      if (!(v >> 63)) asm volatile("red.shared.max.s64 [%0], %1;" ::"r"(a), "l"(v) : "memory");
+      else asm volatile("red.shared.min.u64 [%0], %1;" ::"r"(a), "l"(v) : "memory");
+      break;
+    case A_MINF64:
+      if (!(v >> 63)) asm volatile("red.shared.min.s64 [%0], %1;" ::"r"(a), "l"(v) : "memory");
+      else asm volatile("red.shared.max.u64 [%0], %1;" ::"r"(a), "l"(v) : "memory");
+      break;
+    default: break;
+  }
+}
+
 __device__ __forceinline__ uint64_t mix64(uint64_t x) {
   x ^= x >> 33;
   x *= 0xff51afd7ed558ccdULL;

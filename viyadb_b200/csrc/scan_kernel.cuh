@@ -29,6 +29,7 @@ namespace vgpu {
 constexpr int kChunkRows = 512;                 // rows per warp iteration
 constexpr int kSubChunk = kChunkRows / kSub;    // 128
 constexpr int kWarps = kThreads / 32;
+constexpr uint32_t kSmemTableBytes = 40 * 1024;  // CTA-private group table (3 CTAs/SM: 3 x (17 + 40) KB fit 227 KB)
 constexpr int kListCap = kChunkRows + 32;       // a chunk's worth of rows plus one incomplete batch
 static_assert(kVec * 32 == kSubChunk, "a lane owns kVec consecutive rows of every sub-chunk");
 static_assert(kTileRows % kChunkRows == 0, "slab capacity is a whole number of chunks");
@@ -253,6 +254,13 @@ scan_filter_groupby_kernel(const __grid_constant__ ScanParams P) {
   uint32_t my_passed = 0;
   __shared__ uint32_t s_cursor[kMaxDistinct];  // pairs this CTA appended per count-distinct metric
   if (threadIdx.x < kMaxDistinct) s_cursor[threadIdx.x] = 0;
+  // CTA-private group table (small dense domains): every cell starts as the plan's initial image
+  extern __shared__ __align__(16) uint8_t s_table[];
+  const uint32_t s_table_a = (uint32_t)__cvta_generic_to_shared(s_table);
+  if (P.smem_cells) {
+    const uint32_t wpc = P.smem_stride / 4, nwords = P.smem_cells * wpc;
+    for (uint32_t i = threadIdx.x; i < nwords; i += kThreads) reinterpret_cast<uint32_t *>(s_table)[i] = P.smem_init[i % wpc];
+  }
   __syncthreads();
   const bool can_overflow = P.hash_mode || P.ndistinct;
   const uint64_t pol = make_stream_policy((P.tune & 2u) != 0);
@@ -342,7 +350,8 @@ scan_filter_groupby_kernel(const __grid_constant__ ScanParams P) {
       }
     } else {
       cell = packed;
-      st_u8_hint(P.present + cell * P.present_stride, 1u, tpol);
+      if (P.smem_cells) *reinterpret_cast<volatile uint32_t *>(s_table + (uint32_t)cell * P.smem_stride + P.smem_present_off) = 1u;
+      else st_u8_hint(P.present + cell * P.present_stride, 1u, tpol);
     }
     uint32_t dn = 0;
     for (uint32_t m = 0; m < P.nmetrics; ++m) {
@@ -360,7 +369,8 @@ scan_filter_groupby_kernel(const __grid_constant__ ScanParams P) {
         pre = gather_finish(gather_raw64(a), a, ms.vmask, ms.signbit);
       }
       if (ms.op != A_DISTINCT) {
-        acc_update(reinterpret_cast<uint8_t *>(ms.acc) + cell * ms.stride, ms.op, pre, tpol);
+        if (P.smem_cells) acc_update_shared(s_table_a + (uint32_t)cell * P.smem_stride + ms.soff, ms.op, pre);
+        else acc_update(reinterpret_cast<uint8_t *>(ms.acc) + cell * ms.stride, ms.op, pre, tpol);
         continue;
       }
       // count-distinct: append (cell, id) to this CTA's region; deduplicated after the scan
@@ -516,6 +526,24 @@ scan_filter_groupby_kernel(const __grid_constant__ ScanParams P) {
       __syncwarp();
     }
     unit = next_unit;
+  }
+
+  // merge the CTA-private table into the global one: the same commutative Update(), once per live cell
+  if (P.smem_cells) {
+    __syncthreads();
+    for (uint32_t c = threadIdx.x; c < P.smem_cells; c += kThreads) {
+      const uint8_t *cellp = s_table + c * P.smem_stride;
+      if (*reinterpret_cast<const uint32_t *>(cellp + P.smem_present_off) == 0) continue;
+      st_u8_hint(P.present + (uint64_t)c * P.present_stride, 1u, tpol);
+      for (uint32_t m = 0; m < P.nmetrics; ++m) {
+        const MetSpec &ms = P.mets[m];
+        if (ms.op == A_DISTINCT) continue;
+        const uint64_t v = ms.acc_width == 4 ? (uint64_t)*reinterpret_cast<const uint32_t *>(cellp + ms.soff)
+                                             : *reinterpret_cast<const uint64_t *>(cellp + ms.soff);
+        acc_update(reinterpret_cast<uint8_t *>(ms.acc) + (uint64_t)c * ms.stride, ms.op,
+                   ms.acc_width == 4 && (ms.op == A_ADD32 || ms.op == A_MINS32 || ms.op == A_MAXS32) ? (uint64_t)(int64_t)(int32_t)(uint32_t)v : v, tpol);
+      }
+    }
   }
 
   // counters: one atomic per warp

@@ -103,6 +103,8 @@ struct MetSpec {
   // copy of the metric column's Slot fields (one constant load level instead of two)
   uint64_t col_off, vmask, signbit;
   uint32_t width, row_off, bitset, bitset_idx;
+  uint32_t soff;       // offset of the accumulator inside a cell of the CTA-private table (smem_cells != 0)
+  uint32_t acc_width;  // 4 or 8
 };
 
 // Per-segment descriptor (device array, one per table segment).
@@ -165,6 +167,12 @@ struct ScanParams {
   uint32_t *wstate;        // wide mode: 0 free, 1 being written, 2 ready
   uint64_t *wkeys;         // wide mode: capacity x nkeys words
   uint32_t max_probe;
+
+  // CTA-private copy of a small dense group table in shared memory (smem_cells != 0): every CTA aggregates
+  // into its own copy with shared-memory atomics and merges it into the global table once, at the end —
+  // a few groups would otherwise serialise all RED operations of the GPU on a few L2 addresses
+  uint32_t smem_cells, smem_stride, smem_present_off;
+  uint32_t smem_init[16];   // initial image of a cell (smem_stride / 4 words)
 
   // metrics
   uint32_t nmetrics;

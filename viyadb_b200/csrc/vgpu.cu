@@ -270,7 +270,7 @@ struct vgpu_ctx {
   // rows at enqueue (off: measured slower, it fetches 128-byte lines), bit 12 no unrolled conjunction fast path
   // (always the stack interpreter), bit 13 per-lane instead of bulk L2 prefetch of the next chunk, bit 14 no
   // tightening of key domains from the predicate, bit 15 prefetch the key / metric columns too after dense chunks
-  // (off: measured slower)
+  // (off: measured slower), bit 18 no CTA-private shared-memory copy of small dense group tables
   uint32_t tune = 2;
   int ctas_per_sm = VGPU_MIN_CTAS;  // VGPU_CTAS: resident scan CTAs per SM (2, 3 or 4: picks the register cap)
   uint32_t unit_chunks = 0;  // VGPU_UNIT_CHUNKS: 512-row chunks per dynamically scheduled work unit (0: adaptive)
@@ -993,6 +993,9 @@ int vgpu_init(int device, vgpu_ctx **out) {
     cudaDeviceProp prop;
     CUDA_CK(cudaGetDeviceProperties(&prop, device));
     ctx->sm_count = prop.multiProcessorCount;
+    CUDA_CK(cudaFuncSetAttribute(scan_filter_groupby_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemTableBytes));
+    CUDA_CK(cudaFuncSetAttribute(scan_filter_groupby_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemTableBytes));
+    CUDA_CK(cudaFuncSetAttribute(scan_filter_groupby_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemTableBytes));
     CUDA_CK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
     CUDA_CK(cudaEventCreate(&ctx->ev_begin));
     CUDA_CK(cudaEventCreate(&ctx->ev_scan0));
@@ -2174,6 +2177,30 @@ int vgpu_query_agg(vgpu_table *t, const vgpu_plan *plan, vgpu_result **out) {
       for (size_t m = 0; m < q.accs.size(); ++m) {
         P.mets[m].acc = acc_ptrs[m];
         P.mets[m].stride = acc_stride[m];
+        P.mets[m].acc_width = q.accs[m].acc_width;
+      }
+      // CTA-private shared-memory copy of a small dense table (see ScanParams::smem_cells)
+      P.smem_cells = 0;
+      uint32_t scan_dyn_smem = 0;
+      if (!q.hash_mode && !(ctx->tune & 262144u)) {
+        uint32_t off = 0;
+        for (size_t m = 0; m < q.accs.size(); ++m) if (q.accs[m].acc_width == 8 && q.accs[m].op != A_DISTINCT) { P.mets[m].soff = off; off += 8; }
+        for (size_t m = 0; m < q.accs.size(); ++m) if (q.accs[m].acc_width == 4 && q.accs[m].op != A_DISTINCT) { P.mets[m].soff = off; off += 4; }
+        const uint32_t pres = off;
+        off += 4;
+        const uint32_t sstride = (uint32_t)round_up(off, 8);
+        if (sstride <= 64 && cells * sstride <= kSmemTableBytes) {
+          P.smem_cells = (uint32_t)cells;
+          P.smem_stride = sstride;
+          P.smem_present_off = pres;
+          for (uint32_t w = 0; w < 16; ++w) P.smem_init[w] = 0;
+          for (size_t m = 0; m < q.accs.size(); ++m) {
+            if (q.accs[m].op == A_DISTINCT) continue;
+            P.smem_init[P.mets[m].soff / 4] = (uint32_t)q.accs[m].init;
+            if (q.accs[m].acc_width == 8) P.smem_init[P.mets[m].soff / 4 + 1] = (uint32_t)(q.accs[m].init >> 32);
+          }
+          scan_dyn_smem = (uint32_t)cells * sstride;
+        }
       }
       // per-CTA pair regions: the even share plus 25 % and a constant for the unevenness between CTAs
       const uint64_t region_cap64 = dpair_total_cap / scan_grid + dpair_total_cap / scan_grid / 4 + 1024;
@@ -2199,6 +2226,7 @@ int vgpu_query_agg(vgpu_table *t, const vgpu_plan *plan, vgpu_result **out) {
         cfg.gridDim = dim3(grid);
         cfg.blockDim = dim3(kThreads);
         cfg.stream = stream;
+        cfg.dynamicSmemBytes = scan_dyn_smem;
         cudaLaunchAttribute attr[1];
         cfg.attrs = attr;
         cfg.numAttrs = 0;
