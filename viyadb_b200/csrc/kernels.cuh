@@ -134,28 +134,32 @@ __device__ __forceinline__ uint32_t gather_u32(const uint32_t *p) {
 // UTC calendar arithmetic (proleptic Gregorian, no leap seconds) == glibc gmtime_r / timegm for
 // non-negative time_t, which is all util::Time32/Time64 ever see (unsigned inputs).
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint64_t trunc_days_to(uint64_t days, bool to_year) {
+// T = uint32_t for util::Time32 (seconds fit 32 bits: every division is by a constant, i.e. a multiply-high)
+// and uint64_t for the seconds part of util::Time64.
+template <typename T>
+__device__ __forceinline__ T trunc_days_to(T days, bool to_year) {
   // civil_from_days / days_from_civil (H. Hinnant's public-domain algorithms), days since 1970-01-01
-  uint64_t z = days + 719468;
-  uint64_t era = z / 146097;
-  uint64_t doe = z - era * 146097;
-  uint64_t yoe = (doe - doe / 1460 + doe / 36524 - doe / 146096) / 365;
-  uint64_t doy = doe - (365 * yoe + yoe / 4 - yoe / 100);  // March-based day of year
-  uint64_t mp = (5 * doy + 2) / 153;
-  uint64_t d = doy - (153 * mp + 2) / 5 + 1;
+  T z = days + 719468;
+  T era = z / 146097;
+  T doe = z - era * 146097;
+  T yoe = (doe - doe / 1460 + doe / 36524 - doe / 146096) / 365;
+  T doy = doe - (365 * yoe + yoe / 4 - yoe / 100);  // March-based day of year
+  T mp = (5 * doy + 2) / 153;
+  T d = doy - (153 * mp + 2) / 5 + 1;
   if (!to_year) return days - (d - 1);
   // first of January of the civil year: March-based months 10,11 (Jan, Feb) belong to year yoe+1
-  uint64_t y = yoe + era * 400 + (mp >= 10 ? 1 : 0);
+  T y = yoe + era * 400 + (mp >= 10 ? 1 : 0);
   // days_from_civil(y, 1, 1)
-  uint64_t yy = y - 1;
-  uint64_t era2 = yy / 400;
-  uint64_t yoe2 = yy - era2 * 400;
-  uint64_t doy2 = (153 * 10 + 2) / 5;  // January 1st, March-based
-  uint64_t doe2 = yoe2 * 365 + yoe2 / 4 - yoe2 / 100 + doy2;
+  T yy = y - 1;
+  T era2 = yy / 400;
+  T yoe2 = yy - era2 * 400;
+  T doy2 = (153 * 10 + 2) / 5;  // January 1st, March-based
+  T doe2 = yoe2 * 365 + yoe2 / 4 - yoe2 / 100 + doy2;
   return era2 * 146097 + doe2 - 719468;
 }
 
-__device__ __forceinline__ uint64_t trunc_seconds(uint64_t t, uint32_t unit) {
+template <typename T>
+__device__ __forceinline__ T trunc_seconds(T t, uint32_t unit) {
   switch (unit) {
     case 0: return trunc_days_to(t / 86400, true) * 86400;   // YEAR
     case 1: return trunc_days_to(t / 86400, false) * 86400;  // MONTH
@@ -181,9 +185,9 @@ __device__ __noinline__ uint64_t rollup_value(uint64_t v, const KeySpec &k) {
     uint64_t secs = v / 1000000ull;
     uint64_t micros = v - secs * 1000000ull;
     if (unit != 7) micros = 0;  // Time64::trunc zeroes micros_ for every unit (time.h:129-132)
-    return trunc_seconds(secs, unit) * 1000000ull + micros;
+    return trunc_seconds<uint64_t>(secs, unit) * 1000000ull + micros;
   }
-  return (uint64_t)(uint32_t)trunc_seconds(v, unit);
+  return (uint64_t)trunc_seconds<uint32_t>((uint32_t)v, unit);
 }
 
 // ---------------------------------------------------------------------------------------------

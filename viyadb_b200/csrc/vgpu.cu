@@ -254,6 +254,10 @@ struct vgpu_ctx {
   int sm_count = 148;
   cudaStream_t stream = nullptr;
   bool own_stream = true;
+  // host -> device copies of vgpu_segment_put run on their own stream: the DMA of one segment overlaps the
+  // statistics and row-mirror kernels of the previous one (which stay on `stream`, ordered by ev_copy)
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t ev_copy = nullptr;
   cudaEvent_t ev_begin = nullptr, ev_scan0 = nullptr, ev_scan1 = nullptr, ev_end = nullptr;
   unsigned long long *d_counters = nullptr;  // 16 x u64
   unsigned long long *h_counters = nullptr;  // pinned
@@ -997,6 +1001,8 @@ int vgpu_init(int device, vgpu_ctx **out) {
     CUDA_CK(cudaFuncSetAttribute(scan_filter_groupby_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemTableBytes));
     CUDA_CK(cudaFuncSetAttribute(scan_filter_groupby_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemTableBytes));
     CUDA_CK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    CUDA_CK(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+    CUDA_CK(cudaEventCreateWithFlags(&ctx->ev_copy, cudaEventDisableTiming));
     CUDA_CK(cudaEventCreate(&ctx->ev_begin));
     CUDA_CK(cudaEventCreate(&ctx->ev_scan0));
     CUDA_CK(cudaEventCreate(&ctx->ev_scan1));
@@ -1051,6 +1057,8 @@ void vgpu_shutdown(vgpu_ctx *ctx) {
   if (ctx->d_counters) cudaFree(ctx->d_counters);
   if (ctx->d_plan) cudaFree(ctx->d_plan);
   if (ctx->h_counters) cudaFreeHost(ctx->h_counters);
+  if (ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); }
+  if (ctx->ev_copy) cudaEventDestroy(ctx->ev_copy);
   if (ctx->ev_begin) cudaEventDestroy(ctx->ev_begin);
   if (ctx->ev_scan0) cudaEventDestroy(ctx->ev_scan0);
   if (ctx->ev_scan1) cudaEventDestroy(ctx->ev_scan1);
@@ -1168,6 +1176,7 @@ int vgpu_segment_put(vgpu_table *t, uint32_t seg_idx, uint64_t nrows, const void
     if (seg_idx > t->segs.size() + (1u << 20)) fail(VGPU_ERR_INVALID, "segment index too sparse");
     ensure_segment(t, seg_idx, nrows);
     SegmentData &sd = t->segs[seg_idx];
+    cudaStream_t cs = ctx->copy_stream;
     std::vector<std::vector<uint32_t>> keep;  // converted CSR offsets must outlive the async copies
     for (size_t c = 0; c < t->cols.size(); ++c) {
       const ColInfo &ci = t->cols[c];
@@ -1196,10 +1205,10 @@ int vgpu_segment_put(vgpu_table *t, uint32_t seg_idx, uint64_t nrows, const void
           sd.bs_vcap[ci.bitset_idx] = vcap;
         }
         if (sd.bs_vcap[ci.bitset_idx] > nvalues)
-          CUDA_CK(cudaMemsetAsync(sd.bs_values[ci.bitset_idx] + nvalues, 0, (sd.bs_vcap[ci.bitset_idx] - nvalues) * 4, ctx->stream));
+          CUDA_CK(cudaMemsetAsync(sd.bs_values[ci.bitset_idx] + nvalues, 0, (sd.bs_vcap[ci.bitset_idx] - nvalues) * 4, cs));
         if (nvalues)
           CUDA_CK(cudaMemcpyAsync(sd.bs_values[ci.bitset_idx], csr->values, nvalues * 4,
-                                  cudaMemcpyHostToDevice, ctx->stream));
+                                  cudaMemcpyHostToDevice, cs));
         sd.bs_n[ci.bitset_idx] = nvalues;
         if (!one_per_row) {
           keep.emplace_back(nrows + 1);
@@ -1212,7 +1221,7 @@ int vgpu_segment_put(vgpu_table *t, uint32_t seg_idx, uint64_t nrows, const void
             sd.bs_ocap[ci.bitset_idx] = nrows + 1;
           }
           CUDA_CK(cudaMemcpyAsync(sd.bs_offsets[ci.bitset_idx], o32.data(), (nrows + 1) * 4,
-                                  cudaMemcpyHostToDevice, ctx->stream));
+                                  cudaMemcpyHostToDevice, cs));
           sd.bs_has_offsets[ci.bitset_idx] = true;
         } else {
           sd.bs_has_offsets[ci.bitset_idx] = false;
@@ -1222,14 +1231,18 @@ int vgpu_segment_put(vgpu_table *t, uint32_t seg_idx, uint64_t nrows, const void
       uint8_t *dst = sd.slab + ci.off_per_row * sd.cap;
       if (nrows) {
         if (!col_ptrs[c]) fail(VGPU_ERR_INVALID, "null column pointer");
-        CUDA_CK(cudaMemcpyAsync(dst, col_ptrs[c], nrows * ci.width, cudaMemcpyHostToDevice, ctx->stream));
+        CUDA_CK(cudaMemcpyAsync(dst, col_ptrs[c], nrows * ci.width, cudaMemcpyHostToDevice, cs));
       }
       if (sd.cap > nrows)
-        CUDA_CK(cudaMemsetAsync(dst + nrows * ci.width, 0, (sd.cap - nrows) * ci.width, ctx->stream));
+        CUDA_CK(cudaMemsetAsync(dst + nrows * ci.width, 0, (sd.cap - nrows) * ci.width, cs));
     }
+    // statistics and the row mirror follow the copies on the compute stream; the host only waits for the
+    // copies (its buffers may be reused by the caller now), the kernels overlap the next segment's DMA
+    CUDA_CK(cudaEventRecord(ctx->ev_copy, cs));
+    CUDA_CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_copy, 0));
     compute_stats(t, seg_idx);
     build_row_mirror(t, seg_idx);
-    CUDA_CK(cudaStreamSynchronize(ctx->stream));  // host buffers may be reused by the caller now
+    CUDA_CK(cudaEventSynchronize(ctx->ev_copy));
     sd.valid = true;
   });
 }
