@@ -419,8 +419,12 @@ def measure_e2e(torch, v, db, t, query, runner, plan, rows, nseg, world, dist, s
     import ctypes as C
     from viyadb_b200 import _native as N
     lib = N.load()
-    e_rows = min(rows, args.e2e_rows) if args.e2e_rows else rows
+    # N = 1: the whole table is re-uploaded every step. N > 1: a bounded share per rank (default 2.5e8 rows),
+    # so that the pinned host buffers of all ranks together stay modest; the table is cut down to exactly the
+    # uploaded segments first, so rows scanned == rows uploaded.
+    e_rows = min(rows, args.e2e_rows) if args.e2e_rows else (rows if world == 1 else min(rows, 250_000_000))
     e_nseg = (e_rows + SEG - 1) // SEG
+    e_rows = min(rows, e_nseg * SEG)
     cols = t.dimensions + t.metrics
     pinned, views = {}, {}
     h2d = 0
@@ -437,6 +441,9 @@ def measure_e2e(torch, v, db, t, query, runner, plan, rows, nseg, world, dist, s
     for s in range(e_nseg):
         n = min(SEG, e_rows - s * SEG)
         host.append({c.name: views[c.name][s * SEG:s * SEG + n] for c in cols})
+
+    for s in range(e_nseg, nseg):
+        t.invalidate(s)
 
     def step():
         for s, seg in enumerate(host):
@@ -461,8 +468,7 @@ def measure_e2e(torch, v, db, t, query, runner, plan, rows, nseg, world, dist, s
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         ms = tt.item()
     d2h = sum(a.nbytes for a in g["keys"]) + sum(a.nbytes for a in g["accs"])
-    # the query scans the whole table: segments beyond e_nseg stay resident from the first leg
-    scanned = runner.stats.scanned_recs
+    scanned = runner.stats.scanned_recs   # == e_rows: the table holds exactly the uploaded segments
     return {"value": scanned * world / (ms / 1e3), "unit": "rows/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
             "rows_uploaded_per_gpu_per_step": e_rows, "rows_scanned_per_gpu_per_step": scanned, "ms_per_step": ms, "steps": k,
             "note": "every step re-uploads all columns from pinned host memory (vgpu_segment_put), then runs the query "

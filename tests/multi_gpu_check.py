@@ -34,8 +34,13 @@ def main():
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     nseg_global = 3 * world + 1          # ragged on purpose: ranks own different numbers of segments
-    for wname, flags in (("c1", 0), ("c2", 2), ("c3", 0), ("c4", 0), ("c1", 1), ("c3", 1)):
-        w = bench.WORKLOADS[wname]
+    # low-cardinality variants: the group table is CTA-private in shared memory and merged into per-metric
+    # arrays (the multi-GPU layout) at the end of the scan
+    low = {"c1low": dict(bench.WORKLOADS["c1"], query=dict(bench.WORKLOADS["c1"]["query"], dimensions=["d0"], metrics=["m1", "m2", "count"])),
+           "c2low": dict(bench.WORKLOADS["c2"], query=dict(bench.WORKLOADS["c2"]["query"], dimensions=["d1"], metrics=["mn", "mx", "uid"])),
+           "c0": bench.WORKLOADS["c0"]}
+    for wname, flags in (("c1", 0), ("c2", 2), ("c3", 0), ("c4", 0), ("c1", 1), ("c3", 1), ("c1low", 0), ("c2low", 0), ("c0", 0)):
+        w = low.get(wname) or bench.WORKLOADS[wname]
         conf = dict(w["table"], segment_size=SEG)
         # sharded database, attached to the communicator
         db = v.Database({"tables": [conf]}, device=local)

@@ -408,7 +408,6 @@ scan_filter_groupby_kernel(const __grid_constant__ ScanParams P) {
     return __shfl_sync(0xffffffffu, u, 0);
   };
   uint32_t unit = grab();
-  bool dense_prev = false;  // the last chunk with passing rows gathered from the columns
   while (unit < nunits) {
     const uint32_t next_unit = grab();  // one ahead: its first chunk is prefetched from this unit's last one
     // a full group table / distinct set makes the host grow it and run again: stop wasting time
@@ -436,9 +435,7 @@ scan_filter_groupby_kernel(const __grid_constant__ ScanParams P) {
     // software pipeline: pull the predicate columns of this warp's NEXT chunk into L2 now (one bulk prefetch,
     // TMA unit, per column: lane f takes column f), so that its vector loads find them there instead of
     // paying a DRAM round trip per column. The chunk after the last one of a unit opens the next unit.
-    // After a dense chunk the key / metric columns of the next chunk are prefetched as well: its gathers will
-    // touch nearly every 64-byte atom of them anyway, and then find them in L2.
-    if (!(P.tune & 32u) && lane < P.nfilter_slots + (dense_prev ? P.npf_payload : 0u)) {
+    if (!(P.tune & 32u) && lane < P.nfilter_slots) {
       const uint8_t *a = nullptr;
       if (ci + 1 < c_end) {
         a = seg.slab + P.pf_off[lane] * seg.cap + (uint64_t)(chunk_row + kChunkRows) * P.pf_width[lane];
@@ -492,16 +489,6 @@ scan_filter_groupby_kernel(const __grid_constant__ ScanParams P) {
     }
     __syncwarp();
     const bool rowpath = total <= P.row_thresh;  // sparse chunk: gather from the row-major mirror
-    dense_prev = !rowpath;
-    if (rowpath && (P.tune & 2048u)) {  // start pulling the mirror rows into L2 now: they are gathered a batch later
-      const uint8_t *rows = seg.rows;
-#pragma unroll 1
-      for (uint32_t i = lane; i < total; i += 32) {
-        const uint8_t *a = rows + (uint64_t)list[npend + i] * P.row_stride + P.row_lo;
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(a));
-        if (((uint32_t)(uintptr_t)a & 63u) + P.row_span > 64u) asm volatile("prefetch.global.L2 [%0];" ::"l"(a + P.row_span - 1));
-      }
-    }
     npend += total;
 
     // ---- hand the passing rows to the aggregation stage in full batches of 32 ----

@@ -140,15 +140,13 @@ struct ScanParams {
   // row_thresh passing rows (0: never) — the break-even of the two byte counts, computed by the planner.
   uint32_t row_stride;
   uint32_t row_thresh;
-  uint32_t row_lo, row_span;  // byte range of a mirror row the query's keys and metrics occupy (L2 prefetch at enqueue)
   uint32_t conj;              // predicate is a conjunction of at most 4 vectorisable leaves (unrolled fast path)
 
   // fixed-width columns the predicate reads with vector loads (prefetched one chunk ahead)
   uint32_t nfilter_slots;
   uint8_t filter_slots[kMaxSlots];
   uint8_t pf_width[kMaxSlots];   // per predicate column f: element width and bytes-per-row offset of the column
-  uint64_t pf_off[kMaxSlots];    // in the slab (bulk L2 prefetch of the next chunk, lane f takes column f);
-  uint32_t npf_payload;          // entries nfilter_slots.. : key / metric columns the predicate does not read
+  uint64_t pf_off[kMaxSlots];    // in the slab (bulk L2 prefetch of the next chunk, lane f takes column f)
 
   // predicate
   uint32_t nprog;

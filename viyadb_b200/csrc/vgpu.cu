@@ -270,11 +270,9 @@ struct vgpu_ctx {
   uint64_t l2_persist_bytes = 0, l2_window_max = 0;
   // VGPU_TUNE: bit 0 pin the group table in L2 (off: measured slower), bit 1 evict_first column streams (on),
   // bit 2 evict_last group table, bit 5 no next-chunk L2 prefetch, bit 6 build no row-major mirror,
-  // bit 7 never gather from the mirror, bit 8 always gather from the mirror (tests), bit 11 L2 prefetch of mirror
-  // rows at enqueue (off: measured slower, it fetches 128-byte lines), bit 12 no unrolled conjunction fast path
+  // bit 7 never gather from the mirror, bit 8 always gather from the mirror (tests), bit 12 no unrolled conjunction fast path
   // (always the stack interpreter), bit 13 per-lane instead of bulk L2 prefetch of the next chunk, bit 14 no
-  // tightening of key domains from the predicate, bit 15 prefetch the key / metric columns too after dense chunks
-  // (off: measured slower), bit 18 no CTA-private shared-memory copy of small dense group tables
+  // tightening of key domains from the predicate, bit 18 no CTA-private shared-memory copy of small dense group tables
   uint32_t tune = 2;
   int ctas_per_sm = VGPU_MIN_CTAS;  // VGPU_CTAS: resident scan CTAs per SM (2, 3 or 4: picks the register cap)
   uint32_t unit_chunks = 0;  // VGPU_UNIT_CHUNKS: 512-row chunks per dynamically scheduled work unit (0: adaptive)
@@ -1961,22 +1959,6 @@ int vgpu_query_agg(vgpu_table *t, const vgpu_plan *plan, vgpu_result **out) {
       P.mets[m].width = sl.width; P.mets[m].row_off = sl.row_off;
       P.mets[m].bitset = sl.bitset; P.mets[m].bitset_idx = sl.bitset_idx;
     }
-    {  // key / metric columns after the predicate's in the prefetch table (dense chunks prefetch them too)
-      uint32_t n = P.nfilter_slots;
-      P.npf_payload = 0;
-      auto add = [&](uint32_t slot) {
-        const Slot &sl = P.slots[slot];
-        if (sl.bitset || n >= 31) return;
-        for (uint32_t f = 0; f < P.nfilter_slots; ++f) if (P.filter_slots[f] == slot) return;
-        for (uint32_t f = P.nfilter_slots; f < n; ++f) if (P.pf_off[f] == sl.off) return;
-        P.pf_width[n] = (uint8_t)sl.width;
-        P.pf_off[n] = sl.off;
-        ++n;
-      };
-      for (uint32_t k = 0; k < P.nkeys; ++k) add(P.keys[k].slot);
-      for (uint32_t m = 0; m < P.nmetrics; ++m) add(P.mets[m].slot);
-      if (ctx->tune & 32768u) P.npf_payload = n - P.nfilter_slots;  // off by default: measured slower on C3
-    }
     P.small_plan = P.nkeys <= 4 && P.nmetrics <= 4;
     for (uint32_t k = 0; k < P.nkeys; ++k)
       if (P.slots[P.keys[k].slot].width > 4) P.small_plan = 0;
@@ -2002,7 +1984,6 @@ int vgpu_query_agg(vgpu_table *t, const vgpu_plan *plan, vgpu_result **out) {
       };
       for (uint32_t k = 0; k < P.nkeys; ++k) payload(P.keys[k].slot);
       for (uint32_t m = 0; m < P.nmetrics; ++m) payload(P.mets[m].slot);
-      if (lo_off < hi_off) { P.row_lo = lo_off; P.row_span = hi_off - lo_off; }
       if (all_mirrored && !widths.empty()) {
         const double span = (double)(hi_off - lo_off);
         const double row_cost = 64.0 * (1.0 + (span - 1.0) / 64.0);
