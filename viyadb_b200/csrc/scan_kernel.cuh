@@ -242,7 +242,9 @@ __device__ __noinline__ uint64_t wide_row_cell(const ScanParams &P, const CurSeg
 #define VGPU_MIN_CTAS 3
 #endif
 // kMinCtas CTAs per SM: caps the registers (3 -> 80, 4 -> 64); the host picks (VGPU_CTAS, default VGPU_MIN_CTAS)
-template <int kMinCtas>
+// kSmemTable: the instantiation that aggregates into a CTA-private shared-memory copy of a small dense group
+// table (ScanParams::smem_cells != 0); the other one carries none of that code.
+template <int kMinCtas, bool kSmemTable>
 __global__ void __launch_bounds__(kThreads, kMinCtas)
 scan_filter_groupby_kernel(const __grid_constant__ ScanParams P) {
   __shared__ uint32_t s_list[kWarps][kListCap];  // rows (of the warp's current segment) waiting for aggregation
@@ -257,7 +259,7 @@ scan_filter_groupby_kernel(const __grid_constant__ ScanParams P) {
   // CTA-private group table (small dense domains): every cell starts as the plan's initial image
   extern __shared__ __align__(16) uint8_t s_table[];
   const uint32_t s_table_a = (uint32_t)__cvta_generic_to_shared(s_table);
-  if (P.smem_cells) {
+  if (kSmemTable) {
     const uint32_t wpc = P.smem_stride / 4, nwords = P.smem_cells * wpc;
     for (uint32_t i = threadIdx.x; i < nwords; i += kThreads) reinterpret_cast<uint32_t *>(s_table)[i] = P.smem_init[i % wpc];
   }
@@ -350,7 +352,7 @@ scan_filter_groupby_kernel(const __grid_constant__ ScanParams P) {
       }
     } else {
       cell = packed;
-      if (P.smem_cells) *reinterpret_cast<volatile uint32_t *>(s_table + (uint32_t)cell * P.smem_stride + P.smem_present_off) = 1u;
+      if (kSmemTable) *reinterpret_cast<volatile uint32_t *>(s_table + (uint32_t)cell * P.smem_stride + P.smem_present_off) = 1u;
       else st_u8_hint(P.present + cell * P.present_stride, 1u, tpol);
     }
     uint32_t dn = 0;
@@ -369,7 +371,7 @@ scan_filter_groupby_kernel(const __grid_constant__ ScanParams P) {
         pre = gather_finish(gather_raw64(a), a, ms.vmask, ms.signbit);
       }
       if (ms.op != A_DISTINCT) {
-        if (P.smem_cells) acc_update_shared(s_table_a + (uint32_t)cell * P.smem_stride + ms.soff, ms.op, pre);
+        if (kSmemTable) acc_update_shared(s_table_a + (uint32_t)cell * P.smem_stride + ms.soff, ms.op, pre);
         else acc_update(reinterpret_cast<uint8_t *>(ms.acc) + cell * ms.stride, ms.op, pre, tpol);
         continue;
       }
@@ -516,7 +518,7 @@ scan_filter_groupby_kernel(const __grid_constant__ ScanParams P) {
   }
 
   // merge the CTA-private table into the global one: the same commutative Update(), once per live cell
-  if (P.smem_cells) {
+  if (kSmemTable) {
     __syncthreads();
     for (uint32_t c = threadIdx.x; c < P.smem_cells; c += kThreads) {
       const uint8_t *cellp = s_table + c * P.smem_stride;

@@ -995,9 +995,7 @@ int vgpu_init(int device, vgpu_ctx **out) {
     cudaDeviceProp prop;
     CUDA_CK(cudaGetDeviceProperties(&prop, device));
     ctx->sm_count = prop.multiProcessorCount;
-    CUDA_CK(cudaFuncSetAttribute(scan_filter_groupby_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemTableBytes));
-    CUDA_CK(cudaFuncSetAttribute(scan_filter_groupby_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemTableBytes));
-    CUDA_CK(cudaFuncSetAttribute(scan_filter_groupby_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemTableBytes));
+    CUDA_CK(cudaFuncSetAttribute(scan_filter_groupby_kernel<3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemTableBytes));
     CUDA_CK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
     CUDA_CK(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
     CUDA_CK(cudaEventCreateWithFlags(&ctx->ev_copy, cudaEventDisableTiming));
@@ -2236,9 +2234,10 @@ int vgpu_query_agg(vgpu_table *t, const vgpu_plan *plan, vgpu_result **out) {
           attr[0].val.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
           cfg.numAttrs = 1;
         }
-        if (ctx->ctas_per_sm == 2) CUDA_CK(cudaLaunchKernelEx(&cfg, scan_filter_groupby_kernel<2>, P));
-        else if (ctx->ctas_per_sm == 4) CUDA_CK(cudaLaunchKernelEx(&cfg, scan_filter_groupby_kernel<4>, P));
-        else CUDA_CK(cudaLaunchKernelEx(&cfg, scan_filter_groupby_kernel<3>, P));
+        if (P.smem_cells) CUDA_CK(cudaLaunchKernelEx(&cfg, scan_filter_groupby_kernel<3, true>, P));
+        else if (ctx->ctas_per_sm == 2) CUDA_CK(cudaLaunchKernelEx(&cfg, scan_filter_groupby_kernel<2, false>, P));
+        else if (ctx->ctas_per_sm == 4) CUDA_CK(cudaLaunchKernelEx(&cfg, scan_filter_groupby_kernel<4, false>, P));
+        else CUDA_CK(cudaLaunchKernelEx(&cfg, scan_filter_groupby_kernel<3, false>, P));
         ++launches;
       }
       CUDA_CK(cudaEventRecord(ctx->ev_scan1, stream));
