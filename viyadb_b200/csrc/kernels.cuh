@@ -7,13 +7,9 @@
 //   Update()         src/codegen/db/store.cc:131-161 (+=, std::min, std::max, |=)
 //   count-distinct   src/util/bitset.h:26-67 (set union, cardinality)
 //
-// Design: one persistent launch over all active segments; a CTA processes tiles of
-// 4096 rows; each thread owns 4 sub-tiles x 4 consecutive rows so that every filter-column load is
-// one fully coalesced 128-bit (u32), 64-bit (u16) or 32-bit (u8) request per thread. The predicate
-// program is interpreted per 16-row register vector (uniform control flow, no divergence); key and
-// metric columns are touched only for passing rows, so their HBM traffic is sector-granular in the
-// selectivity. Group accumulators live in L2/HBM (dense mixed-radix cells, or an open-addressing
-// table keyed by the packed 64-bit key) and are updated with native RED/ATOM operations.
+// This header holds the building blocks (streaming / gather loads, UTC calendar arithmetic, accumulator
+// updates, hash cells) and every kernel but the fused scan itself (scan_kernel.cuh): count-distinct partition /
+// dedupe, multi-GPU exchange, group extraction, row-mirror build, column statistics, the synthetic generator.
 #ifndef VGPU_KERNELS_CUH_
 #define VGPU_KERNELS_CUH_
 

@@ -7,18 +7,24 @@
 //   agg_map[key].Update(m)  src/codegen/query/scan.cc:228-242, src/codegen/db/store.cc:131-161
 //   count-distinct          src/util/bitset.h:26-67 (set union; cardinality at output)
 //
-// Execution model: warps are fully independent (no CTA barrier anywhere). A warp owns a chunk of
-// 512 consecutive rows of one segment: 4 sub-chunks of 128 rows, lane l holding rows l*4..l*4+3 of
-// each, so that every filter-column load is one 128-bit (u32), 64-bit (u16) or 32-bit (u8) request
-// per lane and 512/256/128 contiguous bytes per warp instruction — all 4 sub-chunk loads of a
-// column are issued back to back (MLP 4 per lane). The predicate program is interpreted once per
-// 16-row register vector with uniform control flow. Passing rows are compacted with a packed warp
-// prefix sum into a per-warp shared-memory list, then handled one row per lane: all key and metric
-// cells of a row are loaded before anything depends on them (one DRAM round trip), the group cell
-// is found (mixed-radix index, or open-addressing probe on the packed 64-bit key) and the
-// accumulators are updated with native RED/ATOM operations; count-distinct ids go straight into a
-// global (cell,id) hash set. Key/metric HBM traffic is therefore sector-granular in the
-// selectivity, filter columns are read exactly once, nothing is written but accumulators.
+// Execution model. Warps are fully independent (no CTA barrier in the loop). Work is handed
+// out dynamically in units = runs of consecutive 512-row chunks of ONE segment, so a warp keeps the segment's
+// descriptor in registers and its queue of passing rows holds bare row numbers. A chunk is 4 sub-chunks of
+// 128 rows, lane l holding rows l*4..l*4+3 of each, so that every predicate-column load is one 128-bit (u32),
+// 64-bit (u16) or 32-bit (u8) request per lane and 512/256/128 contiguous bytes per warp instruction — the 4
+// sub-chunk loads of a column are issued back to back. Per chunk:
+//   1. one bulk L2 prefetch (cp.async.bulk.prefetch.L2, TMA unit) per predicate column pulls the NEXT chunk in;
+//   2. the predicate runs on 16-row register vectors: a conjunction of up to 4 vectorisable leaves fully
+//      unrolled on constant-bank operands, anything else through a small stack interpreter (uniform control flow);
+//   3. passing rows are compacted with one warp prefix sum into the per-warp shared-memory queue;
+//   4. full batches of 32 rows are aggregated one row per lane: all key and metric cells of a row are loaded
+//      before anything depends on them — from the row-major mirror when the chunk was sparse (the cells of a
+//      row share one or two 64-byte DRAM atoms), from the columns otherwise — the group cell is found
+//      (mixed-radix index, or open-addressing probe on the packed 64-bit key) and the accumulators are updated
+//      with native RED operations, in global memory or in a CTA-private shared-memory copy of a small dense
+//      table; count-distinct ids are appended to a per-CTA region and deduplicated after the scan.
+// Predicate columns are read exactly once, key / metric traffic is atom-granular in the selectivity, nothing is
+// written but accumulators and count-distinct pairs.
 #ifndef VGPU_SCAN_KERNEL_CUH_
 #define VGPU_SCAN_KERNEL_CUH_
 
