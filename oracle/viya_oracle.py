@@ -608,6 +608,133 @@ def run_query(table_conf, segments, dicts, query, now=None, hidden_counts=None):
             "groups": {"keys": gkeys, "accs": gaccs, "hidden_count": ghidden}}
 
 
+def run_select(table_conf, segments, dicts, query, hidden_counts=None):
+    """The reference's select query (codegen/query/scan.cc:75-166, select_query.cc:25-54): every passing row
+    is formatted and sent in (segment, tuple) order; `skip` drops the first passing rows of the whole scan;
+    after `limit` rows have been sent the TUPLE loop breaks — the segment loop goes on, so every further
+    processed segment still sends its first passing row (reproduced as is). Returns {"rows", "stats"}."""
+    dims, mets = parse_schema(table_conf)
+    cols = {c.name: c for c in dims + mets}
+    flt = make_filter(query.get("filter"))
+    sel = []   # (column, output index, time format)
+    if "select" in query:
+        for sc in query["select"]:
+            names = [c.name for c in dims + mets] if sc["column"] == "*" else [sc["column"]]
+            for nme in names:
+                if nme not in cols:
+                    raise ValueError("No such column: " + nme)
+                c = cols[nme]
+                sel.append((c, len(sel), sc.get("format", c.fmt) if (c.is_dim and c.kind == "time") else ""))
+    else:
+        for nme in query.get("dimensions", []):
+            c = cols.get(nme)
+            if c is None or not c.is_dim:
+                raise ValueError("No such dimension: " + nme)
+            sel.append((c, len(sel), ""))
+        for nme in query.get("metrics", []):
+            c = cols.get(nme)
+            if c is None or c.is_dim:
+                raise ValueError("No such metric: " + nme)
+            sel.append((c, len(sel), ""))
+    skip, limit = int(query.get("skip", 0)), int(query.get("limit", 0))
+    # AVG metrics divide by the first selected COUNT metric, else by the table's hidden `count` (scan.cc:133-154)
+    count_col = next((c for c, _, _ in sel if not c.is_dim and c.agg == "count"), None)
+    stats = {"scanned_segments": 0, "scanned_recs": 0, "aggregated_recs": 0, "output_recs": 0}
+    rows = []
+    if query.get("header"):
+        rows.append([c.name for c, _, _ in sel])
+    row_index = 0
+    for si, seg in enumerate(segments):
+        n = _seg_rows(seg, dims + mets)
+        stats["scanned_recs"] += n
+        if not process_segment(flt, seg, n, cols, dicts):
+            continue
+        stats["scanned_segments"] += 1
+        if n == 0:
+            continue
+        passing = np.nonzero(eval_filter(flt, seg, n, cols, dicts))[0]
+        for i in passing.tolist():
+            if skip > 0 and row_index < skip:
+                row_index += 1
+                continue
+            row_index += 1
+            row = []
+            for c, _, fmt in sel:
+                if c.is_dim:
+                    v = seg[c.name][i]
+                    if c.kind == "string":
+                        row.append(dicts[c.name][int(v)])
+                    elif c.kind == "time" and fmt:
+                        row.append(_time.strftime(fmt, _time.gmtime(int(v) & 0xFFFFFFFF)))
+                    elif c.kind == "boolean":
+                        row.append("true" if v else "false")
+                    else:
+                        row.append(_fmt_num(v, c.type))
+                elif c.agg == "bitset":
+                    offsets, values = seg[c.name]
+                    row.append(str(len(set(values[int(offsets[i]):int(offsets[i + 1])].tolist()))))
+                elif c.agg == "avg":
+                    cnt = seg[count_col.name][i] if count_col is not None else hidden_counts[si][i]
+                    with np.errstate(divide="ignore", invalid="ignore"):
+                        row.append("%.15g" % (np.float64(seg[c.name][i]) / np.float64(cnt)))
+                else:
+                    row.append(_fmt_num(seg[c.name][i], c.type))
+            rows.append(row)
+            stats["output_recs"] += 1
+            if limit > 0 and stats["output_recs"] >= limit:
+                break   # leaves the tuple loop only (scan.cc:161): the next segment is still visited
+    return {"rows": rows, "stats": stats}
+
+
+def run_search(table_conf, segments, dicts, query):
+    """The reference's search query (scan.cc:249-299, post_agg.cc:149-166): distinct codes of one dimension
+    over the passing rows, in scan order; a code seen for the first time whose formatted value contains `term`
+    is collected; after `limit` values the tuple loop breaks (the segment loop goes on, like select). The
+    values are sent as ONE row (RowOutput::SendAsCol). stats.aggregated_recs = distinct codes seen."""
+    dims, mets = parse_schema(table_conf)
+    cols = {c.name: c for c in dims + mets}
+    flt = make_filter(query.get("filter"))
+    d = cols.get(query["dimension"])
+    if d is None or not d.is_dim:
+        raise ValueError("No such dimension: " + str(query.get("dimension")))
+    term, limit = query["term"], int(query.get("limit", 0))
+    stats = {"scanned_segments": 0, "scanned_recs": 0, "aggregated_recs": 0, "output_recs": 0}
+    codes, values = set(), []
+    for seg in segments:
+        n = _seg_rows(seg, dims + mets)
+        stats["scanned_recs"] += n
+        if not process_segment(flt, seg, n, cols, dicts):
+            continue
+        stats["scanned_segments"] += 1
+        if n == 0:
+            continue
+        passing = np.nonzero(eval_filter(flt, seg, n, cols, dicts))[0]
+        col = seg[d.name]
+        for i in passing.tolist():
+            v = col[i]
+            key = v.tobytes()
+            if key in codes:
+                continue
+            codes.add(key)
+            if d.kind == "string":
+                s = dicts[d.name][int(v)]
+            elif d.kind == "boolean":
+                s = "true" if v else "false"
+            else:
+                s = _fmt_num(v, d.type)
+            if term in s:
+                values.append(s)
+                if limit > 0 and len(values) >= limit:
+                    break
+    stats["aggregated_recs"] = len(codes)
+    stats["output_recs"] = len(values)
+    rows = []
+    if query.get("header"):
+        rows.append([d.name])
+    rows.append(values)
+    return {"rows": rows, "stats": stats}
+
+
 def _seg_rows(seg, columns):
     for c in columns:
         v = seg[c.name]

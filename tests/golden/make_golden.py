@@ -43,11 +43,11 @@ def from_gtest_capture(run=True):
     if run:
         subprocess.run([os.path.join(ROOT, "oracle", "run_capture.sh")], check=True)
     cap = os.path.join(REF, "capture")
-    out = []
+    out, out_sel = [], []
     for line in open(os.path.join(cap, "capture.jsonl")):
         r = json.loads(line)
         q = r["query"]
-        if q.get("type") != "aggregate":
+        if q.get("type") not in ("aggregate", "select", "search"):
             continue
         tables = [t for t in r["db"].get("tables", []) if t["name"] == q.get("table")]
         if not tables:
@@ -61,20 +61,22 @@ def from_gtest_capture(run=True):
             rec["rows"], rec["stats"] = r["rows"], r["stats"]
         if "dump" in r:
             rec["seg"] = store_dump(os.path.join(cap, r["dump"]))
-        out.append(rec)
-    with open(os.path.join(HERE, "ref_gtest.jsonl"), "w") as f:
-        for rec in out:
-            f.write(json.dumps(rec, sort_keys=True) + "\n")
-    print(f"ref_gtest.jsonl: {len(out)} aggregate queries from the reference's gtests")
+        (out if q.get("type") == "aggregate" else out_sel).append(rec)
+    for name, recs in (("ref_gtest.jsonl", out), ("ref_gtest_select.jsonl", out_sel)):
+        with open(os.path.join(HERE, name), "w") as f:
+            for rec in recs:
+                f.write(json.dumps(rec, sort_keys=True) + "\n")
+    print(f"ref_gtest.jsonl: {len(out)} aggregate queries, ref_gtest_select.jsonl: {len(out_sel)} select / search "
+          f"queries from the reference's gtests")
 
 
-def from_scenarios():
+def from_scenarios(which="SCENARIOS", target="ref_scenarios.jsonl"):
     sys.path.insert(0, HERE)
     import scenarios
     tmp = os.path.join(REF, "scenario_tmp")
     os.makedirs(tmp, exist_ok=True)
     out = []
-    for sc in scenarios.SCENARIOS:
+    for sc in getattr(scenarios, which):
         job = {"state_dir": os.path.join(REF, "state"), "table": sc["table"], "queries": sc["queries"],
                "dump": os.path.join(tmp, sc["name"] + ".bin")}
         for k in ("rows", "generate", "rollup_ts"):
@@ -98,10 +100,10 @@ def from_scenarios():
                 rec["rows"], rec["stats"] = r["rows"], r["stats"]
             out.append(rec)
         print(f"  {sc['name']}: {res['stored_rows']} rows in {res['segments']} segments, {len(sc['queries'])} queries")
-    with open(os.path.join(HERE, "ref_scenarios.jsonl"), "w") as f:
+    with open(os.path.join(HERE, target), "w") as f:
         for rec in out:
             f.write(json.dumps(rec, sort_keys=True) + "\n")
-    print(f"ref_scenarios.jsonl: {len(out)} queries")
+    print(f"{target}: {len(out)} queries")
 
 
 if __name__ == "__main__":
@@ -111,3 +113,5 @@ if __name__ == "__main__":
         from_gtest_capture(run="--no-run" not in what)
     if "scenarios" in what:
         from_scenarios()
+    if "select" in what or not sys.argv[1:]:
+        from_scenarios("SELECT_SCENARIOS", "ref_select_scenarios.jsonl")

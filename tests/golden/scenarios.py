@@ -138,3 +138,70 @@ SCENARIOS = [
      "queries": [agg(select=[{"column": "d0"}, {"column": "t1", "granularity": "hour", "format": "%Y-%m-%d %H:%M:%S"}, {"column": "m1"}, {"column": "count"}]),
                  agg(select=[{"column": "t1", "format": "%Y-%m-%d %H:%M:%S"}, {"column": "count"}])]},
 ]
+
+
+# ---- select / search queries: oracle groundwork, pinned on CPU by tests/test_oracle_select.py.
+# Not part of SCENARIOS: the drop-in GPU tests do not run them yet (GpuQueryRunner delegates them to the stock runner).
+def sel(**kw):
+    q = {"type": "select", "table": "events"}
+    q.update(kw)
+    return q
+
+
+def search(**kw):
+    q = {"type": "search", "table": "events"}
+    q.update(kw)
+    return q
+
+
+def _table(name):
+    return next(sc for sc in SCENARIOS if sc["name"] == name)
+
+
+SELECT_SCENARIOS = [
+    {"name": "select_inapp", "table": INAPP, "rows": INAPP_ROWS, "queries": [
+        sel(dimensions=["event_name", "country"], metrics=["revenue"], filter={"op": "eq", "column": "country", "value": "US"}),
+        sel(dimensions=["country"], metrics=["revenue", "count"], header=True),
+        sel(dimensions=["event_name", "country"], metrics=["revenue"], limit=2),
+        sel(dimensions=["event_name", "country"], metrics=["revenue"], skip=6),
+        sel(select=[{"column": "*"}], filter={"op": "gt", "column": "revenue", "value": "1.05"}, skip=1, limit=3),
+        sel(select=[{"column": "install_time"}, {"column": "count"}], filter={"op": "in", "column": "country", "values": ["KZ", "RU", "XX"]}),
+        search(dimension="country", term="", filter={"op": "gt", "column": "revenue", "value": "1"}),
+        search(dimension="event_name", term="d"),
+        search(dimension="event_name", term="re", limit=1, header=True),
+        search(dimension="install_time", term="2"),
+        search(dimension="country", term="zzz"),
+    ]},
+    # three segments of two rows: `limit` only breaks the tuple loop, later segments still send one row each
+    {"name": "select_multiseg", "table": _table("prune_quirk")["table"], "rows": _table("prune_quirk")["rows"], "queries": [
+        sel(dimensions=["n", "s"], metrics=["count"]),
+        sel(dimensions=["n", "s"], metrics=["count"], limit=1),
+        sel(dimensions=["n", "s"], metrics=["count"], skip=1, limit=2),
+        sel(dimensions=["n"], metrics=[], filter={"op": "ge", "column": "n", "value": "10"}, limit=1),
+        sel(dimensions=["s"], metrics=["count"], filter={"op": "eq", "column": "s", "value": "a"}, skip=2),
+        search(dimension="s", term="", limit=1),
+        search(dimension="n", term="1"),
+        search(dimension="n", term="1", limit=2, filter={"op": "ne", "column": "s", "value": "b"}),
+    ]},
+    {"name": "select_types", "table": _table("metric_types")["table"], "rows": _table("metric_types")["rows"], "queries": [
+        sel(select=[{"column": "*"}]),
+        sel(dimensions=["k"], metrics=["lav", "fmx", "dmx"], filter={"op": "lt", "column": "is", "value": "0"}),
+    ]},
+    {"name": "select_bitset", "table": _table("users_bitset")["table"], "rows": _table("users_bitset")["rows"], "queries": [
+        sel(dimensions=["country", "event_name"], metrics=["user_id"]),
+        sel(dimensions=["country"], metrics=["user_id"], filter={"op": "gt", "column": "user_id", "value": "1"}),
+        search(dimension="event_name", term="p", filter={"op": "eq", "column": "country", "value": "US"}),
+    ]},
+    {"name": "select_time", "rollup_ts": NOW, "table": _table("time_rollup")["table"], "rows": _table("time_rollup")["rows"][:12], "queries": [
+        sel(select=[{"column": "install_time", "format": "%Y-%m-%d %H:%M:%S"}, {"column": "mt"}, {"column": "count"}], limit=5),
+        sel(select=[{"column": "install_time"}, {"column": "country"}], skip=9),
+    ]},
+    {"name": "select_c1", "table": _table("c1_twin")["table"], "generate": _table("c1_twin")["generate"], "queries": [
+        sel(dimensions=["d0", "d1", "d2"], metrics=["m1", "m2", "count"], filter={"op": "eq", "column": "d0", "value": "a7"}, skip=5, limit=10),
+        sel(dimensions=["d3"], metrics=["m1"], filter={"op": "and", "filters": [
+            {"op": "eq", "column": "d1", "value": "b3"}, {"op": "eq", "column": "d2", "value": "c4"}]}),
+        search(dimension="d1", term="b1"),
+        search(dimension="d1", term="b1", limit=3, filter={"op": "eq", "column": "d0", "value": "a2"}),
+        search(dimension="d2", term="c"),
+    ]},
+]
