@@ -240,6 +240,7 @@ def main_reference(args):
     procs = os.cpu_count() or 1
     rows_per_proc = args.ref_rows // procs
     r = run_reference(args.workload, rows_per_proc, procs, args.warmup, args.steps)
+    r1 = run_reference(args.workload, rows_per_proc, 1, 1, 2)   # the reference's real per-query execution: one thread
     w = WORKLOADS[args.workload]
     line = {"impl": "reference", "metric": "scanned rows/sec", "unit": "rows/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -251,7 +252,9 @@ def main_reference(args):
         return 0
     sample = f"{r['rows']} rows of {args.workload} as {procs} shared-nothing single-threaded reference shards"
     line.update({"value": r["value"], "ms_per_step": r["ms_per_step"],
-                 "cpu_baseline": {"value": r["value"], "unit": "rows/s", "cores": procs, "kind": "reference", "sample": sample},
+                 "cpu_baseline": {"value": r["value"], "unit": "rows/s", "cores": procs, "kind": "reference", "sample": sample,
+                                  "value_1core": (r1 or {}).get("value"),
+                                  "sample_1core": f"{rows_per_proc} rows, one single-threaded reference process"},
                  "e2e": {"value": r["value"], "unit": "rows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
     line["config"]["rows"] = r["rows"]
     print(json.dumps(line))
@@ -377,8 +380,10 @@ def main_ours(args):
     if rank == 0 and world == 1 and not args.no_cpu:
         procs = os.cpu_count() or 1
         r = run_reference(args.workload, args.ref_rows // procs, procs, 1, 3)
+        r1 = run_reference(args.workload, args.ref_rows // procs, 1, 1, 2)
         if r and "error" not in r:
             cpu = {"value": r["value"], "unit": "rows/s", "cores": procs, "kind": "reference",
+                   "value_1core": (r1 or {}).get("value"),
                    "sample": f"{r['rows']} rows of {args.workload} as {procs} shared-nothing single-threaded shards of "
                              f"the unmodified reference (oracle/_ref/oracle_cli), query time only, mean of 3"}
         else:
