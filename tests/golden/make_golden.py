@@ -115,3 +115,5 @@ if __name__ == "__main__":
         from_scenarios()
     if "select" in what or not sys.argv[1:]:
         from_scenarios("SELECT_SCENARIOS", "ref_select_scenarios.jsonl")
+    if "edge" in what or not sys.argv[1:]:
+        from_scenarios("EDGE_SCENARIOS", "ref_edge_scenarios.jsonl")

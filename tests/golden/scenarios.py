@@ -205,3 +205,59 @@ SELECT_SCENARIOS = [
         search(dimension="d2", term="c"),
     ]},
 ]
+
+
+# ---- extra edge cases for the aggregate oracle (CPU pinning only; not run by the drop-in GPU tests) ----
+EDGE_SCENARIOS = [
+    {"name": "edge_empty", "table": INAPP, "rows": [], "queries": [
+        agg(dimensions=["country"], metrics=["count", "revenue"]),
+        agg(dimensions=[], metrics=["count"]),
+        agg(dimensions=["country"], metrics=["count"], header=True, sort=[{"column": "count"}], limit=3),
+    ]},
+    {"name": "edge_ragged", "table": {"name": "events", "segment_size": 3,
+                                      "dimensions": [{"name": "k"}, {"name": "n", "type": "int"}, {"name": "f", "type": "double"}],
+                                      "metrics": [{"name": "count", "type": "count"}, {"name": "ulmx", "type": "ulong_max"},
+                                                  {"name": "lmn", "type": "long_min"}, {"name": "isum", "type": "int_sum"}]},
+     "rows": [["a", "-5", "0.0", "18446744073709551615", "-9223372036854775808", "2147483647"],
+              ["a", "-5", "-0.0", "1", "5", "2147483647"],
+              ["b", "7", "1.5", "0", "0", "-1"],
+              ["b", "-2147483648", "1.5", "3", "-3", "1"],
+              ["c", "2147483647", "-1e300", "9", "9", "0"],
+              ["a", "0", "2.5", "4", "4", "4"],
+              ["c", "1", "2.5", "18446744073709551614", "8", "-2147483648"]],
+     "queries": [
+         agg(dimensions=["k"], metrics=["count", "ulmx", "lmn", "isum"]),
+         agg(dimensions=["n"], metrics=["count"], sort=[{"column": "n", "ascending": True}]),
+         agg(dimensions=["f"], metrics=["count", "isum"]),
+         agg(dimensions=["k", "n"], metrics=["ulmx"], filter={"op": "lt", "column": "n", "value": "0"}),
+         agg(dimensions=["k"], metrics=["count"], filter={"op": "ge", "column": "f", "value": "1.5"}),
+         agg(dimensions=["k"], metrics=["isum"], having={"op": "lt", "column": "isum", "value": "0"}),
+         agg(dimensions=["k"], metrics=["count"], filter={"op": "not", "filter": {"op": "in", "column": "k", "values": ["a", "zz"]}}),
+         agg(dimensions=["k"], metrics=["count"], filter={"op": "in", "column": "k", "values": ["zz", "yy"]}),
+         agg(dimensions=["k"], metrics=["lmn"], filter={"op": "gt", "column": "ulmx", "value": "3"},
+             sort=[{"column": "lmn", "ascending": True}, {"column": "k"}]),
+     ]},
+    {"name": "edge_bitset_dups", "table": {"name": "events", "segment_size": 2, "dimensions": [{"name": "c"}],
+                                           "metrics": [{"name": "u", "type": "bitset"}, {"name": "count", "type": "count"}]},
+     "rows": [["x", "1"], ["y", "1"], ["x", "2"], ["x", "1"], ["y", "1"], ["z", "4000000000"], ["x", "3"]],
+     "queries": [
+         agg(dimensions=["c"], metrics=["u", "count"]),
+         agg(dimensions=[], metrics=["u"]),
+         agg(dimensions=["c"], metrics=["u"], having={"op": "ge", "column": "u", "value": "2"}),
+         agg(dimensions=["c"], metrics=["count"], filter={"op": "ge", "column": "u", "value": "2"}),
+     ]},
+    {"name": "edge_time_literals", "rollup_ts": NOW,
+     "table": {"name": "events", "dimensions": [{"name": "t", "type": "time", "format": "posix"}, {"name": "b", "type": "boolean"}],
+               "metrics": [{"name": "count", "type": "count"}]},
+     "rows": [[str(1496275200 + 3600 * h), "true" if h % 3 else "false"] for h in range(0, 96, 5)],
+     "queries": [
+         agg(select=[{"column": "t", "granularity": "day", "format": "%Y-%m-%d"}, {"column": "count"}],
+             filter={"op": "ge", "column": "t", "value": "2017-06-02"}),
+         agg(select=[{"column": "t", "granularity": "day", "format": "%Y-%m-%d"}, {"column": "count"}],
+             filter={"op": "lt", "column": "t", "value": "2017-06-02 12:00:00"}),
+         agg(select=[{"column": "b"}, {"column": "count"}], filter={"op": "gt", "column": "t", "value": "1496361600"}),
+         agg(select=[{"column": "t", "granularity": "month", "format": "%Y-%m"}, {"column": "b"}, {"column": "count"}],
+             filter={"op": "eq", "column": "b", "value": "true"}),
+         agg(dimensions=["b"], metrics=["count"], filter={"op": "ne", "column": "b", "value": "false"}),
+     ]},
+]

@@ -8,6 +8,7 @@ import viya_oracle
 
 GTEST = G.records("ref_gtest.jsonl")
 SCEN = G.records("ref_scenarios.jsonl")
+EDGE = G.records("ref_edge_scenarios.jsonl")   # empty table, ragged segments, type extremes, -0.0 keys, time literals
 
 
 def check(rec):
@@ -43,4 +44,9 @@ def test_oracle_matches_reference_gtests(rec):
 
 @pytest.mark.parametrize("rec", SCEN, ids=[G.rec_id(r) for r in SCEN])
 def test_oracle_matches_reference_scenarios(rec):
+    check(rec)
+
+
+@pytest.mark.parametrize("rec", EDGE, ids=[G.rec_id(r) for r in EDGE])
+def test_oracle_matches_reference_edge_cases(rec):
     check(rec)
