@@ -9,6 +9,7 @@ pytestmark = pytest.mark.gpu
 
 GTEST = G.records("ref_gtest.jsonl")
 SCEN = G.records("ref_scenarios.jsonl")
+EDGE = G.records("ref_edge_scenarios.jsonl")
 
 
 @pytest.fixture(scope="module")
@@ -72,3 +73,15 @@ def test_reference_gtests_hashed_group_table(vdb, rec):
 @pytest.mark.parametrize("rec", SCEN, ids=[G.rec_id(r) for r in SCEN])
 def test_reference_scenarios(vdb, rec):
     run(vdb, rec)
+
+
+@pytest.mark.parametrize("flags", [0, 1], ids=["auto", "force_hash"])
+@pytest.mark.parametrize("rec", EDGE, ids=[G.rec_id(r) for r in EDGE])
+def test_reference_edge_cases(vdb, rec, flags):
+    """Empty table, ragged segments, 64-bit extremes, int wrap, bitset duplicates across segments, time literals."""
+    try:
+        run(vdb, rec, flags=flags)
+    except vdb.VgpuError as e:
+        if flags == 1 and e.code == -2:
+            pytest.skip("key wider than 64 bits")
+        raise
