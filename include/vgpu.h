@@ -221,7 +221,11 @@ int vgpu_table_create(vgpu_ctx *ctx, const vgpu_schema *schema, vgpu_table **out
 void vgpu_table_free(vgpu_table *table);
 /* Copy rows [0,nrows) of every column of segment seg_idx into HBM. col_ptrs[c] is the host base
  * address of the column array (any alignment; may be pageable or pinned), or a vgpu_bitset_csr*
- * for BITSET columns. Replaces any previous content of that segment. */
+ * for BITSET columns. Replaces any previous content of that segment. The host buffers may be reused
+ * as soon as the call returns (the copies run on a dedicated stream and are waited for; the per-column
+ * statistics and the row-major mirror of the segment are built asynchronously behind them and are
+ * ordered before any later query). HBM footprint per row: the column widths, plus the same again
+ * (rounded up to 4 or 8 bytes) for the mirror unless VGPU_TUNE bit 6 is set. */
 int vgpu_segment_put(vgpu_table *table, uint32_t seg_idx, uint64_t nrows,
                      const void *const *col_ptrs);
 int vgpu_table_invalidate(vgpu_table *table, uint32_t seg_idx);
