@@ -253,6 +253,69 @@ int vgpu_query_agg(vgpu_table *table, const vgpu_plan *plan, vgpu_result **out);
 int vgpu_result_get(const vgpu_result *res, vgpu_result_view *view);
 void vgpu_result_free(vgpu_result *res);
 
+/* ---- select and search queries (same segment pruning and row predicate as the aggregate query) ----
+ * vgpu_query_select replaces the generated `viya_query_select` (src/codegen/query/select_query.cc:25-54,
+ * fn type query::SelectQueryFn, src/query/runner.h:30-32, called at runner.cc:29-43) up to the formatting of
+ * the cells: it returns, in the reference's output order, the raw cells of the rows the reference would send
+ * — every passing row in (segment, tuple) order, the first `skip` of them dropped, and `limit` applied the
+ * way scan.cc:161 does (the tuple loop breaks, the segment loop goes on: once `limit` rows are out, every
+ * further processed segment still contributes its first passing row). */
+typedef struct vgpu_rows_plan {
+  uint32_t nnodes;
+  uint32_t nargs;
+  const vgpu_pred_node *nodes;
+  const uint64_t *args;
+  uint32_t ncols;
+  uint32_t reserved;
+  const uint32_t *cols; /* schema columns to materialise (dimensions, metrics, the hidden count), any order */
+  uint64_t skip;        /* SelectQuery::skip()  */
+  uint64_t limit;       /* SelectQuery::limit(), 0 = none */
+} vgpu_rows_plan;
+
+typedef struct vgpu_rows vgpu_rows;
+typedef struct vgpu_rows_view {
+  uint64_t nrows;
+  uint32_t ncols;
+  uint32_t launches;
+  const void *const *cells; /* cells[c]: array[nrows] of the column's element type; BITSET: cardinality, uint64_t */
+  uint64_t scanned_recs;
+  uint64_t scanned_segments;
+  uint64_t passed_rows;     /* passing rows of all processed segments (the reference does not count them) */
+  double gpu_ms;
+} vgpu_rows_view;
+int vgpu_query_select(vgpu_table *table, const vgpu_rows_plan *plan, vgpu_rows **out);
+int vgpu_rows_get(const vgpu_rows *rows, vgpu_rows_view *view);
+void vgpu_rows_free(vgpu_rows *rows);
+
+/* vgpu_query_search replaces the scan of the generated `viya_query_search` (src/codegen/query/scan.cc:249-299):
+ * for every processed segment, in scan order, the distinct values of one integer-typed dimension among the
+ * passing rows with the first row that holds each, ascending by that row. The caller replays the reference's
+ * sequential part on these short lists (codes.insert, substring match on the formatted value, `limit` breaking
+ * the tuple loop only) — string work that needs the host-side dictionary. */
+typedef struct vgpu_search_plan {
+  uint32_t nnodes;
+  uint32_t nargs;
+  const vgpu_pred_node *nodes;
+  const uint64_t *args;
+  uint32_t col; /* the dimension (schema column index); floating-point dimensions are not supported */
+  uint32_t reserved;
+} vgpu_search_plan;
+
+typedef struct vgpu_search vgpu_search;
+typedef struct vgpu_search_view {
+  uint32_t nsegments;          /* processed segments, scan order */
+  uint32_t launches;
+  const uint64_t *seg_offsets; /* [nsegments + 1] into codes / first_row */
+  const uint64_t *codes;       /* raw value, widened to 64 bits (sign-extended for signed types) */
+  const uint32_t *first_row;   /* ascending inside a segment */
+  uint64_t scanned_recs;
+  uint64_t scanned_segments;
+  double gpu_ms;
+} vgpu_search_view;
+int vgpu_query_search(vgpu_table *table, const vgpu_search_plan *plan, vgpu_search **out);
+int vgpu_search_get(const vgpu_search *res, vgpu_search_view *view);
+void vgpu_search_free(vgpu_search *res);
+
 /* ---- multi-GPU (one process per GPU) ----
  * unique_id is the 128-byte ncclUniqueId produced by rank 0 (vgpu_comm_unique_id) and distributed
  * by the host's own plumbing (torch.distributed, MPI, a file...). After vgpu_comm_init,

@@ -639,6 +639,9 @@ def run_select(table_conf, segments, dicts, query, hidden_counts=None):
     skip, limit = int(query.get("skip", 0)), int(query.get("limit", 0))
     # AVG metrics divide by the first selected COUNT metric, else by the table's hidden `count` (scan.cc:133-154)
     count_col = next((c for c, _, _ in sel if not c.is_dim and c.agg == "count"), None)
+    if count_col is None and any((not c.is_dim) and c.agg == "avg" for c, _, _ in sel) and any(m.agg == "count" for m in mets):
+        # tuple_metrics._count only exists when the table has AVG and no COUNT metric (store.cc:286-289)
+        raise RuntimeError("reference JIT compile error: 'struct Metrics' has no member named '_count'")
     stats = {"scanned_segments": 0, "scanned_recs": 0, "aggregated_recs": 0, "output_recs": 0}
     rows = []
     if query.get("header"):

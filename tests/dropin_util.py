@@ -33,7 +33,7 @@ if __name__ == "__main__":
     # pre-warm the reference's JIT cache (oracle/_ref/state) for every scenario: run in the authoring
     # container, where /root/reference and g++ can compile; the .so files then travel with gpurun
     import scenarios
-    for sc in scenarios.SCENARIOS:
+    for sc in scenarios.SCENARIOS + scenarios.SELECT_SCENARIOS:
         out = run_scenario(sc, stock_only=True)
         bad = [r for r in out.get("results", []) if "error" in r.get("stock", {})]
         print(sc["name"], "fatal: " + out["fatal"] if "fatal" in out else f"{len(out['results'])} queries, {len(bad)} errors")

@@ -72,3 +72,24 @@ def rows_equal_numeric(a, b, rtol=1e-12):
             elif not (x == y or abs(x - y) <= rtol * max(abs(x), abs(y))):
                 return False
     return True
+
+
+SEL_GOLD = {r["test"]: r for r in G.records("ref_select_scenarios.jsonl")}
+
+
+@pytest.mark.parametrize("sc", scenarios.SELECT_SCENARIOS, ids=[s["name"] for s in scenarios.SELECT_SCENARIOS])
+def test_gpu_runner_select_search_equals_stock_runner(sc):
+    """Select / search: output order is defined, so the rows of both runners and of the golden run are identical."""
+    if not os.path.exists(D.CLI):
+        pytest.skip("vgpu_cli not built (needs the reference headers: make -C oracle gpu_cli)")
+    out = D.run_scenario(sc)
+    assert "fatal" not in out, out.get("fatal")
+    for qi, (q, res) in enumerate(zip(sc["queries"], out["results"])):
+        stock, gpu = res["stock"], res["gpu"]
+        assert ("error" in stock) == ("error" in gpu), (qi, stock.get("error"), gpu.get("error"))
+        if "error" in stock:
+            continue
+        gold = SEL_GOLD[f"{sc['name']}.{qi}"]
+        assert gpu["rows"] == stock["rows"] == gold["rows"], (qi, gpu["rows"][:3], stock["rows"][:3])
+        for k in ("scanned_segments", "scanned_recs", "aggregated_recs", "output_recs"):
+            assert gpu["stats"][k] == stock["stats"][k] == gold["stats"][k], (qi, k, gpu["stats"], stock["stats"])

@@ -117,4 +117,6 @@ def test_query_validation_errors(db):
     with pytest.raises(ValueError, match="No such column"):
         QueryFactory.create({"type": "aggregate", "table": "events", "select": [{"column": "nope"}]}, db)
     with pytest.raises(NotImplementedError):
+        QueryFactory.create({"type": "show", "table": "events"}, db)
+    with pytest.raises(KeyError):      # config.str("dimension") throws in the reference too (query.cc:141)
         QueryFactory.create({"type": "search", "table": "events"}, db)

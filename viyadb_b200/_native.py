@@ -73,6 +73,29 @@ class ResultView(C.Structure):
                 ("launches", C.c_uint32), ("table_mode", C.c_uint32), ("table_cells", C.c_uint64)]
 
 
+class RowsPlan(C.Structure):
+    _fields_ = [("nnodes", C.c_uint32), ("nargs", C.c_uint32), ("nodes", C.POINTER(PredNode)),
+                ("args", C.POINTER(C.c_uint64)), ("ncols", C.c_uint32), ("reserved", C.c_uint32),
+                ("cols", C.POINTER(C.c_uint32)), ("skip", C.c_uint64), ("limit", C.c_uint64)]
+
+
+class RowsView(C.Structure):
+    _fields_ = [("nrows", C.c_uint64), ("ncols", C.c_uint32), ("launches", C.c_uint32),
+                ("cells", C.POINTER(C.c_void_p)), ("scanned_recs", C.c_uint64), ("scanned_segments", C.c_uint64),
+                ("passed_rows", C.c_uint64), ("gpu_ms", C.c_double)]
+
+
+class SearchPlan(C.Structure):
+    _fields_ = [("nnodes", C.c_uint32), ("nargs", C.c_uint32), ("nodes", C.POINTER(PredNode)),
+                ("args", C.POINTER(C.c_uint64)), ("col", C.c_uint32), ("reserved", C.c_uint32)]
+
+
+class SearchView(C.Structure):
+    _fields_ = [("nsegments", C.c_uint32), ("launches", C.c_uint32), ("seg_offsets", C.POINTER(C.c_uint64)),
+                ("codes", C.POINTER(C.c_uint64)), ("first_row", C.POINTER(C.c_uint32)),
+                ("scanned_recs", C.c_uint64), ("scanned_segments", C.c_uint64), ("gpu_ms", C.c_double)]
+
+
 class GenCol(C.Structure):
     _fields_ = [("lo", C.c_int64), ("range", C.c_uint64), ("mode", C.c_uint32), ("reserved", C.c_uint32),
                 ("div", C.c_uint64)]
@@ -97,6 +120,12 @@ SYMBOLS = [
     ("vgpu_query_agg", C.c_int, [C.c_void_p, C.POINTER(Plan), C.POINTER(C.c_void_p)]),
     ("vgpu_result_get", C.c_int, [C.c_void_p, C.POINTER(ResultView)]),
     ("vgpu_result_free", None, [C.c_void_p]),
+    ("vgpu_query_select", C.c_int, [C.c_void_p, C.POINTER(RowsPlan), C.POINTER(C.c_void_p)]),
+    ("vgpu_rows_get", C.c_int, [C.c_void_p, C.POINTER(RowsView)]),
+    ("vgpu_rows_free", None, [C.c_void_p]),
+    ("vgpu_query_search", C.c_int, [C.c_void_p, C.POINTER(SearchPlan), C.POINTER(C.c_void_p)]),
+    ("vgpu_search_get", C.c_int, [C.c_void_p, C.POINTER(SearchView)]),
+    ("vgpu_search_free", None, [C.c_void_p]),
     ("vgpu_comm_unique_id", C.c_int, [C.c_void_p]),
     ("vgpu_comm_init", C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     ("vgpu_comm_destroy", C.c_int, [C.c_void_p]),

@@ -7,7 +7,7 @@
 // There is NO CPU implementation of the scan in this library: without a CUDA device every entry
 // point fails with VGPU_ERR_CUDA.
 #include "../../include/vgpu.h"
-#include "scan_kernel.cuh"
+#include "select_kernels.cuh"
 
 #include <algorithm>
 #include <cfloat>
@@ -334,6 +334,22 @@ struct vgpu_table {
   // scratch high-water marks so that a repeated query shape never re-runs on overflow
   uint64_t hash_cap_hint = 0;
   uint64_t pairs_cap_hint = 0;
+};
+
+// results of select / search queries: arrays inside one pinned host block
+struct vgpu_rows {
+  std::shared_ptr<PinnedPool> pool;
+  std::pair<void *, size_t> block{nullptr, 0};
+  std::vector<const void *> cell_ptrs;
+  vgpu_rows_view view{};
+  ~vgpu_rows() {
+    if (block.first && pool) pool->release(block);
+  }
+};
+struct vgpu_search {
+  std::vector<uint64_t> seg_offsets, codes;
+  std::vector<uint32_t> first_row;
+  vgpu_search_view view{};
 };
 
 struct vgpu_result {
@@ -1384,6 +1400,57 @@ struct QueryRun {
   QueryRun(vgpu_table *table, const vgpu_plan *p) : t(table), plan(p), planner(table, p) {}
 };
 
+// predicate program -> the columns it streams, the prefetch table, the unrolled-conjunction flag; then the
+// segment loop bookkeeping + pruning (scan.cc:42-51). Shared by the aggregate, select and search queries.
+void finish_predicate_and_prune(vgpu_ctx *ctx, vgpu_table *t, QueryRun &q) {
+  Planner &pl = q.planner;
+  ScanParams &P = pl.P;
+  pl.build_predicate();
+  for (uint32_t i = 0; i < P.nprog; ++i) {
+    const PInstr &in = P.prog[i];
+    if (in.kind > P_OR_LEAF || !(in.cls == C_EQ32 || in.cls == C_LT32 || in.cls == C_RNG32 || in.cls == C_LUT64)) continue;
+    bool seen = false;
+    for (uint32_t f = 0; f < P.nfilter_slots; ++f) seen = seen || P.filter_slots[f] == in.slot;
+    if (!seen) P.filter_slots[P.nfilter_slots++] = in.slot;
+  }
+  for (uint32_t f = 0; f < P.nfilter_slots; ++f) {
+    P.pf_width[f] = (uint8_t)P.slots[P.filter_slots[f]].width;
+    P.pf_off[f] = P.slots[P.filter_slots[f]].off;
+  }
+  // conjunction of at most 4 vectorisable leaves: the kernel's unrolled fast path
+  P.conj = P.nprog >= 1 && P.nprog <= 4 && !(ctx->tune & 4096u);
+  for (uint32_t i = 0; i < P.nprog && P.conj; ++i) {
+    const PInstr &in = P.prog[i];
+    const bool vec = in.cls == C_EQ32 || in.cls == C_LT32 || in.cls == C_RNG32 || in.cls == C_LUT64;
+    if (!vec || in.kind != (i == 0 ? P_PUSH : P_AND_LEAF)) P.conj = 0;
+  }
+  for (uint32_t s = 0; s < t->segs.size(); ++s) {
+    const SegmentData &sd = t->segs[s];
+    if (!sd.valid) continue;
+    q.scanned_recs += sd.nrows;
+    if (!pl.process_segment(sd, pl.root)) continue;
+    q.active.push_back(s);
+    q.active_rows += sd.nrows;
+  }
+}
+
+// the part of ScanParams every scan-core kernel needs besides the predicate: the work list
+void set_work_list(vgpu_table *t, QueryRun &q, Scratch &scratch, cudaStream_t stream) {
+  ScanParams &P = q.planner.P;
+  uint64_t max_rows = 0;
+  for (uint32_t s : q.active) max_rows = std::max(max_rows, t->segs[s].nrows);
+  P.tiles_per_seg = (uint32_t)std::max<uint64_t>(1, (max_rows + kChunkRows - 1) / kChunkRows);
+  P.nactive = (uint32_t)q.active.size();
+  P.total_tiles = (uint64_t)P.nactive * P.tiles_per_seg;
+  upload_descs(t);
+  P.segs = t->d_segs;
+  P.tune = t->ctx->tune;
+  uint32_t *d_active = scratch.alloc<uint32_t>(q.active.size());
+  if (!q.active.empty())
+    CUDA_CK(cudaMemcpyAsync(d_active, q.active.data(), q.active.size() * 4, cudaMemcpyHostToDevice, stream));
+  P.active = d_active;
+}
+
 void validate_plan(const vgpu_table *t, const vgpu_plan *plan) {
   if (plan->nnodes && !plan->nodes) fail(VGPU_ERR_INVALID, "null predicate nodes");
   if (plan->nargs && !plan->args) fail(VGPU_ERR_INVALID, "null predicate args");
@@ -1810,35 +1877,7 @@ int vgpu_query_agg(vgpu_table *t, const vgpu_plan *plan, vgpu_result **out) {
     QueryRun q(t, plan);
     Planner &pl = q.planner;
     ScanParams &P = pl.P;
-    pl.build_predicate();
-    for (uint32_t i = 0; i < P.nprog; ++i) {
-      const PInstr &in = P.prog[i];
-      if (in.kind > P_OR_LEAF || !(in.cls == C_EQ32 || in.cls == C_LT32 || in.cls == C_RNG32 || in.cls == C_LUT64)) continue;
-      bool seen = false;
-      for (uint32_t f = 0; f < P.nfilter_slots; ++f) seen = seen || P.filter_slots[f] == in.slot;
-      if (!seen) P.filter_slots[P.nfilter_slots++] = in.slot;
-    }
-    for (uint32_t f = 0; f < P.nfilter_slots; ++f) {
-      P.pf_width[f] = (uint8_t)P.slots[P.filter_slots[f]].width;
-      P.pf_off[f] = P.slots[P.filter_slots[f]].off;
-    }
-    // conjunction of at most 4 vectorisable leaves: the kernel's unrolled fast path
-    P.conj = P.nprog >= 1 && P.nprog <= 4 && !(ctx->tune & 4096u);
-    for (uint32_t i = 0; i < P.nprog && P.conj; ++i) {
-      const PInstr &in = P.prog[i];
-      const bool vec = in.cls == C_EQ32 || in.cls == C_LT32 || in.cls == C_RNG32 || in.cls == C_LUT64;
-      if (!vec || in.kind != (i == 0 ? P_PUSH : P_AND_LEAF)) P.conj = 0;
-    }
-
-    // ---- segment loop bookkeeping + pruning (scan.cc:42-51) ----
-    for (uint32_t s = 0; s < t->segs.size(); ++s) {
-      const SegmentData &sd = t->segs[s];
-      if (!sd.valid) continue;
-      q.scanned_recs += sd.nrows;
-      if (!pl.process_segment(sd, pl.root)) continue;
-      q.active.push_back(s);
-      q.active_rows += sd.nrows;
-    }
+    finish_predicate_and_prune(ctx, t, q);
 
     // ---- keys ----
     P.nkeys = plan->nkeys;
@@ -2395,6 +2434,243 @@ int vgpu_query_agg(vgpu_table *t, const vgpu_plan *plan, vgpu_result **out) {
     *out = res.release();
   });
 }
+
+// ---------------------------------------------------------------------------------------------
+// select / search
+// ---------------------------------------------------------------------------------------------
+int vgpu_query_select(vgpu_table *t, const vgpu_rows_plan *rp, vgpu_rows **out) {
+  return guard([&] {
+    if (!t || !rp || !out) fail(VGPU_ERR_INVALID, "null argument");
+    *out = nullptr;
+    if (rp->ncols > 32) fail(VGPU_ERR_UNSUPPORTED, "select of more than 32 columns");
+    if (rp->ncols && !rp->cols) fail(VGPU_ERR_INVALID, "null column list");
+    for (uint32_t c = 0; c < rp->ncols; ++c)
+      if (rp->cols[c] >= t->cols.size()) fail(VGPU_ERR_INVALID, "select column out of range");
+    vgpu_ctx *ctx = t->ctx;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CUDA_CK(cudaSetDevice(ctx->device));
+    cudaStream_t stream = ctx->stream;
+    vgpu_plan plan{};
+    plan.nnodes = rp->nnodes; plan.nargs = rp->nargs; plan.nodes = rp->nodes; plan.args = rp->args;
+    validate_plan(t, &plan);
+    fetch_stats(t);
+    QueryRun q(t, &plan);
+    ScanParams &P = q.planner.P;
+    finish_predicate_and_prune(ctx, t, q);
+    Scratch scratch(stream);
+    set_work_list(t, q, scratch, stream);
+    std::unique_ptr<vgpu_rows> res(new vgpu_rows());
+    vgpu_rows_view &view = res->view;
+    view.ncols = rp->ncols;
+    view.scanned_recs = q.scanned_recs;
+    view.scanned_segments = q.active.size();
+    CUDA_CK(cudaEventRecord(ctx->ev_begin, stream));
+    uint32_t launches = 0;
+    const uint32_t A = P.nactive, cps = P.tiles_per_seg;
+    const int grid = (int)std::max<uint64_t>(1, std::min<uint64_t>((P.total_tiles + kWarps - 1) / kWarps, (uint64_t)ctx->sm_count * 4));
+    RowsParams2 R{};
+    std::vector<uint32_t> counts(P.total_tiles);
+    if (P.total_tiles) {
+      R.chunk_counts = scratch.alloc<uint32_t>(P.total_tiles);
+      rows_count_kernel<<<grid, kThreads, 0, stream>>>(P, R);
+      CUDA_CK(cudaGetLastError());
+      ++launches;
+      CUDA_CK(cudaMemcpyAsync(counts.data(), R.chunk_counts, P.total_tiles * 4, cudaMemcpyDeviceToHost, stream));
+      CUDA_CK(cudaStreamSynchronize(stream));
+    }
+    // ordinals + the reference's skip / limit rules (scan.cc:107,161), segment by segment
+    std::vector<uint64_t> chunk_ord(P.total_tiles), want_lo(A), want_n(A), out_base(A);
+    uint64_t skipped = 0, emitted = 0, passed = 0;
+    for (uint32_t si = 0; si < A; ++si) {
+      uint64_t cnt = 0;
+      for (uint32_t ci = 0; ci < cps; ++ci) { chunk_ord[(uint64_t)si * cps + ci] = cnt; cnt += counts[(uint64_t)si * cps + ci]; }
+      passed += cnt;
+      const uint64_t skip_here = std::min<uint64_t>(cnt, rp->skip > skipped ? rp->skip - skipped : 0);
+      skipped += skip_here;
+      const uint64_t avail = cnt - skip_here;
+      uint64_t n = avail;
+      if (rp->limit > 0) n = std::min<uint64_t>(avail, emitted < rp->limit ? rp->limit - emitted : 1);
+      want_lo[si] = skip_here;
+      want_n[si] = n;
+      out_base[si] = emitted;
+      emitted += n;
+    }
+    view.passed_rows = passed;
+    view.nrows = emitted;
+    if (emitted > 0xffffffffull) fail(VGPU_ERR_UNSUPPORTED, "select of more than 2^32 rows in one call: use skip / limit");
+    // cells on the device, then one pinned block on the host
+    std::vector<uint64_t> off_c(rp->ncols);
+    uint64_t bytes = 0;
+    auto out_width = [&](uint32_t c) { const ColInfo &ci = t->cols[rp->cols[c]]; return ci.bitset ? 8u : ci.width; };
+    for (uint32_t c = 0; c < rp->ncols; ++c) { off_c[c] = bytes; bytes += round_up(std::max<uint64_t>(emitted * out_width(c), 1), 64); }
+    res->pool = ctx->pool;
+    res->block = ctx->pool->acquire(std::max<uint64_t>(bytes, 64));
+    uint8_t *hb = static_cast<uint8_t *>(res->block.first);
+    if (emitted) {
+      uint64_t *d_ord = scratch.alloc<uint64_t>(P.total_tiles), *d_lo = scratch.alloc<uint64_t>(A),
+               *d_n = scratch.alloc<uint64_t>(A), *d_base = scratch.alloc<uint64_t>(A);
+      CUDA_CK(cudaMemcpyAsync(d_ord, chunk_ord.data(), P.total_tiles * 8, cudaMemcpyHostToDevice, stream));
+      CUDA_CK(cudaMemcpyAsync(d_lo, want_lo.data(), A * 8, cudaMemcpyHostToDevice, stream));
+      CUDA_CK(cudaMemcpyAsync(d_n, want_n.data(), A * 8, cudaMemcpyHostToDevice, stream));
+      CUDA_CK(cudaMemcpyAsync(d_base, out_base.data(), A * 8, cudaMemcpyHostToDevice, stream));
+      R.chunk_ord = d_ord; R.want_lo = d_lo; R.want_n = d_n; R.out_base = d_base;
+      R.out_row = scratch.alloc<uint32_t>(emitted);
+      R.out_seg = scratch.alloc<uint32_t>(emitted);
+      rows_write_kernel<<<grid, kThreads, 0, stream>>>(P, R);
+      CUDA_CK(cudaGetLastError());
+      ++launches;
+      if (rp->ncols) {
+        GatherParams G{};
+        G.segs = t->d_segs; G.out_row = R.out_row; G.out_seg = R.out_seg; G.nrows = emitted; G.ncols = rp->ncols;
+        std::vector<uint8_t *> d_out(rp->ncols);
+        for (uint32_t c = 0; c < rp->ncols; ++c) {
+          const ColInfo &ci = t->cols[rp->cols[c]];
+          d_out[c] = scratch.alloc<uint8_t>(emitted * out_width(c));
+          G.cols[c].col_off = ci.off_per_row; G.cols[c].width = ci.width; G.cols[c].bitset = ci.bitset;
+          G.cols[c].bitset_idx = ci.bitset_idx; G.cols[c].out = d_out[c];
+        }
+        rows_gather_kernel<<<grid_for(emitted, 256, ctx->sm_count), 256, 0, stream>>>(G);
+        CUDA_CK(cudaGetLastError());
+        ++launches;
+        for (uint32_t c = 0; c < rp->ncols; ++c)
+          CUDA_CK(cudaMemcpyAsync(hb + off_c[c], d_out[c], emitted * out_width(c), cudaMemcpyDeviceToHost, stream));
+      }
+    }
+    CUDA_CK(cudaEventRecord(ctx->ev_end, stream));
+    CUDA_CK(cudaStreamSynchronize(stream));
+    float ms = 0;
+    CUDA_CK(cudaEventElapsedTime(&ms, ctx->ev_begin, ctx->ev_end));
+    view.gpu_ms = ms;
+    view.launches = launches;
+    for (uint32_t c = 0; c < rp->ncols; ++c) res->cell_ptrs.push_back(hb + off_c[c]);
+    view.cells = res->cell_ptrs.empty() ? nullptr : res->cell_ptrs.data();
+    *out = res.release();
+  });
+}
+
+int vgpu_rows_get(const vgpu_rows *rows, vgpu_rows_view *view) {
+  return guard([&] {
+    if (!rows || !view) fail(VGPU_ERR_INVALID, "null argument");
+    *view = rows->view;
+  });
+}
+
+void vgpu_rows_free(vgpu_rows *rows) { delete rows; }
+
+int vgpu_query_search(vgpu_table *t, const vgpu_search_plan *sp, vgpu_search **out) {
+  return guard([&] {
+    if (!t || !sp || !out) fail(VGPU_ERR_INVALID, "null argument");
+    *out = nullptr;
+    if (sp->col >= t->ndims) fail(VGPU_ERR_INVALID, "search column is not a dimension");
+    const ColInfo &dc = t->cols[sp->col];
+    if (type_float(dc.type)) fail(VGPU_ERR_UNSUPPORTED, "search on a floating-point dimension");
+    vgpu_ctx *ctx = t->ctx;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CUDA_CK(cudaSetDevice(ctx->device));
+    cudaStream_t stream = ctx->stream;
+    vgpu_plan plan{};
+    plan.nnodes = sp->nnodes; plan.nargs = sp->nargs; plan.nodes = sp->nodes; plan.args = sp->args;
+    validate_plan(t, &plan);
+    fetch_stats(t);
+    QueryRun q(t, &plan);
+    ScanParams &P = q.planner.P;
+    finish_predicate_and_prune(ctx, t, q);
+    Scratch scratch(stream);
+    set_work_list(t, q, scratch, stream);
+    std::unique_ptr<vgpu_search> res(new vgpu_search());
+    vgpu_search_view &view = res->view;
+    view.scanned_recs = q.scanned_recs;
+    view.scanned_segments = q.active.size();
+    CUDA_CK(cudaEventRecord(ctx->ev_begin, stream));
+    uint32_t launches = 0;
+    const uint32_t A = P.nactive;
+    res->seg_offsets.assign(A + 1, 0);
+    std::vector<std::vector<std::pair<uint32_t, uint64_t>>> per_seg(A);  // (first row, code)
+    // batches of consecutive segments that share one dense first-row array over the dimension's value range
+    const uint64_t kMaxFirstWords = 1ull << 26;  // 256 MB
+    unsigned long long *d_cursor = scratch.alloc<unsigned long long>(1);
+    for (uint32_t b0 = 0; b0 < A;) {
+      uint64_t omin = ~0ull, omax = 0;
+      uint32_t b1 = b0;
+      uint64_t rows_in_batch = 0;
+      while (b1 < A) {
+        const SegmentData &sd = t->segs[q.active[b1]];
+        uint64_t nmin = omin, nmax = omax;
+        if (sd.nrows) { nmin = std::min(omin, sd.omin[sp->col]); nmax = std::max(omax, sd.omax[sp->col]); }
+        const uint64_t range = nmin <= nmax ? nmax - nmin + 1 : 1;
+        if (range == 0 || range > kMaxFirstWords)
+          fail(VGPU_ERR_UNSUPPORTED, "search: value range of the dimension too large for the dense first-row table");
+        if (b1 > b0 && range * (b1 - b0 + 1) > kMaxFirstWords) break;
+        omin = nmin; omax = nmax;
+        rows_in_batch += sd.nrows;
+        ++b1;
+      }
+      if (omin > omax) { b0 = b1; continue; }  // only empty segments
+      SearchParams S{};
+      S.seg_begin = b0; S.seg_end = b1;
+      S.col_off = dc.off_per_row; S.width = dc.width; S.sext = dc.sext;
+      S.lo = from_ordered_int(omin, dc.type);
+      S.range = omax - omin + 1;
+      const uint64_t nfirst = S.range * (b1 - b0);
+      S.first = scratch.alloc<uint32_t>(nfirst);
+      CUDA_CK(cudaMemsetAsync(S.first, 0xff, nfirst * 4, stream));
+      const uint64_t tiles = (uint64_t)(b1 - b0) * P.tiles_per_seg;
+      const int grid = (int)std::max<uint64_t>(1, std::min<uint64_t>((tiles + kWarps - 1) / kWarps, (uint64_t)ctx->sm_count * 4));
+      search_first_kernel<<<grid, kThreads, 0, stream>>>(P, S);
+      CUDA_CK(cudaGetLastError());
+      ++launches;
+      S.cap = std::min<uint64_t>(nfirst, rows_in_batch);
+      S.cursor = d_cursor;
+      CUDA_CK(cudaMemsetAsync(d_cursor, 0, 8, stream));
+      S.out_slot = scratch.alloc<uint32_t>(S.cap);
+      S.out_code = scratch.alloc<uint64_t>(S.cap);
+      S.out_first = scratch.alloc<uint32_t>(S.cap);
+      search_emit_kernel<<<grid_for(nfirst, 256, ctx->sm_count), 256, 0, stream>>>(S);
+      CUDA_CK(cudaGetLastError());
+      ++launches;
+      unsigned long long n = 0;
+      CUDA_CK(cudaMemcpyAsync(&n, d_cursor, 8, cudaMemcpyDeviceToHost, stream));
+      CUDA_CK(cudaStreamSynchronize(stream));
+      if (n > S.cap) fail(VGPU_ERR_CUDA, "search: first-row list overflow");
+      std::vector<uint32_t> h_slot(n), h_first(n);
+      std::vector<uint64_t> h_code(n);
+      if (n) {
+        CUDA_CK(cudaMemcpyAsync(h_slot.data(), S.out_slot, n * 4, cudaMemcpyDeviceToHost, stream));
+        CUDA_CK(cudaMemcpyAsync(h_first.data(), S.out_first, n * 4, cudaMemcpyDeviceToHost, stream));
+        CUDA_CK(cudaMemcpyAsync(h_code.data(), S.out_code, n * 8, cudaMemcpyDeviceToHost, stream));
+        CUDA_CK(cudaStreamSynchronize(stream));
+      }
+      for (uint64_t i = 0; i < n; ++i) per_seg[h_slot[i]].emplace_back(h_first[i], h_code[i]);
+      b0 = b1;
+    }
+    for (uint32_t si = 0; si < A; ++si) {
+      auto &v = per_seg[si];
+      std::sort(v.begin(), v.end());
+      for (auto &e : v) { res->first_row.push_back(e.first); res->codes.push_back(e.second); }
+      res->seg_offsets[si + 1] = res->codes.size();
+    }
+    CUDA_CK(cudaEventRecord(ctx->ev_end, stream));
+    CUDA_CK(cudaStreamSynchronize(stream));
+    float ms = 0;
+    CUDA_CK(cudaEventElapsedTime(&ms, ctx->ev_begin, ctx->ev_end));
+    view.gpu_ms = ms;
+    view.launches = launches;
+    view.nsegments = A;
+    view.seg_offsets = res->seg_offsets.data();
+    view.codes = res->codes.data();
+    view.first_row = res->first_row.data();
+    *out = res.release();
+  });
+}
+
+int vgpu_search_get(const vgpu_search *r, vgpu_search_view *view) {
+  return guard([&] {
+    if (!r || !view) fail(VGPU_ERR_INVALID, "null argument");
+    *view = r->view;
+  });
+}
+
+void vgpu_search_free(vgpu_search *r) { delete r; }
 
 int vgpu_result_get(const vgpu_result *res, vgpu_result_view *view) {
   return guard([&] {

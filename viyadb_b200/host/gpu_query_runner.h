@@ -17,7 +17,8 @@
 //     4. calls vgpu_query_agg — nothing is compiled per query;
 //     5. runs the post-aggregation of src/codegen/query/post_agg.cc:26-147 + sort.cc:24-73 on the
 //        host into the caller's RowOutput and fills the four QueryStats counters.
-//   Visit(SelectQuery*), Visit(SearchQuery*), Visit(ShowTablesQuery*) delegate to the stock runner.
+//   Visit(SelectQuery*), Visit(SearchQuery*) go to the GPU too (rows / distinct values picked on the device,
+//   formatting and the sequential search replay here); Visit(ShowTablesQuery*) delegates to the stock runner.
 //
 // GpuTableBinding mirrors one db::Table into HBM: column base pointers come from SegmentAccess
 // (segment_access.h); segments are re-uploaded when their size() changed (ingest appends rows) or
@@ -47,6 +48,7 @@
 #include <ctime>
 #include <functional>
 #include <map>
+#include <unordered_set>
 #include <memory>
 #include <mutex>
 #include <stdexcept>
@@ -159,6 +161,7 @@ public:
     return col->type() == db::Column::Type::DIMENSION ? col->index() : ndims_ + col->index();
   }
   bool has_hidden_count() const { return hidden_; }
+  size_t hidden_count_index() const { return ndims_ + nmetrics_; }  // last schema column (include/vgpu.h)
 
   // Force the next Sync() to re-upload a segment whose metric cells were updated in place.
   void Invalidate(size_t seg_idx) {
@@ -364,17 +367,194 @@ public:
       : database_(database), output_(output), ctx_(ctx), bindings_(bindings), stock_(database, output),
         stats_(database.statsd()) {}
 
-  void Visit(query::SelectQuery *query) override { delegated_ = true; stock_.Visit(query); }
-  void Visit(query::SearchQuery *query) override { delegated_ = true; stock_.Visit(query); }
   void Visit(query::ShowTablesQuery *query) override { delegated_ = true; stock_.Visit(query); }
+
+  // Replaces QueryRunner::Visit(SelectQuery*) (src/query/runner.cc:29-43): the device picks the rows the
+  // generated viya_query_select would send (codegen/query/scan.cc:75-166, skip / limit rules included) and
+  // returns their raw cells; formatting stays here, with the reference's own util::Format.
+  void Visit(query::SelectQuery *query) override {
+    stats_.OnBegin("select", query->table().name());
+    auto &table = query->table();
+    GpuTableBinding &binding = Bind(table);
+    binding.Sync();
+    stats_.OnCompile();
+    cg::FilterArgsPacker filter_args(table);
+    query->filter()->Accept(filter_args);
+    std::vector<db::AnyNum> fargs = filter_args.args();
+    std::vector<uint64_t> raw_args(fargs.size());
+    for (size_t i = 0; i < fargs.size(); ++i) std::memcpy(&raw_args[i], &fargs[i], 8);
+    PredicateProgramBuilder pred(table, binding);
+    query->filter()->Accept(pred);
+
+    auto &dim_cols = query->dimension_cols();
+    auto &metric_cols = query->metric_cols();
+    std::vector<uint32_t> cols;
+    for (auto &dc : dim_cols) cols.push_back(static_cast<uint32_t>(binding.schema_index(dc.dim())));
+    for (auto &mc : metric_cols) cols.push_back(static_cast<uint32_t>(binding.schema_index(mc.metric())));
+    // AVG cells are divided by the first selected COUNT metric, else by the hidden count (scan.cc:133-154)
+    int count_pos = -1;
+    bool has_avg = false;
+    for (size_t m = 0; m < metric_cols.size(); ++m) {
+      auto agg = metric_cols[m].metric()->agg_type();
+      has_avg |= agg == db::Metric::AggregationType::AVG;
+      if (count_pos < 0 && agg == db::Metric::AggregationType::COUNT) count_pos = (int)(dim_cols.size() + m);
+    }
+    bool hidden_count = false;
+    if (has_avg && count_pos < 0) {
+      if (!binding.has_hidden_count()) throw std::runtime_error("AVG metric selected but the table has no count column");
+      count_pos = (int)cols.size();
+      cols.push_back(static_cast<uint32_t>(binding.hidden_count_index()));
+      hidden_count = true;
+    }
+    vgpu_rows_plan plan{};
+    plan.nnodes = static_cast<uint32_t>(pred.nodes().size());
+    plan.nodes = pred.nodes().data();
+    plan.nargs = static_cast<uint32_t>(raw_args.size());
+    plan.args = raw_args.data();
+    plan.ncols = static_cast<uint32_t>(cols.size());
+    plan.cols = cols.data();
+    plan.skip = query->skip();
+    plan.limit = query->limit();
+    vgpu_rows *res = nullptr;
+    check(vgpu_query_select(binding.handle(), &plan, &res), "vgpu_query_select");
+    std::unique_ptr<vgpu_rows, void (*)(vgpu_rows *)> guard(res, vgpu_rows_free);
+    vgpu_rows_view view{};
+    check(vgpu_rows_get(res, &view), "vgpu_rows_get");
+    stats_.scanned_recs += view.scanned_recs;
+    stats_.scanned_segments += view.scanned_segments;
+
+    using Row = std::vector<std::string>;
+    Row row(dim_cols.size() + metric_cols.size());
+    util::Format fmt;
+    output_.Start();
+    if (query->header()) {
+      for (auto &dc : dim_cols) row[dc.index()] = dc.dim()->name();
+      for (auto &mc : metric_cols) row[mc.index()] = mc.metric()->name();
+      output_.Send(row);
+    }
+    for (uint64_t r = 0; r < view.nrows; ++r) {
+      for (size_t k = 0; k < dim_cols.size(); ++k) {
+        auto dim = dim_cols[k].dim();
+        uint64_t bits = Load(view.cells[k], (uint32_t)dim->num_type().size(), r);
+        auto &cell = row[dim_cols[k].index()];
+        if (dim->dim_type() == db::Dimension::DimType::STRING) {
+          auto dict = static_cast<const db::StrDimension *>(dim)->dict();
+          dict->lock().lock_shared();
+          cell = dict->c2v()[bits];
+          dict->lock().unlock_shared();
+        } else if (dim->dim_type() == db::Dimension::DimType::TIME && !dim_cols[k].format().empty()) {
+          cell = fmt.date(dim_cols[k].format().c_str(), (uint32_t)bits);
+        } else if (dim->dim_type() == db::Dimension::DimType::BOOLEAN) {
+          cell = bits ? "true" : "false";
+        } else {
+          cell = FormatNum(fmt, vgpu_type_of(dim), bits);
+        }
+      }
+      for (size_t m = 0; m < metric_cols.size(); ++m) {
+        auto metric = metric_cols[m].metric();
+        auto &cell = row[metric_cols[m].index()];
+        const void *base = view.cells[dim_cols.size() + m];
+        if (metric->agg_type() == db::Metric::AggregationType::BITSET) {
+          cell = fmt.num((uint64_t)Load(base, 8, r));
+          continue;
+        }
+        uint32_t type = vgpu_type_of(metric);
+        uint64_t bits = Load(base, (uint32_t)metric->num_type().size(), r);
+        if (metric->agg_type() == db::Metric::AggregationType::AVG) {
+          double cnt = hidden_count
+                           ? (double)Load(view.cells[count_pos], 8, r)
+                           : AsDouble(vgpu_type_of(metric_cols[count_pos - dim_cols.size()].metric()),
+                                      Load(view.cells[count_pos],
+                                           (uint32_t)metric_cols[count_pos - dim_cols.size()].metric()->num_type().size(), r));
+          cell = fmt.num(AsDouble(type, bits) / cnt);
+        } else {
+          cell = FormatNum(fmt, type, bits);
+        }
+      }
+      output_.Send(row);
+      ++stats_.output_recs;
+    }
+    output_.Flush();
+    stats_.OnEnd();
+  }
+
+  // Replaces QueryRunner::Visit(SearchQuery*) (src/query/runner.cc:66-80): the device finds, per processed
+  // segment, the distinct values of the dimension among the passing rows with their first rows; the sequential
+  // part of scan.cc:273-295 (codes.insert, substring match, `limit` breaking the tuple loop only) is replayed
+  // here on those short lists, then post_agg.cc:149-166 (SendAsCol).
+  void Visit(query::SearchQuery *query) override {
+    auto dim = query->dimension();
+    const uint32_t dim_type = vgpu_type_of(dim);
+    if (dim_type == VGPU_F32 || dim_type == VGPU_F64) {  // the dense first-row table is keyed by integer values
+      delegated_ = true;
+      stock_.Visit(query);
+      return;
+    }
+    stats_.OnBegin("search", query->table().name());
+    auto &table = query->table();
+    GpuTableBinding &binding = Bind(table);
+    binding.Sync();
+    stats_.OnCompile();
+    cg::FilterArgsPacker filter_args(table);
+    query->filter()->Accept(filter_args);
+    std::vector<db::AnyNum> fargs = filter_args.args();
+    std::vector<uint64_t> raw_args(fargs.size());
+    for (size_t i = 0; i < fargs.size(); ++i) std::memcpy(&raw_args[i], &fargs[i], 8);
+    PredicateProgramBuilder pred(table, binding);
+    query->filter()->Accept(pred);
+    vgpu_search_plan plan{};
+    plan.nnodes = static_cast<uint32_t>(pred.nodes().size());
+    plan.nodes = pred.nodes().data();
+    plan.nargs = static_cast<uint32_t>(raw_args.size());
+    plan.args = raw_args.data();
+    plan.col = static_cast<uint32_t>(binding.schema_index(dim));
+    vgpu_search *res = nullptr;
+    check(vgpu_query_search(binding.handle(), &plan, &res), "vgpu_query_search");
+    std::unique_ptr<vgpu_search, void (*)(vgpu_search *)> guard(res, vgpu_search_free);
+    vgpu_search_view view{};
+    check(vgpu_search_get(res, &view), "vgpu_search_get");
+    stats_.scanned_recs += view.scanned_recs;
+    stats_.scanned_segments += view.scanned_segments;
+
+    util::Format fmt;
+    std::unordered_set<uint64_t> codes;
+    std::vector<std::string> values;
+    std::string check_value;
+    const std::string &term = query->term();
+    const size_t limit = query->limit();
+    for (uint32_t si = 0; si < view.nsegments; ++si) {
+      for (uint64_t i = view.seg_offsets[si]; i < view.seg_offsets[si + 1]; ++i) {
+        const uint64_t code = view.codes[i];
+        if (!codes.insert(code).second) continue;
+        if (dim->dim_type() == db::Dimension::DimType::STRING) {
+          auto dict = static_cast<const db::StrDimension *>(dim)->dict();
+          dict->lock().lock_shared();
+          check_value = dict->c2v()[code];
+          dict->lock().unlock_shared();
+        } else if (dim->dim_type() == db::Dimension::DimType::BOOLEAN) {
+          check_value = code ? "true" : "false";
+        } else {
+          check_value = FormatNum(fmt, vgpu_type_of(dim), code);
+        }
+        if (check_value.find(term) != std::string::npos) {
+          values.push_back(check_value);
+          if (limit > 0 && values.size() >= limit) break;  // the tuple loop of this segment only (scan.cc:291)
+        }
+      }
+    }
+    stats_.aggregated_recs = codes.size();
+    output_.Start();
+    if (query->header()) output_.Send(std::vector<std::string>{dim->name()});
+    output_.SendAsCol(values);
+    stats_.output_recs = values.size();
+    output_.Flush();
+    stats_.OnEnd();
+  }
 
   void Visit(query::AggregateQuery *query) override {
     stats_.OnBegin("aggregate", query->table().name());
     auto &table = query->table();
-    auto it = bindings_.find(table.name());
-    if (it == bindings_.end())
-      it = bindings_.emplace(table.name(), std::make_unique<GpuTableBinding>(ctx_, table)).first;
-    GpuTableBinding &binding = *it->second;
+    GpuTableBinding &binding = Bind(table);
     binding.Sync();
     stats_.OnCompile();  // nothing is compiled: the plan is data
 
@@ -451,6 +631,13 @@ public:
   const query::QueryStats &stats() const { return delegated_ ? stock_.stats() : stats_; }
 
 private:
+  GpuTableBinding &Bind(db::Table &table) {
+    auto it = bindings_.find(table.name());
+    if (it == bindings_.end())
+      it = bindings_.emplace(table.name(), std::make_unique<GpuTableBinding>(ctx_, table)).first;
+    return *it->second;
+  }
+
   static long RollupNow() {
     // VIYA_TEST_ROLLUP_TS pins "now" exactly like codegen/db/rollup.cc:47-49
     const char *test_ts = getenv("VIYA_TEST_ROLLUP_TS");

@@ -220,6 +220,74 @@ class SortColumn:
         self.col, self.index, self.ascending = col, index, ascending
 
 
+class SelectQuery:
+    """query::SelectQuery (src/query/query.cc:48-85)."""
+
+    def __init__(self, conf, table):
+        self.table = table
+        self.header = bool(conf.get("header", False))
+        self.filter = FilterFactory.create(conf.get("filter"))
+        self.skip = int(conf.get("skip", 0))
+        self.limit = int(conf.get("limit", 0))
+        self.dimension_cols, self.metric_cols = [], []
+        idx = 0
+        if "select" in conf:
+            for sel in conf["select"]:
+                name = sel["column"]
+                cols = table.columns() if name == "*" else [table.column(name)]
+                for col in cols:
+                    if col.is_dimension:
+                        self.dimension_cols.append(DimOutputColumn(sel, col, idx))
+                    else:
+                        self.metric_cols.append(MetricOutputColumn(sel, col, idx))
+                    idx += 1
+        else:
+            for name in conf.get("dimensions", []):
+                self.dimension_cols.append(DimOutputColumn(None, table.dimension(name), idx))
+                idx += 1
+            for name in conf.get("metrics", []):
+                self.metric_cols.append(MetricOutputColumn(None, table.metric(name), idx))
+                idx += 1
+        self.ncols = idx
+
+    def accept(self, visitor):
+        visitor.visit_select(self)
+
+
+class SearchQuery:
+    """query::SearchQuery (src/query/query.cc:139-142)."""
+
+    def __init__(self, conf, table):
+        self.table = table
+        self.header = bool(conf.get("header", False))
+        self.filter = FilterFactory.create(conf.get("filter"))
+        self.dimension = table.dimension(conf["dimension"])
+        self.term = conf["term"]
+        self.limit = int(conf.get("limit", 0))
+
+    def accept(self, visitor):
+        visitor.visit_search(self)
+
+
+def replay_search(segment_lists, fmt_value, term, limit):
+    """The sequential part of the reference's search (scan.cc:273-295) over the per-segment lists of
+    (first row, code) the device produced: a code is marked seen when its first occurrence in a segment is
+    reached; `limit` breaks the tuple loop only, so the rest of THAT segment stays unseen while the next
+    segments are still visited. Returns (values, number of distinct codes seen)."""
+    seen, values = set(), []
+    for codes in segment_lists:           # scan order; codes ascending by first row inside a segment
+        for code in codes:
+            if code in seen:
+                continue
+            seen.add(code)
+            v = fmt_value(code)
+            if term in v:
+                values.append(v)
+                if limit > 0 and len(values) >= limit:
+                    break
+    return values, len(seen)
+
+
 class AggregateQuery:
     def __init__(self, conf, table):
         self.table = table
@@ -284,10 +352,12 @@ class QueryFactory:
         qtype = conf["type"]
         if qtype == "aggregate":
             return AggregateQuery(conf, database.get_table(conf["table"]))
-        if qtype in ("search", "select", "show"):
-            raise NotImplementedError(
-                f"'{qtype}' queries stay on the reference's stock QueryRunner (SURVEY.md §8f); "
-                "only the aggregate hot path is GPU-resident")
+        if qtype == "select":
+            return SelectQuery(conf, database.get_table(conf["table"]))
+        if qtype == "search":
+            return SearchQuery(conf, database.get_table(conf["table"]))
+        if qtype == "show":
+            raise NotImplementedError("'show' queries list tables: no device work, they stay on the stock QueryRunner")
         raise ValueError("unsupported query type: " + qtype)
 
 
@@ -489,6 +559,143 @@ class GpuQueryRunner:
         s.gpu_ms, s.kernel_scan_ms, s.launches = view.gpu_ms, view.scan_ms, view.launches
         s.table_mode, s.table_cells = view.table_mode, view.table_cells
         return {"ngroups": n, "keys": keys, "accs": accs, "hidden_count": hidden, "_owner": owner}
+
+    def _predicate(self, query):
+        packer = FilterArgsPacker(query.table).visit(query.filter)
+        nodes = (N.PredNode * max(1, len(packer.nodes)))()
+        for i, (kind, op, col, arg, n) in enumerate(packer.nodes):
+            nodes[i] = N.PredNode(kind, op, col, arg, n, 0)
+        args = (C.c_uint64 * max(1, len(packer.args)))(*packer.args)
+        return packer, nodes, args
+
+    # ---- select (runner.cc:29-43, codegen/query/scan.cc:75-166): device picks the rows, host formats ----
+    def visit_select(self, query):
+        t_begin = _time.perf_counter()
+        lib = N.load()
+        t = query.table
+        packer, nodes, args = self._predicate(query)
+        cols = [dc.dim for dc in query.dimension_cols] + [mc.metric for mc in query.metric_cols]
+        sel = [t.schema_index(c) for c in cols]
+        # AVG cells are divided by the first selected COUNT metric, else by the table's hidden count (scan.cc:133-154)
+        count_pos = next((i for i, c in enumerate(cols) if not c.is_dimension and c.agg == N.AGG_COUNT), None)
+        if count_pos is None and any((not c.is_dimension) and c.agg == N.AGG_AVG for c in cols):
+            hidden = t.hidden_count_index()
+            if hidden is None:
+                raise N.VgpuError(N.ERR_INVALID, "AVG metric selected but the table has neither COUNT nor hidden count")
+            count_pos = len(sel)
+            sel.append(hidden)
+        plan = N.RowsPlan()
+        plan.nnodes, plan.nargs, plan.nodes, plan.args = len(packer.nodes), len(packer.args), nodes, args
+        carr = (C.c_uint32 * max(1, len(sel)))(*sel)
+        plan.ncols, plan.cols, plan.skip, plan.limit = len(sel), carr, query.skip, query.limit
+        res = C.c_void_p()
+        N.check(lib.vgpu_query_select(t.handle, C.byref(plan), C.byref(res)))
+        try:
+            view = N.RowsView()
+            N.check(lib.vgpu_rows_get(res, C.byref(view)))
+            n = view.nrows
+            arrays = []
+            for i, si in enumerate(sel):
+                col = cols[i] if i < len(cols) else None
+                if col is not None and not col.is_dimension and col.agg == N.AGG_BITSET:
+                    dt = np.dtype("<u8")
+                elif col is None:
+                    dt = np.dtype("<u8")            # hidden count
+                else:
+                    dt = np.dtype(N.NP_DTYPES[col.type])
+                if n:
+                    buf = (C.c_char * (n * dt.itemsize)).from_address(view.cells[i])
+                    arrays.append(np.frombuffer(buf, dtype=dt, count=n).copy())
+                else:
+                    arrays.append(np.zeros(0, dt))
+            s = self.stats
+            s.scanned_recs, s.scanned_segments, s.passed_rows = view.scanned_recs, view.scanned_segments, view.passed_rows
+            s.gpu_ms, s.launches = view.gpu_ms, view.launches
+        finally:
+            lib.vgpu_rows_free(res)
+        out = self.output
+        out.start()
+        if query.header:
+            row = [None] * query.ncols
+            for dc in query.dimension_cols:
+                row[dc.index] = dc.dim.name
+            for mc in query.metric_cols:
+                row[mc.index] = mc.metric.name
+            out.send(row)
+        ndim = len(query.dimension_cols)
+        for r in range(n):
+            row = [None] * query.ncols
+            for i, dc in enumerate(query.dimension_cols):
+                v = arrays[i][r]
+                d = dc.dim
+                if d.kind == N.DIM_STRING:
+                    row[dc.index] = d.dict.decode(int(v))
+                elif d.kind == N.DIM_TIME and dc.format:
+                    row[dc.index] = fmt_date(dc.format, int(v))
+                elif d.kind == N.DIM_BOOLEAN:
+                    row[dc.index] = "true" if v else "false"
+                else:
+                    row[dc.index] = fmt_num(v, d.type)
+            for i, mc in enumerate(query.metric_cols):
+                v = arrays[ndim + i][r]
+                m = mc.metric
+                if m.agg == N.AGG_AVG:
+                    with np.errstate(divide="ignore", invalid="ignore"):
+                        row[mc.index] = "%.15g" % (np.float64(v) / np.float64(arrays[count_pos][r]))
+                elif m.agg == N.AGG_BITSET:
+                    row[mc.index] = str(int(v))
+                else:
+                    row[mc.index] = fmt_num(v, m.type)
+            out.send(row)
+        self.stats.output_recs = n
+        out.flush()
+        self.stats.whole_time = _time.perf_counter() - t_begin
+
+    # ---- search (runner.cc:66-80, scan.cc:249-299, post_agg.cc:149-166) ----
+    def visit_search(self, query):
+        t_begin = _time.perf_counter()
+        lib = N.load()
+        t = query.table
+        d = query.dimension
+        packer, nodes, args = self._predicate(query)
+        plan = N.SearchPlan()
+        plan.nnodes, plan.nargs, plan.nodes, plan.args = len(packer.nodes), len(packer.args), nodes, args
+        plan.col = t.schema_index(d)
+        res = C.c_void_p()
+        N.check(lib.vgpu_query_search(t.handle, C.byref(plan), C.byref(res)))
+        try:
+            view = N.SearchView()
+            N.check(lib.vgpu_search_get(res, C.byref(view)))
+            lists = []
+            for si in range(view.nsegments):
+                lo, hi = view.seg_offsets[si], view.seg_offsets[si + 1]
+                lists.append([view.codes[i] for i in range(lo, hi)])
+            s = self.stats
+            s.scanned_recs, s.scanned_segments = view.scanned_recs, view.scanned_segments
+            s.gpu_ms, s.launches = view.gpu_ms, view.launches
+        finally:
+            lib.vgpu_search_free(res)
+        dt = np.dtype(N.NP_DTYPES[d.type])
+
+        def fmt_value(code):
+            if d.kind == N.DIM_STRING:
+                return d.dict.decode(int(code))
+            if d.kind == N.DIM_BOOLEAN:
+                return "true" if code else "false"
+            v = int(code)
+            if dt.kind == "i" and v >= 1 << 63:
+                v -= 1 << 64                      # codes arrive sign-extended to 64 bits
+            return fmt_num(v, d.type)
+        values, ncodes = replay_search(lists, fmt_value, query.term, query.limit)
+        out = self.output
+        out.start()
+        if query.header:
+            out.send([d.name])
+        out.send_as_col(values) if hasattr(out, "send_as_col") else out.send(values)
+        self.stats.aggregated_recs = ncodes
+        self.stats.output_recs = len(values)
+        out.flush()
+        self.stats.whole_time = _time.perf_counter() - t_begin
 
     def visit_aggregate(self, query):
         t_begin = _time.perf_counter()
