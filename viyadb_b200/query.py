@@ -629,7 +629,7 @@ class GpuQueryRunner:
                 v = arrays[i][r]
                 d = dc.dim
                 if d.kind == N.DIM_STRING:
-                    row[dc.index] = d.dict.decode(int(v))
+                    row[dc.index] = d.dict.c2v[int(v)]
                 elif d.kind == N.DIM_TIME and dc.format:
                     row[dc.index] = fmt_date(dc.format, int(v))
                 elif d.kind == N.DIM_BOOLEAN:
@@ -679,7 +679,7 @@ class GpuQueryRunner:
 
         def fmt_value(code):
             if d.kind == N.DIM_STRING:
-                return d.dict.decode(int(code))
+                return d.dict.c2v[int(code)]
             if d.kind == N.DIM_BOOLEAN:
                 return "true" if code else "false"
             v = int(code)
