@@ -55,7 +55,7 @@
 extern "C" {
 #endif
 
-#define VGPU_ABI_VERSION 1
+#define VGPU_ABI_VERSION 2
 
 typedef enum vgpu_status {
   VGPU_OK = 0,
@@ -101,9 +101,13 @@ typedef enum vgpu_time_unit {
 
 typedef struct vgpu_column {
   uint32_t kind; /* vgpu_col_kind */
-  uint32_t type; /* vgpu_type; for BITSET the id width (U32 or U64; U8/U16 ids are widened to U32) */
+  uint32_t type; /* vgpu_type; for BITSET the width the ids travel in: U32 (the reference's ubyte / ushort / uint
+                    bitsets, util::Bitset<4> = Roaring) or U64 (ulong bitsets, util::Bitset<8> = Roaring64Map,
+                    src/util/bitset.h:27-31) */
   uint32_t agg;  /* vgpu_agg for metrics, VGPU_AGG_NONE for dimensions */
-  uint32_t reserved;
+  uint32_t lit_type; /* 0, or 1 + the vgpu_type of a filter literal on this column when it differs from `type`: a
+                    BITSET metric of the reference's `ubyte` / `ushort` type travels as U32, but the AnyNum image of
+                    its filter literal only defines 1 / 2 bytes (src/db/column.h:98-121) */
 } vgpu_column;
 
 /* Columns are listed as the reference indexes them: all dimensions in Table::dimensions() order,
@@ -208,11 +212,22 @@ typedef struct vgpu_result_view {
   uint64_t table_cells;         /* dense cells or hash capacity */
 } vgpu_result_view;
 
-/* ---- lifecycle ---- */
+/* ---- lifecycle ----
+ * Threading (the reference runs `query_threads` queries at once next to one ingest thread, src/db/database.cc:28-33):
+ * every vgpu_query_* call is re-entrant per context — each runs on streams, events and scratch of its own — and
+ * holds its table's lock shared; vgpu_segment_put / _generate / _invalidate hold it exclusively, so a writer waits
+ * for the queries running on that table (and they for it) while other tables are not affected. With a communicator
+ * (vgpu_comm_init) queries of one context are serialised: every rank must issue the same sequence of collectives. */
 int vgpu_abi_version(void);
 int vgpu_init(int device, vgpu_ctx **out);
-/* Use an existing CUDA stream (cudaStream_t as void*) instead of the context's own. */
+/* Order queries after what `cuda_stream` (cudaStream_t as void*) holds when they start, and make it wait for them
+ * when they end: the caller's own events on that stream then bracket a query. NULL detaches. */
 int vgpu_set_stream(vgpu_ctx *ctx, void *cuda_stream);
+/* Test hooks: force the rarely taken branches at test sizes. name = "pairs_cap" (first capacity of the count-distinct
+ * pair regions: overflow + regrow), "hash_cap" (first capacity of hashed group tables: x4 regrow), "bucket_pairs"
+ * (pairs per L2-sized partition of the general dedupe path), "small_pairs" (largest capacity one global set takes),
+ * "set_slots" (slots of the shared-memory sets), "tune" (VGPU_TUNE bits). 0 restores the default. */
+int vgpu_set_test_hook(vgpu_ctx *ctx, const char *name, uint64_t value);
 void vgpu_shutdown(vgpu_ctx *ctx);
 const char *vgpu_last_error(void);
 

@@ -9,7 +9,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libvgpu.so")
 
-VGPU_ABI_VERSION = 1
+VGPU_ABI_VERSION = 2
 
 # vgpu_status
 OK, ERR_INVALID, ERR_UNSUPPORTED, ERR_CUDA, ERR_NOMEM, ERR_NCCL, ERR_STATE = 0, -1, -2, -3, -4, -5, -6
@@ -34,7 +34,7 @@ MAX_ROLLUP_RULES = 8
 
 
 class Column(C.Structure):
-    _fields_ = [("kind", C.c_uint32), ("type", C.c_uint32), ("agg", C.c_uint32), ("reserved", C.c_uint32)]
+    _fields_ = [("kind", C.c_uint32), ("type", C.c_uint32), ("agg", C.c_uint32), ("lit_type", C.c_uint32)]
 
 
 class Schema(C.Structure):
@@ -106,6 +106,7 @@ SYMBOLS = [
     ("vgpu_abi_version", C.c_int, []),
     ("vgpu_init", C.c_int, [C.c_int, C.POINTER(C.c_void_p)]),
     ("vgpu_set_stream", C.c_int, [C.c_void_p, C.c_void_p]),
+    ("vgpu_set_test_hook", C.c_int, [C.c_void_p, C.c_char_p, C.c_uint64]),
     ("vgpu_shutdown", None, [C.c_void_p]),
     ("vgpu_last_error", C.c_char_p, []),
     ("vgpu_table_create", C.c_int, [C.c_void_p, C.POINTER(Schema), C.POINTER(C.c_void_p)]),

@@ -186,6 +186,28 @@ __device__ __noinline__ uint64_t rollup_value(uint64_t v, const KeySpec &k) {
   return (uint64_t)trunc_seconds<uint32_t>((uint32_t)v, unit);
 }
 
+// rank of a rolled-up time value among all attainable ones (TimeDict, scan_params.h): no calendar arithmetic
+__device__ __forceinline__ uint64_t tdict_rank(const TimeDict &T, uint64_t v) {
+  const uint64_t x = T.micro ? v / 1000000ull : v;
+  uint32_t p = 0;
+  for (uint32_t j = 1; j < T.npieces; ++j) p += x >= T.start[j] ? 1u : 0u;   // uniform loop, constant-bank operands
+  const uint32_t d = (uint32_t)(x - T.origin[p]);   // a piece spans less than 2^32 seconds
+  uint32_t q;
+  switch (T.step[p]) {   // divisions by compile-time constants
+    case 0: q = 0; break;
+    case 60: q = d / 60u; break;
+    case 3600: q = d / 3600u; break;
+    case 86400: q = d / 86400u; break;
+    default: q = d; break;   // 1: second granularity
+  }
+  return (uint64_t)(T.base[p] + q);
+}
+
+// floating-point keys: -0.0 groups with +0.0 (KeyEqual uses ==, std::hash<float> maps both to 0; store.cc:46-85)
+__device__ __forceinline__ uint64_t fzero_fix(uint64_t val, uint32_t width) {
+  return (width == 4 ? (uint32_t)(val << 1) == 0u : (val << 1) == 0ull) ? 0ull : val;
+}
+
 // ---------------------------------------------------------------------------------------------
 // accumulator update == Metrics::Update (store.cc:131-161), on native atomics
 // ---------------------------------------------------------------------------------------------
@@ -356,46 +378,146 @@ __device__ __noinline__ uint64_t wide_cell(const ScanParams &P, const uint64_t *
 }
 
 // ---------------------------------------------------------------------------------------------
-// count-distinct: dedupe (cell,id) pairs in an open-addressing set, count new ones per cell
+// count-distinct, after the scan (util::Bitset |= and cardinality(), src/util/bitset.h:26-67, as a set union of
+// (group, id) pairs). The scan leaves the pairs in ragged regions: one per scan CTA (and per owner rank when
+// several GPUs take part). Two ways to deduplicate them, both exact:
+//
+//   fast path       pairs_bucket_kernel scatters the pairs into NB hash buckets small enough for a shared-memory
+//                   set, pairs_dedupe_smem_kernel takes one bucket per CTA iteration: open-addressing set in
+//                   shared memory, a pair seen for the first time bumps distinct[cell] with one RED.
+//                   Measured on B200 (tools/dedupe_probe.cu, 2.5e7 pairs = C2): RED alone 0.15 ms; a global
+//                   atomicCAS set 1.24 ms (DRAM-resident) / 0.71 + 0.20 ms (16 L2-sized partitions, round 1);
+//                   this path 0.30 + 0.25 ms. Plain-store sets with CTA barriers instead of shared-memory
+//                   atomics measured 2.5x SLOWER (0.62 ms) and were dropped.
+//   general path    pairs_partition_kernel (L2-sized hash buckets) + pairs_dedupe_kernel<Pair> (global set):
+//                   any size or skew, and 16-byte pairs (64-bit ids = Roaring64Map, bitset.h:27-31; packed 64-bit
+//                   group keys when hashed group tables are merged across GPUs).
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
-distinct_insert_kernel(const uint64_t *__restrict__ pairs, uint64_t npairs, uint64_t *set,
-                       uint64_t set_mask, uint32_t *distinct, unsigned long long *sentinel_seen) {
-  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < npairs;
-       i += (uint64_t)gridDim.x * blockDim.x) {
-    uint64_t key = pairs[i];
-    if (key == kEmptyKey) {  // (cell 0xffffffff, id 0xffffffff): cannot live in the set
-      if (atomicExch(sentinel_seen, 1ull) == 0ull) atomicAdd(distinct + (key >> 32), 1u);
-      continue;
-    }
-    uint64_t slot = mix64(key) & set_mask;
-    while (true) {
-      uint64_t k = *reinterpret_cast<volatile uint64_t *>(set + slot);
-      if (k == key) break;
-      if (k == kEmptyKey) {
-        unsigned long long old = atomicCAS(reinterpret_cast<unsigned long long *>(set + slot),
-                                           (unsigned long long)kEmptyKey, (unsigned long long)key);
-        if (old == kEmptyKey) {
-          atomicAdd(distinct + (key >> 32), 1u);
-          break;
+struct Pair128 {
+  uint64_t hi;  // cell, or packed group key
+  uint64_t lo;  // id
+};
+__device__ __forceinline__ Pair128 cas128(Pair128 *p, Pair128 cmp, Pair128 val) {
+  Pair128 r;
+  asm volatile(
+      "{\n .reg .b128 c, v, d;\n mov.b128 c, {%2, %3};\n mov.b128 v, {%4, %5};\n"
+      " atom.global.cas.b128 d, [%6], c, v;\n mov.b128 {%0, %1}, d;\n}"
+      : "=l"(r.hi), "=l"(r.lo)
+      : "l"(cmp.hi), "l"(cmp.lo), "l"(val.hi), "l"(val.lo), "l"(p)
+      : "memory");
+  return r;
+}
+// owner rank of a pair (scan kernel, several GPUs): every copy of a pair must meet on one rank
+__device__ __forceinline__ uint32_t pair_owner(uint64_t hi, uint64_t id, uint32_t nranks) {
+  return (uint32_t)((mix64(hi * 0x9E3779B97F4A7C15ull + id) >> 33) % nranks);
+}
+
+constexpr int kBucketThreads = 1024;
+constexpr int kBucketPer = 8;          // pairs per thread and tile
+constexpr uint32_t kMaxSmemBuckets = 16384;
+struct PairsBucketParams {
+  const uint64_t *pairs;       // regions, region r at r * region_cap
+  const uint32_t *counts;      // [nregions]
+  uint32_t nregions;
+  uint32_t region_cap;
+  uint32_t nbuckets;           // power of two <= kMaxSmemBuckets
+  uint32_t bucket_cap;
+  uint32_t *cursors;           // [nbuckets], zeroed; ends up holding the bucket sizes (may exceed bucket_cap)
+  uint64_t *out;               // bucket b at b * bucket_cap
+  unsigned long long *flags;   // set on bucket overflow
+};
+__device__ __forceinline__ uint32_t pair_bucket(uint64_t key, uint32_t nbuckets) {
+  return (uint32_t)(mix64(key) >> 24) & (nbuckets - 1);
+}
+
+// Tile of 8192 pairs per CTA iteration: histogram + rank of every pair in shared memory, one global atomic per
+// non-empty bucket and tile, then the scatter (the L2 write-combines the 8-byte stores of a bucket's tail).
+__global__ void __launch_bounds__(kBucketThreads) pairs_bucket_kernel(const __grid_constant__ PairsBucketParams A) {
+  extern __shared__ uint32_t s_hist[];  // [nbuckets] counts, then [nbuckets] bases
+  uint32_t *s_base = s_hist + A.nbuckets;
+  for (uint32_t r = blockIdx.x; r < A.nregions; r += gridDim.x) {
+    const uint64_t *src = A.pairs + (uint64_t)r * A.region_cap;
+    const uint32_t n = min(A.counts[r], A.region_cap);
+    for (uint32_t t0 = 0; t0 < n; t0 += kBucketThreads * kBucketPer) {
+      for (uint32_t i = threadIdx.x; i < A.nbuckets; i += kBucketThreads) s_hist[i] = 0;
+      __syncthreads();
+      uint64_t key[kBucketPer];
+      uint32_t bkt[kBucketPer], pos[kBucketPer];
+#pragma unroll
+      for (int j = 0; j < kBucketPer; ++j) {
+        const uint32_t i = t0 + j * kBucketThreads + threadIdx.x;
+        bkt[j] = 0xffffffffu;
+        if (i < n) {
+          key[j] = src[i];
+          bkt[j] = pair_bucket(key[j], A.nbuckets);
+          pos[j] = atomicAdd(&s_hist[bkt[j]], 1u);
         }
-        if (old == key) break;
       }
-      slot = (slot + 1) & set_mask;
+      __syncthreads();
+      for (uint32_t i = threadIdx.x; i < A.nbuckets; i += kBucketThreads)
+        if (s_hist[i]) s_base[i] = atomicAdd(&A.cursors[i], s_hist[i]);
+      __syncthreads();
+      bool over = false;
+#pragma unroll
+      for (int j = 0; j < kBucketPer; ++j) {
+        if (bkt[j] == 0xffffffffu) continue;
+        const uint32_t p = s_base[bkt[j]] + pos[j];
+        if (p < A.bucket_cap) A.out[(uint64_t)bkt[j] * A.bucket_cap + p] = key[j];
+        else over = true;
+      }
+      if (over) atomicOr(A.flags, 1ull);
+      __syncthreads();
     }
   }
 }
 
-// ---------------------------------------------------------------------------------------------
-// count-distinct, after the scan: the (cell,id) pairs sit in ragged per-CTA regions.
-//   pairs_partition_kernel  scatters them into B hash buckets (B chosen so that a bucket's dedupe
-//                           table fits L2), CTA-level histogram, one global atomic per bucket per tile
-//   pairs_dedupe_kernel     inserts one bucket into an (L2-resident) open-addressing set; a pair seen
-//                           for the first time bumps distinct[cell] and is optionally written to a
-//                           compact list of unique pairs (multi-GPU exchange)
-// A global 512 MB set probed from the scan kernel cost ~6 B/row of DRAM traffic on C2; this costs the
-// 8-byte pairs written and read twice.
-// ---------------------------------------------------------------------------------------------
+constexpr int kSmemSetThreads = 1024;
+constexpr uint32_t kSmemSetSlots = 12288;   // 96 KB: two CTAs per SM (best of tools/dedupe_probe.cu)
+struct PairsSmemDedupeParams {
+  const uint64_t *buckets;     // bucket b at b * bucket_cap
+  const uint32_t *cursors;     // [nbuckets]
+  uint32_t nbuckets;
+  uint32_t bucket_cap;
+  uint32_t nslots;             // slots of the shared-memory set (8 bytes each)
+  uint32_t limit;              // pairs a bucket may hold (<= 3/4 of the slots)
+  uint8_t *distinct;           // count of cell 0 (uint32), `stride` bytes between cells
+  uint32_t stride;
+  unsigned long long *flags;   // set when a bucket does not fit the set
+};
+
+__global__ void __launch_bounds__(kSmemSetThreads, 2) pairs_dedupe_smem_kernel(const __grid_constant__ PairsSmemDedupeParams D) {
+  extern __shared__ __align__(16) uint64_t s_set[];
+  const uint64_t pol = make_table_policy(false);
+  for (uint32_t b = blockIdx.x; b < D.nbuckets; b += gridDim.x) {
+    const uint32_t n = D.cursors[b];
+    if (n == 0) continue;   // uniform per CTA
+    if (n > D.limit || n > D.bucket_cap) {
+      if (threadIdx.x == 0) atomicOr(D.flags, 1ull);
+      continue;
+    }
+    for (uint32_t i = threadIdx.x; i < D.nslots; i += kSmemSetThreads) s_set[i] = kEmptyKey;
+    __syncthreads();
+    const uint64_t *src = D.buckets + (uint64_t)b * D.bucket_cap;
+    for (uint32_t i = threadIdx.x; i < n; i += kSmemSetThreads) {
+      const uint64_t key = src[i];
+      // the all-ones pair cannot live in the set: cells are < 2^32 - 1 by construction, so it never occurs
+      uint32_t slot = (uint32_t)(((mix64(key ^ 0x5bd1e9955bd1e995ull) >> 32) * D.nslots) >> 32);
+      while (true) {
+        const unsigned long long old = atomicCAS(reinterpret_cast<unsigned long long *>(s_set + slot),
+                                                 (unsigned long long)kEmptyKey, (unsigned long long)key);
+        if (old == kEmptyKey) {
+          red_add_u32(D.distinct + (key >> 32) * D.stride, 1u, pol);
+          break;
+        }
+        if (old == key) break;
+        slot = slot + 1 == D.nslots ? 0 : slot + 1;
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// ---- general path ----
 constexpr int kMaxBuckets = 256;
 struct PairsPartitionParams {
   const uint64_t *pairs;       // regions, region r at r * region_cap
@@ -403,8 +525,7 @@ struct PairsPartitionParams {
   uint64_t total;
   uint32_t nregions;
   uint32_t region_cap;
-  uint32_t nbuckets;           // power of two <= kMaxBuckets (hash buckets), or the number of ranks (owner_parts)
-  uint32_t owner_parts;        // non-zero: bucket = rank that owns the pair's cell (multi-GPU exchange)
+  uint32_t nbuckets;           // power of two <= kMaxBuckets
   uint32_t shift;              // bucket = mix64(pair) >> shift
   uint64_t bucket_cap;
   unsigned long long *cursors; // [nbuckets], zeroed
@@ -418,7 +539,7 @@ __global__ void __launch_bounds__(256) pairs_partition_kernel(const __grid_const
   constexpr int kPer = 8;
   for (uint32_t r = blockIdx.x; r < A.nregions; r += gridDim.x) {
     const uint64_t *src = A.pairs + (uint64_t)r * A.region_cap;
-    const uint32_t n = A.counts ? A.counts[r]
+    const uint32_t n = A.counts ? min(A.counts[r], A.region_cap)
                                 : (uint32_t)min((uint64_t)A.region_cap, A.total - (uint64_t)r * A.region_cap);
     for (uint32_t t0 = 0; t0 < n; t0 += blockDim.x * kPer) {
       for (uint32_t i = threadIdx.x; i < A.nbuckets; i += blockDim.x) s_cnt[i] = 0;
@@ -431,8 +552,7 @@ __global__ void __launch_bounds__(256) pairs_partition_kernel(const __grid_const
         bkt[j] = 0xffffffffu;
         if (i < n) {
           key[j] = src[i];
-          bkt[j] = A.owner_parts ? (uint32_t)((mix64(key[j] >> 32) >> 17) % A.owner_parts)
-                                 : (uint32_t)(mix64(key[j]) >> A.shift) & (A.nbuckets - 1);
+          bkt[j] = (uint32_t)(mix64(key[j]) >> A.shift) & (A.nbuckets - 1);
           pos[j] = atomicAdd(&s_cnt[bkt[j]], 1u);
         }
       }
@@ -452,20 +572,36 @@ __global__ void __launch_bounds__(256) pairs_partition_kernel(const __grid_const
   }
 }
 
+// Pair = uint64_t (cell << 32 | id) or Pair128
+template <class Pair>
 struct PairsDedupeParams {
-  const uint64_t *pairs;       // one bucket, or ragged regions when counts != nullptr
+  const Pair *pairs;           // one bucket, or ragged regions when counts != nullptr
   const uint32_t *counts;      // nullptr: `n` contiguous pairs
   uint32_t nregions, region_cap;
   uint64_t n;
-  uint64_t *set;
+  Pair *set;                   // all-ones = free slot
   uint64_t set_mask;
   uint8_t *distinct;           // count of cell 0 (uint32), `stride` bytes between cells
   uint32_t stride;
-  uint64_t *unique_out;        // optional compact list of first-seen pairs
-  unsigned long long *unique_n;
+  // Pair128 whose `hi` is a packed group key instead of a cell (merge of hashed group tables across GPUs): the
+  // cell is the key's slot in this open-addressing table (the key is always there: its partial record arrived first)
+  const uint64_t *lookup_keys;
+  uint64_t lookup_mask;
+  unsigned long long *sentinel_seen;  // the all-ones Pair128 cannot live in the set: counted once through this flag
 };
 
-__device__ __forceinline__ void pairs_insert(const PairsDedupeParams &D, uint64_t key, uint64_t pol) {
+__device__ __forceinline__ uint64_t lookup_cell(const uint64_t *keys, uint64_t mask, uint64_t key) {
+  if (key == kEmptyKey) return mask + 1;   // the all-ones key lives in its dedicated cell
+  uint64_t slot = mix64(key) & mask;
+  while (true) {
+    const uint64_t k = keys[slot];
+    if (k == key) return slot;
+    if (k == kEmptyKey) return kEmptyKey;  // cannot happen
+    slot = (slot + 1) & mask;
+  }
+}
+
+__device__ __forceinline__ void pairs_insert(const PairsDedupeParams<uint64_t> &D, uint64_t key, uint64_t pol) {
   // the all-ones pair cannot live in the set: cells are < 2^32 - 1 by construction, so it never occurs
   uint64_t slot = mix64(key ^ 0x5bd1e9955bd1e995ull) & D.set_mask;
   while (true) {
@@ -473,15 +609,33 @@ __device__ __forceinline__ void pairs_insert(const PairsDedupeParams &D, uint64_
                                        (unsigned long long)kEmptyKey, (unsigned long long)key);
     if (old == kEmptyKey) {
       red_add_u32(D.distinct + (key >> 32) * D.stride, 1u, pol);
-      if (D.unique_out) D.unique_out[atomicAdd(D.unique_n, 1ull)] = key;
       return;
     }
     if (old == key) return;
     slot = (slot + 1) & D.set_mask;
   }
 }
+__device__ __forceinline__ void pairs_insert(const PairsDedupeParams<Pair128> &D, Pair128 key, uint64_t pol) {
+  bool fresh = false;
+  if (key.hi == kEmptyKey && key.lo == kEmptyKey) {
+    fresh = atomicExch(D.sentinel_seen, 1ull) == 0ull;
+  } else {
+    uint64_t slot = mix64(mix64(key.hi) ^ (key.lo * 0x9E3779B97F4A7C15ull)) & D.set_mask;
+    const Pair128 empty{kEmptyKey, kEmptyKey};
+    while (true) {
+      const Pair128 old = cas128(D.set + slot, empty, key);
+      if (old.hi == kEmptyKey && old.lo == kEmptyKey) { fresh = true; break; }
+      if (old.hi == key.hi && old.lo == key.lo) break;
+      slot = (slot + 1) & D.set_mask;
+    }
+  }
+  if (!fresh) return;
+  const uint64_t cell = D.lookup_keys ? lookup_cell(D.lookup_keys, D.lookup_mask, key.hi) : key.hi;
+  if (cell != kEmptyKey) red_add_u32(D.distinct + cell * D.stride, 1u, pol);
+}
 
-__global__ void __launch_bounds__(256) pairs_dedupe_kernel(const __grid_constant__ PairsDedupeParams D) {
+template <class Pair>
+__global__ void __launch_bounds__(256) pairs_dedupe_kernel(const __grid_constant__ PairsDedupeParams<Pair> D) {
   const uint64_t pol = make_table_policy(false);
   if (D.counts == nullptr) {
     // one insert in flight per thread: the kernel is bound by the L2's atomic throughput, not by latency
@@ -490,8 +644,8 @@ __global__ void __launch_bounds__(256) pairs_dedupe_kernel(const __grid_constant
       pairs_insert(D, D.pairs[i], pol);
   } else {
     for (uint32_t r = blockIdx.x; r < D.nregions; r += gridDim.x) {
-      const uint64_t *src = D.pairs + (uint64_t)r * D.region_cap;
-      const uint32_t n = D.counts[r];
+      const Pair *src = D.pairs + (uint64_t)r * D.region_cap;
+      const uint32_t n = min(D.counts[r], D.region_cap);
       for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) pairs_insert(D, src[i], pol);
     }
   }
@@ -626,6 +780,7 @@ __global__ void __launch_bounds__(256) merge_records_kernel(const __grid_constan
 struct ExtractKey {
   uint64_t lo, div, mod;  // value = lo + (packed / div) % mod   (mod == 0: no modulo)
   uint64_t lut;           // non-zero: the digit is the rank of the value among the set bits (KeySpec::lut)
+  const uint64_t *dict;   // non-null: the digit is the rank of a rolled-up time value (TimeDict), dict[rank] = value
   uint32_t width;
   uint32_t pad;
   void *out;
@@ -650,6 +805,9 @@ struct ExtractParams {
   ExtractMet mets[kMaxMetrics + 1];
   unsigned long long *counter;  // number of groups
   uint32_t count_only;
+  uint64_t cap;                 // rows the output arrays hold: groups beyond it are counted, not written
+  uint32_t *pos_out;            // optional [ncells], preset to 0xffffffff: output position of every present cell
+                                // (extract_late_kernel fills in the accumulators that were not final yet)
 };
 
 __device__ __forceinline__ bool cell_present(const ExtractParams &E, uint64_t c, uint64_t &packed) {
@@ -684,6 +842,8 @@ extract_groups_kernel(const __grid_constant__ ExtractParams E) {
     base = __shfl_sync(0xffffffffu, base, 0);
     if (!pres || E.count_only) continue;
     uint64_t pos = base + __popc(ballot & ((1u << lane) - 1));
+    if (pos >= E.cap) continue;
+    if (E.pos_out) E.pos_out[c] = (uint32_t)pos;
     for (uint32_t k = 0; k < E.nkeys; ++k) {
       const ExtractKey &ek = E.keys[k];
       uint64_t v;
@@ -693,6 +853,7 @@ extract_groups_kernel(const __grid_constant__ ExtractParams E) {
         uint64_t q = packed / ek.div;
         if (ek.mod) q %= ek.mod;
         v = ek.lo + q;
+        if (ek.dict) v = ek.dict[q];
         if (ek.lut) {  // the q-th set bit
           uint64_t x = ek.lut;
           for (uint64_t i = 0; i < q; ++i) x &= x - 1;
@@ -717,6 +878,28 @@ extract_groups_kernel(const __grid_constant__ ExtractParams E) {
         case 4: reinterpret_cast<uint32_t *>(em.out)[pos] = (uint32_t)v; break;
         default: reinterpret_cast<uint64_t *>(em.out)[pos] = v; break;
       }
+    }
+  }
+}
+
+// accumulators that become final after the groups were extracted (count-distinct: the dedupe runs while the
+// keys and the other accumulators already travel to the host)
+struct ExtractLateParams {
+  uint64_t ncells;
+  const uint32_t *pos;   // ExtractParams::pos_out
+  uint32_t nmets;
+  ExtractMet mets[kMaxDistinct];
+};
+__global__ void __launch_bounds__(256) extract_late_kernel(const __grid_constant__ ExtractLateParams L) {
+  for (uint64_t c = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; c < L.ncells; c += (uint64_t)gridDim.x * blockDim.x) {
+    const uint32_t pos = L.pos[c];
+    if (pos == 0xffffffffu) continue;
+    for (uint32_t m = 0; m < L.nmets; ++m) {
+      const ExtractMet &em = L.mets[m];
+      const uint8_t *ap = reinterpret_cast<const uint8_t *>(em.acc) + c * em.stride;
+      const uint64_t v = em.acc_width == 4 ? (uint64_t)*reinterpret_cast<const uint32_t *>(ap) : *reinterpret_cast<const uint64_t *>(ap);
+      if (em.out_width == 8) reinterpret_cast<uint64_t *>(em.out)[pos] = v;
+      else reinterpret_cast<uint32_t *>(em.out)[pos] = (uint32_t)v;
     }
   }
 }

@@ -235,7 +235,7 @@ __device__ __noinline__ uint64_t wide_row_cell(const ScanParams &P, const CurSeg
     const uint8_t *a = seg.slab + sl.off * seg.cap + (uint64_t)row * sl.width;
     uint64_t val = gather_finish(gather_raw64(a), a, sl.vmask, sl.signbit);
     if (ks.rollup) val = rollup_value(val, ks);
-    if (ks.fzero && ((val << 1) == 0 || (sl.width == 4 && (uint32_t)(val << 1) == 0))) val = 0;  // -0.0 == +0.0
+    if (ks.fzero) val = fzero_fix(val, sl.width);
     kw[k] = val;
   }
   return wide_cell(P, kw);
@@ -260,8 +260,8 @@ scan_filter_groupby_kernel(const __grid_constant__ ScanParams P) {
   uint32_t npend = 0;  // rows waiting in the list (warp-uniform)
   CurSeg seg{};        // the segment of the warp's current work unit
   uint32_t my_passed = 0;
-  __shared__ uint32_t s_cursor[kMaxDistinct];  // pairs this CTA appended per count-distinct metric
-  if (threadIdx.x < kMaxDistinct) s_cursor[threadIdx.x] = 0;
+  __shared__ uint32_t s_cursor[kMaxDistinct][kMaxRanks];  // pairs this CTA appended per count-distinct metric and owner rank
+  if (threadIdx.x < kMaxDistinct * kMaxRanks) (&s_cursor[0][0])[threadIdx.x] = 0;
   // CTA-private group table (small dense domains): every cell starts as the plan's initial image
   extern __shared__ __align__(16) uint8_t s_table[];
   const uint32_t s_table_a = (uint32_t)__cvta_generic_to_shared(s_table);
@@ -270,7 +270,7 @@ scan_filter_groupby_kernel(const __grid_constant__ ScanParams P) {
     for (uint32_t i = threadIdx.x; i < nwords; i += kThreads) reinterpret_cast<uint32_t *>(s_table)[i] = P.smem_init[i % wpc];
   }
   __syncthreads();
-  const bool can_overflow = P.hash_mode || P.ndistinct;
+  const bool can_overflow = P.hash_mode != 0;
   const uint64_t pol = make_stream_policy((P.tune & 2u) != 0);
   const uint64_t tpol = make_table_policy((P.tune & 4u) != 0);
 
@@ -325,7 +325,9 @@ scan_filter_groupby_kernel(const __grid_constant__ ScanParams P) {
           const uint32_t pos = rowpath ? ks.row_off : row * ks.width;
           uint64_t val = ((uint64_t)(kv[k] >> ((pos & 3u) * 8u))) & ks.vmask;
           val = (val ^ ks.signbit) - ks.signbit;
-          if (ks.rollup) val = rollup_value(val, ks);
+          if (P.tdict.npieces && k == P.tdict.key) val = tdict_rank(P.tdict, val);  // rank of the rolled-up value
+          else if (ks.rollup) val = rollup_value(val, ks);
+          if (ks.fzero) val = fzero_fix(val, 4);
           if (ks.lut) val = (uint64_t)__popcll(ks.lut & ((1ull << val) - 1ull));  // rank inside the IN list
           else val -= ks.lo;
           packed += val * ks.mul;
@@ -337,7 +339,9 @@ scan_filter_groupby_kernel(const __grid_constant__ ScanParams P) {
         const Slot &sl = P.slots[ks.slot];
         const uint8_t *a = seg.slab + sl.off * seg.cap + (uint64_t)row * sl.width;
         uint64_t val = gather_finish(gather_raw64(a), a, sl.vmask, sl.signbit);
-        if (ks.rollup) val = rollup_value(val, ks);
+        if (P.tdict.npieces && k == P.tdict.key) val = tdict_rank(P.tdict, val);
+        else if (ks.rollup) val = rollup_value(val, ks);
+        if (ks.fzero) val = fzero_fix(val, sl.width);
         if (ks.lut) val = (uint64_t)__popcll(ks.lut & ((1ull << val) - 1ull));
         else val -= ks.lo;
         packed += val * ks.mul;
@@ -347,13 +351,13 @@ scan_filter_groupby_kernel(const __grid_constant__ ScanParams P) {
     if (P.hash_mode == 2) {
       cell = packed;
       if (cell == kEmptyKey) {
-        atomicOr(&P.counters[1], 1ull);
+        atomicOr(&P.counters[kCHashOver], 1ull);
         return;
       }
     } else if (P.hash_mode) {
       cell = hash_cell(P, packed);
       if (cell == kEmptyKey) {
-        atomicOr(&P.counters[1], 1ull);
+        atomicOr(&P.counters[kCHashOver], 1ull);
         return;
       }
     } else {
@@ -381,19 +385,25 @@ scan_filter_groupby_kernel(const __grid_constant__ ScanParams P) {
         else acc_update(reinterpret_cast<uint8_t *>(ms.acc) + cell * ms.stride, ms.op, pre, tpol);
         continue;
       }
-      // count-distinct: append (cell, id) to this CTA's region; deduplicated after the scan
+      // count-distinct: append (cell, id) to this CTA's region (of the pair's owner rank); deduplicated after the scan
       const uint32_t *off = sd.bs_offsets[ms.bitset_idx];
       const uint32_t *vals = sd.bs_values[ms.bitset_idx];
-      uint64_t *region = P.dpairs[dn] + (uint64_t)blockIdx.x * P.dpair_cap;
-      if (off == nullptr) {  // one id per row: `pre` is the id
-        const uint32_t pos = atomicAdd(&s_cursor[dn], 1u);
-        if (pos < P.dpair_cap) region[pos] = (cell << 32) | pre;
-      } else {               // CSR cell: `pre` is offsets[row]
-        const uint32_t lo = (uint32_t)pre, hi = gather_u32(off + row + 1);
-        for (uint32_t q = lo; q < hi; ++q) {
-          const uint32_t pos = atomicAdd(&s_cursor[dn], 1u);
-          if (pos < P.dpair_cap) region[pos] = (cell << 32) | (uint64_t)gather_u32(vals + q);
+      const uint64_t hi = P.dpair_key ? packed : cell;
+      auto append = [&](const uint64_t id) {
+        const uint32_t sub = P.dpair_nsub > 1 ? (P.dpair_key ? owner_of(hi, 0, P.dpair_nsub) : pair_owner(hi, id, P.dpair_nsub)) : 0u;
+        const uint32_t pos = atomicAdd(&s_cursor[dn][sub], 1u);
+        if (pos < P.dpair_cap) {
+          const uint64_t at = ((uint64_t)sub * gridDim.x + blockIdx.x) * P.dpair_cap + pos;
+          if (P.dpair_wide) reinterpret_cast<ulonglong2 *>(P.dpairs[dn])[at] = make_ulonglong2(hi, id);
+          else P.dpairs[dn][at] = (hi << 32) | id;
         }
+      };
+      if (off == nullptr) {  // one id per row: `pre` is the id
+        append(pre);
+      } else {               // CSR cell: `pre` is offsets[row]
+        const uint32_t lo = (uint32_t)pre, hi_q = gather_u32(off + row + 1);
+        for (uint32_t q = lo; q < hi_q; ++q)
+          append(ms.id64 ? __ldg(reinterpret_cast<const unsigned long long *>(vals) + q) : (uint64_t)gather_u32(vals + q));
       }
       ++dn;
     }
@@ -412,7 +422,7 @@ scan_filter_groupby_kernel(const __grid_constant__ ScanParams P) {
   const uint32_t ups = P.units_per_seg, nunits = P.nactive * ups;
   auto grab = [&]() {
     uint32_t u = 0;
-    if (lane == 0) u = atomicAdd(reinterpret_cast<unsigned int *>(&P.counters[8]), 1u);
+    if (lane == 0) u = atomicAdd(reinterpret_cast<unsigned int *>(&P.counters[kCUnit]), 1u);
     return __shfl_sync(0xffffffffu, u, 0);
   };
   uint32_t unit = grab();
@@ -421,7 +431,7 @@ scan_filter_groupby_kernel(const __grid_constant__ ScanParams P) {
     // a full group table / distinct set makes the host grow it and run again: stop wasting time
     if (can_overflow) {
       unsigned long long f = 0;
-      if (lane == 0) f = *reinterpret_cast<volatile unsigned long long *>(&P.counters[1]);
+      if (lane == 0) f = *reinterpret_cast<volatile unsigned long long *>(&P.counters[kCHashOver]);
       if (__shfl_sync(0xffffffffu, f, 0) != 0ull) break;
     }
     const uint32_t si = unit / ups, part = unit - si * ups;
@@ -544,14 +554,16 @@ scan_filter_groupby_kernel(const __grid_constant__ ScanParams P) {
   // counters: one atomic per warp
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) my_passed += __shfl_down_sync(0xffffffffu, my_passed, o);
-  if (lane == 0 && my_passed) atomicAdd(&P.counters[0], (unsigned long long)my_passed);
+  if (lane == 0 && my_passed) atomicAdd(&P.counters[kCPassed], (unsigned long long)my_passed);
   if (P.ndistinct) {  // the only CTA-wide barrier of the kernel: publish the per-CTA pair counts
     __syncthreads();
-    if (threadIdx.x < P.ndistinct) {
-      const uint32_t n = s_cursor[threadIdx.x];
-      P.dpair_count[threadIdx.x][blockIdx.x] = n < P.dpair_cap ? n : P.dpair_cap;
-      if (n > P.dpair_cap) atomicOr(&P.counters[1], 2ull);  // region overflow: the host grows it and re-runs
-      atomicAdd(&P.counters[2 + threadIdx.x], (unsigned long long)n);
+    if (threadIdx.x < P.ndistinct * P.dpair_nsub) {
+      const uint32_t d = threadIdx.x / P.dpair_nsub, sub = threadIdx.x - d * P.dpair_nsub;
+      const uint32_t n = s_cursor[d][sub];
+      P.dpair_count[d][sub * gridDim.x + blockIdx.x] = n < P.dpair_cap ? n : P.dpair_cap;
+      if (n > P.dpair_cap) atomicOr(&P.counters[kCRegionOver], 1ull);  // the host grows the regions and scans again
+      atomicAdd(&P.counters[kCPairs + d], (unsigned long long)n);
+      atomicMax(&P.counters[kCMaxFill + d], (unsigned long long)n);  // fullest region: what the next query sizes them by
     }
   }
 }

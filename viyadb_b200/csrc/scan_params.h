@@ -23,6 +23,26 @@ constexpr int kMaxRules = 8;
 constexpr int kStackDepth = 5;
 constexpr int kMaxDistinct = 2;
 constexpr int kMaxBitsetCols = 4;
+constexpr int kMaxRanks = 8;        // GPUs of one box: owner sub-regions of a CTA's count-distinct pair region
+constexpr int kMaxTimeSegs = 48;    // pieces of a rolled-up time key's bucket dictionary
+
+// Per-query counter block (16 x u64). With several GPUs words [kCSumFirst, kCMaxFirst) are sum-reduced and words
+// [kCMaxFirst, kCLocalFirst) max-reduced across ranks in one exchange, so every flag has a word of its own.
+enum Counter : int {
+  kCPassed = 0,        // rows whose predicate was true
+  kCScannedRecs = 1,   // host-provided: QueryStats.scanned_recs of this rank
+  kCScannedSegs = 2,   // host-provided: QueryStats.scanned_segments of this rank
+  kCPairs = 3,         // +d: count-distinct pairs appended for distinct metric d (all CTAs)
+  kCMaxFill = 5,       // +d: fullest pair region
+  kCHashOver = 7,      // probe limit of the group table reached: grow x4, scan again
+  kCRegionOver = 8,    // a pair region overflowed: grow, scan again
+  kCBucketOver = 9,    // count-distinct fast path: a hash bucket overflowed
+  kCSetOver = 10,      // count-distinct fast path: a bucket does not fit the shared-memory set
+  kCError = 11,        // a rank failed before the exchange: everybody aborts
+  kCGroups = 12,       // groups extracted (local)
+  kCUnit = 13,         // next work unit of the scan (low 32 bits)
+  kCSumFirst = 0, kCMaxFirst = 5, kCLocalFirst = 12
+};
 
 // A column as the kernel sees it.
 struct Slot {
@@ -105,6 +125,26 @@ struct MetSpec {
   uint32_t width, row_off, bitset, bitset_idx;
   uint32_t soff;       // offset of the accumulator inside a cell of the CTA-private table (smem_cells != 0)
   uint32_t acc_width;  // 4 or 8
+  uint32_t id64;       // BITSET column whose ids are 64 bits wide (util::Bitset<8> = Roaring64Map, bitset.h:27-31):
+  uint32_t pad2;       // the segment's id array holds uint64 and the cell always goes through its CSR offsets
+};
+
+// Bucket dictionary of a rolled-up time key. Rule boundaries cut the raw time line into regions with
+// one truncation unit each (rollup.cc:77-95); inside a region the truncated values are equally spaced (minute /
+// hour / day) or one per calendar month / year. When the truncated value never decreases along the raw time line,
+// its RANK among all attainable values is a step function of the raw value: piece j covers raw values from
+// start[j] on, and inside it the rank grows by one every step[j] seconds counted from origin[j] <= start[j] (the
+// unit-aligned start of its first bucket; step 0: the whole piece is one value). The key becomes that rank — a dense domain of a few hundred buckets instead of 2^32 seconds — and the
+// calendar arithmetic runs once per bucket on the host (KeySpec rollup stays the fallback).
+struct TimeDict {
+  uint32_t npieces;      // 0: not in use
+  uint32_t key;          // index of the key it applies to
+  uint32_t micro;        // values are microseconds: pieces are in seconds, value / 1e6 first
+  uint32_t pad;
+  uint64_t start[kMaxTimeSegs];   // ascending (seconds); start[0] <= every value of the column
+  uint64_t origin[kMaxTimeSegs];
+  uint32_t base[kMaxTimeSegs];
+  uint32_t step[kMaxTimeSegs];    // 0, 60, 3600, 86400 (or 1 for second granularity)
 };
 
 // Per-segment descriptor (device array, one per table segment).
@@ -177,14 +217,20 @@ struct ScanParams {
   MetSpec mets[kMaxMetrics];
   uint32_t ndistinct;                 // BITSET metrics selected (count-distinct)
   uint8_t distinct_met[kMaxDistinct]; // their indices into mets
-  // count-distinct: (cell << 32 | id) pairs are appended to a private region per CTA (cursor in shared
-  // memory), deduplicated afterwards in L2-sized hash partitions (pairs_* kernels)
-  uint64_t *dpairs[kMaxDistinct];     // region of CTA b: [b * dpair_cap, (b + 1) * dpair_cap)
-  uint32_t *dpair_count[kMaxDistinct];  // [gridDim.x] pairs written by each CTA
+  // count-distinct: (cell << 32 | id) pairs are appended to private regions per CTA (cursors in shared memory)
+  // and deduplicated after the scan (pairs_* kernels). With several GPUs a CTA keeps one sub-region per owner
+  // rank (owner = hash of the pair), laid out owner-major so that everything bound for one rank is one slab.
+  // dpair_wide: 16-byte pairs {cell or packed group key, 64-bit id} (64-bit ids; hashed group tables across GPUs)
+  uint64_t *dpairs[kMaxDistinct];       // region (sub, b): [(sub * gridDim.x + b) * dpair_cap, ...) elements
+  uint32_t *dpair_count[kMaxDistinct];  // [dpair_nsub * gridDim.x] pairs written per region
   uint32_t dpair_cap;
+  uint32_t dpair_nsub;                  // 1, or the number of ranks
+  uint32_t dpair_wide;
+  uint32_t dpair_key;                   // wide pairs carry the packed group key instead of the local cell (hash_mode 1)
 
-  // counters: [0] passed rows, [1] overflow flag (probe limit of the group table or of a distinct set),
-  // [2+d] pairs appended for distinct metric d (all CTAs), [8] next work unit (low 32 bits)
+  TimeDict tdict;
+
+  // per-query counter block, layout kC* below
   unsigned long long *counters;
 };
 

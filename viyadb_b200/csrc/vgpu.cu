@@ -18,8 +18,10 @@
 #include <cstring>
 #include <dlfcn.h>
 #include <memory>
+#include <atomic>
 #include <mutex>
 #include <nccl.h>
+#include <shared_mutex>
 #include <string>
 #include <vector>
 
@@ -249,21 +251,38 @@ struct PinnedPool {
   }
 };
 
+// Everything one in-flight query needs of its own: vgpu_query_* is re-entrant per context (the reference's generated
+// query function keeps all its state on the stack and runs on `query_threads` pool threads at once,
+// src/db/database.cc:28-33), so no two queries share a stream, an event or a counter block.
+struct QueryScope {
+  cudaStream_t s0 = nullptr, s1 = nullptr;   // main stream; side stream (early group extraction + its copies)
+  cudaEvent_t ev_begin = nullptr, ev_scan0 = nullptr, ev_scan1 = nullptr, ev_end = nullptr;
+  cudaEvent_t ev_a = nullptr, ev_b = nullptr, ev_c = nullptr;  // untimed ordering events between s0 and s1
+  unsigned long long *d_counters = nullptr;  // 16 x u64, layout in query_agg.inl (kC*)
+  unsigned long long *h_counters = nullptr;  // pinned: [0,16) read-back, [16,32) initial image, [32,48) second read-back
+  uint64_t *d_plan = nullptr;                // 64 x u64: plan-time agreement between ranks
+  uint64_t *h_plan = nullptr;                // pinned
+};
+
 struct vgpu_ctx {
   int device = 0;
   int sm_count = 148;
+  // column-store maintenance (put / generate / invalidate) runs on these; one such call at a time per context
   cudaStream_t stream = nullptr;
-  bool own_stream = true;
   // host -> device copies of vgpu_segment_put run on their own stream: the DMA of one segment overlaps the
   // statistics and row-mirror kernels of the previous one (which stay on `stream`, ordered by ev_copy)
   cudaStream_t copy_stream = nullptr;
   cudaEvent_t ev_copy = nullptr;
-  cudaEvent_t ev_begin = nullptr, ev_scan0 = nullptr, ev_scan1 = nullptr, ev_end = nullptr;
-  unsigned long long *d_counters = nullptr;  // 16 x u64
-  unsigned long long *h_counters = nullptr;  // pinned
-  uint64_t *d_plan = nullptr;                // 64 x u64: plan-time agreement between ranks
-  std::mutex mu;                             // one query / put at a time per context
-  // multi-GPU
+  std::mutex put_mu;
+  // the caller's stream (vgpu_set_stream): queries are ordered after what it holds when they start, and it waits
+  // for them when they end, so that the caller's own events bracket a query
+  cudaStream_t user_stream = nullptr;
+  cudaEvent_t ev_user = nullptr;
+  // idle query scopes
+  std::mutex scope_mu;
+  std::vector<QueryScope *> idle_scopes;
+  // multi-GPU: one collective sequence at a time per communicator (every rank must issue the same sequence)
+  std::mutex comm_mu;
   ncclComm_t comm = nullptr;
   int rank = 0, nranks = 1;
   // L2 persistence (group tables are pinned in L2 while the columns stream through it)
@@ -272,10 +291,18 @@ struct vgpu_ctx {
   // bit 2 evict_last group table, bit 5 no next-chunk L2 prefetch, bit 6 build no row-major mirror,
   // bit 7 never gather from the mirror, bit 8 always gather from the mirror (tests), bit 12 no unrolled conjunction fast path
   // (always the stack interpreter), bit 13 per-lane instead of bulk L2 prefetch of the next chunk, bit 14 no
-  // tightening of key domains from the predicate, bit 18 no CTA-private shared-memory copy of small dense group tables
+  // tightening of key domains from the predicate, bit 18 no CTA-private shared-memory copy of small dense group tables,
+  // bit 19 count-distinct: never the shared-memory-set fast path, bit 20 no early group extraction on the side
+  // stream, bit 21 no bucket dictionary for rolled-up time keys
   uint32_t tune = 2;
   int ctas_per_sm = VGPU_MIN_CTAS;  // VGPU_CTAS: resident scan CTAs per SM (2, 3 or 4: picks the register cap)
   uint32_t unit_chunks = 0;  // VGPU_UNIT_CHUNKS: 512-row chunks per dynamically scheduled work unit (0: adaptive)
+  // test hooks that force the rarely taken branches at test sizes (tests/test_gpu_forced_paths.py):
+  uint64_t test_pairs_cap = 0;     // VGPU_TEST_PAIRS_CAP: first-attempt capacity of the count-distinct pair regions (overflow + regrow)
+  uint64_t test_hash_cap = 0;      // VGPU_TEST_HASH_CAP: first-attempt capacity of hashed group tables (x4 regrow)
+  uint64_t test_bucket_pairs = 0;  // VGPU_TEST_BUCKET_PAIRS: pairs per L2-sized partition of the general dedupe path (B > 1)
+  uint64_t test_small_pairs = 0;   // VGPU_TEST_SMALL_PAIRS: largest pair capacity deduplicated by one global set
+  uint32_t test_set_slots = 0;     // VGPU_TEST_SET_SLOTS: slots of the shared-memory sets (small: forces the fallback)
   // pool of pinned host blocks that back vgpu_result (D2H at full PCIe speed, no per-query
   // cudaMallocHost); shared with the results so that they may outlive the context
   std::shared_ptr<PinnedPool> pool = std::make_shared<PinnedPool>();
@@ -286,6 +313,7 @@ namespace {
 
 struct ColInfo {
   uint32_t kind, type, agg;
+  uint32_t lit_type;  // type of a filter literal on this column (BITSET: the reference's id type, which hosts may have widened)
   uint32_t width;
   bool sext;
   bool bitset;
@@ -316,6 +344,10 @@ struct SegmentData {
 
 struct vgpu_table {
   vgpu_ctx *ctx = nullptr;
+  // queries hold it shared from planning to their last device operation; put / generate / invalidate hold it
+  // exclusively (same-table writers wait for running queries, queries on it wait for the writer)
+  std::shared_mutex mu;
+  cudaEvent_t ev_put = nullptr;   // recorded after the device work of the last put: queries' streams wait for it
   std::vector<ColInfo> cols;
   uint32_t ndims = 0;
   uint32_t nbitsets = 0;
@@ -331,9 +363,14 @@ struct vgpu_table {
   size_t d_stats_segs = 0;
   unsigned long long *h_stats_init = nullptr;  // pinned pattern {~0, 0} x ncols
   bool descs_dirty = true;
-  // scratch high-water marks so that a repeated query shape never re-runs on overflow
-  uint64_t hash_cap_hint = 0;
-  uint64_t pairs_cap_hint = 0;
+  bool stats_dirty = false;       // some segment's statistics are still on the device
+  // scratch high-water marks so that a repeated query shape never re-runs on overflow (benign races between
+  // concurrent queries: any value is a valid hint)
+  std::atomic<uint64_t> hash_cap_hint{0};
+  std::atomic<uint64_t> pairs_total_hint{0};   // most count-distinct pairs one query produced
+  std::atomic<uint64_t> pairs_region_hint{0};  // fullest pair region of one query
+  std::atomic<uint64_t> groups_hint{0};        // most groups one query returned
+  std::atomic<uint32_t> distinct_general{0};   // the shared-memory-set path overflowed before: go straight to the general one
 };
 
 // results of select / search queries: arrays inside one pinned host block
@@ -369,9 +406,11 @@ namespace {
 // ---------------------------------------------------------------------------------------------
 struct Scratch {
   cudaStream_t stream;
+  cudaStream_t side;   // a second stream that may still use the allocations when an error unwinds the query
   std::vector<void *> ptrs;
-  explicit Scratch(cudaStream_t s) : stream(s) {}
+  explicit Scratch(cudaStream_t s, cudaStream_t side_stream = nullptr) : stream(s), side(side_stream) {}
   ~Scratch() {
+    if (side) cudaStreamSynchronize(side);
     for (void *p : ptrs) cudaFreeAsync(p, stream);
   }
   template <class T> T *alloc(uint64_t n) {
@@ -379,6 +418,70 @@ struct Scratch {
     CUDA_CK(cudaMallocAsync(&p, std::max<uint64_t>(n, 1) * sizeof(T), stream));
     ptrs.push_back(p);
     return static_cast<T *>(p);
+  }
+};
+
+void destroy_scope(QueryScope *sc) {
+  if (!sc) return;
+  if (sc->s0) cudaStreamDestroy(sc->s0);
+  if (sc->s1) cudaStreamDestroy(sc->s1);
+  for (cudaEvent_t e : {sc->ev_begin, sc->ev_scan0, sc->ev_scan1, sc->ev_end, sc->ev_a, sc->ev_b, sc->ev_c})
+    if (e) cudaEventDestroy(e);
+  if (sc->d_counters) cudaFree(sc->d_counters);
+  if (sc->h_counters) cudaFreeHost(sc->h_counters);
+  if (sc->d_plan) cudaFree(sc->d_plan);
+  if (sc->h_plan) cudaFreeHost(sc->h_plan);
+  delete sc;
+}
+
+// RAII lease of a QueryScope; entering also orders the query after the caller's stream, leaving makes the
+// caller's stream wait for the query
+struct ScopeLease {
+  vgpu_ctx *ctx;
+  QueryScope *sc = nullptr;
+  cudaStream_t user = nullptr;
+  explicit ScopeLease(vgpu_ctx *c) : ctx(c) {
+    {
+      std::lock_guard<std::mutex> lk(ctx->scope_mu);
+      user = ctx->user_stream;
+      if (!ctx->idle_scopes.empty()) { sc = ctx->idle_scopes.back(); ctx->idle_scopes.pop_back(); }
+    }
+    if (!sc) {
+      std::unique_ptr<QueryScope, void (*)(QueryScope *)> n(new QueryScope(), destroy_scope);
+      CUDA_CK(cudaStreamCreateWithFlags(&n->s0, cudaStreamNonBlocking));
+      CUDA_CK(cudaStreamCreateWithFlags(&n->s1, cudaStreamNonBlocking));
+      CUDA_CK(cudaEventCreate(&n->ev_begin));
+      CUDA_CK(cudaEventCreate(&n->ev_scan0));
+      CUDA_CK(cudaEventCreate(&n->ev_scan1));
+      CUDA_CK(cudaEventCreate(&n->ev_end));
+      CUDA_CK(cudaEventCreateWithFlags(&n->ev_a, cudaEventDisableTiming));
+      CUDA_CK(cudaEventCreateWithFlags(&n->ev_b, cudaEventDisableTiming));
+      CUDA_CK(cudaEventCreateWithFlags(&n->ev_c, cudaEventDisableTiming));
+      CUDA_CK(cudaMalloc(&n->d_counters, 16 * sizeof(unsigned long long)));
+      CUDA_CK(cudaMallocHost(&n->h_counters, 48 * sizeof(unsigned long long)));
+      CUDA_CK(cudaMalloc(&n->d_plan, 64 * sizeof(uint64_t)));
+      CUDA_CK(cudaMallocHost(&n->h_plan, 64 * sizeof(uint64_t)));
+      sc = n.release();
+    }
+    if (user) {
+      cudaEvent_t ev = nullptr;   // a private event: ctx->ev_user would race between concurrent queries
+      CUDA_CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+      cudaEventRecord(ev, user);
+      cudaStreamWaitEvent(sc->s0, ev, 0);
+      cudaEventDestroy(ev);
+    }
+  }
+  ~ScopeLease() {
+    if (!sc) return;
+    // whatever happened (errors included), nothing of this query may still be running when the scope is reused
+    cudaStreamSynchronize(sc->s0);
+    cudaStreamSynchronize(sc->s1);
+    if (user) {
+      cudaEventRecord(sc->ev_c, sc->s0);
+      cudaStreamWaitEvent(user, sc->ev_c, 0);
+    }
+    std::lock_guard<std::mutex> lk(ctx->scope_mu);
+    ctx->idle_scopes.push_back(sc);
   }
 };
 
@@ -501,6 +604,7 @@ void compute_stats(vgpu_table *t, uint32_t seg_idx) {
     CUDA_CK(cudaGetLastError());
   }
   sd.stats_pending = true;
+  t->stats_dirty = true;
 }
 
 // (re)build the row-major mirror of a segment from its columns; stream-ordered after the column copies
@@ -554,6 +658,7 @@ void fetch_stats(vgpu_table *t) {
     }
     sd.stats_pending = false;
   }
+  t->stats_dirty = false;
 }
 
 void upload_descs(vgpu_table *t) {
@@ -713,7 +818,7 @@ struct Planner {
     if (mode == 0) push_depth();
     if (ci.bitset) {  // compares cardinality() (filter.cc:215-217)
       in.cls = C_GEN; in.gcls = G_CARD; in.gop = (uint8_t)op;
-      in.arg = widen_arg(raw_arg, ci.type) & (ci.width == 8 ? ~0ull : ((1ull << (8 * ci.width)) - 1));
+      in.arg = widen_arg(raw_arg, ci.lit_type);  // only the literal's own bytes of the AnyNum image are defined
       emit(in);
       return;
     }
@@ -1012,16 +1117,12 @@ int vgpu_init(int device, vgpu_ctx **out) {
     CUDA_CK(cudaGetDeviceProperties(&prop, device));
     ctx->sm_count = prop.multiProcessorCount;
     CUDA_CK(cudaFuncSetAttribute(scan_filter_groupby_kernel<3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemTableBytes));
+    CUDA_CK(cudaFuncSetAttribute(pairs_bucket_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * kMaxSmemBuckets * 4)));
+    CUDA_CK(cudaFuncSetAttribute(pairs_dedupe_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kSmemSetSlots * 8)));
     CUDA_CK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
     CUDA_CK(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
     CUDA_CK(cudaEventCreateWithFlags(&ctx->ev_copy, cudaEventDisableTiming));
-    CUDA_CK(cudaEventCreate(&ctx->ev_begin));
-    CUDA_CK(cudaEventCreate(&ctx->ev_scan0));
-    CUDA_CK(cudaEventCreate(&ctx->ev_scan1));
-    CUDA_CK(cudaEventCreate(&ctx->ev_end));
-    CUDA_CK(cudaMalloc(&ctx->d_counters, 16 * sizeof(unsigned long long)));
-    CUDA_CK(cudaMallocHost(&ctx->h_counters, 16 * sizeof(unsigned long long)));
-    CUDA_CK(cudaMalloc(&ctx->d_plan, 64 * sizeof(uint64_t)));
+    CUDA_CK(cudaEventCreateWithFlags(&ctx->ev_user, cudaEventDisableTiming));
     // keep freed scratch in the pool: repeated queries never go back to the driver
     cudaMemPool_t pool;
     CUDA_CK(cudaDeviceGetDefaultMemPool(&pool, device));
@@ -1031,6 +1132,11 @@ int vgpu_init(int device, vgpu_ctx **out) {
     ctx->trace = getenv("VGPU_TRACE") != nullptr;
     if (const char *e = getenv("VGPU_CTAS")) { int c = atoi(e); if (c >= 2 && c <= 4) ctx->ctas_per_sm = c; }
     if (const char *e = getenv("VGPU_UNIT_CHUNKS")) ctx->unit_chunks = (uint32_t)strtoul(e, nullptr, 0);
+    if (const char *e = getenv("VGPU_TEST_PAIRS_CAP")) ctx->test_pairs_cap = strtoull(e, nullptr, 0);
+    if (const char *e = getenv("VGPU_TEST_HASH_CAP")) ctx->test_hash_cap = strtoull(e, nullptr, 0);
+    if (const char *e = getenv("VGPU_TEST_BUCKET_PAIRS")) ctx->test_bucket_pairs = strtoull(e, nullptr, 0);
+    if (const char *e = getenv("VGPU_TEST_SMALL_PAIRS")) ctx->test_small_pairs = strtoull(e, nullptr, 0);
+    if (const char *e = getenv("VGPU_TEST_SET_SLOTS")) ctx->test_set_slots = (uint32_t)strtoul(e, nullptr, 0);
     // carve out the persisting part of L2 for group tables
     if (ctx->tune & 1u) {
       int max_persist = 0, max_window = 0;
@@ -1050,32 +1156,35 @@ int vgpu_init(int device, vgpu_ctx **out) {
 int vgpu_set_stream(vgpu_ctx *ctx, void *cuda_stream) {
   return guard([&] {
     if (!ctx) fail(VGPU_ERR_INVALID, "null context");
-    std::lock_guard<std::mutex> lk(ctx->mu);
-    CUDA_CK(cudaSetDevice(ctx->device));
-    if (ctx->own_stream && ctx->stream) {
-      CUDA_CK(cudaStreamSynchronize(ctx->stream));
-      CUDA_CK(cudaStreamDestroy(ctx->stream));
-    }
-    ctx->stream = static_cast<cudaStream_t>(cuda_stream);
-    ctx->own_stream = false;
+    std::lock_guard<std::mutex> lk(ctx->scope_mu);
+    ctx->user_stream = static_cast<cudaStream_t>(cuda_stream);
+  });
+}
+
+int vgpu_set_test_hook(vgpu_ctx *ctx, const char *name, uint64_t value) {
+  return guard([&] {
+    if (!ctx || !name) fail(VGPU_ERR_INVALID, "null argument");
+    const std::string n(name);
+    if (n == "pairs_cap") ctx->test_pairs_cap = value;
+    else if (n == "hash_cap") ctx->test_hash_cap = value;
+    else if (n == "bucket_pairs") ctx->test_bucket_pairs = value;
+    else if (n == "small_pairs") ctx->test_small_pairs = value;
+    else if (n == "set_slots") ctx->test_set_slots = (uint32_t)value;
+    else if (n == "tune") ctx->tune = (uint32_t)value;
+    else fail(VGPU_ERR_INVALID, "unknown test hook " + n);
   });
 }
 
 void vgpu_shutdown(vgpu_ctx *ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
-  if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+  cudaDeviceSynchronize();
   if (ctx->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(ctx->comm);
-  if (ctx->d_counters) cudaFree(ctx->d_counters);
-  if (ctx->d_plan) cudaFree(ctx->d_plan);
-  if (ctx->h_counters) cudaFreeHost(ctx->h_counters);
-  if (ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); }
+  for (QueryScope *sc : ctx->idle_scopes) destroy_scope(sc);
+  if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   if (ctx->ev_copy) cudaEventDestroy(ctx->ev_copy);
-  if (ctx->ev_begin) cudaEventDestroy(ctx->ev_begin);
-  if (ctx->ev_scan0) cudaEventDestroy(ctx->ev_scan0);
-  if (ctx->ev_scan1) cudaEventDestroy(ctx->ev_scan1);
-  if (ctx->ev_end) cudaEventDestroy(ctx->ev_end);
-  if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+  if (ctx->ev_user) cudaEventDestroy(ctx->ev_user);
+  if (ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
 
@@ -1092,6 +1201,8 @@ int vgpu_table_create(vgpu_ctx *ctx, const vgpu_schema *schema, vgpu_table **out
     if (schema->segment_size > (1ull << 31)) fail(VGPU_ERR_UNSUPPORTED, "segment_size above 2^31 rows");
     std::unique_ptr<vgpu_table> t(new vgpu_table());
     t->ctx = ctx;
+    CUDA_CK(cudaSetDevice(ctx->device));
+    CUDA_CK(cudaEventCreateWithFlags(&t->ev_put, cudaEventDisableTiming));
     t->ndims = schema->ndims;
     t->segment_size = schema->segment_size;
     uint64_t off = 0;
@@ -1099,6 +1210,8 @@ int vgpu_table_create(vgpu_ctx *ctx, const vgpu_schema *schema, vgpu_table **out
       const vgpu_column &sc = schema->cols[c];
       ColInfo ci{};
       ci.kind = sc.kind; ci.type = sc.type; ci.agg = sc.agg;
+      ci.lit_type = sc.lit_type ? sc.lit_type - 1 : sc.type;
+      if (ci.lit_type > VGPU_F64) fail(VGPU_ERR_INVALID, "bad literal type");
       const bool is_dim = c < schema->ndims;
       if (is_dim != (sc.kind <= VGPU_DIM_BOOLEAN))
         fail(VGPU_ERR_INVALID, "dimensions must precede metrics in the schema");
@@ -1123,9 +1236,7 @@ int vgpu_table_create(vgpu_ctx *ctx, const vgpu_schema *schema, vgpu_table **out
           ci.agg = VGPU_AGG_COUNT;
           break;
         case VGPU_METRIC_BITSET:
-          if (sc.type == VGPU_U64)
-            fail(VGPU_ERR_UNSUPPORTED, "64-bit bitset ids (Roaring64Map) are not supported yet");
-          if (sc.type > VGPU_U32) fail(VGPU_ERR_INVALID, "bitset ids are unsigned");
+          if (sc.type != VGPU_U32 && sc.type != VGPU_U64) fail(VGPU_ERR_INVALID, "bitset ids travel as uint32 or uint64");
           break;
         default:
           fail(VGPU_ERR_INVALID, "unknown column kind");
@@ -1171,7 +1282,8 @@ int vgpu_table_create(vgpu_ctx *ctx, const vgpu_schema *schema, vgpu_table **out
 void vgpu_table_free(vgpu_table *table) {
   if (!table) return;
   cudaSetDevice(table->ctx->device);
-  cudaStreamSynchronize(table->ctx->stream);
+  cudaDeviceSynchronize();
+  if (table->ev_put) cudaEventDestroy(table->ev_put);
   for (auto &sd : table->segs) free_segment(sd);
   if (table->d_segs) cudaFree(table->d_segs);
   if (table->d_stats) cudaFree(table->d_stats);
@@ -1183,7 +1295,8 @@ int vgpu_segment_put(vgpu_table *t, uint32_t seg_idx, uint64_t nrows, const void
   return guard([&] {
     if (!t || (!col_ptrs && nrows)) fail(VGPU_ERR_INVALID, "null argument");
     vgpu_ctx *ctx = t->ctx;
-    std::lock_guard<std::mutex> lk(ctx->mu);
+    std::lock_guard<std::mutex> put_lk(ctx->put_mu);
+    std::unique_lock<std::shared_mutex> lk(t->mu);
     CUDA_CK(cudaSetDevice(ctx->device));
     if (seg_idx > t->segs.size() + (1u << 20)) fail(VGPU_ERR_INVALID, "segment index too sparse");
     ensure_segment(t, seg_idx, nrows);
@@ -1200,7 +1313,8 @@ int vgpu_segment_put(vgpu_table *t, uint32_t seg_idx, uint64_t nrows, const void
         if (csr->offsets && csr->nvalues != nvalues) fail(VGPU_ERR_INVALID, "bitset CSR: nvalues != offsets[nrows]");
         if (!csr->offsets && csr->nvalues != nrows) fail(VGPU_ERR_INVALID, "bitset without offsets needs one id per row");
         if (nvalues >= (1ull << 32)) fail(VGPU_ERR_UNSUPPORTED, "more than 2^32 bitset ids in one segment");
-        bool one_per_row = true;
+        const uint32_t idw = ci.width == 8 ? 8u : 4u;   // 64-bit ids: util::Bitset<8> = Roaring64Map (bitset.h:27-31)
+        bool one_per_row = idw == 4;  // cells of 64-bit ids always go through CSR offsets (MetSpec::id64)
         if (csr->offsets) {
           if (csr->offsets[0] != 0) fail(VGPU_ERR_INVALID, "bitset CSR: offsets[0] != 0");
           for (uint64_t r = 0; r < nrows; ++r) {
@@ -1209,23 +1323,23 @@ int vgpu_segment_put(vgpu_table *t, uint32_t seg_idx, uint64_t nrows, const void
           }
         }
         // values padded to a whole tile so that speculative reads stay in bounds
-        uint64_t vcap = round_up(std::max<uint64_t>(nvalues, 1), kTileRows);
+        uint64_t vcap = round_up(std::max<uint64_t>(nvalues, 1), kTileRows) * (idw / 4);   // in uint32 words
         if (sd.bs_vcap[ci.bitset_idx] < vcap) {
           if (sd.bs_values[ci.bitset_idx]) cudaFree(sd.bs_values[ci.bitset_idx]);
           sd.bs_values[ci.bitset_idx] = nullptr;
           CUDA_CK(cudaMalloc(&sd.bs_values[ci.bitset_idx], vcap * 4));
           sd.bs_vcap[ci.bitset_idx] = vcap;
         }
-        if (sd.bs_vcap[ci.bitset_idx] > nvalues)
-          CUDA_CK(cudaMemsetAsync(sd.bs_values[ci.bitset_idx] + nvalues, 0, (sd.bs_vcap[ci.bitset_idx] - nvalues) * 4, cs));
+        if (sd.bs_vcap[ci.bitset_idx] * 4 > nvalues * idw)
+          CUDA_CK(cudaMemsetAsync(reinterpret_cast<uint8_t *>(sd.bs_values[ci.bitset_idx]) + nvalues * idw, 0,
+                                  sd.bs_vcap[ci.bitset_idx] * 4 - nvalues * idw, cs));
         if (nvalues)
-          CUDA_CK(cudaMemcpyAsync(sd.bs_values[ci.bitset_idx], csr->values, nvalues * 4,
-                                  cudaMemcpyHostToDevice, cs));
+          CUDA_CK(cudaMemcpyAsync(sd.bs_values[ci.bitset_idx], csr->values, nvalues * idw, cudaMemcpyHostToDevice, cs));
         sd.bs_n[ci.bitset_idx] = nvalues;
         if (!one_per_row) {
           keep.emplace_back(nrows + 1);
           auto &o32 = keep.back();
-          for (uint64_t r = 0; r <= nrows; ++r) o32[r] = (uint32_t)csr->offsets[r];
+          for (uint64_t r = 0; r <= nrows; ++r) o32[r] = csr->offsets ? (uint32_t)csr->offsets[r] : (uint32_t)r;
           if (sd.bs_ocap[ci.bitset_idx] < nrows + 1) {
             if (sd.bs_offsets[ci.bitset_idx]) cudaFree(sd.bs_offsets[ci.bitset_idx]);
             sd.bs_offsets[ci.bitset_idx] = nullptr;
@@ -1254,6 +1368,7 @@ int vgpu_segment_put(vgpu_table *t, uint32_t seg_idx, uint64_t nrows, const void
     CUDA_CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_copy, 0));
     compute_stats(t, seg_idx);
     build_row_mirror(t, seg_idx);
+    CUDA_CK(cudaEventRecord(t->ev_put, ctx->stream));
     CUDA_CK(cudaEventSynchronize(ctx->ev_copy));
     sd.valid = true;
   });
@@ -1264,7 +1379,8 @@ int vgpu_segment_generate(vgpu_table *t, uint32_t seg_idx, uint64_t nrows, const
   return guard([&] {
     if (!t || !gens) fail(VGPU_ERR_INVALID, "null argument");
     vgpu_ctx *ctx = t->ctx;
-    std::lock_guard<std::mutex> lk(ctx->mu);
+    std::lock_guard<std::mutex> put_lk(ctx->put_mu);
+    std::unique_lock<std::shared_mutex> lk(t->mu);
     CUDA_CK(cudaSetDevice(ctx->device));
     if (t->cols.size() > 32) fail(VGPU_ERR_UNSUPPORTED, "generator supports at most 32 columns");
     ensure_segment(t, seg_idx, nrows);
@@ -1291,6 +1407,7 @@ int vgpu_segment_generate(vgpu_table *t, uint32_t seg_idx, uint64_t nrows, const
       gc.is_f32 = ci.type == VGPU_F32;
       gc.is_f64 = ci.type == VGPU_F64;
       gc.bitset_out = nullptr;
+      if (ci.bitset && ci.width == 8) fail(VGPU_ERR_UNSUPPORTED, "the synthetic generator writes 32-bit bitset ids only");
       if (ci.bitset) {
         uint64_t vcap = round_up(std::max<uint64_t>(nrows, 1), kTileRows);
         if (sd.bs_vcap[ci.bitset_idx] < vcap) {
@@ -1311,6 +1428,7 @@ int vgpu_segment_generate(vgpu_table *t, uint32_t seg_idx, uint64_t nrows, const
     }
     compute_stats(t, seg_idx);
     build_row_mirror(t, seg_idx);
+    CUDA_CK(cudaEventRecord(t->ev_put, ctx->stream));
     sd.valid = true;
   });
 }
@@ -1319,7 +1437,8 @@ int vgpu_segment_read(vgpu_table *t, uint32_t seg_idx, uint32_t col, void *out) 
   return guard([&] {
     if (!t || !out) fail(VGPU_ERR_INVALID, "null argument");
     vgpu_ctx *ctx = t->ctx;
-    std::lock_guard<std::mutex> lk(ctx->mu);
+    std::lock_guard<std::mutex> put_lk(ctx->put_mu);
+    std::shared_lock<std::shared_mutex> lk(t->mu);
     CUDA_CK(cudaSetDevice(ctx->device));
     if (seg_idx >= t->segs.size() || !t->segs[seg_idx].valid) fail(VGPU_ERR_STATE, "no such segment");
     if (col >= t->cols.size()) fail(VGPU_ERR_INVALID, "column index out of range");
@@ -1327,7 +1446,7 @@ int vgpu_segment_read(vgpu_table *t, uint32_t seg_idx, uint32_t col, void *out) 
     const ColInfo &ci = t->cols[col];
     if (ci.bitset) {
       if (sd.bs_n[ci.bitset_idx])
-        CUDA_CK(cudaMemcpyAsync(out, sd.bs_values[ci.bitset_idx], sd.bs_n[ci.bitset_idx] * 4,
+        CUDA_CK(cudaMemcpyAsync(out, sd.bs_values[ci.bitset_idx], sd.bs_n[ci.bitset_idx] * (ci.width == 8 ? 8 : 4),
                                 cudaMemcpyDeviceToHost, ctx->stream));
     } else if (sd.nrows) {
       CUDA_CK(cudaMemcpyAsync(out, sd.slab + ci.off_per_row * sd.cap, sd.nrows * ci.width,
@@ -1340,7 +1459,8 @@ int vgpu_segment_read(vgpu_table *t, uint32_t seg_idx, uint32_t col, void *out) 
 int vgpu_table_invalidate(vgpu_table *t, uint32_t seg_idx) {
   return guard([&] {
     if (!t) fail(VGPU_ERR_INVALID, "null table");
-    std::lock_guard<std::mutex> lk(t->ctx->mu);
+    std::lock_guard<std::mutex> put_lk(t->ctx->put_mu);
+    std::unique_lock<std::shared_mutex> lk(t->mu);   // no query is using the segment any more
     if (seg_idx >= t->segs.size()) fail(VGPU_ERR_STATE, "no such segment");
     CUDA_CK(cudaSetDevice(t->ctx->device));
     CUDA_CK(cudaStreamSynchronize(t->ctx->stream));
@@ -1368,9 +1488,10 @@ uint64_t vgpu_table_bytes(const vgpu_table *t) {
     if (!sd.valid) continue;
     n += sd.cap * t->row_bytes;
     if (sd.rows) n += sd.rows_cap * t->row_stride;
-    for (int b = 0; b < kMaxBitsetCols; ++b) {
-      n += sd.bs_n[b] * 4;
-      if (sd.bs_has_offsets[b]) n += (sd.nrows + 1) * 4;
+    for (const ColInfo &ci : t->cols) {
+      if (!ci.bitset) continue;
+      n += sd.bs_n[ci.bitset_idx] * (ci.width == 8 ? 8 : 4);
+      if (sd.bs_has_offsets[ci.bitset_idx]) n += (sd.nrows + 1) * 4;
     }
   }
   return n;
@@ -1442,7 +1563,6 @@ void set_work_list(vgpu_table *t, QueryRun &q, Scratch &scratch, cudaStream_t st
   P.tiles_per_seg = (uint32_t)std::max<uint64_t>(1, (max_rows + kChunkRows - 1) / kChunkRows);
   P.nactive = (uint32_t)q.active.size();
   P.total_tiles = (uint64_t)P.nactive * P.tiles_per_seg;
-  upload_descs(t);
   P.segs = t->d_segs;
   P.tune = t->ctx->tune;
   uint32_t *d_active = scratch.alloc<uint32_t>(q.active.size());
@@ -1488,952 +1608,9 @@ int find_hidden_count(const vgpu_table *t) {
   return -1;
 }
 
-// ---- multi-GPU merge of partial group tables (dense mode) ----
-void nccl_merge_dense(vgpu_ctx *ctx, QueryRun &q, ScanParams &P, std::vector<void *> &acc_ptrs) {
-  NCCL_CK(g_nccl.GroupStart());
-  for (size_t m = 0; m < q.accs.size(); ++m) {
-    if (q.accs[m].op == A_DISTINCT) continue;
-    NCCL_CK(g_nccl.AllReduce(acc_ptrs[m], acc_ptrs[m], q.ncells, q.accs[m].nccl_type, q.accs[m].nccl_op,
-                             ctx->comm, ctx->stream));
-  }
-  NCCL_CK(g_nccl.AllReduce(P.present, P.present, q.ncells, ncclUint8, ncclMax, ctx->comm, ctx->stream));
-  NCCL_CK(g_nccl.GroupEnd());
-}
-
-// bucket sizes of every rank: matrix[r * G + o] = entries rank r holds for owner o
-std::vector<uint64_t> exchange_counts(vgpu_ctx *ctx, unsigned long long *d_cursors, Scratch &scratch) {
-  const int G = ctx->nranks;
-  uint64_t *d_matrix = scratch.alloc<uint64_t>((uint64_t)G * G);
-  NCCL_CK(g_nccl.AllGather(d_cursors, d_matrix, G, ncclUint64, ctx->comm, ctx->stream));
-  std::vector<uint64_t> matrix((size_t)G * G);
-  CUDA_CK(cudaMemcpyAsync(matrix.data(), d_matrix, matrix.size() * 8, cudaMemcpyDeviceToHost, ctx->stream));
-  CUDA_CK(cudaStreamSynchronize(ctx->stream));
-  return matrix;
-}
-
-// all-to-all of one bucketed array: rank `me` sends bucket o (matrix[me][o] elements) to rank o and
-// receives matrix[r][me] elements from every r into recv + recv_off[r]. Must be called inside a group.
-void exchange_array(vgpu_ctx *ctx, const void *send, uint64_t bucket_cap, uint32_t elem, void *recv,
-                    const std::vector<uint64_t> &matrix, const std::vector<uint64_t> &recv_off) {
-  const int G = ctx->nranks, me = ctx->rank;
-  const uint8_t *sb = static_cast<const uint8_t *>(send);
-  uint8_t *rb = static_cast<uint8_t *>(recv);
-  for (int r = 0; r < G; ++r) {
-    const uint64_t ns = matrix[(size_t)me * G + r], nr = matrix[(size_t)r * G + me];
-    if (r == me) {
-      if (ns) CUDA_CK(cudaMemcpyAsync(rb + recv_off[r] * elem, sb + (uint64_t)r * bucket_cap * elem, ns * elem,
-                                      cudaMemcpyDeviceToDevice, ctx->stream));
-      continue;
-    }
-    if (ns) NCCL_CK(g_nccl.Send(sb + (uint64_t)r * bucket_cap * elem, ns * elem, ncclUint8, r, ctx->comm, ctx->stream));
-    if (nr) NCCL_CK(g_nccl.Recv(rb + recv_off[r] * elem, nr * elem, ncclUint8, r, ctx->comm, ctx->stream));
-  }
-}
-
-// Deduplicate the (cell,id) pairs of one count-distinct metric and count them per cell.
-// Input: ragged per-CTA regions (d_counts != nullptr) or `total` contiguous pairs. The pairs are hash-
-// partitioned into buckets whose open-addressing sets fit L2, then each bucket is inserted; a pair seen
-// for the first time bumps distinct[cell] and, if asked, lands in `unique_out`.
-void dedupe_pairs(vgpu_ctx *ctx, Scratch &scratch, const uint64_t *pairs, const uint32_t *d_counts, uint32_t nregions,
-                  uint32_t region_cap, uint64_t total, uint8_t *distinct, uint32_t stride, uint64_t *unique_out,
-                  unsigned long long *d_unique_n, uint32_t &launches) {
-  if (total == 0) return;
-  cudaStream_t stream = ctx->stream;
-  const uint64_t kBucketPairs = 1ull << 21;  // 2^22-slot set = 32 MB: stays in the 126 MB L2
-  uint32_t B = (uint32_t)std::min<uint64_t>(pow2_ceil((total + kBucketPairs - 1) / kBucketPairs), kMaxBuckets);
-  PairsDedupeParams D{};
-  D.distinct = distinct;
-  D.stride = stride;
-  D.unique_out = unique_out;
-  D.unique_n = d_unique_n;
-  if (B <= 1) {
-    const uint64_t set_cap = pow2_ceil(std::max<uint64_t>(2 * total, 1024));
-    uint64_t *set = scratch.alloc<uint64_t>(set_cap);
-    CUDA_CK(cudaMemsetAsync(set, 0xff, set_cap * 8, stream));
-    D.pairs = pairs;
-    D.counts = d_counts;
-    D.nregions = nregions;
-    D.region_cap = region_cap;
-    D.n = total;
-    D.set = set;
-    D.set_mask = set_cap - 1;
-    const int grid = d_counts ? (int)std::min<uint32_t>(nregions, ctx->sm_count * 8) : grid_for(total, 256, ctx->sm_count);
-    pairs_dedupe_kernel<<<std::max(grid, 1), 256, 0, stream>>>(D);
-    CUDA_CK(cudaGetLastError());
-    ++launches;
-    return;
-  }
-  // 1. partition
-  uint64_t bucket_cap = total / B + total / B / 8 + 8192;
-  unsigned long long *cursors = scratch.alloc<unsigned long long>(kMaxBuckets + 1);
-  std::vector<unsigned long long> h_cursors(kMaxBuckets + 1);
-  uint64_t *buckets = nullptr;
-  for (int attempt = 0; attempt < 2; ++attempt) {
-    buckets = scratch.alloc<uint64_t>(bucket_cap * B);
-    CUDA_CK(cudaMemsetAsync(cursors, 0, (kMaxBuckets + 1) * sizeof(unsigned long long), stream));
-    PairsPartitionParams A{};
-    A.pairs = pairs;
-    A.counts = d_counts;
-    A.total = total;
-    if (d_counts) {
-      A.nregions = nregions;
-      A.region_cap = region_cap;
-    } else {
-      A.region_cap = 1u << 16;
-      A.nregions = (uint32_t)((total + A.region_cap - 1) / A.region_cap);
-    }
-    A.nbuckets = B;
-    A.shift = 40;
-    A.bucket_cap = bucket_cap;
-    A.cursors = cursors;
-    A.out = buckets;
-    A.overflow = cursors + kMaxBuckets;
-    pairs_partition_kernel<<<(int)std::min<uint32_t>(A.nregions, ctx->sm_count * 8), 256, 0, stream>>>(A);
-    CUDA_CK(cudaGetLastError());
-    ++launches;
-    CUDA_CK(cudaMemcpyAsync(h_cursors.data(), cursors, (kMaxBuckets + 1) * sizeof(unsigned long long),
-                            cudaMemcpyDeviceToHost, stream));
-    CUDA_CK(cudaStreamSynchronize(stream));
-    if (h_cursors[kMaxBuckets] == 0) break;
-    if (attempt == 1) fail(VGPU_ERR_CUDA, "count-distinct partitioning overflowed twice");
-    bucket_cap = 0;  // a skewed hash bucket: size every bucket for the largest one and scatter again
-    for (uint32_t b = 0; b < B; ++b) bucket_cap = std::max<uint64_t>(bucket_cap, h_cursors[b]);
-  }
-  // 2. one L2-resident set, reused bucket after bucket
-  uint64_t max_n = 0;
-  for (uint32_t b = 0; b < B; ++b) max_n = std::max<uint64_t>(max_n, h_cursors[b]);
-  const uint64_t set_cap_max = pow2_ceil(std::max<uint64_t>(2 * max_n, 1024));
-  uint64_t *set = scratch.alloc<uint64_t>(set_cap_max);
-  for (uint32_t b = 0; b < B; ++b) {
-    const uint64_t n = h_cursors[b];
-    if (n == 0) continue;
-    const uint64_t set_cap = pow2_ceil(std::max<uint64_t>(2 * n, 1024));
-    CUDA_CK(cudaMemsetAsync(set, 0xff, set_cap * 8, stream));
-    D.pairs = buckets + (uint64_t)b * bucket_cap;
-    D.counts = nullptr;
-    D.n = n;
-    D.set = set;
-    D.set_mask = set_cap - 1;
-    pairs_dedupe_kernel<<<grid_for(n, 256, ctx->sm_count), 256, 0, stream>>>(D);
-    CUDA_CK(cudaGetLastError());
-    ++launches;
-  }
-}
-
-// count-distinct across ranks (dense group table): the (cell,id) sets of all ranks are united. Every
-// rank dedupes its own pairs, each unique pair travels to the rank that owns its cell, owners dedupe
-// and count, one sum-allreduce of the per-cell counts gives every rank the full answer. Per-rank work
-// stays constant as ranks are added.
-void nccl_merge_distinct(vgpu_ctx *ctx, Scratch &scratch, const uint64_t *regions, const uint32_t *d_counts,
-                         uint32_t nregions, uint32_t region_cap, uint64_t total_pairs, uint32_t *distinct,
-                         uint64_t acc_cells, uint32_t &launches) {
-  const int G = ctx->nranks, me = ctx->rank;
-  cudaStream_t stream = ctx->stream;
-  // 1. straight from the scan's per-CTA regions to one bucket per owner rank (no local dedupe pass: the
-  //    owners dedupe anyway, and an extra pass over the pairs costs more than the duplicates it would save)
-  uint64_t bucket_cap = total_pairs / G + total_pairs / G / 4 + 65536;
-  unsigned long long *cursors = scratch.alloc<unsigned long long>(kMaxBuckets + 1);
-  std::vector<unsigned long long> h_cursors(kMaxBuckets + 1);
-  uint64_t *send = nullptr;
-  for (int attempt = 0; attempt < 2; ++attempt) {
-    send = scratch.alloc<uint64_t>(bucket_cap * G);
-    CUDA_CK(cudaMemsetAsync(cursors, 0, (kMaxBuckets + 1) * sizeof(unsigned long long), stream));
-    PairsPartitionParams A{};
-    A.pairs = regions;
-    A.counts = d_counts;
-    A.total = total_pairs;
-    A.nregions = nregions;
-    A.region_cap = region_cap;
-    A.nbuckets = (uint32_t)G;
-    A.owner_parts = (uint32_t)G;
-    A.bucket_cap = bucket_cap;
-    A.cursors = cursors;
-    A.out = send;
-    A.overflow = cursors + kMaxBuckets;
-    pairs_partition_kernel<<<(int)std::min<uint32_t>(std::max<uint32_t>(nregions, 1), ctx->sm_count * 8), 256, 0, stream>>>(A);
-    CUDA_CK(cudaGetLastError());
-    ++launches;
-    // every rank must take the same retry decision (the exchange below is collective)
-    NCCL_CK(g_nccl.AllReduce(cursors + kMaxBuckets, cursors + kMaxBuckets, 1, ncclUint64, ncclMax, ctx->comm, stream));
-    CUDA_CK(cudaMemcpyAsync(h_cursors.data(), cursors, (kMaxBuckets + 1) * sizeof(unsigned long long),
-                            cudaMemcpyDeviceToHost, stream));
-    CUDA_CK(cudaStreamSynchronize(stream));
-    if (h_cursors[kMaxBuckets] == 0) break;
-    if (attempt == 1) fail(VGPU_ERR_CUDA, "count-distinct owner partitioning overflowed twice");
-    bucket_cap = total_pairs + 1;  // skewed owners: room for everything in every bucket
-  }
-  std::vector<uint64_t> matrix = exchange_counts(ctx, cursors, scratch);
-  std::vector<uint64_t> recv_off(G);
-  uint64_t total = 0;
-  for (int r = 0; r < G; ++r) { recv_off[r] = total; total += matrix[(size_t)r * G + me]; }
-  uint64_t *recv = scratch.alloc<uint64_t>(total);
-  NCCL_CK(g_nccl.GroupStart());
-  exchange_array(ctx, send, bucket_cap, 8, recv, matrix, recv_off);
-  NCCL_CK(g_nccl.GroupEnd());
-  // 3. owners dedupe what they received and count per cell; 4. everybody gets every count
-  CUDA_CK(cudaMemsetAsync(distinct, 0, acc_cells * 4, stream));
-  dedupe_pairs(ctx, scratch, recv, nullptr, 0, 0, total, reinterpret_cast<uint8_t *>(distinct), 4, nullptr, nullptr, launches);
-  NCCL_CK(g_nccl.AllReduce(distinct, distinct, acc_cells, ncclUint32, ncclSum, ctx->comm, stream));
-}
-
-// hashed group tables across ranks: every (packed key, partial accumulators) record travels to the
-// rank that owns the key, owners merge with the same Update() as the scan, then the owned groups are
-// all-gathered so that every rank returns the full result. On return P / acc_ptrs / acc_cells
-// describe a table that holds ALL groups of all ranks (rebuilt from the gathered records).
-void nccl_merge_hash(vgpu_ctx *ctx, QueryRun &q, ScanParams &P, std::vector<void *> &acc_ptrs, Scratch &scratch,
-                     uint64_t &acc_cells, uint32_t &launches) {
-  const int G = ctx->nranks, me = ctx->rank;
-  cudaStream_t stream = ctx->stream;
-  const size_t nm = q.accs.size();
-  // how many groups does this rank hold?
-  ExtractParams E{};
-  E.ncells = acc_cells;
-  E.hash_mode = 1;
-  E.hkeys = P.hkeys;
-  E.present = P.present;
-  E.hkey_stride = P.hkey_stride;
-  E.present_stride = P.present_stride;
-  E.count_only = 1;
-  unsigned long long *d_n = scratch.alloc<unsigned long long>(1);
-  CUDA_CK(cudaMemsetAsync(d_n, 0, 8, stream));
-  E.counter = d_n;
-  extract_groups_kernel<<<grid_for(acc_cells, 256, ctx->sm_count), 256, 0, stream>>>(E);
-  CUDA_CK(cudaGetLastError());
-  ++launches;
-  uint64_t n_local = 0;
-  CUDA_CK(cudaMemcpyAsync(&n_local, d_n, 8, cudaMemcpyDeviceToHost, stream));
-  CUDA_CK(cudaStreamSynchronize(stream));
-
-  auto run_exchange = [&](const uint64_t *keys, uint64_t nslots, uint64_t sentinel_slot, const uint8_t *sentinel_present,
-                          const std::vector<void *> &src, uint64_t n_hint, bool all_to_root_of_key,
-                          uint64_t *&out_keys, std::vector<void *> &out_acc) -> uint64_t {
-    (void)all_to_root_of_key;
-    const uint64_t bucket_cap = std::max<uint64_t>(n_hint, 1);
-    unsigned long long *cursors = scratch.alloc<unsigned long long>(kMaxParts);
-    CUDA_CK(cudaMemsetAsync(cursors, 0, kMaxParts * sizeof(unsigned long long), stream));
-    uint64_t *send_keys = scratch.alloc<uint64_t>(bucket_cap * G);
-    std::vector<void *> send_acc(nm);
-    PartitionParams A{};
-    A.keys = keys;
-    A.nslots = nslots;
-    A.sentinel_slot = sentinel_slot;
-    A.sentinel_present = sentinel_present;
-    A.nparts = (uint32_t)G;
-    A.owner_shift = 0;
-    A.bucket_cap = bucket_cap;
-    A.cursors = cursors;
-    A.out_keys = send_keys;
-    A.npay = (uint32_t)nm;
-    for (size_t m = 0; m < nm; ++m) {
-      send_acc[m] = scratch.alloc<uint8_t>(bucket_cap * G * q.accs[m].acc_width);
-      A.pay_width[m] = q.accs[m].acc_width;
-      A.pay_src[m] = src[m];
-      A.pay_dst[m] = send_acc[m];
-    }
-    partition_table_kernel<<<grid_for(nslots + 1, 256 * kPartPerThread, ctx->sm_count, 8), 256, 0, stream>>>(A);
-    CUDA_CK(cudaGetLastError());
-    ++launches;
-    std::vector<uint64_t> matrix = exchange_counts(ctx, cursors, scratch);
-    std::vector<uint64_t> recv_off(G);
-    uint64_t total = 0;
-    for (int r = 0; r < G; ++r) { recv_off[r] = total; total += matrix[(size_t)r * G + me]; }
-    out_keys = scratch.alloc<uint64_t>(total);
-    out_acc.resize(nm);
-    for (size_t m = 0; m < nm; ++m) out_acc[m] = scratch.alloc<uint8_t>(total * q.accs[m].acc_width);
-    NCCL_CK(g_nccl.GroupStart());
-    exchange_array(ctx, send_keys, bucket_cap, 8, out_keys, matrix, recv_off);
-    for (size_t m = 0; m < nm; ++m)
-      exchange_array(ctx, send_acc[m], bucket_cap, q.accs[m].acc_width, out_acc[m], matrix, recv_off);
-    NCCL_CK(g_nccl.GroupEnd());
-    return total;
-  };
-
-  // build a fresh table from records
-  auto build_table = [&](const uint64_t *keys, const std::vector<void *> &src, uint64_t n, uint64_t cap) {
-    uint64_t block_bytes = 0;
-    auto carve = [&](uint64_t bytes) { uint64_t o = block_bytes; block_bytes += round_up(bytes, 256); return o; };
-    const uint64_t o_h = carve(cap * 8), o_p = carve(16);
-    std::vector<uint64_t> o_a(nm);
-    for (size_t m = 0; m < nm; ++m) o_a[m] = carve((cap + 1) * q.accs[m].acc_width);
-    uint8_t *block = scratch.alloc<uint8_t>(block_bytes);
-    MergeParams M{};
-    M.keys = keys;
-    M.n = n;
-    M.nmets = (uint32_t)nm;
-    M.hkeys = reinterpret_cast<uint64_t *>(block + o_h);
-    M.hmask = cap - 1;
-    M.present = block + o_p;
-    M.max_probe = (uint32_t)std::min<uint64_t>(cap, 1u << 20);
-    M.overflow = scratch.alloc<unsigned long long>(1);
-    CUDA_CK(cudaMemsetAsync(M.overflow, 0, 8, stream));
-    fill64(stream, ctx->sm_count, M.hkeys, cap, kEmptyKey);
-    CUDA_CK(cudaMemsetAsync(M.present, 0, 16, stream));
-    for (size_t m = 0; m < nm; ++m) {
-      M.ops[m] = q.accs[m].op;
-      M.widths[m] = q.accs[m].acc_width;
-      M.src[m] = src[m];
-      M.acc[m] = block + o_a[m];
-      if (q.accs[m].acc_width == 4) launches += fill32(stream, ctx->sm_count, M.acc[m], cap + 1, (uint32_t)q.accs[m].init);
-      else launches += fill64(stream, ctx->sm_count, M.acc[m], cap + 1, q.accs[m].init);
-    }
-    if (n) {
-      merge_records_kernel<<<grid_for(n, 256, ctx->sm_count), 256, 0, stream>>>(M);
-      CUDA_CK(cudaGetLastError());
-      ++launches;
-    }
-    P.hkeys = M.hkeys;
-    P.hkey_stride = 8;
-    P.hmask = M.hmask;
-    P.present = M.present;
-    P.present_stride = 1;
-    for (size_t m = 0; m < nm; ++m) {
-      acc_ptrs[m] = M.acc[m];
-      P.mets[m].acc = M.acc[m];
-      P.mets[m].stride = q.accs[m].acc_width;
-    }
-    acc_cells = cap + 1;
-  };
-
-  // 1. records to their owners, owners merge
-  uint64_t *own_keys = nullptr;
-  std::vector<void *> own_acc;
-  const uint64_t n_owned_in = run_exchange(P.hkeys, P.hmask + 1, P.hmask + 1, P.present, acc_ptrs, n_local, false, own_keys, own_acc);
-  build_table(own_keys, own_acc, n_owned_in, pow2_ceil(std::max<uint64_t>(2 * n_owned_in, 1024)));
-
-  // 2. all-gather the owned groups: every rank sends its whole (merged) table to every rank
-  //    (bucket routing with owner := destination is not needed: broadcast each table's live records)
-  //    live records of this rank, compacted:
-  uint64_t *send_keys = nullptr;
-  std::vector<void *> send_acc;
-  {
-    // reuse the partition kernel with ONE bucket to compact the merged table
-    const uint64_t cap = P.hmask + 1;
-    unsigned long long *cursor = scratch.alloc<unsigned long long>(kMaxParts);
-    CUDA_CK(cudaMemsetAsync(cursor, 0, kMaxParts * sizeof(unsigned long long), stream));
-    const uint64_t bucket_cap = std::max<uint64_t>(n_owned_in, 1);
-    send_keys = scratch.alloc<uint64_t>(bucket_cap);
-    send_acc.resize(nm);
-    PartitionParams A{};
-    A.keys = P.hkeys;
-    A.nslots = cap;
-    A.sentinel_slot = cap;
-    A.sentinel_present = P.present;
-    A.nparts = 1;
-    A.owner_shift = 0;
-    A.bucket_cap = bucket_cap;
-    A.cursors = cursor;
-    A.out_keys = send_keys;
-    A.npay = (uint32_t)nm;
-    for (size_t m = 0; m < nm; ++m) {
-      send_acc[m] = scratch.alloc<uint8_t>(bucket_cap * q.accs[m].acc_width);
-      A.pay_width[m] = q.accs[m].acc_width;
-      A.pay_src[m] = acc_ptrs[m];
-      A.pay_dst[m] = send_acc[m];
-    }
-    partition_table_kernel<<<grid_for(cap + 1, 256 * kPartPerThread, ctx->sm_count, 8), 256, 0, stream>>>(A);
-    CUDA_CK(cudaGetLastError());
-    ++launches;
-    // group counts of every rank
-    uint64_t *d_all = scratch.alloc<uint64_t>(G);
-    NCCL_CK(g_nccl.AllGather(cursor, d_all, 1, ncclUint64, ctx->comm, stream));
-    std::vector<uint64_t> counts(G);
-    CUDA_CK(cudaMemcpyAsync(counts.data(), d_all, G * 8, cudaMemcpyDeviceToHost, stream));
-    CUDA_CK(cudaStreamSynchronize(stream));
-    std::vector<uint64_t> off(G);
-    uint64_t total = 0;
-    for (int r = 0; r < G; ++r) { off[r] = total; total += counts[r]; }
-    uint64_t *all_keys = scratch.alloc<uint64_t>(total);
-    std::vector<void *> all_acc(nm);
-    for (size_t m = 0; m < nm; ++m) all_acc[m] = scratch.alloc<uint8_t>(total * q.accs[m].acc_width);
-    NCCL_CK(g_nccl.GroupStart());
-    for (int r = 0; r < G; ++r) {
-      if (counts[r] == 0) continue;
-      NCCL_CK(g_nccl.Broadcast(send_keys, all_keys + off[r], counts[r] * 8, ncclUint8, r, ctx->comm, stream));
-      for (size_t m = 0; m < nm; ++m) {
-        const uint32_t w = q.accs[m].acc_width;
-        NCCL_CK(g_nccl.Broadcast(send_acc[m], static_cast<uint8_t *>(all_acc[m]) + off[r] * w, counts[r] * w, ncclUint8, r,
-                                 ctx->comm, stream));
-      }
-    }
-    NCCL_CK(g_nccl.GroupEnd());
-    // 3. the full table, identical on every rank (keys are disjoint between owners: plain inserts)
-    build_table(all_keys, all_acc, total, pow2_ceil(std::max<uint64_t>(2 * total, 1024)));
-  }
-}
-
 }  // namespace
 
-int vgpu_query_agg(vgpu_table *t, const vgpu_plan *plan, vgpu_result **out) {
-  return guard([&] {
-    if (!t || !plan || !out) fail(VGPU_ERR_INVALID, "null argument");
-    *out = nullptr;
-    vgpu_ctx *ctx = t->ctx;
-    std::lock_guard<std::mutex> lk(ctx->mu);
-    CUDA_CK(cudaSetDevice(ctx->device));
-    cudaStream_t stream = ctx->stream;
-    validate_plan(t, plan);
-
-    fetch_stats(t);
-    QueryRun q(t, plan);
-    Planner &pl = q.planner;
-    ScanParams &P = pl.P;
-    finish_predicate_and_prune(ctx, t, q);
-
-    // ---- keys ----
-    P.nkeys = plan->nkeys;
-    q.ranges.resize(plan->nkeys);
-    for (uint32_t k = 0; k < plan->nkeys; ++k) {
-      const vgpu_key &key = plan->keys[k];
-      const ColInfo &ci = t->cols[key.col];
-      if (ci.bitset) fail(VGPU_ERR_INVALID, "bitset column as a key");
-      KeySpec &ks = P.keys[k];
-      ks.slot = (uint8_t)pl.slot_of(key.col);
-      ks.rollup = key.nrules > 0 || key.query_granularity != VGPU_TU_NONE;
-      ks.micro = ci.kind == VGPU_DIM_MICROTIME;
-      ks.nrules = (uint8_t)key.nrules;
-      ks.query_unit = (uint8_t)key.query_granularity;
-      for (uint32_t r = 0; r < key.nrules; ++r) {
-        ks.rule_unit[r] = (uint8_t)key.rule_granularity[r];
-        ks.rule_boundary[r] = key.rule_boundary[r];
-      }
-    }
-    // value range of every key over the active segments (ordered domain). With several ranks the
-    // ranges — hence the cell numbering / key packing — must be the same everywhere: min-reduce them.
-    std::vector<uint64_t> kmin(plan->nkeys, ~0ull), kmax(plan->nkeys, 0ull);
-    for (uint32_t k = 0; k < plan->nkeys; ++k) {
-      const uint32_t col = plan->keys[k].col;
-      for (uint32_t s : q.active) {
-        const SegmentData &sd = t->segs[s];
-        if (sd.nrows == 0) continue;
-        kmin[k] = std::min(kmin[k], sd.omin[col]);
-        kmax[k] = std::max(kmax[k], sd.omax[col]);
-      }
-    }
-    uint64_t global_active_rows = q.active_rows;
-    if (ctx->nranks > 1) {
-      std::vector<uint64_t> h(2 * plan->nkeys + 1);
-      for (uint32_t k = 0; k < plan->nkeys; ++k) { h[2 * k] = kmin[k]; h[2 * k + 1] = ~kmax[k]; }
-      h[2 * plan->nkeys] = ~q.active_rows;  // min of complements == complement of the max
-      uint64_t *d = ctx->d_plan;
-      CUDA_CK(cudaMemcpyAsync(d, h.data(), h.size() * 8, cudaMemcpyHostToDevice, stream));
-      NCCL_CK(g_nccl.AllReduce(d, d, h.size(), ncclUint64, ncclMin, ctx->comm, stream));
-      CUDA_CK(cudaMemcpyAsync(h.data(), d, h.size() * 8, cudaMemcpyDeviceToHost, stream));
-      CUDA_CK(cudaStreamSynchronize(stream));
-      for (uint32_t k = 0; k < plan->nkeys; ++k) { kmin[k] = h[2 * k]; kmax[k] = ~h[2 * k + 1]; }
-      global_active_rows = ~h[2 * plan->nkeys] * (uint64_t)ctx->nranks;  // upper bound, same on every rank
-    }
-    for (uint32_t k = 0; k < plan->nkeys; ++k) {
-      const ColInfo &ci = t->cols[plan->keys[k].col];
-      const KeySpec &ks = P.keys[k];
-      KeyRange kr{0, 1};
-      if (type_float(ci.type)) {
-        kr.lo = 0;
-        kr.range = ci.width == 4 ? (1ull << 32) : 0;  // keyed by raw bits
-      } else if (kmin[k] <= kmax[k]) {
-        uint64_t lo = from_ordered_int(kmin[k], ci.type), hi = from_ordered_int(kmax[k], ci.type);
-        if (ks.rollup) {  // truncation only moves values down, at most to the start of their year
-          if (ks.micro) lo = host_trunc_year_seconds(lo / 1000000ull) * 1000000ull;
-          else lo = host_trunc_year_seconds(lo);
-        }
-        // A top-level conjunction restricts what a key can be for passing rows: tighten the key domain
-        // (unsigned keys of at most 4 bytes, no rollup; leaf arguments are raw zero-extended values).
-        uint64_t lut = 0;
-        if (P.conj && !ks.rollup && !type_signed(ci.type) && ci.width <= 4 && !(ctx->tune & 16384u)) {
-          for (uint32_t i = 0; i < P.nprog; ++i) {
-            const PInstr &in = P.prog[i];
-            if (in.slot != ks.slot || in.neg) continue;
-            const uint64_t a = (uint32_t)in.arg;
-            if (in.cls == C_EQ32) { lo = std::max(lo, a); hi = std::min(hi, a); }
-            else if (in.cls == C_RNG32 && in.bias == 0) { lo = std::max(lo, a); hi = std::min(hi, a + in.arg2 - 1); }
-            else if (in.cls == C_LT32 && in.bias == 0 && a > 0) { hi = std::min(hi, a - 1); }
-            else if (in.cls == C_LUT64) lut = lut ? (lut & in.arg) : in.arg;
-          }
-          if (lo > hi) hi = lo;  // nothing can pass: any one-value domain will do
-          if (lut) {
-            for (uint32_t b = 0; b < 64; ++b)
-              if (b < lo || b > hi) lut &= ~(1ull << b);
-          }
-        }
-        kr.lo = lo;
-        kr.range = hi - lo + 1;  // wraps to 0 for the full 64-bit domain
-        if (lut) { kr.lo = 0; kr.range = (uint64_t)__builtin_popcountll(lut); }
-        P.keys[k].lut = lut;
-      }
-      q.ranges[k] = kr;
-    }
-
-    // ---- metrics ----
-    const int hidden_col = find_hidden_count(t);
-    if (plan->need_hidden_count && hidden_col < 0)
-      fail(VGPU_ERR_INVALID, "plan needs the hidden count column but the table has none");
-    for (uint32_t m = 0; m < plan->nmetrics; ++m) {
-      q.acc_cols.push_back(plan->metric_cols[m]);
-      q.accs.push_back(acc_for(t->cols[plan->metric_cols[m]]));
-    }
-    if (plan->need_hidden_count) {
-      q.acc_cols.push_back((uint32_t)hidden_col);
-      q.accs.push_back(acc_for(t->cols[hidden_col]));
-    }
-    P.nmetrics = (uint32_t)q.accs.size();
-    P.ndistinct = 0;
-    for (uint32_t m = 0; m < P.nmetrics; ++m) {
-      P.mets[m].slot = (uint8_t)pl.slot_of(q.acc_cols[m]);
-      P.mets[m].op = (uint8_t)q.accs[m].op;
-      if (q.accs[m].op == A_DISTINCT) {
-        if (P.ndistinct >= kMaxDistinct) fail(VGPU_ERR_UNSUPPORTED, "too many count-distinct metrics in one query");
-        P.distinct_met[P.ndistinct++] = (uint8_t)m;
-      }
-    }
-
-    for (uint32_t k = 0; k < P.nkeys; ++k) {
-      const Slot &sl = P.slots[P.keys[k].slot];
-      P.keys[k].col_off = sl.off; P.keys[k].vmask = sl.vmask; P.keys[k].signbit = sl.signbit;
-      P.keys[k].width = sl.width; P.keys[k].row_off = sl.row_off;
-    }
-    for (uint32_t m = 0; m < P.nmetrics; ++m) {
-      const Slot &sl = P.slots[P.mets[m].slot];
-      P.mets[m].col_off = sl.off; P.mets[m].vmask = sl.vmask; P.mets[m].signbit = sl.signbit;
-      P.mets[m].width = sl.width; P.mets[m].row_off = sl.row_off;
-      P.mets[m].bitset = sl.bitset; P.mets[m].bitset_idx = sl.bitset_idx;
-    }
-    P.small_plan = P.nkeys <= 4 && P.nmetrics <= 4;
-    for (uint32_t k = 0; k < P.nkeys; ++k)
-      if (P.slots[P.keys[k].slot].width > 4) P.small_plan = 0;
-
-    // ---- row-major mirror or columns for the cells of passing rows? (per chunk, in the kernel) ----
-    // Bytes of DRAM atoms (64 B) each way for a 512-row chunk with n passing rows: the mirror costs the
-    // atoms one row's cells span; a column costs every atom that holds at least one passing row. Columns
-    // the predicate has just streamed are in L2 either way.
-    P.row_stride = t->row_stride;
-    P.row_thresh = 0;
-    if (t->row_stride && P.small_plan && !(ctx->tune & 128u) && (plan->nnodes > 0 || (ctx->tune & 256u))) {
-      bool all_mirrored = true;
-      for (uint32_t s : q.active) all_mirrored = all_mirrored && t->segs[s].rows != nullptr;
-      uint32_t lo_off = ~0u, hi_off = 0;
-      std::vector<uint32_t> widths;
-      auto payload = [&](uint32_t slot) {
-        const Slot &sl = P.slots[slot];
-        lo_off = std::min(lo_off, sl.row_off);
-        hi_off = std::max(hi_off, sl.row_off + sl.width);
-        bool streamed = false;
-        for (uint32_t f = 0; f < P.nfilter_slots; ++f) streamed = streamed || P.filter_slots[f] == slot;
-        if (!streamed) widths.push_back(sl.width);
-      };
-      for (uint32_t k = 0; k < P.nkeys; ++k) payload(P.keys[k].slot);
-      for (uint32_t m = 0; m < P.nmetrics; ++m) payload(P.mets[m].slot);
-      if (all_mirrored && !widths.empty()) {
-        const double span = (double)(hi_off - lo_off);
-        const double row_cost = 64.0 * (1.0 + (span - 1.0) / 64.0);
-        for (uint32_t n = 1; n <= (uint32_t)kChunkRows; ++n) {
-          double col_cost = 0;
-          for (uint32_t w : widths)
-            col_cost += 8.0 * w * 64.0 * (1.0 - std::pow(1.0 - (double)n / kChunkRows, 64.0 / w));
-          if (n * row_cost < col_cost) P.row_thresh = n; else break;
-        }
-      }
-      if (all_mirrored && (ctx->tune & 256u)) P.row_thresh = kChunkRows;  // tests: every batch from the mirror
-    }
-
-    // ---- dense or hash ----
-    unsigned __int128 cells128 = 1;
-    bool fits64 = true;
-    for (auto &r : q.ranges) {
-      cells128 *= range128(r);
-      if (cells128 > ((unsigned __int128)1 << 64) - 2) { fits64 = false; break; }
-    }
-    const bool wide = !fits64;  // key tuple wider than 64 bits: hash on the full tuple
-    if (wide && ctx->nranks > 1) fail(VGPU_ERR_UNSUPPORTED, "multi-GPU merge of key tuples wider than 64 bits is not implemented yet");
-    if (wide && (plan->flags & VGPU_PLAN_FORCE_DENSE)) fail(VGPU_ERR_UNSUPPORTED, "key domain too large for a dense group table");
-    const uint64_t cells = wide ? ~0ull : (uint64_t)cells128;
-    uint64_t dense_limit = std::min<uint64_t>(std::max<uint64_t>(4 * global_active_rows, 1ull << 22), 1ull << 28);
-    if (P.ndistinct) dense_limit = std::min<uint64_t>(dense_limit, 0xffffffffull);
-    bool dense = !wide && cells <= dense_limit;
-    if (plan->flags & VGPU_PLAN_FORCE_HASH) dense = false;
-    if (plan->flags & VGPU_PLAN_FORCE_DENSE) {
-      if (cells > (1ull << 30)) fail(VGPU_ERR_UNSUPPORTED, "key domain too large for a dense group table");
-      dense = true;
-    }
-    q.hash_mode = !dense;
-    q.wide = wide;
-    if (wide) P.row_thresh = 0;  // the wide-tuple path gathers from the columns
-    for (uint32_t k = 0; k < plan->nkeys; ++k) P.keys[k].fzero = wide && type_float(t->cols[plan->keys[k].col].type);
-    if (ctx->trace) {
-      fprintf(stderr, "[vgpu r%d] cells=%llu dense_limit=%llu dense=%d active_rows=%llu global=%llu\n", ctx->rank, (unsigned long long)cells, (unsigned long long)dense_limit, (int)dense, (unsigned long long)q.active_rows, (unsigned long long)global_active_rows);
-      for (uint32_t k = 0; k < plan->nkeys; ++k) fprintf(stderr, "[vgpu r%d]   key %u lo=%llu range=%llu kmin=%llu kmax=%llu\n", ctx->rank, k, (unsigned long long)q.ranges[k].lo, (unsigned long long)q.ranges[k].range, (unsigned long long)kmin[k], (unsigned long long)kmax[k]);
-    }
-    {
-      uint64_t mul = 1;
-      for (uint32_t k = 0; k < plan->nkeys; ++k) {
-        P.keys[k].lo = q.ranges[k].lo;
-        P.keys[k].mul = mul;
-        mul *= q.ranges[k].range;  // the last multiplication may wrap only if it is never used
-      }
-    }
-
-    // ---- work list ----
-    uint64_t max_rows = 0;
-    for (uint32_t s : q.active) max_rows = std::max(max_rows, t->segs[s].nrows);
-    P.tiles_per_seg = (uint32_t)std::max<uint64_t>(1, (max_rows + kChunkRows - 1) / kChunkRows);
-    P.nactive = (uint32_t)q.active.size();
-    P.total_tiles = (uint64_t)P.nactive * P.tiles_per_seg;
-    // work units: about 8 per resident warp so that dynamic scheduling evens out the tail, at most 64 chunks
-    P.unit_chunks = ctx->unit_chunks;
-    if (P.unit_chunks == 0) {
-      const uint64_t warps = (uint64_t)ctx->sm_count * ctx->ctas_per_sm * kWarps;
-      P.unit_chunks = (uint32_t)std::min<uint64_t>(64, std::max<uint64_t>(4, P.total_tiles / (8 * warps)));
-    }
-    P.units_per_seg = (P.tiles_per_seg + P.unit_chunks - 1) / P.unit_chunks;
-    if ((uint64_t)P.nactive * P.units_per_seg > 0x7fffffffull) fail(VGPU_ERR_UNSUPPORTED, "too many work units");
-    upload_descs(t);
-    P.segs = t->d_segs;
-    P.tune = ctx->tune;
-
-    std::unique_ptr<vgpu_result> res(new vgpu_result());
-    vgpu_result_view &view = res->view;
-    view.nkeys = plan->nkeys;
-    view.nmetrics = plan->nmetrics;
-    view.scanned_recs = q.scanned_recs;
-    view.scanned_segments = q.active.size();
-
-    CUDA_CK(cudaEventRecord(ctx->ev_begin, stream));
-    uint32_t launches = 0;
-    float scan_ms_total = 0;
-
-    uint64_t hash_cap = 0;
-    if (q.hash_mode) {
-      uint64_t est = std::min<uint64_t>(cells, std::max<uint64_t>(global_active_rows, 1));
-      uint64_t want = pow2_ceil(std::max<uint64_t>(2 * est, 1024));
-      hash_cap = std::min<uint64_t>(want, 1ull << 24);
-      hash_cap = std::max(hash_cap, std::min(t->hash_cap_hint, want));
-      if (hash_cap > 0xfffffffeull && P.ndistinct) fail(VGPU_ERR_UNSUPPORTED, "count-distinct over more than 2^32 groups");
-    }
-    // the scan grid (also the number of count-distinct pair regions)
-    const int scan_grid = (int)std::max<uint64_t>(1, std::min<uint64_t>((P.total_tiles + kWarps - 1) / kWarps,
-                                                                       (uint64_t)ctx->sm_count * ctx->ctas_per_sm));
-    // count-distinct: every CTA appends its (cell,id) pairs to a private region. The region capacity
-    // follows the high-water mark of earlier queries on this table; overflow => grow and re-run the scan
-    uint64_t dpair_total_cap = 0;
-    if (P.ndistinct) {
-      dpair_total_cap = std::max<uint64_t>(1ull << 16, q.active_rows / 16);
-      dpair_total_cap = std::max(dpair_total_cap, t->pairs_cap_hint);
-    }
-
-    for (int attempt = 0;; ++attempt) {
-      if (attempt > 12) fail(VGPU_ERR_NOMEM, "group table keeps overflowing");
-      Scratch scratch(stream);
-      q.ncells = q.hash_mode ? hash_cap : cells;
-      const uint64_t acc_cells = q.hash_mode ? hash_cap + 1 : cells;  // + the all-ones-key cell
-      P.hash_mode = q.wide ? 2u : (q.hash_mode ? 1u : 0u);
-      P.max_probe = 512;
-      // Group table layout. Single GPU: the fields of a cell (key, accumulators, presence flag) are
-      // INTERLEAVED, so that one passing row touches one line of the table instead of one line per
-      // metric array (tables beyond a few MB are DRAM-resident under the column stream: measured
-      // +3..10 B/row of traffic with separate arrays). Several GPUs: one array per field, because the
-      // NCCL merge reduces each array with its own type and operator.
-      const bool interleave = ctx->nranks == 1;
-      uint64_t block_bytes = 0;
-      auto carve = [&](uint64_t bytes) { uint64_t o = block_bytes; block_bytes += round_up(bytes, 256); return o; };
-      const uint64_t o_wstate = q.wide ? carve(hash_cap * 4) : 0;
-      const uint64_t o_wkeys = q.wide ? carve(hash_cap * 8 * std::max<uint32_t>(plan->nkeys, 1)) : 0;
-      std::vector<void *> acc_ptrs(q.accs.size());
-      std::vector<uint32_t> acc_stride(q.accs.size());
-      uint8_t *block = nullptr;
-      const bool key_in_cell = q.hash_mode && !q.wide;
-      if (interleave) {
-        // cell = [key u64]? [8-byte accumulators] [4-byte accumulators] [presence u32]?
-        uint32_t off = 0;
-        uint32_t o_key = 0, o_pres = 0;
-        std::vector<uint32_t> o_f(q.accs.size());
-        if (key_in_cell) { o_key = off; off += 8; }
-        for (size_t m = 0; m < q.accs.size(); ++m) if (q.accs[m].acc_width == 8) { o_f[m] = off; off += 8; }
-        for (size_t m = 0; m < q.accs.size(); ++m) if (q.accs[m].acc_width == 4) { o_f[m] = off; off += 4; }
-        const bool need_present = !q.hash_mode;
-        if (need_present) { o_pres = off; off += 4; }
-        uint32_t stride = off <= 4 ? 4 : off <= 8 ? 8 : off <= 16 ? 16 : off <= 32 ? 32 : (uint32_t)round_up(off, 8);
-        if (stride / 4 > 48) fail(VGPU_ERR_UNSUPPORTED, "group cell too wide");
-        const uint64_t o_cells = carve(acc_cells * (uint64_t)stride);
-        const uint64_t o_flag = carve(16);
-        block = scratch.alloc<uint8_t>(block_bytes);
-        CellPattern C{};
-        C.words = stride / 4;
-        if (key_in_cell) { C.w[o_key / 4] = 0xffffffffu; C.w[o_key / 4 + 1] = 0xffffffffu; }
-        for (size_t m = 0; m < q.accs.size(); ++m) {
-          C.w[o_f[m] / 4] = (uint32_t)q.accs[m].init;
-          if (q.accs[m].acc_width == 8) C.w[o_f[m] / 4 + 1] = (uint32_t)(q.accs[m].init >> 32);
-          acc_ptrs[m] = block + o_cells + o_f[m];
-          acc_stride[m] = stride;
-        }
-        const uint64_t total_words = acc_cells * (uint64_t)(stride / 4);
-        fill_cells_kernel<<<grid_for(total_words, 256, ctx->sm_count), 256, 0, stream>>>(
-            reinterpret_cast<uint32_t *>(block + o_cells), total_words, C);
-        CUDA_CK(cudaGetLastError());
-        ++launches;
-        P.hkeys = key_in_cell ? reinterpret_cast<uint64_t *>(block + o_cells + o_key) : nullptr;
-        P.hkey_stride = stride;
-        P.hmask = q.hash_mode ? hash_cap - 1 : 0;
-        if (need_present) {
-          P.present = block + o_cells + o_pres;
-          P.present_stride = stride;
-        } else {
-          P.present = block + o_flag;  // present[0] flags the all-ones key
-          P.present_stride = 1;
-          CUDA_CK(cudaMemsetAsync(P.present, 0, 16, stream));
-        }
-      } else {
-        const uint64_t o_hkeys = key_in_cell ? carve(hash_cap * 8) : 0;
-        const uint64_t o_present = carve(q.hash_mode ? 16 : acc_cells);
-        std::vector<uint64_t> o_acc(q.accs.size());
-        for (size_t m = 0; m < q.accs.size(); ++m) o_acc[m] = carve(acc_cells * q.accs[m].acc_width);
-        block = scratch.alloc<uint8_t>(block_bytes);
-        P.hkeys = key_in_cell ? reinterpret_cast<uint64_t *>(block + o_hkeys) : nullptr;
-        P.hkey_stride = 8;
-        P.hmask = q.hash_mode ? hash_cap - 1 : 0;
-        if (key_in_cell) fill64(stream, ctx->sm_count, P.hkeys, hash_cap, kEmptyKey);
-        P.present = block + o_present;
-        P.present_stride = 1;
-        CUDA_CK(cudaMemsetAsync(P.present, 0, q.hash_mode ? 16 : acc_cells, stream));
-        for (size_t m = 0; m < q.accs.size(); ++m) {
-          const AccInfo &a = q.accs[m];
-          acc_ptrs[m] = block + o_acc[m];
-          acc_stride[m] = a.acc_width;
-          if (a.acc_width == 4) launches += fill32(stream, ctx->sm_count, acc_ptrs[m], acc_cells, (uint32_t)a.init);
-          else launches += fill64(stream, ctx->sm_count, acc_ptrs[m], acc_cells, a.init);
-        }
-      }
-      if (q.wide) {
-        P.wstate = reinterpret_cast<uint32_t *>(block + o_wstate);
-        P.wkeys = reinterpret_cast<uint64_t *>(block + o_wkeys);
-        CUDA_CK(cudaMemsetAsync(P.wstate, 0, hash_cap * 4, stream));
-      }
-      for (size_t m = 0; m < q.accs.size(); ++m) {
-        P.mets[m].acc = acc_ptrs[m];
-        P.mets[m].stride = acc_stride[m];
-        P.mets[m].acc_width = q.accs[m].acc_width;
-      }
-      // CTA-private shared-memory copy of a small dense table (see ScanParams::smem_cells)
-      P.smem_cells = 0;
-      uint32_t scan_dyn_smem = 0;
-      if (!q.hash_mode && !(ctx->tune & 262144u)) {
-        uint32_t off = 0;
-        for (size_t m = 0; m < q.accs.size(); ++m) if (q.accs[m].acc_width == 8 && q.accs[m].op != A_DISTINCT) { P.mets[m].soff = off; off += 8; }
-        for (size_t m = 0; m < q.accs.size(); ++m) if (q.accs[m].acc_width == 4 && q.accs[m].op != A_DISTINCT) { P.mets[m].soff = off; off += 4; }
-        const uint32_t pres = off;
-        off += 4;
-        const uint32_t sstride = (uint32_t)round_up(off, 8);
-        if (sstride <= 64 && cells * sstride <= kSmemTableBytes) {
-          P.smem_cells = (uint32_t)cells;
-          P.smem_stride = sstride;
-          P.smem_present_off = pres;
-          for (uint32_t w = 0; w < 16; ++w) P.smem_init[w] = 0;
-          for (size_t m = 0; m < q.accs.size(); ++m) {
-            if (q.accs[m].op == A_DISTINCT) continue;
-            P.smem_init[P.mets[m].soff / 4] = (uint32_t)q.accs[m].init;
-            if (q.accs[m].acc_width == 8) P.smem_init[P.mets[m].soff / 4 + 1] = (uint32_t)(q.accs[m].init >> 32);
-          }
-          scan_dyn_smem = (uint32_t)cells * sstride;
-        }
-      }
-      // per-CTA pair regions: the even share plus 25 % and a constant for the unevenness between CTAs
-      const uint64_t region_cap64 = dpair_total_cap / scan_grid + dpair_total_cap / scan_grid / 4 + 1024;
-      if (P.ndistinct && region_cap64 > 0xffffffffull) fail(VGPU_ERR_NOMEM, "count-distinct pair regions too large");
-      P.dpair_cap = (uint32_t)region_cap64;
-      for (uint32_t d = 0; d < P.ndistinct; ++d) {
-        P.dpairs[d] = scratch.alloc<uint64_t>(region_cap64 * scan_grid);
-        P.dpair_count[d] = scratch.alloc<uint32_t>(scan_grid);
-        CUDA_CK(cudaMemsetAsync(P.dpair_count[d], 0, scan_grid * 4, stream));
-      }
-      CUDA_CK(cudaMemsetAsync(ctx->d_counters, 0, 16 * sizeof(unsigned long long), stream));
-      P.counters = ctx->d_counters;
-      uint32_t *d_active = scratch.alloc<uint32_t>(q.active.size());
-      if (!q.active.empty())
-        CUDA_CK(cudaMemcpyAsync(d_active, q.active.data(), q.active.size() * 4, cudaMemcpyHostToDevice, stream));
-      P.active = d_active;
-
-      // ---- the fused scan ----
-      CUDA_CK(cudaEventRecord(ctx->ev_scan0, stream));
-      if (P.total_tiles > 0) {
-        const int grid = scan_grid;
-        cudaLaunchConfig_t cfg{};
-        cfg.gridDim = dim3(grid);
-        cfg.blockDim = dim3(kThreads);
-        cfg.stream = stream;
-        cfg.dynamicSmemBytes = scan_dyn_smem;
-        cudaLaunchAttribute attr[1];
-        cfg.attrs = attr;
-        cfg.numAttrs = 0;
-        if ((ctx->tune & 1u) && ctx->l2_persist_bytes > 0 && block_bytes > 0) {
-          // pin as much of the group table as the persisting carve-out holds
-          const uint64_t win = std::min<uint64_t>(block_bytes, ctx->l2_window_max);
-          attr[0].id = cudaLaunchAttributeAccessPolicyWindow;
-          attr[0].val.accessPolicyWindow.base_ptr = block;
-          attr[0].val.accessPolicyWindow.num_bytes = win;
-          attr[0].val.accessPolicyWindow.hitRatio =
-              (float)std::min(1.0, (double)ctx->l2_persist_bytes / (double)win);
-          attr[0].val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
-          attr[0].val.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
-          cfg.numAttrs = 1;
-        }
-        if (P.smem_cells) CUDA_CK(cudaLaunchKernelEx(&cfg, scan_filter_groupby_kernel<3, true>, P));
-        else if (ctx->ctas_per_sm == 2) CUDA_CK(cudaLaunchKernelEx(&cfg, scan_filter_groupby_kernel<2, false>, P));
-        else if (ctx->ctas_per_sm == 4) CUDA_CK(cudaLaunchKernelEx(&cfg, scan_filter_groupby_kernel<4, false>, P));
-        else CUDA_CK(cudaLaunchKernelEx(&cfg, scan_filter_groupby_kernel<3, false>, P));
-        ++launches;
-      }
-      CUDA_CK(cudaEventRecord(ctx->ev_scan1, stream));
-      if (ctx->nranks > 1)  // every rank must take the same grow-and-retry decision
-        NCCL_CK(g_nccl.AllReduce(ctx->d_counters + 1, ctx->d_counters + 1, 1, ncclUint64, ncclMax, ctx->comm, stream));
-      CUDA_CK(cudaMemcpyAsync(ctx->h_counters, ctx->d_counters, 16 * sizeof(unsigned long long),
-                              cudaMemcpyDeviceToHost, stream));
-      CUDA_CK(cudaStreamSynchronize(stream));
-      {
-        float ms = 0;
-        CUDA_CK(cudaEventElapsedTime(&ms, ctx->ev_scan0, ctx->ev_scan1));
-        scan_ms_total += ms;
-      }
-      const uint64_t passed = ctx->h_counters[0];
-      if (ctx->h_counters[1] != 0) {  // overflow (bit 0: group table, bit 1: a distinct set): grow, run again
-        if (ctx->h_counters[1] & 1ull) {
-          if (!q.hash_mode) fail(VGPU_ERR_CUDA, "unexpected overflow flag in dense mode");
-          hash_cap *= 4;
-        }
-        if (ctx->h_counters[1] & 2ull) {  // a pair region overflowed: size for what was actually produced
-          uint64_t most = 0;
-          for (uint32_t d = 0; d < P.ndistinct; ++d) most = std::max<uint64_t>(most, ctx->h_counters[2 + d]);
-          dpair_total_cap = std::max<uint64_t>(2 * dpair_total_cap, most + most / 4);
-        }
-        continue;
-      }
-      if (q.hash_mode) t->hash_cap_hint = std::max(t->hash_cap_hint, hash_cap);
-      if (P.ndistinct) {
-        uint64_t most = 0;
-        for (uint32_t d = 0; d < P.ndistinct; ++d) most = std::max<uint64_t>(most, ctx->h_counters[2 + d]);
-        t->pairs_cap_hint = std::max(t->pairs_cap_hint, most);
-      }
-      view.passed_rows = passed;
-
-      // ---- multi-GPU: merge the partial group tables ----
-      uint64_t acc_cells_x = acc_cells;  // group table the extraction reads (replaced by the merged one)
-      if (ctx->nranks > 1) {
-        if (q.hash_mode) {
-          if (P.ndistinct) fail(VGPU_ERR_UNSUPPORTED, "multi-GPU count-distinct over a hashed group table is not implemented yet");
-          nccl_merge_hash(ctx, q, P, acc_ptrs, scratch, acc_cells_x, launches);
-        } else {
-          nccl_merge_dense(ctx, q, P, acc_ptrs);
-          for (uint32_t d = 0; d < P.ndistinct; ++d)
-            nccl_merge_distinct(ctx, scratch, P.dpairs[d], P.dpair_count[d], (uint32_t)scan_grid, P.dpair_cap,
-                                ctx->h_counters[2 + d], static_cast<uint32_t *>(acc_ptrs[P.distinct_met[d]]), acc_cells, launches);
-        }
-      } else {
-        // ---- count-distinct: dedupe the pairs in L2-sized partitions ----
-        for (uint32_t d = 0; d < P.ndistinct; ++d)
-          dedupe_pairs(ctx, scratch, P.dpairs[d], P.dpair_count[d], (uint32_t)scan_grid, P.dpair_cap, ctx->h_counters[2 + d],
-                       static_cast<uint8_t *>(acc_ptrs[P.distinct_met[d]]), P.mets[P.distinct_met[d]].stride, nullptr, nullptr,
-                       launches);
-      }
-
-      // ---- extract the groups ----
-      ExtractParams E{};
-      E.ncells = acc_cells_x;
-      E.hash_mode = q.wide ? 2u : (q.hash_mode ? 1u : 0u);
-      E.nkeys = plan->nkeys;
-      E.nmets = (uint32_t)q.accs.size();
-      E.hkeys = P.hkeys;
-      E.present = P.present;
-      E.hkey_stride = P.hkey_stride;
-      E.present_stride = P.present_stride;
-      E.wstate = P.wstate;
-      E.wkeys = P.wkeys;
-      unsigned long long *d_ngroups = ctx->d_counters + 12;
-      E.counter = d_ngroups;
-      uint64_t bound = std::min<uint64_t>(acc_cells_x, passed);
-      if (ctx->nranks > 1) {  // merged tables: `passed` is only this rank's share, count first
-        E.count_only = 1;
-        extract_groups_kernel<<<grid_for(acc_cells_x, 256, ctx->sm_count), 256, 0, stream>>>(E);
-        CUDA_CK(cudaGetLastError());
-        ++launches;
-        CUDA_CK(cudaMemcpyAsync(ctx->h_counters, ctx->d_counters, 16 * sizeof(unsigned long long),
-                                cudaMemcpyDeviceToHost, stream));
-        CUDA_CK(cudaStreamSynchronize(stream));
-        bound = ctx->h_counters[12];
-        CUDA_CK(cudaMemsetAsync(d_ngroups, 0, sizeof(unsigned long long), stream));
-      }
-      E.count_only = 0;
-      std::vector<void *> d_keys(plan->nkeys), d_accs(q.accs.size());
-      for (uint32_t k = 0; k < plan->nkeys; ++k) {
-        const ColInfo &ci = t->cols[plan->keys[k].col];
-        d_keys[k] = scratch.alloc<uint8_t>(bound * ci.width);
-        E.keys[k].lo = q.ranges[k].lo;
-        E.keys[k].lut = P.keys[k].lut;
-        E.keys[k].div = P.keys[k].mul;
-        E.keys[k].mod = (k + 1 < plan->nkeys) ? q.ranges[k].range : 0;
-        E.keys[k].width = ci.width;
-        E.keys[k].out = d_keys[k];
-      }
-      for (size_t m = 0; m < q.accs.size(); ++m) {
-        d_accs[m] = scratch.alloc<uint8_t>(bound * q.accs[m].out_width);
-        E.mets[m].acc = acc_ptrs[m];
-        E.mets[m].stride = P.mets[m].stride;
-        E.mets[m].acc_width = q.accs[m].acc_width;
-        E.mets[m].out_width = q.accs[m].out_width;
-        E.mets[m].out = d_accs[m];
-      }
-      if (bound > 0) {
-        extract_groups_kernel<<<grid_for(acc_cells_x, 256, ctx->sm_count), 256, 0, stream>>>(E);
-        CUDA_CK(cudaGetLastError());
-        ++launches;
-      }
-      CUDA_CK(cudaMemcpyAsync(ctx->h_counters, ctx->d_counters, 16 * sizeof(unsigned long long),
-                              cudaMemcpyDeviceToHost, stream));
-      CUDA_CK(cudaStreamSynchronize(stream));
-      const uint64_t ngroups = bound > 0 ? ctx->h_counters[12] : 0;
-      if (ngroups > bound) fail(VGPU_ERR_CUDA, "group extraction overflow");
-
-      // ---- results to the host: one pinned block, arrays 64-byte aligned ----
-      {
-        uint64_t bytes = 0;
-        std::vector<uint64_t> off_k(plan->nkeys), off_m(plan->nmetrics);
-        uint64_t off_h = 0;
-        auto place = [&](uint64_t n) { uint64_t o = bytes; bytes += round_up(std::max<uint64_t>(n, 1), 64); return o; };
-        for (uint32_t k = 0; k < plan->nkeys; ++k) off_k[k] = place(ngroups * t->cols[plan->keys[k].col].width);
-        for (uint32_t m = 0; m < plan->nmetrics; ++m) off_m[m] = place(ngroups * q.accs[m].out_width);
-        if (plan->need_hidden_count) off_h = place(ngroups * 8);
-        res->pool = ctx->pool;
-        res->block = ctx->pool->acquire(bytes);
-        uint8_t *hb = static_cast<uint8_t *>(res->block.first);
-        for (uint32_t k = 0; k < plan->nkeys; ++k) {
-          const uint64_t n = ngroups * t->cols[plan->keys[k].col].width;
-          if (n) CUDA_CK(cudaMemcpyAsync(hb + off_k[k], d_keys[k], n, cudaMemcpyDeviceToHost, stream));
-          res->key_ptrs.push_back(hb + off_k[k]);
-        }
-        for (uint32_t m = 0; m < plan->nmetrics; ++m) {
-          const uint64_t n = ngroups * q.accs[m].out_width;
-          if (n) CUDA_CK(cudaMemcpyAsync(hb + off_m[m], d_accs[m], n, cudaMemcpyDeviceToHost, stream));
-          res->acc_ptrs.push_back(hb + off_m[m]);
-        }
-        if (plan->need_hidden_count) {
-          if (ngroups) CUDA_CK(cudaMemcpyAsync(hb + off_h, d_accs[plan->nmetrics], ngroups * 8, cudaMemcpyDeviceToHost, stream));
-          view.hidden_count = reinterpret_cast<const uint64_t *>(hb + off_h);
-        }
-      }
-      CUDA_CK(cudaEventRecord(ctx->ev_end, stream));
-      CUDA_CK(cudaStreamSynchronize(stream));
-      float total_ms = 0;
-      CUDA_CK(cudaEventElapsedTime(&total_ms, ctx->ev_begin, ctx->ev_end));
-      view.ngroups = ngroups;
-      view.aggregated_recs = ngroups;
-      view.gpu_ms = total_ms;
-      view.scan_ms = scan_ms_total;
-      view.launches = launches;
-      view.table_mode = q.wide ? 2 : (q.hash_mode ? 1 : 0);
-      view.table_cells = q.ncells;
-      break;
-    }
-
-    view.keys = res->key_ptrs.empty() ? nullptr : res->key_ptrs.data();
-    view.accs = res->acc_ptrs.empty() ? nullptr : res->acc_ptrs.data();
-    *out = res.release();
-  });
-}
+#include "query_agg.inl"
 
 // ---------------------------------------------------------------------------------------------
 // select / search
@@ -2447,13 +1624,15 @@ int vgpu_query_select(vgpu_table *t, const vgpu_rows_plan *rp, vgpu_rows **out) 
     for (uint32_t c = 0; c < rp->ncols; ++c)
       if (rp->cols[c] >= t->cols.size()) fail(VGPU_ERR_INVALID, "select column out of range");
     vgpu_ctx *ctx = t->ctx;
-    std::lock_guard<std::mutex> lk(ctx->mu);
     CUDA_CK(cudaSetDevice(ctx->device));
-    cudaStream_t stream = ctx->stream;
+    std::shared_lock<std::shared_mutex> table_lk = lock_table_for_query(t);
+    ScopeLease lease(ctx);
+    QueryScope *sc = lease.sc;
+    cudaStream_t stream = sc->s0;
+    CUDA_CK(cudaStreamWaitEvent(stream, t->ev_put, 0));
     vgpu_plan plan{};
     plan.nnodes = rp->nnodes; plan.nargs = rp->nargs; plan.nodes = rp->nodes; plan.args = rp->args;
     validate_plan(t, &plan);
-    fetch_stats(t);
     QueryRun q(t, &plan);
     ScanParams &P = q.planner.P;
     finish_predicate_and_prune(ctx, t, q);
@@ -2464,7 +1643,7 @@ int vgpu_query_select(vgpu_table *t, const vgpu_rows_plan *rp, vgpu_rows **out) 
     view.ncols = rp->ncols;
     view.scanned_recs = q.scanned_recs;
     view.scanned_segments = q.active.size();
-    CUDA_CK(cudaEventRecord(ctx->ev_begin, stream));
+    CUDA_CK(cudaEventRecord(sc->ev_begin, stream));
     uint32_t launches = 0;
     const uint32_t A = P.nactive, cps = P.tiles_per_seg;
     const int grid = (int)std::max<uint64_t>(1, std::min<uint64_t>((P.total_tiles + kWarps - 1) / kWarps, (uint64_t)ctx->sm_count * 4));
@@ -2536,10 +1715,10 @@ int vgpu_query_select(vgpu_table *t, const vgpu_rows_plan *rp, vgpu_rows **out) 
           CUDA_CK(cudaMemcpyAsync(hb + off_c[c], d_out[c], emitted * out_width(c), cudaMemcpyDeviceToHost, stream));
       }
     }
-    CUDA_CK(cudaEventRecord(ctx->ev_end, stream));
+    CUDA_CK(cudaEventRecord(sc->ev_end, stream));
     CUDA_CK(cudaStreamSynchronize(stream));
     float ms = 0;
-    CUDA_CK(cudaEventElapsedTime(&ms, ctx->ev_begin, ctx->ev_end));
+    CUDA_CK(cudaEventElapsedTime(&ms, sc->ev_begin, sc->ev_end));
     view.gpu_ms = ms;
     view.launches = launches;
     for (uint32_t c = 0; c < rp->ncols; ++c) res->cell_ptrs.push_back(hb + off_c[c]);
@@ -2565,13 +1744,15 @@ int vgpu_query_search(vgpu_table *t, const vgpu_search_plan *sp, vgpu_search **o
     const ColInfo &dc = t->cols[sp->col];
     if (type_float(dc.type)) fail(VGPU_ERR_UNSUPPORTED, "search on a floating-point dimension");
     vgpu_ctx *ctx = t->ctx;
-    std::lock_guard<std::mutex> lk(ctx->mu);
     CUDA_CK(cudaSetDevice(ctx->device));
-    cudaStream_t stream = ctx->stream;
+    std::shared_lock<std::shared_mutex> table_lk = lock_table_for_query(t);
+    ScopeLease lease(ctx);
+    QueryScope *sc = lease.sc;
+    cudaStream_t stream = sc->s0;
+    CUDA_CK(cudaStreamWaitEvent(stream, t->ev_put, 0));
     vgpu_plan plan{};
     plan.nnodes = sp->nnodes; plan.nargs = sp->nargs; plan.nodes = sp->nodes; plan.args = sp->args;
     validate_plan(t, &plan);
-    fetch_stats(t);
     QueryRun q(t, &plan);
     ScanParams &P = q.planner.P;
     finish_predicate_and_prune(ctx, t, q);
@@ -2581,7 +1762,7 @@ int vgpu_query_search(vgpu_table *t, const vgpu_search_plan *sp, vgpu_search **o
     vgpu_search_view &view = res->view;
     view.scanned_recs = q.scanned_recs;
     view.scanned_segments = q.active.size();
-    CUDA_CK(cudaEventRecord(ctx->ev_begin, stream));
+    CUDA_CK(cudaEventRecord(sc->ev_begin, stream));
     uint32_t launches = 0;
     const uint32_t A = P.nactive;
     res->seg_offsets.assign(A + 1, 0);
@@ -2649,10 +1830,10 @@ int vgpu_query_search(vgpu_table *t, const vgpu_search_plan *sp, vgpu_search **o
       for (auto &e : v) { res->first_row.push_back(e.first); res->codes.push_back(e.second); }
       res->seg_offsets[si + 1] = res->codes.size();
     }
-    CUDA_CK(cudaEventRecord(ctx->ev_end, stream));
+    CUDA_CK(cudaEventRecord(sc->ev_end, stream));
     CUDA_CK(cudaStreamSynchronize(stream));
     float ms = 0;
-    CUDA_CK(cudaEventElapsedTime(&ms, ctx->ev_begin, ctx->ev_end));
+    CUDA_CK(cudaEventElapsedTime(&ms, sc->ev_begin, sc->ev_end));
     view.gpu_ms = ms;
     view.launches = launches;
     view.nsegments = A;
@@ -2699,7 +1880,7 @@ int vgpu_comm_init(vgpu_ctx *ctx, int rank, int nranks, const void *unique_id_12
   return guard([&] {
     if (!ctx || !unique_id_128) fail(VGPU_ERR_INVALID, "null argument");
     if (nranks < 1 || rank < 0 || rank >= nranks) fail(VGPU_ERR_INVALID, "bad rank / nranks");
-    std::lock_guard<std::mutex> lk(ctx->mu);
+    std::lock_guard<std::mutex> lk(ctx->comm_mu);
     if (ctx->comm) fail(VGPU_ERR_STATE, "communicator already initialised");
     nccl_load();
     CUDA_CK(cudaSetDevice(ctx->device));
@@ -2714,10 +1895,10 @@ int vgpu_comm_init(vgpu_ctx *ctx, int rank, int nranks, const void *unique_id_12
 int vgpu_comm_destroy(vgpu_ctx *ctx) {
   return guard([&] {
     if (!ctx) fail(VGPU_ERR_INVALID, "null context");
-    std::lock_guard<std::mutex> lk(ctx->mu);
+    std::lock_guard<std::mutex> lk(ctx->comm_mu);
     if (ctx->comm) {
       CUDA_CK(cudaSetDevice(ctx->device));
-      CUDA_CK(cudaStreamSynchronize(ctx->stream));
+      CUDA_CK(cudaDeviceSynchronize());
       NCCL_CK(g_nccl.CommDestroy(ctx->comm));
       ctx->comm = nullptr;
     }

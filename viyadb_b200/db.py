@@ -196,10 +196,10 @@ class Table:
         cols = (N.Column * self.ncols)()
         i = 0
         for c in self.dimensions + self.metrics:
-            btype = c.type
+            btype, lit = c.type, 0
             if c.kind == N.METRIC_BITSET and c.type in (N.U8, N.U16):
-                btype = N.U32  # ids travel as uint32 (include/vgpu.h: vgpu_column.type)
-            cols[i] = N.Column(c.kind, btype, c.agg, 0)
+                btype, lit = N.U32, c.type + 1  # ids travel as uint32, filter literals keep their own width (vgpu.h)
+            cols[i] = N.Column(c.kind, btype, c.agg, lit)
             i += 1
         if self.has_hidden_count:
             cols[i] = N.Column(N.METRIC_HIDDEN_COUNT, N.U64, N.AGG_COUNT, 0)

@@ -579,7 +579,7 @@ class GpuQueryRunner:
         # AVG cells are divided by the first selected COUNT metric, else by the table's hidden count (scan.cc:133-154)
         count_pos = next((i for i, c in enumerate(cols) if not c.is_dimension and c.agg == N.AGG_COUNT), None)
         if count_pos is None and any((not c.is_dimension) and c.agg == N.AGG_AVG for c in cols):
-            hidden = t.hidden_count_index()
+            hidden = t.hidden_count_index
             if hidden is None:
                 raise N.VgpuError(N.ERR_INVALID, "AVG metric selected but the table has neither COUNT nor hidden count")
             count_pos = len(sel)
