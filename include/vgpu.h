@@ -208,9 +208,18 @@ typedef struct vgpu_result_view {
   double gpu_ms;                /* device time of all kernels of this query (CUDA events) */
   double scan_ms;               /* device time of the fused scan kernel alone             */
   uint32_t launches;            /* kernels launched for this query                        */
-  uint32_t table_mode;          /* 0 dense, 1 hash64 */
+  uint32_t table_mode;          /* 0 dense, 1 hash64, 2 wide key tuples */
   uint64_t table_cells;         /* dense cells or hash capacity */
+  uint32_t attempts;            /* scans run: > 1 after a hash-table or pair-region overflow (grow and scan again) */
+  uint32_t distinct_paths;      /* count-distinct dedupe paths taken, VGPU_DEDUPE_* bits */
 } vgpu_result_view;
+
+#define VGPU_DEDUPE_SMALL 1u    /* one global set */
+#define VGPU_DEDUPE_FAST 2u     /* hash buckets + shared-memory sets */
+#define VGPU_DEDUPE_WIDE 4u     /* 16-byte pairs (64-bit ids / packed group keys), one global set */
+#define VGPU_DEDUPE_GENERAL 8u  /* L2-sized partitions + global sets */
+#define VGPU_DEDUPE_REDONE 16u  /* the fast path overflowed and the general one ran instead */
+#define VGPU_DEDUPE_PARTITIONED 32u /* the general path really cut the pairs into more than one partition */
 
 /* ---- lifecycle ----
  * Threading (the reference runs `query_threads` queries at once next to one ingest thread, src/db/database.cc:28-33):
@@ -226,7 +235,8 @@ int vgpu_set_stream(vgpu_ctx *ctx, void *cuda_stream);
 /* Test hooks: force the rarely taken branches at test sizes. name = "pairs_cap" (first capacity of the count-distinct
  * pair regions: overflow + regrow), "hash_cap" (first capacity of hashed group tables: x4 regrow), "bucket_pairs"
  * (pairs per L2-sized partition of the general dedupe path), "small_pairs" (largest capacity one global set takes),
- * "set_slots" (slots of the shared-memory sets), "tune" (VGPU_TUNE bits). 0 restores the default. */
+ * "set_slots" (slots of the shared-memory sets), "expect_pairs" (pairs the fast dedupe path sizes its buckets for: too
+ * few forces its overflow + the fallback), "tune" (VGPU_TUNE bits). 0 restores the default. */
 int vgpu_set_test_hook(vgpu_ctx *ctx, const char *name, uint64_t value);
 void vgpu_shutdown(vgpu_ctx *ctx);
 const char *vgpu_last_error(void);

@@ -466,7 +466,13 @@ def run_query(table_conf, segments, dicts, query, now=None, hidden_counts=None):
         for k, (m, _) in enumerate(sel_mets):
             if m.agg == "bitset":
                 offsets, values = seg[m.name]
-                met_parts[k].append([values[offsets[i]:offsets[i + 1]] for i in sel])
+                offsets = np.asarray(offsets)
+                if len(values) == n and int(offsets[-1]) == n and bool((np.diff(offsets[:n + 1]) == 1).all()):
+                    # every cell holds exactly one id (the usual state after ingesting raw rows): keep the ids flat,
+                    # the union per group below is then one np.unique over (group, id) pairs — same result, no Python loop
+                    met_parts[k].append(np.asarray(values)[sel].view(_OneIdPerCell))
+                else:
+                    met_parts[k].append([values[offsets[i]:offsets[i + 1]] for i in sel])
             else:
                 met_parts[k].append(seg[m.name][sel])
         if need_hidden:
@@ -497,9 +503,18 @@ def run_query(table_conf, segments, dicts, query, now=None, hidden_counts=None):
 
     gaccs = []
     for (m, _), parts in zip(sel_mets, met_parts):
+        if m.agg == "bitset" and parts and all(isinstance(p, _OneIdPerCell) for p in parts):
+            ids = np.concatenate([np.asarray(p) for p in parts]).astype("<u8")
+            if len(ids) and int(ids.max()) < 2**32:
+                owners = np.unique((gid.astype("<u8") << np.uint64(32)) | ids) >> np.uint64(32)
+            else:
+                owners = np.unique(np.stack([gid.astype("<u8"), ids], axis=1), axis=0)[:, 0]
+            gaccs.append(np.bincount(owners.astype(np.int64), minlength=ngroups).astype("<u8"))
+            continue
         if m.agg == "bitset":
             sets = [set() for _ in range(ngroups)]
-            flat = [cell for part in parts for cell in part]
+            flat = [cell if not isinstance(part, _OneIdPerCell) else np.asarray(cell).reshape(1)
+                    for part in parts for cell in part]
             for g, cell in zip(gid.tolist(), flat):
                 sets[g].update(cell.tolist())
             gaccs.append(np.array([len(s) for s in sets], dtype="<u8"))
@@ -745,6 +760,10 @@ def _seg_rows(seg, columns):
             return len(v[0]) - 1
         return len(v)
     return 0
+
+
+class _OneIdPerCell(np.ndarray):
+    """ids of bitset cells that hold exactly one id each (tag type, see run_query)"""
 
 
 def _count_passed(met_parts, hid_parts, segments, flt, cols, dicts, columns):

@@ -59,7 +59,7 @@ def upload(table, segs, dicts, hidden):
     for i, seg in enumerate(segs):
         g = {}
         for k, v in seg.items():
-            g[k] = (v[0], v[1].astype("<u4")) if isinstance(v, tuple) else v
+            g[k] = v   # bitset cells: (offsets, ids); Table.put_segment narrows the ids to the column's width
         table.put_segment(i, g, hidden[i] if hidden else None)
 
 

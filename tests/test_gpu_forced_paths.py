@@ -1,0 +1,313 @@
+"""The branches of the device path that only large or uneven inputs reach, forced at test sizes and checked against the
+oracle: the shared-memory-set dedupe of count-distinct pairs (the path the timed C2 configuration takes), the general
+L2-partitioned path with more than one partition, the fast path overflowing into the general one, pair-region overflow
++ regrow, hash-table x4 regrow, 64-bit bitset ids (util::Bitset<8> = Roaring64Map, src/util/bitset.h:27-31), float
+keys with -0.0 in 64-bit-packed hash tables, the bucket dictionary of rolled-up time keys, and concurrent queries next
+to a concurrent put on one context (src/db/database.cc:28-33). All through the C ABI; which path ran is asserted from
+vgpu_result_view.distinct_paths / attempts, so a test cannot pass on the default branch by accident."""
+import threading
+
+import numpy as np
+import pytest
+
+import viya_oracle
+from helpers import random_table, rows_equal, upload
+
+pytestmark = pytest.mark.gpu
+NOW = 1496570140
+
+MID = {"name": "mid", "segment_size": 1000000,
+       "dimensions": [{"name": "d0"}, {"name": "d1", "cardinality": 200}, {"name": "n2", "type": "ushort"}],
+       "metrics": [{"name": "mn", "type": "int_min"}, {"name": "uid", "type": "bitset"}]}
+
+
+def mid_table(seed=99, nsegs=5, last=234567, ids=1000000):
+    rng = np.random.default_rng(seed)
+    dicts = {"d0": ["__exceeded"] + [f"a{i}" for i in range(1, 51)], "d1": ["__exceeded"] + [f"b{i}" for i in range(1, 21)]}
+    segs = []
+    for s in range(nsegs):
+        n = 1000000 if s < nsegs - 1 else last
+        segs.append({"d0": rng.integers(1, 51, n).astype("<u4"), "d1": rng.integers(1, 21, n).astype("<u1"),
+                     "n2": rng.integers(0, 1000, n).astype("<u2"),
+                     "mn": rng.integers(-2**31, 2**31, n).astype("<i4"),
+                     "uid": (np.arange(n + 1, dtype="<u8"), rng.integers(0, ids, n).astype("<u8"))})
+    return segs, dicts
+
+
+@pytest.fixture(scope="module")
+def mid(built_lib):
+    import viyadb_b200 as v
+    segs, dicts = mid_table()
+    db = v.Database({"tables": [MID]}, device=0)
+    upload(db.get_table("mid"), segs, dicts, None)
+    want = {}
+    yield v, db, segs, dicts, want
+    db.close()
+
+
+Q_ALL = {"type": "aggregate", "table": "mid", "dimensions": ["d0", "d1"], "metrics": ["mn", "uid"]}          # 4.2e6 pairs > 2^21
+Q_SEL = {"type": "aggregate", "table": "mid", "dimensions": ["d0", "d1", "n2"], "metrics": ["uid", "mn"],
+         "filter": {"op": "and", "filters": [{"op": "in", "column": "d0", "values": ["a3", "a11", "a19", "a27", "a42"]},
+                                             {"op": "ge", "column": "n2", "value": "250"}, {"op": "lt", "column": "n2", "value": "750"}]}}
+
+
+def run(mid, q, hooks=None, flags=0):
+    v, db, segs, dicts, want = mid
+    key = repr(sorted(q.items(), key=lambda kv: kv[0]))
+    if key not in want:
+        want[key] = viya_oracle.run_query(MID, segs, dicts, q, now=NOW)
+    for name, val in (hooks or {}).items():
+        db.set_test_hook(name, val)
+    try:
+        out = v.MemoryRowOutput()
+        stats = db.query(q, out, now=NOW, flags=flags)
+    finally:
+        for name in (hooks or {}):
+            db.set_test_hook(name, 2 if name == "tune" else 0)
+    w = want[key]
+    assert sorted(out.rows) == sorted(w["rows"])
+    for k in ("scanned_segments", "scanned_recs", "aggregated_recs", "output_recs"):
+        assert getattr(stats, k) == w["stats"][k], k
+    return v, stats
+
+
+def test_fast_path_shared_memory_sets(mid):
+    """4.2e6 pairs from 1e6-row segments: buckets + shared-memory sets, one scan, no fallback."""
+    from viyadb_b200 import _native as N
+    v, stats = run(mid, Q_ALL)   # the first query of a table sizes its pair regions for rows / 16: one regrow here
+    assert stats.distinct_paths & N.DEDUPE_FAST, stats.distinct_paths
+    v, stats = run(mid, Q_ALL)   # from then on the table's high-water marks size everything: one scan
+    assert stats.distinct_paths == N.DEDUPE_FAST, stats.distinct_paths
+    assert stats.attempts == 1
+    v, stats = run(mid, Q_SEL)   # 2.1e5 pairs over 1.25e5 groups (the C2 shape): one global set
+    assert stats.distinct_paths & (N.DEDUPE_FAST | N.DEDUPE_SMALL)
+
+
+def test_fast_path_small_sets_many_buckets(mid):
+    from viyadb_b200 import _native as N
+    v, stats = run(mid, Q_ALL, {"set_slots": 1024})   # 8192 buckets of ~500 pairs
+    assert stats.distinct_paths == N.DEDUPE_FAST
+
+
+def test_general_path_partitioned(mid):
+    """The general path with B = 16 L2-sized partitions (what C2 ran in round 1)."""
+    from viyadb_b200 import _native as N
+    v, stats = run(mid, Q_ALL, {"tune": 2 | (1 << 19), "bucket_pairs": 1 << 18})
+    assert stats.distinct_paths == N.DEDUPE_GENERAL | N.DEDUPE_PARTITIONED, stats.distinct_paths
+
+
+def test_fast_path_overflow_falls_back(mid):
+    """Buckets sized for far too few pairs: bucket overflow flag -> the general path redoes the counts."""
+    from viyadb_b200 import _native as N
+    v, stats = run(mid, Q_ALL, {"expect_pairs": 50000})
+    assert stats.distinct_paths & N.DEDUPE_REDONE and stats.distinct_paths & N.DEDUPE_GENERAL, stats.distinct_paths
+    v, stats = run(mid, Q_ALL)            # and the table is not stuck on the slow path
+    assert stats.distinct_paths == N.DEDUPE_FAST
+
+
+def test_pair_region_overflow_regrows(mid):
+    v, stats = run(mid, Q_ALL, {"pairs_cap": 100000})
+    assert stats.attempts >= 2, stats.attempts
+
+
+def test_small_path_single_global_set(mid):
+    from viyadb_b200 import _native as N
+    v, stats = run(mid, Q_ALL, {"small_pairs": 1 << 26})
+    assert stats.distinct_paths == N.DEDUPE_SMALL
+
+
+def test_hash_table_regrows_x4(mid):
+    from viyadb_b200 import _native as N
+    v, stats = run(mid, Q_SEL, {"hash_cap": 1024}, flags=N.PLAN_FORCE_HASH)   # 1.25e5 groups: 1024 -> ... -> 2^18+
+    assert stats.table_mode == 1 and stats.attempts >= 4, (stats.table_mode, stats.attempts)
+    v, stats = run(mid, Q_ALL, {"hash_cap": 64, "pairs_cap": 50000}, flags=N.PLAN_FORCE_HASH)   # both overflows at once
+    assert stats.attempts >= 3
+
+
+# ---- 64-bit bitset ids ----
+WIDE = {"name": "wide", "segment_size": 40000,
+        "dimensions": [{"name": "d0"}, {"name": "n1", "type": "ushort"}],
+        "metrics": [{"name": "count", "type": "count"}, {"name": "big", "type": "bitset", "max": 2**40},
+                    {"name": "uid", "type": "bitset"}]}
+
+
+def test_64bit_bitset_ids(built_lib):
+    import viyadb_b200 as v
+    from viyadb_b200 import _native as N
+    rng = np.random.default_rng(5)
+    dicts = {"d0": ["__exceeded"] + [f"a{i}" for i in range(1, 9)]}
+    pool = np.concatenate([rng.integers(0, 2**40, 3000).astype("<u8"), np.array([2**40 - 1, 2**32, 2**32 - 1, 0, 0xFFFFFFFFFFFFFFFF], "<u8")])
+    segs = []
+    for s in range(3):
+        n = 40000 if s < 2 else 17001
+        counts = rng.integers(0, 4, n)    # cells with 0..3 ids, drawn from a pool so that groups really share ids
+        offsets = np.zeros(n + 1, "<u8")
+        offsets[1:] = np.cumsum(counts)
+        values = pool[rng.integers(0, len(pool), int(offsets[-1]))]
+        for r in np.nonzero(counts > 1)[0][:5000]:   # ids of one cell are a set
+            lo, hi = int(offsets[r]), int(offsets[r + 1])
+            values[lo:hi] = pool[rng.choice(len(pool), hi - lo, replace=False)]
+        segs.append({"d0": rng.integers(1, 9, n).astype("<u4"), "n1": rng.integers(0, 50, n).astype("<u2"),
+                     "count": np.ones(n, "<u4"), "big": (offsets, values),
+                     "uid": (np.arange(n + 1, dtype="<u8"), rng.integers(0, 300, n).astype("<u8"))})
+    db = v.Database({"tables": [WIDE]}, device=0)
+    try:
+        upload(db.get_table("wide"), segs, dicts, None)
+        for q, flags in (({"dimensions": ["d0", "n1"], "metrics": ["big", "count", "uid"]}, 0),
+                         ({"dimensions": ["d0"], "metrics": ["big"], "filter": {"op": "ge", "column": "big", "value": "2"}}, 0),
+                         ({"dimensions": ["n1", "d0"], "metrics": ["uid", "big"]}, N.PLAN_FORCE_HASH)):
+            q = dict(q, type="aggregate", table="wide")
+            out = v.MemoryRowOutput()
+            stats = db.query(q, out, now=NOW, flags=flags)
+            want = viya_oracle.run_query(WIDE, segs, dicts, q, now=NOW)
+            assert sorted(out.rows) == sorted(want["rows"])
+            assert stats.aggregated_recs == want["stats"]["aggregated_recs"]
+            assert stats.distinct_paths & N.DEDUPE_WIDE
+    finally:
+        db.close()
+
+
+# ---- float keys: -0.0 == +0.0 in every table mode (KeyEqual uses ==, store.cc:46-63) ----
+FKEY = {"name": "fkey", "segment_size": 5000,
+        "dimensions": [{"name": "f", "type": "float"}, {"name": "s"}, {"name": "g", "type": "double"}],
+        "metrics": [{"name": "count", "type": "count"}, {"name": "ls", "type": "long_sum"}]}
+
+
+@pytest.mark.parametrize("dims", [["f"], ["f", "s"], ["s", "f"], ["g"], ["f", "g"]], ids=lambda d: "+".join(d))
+def test_float_key_negative_zero(built_lib, dims):
+    import viyadb_b200 as v
+    rng = np.random.default_rng(11)
+    dicts = {"s": ["__exceeded", "x", "y", "z"]}
+    segs = []
+    for s in range(2):
+        n = 5000 if s == 0 else 1234
+        segs.append({"f": rng.choice(np.array([0.0, -0.0, 1.5, -1.5, 3.25], "<f4"), n),
+                     "s": rng.integers(1, 4, n).astype("<u4"),
+                     "g": rng.choice(np.array([0.0, -0.0, 2.5, -2.5], "<f8"), n),
+                     "count": np.ones(n, "<u4"), "ls": rng.integers(-1000, 1000, n).astype("<i8")})
+    db = v.Database({"tables": [FKEY]}, device=0)
+    try:
+        upload(db.get_table("fkey"), segs, dicts, None)
+        q = {"type": "aggregate", "table": "fkey", "dimensions": dims, "metrics": ["count", "ls"]}
+        out = v.MemoryRowOutput()
+        stats = db.query(q, out, now=NOW)
+        want = viya_oracle.run_query(FKEY, segs, dicts, q, now=NOW)
+        # the sign of a zero key that reaches the output is whichever row came first in the reference: compare it unsigned
+        norm = lambda rows: sorted([[c[1:] if c in ("-0",) else c for c in r] for r in rows])
+        assert norm(out.rows) == norm(want["rows"])
+        assert stats.aggregated_recs == want["stats"]["aggregated_recs"]
+    finally:
+        db.close()
+
+
+# ---- rolled-up time keys: the bucket dictionary gives the same groups as per-row calendar arithmetic ----
+ROLL = {"name": "roll", "segment_size": 60000,
+        "dimensions": [{"name": "d0", "cardinality": 300},
+                       {"name": "t1", "type": "time",
+                        "rollup_rules": [{"granularity": "hour", "after": "1 days"}, {"granularity": "day", "after": "1 weeks"},
+                                         {"granularity": "month", "after": "1 years"}]},
+                       {"name": "mt", "type": "microtime",
+                        "rollup_rules": [{"granularity": "minute", "after": "2 hours"}, {"granularity": "day", "after": "3 days"},
+                                         {"granularity": "year", "after": "2 years"}]}],
+        "metrics": [{"name": "count", "type": "count"}, {"name": "ls", "type": "long_sum"}, {"name": "uid", "type": "bitset"}]}
+ROLL_SPEC = {"d0": (1, 200), "t1": (NOW - 800 * 86400, NOW + 5), "mt": ((NOW - 1100 * 86400) * 1000000, (NOW + 5) * 1000000),
+             "count": (1, 3), "ls": (-2**40, 2**40), "uid": ("ids", 2000, 1)}
+ROLL_QUERIES = [
+    {"select": [{"column": "d0"}, {"column": "t1", "granularity": "hour"}, {"column": "ls"}, {"column": "count"}]},   # the C4 shape
+    {"select": [{"column": "t1"}, {"column": "count"}, {"column": "uid"}]},
+    {"select": [{"column": "t1", "granularity": "month", "format": "%Y-%m"}, {"column": "count"}],
+     "filter": {"op": "gt", "column": "t1", "value": str(NOW - 500 * 86400)}},
+    {"select": [{"column": "t1", "granularity": "year"}, {"column": "ls"}]},
+    {"select": [{"column": "mt", "granularity": "day"}, {"column": "count"}]},
+    {"select": [{"column": "mt", "granularity": "hour"}, {"column": "d0"}, {"column": "count"}]},
+    {"select": [{"column": "mt", "granularity": "second"}, {"column": "count"}],
+     "filter": {"op": "gt", "column": "mt", "value": str((NOW - 600) * 1000000)}},
+    {"select": [{"column": "t1", "granularity": "minute"}, {"column": "mt", "granularity": "month"}, {"column": "count"}]},
+]
+
+
+@pytest.fixture(scope="module")
+def roll(built_lib):
+    import viyadb_b200 as v
+    segs, dicts, hidden = random_table(ROLL, 3, 60000, 77, ROLL_SPEC, last_rows=31337)
+    for seg in segs:   # rows right at the rule boundaries and at month / year starts
+        edge = np.array([NOW - 86400, NOW - 86400 - 1, NOW - 7 * 86400, NOW - 7 * 86400 - 1, 1464739200, 1464739199, 1483228800, 1483228799, NOW],
+                        dtype="<u4")
+        seg["t1"][:len(edge)] = edge
+        seg["mt"][:len(edge)] = edge.astype("<u8") * 1000000 + np.arange(len(edge), dtype="<u8") * 111111
+    db = v.Database({"tables": [ROLL]}, device=0)
+    upload(db.get_table("roll"), segs, dicts, hidden)
+    yield v, db, segs, dicts, hidden
+    db.close()
+
+
+@pytest.mark.parametrize("mode", ["dictionary", "calendar"])
+@pytest.mark.parametrize("qi", range(len(ROLL_QUERIES)))
+def test_rollup_bucket_dictionary(roll, qi, mode):
+    v, db, segs, dicts, hidden = roll
+    q = dict(ROLL_QUERIES[qi], type="aggregate", table="roll")
+    db.set_test_hook("tune", 2 | ((1 << 21) if mode == "calendar" else 0))
+    try:
+        out = v.MemoryRowOutput()
+        stats = db.query(q, out, now=NOW)
+    finally:
+        db.set_test_hook("tune", 2)
+    want = viya_oracle.run_query(ROLL, segs, dicts, q, now=NOW, hidden_counts=hidden)
+    assert sorted(out.rows) == sorted(want["rows"])
+    assert stats.aggregated_recs == want["stats"]["aggregated_recs"]
+    if mode == "dictionary" and qi == 0:
+        assert stats.table_mode == 0, "the C4 shape must aggregate into a dense table through the bucket dictionary"
+
+
+# ---- re-entrancy: concurrent queries and a concurrent put on one context ----
+def test_concurrent_queries_and_put(mid):
+    v, db, segs, dicts, want = mid
+    queries = [Q_ALL, Q_SEL,
+               {"type": "aggregate", "table": "mid", "dimensions": ["d1"], "metrics": ["mn"],
+                "filter": {"op": "eq", "column": "d0", "value": "a7"}},
+               {"type": "aggregate", "table": "mid", "dimensions": ["n2"], "metrics": ["uid"],
+                "filter": {"op": "lt", "column": "n2", "value": "40"}}]
+    serial = []
+    for q in queries:
+        out = v.MemoryRowOutput()
+        db.query(q, out, now=NOW)
+        serial.append(sorted(out.rows))
+    # a second table on the same context takes puts while the queries run
+    other = dict(MID, name="other", segment_size=100000)
+    db.create_table(other)
+    t2 = db.get_table("other")
+    for name, c2v in dicts.items():
+        t2.dimension(name).dict.c2v = list(c2v)
+    errors, results = [], [[None] * 3 for _ in queries]
+
+    def worker(i):
+        try:
+            for rep in range(3):
+                out = v.MemoryRowOutput()
+                db.query(queries[i], out, now=NOW)
+                results[i][rep] = sorted(out.rows)
+        except Exception as e:   # noqa: BLE001
+            errors.append(e)
+
+    def putter():
+        try:
+            for s in range(6):
+                seg = {k: (val[0][:100001], val[1][:100000]) if isinstance(val, tuple) else val[:100000] for k, val in segs[s % len(segs)].items()}
+                t2.put_segment(s, seg)
+            # and a put on the table under query: replaces segment 4 with identical data (results must not change)
+            db.get_table("mid").put_segment(4, segs[4])
+        except Exception as e:   # noqa: BLE001
+            errors.append(e)
+
+    threads = [threading.Thread(target=worker, args=(i,)) for i in range(len(queries))] + [threading.Thread(target=putter)]
+    for th in threads:
+        th.start()
+    for th in threads:
+        th.join()
+    assert not errors, errors
+    for i in range(len(queries)):
+        for rep in range(3):
+            assert results[i][rep] == serial[i], (i, rep)
+    out = v.MemoryRowOutput()
+    stats = db.query({"type": "aggregate", "table": "other", "dimensions": ["d0"], "metrics": ["uid"]}, out, now=NOW)
+    assert stats.scanned_recs == 600000

@@ -30,6 +30,7 @@ NODE_RELOP, NODE_IN, NODE_AND, NODE_OR, NODE_EMPTY = range(5)
 # vgpu_relop (== query::RelOpFilter::Operator order)
 OP_EQ, OP_NE, OP_LT, OP_LE, OP_GT, OP_GE = range(6)
 PLAN_FORCE_HASH, PLAN_FORCE_DENSE = 1, 2
+DEDUPE_SMALL, DEDUPE_FAST, DEDUPE_WIDE, DEDUPE_GENERAL, DEDUPE_REDONE, DEDUPE_PARTITIONED = 1, 2, 4, 8, 16, 32
 MAX_ROLLUP_RULES = 8
 
 
@@ -70,7 +71,8 @@ class ResultView(C.Structure):
                 ("hidden_count", C.POINTER(C.c_uint64)), ("scanned_recs", C.c_uint64),
                 ("scanned_segments", C.c_uint64), ("aggregated_recs", C.c_uint64),
                 ("passed_rows", C.c_uint64), ("gpu_ms", C.c_double), ("scan_ms", C.c_double),
-                ("launches", C.c_uint32), ("table_mode", C.c_uint32), ("table_cells", C.c_uint64)]
+                ("launches", C.c_uint32), ("table_mode", C.c_uint32), ("table_cells", C.c_uint64),
+                ("attempts", C.c_uint32), ("distinct_paths", C.c_uint32)]
 
 
 class RowsPlan(C.Structure):

@@ -187,7 +187,7 @@ __device__ __noinline__ uint64_t rollup_value(uint64_t v, const KeySpec &k) {
 }
 
 // rank of a rolled-up time value among all attainable ones (TimeDict, scan_params.h): no calendar arithmetic
-__device__ __forceinline__ uint64_t tdict_rank(const TimeDict &T, uint64_t v) {
+__device__ __noinline__ uint64_t tdict_rank(const TimeDict &T, uint64_t v) {
   const uint64_t x = T.micro ? v / 1000000ull : v;
   uint32_t p = 0;
   for (uint32_t j = 1; j < T.npieces; ++j) p += x >= T.start[j] ? 1u : 0u;   // uniform loop, constant-bank operands

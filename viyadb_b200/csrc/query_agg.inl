@@ -170,10 +170,11 @@ DedupeMode choose_dedupe_mode(const vgpu_ctx *ctx, const vgpu_table *t, const Pa
 
 // sync-free paths: everything is sized from capacities, overflow raises a flag in the counter block
 void dedupe_enqueue(vgpu_ctx *ctx, QueryScope *sc, Scratch &scratch, DedupeMode mode, uint32_t nbuckets, const PairInput &in,
-                    const DistinctTarget &tg, uint32_t &launches) {
+                    const DistinctTarget &tg, uint32_t &launches, uint32_t &paths) {
   cudaStream_t stream = sc->s0;
   const uint64_t cap_total = (uint64_t)in.nregions * in.region_cap;
   if (cap_total == 0) return;
+  paths |= mode == kDedupeSmall ? VGPU_DEDUPE_SMALL : mode == kDedupeWide ? VGPU_DEDUPE_WIDE : VGPU_DEDUPE_FAST;
   if (mode == kDedupeSmall) {
     const uint64_t set_cap = pow2_ceil(std::max<uint64_t>(2 * cap_total, 1024));
     uint64_t *set = scratch.alloc<uint64_t>(set_cap);
@@ -254,8 +255,9 @@ void dedupe_enqueue(vgpu_ctx *ctx, QueryScope *sc, Scratch &scratch, DedupeMode 
 // General path, any size or skew (host knows `total`; synchronises): the pairs are hash-partitioned into buckets
 // whose open-addressing sets stay in L2, then each bucket is inserted into one reused global set.
 void dedupe_general(vgpu_ctx *ctx, QueryScope *sc, Scratch &scratch, const PairInput &in, uint64_t total, const DistinctTarget &tg,
-                    uint32_t &launches) {
+                    uint32_t &launches, uint32_t &paths) {
   if (total == 0) return;
+  paths |= VGPU_DEDUPE_GENERAL;
   cudaStream_t stream = sc->s0;
   const uint64_t bucket_pairs = ctx->test_bucket_pairs ? ctx->test_bucket_pairs : (1ull << 21);  // 2^22-slot set = 32 MB: stays in L2
   const uint32_t B = (uint32_t)std::min<uint64_t>(pow2_ceil((total + bucket_pairs - 1) / bucket_pairs), kMaxBuckets);
@@ -277,6 +279,7 @@ void dedupe_general(vgpu_ctx *ctx, QueryScope *sc, Scratch &scratch, const PairI
     ++launches;
     return;
   }
+  paths |= VGPU_DEDUPE_PARTITIONED;
   uint64_t bucket_cap = total / B + total / B / 8 + 8192;
   unsigned long long *cursors = scratch.alloc<unsigned long long>(kMaxBuckets + 1);
   std::vector<unsigned long long> h_cursors(kMaxBuckets + 1);
@@ -820,7 +823,7 @@ int vgpu_query_agg(vgpu_table *t, const vgpu_plan *plan, vgpu_result **out) {
     view.nmetrics = plan->nmetrics;
 
     CUDA_CK(cudaEventRecord(sc->ev_begin, stream));
-    uint32_t launches = 0;
+    uint32_t launches = 0, paths = 0;
     float scan_ms_total = 0;
 
     uint64_t hash_cap = 0;
@@ -1014,10 +1017,15 @@ int vgpu_query_agg(vgpu_table *t, const vgpu_plan *plan, vgpu_result **out) {
           attr[0].val.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
           cfg.numAttrs = 1;
         }
-        if (P.smem_cells) CUDA_CK(cudaLaunchKernelEx(&cfg, scan_filter_groupby_kernel<3, true>, P));
-        else if (ctx->ctas_per_sm == 2) CUDA_CK(cudaLaunchKernelEx(&cfg, scan_filter_groupby_kernel<2, false>, P));
-        else if (ctx->ctas_per_sm == 4) CUDA_CK(cudaLaunchKernelEx(&cfg, scan_filter_groupby_kernel<4, false>, P));
-        else CUDA_CK(cudaLaunchKernelEx(&cfg, scan_filter_groupby_kernel<3, false>, P));
+        bool plain_keys = P.tdict.npieces == 0 && !q.wide;
+        for (uint32_t k = 0; k < P.nkeys; ++k) plain_keys = plain_keys && !P.keys[k].rollup && !P.keys[k].fzero;
+        if (P.smem_cells) {
+          if (plain_keys) CUDA_CK(cudaLaunchKernelEx(&cfg, scan_filter_groupby_kernel<3, true, true>, P));
+          else CUDA_CK(cudaLaunchKernelEx(&cfg, scan_filter_groupby_kernel<3, true, false>, P));
+        } else if (ctx->ctas_per_sm == 2) CUDA_CK(cudaLaunchKernelEx(&cfg, scan_filter_groupby_kernel<2, false, false>, P));
+        else if (ctx->ctas_per_sm == 4) CUDA_CK(cudaLaunchKernelEx(&cfg, scan_filter_groupby_kernel<4, false, false>, P));
+        else if (plain_keys) CUDA_CK(cudaLaunchKernelEx(&cfg, scan_filter_groupby_kernel<3, false, true>, P));
+        else CUDA_CK(cudaLaunchKernelEx(&cfg, scan_filter_groupby_kernel<3, false, false>, P));
         ++launches;
       }
       CUDA_CK(cudaEventRecord(sc->ev_scan1, stream));
@@ -1034,6 +1042,7 @@ int vgpu_query_agg(vgpu_table *t, const vgpu_plan *plan, vgpu_result **out) {
         pin[d].wide = P.dpair_wide != 0;
         pin[d].expect = hint_load(t->pairs_total_hint);
         if (ctx->test_pairs_cap) pin[d].expect = 0;
+        if (ctx->test_expect) pin[d].expect = ctx->test_expect;
         dmode[d] = choose_dedupe_mode(ctx, t, pin[d], dnb[d]);
       }
 
@@ -1077,7 +1086,7 @@ int vgpu_query_agg(vgpu_table *t, const vgpu_plan *plan, vgpu_result **out) {
               // count-distinct: the owner's table holds every key it owns; dedupe the pairs of those keys against it
               for (uint32_t d = 0; d < P.ndistinct; ++d) {
                 DistinctTarget tg{static_cast<uint8_t *>(acc_ptrs[P.distinct_met[d]]), 4, P.hkeys, P.hmask};
-                dedupe_enqueue(ctx, sc, scratch, kDedupeWide, 0, pin[d], tg, launches);
+                dedupe_enqueue(ctx, sc, scratch, kDedupeWide, 0, pin[d], tg, launches, paths);
               }
             });
           }
@@ -1161,7 +1170,7 @@ int vgpu_query_agg(vgpu_table *t, const vgpu_plan *plan, vgpu_result **out) {
       auto run_dedupe = [&] {
         for (uint32_t d = 0; d < P.ndistinct; ++d) {
           DistinctTarget tg{static_cast<uint8_t *>(acc_ptrs[P.distinct_met[d]]), P.mets[P.distinct_met[d]].stride};
-          dedupe_enqueue(ctx, sc, scratch, dmode[d], dnb[d], pin[d], tg, launches);
+          dedupe_enqueue(ctx, sc, scratch, dmode[d], dnb[d], pin[d], tg, launches, paths);
         }
         if (G > 1) {  // every pair was counted on exactly one rank; a rank whose fast path overflowed tells everybody
           NCCL_CK(g_nccl.GroupStart());
@@ -1239,9 +1248,9 @@ int vgpu_query_agg(vgpu_table *t, const vgpu_plan *plan, vgpu_result **out) {
           DistinctTarget tg{static_cast<uint8_t *>(acc_ptrs[P.distinct_met[d]]), P.mets[P.distinct_met[d]].stride};
           if (dmode[d] == kDedupeGeneral) {
             // several ranks: pairs_total is the sum over all ranks, an upper bound of what this owner received
-            dedupe_general(ctx, sc, scratch, pin[d], pairs_total[d], tg, launches);
+            dedupe_general(ctx, sc, scratch, pin[d], pairs_total[d], tg, launches, paths);
           } else {
-            dedupe_enqueue(ctx, sc, scratch, dmode[d], dnb[d], pin[d], tg, launches);
+            dedupe_enqueue(ctx, sc, scratch, dmode[d], dnb[d], pin[d], tg, launches, paths);
           }
         }
         if (G > 1)
@@ -1251,14 +1260,17 @@ int vgpu_query_agg(vgpu_table *t, const vgpu_plan *plan, vgpu_result **out) {
       }
       // ---- the fast path reports bucket / set overflow through the counter block: run the general path instead ----
       auto redo_distinct_general = [&] {
-        t->distinct_general.store(1, std::memory_order_relaxed);
+        paths |= VGPU_DEDUPE_REDONE;
         for (uint32_t d = 0; d < P.ndistinct; ++d) {
           if (dmode[d] != kDedupeFast) continue;
           uint8_t *acc = static_cast<uint8_t *>(acc_ptrs[P.distinct_met[d]]);
           const uint32_t stride = P.mets[P.distinct_met[d]].stride;
+          // buckets sized from a good estimate and still too small: the data is too uneven for this table, stay general
+          if (pin[d].expect && pin[d].expect >= (G > 1 ? pairs_total[d] / G : pairs_total[d]) * 4 / 5 && !ctx->test_expect)
+            t->distinct_general.store(1, std::memory_order_relaxed);
           CUDA_CK(cudaMemset2DAsync(acc, stride, 0, 4, acc_cells_x, stream));  // forget the partial (and summed) counts
           DistinctTarget tg{acc, stride};
-          dedupe_general(ctx, sc, scratch, pin[d], pairs_total[d], tg, launches);
+          dedupe_general(ctx, sc, scratch, pin[d], pairs_total[d], tg, launches, paths);
           if (G > 1) NCCL_CK(g_nccl.AllReduce(acc, acc, q.ncells, ncclUint32, ncclSum, ctx->comm, stream));
         }
       };
@@ -1352,6 +1364,8 @@ int vgpu_query_agg(vgpu_table *t, const vgpu_plan *plan, vgpu_result **out) {
       view.launches = launches;
       view.table_mode = q.wide ? 2 : (q.hash_mode ? 1 : 0);
       view.table_cells = q.ncells;
+      view.attempts = (uint32_t)attempt + 1;
+      view.distinct_paths = paths;
       break;
     }
 

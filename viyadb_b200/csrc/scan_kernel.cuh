@@ -250,7 +250,9 @@ __device__ __noinline__ uint64_t wide_row_cell(const ScanParams &P, const CurSeg
 // kMinCtas CTAs per SM: caps the registers (3 -> 80, 4 -> 64); the host picks (VGPU_CTAS, default VGPU_MIN_CTAS)
 // kSmemTable: the instantiation that aggregates into a CTA-private shared-memory copy of a small dense group
 // table (ScanParams::smem_cells != 0); the other one carries none of that code.
-template <int kMinCtas, bool kSmemTable>
+// kPlainKeys: no group key needs a time rollup, a bucket-dictionary lookup or the -0.0 fix (the common case: dictionary
+// codes and plain integers): the per-key checks for them are compiled out of the per-row path, which is issue-bound.
+template <int kMinCtas, bool kSmemTable, bool kPlainKeys>
 __global__ void __launch_bounds__(kThreads, kMinCtas)
 scan_filter_groupby_kernel(const __grid_constant__ ScanParams P) {
   __shared__ uint32_t s_list[kWarps][kListCap];  // rows (of the warp's current segment) waiting for aggregation
@@ -325,9 +327,11 @@ scan_filter_groupby_kernel(const __grid_constant__ ScanParams P) {
           const uint32_t pos = rowpath ? ks.row_off : row * ks.width;
           uint64_t val = ((uint64_t)(kv[k] >> ((pos & 3u) * 8u))) & ks.vmask;
           val = (val ^ ks.signbit) - ks.signbit;
-          if (P.tdict.npieces && k == P.tdict.key) val = tdict_rank(P.tdict, val);  // rank of the rolled-up value
-          else if (ks.rollup) val = rollup_value(val, ks);
-          if (ks.fzero) val = fzero_fix(val, 4);
+          if (!kPlainKeys) {
+            if (P.tdict.npieces && k == P.tdict.key) val = tdict_rank(P.tdict, val);  // rank of the rolled-up value
+            else if (ks.rollup) val = rollup_value(val, ks);
+            if (ks.fzero) val = fzero_fix(val, 4);
+          }
           if (ks.lut) val = (uint64_t)__popcll(ks.lut & ((1ull << val) - 1ull));  // rank inside the IN list
           else val -= ks.lo;
           packed += val * ks.mul;
@@ -339,9 +343,11 @@ scan_filter_groupby_kernel(const __grid_constant__ ScanParams P) {
         const Slot &sl = P.slots[ks.slot];
         const uint8_t *a = seg.slab + sl.off * seg.cap + (uint64_t)row * sl.width;
         uint64_t val = gather_finish(gather_raw64(a), a, sl.vmask, sl.signbit);
-        if (P.tdict.npieces && k == P.tdict.key) val = tdict_rank(P.tdict, val);
-        else if (ks.rollup) val = rollup_value(val, ks);
-        if (ks.fzero) val = fzero_fix(val, sl.width);
+        if (!kPlainKeys) {
+          if (P.tdict.npieces && k == P.tdict.key) val = tdict_rank(P.tdict, val);
+          else if (ks.rollup) val = rollup_value(val, ks);
+          if (ks.fzero) val = fzero_fix(val, sl.width);
+        }
         if (ks.lut) val = (uint64_t)__popcll(ks.lut & ((1ull << val) - 1ull));
         else val -= ks.lo;
         packed += val * ks.mul;

@@ -302,7 +302,8 @@ struct vgpu_ctx {
   uint64_t test_hash_cap = 0;      // VGPU_TEST_HASH_CAP: first-attempt capacity of hashed group tables (x4 regrow)
   uint64_t test_bucket_pairs = 0;  // VGPU_TEST_BUCKET_PAIRS: pairs per L2-sized partition of the general dedupe path (B > 1)
   uint64_t test_small_pairs = 0;   // VGPU_TEST_SMALL_PAIRS: largest pair capacity deduplicated by one global set
-  uint32_t test_set_slots = 0;     // VGPU_TEST_SET_SLOTS: slots of the shared-memory sets (small: forces the fallback)
+  uint32_t test_set_slots = 0;     // VGPU_TEST_SET_SLOTS: slots of the shared-memory sets
+  uint64_t test_expect = 0;        // "expect_pairs": pairs the fast path sizes its buckets for (too few: overflow + fallback)
   // pool of pinned host blocks that back vgpu_result (D2H at full PCIe speed, no per-query
   // cudaMallocHost); shared with the results so that they may outlive the context
   std::shared_ptr<PinnedPool> pool = std::make_shared<PinnedPool>();
@@ -1116,7 +1117,8 @@ int vgpu_init(int device, vgpu_ctx **out) {
     cudaDeviceProp prop;
     CUDA_CK(cudaGetDeviceProperties(&prop, device));
     ctx->sm_count = prop.multiProcessorCount;
-    CUDA_CK(cudaFuncSetAttribute(scan_filter_groupby_kernel<3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemTableBytes));
+    CUDA_CK(cudaFuncSetAttribute(scan_filter_groupby_kernel<3, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemTableBytes));
+    CUDA_CK(cudaFuncSetAttribute(scan_filter_groupby_kernel<3, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemTableBytes));
     CUDA_CK(cudaFuncSetAttribute(pairs_bucket_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * kMaxSmemBuckets * 4)));
     CUDA_CK(cudaFuncSetAttribute(pairs_dedupe_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kSmemSetSlots * 8)));
     CUDA_CK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
@@ -1170,6 +1172,7 @@ int vgpu_set_test_hook(vgpu_ctx *ctx, const char *name, uint64_t value) {
     else if (n == "bucket_pairs") ctx->test_bucket_pairs = value;
     else if (n == "small_pairs") ctx->test_small_pairs = value;
     else if (n == "set_slots") ctx->test_set_slots = (uint32_t)value;
+    else if (n == "expect_pairs") ctx->test_expect = value;
     else if (n == "tune") ctx->tune = (uint32_t)value;
     else fail(VGPU_ERR_INVALID, "unknown test hook " + n);
   });

@@ -227,14 +227,15 @@ class Table:
             v = columns[c.name]
             si = self.schema_index(c)
             if c.kind == N.METRIC_BITSET:
+                idt = "<u8" if c.type == N.U64 else "<u4"   # util::Bitset<8> (Roaring64Map) ids travel as uint64
                 if isinstance(v, tuple):
                     offsets = np.ascontiguousarray(v[0], dtype="<u8")
-                    values = np.ascontiguousarray(v[1], dtype="<u4")
+                    values = np.ascontiguousarray(v[1], dtype=idt)
                     n = len(offsets) - 1
                     csr = N.BitsetCsr(offsets.ctypes.data_as(C.POINTER(C.c_uint64)), values.ctypes.data, len(values))
                     keep += [offsets, values]
                 else:
-                    values = np.ascontiguousarray(v, dtype="<u4")
+                    values = np.ascontiguousarray(v, dtype=idt)
                     n = len(values)
                     csr = N.BitsetCsr(None, values.ctypes.data, len(values))
                     keep.append(values)
@@ -318,9 +319,7 @@ class Table:
                 if c.kind == N.METRIC_BITSET:
                     offsets = np.frombuffer(blob, dtype="<u8", count=size + 1, offset=cj["off"])
                     values = np.frombuffer(blob, dtype="<u8", count=cj["values"], offset=cj["values_off"])
-                    if len(values) and int(values.max()) > 0xFFFFFFFF:
-                        raise N.VgpuError(N.ERR_UNSUPPORTED, "64-bit bitset ids are not supported yet")
-                    cols[c.name] = (offsets, values.astype("<u4"))
+                    cols[c.name] = (offsets, values)
                 else:
                     cols[c.name] = np.frombuffer(blob, dtype=N.NP_DTYPES[c.type], count=size, offset=cj["off"])
             hidden = None
@@ -381,6 +380,10 @@ class Database:
         return runner.stats
 
     # ---- multi-GPU: one process per GPU ----
+    def set_test_hook(self, name, value):
+        """vgpu_set_test_hook: force the rarely taken branches of the device path at test sizes."""
+        N.check(N.load().vgpu_set_test_hook(self.ctx, name.encode(), int(value)))
+
     def init_comm(self, rank, nranks, unique_id):
         N.check(N.load().vgpu_comm_init(self.ctx, rank, nranks, unique_id))
         self.rank, self.nranks = rank, nranks

@@ -394,6 +394,8 @@ class QueryStats:
         self.launches = 0
         self.table_mode = 0
         self.table_cells = 0
+        self.attempts = 0
+        self.distinct_paths = 0
 
 
 # ------------------------------------------------------------------------------------------------
@@ -558,6 +560,7 @@ class GpuQueryRunner:
         s.aggregated_recs, s.passed_rows = view.aggregated_recs, view.passed_rows
         s.gpu_ms, s.kernel_scan_ms, s.launches = view.gpu_ms, view.scan_ms, view.launches
         s.table_mode, s.table_cells = view.table_mode, view.table_cells
+        s.attempts, s.distinct_paths = view.attempts, view.distinct_paths
         return {"ngroups": n, "keys": keys, "accs": accs, "hidden_count": hidden, "_owner": owner}
 
     def _predicate(self, query):
@@ -630,7 +633,7 @@ class GpuQueryRunner:
                 d = dc.dim
                 if d.kind == N.DIM_STRING:
                     row[dc.index] = d.dict.c2v[int(v)]
-                elif d.kind == N.DIM_TIME and dc.format:
+                elif d.kind in (N.DIM_TIME, N.DIM_MICROTIME) and dc.format:
                     row[dc.index] = fmt_date(dc.format, int(v))
                 elif d.kind == N.DIM_BOOLEAN:
                     row[dc.index] = "true" if v else "false"
