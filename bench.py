@@ -204,9 +204,10 @@ def reference_job(wname, rows, row_offset, repeat):
             "queries": [w["query"]], "repeat": repeat}
 
 
-def run_reference(wname, rows_per_proc, procs, warmup, steps):
+def run_reference(wname, rows_per_proc, procs, warmup, steps, want_rows=False):
     """P shared-nothing single-threaded reference processes, each owning rows_per_proc rows, all
-    running the same query concurrently. Returns (rows/s, ms_per_step, total_rows, detail)."""
+    running the same query concurrently. Returns (rows/s, ms_per_step, total_rows, detail); with want_rows also the
+    formatted result rows of shard 0 (its rows are generator rows [0, rows_per_proc))."""
     cli = oracle_cli_path()
     if not os.path.exists(cli):
         return None
@@ -217,8 +218,8 @@ def run_reference(wname, rows_per_proc, procs, warmup, steps):
         jp = os.path.join(tmp, f"job{p}.json")
         json.dump(job, open(jp, "w"))
         ps.append(subprocess.Popen([cli, jp], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True))
-    per_proc, scanned = [], 0
-    for p in ps:
+    per_proc, scanned, rows0 = [], 0, None
+    for pi, p in enumerate(ps):
         out, err = p.communicate()
         lines = out.strip().splitlines()
         if p.returncode != 0 or not lines:
@@ -229,9 +230,11 @@ def run_reference(wname, rows_per_proc, procs, warmup, steps):
             return {"error": r["error"][-300:]}
         per_proc.append([t["whole_ms"] - t["compile_ms"] for t in r["timings"]][warmup:])
         scanned += r["stats"]["scanned_recs"]
+        if pi == 0 and want_rows:
+            rows0 = r["rows"]
     step_ms = [max(pp[i] for pp in per_proc) for i in range(steps)]
     ms = sum(step_ms) / len(step_ms)
-    return {"value": scanned / (ms / 1e3), "ms_per_step": ms, "rows": scanned, "best_ms": min(step_ms)}
+    return {"value": scanned / (ms / 1e3), "ms_per_step": ms, "rows": scanned, "best_ms": min(step_ms), "rows0": rows0}
 
 
 def main_reference(args):
@@ -272,26 +275,55 @@ def describe(wname):
 # ------------------------------------------------------------------------------------------------
 # the CUDA arm
 # ------------------------------------------------------------------------------------------------
-def main_ours(args):
-    import torch
-    import viyadb_b200 as v
+def parity_check(v, dist, rank, world, local, wname, check_rows):
+    """The CUDA path against the REAL reference on the same rows, inside the bench, at every N: rank 0 runs one
+    reference process (oracle/_ref/oracle_cli, the unmodified ViyaDB sources) over generator rows [0, check_rows);
+    all ranks scan the same rows, sharded round-robin and merged over NCCL like the timed table; the formatted
+    result rows must be identical as sorted sets."""
+    w = WORKLOADS[wname]
+    ref = None
+    if rank == 0:
+        ref = run_reference(wname, check_rows, 1, 0, 1, want_rows=True)
+    nseg = 2 * world + 1                                  # ragged on purpose
+    seg = (check_rows + nseg - 1) // nseg
+    conf = dict(w["table"], segment_size=seg)
+    db = v.Database({"tables": [conf]}, device=local)
+    try:
+        if world > 1:
+            uid = [v.Database.comm_unique_id() if rank == 0 else None]
+            dist.broadcast_object_list(uid, src=0)
+            db.init_comm(rank, world, uid[0])
+        t = db.get_table("events")
+        for d, g, prefix in zip(t.dimensions, w["gens"], w["prefix"]):
+            if d.dict is not None:
+                for k in range(1, g[0] + g[1]):
+                    d.dict.encode(f"{prefix}{k}")
+        ls = 0
+        for gs in range(nseg):
+            if gs % world != rank:
+                continue
+            n = min(seg, check_rows - gs * seg)
+            t.generate_segment(ls, n, w["gens"], seed=42, row_offset=gs * seg)
+            ls += 1
+        out = v.MemoryRowOutput()
+        stats = db.query(w["query"], out, now=NOW)
+    finally:
+        db.close()
+    if rank != 0:
+        return None
+    if ref is None or "error" in ref or ref.get("rows0") is None:
+        return {"rows": check_rows, "ok": None, "error": "reference unavailable: " + str((ref or {}).get("error", "oracle_cli missing"))}
+    got, want = sorted(out.rows), sorted(ref["rows0"])
+    return {"rows": check_rows, "groups": len(got), "reference_groups": len(want), "ok": got == want,
+            "scanned_recs": stats.scanned_recs, "n_gpus": world,
+            "against": "unmodified reference (oracle/_ref/oracle_cli), formatted rows compared as sorted sets"}
+
+
+def run_workload(args, wname, steps, torch, v, dist, rank, world, local, full):
+    """One workload on the resident table: returns the JSON line (rank 0) or None."""
     from viyadb_b200 import _native as N
     from viyadb_b200.query import GpuQueryRunner, QueryFactory
-
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if world != args.gpus and world > 1:
-        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device: viyadb_b200 has no CPU path")
-    torch.cuda.set_device(local)
-    dist = None
-    if world > 1:
-        import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-
-    w = WORKLOADS[args.workload]
+    w = WORKLOADS[wname]
     rows = args.rows or w["rows"]
     table_conf = dict(w["table"])
     db = v.Database({"tables": [table_conf]}, device=local)
@@ -343,7 +375,7 @@ def main_ours(args):
     torch.cuda.cudart().cudaProfilerStart()   # `ncu --profile-from-start off` lists the timed region only
     wall0 = time.time()
     ev0.record(stream)
-    for _ in range(args.steps):
+    for _ in range(steps):
         groups = step()
         scan_ms.append(runner.stats.kernel_scan_ms)
         gpu_ms.append(runner.stats.gpu_ms)
@@ -354,26 +386,102 @@ def main_ours(args):
     torch.cuda.cudart().cudaProfilerStop()
     elapsed_ms = ev0.elapsed_time(ev1)
     if dist is not None:
-        tt = torch.tensor([elapsed_ms, sum(scan_ms) / len(scan_ms)], device="cuda", dtype=torch.float64)
+        tt = torch.tensor([elapsed_ms, sum(scan_ms) / len(scan_ms), sum(gpu_ms) / len(gpu_ms)], device="cuda", dtype=torch.float64)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        elapsed_ms, scan_avg = tt.tolist()
+        elapsed_ms, scan_avg, gpu_avg = tt.tolist()
     else:
         scan_avg = sum(scan_ms) / len(scan_ms)
+        gpu_avg = sum(gpu_ms) / len(gpu_ms)
     clocks = sampler.stop(wall0, wall1) if rank == 0 else None
     total_rows = rows * world
-    passed = runner.stats.passed_rows
+    passed = runner.stats.passed_rows          # all ranks (summed in the merge)
     ngroups = groups["ngroups"]
-    selectivity = passed / max(1, runner.stats.scanned_recs)   # this rank's share
+    selectivity = passed / max(1, runner.stats.scanned_recs)
     b_alg = w["filter_bytes"] + selectivity * w["payload_bytes"]
     peak, peak_src = load_peaks()
-    traffic, traffic_src = load_traffic(args.workload) if rows == w["rows"] else (None, None)
-    achieved = rows * b_alg / (scan_avg / 1e3) / 1e9
-    value = total_rows * args.steps / (elapsed_ms / 1e3)
+    traffic, traffic_src = load_traffic(wname) if rows == w["rows"] else (None, None)
+    alg_bytes = rows * b_alg                   # per GPU and launch
+    achieved = alg_bytes / (scan_avg / 1e3) / 1e9
+    step_ms = elapsed_ms / steps
+    value = total_rows * steps / (elapsed_ms / 1e3)
+    paths = runner.stats.distinct_paths
 
     # ---- e2e: host buffers -> put_segment (H2D from pinned memory) -> query -> groups on host ----
+    resident = t.device_bytes
     e2e = None
-    if not args.no_e2e:
+    if full and not args.no_e2e:
         e2e = measure_e2e(torch, v, db, t, query, runner, plan, rows, nseg, world, dist, stream, args)
+    db.close()
+
+    line = None
+    if rank == 0:
+        line = {
+            "metric": "scanned rows/sec", "value": value, "unit": "rows/s", "n_gpus": world, "steps": steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": step_ms, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": w["dtype"], "data": "synthetic",
+            "config": {"workload": f"{wname} ({describe(wname)})", "rows_per_gpu": rows,
+                       "segments_per_gpu": nseg, "segment_size": SEG, "groups": ngroups,
+                       "selectivity": selectivity, "resident_bytes_per_gpu": resident,
+                       "l2_policy": "inputs larger than L2 (table >> 126 MB), no flush needed",
+                       "group_table": "dense" if runner.stats.table_mode == 0 else "hash",
+                       "count_distinct_path": [n for b, n in ((1, "one global set"), (2, "hash buckets + shared-memory sets"),
+                                                              (4, "16-byte pairs, global set"), (8, "L2 partitions + global sets"),
+                                                              (16, "fast path overflowed, redone")) if paths & b],
+                       "parallelism": f"segment-sharded x{world}, one NCCL merge of partial group tables" if world > 1 else "single GPU"},
+            # three fractions of the same algorithmic bytes: over the fused scan kernel alone, over the
+            # device time of the whole query (scan + count-distinct dedupe + merge + extraction, first to last
+            # operation on its stream), and over the wall-clock step (what `value` is computed from)
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "frac_query_device": alg_bytes / (gpu_avg / 1e3) / 1e9 / peak,
+                         "frac_step": alg_bytes / (step_ms / 1e3) / 1e9 / peak,
+                         "traffic": traffic, "traffic_unit": "bytes/launch (dram__bytes_read.sum + dram__bytes_write.sum)",
+                         "traffic_source": traffic_src, "kernel": "scan_filter_groupby_kernel", "kernel_ms": scan_avg,
+                         "algorithmic_bytes_per_row": b_alg, "algorithmic_bytes_per_launch": alg_bytes,
+                         "peak_source": peak_src},
+            "gpu_launches": launches, "gpu_ms_per_step": gpu_avg,
+            "clocks": clocks, "e2e": e2e, "generate_s": t_gen,
+        }
+    return line
+
+
+def main_ours(args):
+    import torch
+    import viyadb_b200 as v
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: viyadb_b200 has no CPU path")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    line = run_workload(args, args.workload, args.steps, torch, v, dist, rank, world, local, full=True)
+
+    # ---- the same path against the real reference on the same rows, at every N ----
+    check = None
+    if not args.no_check:
+        check = parity_check(v, dist, rank, world, local, args.workload, args.check_rows)
+
+    # ---- the other named configurations, driver-witnessed at every N (shorter runs) ----
+    also = {}
+    if args.workload == "c2" and not args.no_also and not args.rows:
+        for wname in ("c3", "c4"):
+            r = run_workload(args, wname, max(3, args.steps // 4), torch, v, dist, rank, world, local, full=False)
+            if r is not None:
+                also[wname] = {k: r[k] for k in ("value", "unit", "ms_per_step", "n_gpus", "steps", "gpu_launches", "gpu_ms_per_step")}
+                also[wname]["config"] = r["config"]
+                also[wname]["roofline"] = {k: r["roofline"][k] for k in ("frac", "frac_query_device", "frac_step", "kernel_ms", "achieved",
+                                                                           "algorithmic_bytes_per_row")}
+            if not args.no_check:
+                c = parity_check(v, dist, rank, world, local, wname, min(args.check_rows, 500_000))
+                if r is not None:
+                    also[wname]["parity_check"] = c
 
     # ---- CPU baseline (rank 0, N=1 only) ----
     cpu = None
@@ -391,29 +499,14 @@ def main_ours(args):
                    "sample": "unavailable: " + ("oracle_cli missing" if r is None else r["error"])}
 
     if rank == 0:
-        line = {
-            "metric": "scanned rows/sec", "value": value, "unit": "rows/s", "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": w["dtype"], "data": "synthetic",
-            "config": {"workload": f"{args.workload} ({describe(args.workload)})", "rows_per_gpu": rows,
-                       "segments_per_gpu": nseg, "segment_size": SEG, "groups": ngroups,
-                       "selectivity": selectivity, "resident_bytes_per_gpu": t.device_bytes,
-                       "l2_policy": "inputs larger than L2 (table >> 126 MB), no flush needed",
-                       "group_table": "dense" if runner.stats.table_mode == 0 else "hash",
-                       "parallelism": f"segment-sharded x{world}, one NCCL merge of partial group tables" if world > 1 else "single GPU"},
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "traffic_unit": "bytes/launch (dram__bytes_read.sum + dram__bytes_write.sum)",
-                         "traffic_source": traffic_src, "kernel": "scan_filter_groupby_kernel", "kernel_ms": scan_avg,
-                         "algorithmic_bytes_per_row": b_alg, "algorithmic_bytes_per_launch": rows * b_alg,
-                         "peak_source": peak_src},
-            "gpu_launches": launches, "gpu_ms_per_step": sum(gpu_ms) / len(gpu_ms),
-            "clocks": clocks, "e2e": e2e, "cpu_baseline": cpu, "generate_s": t_gen,
-        }
+        line["parity_check"] = check
+        line["cpu_baseline"] = cpu
+        if also:
+            line["also"] = also
         print(json.dumps(line))
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
-    db.close()
     return 0
 
 
@@ -491,6 +584,9 @@ def main():
     ap.add_argument("--e2e-rows", type=int, default=0, help="rows per GPU re-uploaded per e2e step (0 = the whole table)")
     ap.add_argument("--ref-rows", type=int, default=16_000_000, help="total rows of the bounded CPU sample")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-check", action="store_true", help="skip the in-bench parity check against the reference")
+    ap.add_argument("--no-also", action="store_true", help="skip the extra c3 / c4 lines of the default run")
+    ap.add_argument("--check-rows", type=int, default=1_000_000, help="rows of the in-bench parity check")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -1,7 +1,8 @@
 #!/usr/bin/env python
-"""Run under torchrun on N GPUs: every workload's N-GPU result (segments sharded round-robin, NCCL
-merge) must equal the single-GPU result over the union of all segments, bit for bit, on every rank.
-Prints MULTI_GPU_OK on rank 0."""
+"""Run under torchrun on N GPUs: every workload's N-GPU result (segments sharded round-robin, NCCL merge) must equal,
+on every rank, (1) the ORACLE's result (oracle/viya_oracle.py, pinned to the reference by tests/test_oracle_golden.py)
+over the union of all segments — formatted rows as sorted sets and all four QueryStats counters — and (2) the
+single-GPU result of the library, bit for bit. Prints MULTI_GPU_OK on rank 0."""
 import os
 import sys
 
@@ -11,7 +12,9 @@ import numpy as np
 import torch
 import torch.distributed as dist
 
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
 import bench
+import viya_oracle
 import viyadb_b200 as v
 from viyadb_b200 import dist as vdist
 from viyadb_b200.query import GpuQueryRunner, QueryFactory
@@ -39,7 +42,8 @@ def main():
     low = {"c1low": dict(bench.WORKLOADS["c1"], query=dict(bench.WORKLOADS["c1"]["query"], dimensions=["d0"], metrics=["m1", "m2", "count"])),
            "c2low": dict(bench.WORKLOADS["c2"], query=dict(bench.WORKLOADS["c2"]["query"], dimensions=["d1"], metrics=["mn", "mx", "uid"])),
            "c0": bench.WORKLOADS["c0"]}
-    for wname, flags in (("c1", 0), ("c2", 2), ("c3", 0), ("c4", 0), ("c1", 1), ("c3", 1), ("c1low", 0), ("c2low", 0), ("c0", 0)):
+    for wname, flags in (("c1", 0), ("c2", 2), ("c3", 0), ("c4", 0), ("c1", 1), ("c3", 1), ("c2", 1), ("c4", 1), ("c1low", 0), ("c2low", 0),
+                         ("c0", 0)):
         w = low.get(wname) or bench.WORKLOADS[wname]
         conf = dict(w["table"], segment_size=SEG)
         # sharded database, attached to the communicator
@@ -51,7 +55,7 @@ def main():
             t.generate_segment(ls, n, w["gens"], seed=42, row_offset=gs * SEG)
         for d, g, prefix in zip(t.dimensions, w["gens"], w["prefix"]):
             if d.dict is not None:
-                for k in range(1, min(g[0] + g[1], 1001)):
+                for k in range(1, min(g[0] + g[1], 20001)):
                     d.dict.encode(f"{prefix}{k}")
         # for the IN/eq literals to exist in the dictionaries of c1/c2 the prefixes above suffice
         keys, accs, stats = run(db, w, w["query"], flags)
@@ -67,6 +71,24 @@ def main():
         assert len(keys) == len(keys1) and all(np.array_equal(a, b) for a, b in zip(keys, keys1)), (wname, "keys differ")
         assert all(np.array_equal(a, b) for a, b in zip(accs, accs1)), (wname, "aggregates differ")
         assert stats.aggregated_recs == stats1.aggregated_recs
+        for k in ("scanned_recs", "scanned_segments", "passed_rows"):
+            assert getattr(stats, k) == getattr(stats1, k), (wname, k, getattr(stats, k), getattr(stats1, k))
+        # (1) against the oracle: the union table read back from the device, formatted rows + QueryStats
+        segs = []
+        for gs in range(nseg_global):
+            n = SEG if gs < nseg_global - 1 else SEG // 3
+            seg = {}
+            for c in t1.dimensions + t1.metrics:
+                col = t1.read_column(gs, c, n)
+                seg[c.name] = (np.arange(n + 1, dtype="<u8"), col.astype("<u8")) if c.kind == v._native.METRIC_BITSET else col
+            segs.append(seg)
+        dicts = {d.name: list(d.dict.c2v) for d in t1.dimensions if d.dict is not None}
+        want = viya_oracle.run_query(conf, segs, dicts, w["query"], now=bench.NOW)
+        out = v.MemoryRowOutput()
+        st = db.query(w["query"], out, now=bench.NOW, flags=flags)
+        assert sorted(out.rows) == sorted(want["rows"]), (wname, flags, "rows differ from the oracle")
+        for k in ("scanned_segments", "scanned_recs", "aggregated_recs", "output_recs"):
+            assert getattr(st, k) == want["stats"][k], (wname, k, getattr(st, k), want["stats"][k])
         if rank == 0:
             print(f"{wname} flags={flags}: {stats.aggregated_recs} groups identical on {world} GPUs "
                   f"(table mode {stats.table_mode})", flush=True)
