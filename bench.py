@@ -189,7 +189,7 @@ def oracle_cli_path():
     return os.path.join(ROOT, "oracle", "_ref", "oracle_cli")
 
 
-def reference_job(wname, rows, row_offset, repeat):
+def reference_job(wname, rows, row_offset, repeat, dump=None):
     w = WORKLOADS[wname]
     cols = []
     table = w["table"]
@@ -199,12 +199,15 @@ def reference_job(wname, rows, row_offset, repeat):
         if mt is not None and mt["type"] == "count":
             continue  # count is not an input column
         cols.append({"prefix": prefix, "lo": g[0], "range": g[1]})
-    return {"state_dir": os.path.join(ROOT, "oracle", "_ref", "state"), "rollup_ts": NOW, "table": table,
-            "generate": {"n": rows, "seed": 42, "row_offset": row_offset, "columns": cols},
-            "queries": [w["query"]], "repeat": repeat}
+    job = {"state_dir": os.path.join(ROOT, "oracle", "_ref", "state"), "rollup_ts": NOW, "table": table,
+           "generate": {"n": rows, "seed": 42, "row_offset": row_offset, "columns": cols},
+           "queries": [w["query"]], "repeat": repeat}
+    if dump:
+        job["dump"] = dump
+    return job
 
 
-def run_reference(wname, rows_per_proc, procs, warmup, steps, want_rows=False):
+def run_reference(wname, rows_per_proc, procs, warmup, steps, want_rows=False, dump=None):
     """P shared-nothing single-threaded reference processes, each owning rows_per_proc rows, all
     running the same query concurrently. Returns (rows/s, ms_per_step, total_rows, detail); with want_rows also the
     formatted result rows of shard 0 (its rows are generator rows [0, rows_per_proc))."""
@@ -214,7 +217,7 @@ def run_reference(wname, rows_per_proc, procs, warmup, steps, want_rows=False):
     tmp = tempfile.mkdtemp(prefix="vgpu_ref_")
     ps = []
     for p in range(procs):
-        job = reference_job(wname, rows_per_proc, p * rows_per_proc, warmup + steps)
+        job = reference_job(wname, rows_per_proc, p * rows_per_proc, warmup + steps, dump if p == 0 else None)
         jp = os.path.join(tmp, f"job{p}.json")
         json.dump(job, open(jp, "w"))
         ps.append(subprocess.Popen([cli, jp], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True))
@@ -276,47 +279,48 @@ def describe(wname):
 # the CUDA arm
 # ------------------------------------------------------------------------------------------------
 def parity_check(v, dist, rank, world, local, wname, check_rows):
-    """The CUDA path against the REAL reference on the same rows, inside the bench, at every N: rank 0 runs one
-    reference process (oracle/_ref/oracle_cli, the unmodified ViyaDB sources) over generator rows [0, check_rows);
-    all ranks scan the same rows, sharded round-robin and merged over NCCL like the timed table; the formatted
-    result rows must be identical as sorted sets."""
+    """The CUDA path against the REAL reference on the same table, inside the bench, at every N: rank 0 runs one
+    reference process (oracle/_ref/oracle_cli, the unmodified ViyaDB sources) that ingests generator rows
+    [0, check_rows), answers the query and dumps its segments; all ranks upload those very segments — cut into pieces,
+    sharded round-robin and merged over NCCL like the timed table — and the formatted result rows must be identical
+    as sorted sets."""
     w = WORKLOADS[wname]
-    ref = None
+    ref, dump = None, [None]
     if rank == 0:
-        ref = run_reference(wname, check_rows, 1, 0, 1, want_rows=True)
-    nseg = 2 * world + 1                                  # ragged on purpose
-    seg = (check_rows + nseg - 1) // nseg
-    conf = dict(w["table"], segment_size=seg)
-    db = v.Database({"tables": [conf]}, device=local)
+        dump[0] = os.path.join(tempfile.mkdtemp(prefix="vgpu_check_"), "segments.bin")
+        ref = run_reference(wname, check_rows, 1, 0, 1, want_rows=True, dump=dump[0])
+        if ref is None or "error" in ref:
+            dump[0] = None
+    if dist is not None:
+        dist.broadcast_object_list(dump, src=0)
+    if dump[0] is None:
+        return {"rows": check_rows, "ok": None,
+                "error": "reference unavailable: " + str((ref or {}).get("error", "oracle_cli missing"))} if rank == 0 else None
+    db = v.Database({"tables": [dict(w["table"])]}, device=local)
     try:
         if world > 1:
             uid = [v.Database.comm_unique_id() if rank == 0 else None]
             dist.broadcast_object_list(uid, src=0)
             db.init_comm(rank, world, uid[0])
         t = db.get_table("events")
-        for d, g, prefix in zip(t.dimensions, w["gens"], w["prefix"]):
-            if d.dict is not None:
-                for k in range(1, g[0] + g[1]):
-                    d.dict.encode(f"{prefix}{k}")
-        ls = 0
-        for gs in range(nseg):
-            if gs % world != rank:
-                continue
-            n = min(seg, check_rows - gs * seg)
-            t.generate_segment(ls, n, w["gens"], seed=42, row_offset=gs * seg)
-            ls += 1
+        chunk = max(1, check_rows // (2 * world + 1))          # ragged on purpose
+        t.load_dump(dump[0], shard=(rank, world), chunk_rows=chunk)
         out = v.MemoryRowOutput()
         stats = db.query(w["query"], out, now=NOW)
     finally:
         db.close()
+    if dist is not None:
+        dist.barrier()
     if rank != 0:
         return None
-    if ref is None or "error" in ref or ref.get("rows0") is None:
-        return {"rows": check_rows, "ok": None, "error": "reference unavailable: " + str((ref or {}).get("error", "oracle_cli missing"))}
+    try:
+        os.remove(dump[0])
+    except OSError:
+        pass
     got, want = sorted(out.rows), sorted(ref["rows0"])
-    return {"rows": check_rows, "groups": len(got), "reference_groups": len(want), "ok": got == want,
-            "scanned_recs": stats.scanned_recs, "n_gpus": world,
-            "against": "unmodified reference (oracle/_ref/oracle_cli), formatted rows compared as sorted sets"}
+    return {"rows": check_rows, "table_rows": stats.scanned_recs, "groups": len(got), "reference_groups": len(want),
+            "ok": got == want, "n_gpus": world,
+            "against": "unmodified reference (oracle/_ref/oracle_cli): its own segments uploaded, formatted rows compared as sorted sets"}
 
 
 def run_workload(args, wname, steps, torch, v, dist, rank, world, local, full):

@@ -93,3 +93,34 @@ def test_gpu_runner_select_search_equals_stock_runner(sc):
         assert gpu["rows"] == stock["rows"] == gold["rows"], (qi, gpu["rows"][:3], stock["rows"][:3])
         for k in ("scanned_segments", "scanned_recs", "aggregated_recs", "output_recs"):
             assert gpu["stats"][k] == stock["stats"][k] == gold["stats"][k], (qi, k, gpu["stats"], stock["stats"])
+
+
+def test_resident_copy_follows_in_place_upserts():
+    """A second ingest batch into the SAME dimension tuples updates metric cells of existing rows in place
+    (src/codegen/db/upsert.cc:386-393): no segment grows, yet the resident HBM copy is stale. The GPU runner must
+    return what the stock runner returns, before and after."""
+    if not os.path.exists(D.CLI):
+        pytest.skip("vgpu_cli not built (needs the reference headers: make -C oracle gpu_cli)")
+    sc = next(s for s in scenarios.SCENARIOS if s["name"] == "inapp")
+    # same tuples again with other metric values, plus one new tuple
+    reload_rows = [r[:3] + [str(float(r[3]) * 3 + 1)] for r in sc["rows"]] + [["IL", "gift", "20141114", "7.5"]]
+    out = D.run_scenario(dict(sc, reload_rows=reload_rows))
+    assert "fatal" not in out, out.get("fatal")
+    changed = 0
+    for key in ("results", "results_after_reload"):
+        for qi, res in enumerate(out[key]):
+            stock, gpu = res["stock"], res["gpu"]
+            assert ("error" in stock) == ("error" in gpu), (key, qi)
+            if "error" in stock:
+                continue
+            q = sc["queries"][qi]
+            if (q.get("limit") or q.get("skip")) and not q.get("sort"):
+                assert len(gpu["rows"]) == len(stock["rows"]), (key, qi)
+            else:
+                assert rows_equal_numeric(gpu["rows"], stock["rows"]), (key, qi, gpu["rows"][:3], stock["rows"][:3])
+            for k in ("scanned_segments", "scanned_recs", "aggregated_recs", "output_recs"):
+                assert gpu["stats"][k] == stock["stats"][k], (key, qi, k)
+    for a, b in zip(out["results"], out["results_after_reload"]):
+        if "error" not in a["stock"] and sorted(a["stock"]["rows"]) != sorted(b["stock"]["rows"]):
+            changed += 1
+    assert changed > 0, "the second batch must change some results, or the test proves nothing"

@@ -301,9 +301,11 @@ class Table:
             self._handle = None
 
     # ---- loading the reference's own segments (oracle_cli "dump": VGPUSEG1 container) ----
-    def load_dump(self, path):
+    def load_dump(self, path, shard=None, chunk_rows=None):
         """Upload segments dumped from the reference's SegmentStore so the CUDA path scans the very
-        bytes the reference scanned. Returns the dump header."""
+        bytes the reference scanned. Returns the dump header. With chunk_rows the reference's segments are cut
+        into pieces of that many rows; with shard=(rank, world) only every world-th piece is uploaded (one process
+        per GPU: the pieces of all ranks together are the reference's table)."""
         hdr, blob = read_dump(path)
         for d in self.dimensions:
             if d.kind == N.DIM_STRING:
@@ -312,7 +314,8 @@ class Table:
                 d.dict.v2c = {v: i for i, v in enumerate(c2v)}
         ncol_file = len(hdr["dims"]) + len(hdr["metrics"])
         assert ncol_file == len(self.dimensions) + len(self.metrics), "dump/schema column count mismatch"
-        for si, seg in enumerate(hdr["segments"]):
+        piece, local = 0, 0
+        for seg in hdr["segments"]:
             size = seg["size"]
             cols = {}
             for c, cj in zip(self.dimensions + self.metrics, seg["cols"]):
@@ -325,7 +328,22 @@ class Table:
             hidden = None
             if self.has_hidden_count:
                 hidden = np.frombuffer(blob, dtype="<u8", count=size, offset=seg["hidden_count"]["off"])
-            self.put_segment(si, cols, hidden)
+            step = chunk_rows or max(size, 1)
+            for lo in range(0, max(size, 1), step):
+                hi = min(size, lo + step)
+                mine = shard is None or piece % shard[1] == shard[0]
+                piece += 1
+                if not mine:
+                    continue
+                part = {}
+                for name, v in cols.items():
+                    if isinstance(v, tuple):
+                        o = v[0][lo:hi + 1]
+                        part[name] = (o - o[0], v[1][int(o[0]):int(o[-1])]) if len(o) else (np.zeros(1, "<u8"), v[1][:0])
+                    else:
+                        part[name] = v[lo:hi]
+                self.put_segment(local, part, None if hidden is None else hidden[lo:hi])
+                local += 1
         return hdr
 
 

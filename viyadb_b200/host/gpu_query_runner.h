@@ -47,6 +47,7 @@
 #include <cstring>
 #include <ctime>
 #include <functional>
+#include <atomic>
 #include <map>
 #include <unordered_set>
 #include <memory>
@@ -109,6 +110,23 @@ inline uint32_t vgpu_type_of(const db::Column *col) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// Ingest notifications. The reference's upsert aggregates into EXISTING tuples in place
+// (src/codegen/db/upsert.cc:386-393, `m.Update(upsert_tuple.m, tuple_idx)`): metric cells — and bitset cells — of
+// any segment may change without any SegmentBase::size() changing, so "size unchanged" does not mean "resident copy
+// still valid". Every load batch ends in input::Loader::AfterLoad() (src/input/loader.cc:39); the integration calls
+// IngestEpoch::Bump() there (the gtest drop-in binary wraps that very function), and a binding whose
+// epoch is behind re-uploads its table on the next query.
+// ---------------------------------------------------------------------------------------------
+struct IngestEpoch {
+  static std::atomic<uint64_t> &counter() {
+    static std::atomic<uint64_t> c{1};
+    return c;
+  }
+  static void Bump() { counter().fetch_add(1, std::memory_order_release); }
+  static uint64_t Load() { return counter().load(std::memory_order_acquire); }
+};
+
+// ---------------------------------------------------------------------------------------------
 // one db::Table resident in HBM
 // ---------------------------------------------------------------------------------------------
 class GpuTableBinding {
@@ -138,6 +156,10 @@ public:
       if (m->agg_type() == db::Metric::AggregationType::BITSET) {
         c.kind = VGPU_METRIC_BITSET;
         c.type = m->num_type().size() == db::BaseNumType::_8 ? VGPU_U64 : VGPU_U32;
+        // ubyte / ushort bitsets travel as uint32, but the AnyNum image of a filter literal only defines the
+        // bytes of its own type (src/db/column.h:98-121): tell the library which ones to look at
+        if (m->num_type().size() == db::BaseNumType::_1) c.lit_type = VGPU_U8 + 1;
+        if (m->num_type().size() == db::BaseNumType::_2) c.lit_type = VGPU_U16 + 1;
       } else {
         c.kind = VGPU_METRIC_VALUE;
         c.type = vgpu_type_of(m);
@@ -176,6 +198,12 @@ public:
   // Snapshot semantics of scan.cc:42-44: the segment list is copied, each size() read once.
   void Sync() {
     std::lock_guard<std::mutex> lk(mu_);
+    // an ingest batch finished since the last upload: cells of any segment may have been updated in place
+    const uint64_t epoch = IngestEpoch::Load();
+    if (epoch != epoch_seen_) {
+      std::fill(uploaded_.begin(), uploaded_.end(), static_cast<size_t>(-1));
+      epoch_seen_ = epoch;
+    }
     auto segments = table_.store()->segments_copy();
     if (uploaded_.size() < segments.size()) uploaded_.resize(segments.size(), static_cast<size_t>(-1));
     std::vector<const void *> dims(ndims_), metrics(nmetrics_);
@@ -188,6 +216,7 @@ public:
       std::vector<const void *> ptrs;
       std::vector<std::vector<uint64_t>> offsets_keep;
       std::vector<std::vector<uint32_t>> values_keep;
+      std::vector<std::vector<uint64_t>> wide_keep;
       std::vector<std::unique_ptr<vgpu_bitset_csr>> csr_keep;
       for (size_t d = 0; d < ndims_; ++d) ptrs.push_back(dims[d]);
       for (auto *m : table_.metrics()) {
@@ -199,15 +228,17 @@ public:
         offsets_keep.emplace_back(size + 1);
         auto &offsets = offsets_keep.back();
         uint64_t total = access_.bitset()(segments[si], m->index(), size, offsets.data(), nullptr);
-        std::vector<uint64_t> wide(total + 1);
+        wide_keep.emplace_back(total + 1);
+        auto &wide = wide_keep.back();
         access_.bitset()(segments[si], m->index(), size, offsets.data(), wide.data());
-        values_keep.emplace_back(total + 1);
-        auto &values = values_keep.back();
-        for (uint64_t i = 0; i < total; ++i) {
-          if (wide[i] > 0xffffffffull) throw std::runtime_error("64-bit bitset ids are not supported on the GPU path yet");
-          values[i] = static_cast<uint32_t>(wide[i]);
+        if (m->num_type().size() == db::BaseNumType::_8) {   // util::Bitset<8> = Roaring64Map: ids travel as uint64
+          csr_keep.emplace_back(new vgpu_bitset_csr{offsets.data(), wide.data(), total});
+        } else {
+          values_keep.emplace_back(total + 1);
+          auto &values = values_keep.back();
+          for (uint64_t i = 0; i < total; ++i) values[i] = static_cast<uint32_t>(wide[i]);
+          csr_keep.emplace_back(new vgpu_bitset_csr{offsets.data(), values.data(), total});
         }
-        csr_keep.emplace_back(new vgpu_bitset_csr{offsets.data(), values.data(), total});
         ptrs.push_back(csr_keep.back().get());
       }
       if (hidden_) ptrs.push_back(hidden);
@@ -223,6 +254,7 @@ private:
   size_t ndims_ = 0, nmetrics_ = 0;
   bool hidden_ = false;
   std::vector<size_t> uploaded_;
+  uint64_t epoch_seen_ = 0;
   std::mutex mu_;
 };
 

@@ -108,7 +108,8 @@ int main(int argc, char **argv) {
       // pre-warm the accessor .so too (SegmentAccess compiles through the reference's Compiler)
       vgpu_host::SegmentAccess access(*table);
     }
-    out["results"] = json::array();
+    auto run_queries = [&](const char *key) {
+    out[key] = json::array();
     for (auto &q : job["queries"]) {
       json res;
       for (int pass = 0; pass < (stock_only ? 1 : 2); ++pass) {
@@ -132,7 +133,27 @@ int main(int argc, char **argv) {
           res[name] = {{"error", e.what()}, {"error_type", "exception"}};
         }
       }
-      out["results"].push_back(res);
+      out[key].push_back(res);
+    }
+    };
+    run_queries("results");
+    // Second ingest batch into the SAME dimension tuples: the reference's upsert updates the metric cells of existing
+    // rows in place (src/codegen/db/upsert.cc:386-393), no segment size changes. The integration's one line in
+    // input::Loader::AfterLoad — IngestEpoch::Bump() — tells the resident copy it is stale.
+    if (job.count("reload_rows")) {
+      struct L : input::SimpleLoader {
+        using input::SimpleLoader::SimpleLoader;
+        void Before() { BeforeLoad(); }
+        void After() { AfterLoad(); }
+      } l(*table);
+      l.Before();
+      for (auto &r : job["reload_rows"]) {
+        std::vector<std::string> row = r.get<std::vector<std::string>>();
+        l.Load(row);
+      }
+      l.After();
+      vgpu_host::IngestEpoch::Bump();
+      run_queries("results_after_reload");
     }
     bindings.clear();
     if (ctx) vgpu_shutdown(ctx);
