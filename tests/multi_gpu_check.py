@@ -42,8 +42,11 @@ def main():
     low = {"c1low": dict(bench.WORKLOADS["c1"], query=dict(bench.WORKLOADS["c1"]["query"], dimensions=["d0"], metrics=["m1", "m2", "count"])),
            "c2low": dict(bench.WORKLOADS["c2"], query=dict(bench.WORKLOADS["c2"]["query"], dimensions=["d1"], metrics=["mn", "mx", "uid"])),
            "c0": bench.WORKLOADS["c0"]}
+    only = os.environ.get("VGPU_CHECK_ONLY")
     for wname, flags in (("c1", 0), ("c2", 2), ("c3", 0), ("c4", 0), ("c1", 1), ("c3", 1), ("c2", 1), ("c4", 1), ("c1low", 0), ("c2low", 0),
                          ("c0", 0)):
+        if only and wname != only:
+            continue
         w = low.get(wname) or bench.WORKLOADS[wname]
         conf = dict(w["table"], segment_size=SEG)
         # sharded database, attached to the communicator
@@ -69,6 +72,15 @@ def main():
             d1.dict = d.dict
         keys1, accs1, stats1 = run(db1, w, w["query"], flags)
         assert len(keys) == len(keys1) and all(np.array_equal(a, b) for a, b in zip(keys, keys1)), (wname, "keys differ")
+        for mi, (a, b) in enumerate(zip(accs, accs1)):
+            if not np.array_equal(a, b):
+                bad = np.nonzero(a != b)[0]
+                if rank == 0:
+                    cells = [int(k.astype(np.int64)[bad[0]]) for k in keys]
+                    print(f"[rank 0] bad group index range {bad.min()}..{bad.max()} (keys of first: {cells}); runs of consecutive bad: "
+                          f"{int((np.diff(bad) == 1).sum())}", flush=True)
+                print(f"[rank {rank}] {wname} flags={flags}: aggregate {mi} differs in {len(bad)} of {len(a)} groups; sums {int(a.astype(np.int64).sum())} vs "
+                      f"{int(b.astype(np.int64).sum())}; first {a[bad[:5]].tolist()} vs {b[bad[:5]].tolist()}; paths {stats.distinct_paths} attempts {stats.attempts}", flush=True)
         assert all(np.array_equal(a, b) for a, b in zip(accs, accs1)), (wname, "aggregates differ")
         assert stats.aggregated_recs == stats1.aggregated_recs
         for k in ("scanned_recs", "scanned_segments", "passed_rows"):

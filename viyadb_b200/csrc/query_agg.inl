@@ -1056,7 +1056,12 @@ int vgpu_query_agg(vgpu_table *t, const vgpu_plan *plan, vgpu_result **out) {
         counters_read = true;
       };
       if (G > 1) {
-        NCCL_CK(g_nccl.GroupStart());
+        // One launch per all-reduce. Measured on 8 B200s (NCCL 2.28.9, tools/gpu_n8_debug.sh): with the all-reduces of the
+        // accumulator arrays inside ONE ncclGroup the NVLS algorithm lost min-updates of the first array in ~2 % of the
+        // cells (a different set every run); ungrouped, NCCL_ALGO=Ring and NCCL_NVLS_ENABLE=0 are all exact. Only the
+        // point-to-point exchange of the count-distinct pairs needs a group. VGPU_NCCL_GROUP=1 restores the grouped form.
+        static const bool ungroup = getenv("VGPU_NCCL_GROUP") == nullptr;
+        if (!ungroup) NCCL_CK(g_nccl.GroupStart());
         NCCL_CK(g_nccl.AllReduce(sc->d_counters + kCSumFirst, sc->d_counters + kCSumFirst, kCMaxFirst - kCSumFirst, ncclUint64,
                                  ncclSum, ctx->comm, stream));
         NCCL_CK(g_nccl.AllReduce(sc->d_counters + kCMaxFirst, sc->d_counters + kCMaxFirst, kCLocalFirst - kCMaxFirst, ncclUint64,
@@ -1069,6 +1074,7 @@ int vgpu_query_agg(vgpu_table *t, const vgpu_plan *plan, vgpu_result **out) {
           NCCL_CK(g_nccl.AllReduce(P.present, P.present, q.ncells, ncclUint8, ncclMax, ctx->comm, stream));
         }
         // pairs to their owners: what a rank receives has the shape of what it sends
+        if (ungroup && P.ndistinct) NCCL_CK(g_nccl.GroupStart());
         for (uint32_t d = 0; d < P.ndistinct; ++d) {
           void *recv = scratch.alloc<uint8_t>(region_cap64 * nregions * pair_elem);
           uint32_t *recv_counts = scratch.alloc<uint32_t>(nregions);
@@ -1076,7 +1082,7 @@ int vgpu_query_agg(vgpu_table *t, const vgpu_plan *plan, vgpu_result **out) {
           pin[d].pairs = recv;
           pin[d].counts = recv_counts;
         }
-        NCCL_CK(g_nccl.GroupEnd());
+        if (!ungroup || P.ndistinct) NCCL_CK(g_nccl.GroupEnd());
         if (q.hash_mode) {
           // every rank must take the same grow-and-retry decision before the records travel
           read_counters(stream);
@@ -1173,11 +1179,9 @@ int vgpu_query_agg(vgpu_table *t, const vgpu_plan *plan, vgpu_result **out) {
           dedupe_enqueue(ctx, sc, scratch, dmode[d], dnb[d], pin[d], tg, launches, paths);
         }
         if (G > 1) {  // every pair was counted on exactly one rank; a rank whose fast path overflowed tells everybody
-          NCCL_CK(g_nccl.GroupStart());
           for (uint32_t d = 0; d < P.ndistinct; ++d)
             NCCL_CK(g_nccl.AllReduce(acc_ptrs[P.distinct_met[d]], acc_ptrs[P.distinct_met[d]], q.ncells, ncclUint32, ncclSum, ctx->comm, stream));
           NCCL_CK(g_nccl.AllReduce(sc->d_counters + kCBucketOver, sc->d_counters + kCBucketOver, 2, ncclUint64, ncclMax, ctx->comm, stream));
-          NCCL_CK(g_nccl.GroupEnd());
         }
       };
 
