@@ -114,6 +114,10 @@ SYMBOLS = [
     ("vgpu_table_create", C.c_int, [C.c_void_p, C.POINTER(Schema), C.POINTER(C.c_void_p)]),
     ("vgpu_table_free", None, [C.c_void_p]),
     ("vgpu_segment_put", C.c_int, [C.c_void_p, C.c_uint32, C.c_uint64, C.POINTER(C.c_void_p)]),
+    ("vgpu_segment_put_async", C.c_int, [C.c_void_p, C.c_uint32, C.c_uint64, C.POINTER(C.c_void_p)]),
+    ("vgpu_table_sync", C.c_int, [C.c_void_p]),
+    ("vgpu_host_pin", C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
+    ("vgpu_host_unpin", C.c_int, [C.c_void_p, C.c_void_p]),
     ("vgpu_table_invalidate", C.c_int, [C.c_void_p, C.c_uint32]),
     ("vgpu_table_segments", C.c_uint32, [C.c_void_p]),
     ("vgpu_table_rows", C.c_uint64, [C.c_void_p]),

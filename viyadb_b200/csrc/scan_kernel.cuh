@@ -241,6 +241,47 @@ __device__ __noinline__ uint64_t wide_row_cell(const ScanParams &P, const CurSeg
   return wide_cell(P, kw);
 }
 
+// Key tuples outside the register-staged fast path (more than 4 keys, or 8-byte keys): gather, roll up and pack one
+// row's key. Out of line: its registers must not weigh on the common path (the kernel is capped at 80).
+template <bool kPlainKeys>
+__device__ __noinline__ uint64_t general_row_key(const ScanParams &P, const CurSeg &seg, uint32_t row) {
+  uint64_t packed = 0;
+  for (uint32_t k = 0; k < P.nkeys; ++k) {
+    const KeySpec &ks = P.keys[k];
+    const Slot &sl = P.slots[ks.slot];
+    const uint8_t *a = seg.slab + sl.off * seg.cap + (uint64_t)row * sl.width;
+    uint64_t val = gather_finish(gather_raw64(a), a, sl.vmask, sl.signbit);
+    if (!kPlainKeys) {
+      if (P.tdict.npieces && k == P.tdict.key) val = tdict_rank(P.tdict, val);
+      else if (ks.rollup) val = rollup_value(val, ks);
+      if (ks.fzero) val = fzero_fix(val, sl.width);
+    }
+    if (ks.lut) val = (uint64_t)__popcll(ks.lut & ((1ull << val) - 1ull));
+    else val -= ks.lo;
+    packed += val * ks.mul;
+  }
+  return packed;
+}
+__device__ __noinline__ uint64_t hash_cell_call(const ScanParams &P, uint64_t key) { return hash_cell(P, key); }
+
+// append one count-distinct pair to the CTA's region of the pair's owner rank; `cursor` = s_cursor[dn]
+__device__ __forceinline__ void append_pair(const ScanParams &P, uint32_t *cursor, uint32_t dn, uint64_t hi, uint64_t id) {
+  uint32_t sub = 0;
+  if (P.dpair_nsub > 1) sub = P.dpair_key ? owner_of(hi, 0, P.dpair_nsub) : pair_owner(hi, id, P.dpair_nsub);
+  const uint32_t pos = atomicAdd(cursor + sub, 1u);
+  if (pos < P.dpair_cap) {
+    const uint64_t at = ((uint64_t)sub * gridDim.x + blockIdx.x) * P.dpair_cap + pos;
+    if (P.dpair_wide) reinterpret_cast<ulonglong2 *>(P.dpairs[dn])[at] = make_ulonglong2(hi, id);
+    else P.dpairs[dn][at] = (hi << 32) | id;
+  }
+}
+// a bitset cell that holds several ids (CSR): rare after ingesting raw rows, out of line
+__device__ __noinline__ void append_csr_cell(const ScanParams &P, uint32_t *cursor, uint32_t dn, uint64_t hi, const uint32_t *vals,
+                                             uint32_t lo, uint32_t hi_q, uint32_t id64) {
+  for (uint32_t q = lo; q < hi_q; ++q)
+    append_pair(P, cursor, dn, hi, id64 ? __ldg(reinterpret_cast<const unsigned long long *>(vals) + q) : (uint64_t)gather_u32(vals + q));
+}
+
 // ---------------------------------------------------------------------------------------------
 // the fused scan kernel
 // ---------------------------------------------------------------------------------------------
@@ -338,20 +379,7 @@ scan_filter_groupby_kernel(const __grid_constant__ ScanParams P) {
         }
       }
     } else {
-      for (uint32_t k = 0; k < P.nkeys; ++k) {
-        const KeySpec &ks = P.keys[k];
-        const Slot &sl = P.slots[ks.slot];
-        const uint8_t *a = seg.slab + sl.off * seg.cap + (uint64_t)row * sl.width;
-        uint64_t val = gather_finish(gather_raw64(a), a, sl.vmask, sl.signbit);
-        if (!kPlainKeys) {
-          if (P.tdict.npieces && k == P.tdict.key) val = tdict_rank(P.tdict, val);
-          else if (ks.rollup) val = rollup_value(val, ks);
-          if (ks.fzero) val = fzero_fix(val, sl.width);
-        }
-        if (ks.lut) val = (uint64_t)__popcll(ks.lut & ((1ull << val) - 1ull));
-        else val -= ks.lo;
-        packed += val * ks.mul;
-      }
+      packed = general_row_key<kPlainKeys>(P, seg, row);
     }
     uint64_t cell;
     if (P.hash_mode == 2) {
@@ -361,7 +389,7 @@ scan_filter_groupby_kernel(const __grid_constant__ ScanParams P) {
         return;
       }
     } else if (P.hash_mode) {
-      cell = hash_cell(P, packed);
+      cell = hash_cell_call(P, packed);
       if (cell == kEmptyKey) {
         atomicOr(&P.counters[kCHashOver], 1ull);
         return;
@@ -393,24 +421,9 @@ scan_filter_groupby_kernel(const __grid_constant__ ScanParams P) {
       }
       // count-distinct: append (cell, id) to this CTA's region (of the pair's owner rank); deduplicated after the scan
       const uint32_t *off = sd.bs_offsets[ms.bitset_idx];
-      const uint32_t *vals = sd.bs_values[ms.bitset_idx];
       const uint64_t hi = P.dpair_key ? packed : cell;
-      auto append = [&](const uint64_t id) {
-        const uint32_t sub = P.dpair_nsub > 1 ? (P.dpair_key ? owner_of(hi, 0, P.dpair_nsub) : pair_owner(hi, id, P.dpair_nsub)) : 0u;
-        const uint32_t pos = atomicAdd(&s_cursor[dn][sub], 1u);
-        if (pos < P.dpair_cap) {
-          const uint64_t at = ((uint64_t)sub * gridDim.x + blockIdx.x) * P.dpair_cap + pos;
-          if (P.dpair_wide) reinterpret_cast<ulonglong2 *>(P.dpairs[dn])[at] = make_ulonglong2(hi, id);
-          else P.dpairs[dn][at] = (hi << 32) | id;
-        }
-      };
-      if (off == nullptr) {  // one id per row: `pre` is the id
-        append(pre);
-      } else {               // CSR cell: `pre` is offsets[row]
-        const uint32_t lo = (uint32_t)pre, hi_q = gather_u32(off + row + 1);
-        for (uint32_t q = lo; q < hi_q; ++q)
-          append(ms.id64 ? __ldg(reinterpret_cast<const unsigned long long *>(vals) + q) : (uint64_t)gather_u32(vals + q));
-      }
+      if (off == nullptr) append_pair(P, s_cursor[dn], dn, hi, pre);   // one id per row: `pre` is the id
+      else append_csr_cell(P, s_cursor[dn], dn, hi, sd.bs_values[ms.bitset_idx], (uint32_t)pre, gather_u32(off + row + 1), ms.id64);
       ++dn;
     }
   };

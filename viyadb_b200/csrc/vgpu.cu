@@ -334,6 +334,7 @@ struct SegmentData {
   uint64_t bs_vcap[kMaxBitsetCols] = {0, 0, 0, 0};  // allocated ids / offsets (elements)
   uint64_t bs_ocap[kMaxBitsetCols] = {0, 0, 0, 0};
   bool bs_has_offsets[kMaxBitsetCols] = {false, false, false, false};  // CSR offsets in use (else one id per row)
+  uint64_t hi_rows = 0;        // rows [hi_rows, cap) of every column are known to be zero (no tail memsets on re-put)
   uint8_t *rows = nullptr;     // row-major mirror of every column, or nullptr
   uint64_t rows_cap = 0;       // rows the mirror was allocated for
   bool stats_pending = false;  // min/max computed on the device, not yet read back
@@ -365,6 +366,8 @@ struct vgpu_table {
   unsigned long long *h_stats_init = nullptr;  // pinned pattern {~0, 0} x ncols
   bool descs_dirty = true;
   bool stats_dirty = false;       // some segment's statistics are still on the device
+  // vgpu_segment_put_async: converted CSR offsets that must outlive the copies still in flight
+  std::vector<std::vector<uint32_t>> pending_keep;
   // scratch high-water marks so that a repeated query shape never re-runs on overflow (benign races between
   // concurrent queries: any value is a valid hint)
   std::atomic<uint64_t> hash_cap_hint{0};
@@ -522,7 +525,7 @@ void free_segment(SegmentData &sd) {
   sd = SegmentData();
 }
 
-void ensure_segment(vgpu_table *t, uint32_t seg_idx, uint64_t nrows) {
+void ensure_segment(vgpu_table *t, uint32_t seg_idx, uint64_t nrows, cudaStream_t zero_stream) {
   if (nrows > t->segment_size)
     fail(VGPU_ERR_INVALID, "segment rows " + std::to_string(nrows) + " exceed segment_size " +
                                std::to_string(t->segment_size));
@@ -533,19 +536,23 @@ void ensure_segment(vgpu_table *t, uint32_t seg_idx, uint64_t nrows) {
     free_segment(sd);
     if (t->row_bytes > 0) {
       CUDA_CK(cudaMalloc(&sd.slab, t->row_bytes * cap));
+      // zero once: vector loads may over-read to the end of a chunk; later puts only clear what shrinks
+      CUDA_CK(cudaMemsetAsync(sd.slab, 0, t->row_bytes * cap, zero_stream));
     }
     sd.cap = cap;
+    sd.hi_rows = 0;
     if (t->row_stride) {
       // the mirror is an optimisation: without memory for it the columnar gathers serve every query
       if (cudaMalloc(&sd.rows, (uint64_t)t->row_stride * cap + 64) == cudaSuccess) sd.rows_cap = cap;
       else { sd.rows = nullptr; cudaGetLastError(); }
     }
+    t->descs_dirty = true;
   } else {
     for (int b = 0; b < kMaxBitsetCols; ++b) sd.bs_n[b] = 0;  // buffers are kept and reused
   }
+  if (sd.nrows != nrows || !sd.valid) t->descs_dirty = true;
   sd.nrows = nrows;
   sd.valid = false;
-  t->descs_dirty = true;
 }
 
 // per-column min/max of the stored cells (device reduction), kept in the ordered domain. Launch only:
@@ -1294,7 +1301,7 @@ void vgpu_table_free(vgpu_table *table) {
   delete table;
 }
 
-int vgpu_segment_put(vgpu_table *t, uint32_t seg_idx, uint64_t nrows, const void *const *col_ptrs) {
+static int put_impl(vgpu_table *t, uint32_t seg_idx, uint64_t nrows, const void *const *col_ptrs, bool wait) {
   return guard([&] {
     if (!t || (!col_ptrs && nrows)) fail(VGPU_ERR_INVALID, "null argument");
     vgpu_ctx *ctx = t->ctx;
@@ -1302,10 +1309,11 @@ int vgpu_segment_put(vgpu_table *t, uint32_t seg_idx, uint64_t nrows, const void
     std::unique_lock<std::shared_mutex> lk(t->mu);
     CUDA_CK(cudaSetDevice(ctx->device));
     if (seg_idx > t->segs.size() + (1u << 20)) fail(VGPU_ERR_INVALID, "segment index too sparse");
-    ensure_segment(t, seg_idx, nrows);
-    SegmentData &sd = t->segs[seg_idx];
     cudaStream_t cs = ctx->copy_stream;
-    std::vector<std::vector<uint32_t>> keep;  // converted CSR offsets must outlive the async copies
+    ensure_segment(t, seg_idx, nrows, cs);
+    SegmentData &sd = t->segs[seg_idx];
+    std::vector<std::vector<uint32_t>> &keep = t->pending_keep;  // converted CSR offsets must outlive the async copies
+    const uint64_t old_hi = sd.hi_rows;
     for (size_t c = 0; c < t->cols.size(); ++c) {
       const ColInfo &ci = t->cols[c];
       if (ci.bitset) {
@@ -1332,6 +1340,7 @@ int vgpu_segment_put(vgpu_table *t, uint32_t seg_idx, uint64_t nrows, const void
           sd.bs_values[ci.bitset_idx] = nullptr;
           CUDA_CK(cudaMalloc(&sd.bs_values[ci.bitset_idx], vcap * 4));
           sd.bs_vcap[ci.bitset_idx] = vcap;
+          t->descs_dirty = true;
         }
         if (sd.bs_vcap[ci.bitset_idx] * 4 > nvalues * idw)
           CUDA_CK(cudaMemsetAsync(reinterpret_cast<uint8_t *>(sd.bs_values[ci.bitset_idx]) + nvalues * idw, 0,
@@ -1348,11 +1357,14 @@ int vgpu_segment_put(vgpu_table *t, uint32_t seg_idx, uint64_t nrows, const void
             sd.bs_offsets[ci.bitset_idx] = nullptr;
             CUDA_CK(cudaMalloc(&sd.bs_offsets[ci.bitset_idx], (nrows + 1) * 4));
             sd.bs_ocap[ci.bitset_idx] = nrows + 1;
+            t->descs_dirty = true;
           }
           CUDA_CK(cudaMemcpyAsync(sd.bs_offsets[ci.bitset_idx], o32.data(), (nrows + 1) * 4,
                                   cudaMemcpyHostToDevice, cs));
+          if (!sd.bs_has_offsets[ci.bitset_idx]) t->descs_dirty = true;
           sd.bs_has_offsets[ci.bitset_idx] = true;
         } else {
+          if (sd.bs_has_offsets[ci.bitset_idx]) t->descs_dirty = true;
           sd.bs_has_offsets[ci.bitset_idx] = false;
         }
         continue;
@@ -1362,9 +1374,10 @@ int vgpu_segment_put(vgpu_table *t, uint32_t seg_idx, uint64_t nrows, const void
         if (!col_ptrs[c]) fail(VGPU_ERR_INVALID, "null column pointer");
         CUDA_CK(cudaMemcpyAsync(dst, col_ptrs[c], nrows * ci.width, cudaMemcpyHostToDevice, cs));
       }
-      if (sd.cap > nrows)
-        CUDA_CK(cudaMemsetAsync(dst + nrows * ci.width, 0, (sd.cap - nrows) * ci.width, cs));
+      if (old_hi > nrows)   // the segment shrank: clear what the previous content left behind
+        CUDA_CK(cudaMemsetAsync(dst + nrows * ci.width, 0, (old_hi - nrows) * ci.width, cs));
     }
+    sd.hi_rows = nrows;
     // statistics and the row mirror follow the copies on the compute stream; the host only waits for the
     // copies (its buffers may be reused by the caller now), the kernels overlap the next segment's DMA
     CUDA_CK(cudaEventRecord(ctx->ev_copy, cs));
@@ -1372,10 +1385,61 @@ int vgpu_segment_put(vgpu_table *t, uint32_t seg_idx, uint64_t nrows, const void
     compute_stats(t, seg_idx);
     build_row_mirror(t, seg_idx);
     CUDA_CK(cudaEventRecord(t->ev_put, ctx->stream));
-    CUDA_CK(cudaEventSynchronize(ctx->ev_copy));
     sd.valid = true;
+    if (wait) {
+      CUDA_CK(cudaEventSynchronize(ctx->ev_copy));
+      t->pending_keep.clear();
+    }
   });
 }
+
+int vgpu_segment_put(vgpu_table *t, uint32_t seg_idx, uint64_t nrows, const void *const *col_ptrs) {
+  return put_impl(t, seg_idx, nrows, col_ptrs, true);
+}
+
+int vgpu_segment_put_async(vgpu_table *t, uint32_t seg_idx, uint64_t nrows, const void *const *col_ptrs) {
+  return put_impl(t, seg_idx, nrows, col_ptrs, false);
+}
+
+int vgpu_table_sync(vgpu_table *t) {
+  return guard([&] {
+    if (!t) fail(VGPU_ERR_INVALID, "null table");
+    vgpu_ctx *ctx = t->ctx;
+    std::lock_guard<std::mutex> put_lk(ctx->put_mu);
+    CUDA_CK(cudaSetDevice(ctx->device));
+    CUDA_CK(cudaStreamSynchronize(ctx->copy_stream));
+    std::unique_lock<std::shared_mutex> lk(t->mu);
+    t->pending_keep.clear();
+  });
+}
+
+int vgpu_host_pin(vgpu_ctx *ctx, const void *ptr, size_t bytes) {
+  return guard([&] {
+    if (!ctx || !ptr || !bytes) fail(VGPU_ERR_INVALID, "null argument");
+    CUDA_CK(cudaSetDevice(ctx->device));
+    const uintptr_t lo = reinterpret_cast<uintptr_t>(ptr) & ~uintptr_t(4095);
+    const uintptr_t hi = (reinterpret_cast<uintptr_t>(ptr) + bytes + 4095) & ~uintptr_t(4095);
+    cudaError_t e = cudaHostRegister(reinterpret_cast<void *>(lo), hi - lo, cudaHostRegisterDefault);
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      fail(VGPU_ERR_CUDA, std::string("cudaHostRegister: ") + cudaGetErrorString(e));
+    }
+  });
+}
+
+int vgpu_host_unpin(vgpu_ctx *ctx, const void *ptr) {
+  return guard([&] {
+    if (!ctx || !ptr) fail(VGPU_ERR_INVALID, "null argument");
+    CUDA_CK(cudaSetDevice(ctx->device));
+    cudaError_t e = cudaHostUnregister(reinterpret_cast<void *>(reinterpret_cast<uintptr_t>(ptr) & ~uintptr_t(4095)));
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      fail(VGPU_ERR_CUDA, std::string("cudaHostUnregister: ") + cudaGetErrorString(e));
+    }
+  });
+}
+
+
 
 int vgpu_segment_generate(vgpu_table *t, uint32_t seg_idx, uint64_t nrows, const vgpu_gen_col *gens,
                           uint64_t seed, uint64_t row_offset) {
@@ -1386,9 +1450,11 @@ int vgpu_segment_generate(vgpu_table *t, uint32_t seg_idx, uint64_t nrows, const
     std::unique_lock<std::shared_mutex> lk(t->mu);
     CUDA_CK(cudaSetDevice(ctx->device));
     if (t->cols.size() > 32) fail(VGPU_ERR_UNSUPPORTED, "generator supports at most 32 columns");
-    ensure_segment(t, seg_idx, nrows);
+    ensure_segment(t, seg_idx, nrows, ctx->stream);
     SegmentData &sd = t->segs[seg_idx];
     if (sd.slab) CUDA_CK(cudaMemsetAsync(sd.slab, 0, t->row_bytes * sd.cap, ctx->stream));
+    sd.hi_rows = nrows;
+    t->descs_dirty = true;
     GenParams G{};
     G.slab = sd.slab;
     G.nrows = nrows;

@@ -215,7 +215,28 @@ class Table:
                                "for plan-only use); there is no CPU scan path")
         return self._handle
 
-    def put_segment(self, seg_idx, columns, hidden_count=None):
+    def sync(self):
+        """Wait for the copies of earlier put_segment(..., wait=False) calls (vgpu_table_sync)."""
+        N.check(N.load().vgpu_table_sync(self.handle))
+        self._async_keep = []
+
+    def put_segment(self, seg_idx, columns, hidden_count=None, wait=True):
+        self.put_prepared(seg_idx, self.prepare_segment(columns, hidden_count), wait)
+
+    def put_prepared(self, seg_idx, prepared, wait=True):
+        """vgpu_segment_put / _put_async of host columns marshalled once by prepare_segment (a caller that uploads the same
+        host buffers again and again — bench.py's end-to-end leg — pays the ctypes marshalling once)."""
+        lib = N.load()
+        ptrs, nrows, keep = prepared
+        if wait:
+            N.check(lib.vgpu_segment_put(self.handle, seg_idx, nrows, ptrs))
+        else:   # the host arrays must outlive the copies: kept until sync()
+            N.check(lib.vgpu_segment_put_async(self.handle, seg_idx, nrows, ptrs))
+            if not hasattr(self, "_async_keep"):
+                self._async_keep = []
+            self._async_keep.append(keep)
+
+    def prepare_segment(self, columns, hidden_count=None):
         """Copy one segment into HBM. `columns`: name -> numpy array (dict codes / numbers), or for a
         BITSET metric either a 1-D uint32 array (one id per row) or a pair (offsets uint64[n+1],
         values uint32[nvalues])."""
@@ -258,7 +279,7 @@ class Table:
                 raise ValueError("hidden count length mismatch")
             keep.append(arr)
             ptrs[self.ncols - 1] = arr.ctypes.data
-        N.check(lib.vgpu_segment_put(self.handle, seg_idx, nrows or 0, ptrs))
+        return ptrs, nrows or 0, keep
 
     def generate_segment(self, seg_idx, nrows, gens, seed=42, row_offset=0):
         """Synthetic segment written directly in HBM (vgpu_segment_generate). `gens`: one

@@ -49,6 +49,7 @@
 #include <functional>
 #include <atomic>
 #include <map>
+#include <set>
 #include <unordered_set>
 #include <memory>
 #include <mutex>
@@ -131,7 +132,7 @@ struct IngestEpoch {
 // ---------------------------------------------------------------------------------------------
 class GpuTableBinding {
 public:
-  GpuTableBinding(vgpu_ctx *ctx, db::Table &table) : table_(table), access_(table) {
+  GpuTableBinding(vgpu_ctx *ctx, db::Table &table) : ctx_(ctx), table_(table), access_(table) {
     ndims_ = table.dimensions().size();
     nmetrics_ = table.metrics().size();
     hidden_ = access_.has_hidden_count();
@@ -174,7 +175,10 @@ public:
     schema.cols = cols.data();
     check(vgpu_table_create(ctx, &schema, &handle_), "vgpu_table_create");
   }
-  ~GpuTableBinding() { vgpu_table_free(handle_); }
+  ~GpuTableBinding() {
+    vgpu_table_free(handle_);
+    for (const void *p : pinned_) vgpu_host_unpin(ctx_, p);
+  }
   GpuTableBinding(const GpuTableBinding &) = delete;
   GpuTableBinding &operator=(const GpuTableBinding &) = delete;
 
@@ -208,16 +212,22 @@ public:
     if (uploaded_.size() < segments.size()) uploaded_.resize(segments.size(), static_cast<size_t>(-1));
     std::vector<const void *> dims(ndims_), metrics(nmetrics_);
     std::vector<uint64_t> stats(2 * ndims_ + 2);
+    // CSR images of bitset cells must outlive the asynchronous copies: kept until vgpu_table_sync below
+    std::vector<std::vector<uint64_t>> offsets_keep;
+    std::vector<std::vector<uint32_t>> values_keep;
+    std::vector<std::vector<uint64_t>> wide_keep;
+    std::vector<std::unique_ptr<vgpu_bitset_csr>> csr_keep;
+    bool any = false;
     for (size_t si = 0; si < segments.size(); ++si) {
       size_t size = segments[si]->size();
       if (uploaded_[si] == size) continue;
+      // the segment is one heap object holding every fixed-width column: page-lock it once, so that this and every
+      // later upload is a straight DMA (a failure only means the driver stages the copies)
+      if (pinned_.insert(segments[si]).second && vgpu_host_pin(ctx_, segments[si], access_.segment_bytes()) != VGPU_OK)
+        pinned_.erase(segments[si]);
       const void *hidden = nullptr;
       access_.columns()(segments[si], dims.data(), metrics.data(), &hidden, stats.data());
       std::vector<const void *> ptrs;
-      std::vector<std::vector<uint64_t>> offsets_keep;
-      std::vector<std::vector<uint32_t>> values_keep;
-      std::vector<std::vector<uint64_t>> wide_keep;
-      std::vector<std::unique_ptr<vgpu_bitset_csr>> csr_keep;
       for (size_t d = 0; d < ndims_; ++d) ptrs.push_back(dims[d]);
       for (auto *m : table_.metrics()) {
         if (m->agg_type() != db::Metric::AggregationType::BITSET) {
@@ -242,15 +252,19 @@ public:
         ptrs.push_back(csr_keep.back().get());
       }
       if (hidden_) ptrs.push_back(hidden);
-      check(vgpu_segment_put(handle_, static_cast<uint32_t>(si), size, ptrs.data()), "vgpu_segment_put");
+      check(vgpu_segment_put_async(handle_, static_cast<uint32_t>(si), size, ptrs.data()), "vgpu_segment_put_async");
       uploaded_[si] = size;
+      any = true;
     }
+    if (any) check(vgpu_table_sync(handle_), "vgpu_table_sync");
   }
 
 private:
+  vgpu_ctx *ctx_;
   db::Table &table_;
   SegmentAccess access_;
   vgpu_table *handle_ = nullptr;
+  std::set<const void *> pinned_;
   size_t ndims_ = 0, nmetrics_ = 0;
   bool hidden_ = false;
   std::vector<size_t> uploaded_;

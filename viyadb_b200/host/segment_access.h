@@ -43,6 +43,8 @@ using SegmentColumnsFn = void (*)(db::SegmentBase *seg, const void **dims, const
 // offsets[0..nrows] are written (sizing pass). Values are widened to uint64_t.
 using SegmentBitsetFn = uint64_t (*)(db::SegmentBase *seg, uint32_t metric_idx, uint64_t nrows,
                                      uint64_t *offsets, uint64_t *values);
+// sizeof(Segment): the heap object that holds every fixed-width column of a segment (pinned once for DMA)
+using SegmentSizeofFn = uint64_t (*)();
 
 class SegmentAccess {
 public:
@@ -50,10 +52,12 @@ public:
     lib_ = const_cast<db::Database &>(table.database()).compiler().Compile(GenerateCode());
     columns_ = lib_->GetFunction<SegmentColumnsFn>("vgpu_segment_columns");
     bitset_ = lib_->GetFunction<SegmentBitsetFn>("vgpu_segment_bitset");
+    sizeof_ = lib_->GetFunction<SegmentSizeofFn>("vgpu_segment_sizeof");
   }
 
   SegmentColumnsFn columns() const { return columns_; }
   SegmentBitsetFn bitset() const { return bitset_; }
+  uint64_t segment_bytes() const { return sizeof_(); }
 
   bool has_hidden_count() const {
     bool has_avg = false, has_count = false;
@@ -116,6 +120,9 @@ private:
     }
     code << "}\n";
 
+    code << "extern \"C\" uint64_t vgpu_segment_sizeof() " << vis << ";\n";
+    code << "extern \"C\" uint64_t vgpu_segment_sizeof() { return sizeof(Segment); }\n";
+
     code << "extern \"C\" uint64_t vgpu_segment_bitset(db::SegmentBase* sb, uint32_t metric_idx, "
             "uint64_t nrows, uint64_t* offsets, uint64_t* values) "
          << vis << ";\n";
@@ -160,6 +167,7 @@ private:
   std::shared_ptr<cg::SharedLibrary> lib_;
   SegmentColumnsFn columns_;
   SegmentBitsetFn bitset_;
+  SegmentSizeofFn sizeof_;
 };
 
 } // namespace vgpu_host
