@@ -7,7 +7,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libvgpu.so")
+LIB_PATH = os.environ.get("VGPU_LIB_PATH") or os.path.join(_HERE, "libvgpu.so")   # override: A/B of kernel variants
 
 VGPU_ABI_VERSION = 2
 

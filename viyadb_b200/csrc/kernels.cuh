@@ -799,6 +799,7 @@ struct ExtractParams {
   const uint64_t *hkeys;
   const uint8_t *present;
   uint32_t hkey_stride, present_stride;
+  uint32_t present_width;   // dense: bytes of the presence word (1: flag; 4 / 8: a COUNT accumulator, ScanParams::skip_present)
   const uint32_t *wstate;
   const uint64_t *wkeys;
   ExtractKey keys[kMaxKeys];
@@ -813,7 +814,10 @@ struct ExtractParams {
 __device__ __forceinline__ bool cell_present(const ExtractParams &E, uint64_t c, uint64_t &packed) {
   if (!E.hash_mode) {
     packed = c;
-    return E.present[c * E.present_stride] != 0;
+    const uint8_t *p = E.present + c * E.present_stride;
+    if (E.present_width == 4) return *reinterpret_cast<const uint32_t *>(p) != 0u;
+    if (E.present_width == 8) return *reinterpret_cast<const uint64_t *>(p) != 0ull;
+    return *p != 0;
   }
   if (E.hash_mode == 2) {
     packed = c;
@@ -880,6 +884,12 @@ extract_groups_kernel(const __grid_constant__ ExtractParams E) {
       }
     }
   }
+}
+
+// presence flags from a COUNT accumulator (several GPUs: the flags are what the ranks max-reduce)
+__global__ void __launch_bounds__(256) derive_present_kernel(uint8_t *present, const uint8_t *acc, uint32_t width, uint64_t ncells) {
+  for (uint64_t c = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; c < ncells; c += (uint64_t)gridDim.x * blockDim.x)
+    present[c] = (width == 4 ? *reinterpret_cast<const uint32_t *>(acc + c * 4) != 0u : *reinterpret_cast<const uint64_t *>(acc + c * 8) != 0ull) ? 1 : 0;
 }
 
 // accumulators that become final after the groups were extracted (count-distinct: the dedupe runs while the

@@ -809,7 +809,7 @@ int vgpu_query_agg(vgpu_table *t, const vgpu_plan *plan, vgpu_result **out) {
     // work units: about 8 per resident warp so that dynamic scheduling evens out the tail, at most 64 chunks
     P.unit_chunks = ctx->unit_chunks;
     if (P.unit_chunks == 0) {
-      const uint64_t warps = (uint64_t)ctx->sm_count * ctx->ctas_per_sm * kWarps;
+      const uint64_t warps = (uint64_t)ctx->sm_count * ctx->ctas_per_sm * kScanWarps;
       P.unit_chunks = (uint32_t)std::min<uint64_t>(64, std::max<uint64_t>(4, P.total_tiles / (8 * warps)));
     }
     P.units_per_seg = (P.tiles_per_seg + P.unit_chunks - 1) / P.unit_chunks;
@@ -836,7 +836,7 @@ int vgpu_query_agg(vgpu_table *t, const vgpu_plan *plan, vgpu_result **out) {
       if (hash_cap > 0xfffffffeull && P.ndistinct) fail(VGPU_ERR_UNSUPPORTED, "count-distinct over more than 2^32 groups");
     }
     // the scan grid (also the number of count-distinct pair regions per owner)
-    const int scan_grid = (int)std::max<uint64_t>(1, std::min<uint64_t>((P.total_tiles + kWarps - 1) / kWarps,
+    const int scan_grid = (int)std::max<uint64_t>(1, std::min<uint64_t>((P.total_tiles + kScanWarps - 1) / kScanWarps,
                                                                        (uint64_t)ctx->sm_count * ctx->ctas_per_sm));
     // With several ranks every buffer that takes part in an exchange must have the same size everywhere: the grid is
     // the full one (ranks with less work leave regions empty) and capacities come from agreed numbers only.
@@ -851,7 +851,7 @@ int vgpu_query_agg(vgpu_table *t, const vgpu_plan *plan, vgpu_result **out) {
     if (P.ndistinct) {
       const uint64_t nregions = (uint64_t)region_grid * P.dpair_nsub;
       const uint64_t fill_hint = hint_load(t->pairs_region_hint);
-      if (fill_hint) region_cap64 = fill_hint + fill_hint / 8 + 256;
+      if (fill_hint) region_cap64 = fill_hint + fill_hint / 2 + 2048;   // work units are handed out dynamically: a CTA's share varies from run to run
       else region_cap64 = std::max<uint64_t>(1ull << 16, max_active_rows / 16) / nregions * 5 / 4 + 1024;
       if (ctx->test_pairs_cap) region_cap64 = std::max<uint64_t>(ctx->test_pairs_cap / nregions, 4);
     }
@@ -971,6 +971,28 @@ int vgpu_query_agg(vgpu_table *t, const vgpu_plan *plan, vgpu_result **out) {
           scan_dyn_smem = (uint32_t)cells * sstride;
         }
       }
+      // Presence from a COUNT accumulator: every count cell of the active segments is >= 1 (statistics reduced at put
+      // time) and this rank's sums cannot wrap, so "count != 0" is exactly "some row reached the cell".
+      P.skip_present = 0;
+      int present_acc = -1;
+      if (!q.hash_mode && !P.smem_cells && !(ctx->tune & (1u << 22))) {
+        for (size_t m = 0; m < q.accs.size() && present_acc < 0; ++m) {
+          const ColInfo &ci = t->cols[q.acc_cols[m]];
+          if (ci.agg != VGPU_AGG_COUNT || (q.accs[m].op != A_ADD32 && q.accs[m].op != A_ADD64)) continue;
+          uint64_t cmin = ~0ull, cmax = 0;
+          for (uint32_t s : q.active) {
+            const SegmentData &sd = t->segs[s];
+            if (sd.nrows == 0) continue;
+            cmin = std::min(cmin, sd.omin[q.acc_cols[m]]);
+            cmax = std::max(cmax, sd.omax[q.acc_cols[m]]);
+          }
+          if (cmin < 1 || cmin > cmax) continue;
+          const unsigned __int128 bound = (unsigned __int128)cmax * std::max<uint64_t>(q.active_rows, 1);
+          if (bound >= ((unsigned __int128)1 << (8 * q.accs[m].acc_width))) continue;
+          present_acc = (int)m;
+        }
+        P.skip_present = present_acc >= 0;
+      }
       // count-distinct pair regions
       if (P.ndistinct && region_cap64 > 0xffffffffull) fail(VGPU_ERR_NOMEM, "count-distinct pair regions too large");
       P.dpair_cap = (uint32_t)region_cap64;
@@ -999,7 +1021,7 @@ int vgpu_query_agg(vgpu_table *t, const vgpu_plan *plan, vgpu_result **out) {
       if (P.total_tiles > 0) {
         cudaLaunchConfig_t cfg{};
         cfg.gridDim = dim3(G > 1 && P.ndistinct ? region_grid : scan_grid);
-        cfg.blockDim = dim3(kThreads);
+        cfg.blockDim = dim3(kScanThreads);
         cfg.stream = stream;
         cfg.dynamicSmemBytes = scan_dyn_smem;
         cudaLaunchAttribute attr[1];
@@ -1019,13 +1041,24 @@ int vgpu_query_agg(vgpu_table *t, const vgpu_plan *plan, vgpu_result **out) {
         }
         bool plain_keys = P.tdict.npieces == 0 && !q.wide;
         for (uint32_t k = 0; k < P.nkeys; ++k) plain_keys = plain_keys && !P.keys[k].rollup && !P.keys[k].fzero;
-        if (P.smem_cells) {
-          if (plain_keys) CUDA_CK(cudaLaunchKernelEx(&cfg, scan_filter_groupby_kernel<3, true, true>, P));
-          else CUDA_CK(cudaLaunchKernelEx(&cfg, scan_filter_groupby_kernel<3, true, false>, P));
-        } else if (ctx->ctas_per_sm == 2) CUDA_CK(cudaLaunchKernelEx(&cfg, scan_filter_groupby_kernel<2, false, false>, P));
-        else if (ctx->ctas_per_sm == 4) CUDA_CK(cudaLaunchKernelEx(&cfg, scan_filter_groupby_kernel<4, false, false>, P));
-        else if (plain_keys) CUDA_CK(cudaLaunchKernelEx(&cfg, scan_filter_groupby_kernel<3, false, true>, P));
-        else CUDA_CK(cudaLaunchKernelEx(&cfg, scan_filter_groupby_kernel<3, false, false>, P));
+        // the fast instantiation: register-staged keys and metrics, 8-byte count-distinct pairs (scan_kernel.cuh)
+        const bool fast = P.small_plan && !q.wide && !P.dpair_wide;
+        auto launch = [&](auto kernel) { CUDA_CK(cudaLaunchKernelEx(&cfg, kernel, P)); };
+        const int variant = (fast && P.conj ? 8 : 0) | (P.smem_cells ? 4 : 0) | (plain_keys ? 2 : 0) | (fast ? 1 : 0);
+        switch (variant) {
+          case 9: launch(scan_filter_groupby_kernel<VGPU_MIN_CTAS, false, false, true, true>); break;
+          case 11: launch(scan_filter_groupby_kernel<VGPU_MIN_CTAS, false, true, true, true>); break;
+          case 13: launch(scan_filter_groupby_kernel<VGPU_MIN_CTAS, true, false, true, true>); break;
+          case 15: launch(scan_filter_groupby_kernel<VGPU_MIN_CTAS, true, true, true, true>); break;
+          case 0: launch(scan_filter_groupby_kernel<VGPU_MIN_CTAS, false, false, false>); break;
+          case 1: launch(scan_filter_groupby_kernel<VGPU_MIN_CTAS, false, false, true>); break;
+          case 2: launch(scan_filter_groupby_kernel<VGPU_MIN_CTAS, false, true, false>); break;
+          case 3: launch(scan_filter_groupby_kernel<VGPU_MIN_CTAS, false, true, true>); break;
+          case 4: launch(scan_filter_groupby_kernel<VGPU_MIN_CTAS, true, false, false>); break;
+          case 5: launch(scan_filter_groupby_kernel<VGPU_MIN_CTAS, true, false, true>); break;
+          case 6: launch(scan_filter_groupby_kernel<VGPU_MIN_CTAS, true, true, false>); break;
+          default: launch(scan_filter_groupby_kernel<VGPU_MIN_CTAS, true, true, true>); break;
+        }
         ++launches;
       }
       CUDA_CK(cudaEventRecord(sc->ev_scan1, stream));
@@ -1067,6 +1100,12 @@ int vgpu_query_agg(vgpu_table *t, const vgpu_plan *plan, vgpu_result **out) {
         NCCL_CK(g_nccl.AllReduce(sc->d_counters + kCMaxFirst, sc->d_counters + kCMaxFirst, kCLocalFirst - kCMaxFirst, ncclUint64,
                                  ncclMax, ctx->comm, stream));
         if (!q.hash_mode) {
+          if (P.skip_present) {   // the flags are what the ranks max-reduce: read them off the local counts first
+            derive_present_kernel<<<grid_for(q.ncells, 256, ctx->sm_count), 256, 0, stream>>>(
+                P.present, static_cast<const uint8_t *>(acc_ptrs[present_acc]), q.accs[present_acc].acc_width, q.ncells);
+            CUDA_CK(cudaGetLastError());
+            ++launches;
+          }
           for (size_t m = 0; m < q.accs.size(); ++m) {
             if (q.accs[m].op == A_DISTINCT) continue;
             NCCL_CK(g_nccl.AllReduce(acc_ptrs[m], acc_ptrs[m], q.ncells, q.accs[m].nccl_type, q.accs[m].nccl_op, ctx->comm, stream));
@@ -1113,6 +1152,12 @@ int vgpu_query_agg(vgpu_table *t, const vgpu_plan *plan, vgpu_result **out) {
       E.present = P.present;
       E.hkey_stride = P.hkey_stride;
       E.present_stride = P.present_stride;
+      E.present_width = 1;
+      if (P.skip_present && G == 1) {   // single GPU: the count accumulator is the presence word
+        E.present = static_cast<const uint8_t *>(acc_ptrs[present_acc]);
+        E.present_stride = P.mets[present_acc].stride;
+        E.present_width = q.accs[present_acc].acc_width;
+      }
       E.wstate = P.wstate;
       E.wkeys = P.wkeys;
       E.counter = sc->d_counters + kCGroups;

@@ -34,7 +34,15 @@ namespace vgpu {
 
 constexpr int kChunkRows = 512;                 // rows per warp iteration
 constexpr int kSubChunk = kChunkRows / kSub;    // 128
-constexpr int kWarps = kThreads / 32;
+constexpr int kWarps = kThreads / 32;     // select / search kernels
+// The fused scan kernel's own CTA shape: threads per CTA x resident CTAs per SM fixes the register budget
+// (65536 / (threads x CTAs), rounded down to 8). Measured on B200 (tools/gpu_ab.sh): at 256 x 3 (80 registers) the
+// kernel sits on a spill cliff — harmless edits moved the C2 scan between 2.40 and 2.76 ms.
+#ifndef VGPU_SCAN_THREADS
+#define VGPU_SCAN_THREADS 256
+#endif
+constexpr int kScanThreads = VGPU_SCAN_THREADS;
+constexpr int kScanWarps = kScanThreads / 32;
 constexpr uint32_t kSmemTableBytes = 40 * 1024;  // CTA-private group table (3 CTAs/SM: 3 x (17 + 40) KB fit 227 KB)
 constexpr int kListCap = kChunkRows + 32;       // a chunk's worth of rows plus one incomplete batch
 static_assert(kVec * 32 == kSubChunk, "a lane owns kVec consecutive rows of every sub-chunk");
@@ -145,10 +153,12 @@ __device__ __forceinline__ uint32_t leaf_mask16(const PInstr &in, const uint32_t
 }
 
 // row0 = first row of the lane inside the segment (chunk_row0 + lane*4)
+// kConjOnly: the caller knows the predicate is an unrolled conjunction (P.conj): the interpreter is not compiled in
+template <bool kConjOnly = false>
 __device__ __forceinline__ uint32_t eval_predicate(const ScanParams &P, const CurSeg &seg,
                                                    uint32_t row0, uint64_t pol) {
   uint32_t v[kRowsPerThread];
-  if (P.conj) {
+  if (kConjOnly || P.conj) {
     // The common shape — a conjunction of up to 4 vectorisable leaves — with the program counter
     // unrolled: every operand of a leaf is a constant-bank operand, nothing is interpreted.
     uint32_t m = 0xffffu;
@@ -167,6 +177,7 @@ __device__ __forceinline__ uint32_t eval_predicate(const ScanParams &P, const Cu
     }
     return m;
   }
+  if (kConjOnly) return 0;
   uint32_t stk[kStackDepth];
 #pragma unroll
   for (int i = 0; i < kStackDepth; ++i) stk[i] = 0;
@@ -293,10 +304,15 @@ __device__ __noinline__ void append_csr_cell(const ScanParams &P, uint32_t *curs
 // table (ScanParams::smem_cells != 0); the other one carries none of that code.
 // kPlainKeys: no group key needs a time rollup, a bucket-dictionary lookup or the -0.0 fix (the common case: dictionary
 // codes and plain integers): the per-key checks for them are compiled out of the per-row path, which is issue-bound.
-template <int kMinCtas, bool kSmemTable, bool kPlainKeys>
-__global__ void __launch_bounds__(kThreads, kMinCtas)
+// kFast: at most 4 keys of at most 4 bytes, at most 4 metrics, no wide key tuples, 8-byte count-distinct pairs — what
+// nearly every query is. This instantiation holds nothing else: no call, no key loop over memory, no 16-byte pairs. The
+// kernel is capped at 80 registers and sat on a spill cliff when the rare paths shared its code (tools/gpu_ab.sh:
+// harmless edits moved the C2 scan between 2.40 and 2.76 ms); the other instantiation takes everything.
+// kConj (fast instantiations only): the predicate is the unrolled conjunction; no interpreter, hence no call at all.
+template <int kMinCtas, bool kSmemTable, bool kPlainKeys, bool kFast, bool kConj = false>
+__global__ void __launch_bounds__(kScanThreads, kMinCtas)
 scan_filter_groupby_kernel(const __grid_constant__ ScanParams P) {
-  __shared__ uint32_t s_list[kWarps][kListCap];  // rows (of the warp's current segment) waiting for aggregation
+  __shared__ uint32_t s_list[kScanWarps][kListCap];  // rows (of the warp's current segment) waiting for aggregation
 
   const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   uint32_t *list = s_list[warp];
@@ -310,7 +326,7 @@ scan_filter_groupby_kernel(const __grid_constant__ ScanParams P) {
   const uint32_t s_table_a = (uint32_t)__cvta_generic_to_shared(s_table);
   if (kSmemTable) {
     const uint32_t wpc = P.smem_stride / 4, nwords = P.smem_cells * wpc;
-    for (uint32_t i = threadIdx.x; i < nwords; i += kThreads) reinterpret_cast<uint32_t *>(s_table)[i] = P.smem_init[i % wpc];
+    for (uint32_t i = threadIdx.x; i < nwords; i += kScanThreads) reinterpret_cast<uint32_t *>(s_table)[i] = P.smem_init[i % wpc];
   }
   __syncthreads();
   const bool can_overflow = P.hash_mode != 0;
@@ -319,7 +335,7 @@ scan_filter_groupby_kernel(const __grid_constant__ ScanParams P) {
 
   // ---- aggregate one passing row of the current segment (one row per lane) ----
   // fast path: up to 4 keys of at most 4 bytes and up to 4 metrics, staged in 12 registers
-  const bool small_plan = P.small_plan != 0 && P.hash_mode != 2;  // uniform
+  const bool small_plan = kFast || (P.small_plan != 0 && P.hash_mode != 2);  // uniform
   auto process_row = [&](const uint32_t row, const bool rowpath) {
     uint32_t kv[4];
     uint64_t mv[4];
@@ -358,7 +374,7 @@ scan_filter_groupby_kernel(const __grid_constant__ ScanParams P) {
       }
     }
     uint64_t packed = 0;
-    if (P.hash_mode == 2) {
+    if (!kFast && P.hash_mode == 2) {
       packed = wide_row_cell(P, seg, row);  // rare path, out of line
     } else if (small_plan) {
 #pragma unroll
@@ -378,18 +394,18 @@ scan_filter_groupby_kernel(const __grid_constant__ ScanParams P) {
           packed += val * ks.mul;
         }
       }
-    } else {
+    } else if (!kFast) {
       packed = general_row_key<kPlainKeys>(P, seg, row);
     }
     uint64_t cell;
-    if (P.hash_mode == 2) {
+    if (!kFast && P.hash_mode == 2) {
       cell = packed;
       if (cell == kEmptyKey) {
         atomicOr(&P.counters[kCHashOver], 1ull);
         return;
       }
     } else if (P.hash_mode) {
-      cell = hash_cell_call(P, packed);
+      cell = kFast ? hash_cell(P, packed) : hash_cell_call(P, packed);
       if (cell == kEmptyKey) {
         atomicOr(&P.counters[kCHashOver], 1ull);
         return;
@@ -397,7 +413,7 @@ scan_filter_groupby_kernel(const __grid_constant__ ScanParams P) {
     } else {
       cell = packed;
       if (kSmemTable) *reinterpret_cast<volatile uint32_t *>(s_table + (uint32_t)cell * P.smem_stride + P.smem_present_off) = 1u;
-      else st_u8_hint(P.present + cell * P.present_stride, 1u, tpol);
+      else if (!P.skip_present) st_u8_hint(P.present + cell * P.present_stride, 1u, tpol);
     }
     uint32_t dn = 0;
     for (uint32_t m = 0; m < P.nmetrics; ++m) {
@@ -408,11 +424,13 @@ scan_filter_groupby_kernel(const __grid_constant__ ScanParams P) {
         const uint32_t pos = rowpath ? rpos + ms.row_off : row * ms.width;
         pre = (raw >> ((pos & 7u) * 8u)) & ms.vmask;
         pre = (pre ^ ms.signbit) - ms.signbit;
-      } else {
+      } else if (!kFast) {
         const uint32_t *off = sd.bs_offsets[ms.bitset_idx];
         const uint8_t *a = ms.bitset ? reinterpret_cast<const uint8_t *>((off == nullptr ? sd.bs_values[ms.bitset_idx] : off) + row)
                                      : seg.slab + ms.col_off * seg.cap + (uint64_t)row * ms.width;
         pre = gather_finish(gather_raw64(a), a, ms.vmask, ms.signbit);
+      } else {
+        pre = 0;
       }
       if (ms.op != A_DISTINCT) {
         if (kSmemTable) acc_update_shared(s_table_a + (uint32_t)cell * P.smem_stride + ms.soff, ms.op, pre);
@@ -421,9 +439,26 @@ scan_filter_groupby_kernel(const __grid_constant__ ScanParams P) {
       }
       // count-distinct: append (cell, id) to this CTA's region (of the pair's owner rank); deduplicated after the scan
       const uint32_t *off = sd.bs_offsets[ms.bitset_idx];
-      const uint64_t hi = P.dpair_key ? packed : cell;
-      if (off == nullptr) append_pair(P, s_cursor[dn], dn, hi, pre);   // one id per row: `pre` is the id
-      else append_csr_cell(P, s_cursor[dn], dn, hi, sd.bs_values[ms.bitset_idx], (uint32_t)pre, gather_u32(off + row + 1), ms.id64);
+      if (kFast) {   // 8-byte pairs (cell, 32-bit id); one sub-region per owner rank when several GPUs take part
+        const uint32_t *vals = sd.bs_values[ms.bitset_idx];
+        if (off == nullptr) {  // one id per row: `pre` is the id
+          const uint32_t sub = P.dpair_nsub > 1 ? pair_owner(cell, pre, P.dpair_nsub) : 0u;
+          const uint32_t pos = atomicAdd(&s_cursor[dn][sub], 1u);
+          if (pos < P.dpair_cap) P.dpairs[dn][((uint64_t)sub * gridDim.x + blockIdx.x) * P.dpair_cap + pos] = (cell << 32) | pre;
+        } else {               // CSR cell: `pre` is offsets[row]
+          const uint32_t lo = (uint32_t)pre, hi_q = gather_u32(off + row + 1);
+          for (uint32_t q = lo; q < hi_q; ++q) {
+            const uint64_t id = gather_u32(vals + q);
+            const uint32_t sub = P.dpair_nsub > 1 ? pair_owner(cell, id, P.dpair_nsub) : 0u;
+            const uint32_t pos = atomicAdd(&s_cursor[dn][sub], 1u);
+            if (pos < P.dpair_cap) P.dpairs[dn][((uint64_t)sub * gridDim.x + blockIdx.x) * P.dpair_cap + pos] = (cell << 32) | id;
+          }
+        }
+      } else {
+        const uint64_t hi = P.dpair_key ? packed : cell;
+        if (off == nullptr) append_pair(P, s_cursor[dn], dn, hi, pre);   // one id per row: `pre` is the id
+        else append_csr_cell(P, s_cursor[dn], dn, hi, sd.bs_values[ms.bitset_idx], (uint32_t)pre, gather_u32(off + row + 1), ms.id64);
+      }
       ++dn;
     }
   };
@@ -486,7 +521,7 @@ scan_filter_groupby_kernel(const __grid_constant__ ScanParams P) {
         asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a), "r"((uint32_t)kChunkRows * P.pf_width[lane]) : "memory");
     }
 
-    uint32_t mask = eval_predicate(P, seg, row0, pol);
+    uint32_t mask = eval_predicate<kConj>(P, seg, row0, pol);
     // rows past the end of a partially filled segment never count
     if (chunk_row + kChunkRows > nrows) {
 #pragma unroll
@@ -555,7 +590,7 @@ scan_filter_groupby_kernel(const __grid_constant__ ScanParams P) {
   // merge the CTA-private table into the global one: the same commutative Update(), once per live cell
   if (kSmemTable) {
     __syncthreads();
-    for (uint32_t c = threadIdx.x; c < P.smem_cells; c += kThreads) {
+    for (uint32_t c = threadIdx.x; c < P.smem_cells; c += kScanThreads) {
       const uint8_t *cellp = s_table + c * P.smem_stride;
       if (*reinterpret_cast<const uint32_t *>(cellp + P.smem_present_off) == 0) continue;
       st_u8_hint(P.present + (uint64_t)c * P.present_stride, 1u, tpol);

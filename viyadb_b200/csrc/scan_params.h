@@ -202,6 +202,8 @@ struct ScanParams {
   uint32_t present_stride; // bytes between the presence flags of consecutive cells (dense)
   uint64_t hmask;          // capacity - 1
   uint8_t *present;        // dense: 1 byte per cell; hash: present[0] flags the sentinel key
+  uint32_t skip_present;   // dense: no presence store per row — a COUNT accumulator whose cells are all >= 1 (segment
+                           // statistics) is non-zero exactly for the groups that exist: one L2 operation less per row
   uint32_t *wstate;        // wide mode: 0 free, 1 being written, 2 ready
   uint64_t *wkeys;         // wide mode: capacity x nkeys words
   uint32_t max_probe;

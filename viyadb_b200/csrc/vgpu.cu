@@ -293,9 +293,10 @@ struct vgpu_ctx {
   // (always the stack interpreter), bit 13 per-lane instead of bulk L2 prefetch of the next chunk, bit 14 no
   // tightening of key domains from the predicate, bit 18 no CTA-private shared-memory copy of small dense group tables,
   // bit 19 count-distinct: never the shared-memory-set fast path, bit 20 no early group extraction on the side
-  // stream, bit 21 no bucket dictionary for rolled-up time keys
+  // stream, bit 21 no bucket dictionary for rolled-up time keys, bit 22 always store presence flags (never read them
+  // off a COUNT accumulator)
   uint32_t tune = 2;
-  int ctas_per_sm = VGPU_MIN_CTAS;  // VGPU_CTAS: resident scan CTAs per SM (2, 3 or 4: picks the register cap)
+  int ctas_per_sm = VGPU_MIN_CTAS;  // resident scan CTAs per SM (compile time: with kScanThreads it fixes the register cap)
   uint32_t unit_chunks = 0;  // VGPU_UNIT_CHUNKS: 512-row chunks per dynamically scheduled work unit (0: adaptive)
   // test hooks that force the rarely taken branches at test sizes (tests/test_gpu_forced_paths.py):
   uint64_t test_pairs_cap = 0;     // VGPU_TEST_PAIRS_CAP: first-attempt capacity of the count-distinct pair regions (overflow + regrow)
@@ -588,6 +589,10 @@ void compute_stats(vgpu_table *t, uint32_t seg_idx) {
   std::vector<uint32_t> want;
   for (uint32_t c = 0; c < t->ndims; ++c)
     if (!t->cols[c].bitset) want.push_back(c);
+  // COUNT metrics too: a count cell is the number of raw rows behind a stored row, >= 1 in every table the reference
+  // builds — when the statistics confirm it, "group present" can be read off the count accumulator (query_agg.inl)
+  for (uint32_t c = t->ndims; c < t->cols.size(); ++c)
+    if (!t->cols[c].bitset && t->cols[c].agg == VGPU_AGG_COUNT && !type_float(t->cols[c].type) && !type_signed(t->cols[c].type)) want.push_back(c);
   if (sd.nrows == 0 || want.empty()) return;
   ensure_stats_capacity(t, t->segs.size());
   unsigned long long *d_out = t->d_stats + (size_t)seg_idx * 2 * ncols;
@@ -1124,8 +1129,12 @@ int vgpu_init(int device, vgpu_ctx **out) {
     cudaDeviceProp prop;
     CUDA_CK(cudaGetDeviceProperties(&prop, device));
     ctx->sm_count = prop.multiProcessorCount;
-    CUDA_CK(cudaFuncSetAttribute(scan_filter_groupby_kernel<3, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemTableBytes));
-    CUDA_CK(cudaFuncSetAttribute(scan_filter_groupby_kernel<3, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemTableBytes));
+    CUDA_CK(cudaFuncSetAttribute(scan_filter_groupby_kernel<VGPU_MIN_CTAS, true, true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemTableBytes));
+    CUDA_CK(cudaFuncSetAttribute(scan_filter_groupby_kernel<VGPU_MIN_CTAS, true, false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemTableBytes));
+    CUDA_CK(cudaFuncSetAttribute(scan_filter_groupby_kernel<VGPU_MIN_CTAS, true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemTableBytes));
+    CUDA_CK(cudaFuncSetAttribute(scan_filter_groupby_kernel<VGPU_MIN_CTAS, true, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemTableBytes));
+    CUDA_CK(cudaFuncSetAttribute(scan_filter_groupby_kernel<VGPU_MIN_CTAS, true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemTableBytes));
+    CUDA_CK(cudaFuncSetAttribute(scan_filter_groupby_kernel<VGPU_MIN_CTAS, true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemTableBytes));
     CUDA_CK(cudaFuncSetAttribute(pairs_bucket_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * kMaxSmemBuckets * 4)));
     CUDA_CK(cudaFuncSetAttribute(pairs_dedupe_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kSmemSetSlots * 8)));
     CUDA_CK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
@@ -1139,7 +1148,6 @@ int vgpu_init(int device, vgpu_ctx **out) {
     CUDA_CK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &threshold));
     if (const char *e = getenv("VGPU_TUNE")) ctx->tune = (uint32_t)strtoul(e, nullptr, 0);
     ctx->trace = getenv("VGPU_TRACE") != nullptr;
-    if (const char *e = getenv("VGPU_CTAS")) { int c = atoi(e); if (c >= 2 && c <= 4) ctx->ctas_per_sm = c; }
     if (const char *e = getenv("VGPU_UNIT_CHUNKS")) ctx->unit_chunks = (uint32_t)strtoul(e, nullptr, 0);
     if (const char *e = getenv("VGPU_TEST_PAIRS_CAP")) ctx->test_pairs_cap = strtoull(e, nullptr, 0);
     if (const char *e = getenv("VGPU_TEST_HASH_CAP")) ctx->test_hash_cap = strtoull(e, nullptr, 0);
