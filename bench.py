@@ -355,7 +355,8 @@ def run_workload(args, wname, steps, torch, v, dist, rank, world, local, full):
     t_gen = time.time() - t_gen
 
     query = QueryFactory.create(w["query"], db)
-    runner = GpuQueryRunner(db, v.MemoryRowOutput(), now=NOW)
+    # several GPUs: the merged groups are copied to rank 0's host only (one client gets one answer)
+    runner = GpuQueryRunner(db, v.MemoryRowOutput(), now=NOW, flags=N.PLAN_RESULT_ON_ROOT if world > 1 else 0)
     plan = runner.build_plan(query)
 
     def step():
@@ -399,7 +400,7 @@ def run_workload(args, wname, steps, torch, v, dist, rank, world, local, full):
     clocks = sampler.stop(wall0, wall1) if rank == 0 else None
     total_rows = rows * world
     passed = runner.stats.passed_rows          # all ranks (summed in the merge)
-    ngroups = groups["ngroups"]
+    ngroups = runner.stats.aggregated_recs
     selectivity = passed / max(1, runner.stats.scanned_recs)
     b_alg = w["filter_bytes"] + selectivity * w["payload_bytes"]
     peak, peak_src = load_peaks()

@@ -29,7 +29,7 @@ TU_YEAR, TU_MONTH, TU_WEEK, TU_DAY, TU_HOUR, TU_MINUTE, TU_SECOND, TU_NONE = ran
 NODE_RELOP, NODE_IN, NODE_AND, NODE_OR, NODE_EMPTY = range(5)
 # vgpu_relop (== query::RelOpFilter::Operator order)
 OP_EQ, OP_NE, OP_LT, OP_LE, OP_GT, OP_GE = range(6)
-PLAN_FORCE_HASH, PLAN_FORCE_DENSE = 1, 2
+PLAN_FORCE_HASH, PLAN_FORCE_DENSE, PLAN_RESULT_ON_ROOT = 1, 2, 4
 DEDUPE_SMALL, DEDUPE_FAST, DEDUPE_WIDE, DEDUPE_GENERAL, DEDUPE_REDONE, DEDUPE_PARTITIONED = 1, 2, 4, 8, 16, 32
 MAX_ROLLUP_RULES = 8
 

@@ -851,7 +851,7 @@ int vgpu_query_agg(vgpu_table *t, const vgpu_plan *plan, vgpu_result **out) {
     if (P.ndistinct) {
       const uint64_t nregions = (uint64_t)region_grid * P.dpair_nsub;
       const uint64_t fill_hint = hint_load(t->pairs_region_hint);
-      if (fill_hint) region_cap64 = fill_hint + fill_hint / 2 + 2048;   // work units are handed out dynamically: a CTA's share varies from run to run
+      if (fill_hint) region_cap64 = fill_hint + fill_hint / 8 + std::min<uint64_t>(fill_hint / 2, 4096) + 256;   // work units are handed out dynamically: a CTA's share varies from run to run (small tables most)
       else region_cap64 = std::max<uint64_t>(1ull << 16, max_active_rows / 16) / nregions * 5 / 4 + 1024;
       if (ctx->test_pairs_cap) region_cap64 = std::max<uint64_t>(ctx->test_pairs_cap / nregions, 4);
     }
@@ -1371,7 +1371,9 @@ int vgpu_query_agg(vgpu_table *t, const vgpu_plan *plan, vgpu_result **out) {
         }
       }
       if (ngroups > rows_bound) fail(VGPU_ERR_CUDA, "group extraction overflow");
-      host_copy(ngroups);
+      // several GPUs, VGPU_PLAN_RESULT_ON_ROOT: the merged groups go to rank 0's host only
+      const uint64_t out_rows = (G > 1 && (plan->flags & VGPU_PLAN_RESULT_ON_ROOT) && ctx->rank != 0) ? 0 : ngroups;
+      host_copy(out_rows);
       // the flags of the fast dedupe path travel behind everything on s0
       unsigned long long *hc2 = sc->h_counters + 32;
       CUDA_CK(cudaMemcpyAsync(hc2, sc->d_counters, 16 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream));
@@ -1389,16 +1391,16 @@ int vgpu_query_agg(vgpu_table *t, const vgpu_plan *plan, vgpu_result **out) {
         }
         for (uint32_t d = 0; d < P.ndistinct; ++d) {
           const uint32_t m = P.distinct_met[d];
-          if (m < plan->nmetrics && ngroups)
-            CUDA_CK(cudaMemcpyAsync(const_cast<void *>(res->acc_ptrs[m]), d_accs[m], ngroups * q.accs[m].out_width, cudaMemcpyDeviceToHost, stream));
+          if (m < plan->nmetrics && out_rows)
+            CUDA_CK(cudaMemcpyAsync(const_cast<void *>(res->acc_ptrs[m]), d_accs[m], out_rows * q.accs[m].out_width, cudaMemcpyDeviceToHost, stream));
         }
         if (!early) {  // the whole extraction was redone: the order of the groups changed with it
           for (uint32_t k = 0; k < plan->nkeys; ++k)
-            if (ngroups) CUDA_CK(cudaMemcpyAsync(const_cast<void *>(res->key_ptrs[k]), d_keys[k], ngroups * t->cols[plan->keys[k].col].width, cudaMemcpyDeviceToHost, stream));
+            if (out_rows) CUDA_CK(cudaMemcpyAsync(const_cast<void *>(res->key_ptrs[k]), d_keys[k], out_rows * t->cols[plan->keys[k].col].width, cudaMemcpyDeviceToHost, stream));
           for (uint32_t m = 0; m < plan->nmetrics; ++m)
-            if (ngroups) CUDA_CK(cudaMemcpyAsync(const_cast<void *>(res->acc_ptrs[m]), d_accs[m], ngroups * q.accs[m].out_width, cudaMemcpyDeviceToHost, stream));
-          if (plan->need_hidden_count && ngroups)
-            CUDA_CK(cudaMemcpyAsync(const_cast<uint64_t *>(view.hidden_count), d_accs[plan->nmetrics], ngroups * 8, cudaMemcpyDeviceToHost, stream));
+            if (out_rows) CUDA_CK(cudaMemcpyAsync(const_cast<void *>(res->acc_ptrs[m]), d_accs[m], out_rows * q.accs[m].out_width, cudaMemcpyDeviceToHost, stream));
+          if (plan->need_hidden_count && out_rows)
+            CUDA_CK(cudaMemcpyAsync(const_cast<uint64_t *>(view.hidden_count), d_accs[plan->nmetrics], out_rows * 8, cudaMemcpyDeviceToHost, stream));
         }
         CUDA_CK(cudaEventRecord(sc->ev_end, stream));
         CUDA_CK(cudaStreamSynchronize(stream));
@@ -1406,7 +1408,7 @@ int vgpu_query_agg(vgpu_table *t, const vgpu_plan *plan, vgpu_result **out) {
       hint_raise(t->groups_hint, ngroups);
       float total_ms = 0;
       CUDA_CK(cudaEventElapsedTime(&total_ms, sc->ev_begin, sc->ev_end));
-      view.ngroups = ngroups;
+      view.ngroups = out_rows;
       view.aggregated_recs = ngroups;
       view.gpu_ms = total_ms;
       view.scan_ms = scan_ms_total;

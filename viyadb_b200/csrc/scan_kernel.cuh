@@ -177,7 +177,9 @@ __device__ __forceinline__ uint32_t eval_predicate(const ScanParams &P, const Cu
     }
     return m;
   }
-  if (kConjOnly) return 0;
+  if constexpr (kConjOnly) {
+    return 0;
+  } else {
   uint32_t stk[kStackDepth];
 #pragma unroll
   for (int i = 0; i < kStackDepth; ++i) stk[i] = 0;
@@ -234,6 +236,7 @@ __device__ __forceinline__ uint32_t eval_predicate(const ScanParams &P, const Cu
     }
   }
   return stk[0];
+  }
 }
 
 // Wide key tuples (hash_mode 2): gather the key words of one row and find / claim its slot. Out of line
