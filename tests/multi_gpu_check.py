@@ -41,10 +41,18 @@ def main():
     # arrays (the multi-GPU layout) at the end of the scan
     low = {"c1low": dict(bench.WORKLOADS["c1"], query=dict(bench.WORKLOADS["c1"]["query"], dimensions=["d0"], metrics=["m1", "m2", "count"])),
            "c2low": dict(bench.WORKLOADS["c2"], query=dict(bench.WORKLOADS["c2"]["query"], dimensions=["d1"], metrics=["mn", "mx", "uid"])),
-           "c0": bench.WORKLOADS["c0"]}
+           "c0": bench.WORKLOADS["c0"],
+           # key tuple wider than 64 bits (float + double + code): wide-tuple hash tables, merged by gathering every rank's records
+           "wide": {"table": {"name": "events", "segment_size": SEG,
+                              "dimensions": [{"name": "f", "type": "float"}, {"name": "g", "type": "double"}, {"name": "d0"}],
+                              "metrics": [{"name": "count", "type": "count"}, {"name": "m1", "type": "long_sum"},
+                                          {"name": "mx", "type": "int_max"}]},
+                    "gens": [(-3, 7), (-40, 90), (1, 30), (1, 1), (0, 1000), (-2**31, 2**32)], "prefix": ["", "", "a", "", "", ""],
+                    "query": {"type": "aggregate", "table": "events", "dimensions": ["f", "g", "d0"], "metrics": ["m1", "count", "mx"],
+                              "filter": {"op": "gt", "column": "m1", "value": "100"}}}}
     only = os.environ.get("VGPU_CHECK_ONLY")
     for wname, flags in (("c1", 0), ("c2", 2), ("c3", 0), ("c4", 0), ("c1", 1), ("c3", 1), ("c2", 1), ("c4", 1), ("c1low", 0), ("c2low", 0),
-                         ("c0", 0)):
+                         ("c0", 0), ("wide", 0)):
         if only and wname != only:
             continue
         w = low.get(wname) or bench.WORKLOADS[wname]

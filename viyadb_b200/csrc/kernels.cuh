@@ -774,6 +774,59 @@ __global__ void __launch_bounds__(256) merge_records_kernel(const __grid_constan
   }
 }
 
+// Wide key tuples across ranks: compact the live slots of a wide table (state 2) into records (nkeys key words + one
+// partial accumulator per metric), and merge records into a wide table with the same Update().
+struct WideCompactParams {
+  const uint32_t *wstate;
+  const uint64_t *wkeys;
+  uint64_t nslots;
+  uint32_t nkeys, nmets;
+  uint64_t cap;                      // records the outputs hold
+  unsigned long long *cursor;
+  uint64_t *out_keys;                // [cap * nkeys]
+  uint32_t widths[kMaxMetrics + 1];
+  const void *src[kMaxMetrics + 1];  // indexed by slot
+  void *dst[kMaxMetrics + 1];        // indexed by record
+};
+__global__ void __launch_bounds__(256) wide_compact_kernel(const __grid_constant__ WideCompactParams W) {
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < W.nslots; i += (uint64_t)gridDim.x * blockDim.x) {
+    if (W.wstate[i] != 2u) continue;
+    const unsigned long long p = atomicAdd(W.cursor, 1ull);
+    if (p >= W.cap) continue;
+    for (uint32_t k = 0; k < W.nkeys; ++k) W.out_keys[p * W.nkeys + k] = W.wkeys[i * W.nkeys + k];
+    for (uint32_t m = 0; m < W.nmets; ++m) {
+      if (W.widths[m] == 4) reinterpret_cast<uint32_t *>(W.dst[m])[p] = reinterpret_cast<const uint32_t *>(W.src[m])[i];
+      else reinterpret_cast<uint64_t *>(W.dst[m])[p] = reinterpret_cast<const uint64_t *>(W.src[m])[i];
+    }
+  }
+}
+struct WideMergeParams {
+  const uint64_t *keys;              // [n * nkeys]
+  uint64_t n;
+  uint32_t nmets;
+  uint32_t ops[kMaxMetrics + 1];
+  uint32_t widths[kMaxMetrics + 1];
+  const void *src[kMaxMetrics + 1];
+  void *acc[kMaxMetrics + 1];
+  unsigned long long *overflow;
+};
+// T carries the destination table (wstate, wkeys, hmask, nkeys, max_probe): wide_cell() finds or claims the slot
+__global__ void __launch_bounds__(256) wide_merge_kernel(const __grid_constant__ ScanParams T, const __grid_constant__ WideMergeParams M) {
+  const uint64_t pol = make_table_policy(false);
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < M.n; i += (uint64_t)gridDim.x * blockDim.x) {
+    uint64_t kw[kMaxKeys];
+    for (uint32_t k = 0; k < T.nkeys; ++k) kw[k] = M.keys[i * T.nkeys + k];
+    const uint64_t cell = wide_cell(T, kw);
+    if (cell == kEmptyKey) { atomicExch(M.overflow, 1ull); continue; }
+    for (uint32_t m = 0; m < M.nmets; ++m) {
+      uint64_t v = M.widths[m] == 4 ? (uint64_t)reinterpret_cast<const uint32_t *>(M.src[m])[i]
+                                    : reinterpret_cast<const uint64_t *>(M.src[m])[i];
+      if (M.ops[m] == A_ADD32 || M.ops[m] == A_MINS32 || M.ops[m] == A_MAXS32) v = (uint64_t)(int64_t)(int32_t)(uint32_t)v;
+      acc_update(reinterpret_cast<uint8_t *>(M.acc[m]) + cell * M.widths[m], M.ops[m], v, pol);
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // group extraction: present cells -> dense SoA result
 // ---------------------------------------------------------------------------------------------

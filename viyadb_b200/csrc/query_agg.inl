@@ -568,6 +568,103 @@ void nccl_merge_hash(vgpu_ctx *ctx, QueryScope *sc, QueryRun &q, ScanParams &P, 
   }
 }
 
+// Wide key tuples (hash_mode 2) across ranks: every rank compacts its live (key tuple, partial accumulators) records,
+// all records are gathered on every rank (broadcast per rank: wide tables are the rare case, no owner step) and merged
+// into a fresh wide table with the same Update(). On return P / acc_ptrs / acc_cells describe the merged table.
+void nccl_merge_wide(vgpu_ctx *ctx, QueryScope *sc, QueryRun &q, ScanParams &P, std::vector<void *> &acc_ptrs, Scratch &scratch,
+                     uint64_t &acc_cells, uint64_t local_bound, uint32_t &launches) {
+  const int G = ctx->nranks;
+  cudaStream_t stream = sc->s0;
+  const size_t nm = q.accs.size();
+  const uint32_t nkeys = std::max<uint32_t>(P.nkeys, 1);
+  const uint64_t nslots = P.hmask + 1;
+  const uint64_t cap = std::max<uint64_t>(1, std::min(nslots, local_bound));
+  WideCompactParams W{};
+  W.wstate = P.wstate;
+  W.wkeys = P.wkeys;
+  W.nslots = nslots;
+  W.nkeys = nkeys;
+  W.nmets = (uint32_t)nm;
+  W.cap = cap;
+  W.cursor = scratch.alloc<unsigned long long>(1);
+  CUDA_CK(cudaMemsetAsync(W.cursor, 0, 8, stream));
+  W.out_keys = scratch.alloc<uint64_t>(cap * nkeys);
+  std::vector<void *> send_acc(nm);
+  for (size_t m = 0; m < nm; ++m) {
+    send_acc[m] = scratch.alloc<uint8_t>(cap * q.accs[m].acc_width);
+    W.widths[m] = q.accs[m].acc_width;
+    W.src[m] = acc_ptrs[m];
+    W.dst[m] = send_acc[m];
+  }
+  wide_compact_kernel<<<grid_for(nslots, 256, ctx->sm_count), 256, 0, stream>>>(W);
+  CUDA_CK(cudaGetLastError());
+  ++launches;
+  uint64_t *d_all = scratch.alloc<uint64_t>(G);
+  NCCL_CK(g_nccl.AllGather(W.cursor, d_all, 1, ncclUint64, ctx->comm, stream));
+  std::vector<uint64_t> counts(G);
+  CUDA_CK(cudaMemcpyAsync(counts.data(), d_all, G * 8, cudaMemcpyDeviceToHost, stream));
+  CUDA_CK(cudaStreamSynchronize(stream));
+  std::vector<uint64_t> off(G);
+  uint64_t total = 0;
+  for (int r = 0; r < G; ++r) { off[r] = total; total += counts[r]; }
+  uint64_t *all_keys = scratch.alloc<uint64_t>(total * nkeys);
+  std::vector<void *> all_acc(nm);
+  for (size_t m = 0; m < nm; ++m) all_acc[m] = scratch.alloc<uint8_t>(total * q.accs[m].acc_width);
+  NCCL_CK(g_nccl.GroupStart());
+  for (int r = 0; r < G; ++r) {
+    if (counts[r] == 0) continue;
+    NCCL_CK(g_nccl.Broadcast(W.out_keys, all_keys + off[r] * nkeys, counts[r] * nkeys * 8, ncclUint8, r, ctx->comm, stream));
+    for (size_t m = 0; m < nm; ++m) {
+      const uint32_t w = q.accs[m].acc_width;
+      NCCL_CK(g_nccl.Broadcast(send_acc[m], static_cast<uint8_t *>(all_acc[m]) + off[r] * w, counts[r] * w, ncclUint8, r, ctx->comm, stream));
+    }
+  }
+  NCCL_CK(g_nccl.GroupEnd());
+  // the merged table
+  const uint64_t mcap = pow2_ceil(std::max<uint64_t>(2 * total, 1024));
+  uint64_t block_bytes = 0;
+  auto carve = [&](uint64_t bytes) { uint64_t o = block_bytes; block_bytes += round_up(bytes, 256); return o; };
+  const uint64_t o_state = carve(mcap * 4), o_keys = carve(mcap * 8 * nkeys);
+  std::vector<uint64_t> o_a(nm);
+  for (size_t m = 0; m < nm; ++m) o_a[m] = carve((mcap + 1) * q.accs[m].acc_width);
+  uint8_t *block = scratch.alloc<uint8_t>(block_bytes);
+  ScanParams T{};
+  T.nkeys = P.nkeys;
+  T.hmask = mcap - 1;
+  T.max_probe = (uint32_t)std::min<uint64_t>(mcap, 1u << 20);
+  T.wstate = reinterpret_cast<uint32_t *>(block + o_state);
+  T.wkeys = reinterpret_cast<uint64_t *>(block + o_keys);
+  CUDA_CK(cudaMemsetAsync(T.wstate, 0, mcap * 4, stream));
+  WideMergeParams M{};
+  M.keys = all_keys;
+  M.n = total;
+  M.nmets = (uint32_t)nm;
+  M.overflow = scratch.alloc<unsigned long long>(1);
+  CUDA_CK(cudaMemsetAsync(M.overflow, 0, 8, stream));
+  for (size_t m = 0; m < nm; ++m) {
+    M.ops[m] = q.accs[m].op;
+    M.widths[m] = q.accs[m].acc_width;
+    M.src[m] = all_acc[m];
+    M.acc[m] = block + o_a[m];
+    if (q.accs[m].acc_width == 4) launches += fill32(stream, ctx->sm_count, M.acc[m], mcap + 1, (uint32_t)q.accs[m].init);
+    else launches += fill64(stream, ctx->sm_count, M.acc[m], mcap + 1, q.accs[m].init);
+  }
+  if (total) {
+    wide_merge_kernel<<<grid_for(total, 256, ctx->sm_count), 256, 0, stream>>>(T, M);
+    CUDA_CK(cudaGetLastError());
+    ++launches;
+  }
+  P.wstate = T.wstate;
+  P.wkeys = T.wkeys;
+  P.hmask = T.hmask;
+  for (size_t m = 0; m < nm; ++m) {
+    acc_ptrs[m] = M.acc[m];
+    P.mets[m].acc = M.acc[m];
+    P.mets[m].stride = q.accs[m].acc_width;
+  }
+  acc_cells = mcap + 1;
+}
+
 }  // namespace
 }  // extern "C++"
 
@@ -773,7 +870,8 @@ int vgpu_query_agg(vgpu_table *t, const vgpu_plan *plan, vgpu_result **out) {
       if (cells128 > ((unsigned __int128)1 << 64) - 2) { fits64 = false; break; }
     }
     const bool wide = !fits64;  // key tuple wider than 64 bits: hash on the full tuple
-    if (wide && G > 1) fail(VGPU_ERR_UNSUPPORTED, "multi-GPU merge of key tuples wider than 64 bits is not implemented yet");
+    if (wide && G > 1 && P.ndistinct)
+      fail(VGPU_ERR_UNSUPPORTED, "multi-GPU count-distinct over key tuples wider than 64 bits is not implemented");
     if (wide && (plan->flags & VGPU_PLAN_FORCE_DENSE)) fail(VGPU_ERR_UNSUPPORTED, "key domain too large for a dense group table");
     const uint64_t cells = wide ? ~0ull : (uint64_t)cells128;
     uint64_t dense_limit = std::min<uint64_t>(std::max<uint64_t>(4 * global_active_rows, 1ull << 22), 1ull << 28);
@@ -1126,7 +1224,9 @@ int vgpu_query_agg(vgpu_table *t, const vgpu_plan *plan, vgpu_result **out) {
           // every rank must take the same grow-and-retry decision before the records travel
           read_counters(stream);
           abort_attempt = hc[kCHashOver] != 0 || hc[kCRegionOver] != 0;
-          if (!abort_attempt) {
+          if (!abort_attempt && q.wide) {
+            nccl_merge_wide(ctx, sc, q, P, acc_ptrs, scratch, acc_cells_x, std::max<uint64_t>(q.active_rows, 1), launches);
+          } else if (!abort_attempt) {
             nccl_merge_hash(ctx, sc, q, P, acc_ptrs, scratch, acc_cells_x, launches, [&] {
               // count-distinct: the owner's table holds every key it owns; dedupe the pairs of those keys against it
               for (uint32_t d = 0; d < P.ndistinct; ++d) {
