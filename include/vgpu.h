@@ -266,6 +266,14 @@ int vgpu_segment_put(vgpu_table *table, uint32_t seg_idx, uint64_t nrows,
 int vgpu_segment_put_async(vgpu_table *table, uint32_t seg_idx, uint64_t nrows,
                            const void *const *col_ptrs);
 int vgpu_table_sync(vgpu_table *table);
+/* Incremental sync (the live store grows and its upserts update metric cells in place, src/codegen/db/upsert.cc:386-411):
+ * replace rows [row_begin, row_begin + nrows) of an uploaded segment — col_ptrs[c] addresses the cell of row `row_begin` —
+ * and/or append behind its last row (row_begin <= rows so far). Only the range crosses PCIe; the per-column statistics
+ * are reduced again on the device and the row-major mirror is rebuilt for the range only. VGPU_ERR_STATE when the range
+ * does not fit the segment's device buffers, VGPU_ERR_UNSUPPORTED for bitset columns whose cells do not hold exactly one
+ * 32-bit id: the caller then puts the whole segment. */
+int vgpu_segment_update(vgpu_table *table, uint32_t seg_idx, uint64_t row_begin, uint64_t nrows,
+                        const void *const *col_ptrs);
 /* Page-lock a host range for DMA (cudaHostRegister) / release it: the reference's segments are single heap objects
  * (`new Segment`, src/codegen/db/store.cc:203-356) that the adapter pins once, when it first uploads them. */
 int vgpu_host_pin(vgpu_ctx *ctx, const void *ptr, size_t bytes);

@@ -15,7 +15,7 @@ sys.path.insert(0, os.path.join(HERE, "golden"))
 def run_scenario(sc, stock_only=False, timeout=600):
     job = {"ref_root": os.path.join(REF, "root"), "state_dir": os.path.join(REF, "state"),
            "table": sc["table"], "queries": sc["queries"], "stock_only": stock_only}
-    for k in ("rows", "generate", "rollup_ts", "reload_rows"):
+    for k in ("rows", "generate", "rollup_ts", "reload_rows", "reload_mode"):
         if k in sc:
             job[k] = sc[k]
     fd, path = tempfile.mkstemp(suffix=".json", prefix="vgpu_job_")

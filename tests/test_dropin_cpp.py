@@ -95,7 +95,8 @@ def test_gpu_runner_select_search_equals_stock_runner(sc):
             assert gpu["stats"][k] == stock["stats"][k] == gold["stats"][k], (qi, k, gpu["stats"], stock["stats"])
 
 
-def test_resident_copy_follows_in_place_upserts():
+@pytest.mark.parametrize("mode", ["epoch", "mark"])
+def test_resident_copy_follows_in_place_upserts(mode):
     """A second ingest batch into the SAME dimension tuples updates metric cells of existing rows in place
     (src/codegen/db/upsert.cc:386-393): no segment grows, yet the resident HBM copy is stale. The GPU runner must
     return what the stock runner returns, before and after."""
@@ -104,8 +105,11 @@ def test_resident_copy_follows_in_place_upserts():
     sc = next(s for s in scenarios.SCENARIOS if s["name"] == "inapp")
     # same tuples again with other metric values, plus one new tuple
     reload_rows = [r[:3] + [str(float(r[3]) * 3 + 1)] for r in sc["rows"]] + [["IL", "gift", "20141114", "7.5"]]
-    out = D.run_scenario(dict(sc, reload_rows=reload_rows))
+    out = D.run_scenario(dict(sc, reload_rows=reload_rows, reload_mode=mode))
     assert "fatal" not in out, out.get("fatal")
+    # "mark": exact dirty ranges (what an upsert hook reports) -> only those rows and the appended ones are uploaded
+    # again (vgpu_segment_update); "epoch": the coarse notification -> whole segments
+    assert (out["partial_updates"] > 0) == (mode == "mark"), out["partial_updates"]
     changed = 0
     for key in ("results", "results_after_reload"):
         for qi, res in enumerate(out[key]):

@@ -314,3 +314,58 @@ def test_concurrent_queries_and_put(mid):
     out = v.MemoryRowOutput()
     stats = db.query({"type": "aggregate", "table": "other", "dimensions": ["d0"], "metrics": ["uid"]}, out, now=NOW)
     assert stats.scanned_recs == 600000
+
+
+# ---- incremental sync: in-place updates of a row range + appended rows (vgpu_segment_update) ----
+def test_segment_update_ranges(built_lib):
+    import viyadb_b200 as v
+    conf = {"name": "live", "segment_size": 60000,
+            "dimensions": [{"name": "d0"}, {"name": "n1", "type": "ushort"}, {"name": "t2", "type": "time"}],
+            "metrics": [{"name": "count", "type": "count"}, {"name": "ls", "type": "long_sum"}, {"name": "mx", "type": "int_max"},
+                        {"name": "uid", "type": "bitset"}]}
+    spec = {"d0": (1, 12), "n1": (0, 300), "t2": (NOW - 90 * 86400, NOW), "count": (1, 3), "ls": (-2**40, 2**40),
+            "mx": (-2**31, 2**31 - 1), "uid": ("ids", 4000, 1)}
+    segs, dicts, hidden = random_table(conf, 3, 50000, 31, spec, last_rows=20000)
+    more, _, _ = random_table(conf, 1, 30000, 32, spec)       # replacement cells and appended rows
+    db = v.Database({"tables": [conf]}, device=0)
+    try:
+        t = db.get_table("live")
+        upload(t, segs, dicts, hidden)
+        q = {"type": "aggregate", "table": "live", "select": [{"column": "d0"}, {"column": "t2", "granularity": "day"}, {"column": "count"},
+                                                               {"column": "ls"}, {"column": "mx"}, {"column": "uid"}],
+             "filter": {"op": "lt", "column": "n1", "value": "200"}}
+
+        def check():
+            out = v.MemoryRowOutput()
+            stats = db.query(q, out, now=NOW)
+            want = viya_oracle.run_query(conf, segs, dicts, q, now=NOW)
+            assert sorted(out.rows) == sorted(want["rows"])
+            for k in ("scanned_segments", "scanned_recs", "aggregated_recs"):
+                assert getattr(stats, k) == want["stats"][k], k
+        check()
+        # 1. in-place update of rows [1000, 9000) of segment 1: metric cells change, dimensions stay (what an upsert does)
+        for name in ("count", "ls", "mx"):
+            segs[1][name] = segs[1][name].copy()
+            segs[1][name][1000:9000] = more[0][name][:8000]
+        ids = segs[1]["uid"][1].copy()
+        ids[1000:9000] = more[0]["uid"][1][:8000]
+        segs[1]["uid"] = (segs[1]["uid"][0], ids)
+        part = {k: (val[1000:9000] if not isinstance(val, tuple) else val[1][1000:9000]) for k, val in segs[1].items()}
+        t.update_segment(1, 1000, part)
+        check()
+        # 2. the last segment grows: 7000 rows appended behind its 20000 (one call), then 3 more rows and an update that
+        #    straddles old and new rows
+        last = segs[2]
+        grown = {}
+        for k, val in last.items():
+            if isinstance(val, tuple):
+                grown[k] = (np.arange(27001, dtype="<u8"), np.concatenate([val[1], more[0]["uid"][1][10000:17000]]))
+            else:
+                grown[k] = np.concatenate([val, more[0][k][10000:17000]])
+        segs[2] = grown
+        t.update_segment(2, 20000, {k: (val[20000:] if not isinstance(val, tuple) else val[1][20000:]) for k, val in grown.items()})
+        check()
+        with pytest.raises(v.VgpuError):   # a hole behind the last row is refused
+            t.update_segment(2, 27005, {k: (val[:3] if not isinstance(val, tuple) else val[1][:3]) for k, val in grown.items()})
+    finally:
+        db.close()

@@ -116,6 +116,7 @@ SYMBOLS = [
     ("vgpu_segment_put", C.c_int, [C.c_void_p, C.c_uint32, C.c_uint64, C.POINTER(C.c_void_p)]),
     ("vgpu_segment_put_async", C.c_int, [C.c_void_p, C.c_uint32, C.c_uint64, C.POINTER(C.c_void_p)]),
     ("vgpu_table_sync", C.c_int, [C.c_void_p]),
+    ("vgpu_segment_update", C.c_int, [C.c_void_p, C.c_uint32, C.c_uint64, C.c_uint64, C.POINTER(C.c_void_p)]),
     ("vgpu_host_pin", C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
     ("vgpu_host_unpin", C.c_int, [C.c_void_p, C.c_void_p]),
     ("vgpu_table_invalidate", C.c_int, [C.c_void_p, C.c_uint32]),

@@ -621,14 +621,17 @@ void compute_stats(vgpu_table *t, uint32_t seg_idx) {
 }
 
 // (re)build the row-major mirror of a segment from its columns; stream-ordered after the column copies
-void build_row_mirror(vgpu_table *t, uint32_t seg_idx) {
+void build_row_mirror(vgpu_table *t, uint32_t seg_idx, uint64_t row_begin = 0, uint64_t row_count = ~0ull) {
   vgpu_ctx *ctx = t->ctx;
   SegmentData &sd = t->segs[seg_idx];
   if (sd.rows == nullptr || sd.nrows == 0) return;
   if (t->cols.size() > 32) fail(VGPU_ERR_UNSUPPORTED, "row mirror supports at most 32 columns");
+  row_begin = std::min(row_begin, sd.nrows);
+  row_count = std::min(row_count, sd.nrows - row_begin);
+  if (row_count == 0) return;
   RowsParams R{};
-  R.rows = sd.rows;
-  R.nrows = sd.nrows;
+  R.rows = sd.rows + row_begin * t->row_stride;
+  R.nrows = row_count;
   R.stride = t->row_stride;
   R.ncols = (uint32_t)t->cols.size();
   for (size_t c = 0; c < t->cols.size(); ++c) {
@@ -638,14 +641,14 @@ void build_row_mirror(vgpu_table *t, uint32_t seg_idx) {
     if (ci.bitset) {  // the first word a count-distinct needs: the id, or the CSR offset of the cell
       rc.width = 4;
       rc.src = reinterpret_cast<const uint8_t *>(sd.bs_has_offsets[ci.bitset_idx] ? sd.bs_offsets[ci.bitset_idx]
-                                                                                    : sd.bs_values[ci.bitset_idx]);
+                                                                                    : sd.bs_values[ci.bitset_idx]) + row_begin * 4;
     } else {
       rc.width = ci.width;
-      rc.src = sd.slab + ci.off_per_row * sd.cap;
+      rc.src = sd.slab + ci.off_per_row * sd.cap + row_begin * ci.width;
     }
   }
   const uint32_t tile_rows = kRowsTileBytes / R.stride;
-  const uint64_t ntiles = (sd.nrows + tile_rows - 1) / tile_rows;
+  const uint64_t ntiles = (row_count + tile_rows - 1) / tile_rows;
   const int grid = (int)std::min<uint64_t>(ntiles, (uint64_t)ctx->sm_count * 8);
   build_rows_kernel<<<grid, 256, 0, ctx->stream>>>(R);
   CUDA_CK(cudaGetLastError());
@@ -1448,6 +1451,54 @@ int vgpu_host_unpin(vgpu_ctx *ctx, const void *ptr) {
 }
 
 
+
+int vgpu_segment_update(vgpu_table *t, uint32_t seg_idx, uint64_t row_begin, uint64_t nrows, const void *const *col_ptrs) {
+  return guard([&] {
+    if (!t || (!col_ptrs && nrows)) fail(VGPU_ERR_INVALID, "null argument");
+    vgpu_ctx *ctx = t->ctx;
+    std::lock_guard<std::mutex> put_lk(ctx->put_mu);
+    std::unique_lock<std::shared_mutex> lk(t->mu);
+    CUDA_CK(cudaSetDevice(ctx->device));
+    if (seg_idx >= t->segs.size() || !t->segs[seg_idx].valid) fail(VGPU_ERR_STATE, "no such segment: put it first");
+    SegmentData &sd = t->segs[seg_idx];
+    if (row_begin > sd.nrows) fail(VGPU_ERR_INVALID, "update would leave a hole behind the segment's rows");
+    if (row_begin + nrows > sd.cap || row_begin + nrows > t->segment_size)
+      fail(VGPU_ERR_STATE, "update beyond the segment's device capacity: put the whole segment");
+    if (nrows == 0) return;
+    cudaStream_t cs = ctx->copy_stream;
+    // queries that are still reading the segment finished before the exclusive lock was granted; the kernels of
+    // earlier puts on ctx->stream must finish before their input is overwritten
+    CUDA_CK(cudaEventRecord(ctx->ev_copy, ctx->stream));
+    CUDA_CK(cudaStreamWaitEvent(cs, ctx->ev_copy, 0));
+    for (size_t c = 0; c < t->cols.size(); ++c) {
+      const ColInfo &ci = t->cols[c];
+      if (!col_ptrs[c]) fail(VGPU_ERR_INVALID, "null column pointer");
+      if (ci.bitset) {
+        // one id per cell on both sides: anything else changes the CSR layout of the whole segment
+        const vgpu_bitset_csr *csr = static_cast<const vgpu_bitset_csr *>(col_ptrs[c]);
+        if (sd.bs_has_offsets[ci.bitset_idx] || ci.width == 8 || csr->offsets != nullptr || csr->nvalues != nrows)
+          fail(VGPU_ERR_UNSUPPORTED, "partial update of a bitset column whose cells do not hold exactly one 32-bit id: put the whole segment");
+        if ((row_begin + nrows) > sd.bs_vcap[ci.bitset_idx]) fail(VGPU_ERR_STATE, "update beyond the bitset capacity: put the whole segment");
+        CUDA_CK(cudaMemcpyAsync(sd.bs_values[ci.bitset_idx] + row_begin, csr->values, nrows * 4, cudaMemcpyHostToDevice, cs));
+        sd.bs_n[ci.bitset_idx] = std::max<uint64_t>(sd.bs_n[ci.bitset_idx], row_begin + nrows);
+        continue;
+      }
+      CUDA_CK(cudaMemcpyAsync(sd.slab + ci.off_per_row * sd.cap + row_begin * ci.width, col_ptrs[c], nrows * ci.width,
+                              cudaMemcpyHostToDevice, cs));
+    }
+    if (row_begin + nrows > sd.nrows) {
+      sd.nrows = row_begin + nrows;
+      t->descs_dirty = true;
+    }
+    sd.hi_rows = std::max(sd.hi_rows, sd.nrows);
+    CUDA_CK(cudaEventRecord(ctx->ev_copy, cs));
+    CUDA_CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_copy, 0));
+    compute_stats(t, seg_idx);                        // whole segment, on the device: no PCIe traffic
+    build_row_mirror(t, seg_idx, row_begin, nrows);   // the updated rows only
+    CUDA_CK(cudaEventRecord(t->ev_put, ctx->stream));
+    CUDA_CK(cudaEventSynchronize(ctx->ev_copy));
+  });
+}
 
 int vgpu_segment_generate(vgpu_table *t, uint32_t seg_idx, uint64_t nrows, const vgpu_gen_col *gens,
                           uint64_t seed, uint64_t row_offset) {

@@ -236,6 +236,12 @@ class Table:
                 self._async_keep = []
             self._async_keep.append(keep)
 
+    def update_segment(self, seg_idx, row_begin, columns, hidden_count=None):
+        """vgpu_segment_update: replace / append rows [row_begin, row_begin + n) of an uploaded segment; `columns` hold
+        the n rows of the range only."""
+        ptrs, nrows, keep = self.prepare_segment(columns, hidden_count)
+        N.check(N.load().vgpu_segment_update(self.handle, seg_idx, row_begin, nrows, ptrs))
+
     def prepare_segment(self, columns, hidden_count=None):
         """Copy one segment into HBM. `columns`: name -> numpy array (dict codes / numbers), or for a
         BITSET metric either a 1-D uint32 array (one id per row) or a pair (offsets uint64[n+1],

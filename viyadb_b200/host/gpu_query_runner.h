@@ -174,8 +174,17 @@ public:
     schema.segment_size = table.segment_size();
     schema.cols = cols.data();
     check(vgpu_table_create(ctx, &schema, &handle_), "vgpu_table_create");
+    for (auto &c : cols) widths_.push_back(c.kind == VGPU_METRIC_BITSET ? 0u : width_of(c.type));
+    has_bitset_ = false;
+    for (auto &c : cols) has_bitset_ = has_bitset_ || c.kind == VGPU_METRIC_BITSET;
+    std::lock_guard<std::mutex> lk(registry_mu());
+    registry()[&table_] = this;
   }
   ~GpuTableBinding() {
+    {
+      std::lock_guard<std::mutex> lk(registry_mu());
+      registry().erase(&table_);
+    }
     vgpu_table_free(handle_);
     for (const void *p : pinned_) vgpu_host_unpin(ctx_, p);
   }
@@ -188,6 +197,23 @@ public:
   }
   bool has_hidden_count() const { return hidden_; }
   size_t hidden_count_index() const { return ndims_ + nmetrics_; }  // last schema column (include/vgpu.h)
+
+  // Exact change notification (incremental sync): rows [row_begin, row_end) of a segment were updated
+  // in place. The upsert knows both numbers where it calls `m.Update(upsert_tuple.m, tuple_idx)`
+  // (src/codegen/db/upsert.cc:386-393); an integration that reports them there never needs
+  // IngestEpoch::Bump(): only the dirty ranges and the rows appended since the last upload cross PCIe.
+  void MarkDirty(size_t seg_idx, size_t row_begin, size_t row_end) {
+    std::lock_guard<std::mutex> lk(mu_);
+    if (row_end <= row_begin) return;
+    if (dirty_.size() <= seg_idx) dirty_.resize(seg_idx + 1);
+    dirty_[seg_idx].emplace_back(row_begin, row_end);
+  }
+  static void MarkDirty(const db::Table *table, size_t seg_idx, size_t row_begin, size_t row_end) {
+    std::lock_guard<std::mutex> lk(registry_mu());
+    auto it = registry().find(table);
+    if (it != registry().end()) it->second->MarkDirty(seg_idx, row_begin, row_end);
+  }
+  uint64_t partial_updates() const { return partial_updates_; }   // vgpu_segment_update calls issued so far (tests)
 
   // Force the next Sync() to re-upload a segment whose metric cells were updated in place.
   void Invalidate(size_t seg_idx) {
@@ -210,6 +236,7 @@ public:
     }
     auto segments = table_.store()->segments_copy();
     if (uploaded_.size() < segments.size()) uploaded_.resize(segments.size(), static_cast<size_t>(-1));
+    if (dirty_.size() < segments.size()) dirty_.resize(segments.size());
     std::vector<const void *> dims(ndims_), metrics(nmetrics_);
     std::vector<uint64_t> stats(2 * ndims_ + 2);
     // CSR images of bitset cells must outlive the asynchronous copies: kept until vgpu_table_sync below
@@ -220,7 +247,14 @@ public:
     bool any = false;
     for (size_t si = 0; si < segments.size(); ++si) {
       size_t size = segments[si]->size();
-      if (uploaded_[si] == size) continue;
+      if (uploaded_[si] == size && dirty_[si].empty()) continue;
+      // incremental: the rows reported dirty plus the rows appended since the last upload, nothing else
+      if (uploaded_[si] != static_cast<size_t>(-1) && !has_bitset_ && SyncRanges(segments[si], si, size)) {
+        uploaded_[si] = size;
+        dirty_[si].clear();
+        continue;
+      }
+      dirty_[si].clear();
       // the segment is one heap object holding every fixed-width column: page-lock it once, so that this and every
       // later upload is a straight DMA (a failure only means the driver stages the copies)
       if (pinned_.insert(segments[si]).second && vgpu_host_pin(ctx_, segments[si], access_.segment_bytes()) != VGPU_OK)
@@ -260,6 +294,56 @@ public:
   }
 
 private:
+  static uint32_t width_of(uint32_t type) {
+    switch (type) {
+    case VGPU_U8: case VGPU_I8: return 1;
+    case VGPU_U16: case VGPU_I16: return 2;
+    case VGPU_U32: case VGPU_I32: case VGPU_F32: return 4;
+    default: return 8;
+    }
+  }
+  static std::map<const db::Table *, GpuTableBinding *> &registry() {
+    static std::map<const db::Table *, GpuTableBinding *> r;
+    return r;
+  }
+  static std::mutex &registry_mu() {
+    static std::mutex m;
+    return m;
+  }
+  // upload the dirty ranges of one segment (merged) and what was appended; false: the library wants the whole segment
+  bool SyncRanges(db::SegmentBase *seg, size_t si, size_t size) {
+    std::vector<std::pair<size_t, size_t>> ranges = dirty_[si];
+    if (size > uploaded_[si]) ranges.emplace_back(uploaded_[si], size);
+    std::sort(ranges.begin(), ranges.end());
+    std::vector<std::pair<size_t, size_t>> merged;
+    for (auto &r : ranges) {
+      size_t b = r.first, e = std::min(r.second, size);
+      if (e <= b) continue;
+      if (!merged.empty() && b <= merged.back().second) merged.back().second = std::max(merged.back().second, e);
+      else merged.emplace_back(b, e);
+    }
+    std::vector<const void *> dims(ndims_), metrics(nmetrics_);
+    std::vector<uint64_t> stats(2 * ndims_ + 2);
+    const void *hidden = nullptr;
+    access_.columns()(seg, dims.data(), metrics.data(), &hidden, stats.data());
+    for (auto &r : merged) {
+      std::vector<const void *> ptrs;
+      size_t c = 0;
+      for (size_t d = 0; d < ndims_; ++d, ++c) ptrs.push_back(static_cast<const uint8_t *>(dims[d]) + r.first * widths_[c]);
+      for (size_t m = 0; m < nmetrics_; ++m, ++c) ptrs.push_back(static_cast<const uint8_t *>(metrics[m]) + r.first * widths_[c]);
+      if (hidden_) ptrs.push_back(static_cast<const uint8_t *>(hidden) + r.first * 8);
+      int rc = vgpu_segment_update(handle_, static_cast<uint32_t>(si), r.first, r.second - r.first, ptrs.data());
+      if (rc == VGPU_ERR_STATE || rc == VGPU_ERR_UNSUPPORTED) return false;
+      check(rc, "vgpu_segment_update");
+      ++partial_updates_;
+    }
+    return true;
+  }
+
+  std::vector<uint32_t> widths_;
+  bool has_bitset_ = false;
+  std::vector<std::vector<std::pair<size_t, size_t>>> dirty_;
+  uint64_t partial_updates_ = 0;
   vgpu_ctx *ctx_;
   db::Table &table_;
   SegmentAccess access_;

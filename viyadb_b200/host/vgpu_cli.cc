@@ -141,6 +141,8 @@ int main(int argc, char **argv) {
     // rows in place (src/codegen/db/upsert.cc:386-393), no segment size changes. The integration's one line in
     // input::Loader::AfterLoad — IngestEpoch::Bump() — tells the resident copy it is stale.
     if (job.count("reload_rows")) {
+      std::vector<size_t> sizes_before;
+      for (auto *sgm : table->store()->segments_copy()) sizes_before.push_back(sgm->size());
       struct L : input::SimpleLoader {
         using input::SimpleLoader::SimpleLoader;
         void Before() { BeforeLoad(); }
@@ -152,8 +154,18 @@ int main(int argc, char **argv) {
         l.Load(row);
       }
       l.After();
-      vgpu_host::IngestEpoch::Bump();
+      if (job.value("reload_mode", std::string("epoch")) == "mark") {
+        // exact notifications, as an upsert hook would give them (here: every row that existed before may have been
+        // updated in place); the appended rows are found by the binding itself
+        for (size_t si = 0; si < sizes_before.size(); ++si)
+          vgpu_host::GpuTableBinding::MarkDirty(table, si, 0, sizes_before[si]);
+      } else {
+        vgpu_host::IngestEpoch::Bump();
+      }
       run_queries("results_after_reload");
+      uint64_t partial = 0;
+      for (auto &b : bindings) partial += b.second->partial_updates();
+      out["partial_updates"] = partial;
     }
     bindings.clear();
     if (ctx) vgpu_shutdown(ctx);
