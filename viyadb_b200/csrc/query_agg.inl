@@ -1238,6 +1238,7 @@ int vgpu_query_agg(vgpu_table *t, const vgpu_plan *plan, vgpu_result **out) {
         }
       }
 
+      if (ctx->trace) CUDA_CK(cudaEventRecord(sc->ev_phase[0], stream));   // merge / exchange enqueued
       // ---- extraction plumbing ----
       // rows the output arrays can hold: an upper bound of the number of groups known before the scan has run
       const uint64_t rows_bound = G > 1 ? std::min<uint64_t>(acc_cells_x, std::max<uint64_t>(global_active_rows, 1))
@@ -1343,6 +1344,7 @@ int vgpu_query_agg(vgpu_table *t, const vgpu_plan *plan, vgpu_result **out) {
           cstream = sc->s1;
           if (!dedupe_after_sync) {
             run_dedupe();
+            if (ctx->trace) CUDA_CK(cudaEventRecord(sc->ev_phase[1], stream));
             CUDA_CK(cudaStreamWaitEvent(stream, sc->ev_b, 0));   // the position map
             run_extract_late(stream);
           }
@@ -1508,6 +1510,21 @@ int vgpu_query_agg(vgpu_table *t, const vgpu_plan *plan, vgpu_result **out) {
       hint_raise(t->groups_hint, ngroups);
       float total_ms = 0;
       CUDA_CK(cudaEventElapsedTime(&total_ms, sc->ev_begin, sc->ev_end));
+      if (ctx->trace) {   // device time of the phases on s0 (what a multi-GPU step spends outside the scan)
+        float a = 0, b = 0, c = 0, d = 0, e = 0;
+        cudaEventElapsedTime(&a, sc->ev_begin, sc->ev_scan0);
+        cudaEventElapsedTime(&b, sc->ev_scan0, sc->ev_scan1);
+        cudaEventElapsedTime(&c, sc->ev_scan1, sc->ev_phase[0]);
+        if (early && !dedupe_after_sync && have_rows) {
+          cudaEventElapsedTime(&d, sc->ev_phase[0], sc->ev_phase[1]);
+          cudaEventElapsedTime(&e, sc->ev_phase[1], sc->ev_end);
+        } else {
+          cudaEventElapsedTime(&e, sc->ev_phase[0], sc->ev_end);
+        }
+        cudaGetLastError();
+        fprintf(stderr, "[vgpu r%d] phases ms: setup %.3f scan %.3f merge/exchange %.3f dedupe(+allreduce) %.3f extract+copy %.3f total %.3f\n",
+                ctx->rank, a, b, c, d, e, total_ms);
+      }
       view.ngroups = out_rows;
       view.aggregated_recs = ngroups;
       view.gpu_ms = total_ms;

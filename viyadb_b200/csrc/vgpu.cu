@@ -258,6 +258,7 @@ struct QueryScope {
   cudaStream_t s0 = nullptr, s1 = nullptr;   // main stream; side stream (early group extraction + its copies)
   cudaEvent_t ev_begin = nullptr, ev_scan0 = nullptr, ev_scan1 = nullptr, ev_end = nullptr;
   cudaEvent_t ev_a = nullptr, ev_b = nullptr, ev_c = nullptr;  // untimed ordering events between s0 and s1
+  cudaEvent_t ev_phase[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // VGPU_TRACE: phase boundaries on s0
   unsigned long long *d_counters = nullptr;  // 16 x u64, layout in query_agg.inl (kC*)
   unsigned long long *h_counters = nullptr;  // pinned: [0,16) read-back, [16,32) initial image, [32,48) second read-back
   uint64_t *d_plan = nullptr;                // 64 x u64: plan-time agreement between ranks
@@ -432,6 +433,8 @@ void destroy_scope(QueryScope *sc) {
   if (sc->s1) cudaStreamDestroy(sc->s1);
   for (cudaEvent_t e : {sc->ev_begin, sc->ev_scan0, sc->ev_scan1, sc->ev_end, sc->ev_a, sc->ev_b, sc->ev_c})
     if (e) cudaEventDestroy(e);
+  for (cudaEvent_t e : sc->ev_phase)
+    if (e) cudaEventDestroy(e);
   if (sc->d_counters) cudaFree(sc->d_counters);
   if (sc->h_counters) cudaFreeHost(sc->h_counters);
   if (sc->d_plan) cudaFree(sc->d_plan);
@@ -462,6 +465,7 @@ struct ScopeLease {
       CUDA_CK(cudaEventCreateWithFlags(&n->ev_a, cudaEventDisableTiming));
       CUDA_CK(cudaEventCreateWithFlags(&n->ev_b, cudaEventDisableTiming));
       CUDA_CK(cudaEventCreateWithFlags(&n->ev_c, cudaEventDisableTiming));
+      for (cudaEvent_t &e : n->ev_phase) CUDA_CK(cudaEventCreate(&e));
       CUDA_CK(cudaMalloc(&n->d_counters, 16 * sizeof(unsigned long long)));
       CUDA_CK(cudaMallocHost(&n->h_counters, 48 * sizeof(unsigned long long)));
       CUDA_CK(cudaMalloc(&n->d_plan, 64 * sizeof(uint64_t)));
