@@ -537,6 +537,9 @@ void ensure_segment(vgpu_table *t, uint32_t seg_idx, uint64_t nrows, cudaStream_
   if (seg_idx >= t->segs.size()) t->segs.resize(seg_idx + 1);
   SegmentData &sd = t->segs[seg_idx];
   uint64_t cap = round_up(std::max<uint64_t>(nrows, 1), kTileRows);
+  // the newest segment is the one the live store still appends to (db/store.h:46-52): room for a whole segment, so
+  // that vgpu_segment_update can append behind its rows without a re-put
+  if (seg_idx + 1 == t->segs.size() && t->segment_size <= (1ull << 24)) cap = std::max(cap, round_up(t->segment_size, kTileRows));
   if (sd.slab == nullptr || sd.cap < cap) {
     free_segment(sd);
     if (t->row_bytes > 0) {
@@ -1350,6 +1353,7 @@ static int put_impl(vgpu_table *t, uint32_t seg_idx, uint64_t nrows, const void 
         }
         // values padded to a whole tile so that speculative reads stay in bounds
         uint64_t vcap = round_up(std::max<uint64_t>(nvalues, 1), kTileRows) * (idw / 4);   // in uint32 words
+        if (one_per_row) vcap = std::max<uint64_t>(vcap, sd.cap);   // appends (vgpu_segment_update) fit like in the slab
         if (sd.bs_vcap[ci.bitset_idx] < vcap) {
           if (sd.bs_values[ci.bitset_idx]) cudaFree(sd.bs_values[ci.bitset_idx]);
           sd.bs_values[ci.bitset_idx] = nullptr;
