@@ -949,7 +949,7 @@ int vgpu_query_agg(vgpu_table *t, const vgpu_plan *plan, vgpu_result **out) {
     if (P.ndistinct) {
       const uint64_t nregions = (uint64_t)region_grid * P.dpair_nsub;
       const uint64_t fill_hint = hint_load(t->pairs_region_hint);
-      if (fill_hint) region_cap64 = fill_hint + fill_hint / 8 + std::min<uint64_t>(fill_hint / 2, 4096) + 256;   // work units are handed out dynamically: a CTA's share varies from run to run (small tables most)
+      if (fill_hint) region_cap64 = fill_hint + fill_hint / 16 + std::min<uint64_t>(fill_hint / 4, 1024) + 256;   // work units are handed out dynamically: a CTA's share varies from run to run (small tables most)
       else region_cap64 = std::max<uint64_t>(1ull << 16, max_active_rows / 16) / nregions * 5 / 4 + 1024;
       if (ctx->test_pairs_cap) region_cap64 = std::max<uint64_t>(ctx->test_pairs_cap / nregions, 4);
     }
