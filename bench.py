@@ -583,9 +583,10 @@ def measure_e2e(torch, v, db, t, query, runner, plan, rows, nseg, world, dist, s
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         ms = tt.item()
     d2h = sum(a.nbytes for a in g["keys"]) + sum(a.nbytes for a in g["accs"])
-    scanned = runner.stats.scanned_recs   # == e_rows: the table holds exactly the uploaded segments
-    return {"value": scanned * world / (ms / 1e3), "unit": "rows/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-            "rows_uploaded_per_gpu_per_step": e_rows, "rows_scanned_per_gpu_per_step": scanned, "ms_per_step": ms, "steps": k,
+    scanned = runner.stats.scanned_recs   # all ranks (QueryStats are merged): the tables hold exactly the uploaded segments
+    assert scanned == e_rows * world, (scanned, e_rows, world)
+    return {"value": scanned / (ms / 1e3), "unit": "rows/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+            "rows_uploaded_per_gpu_per_step": e_rows, "rows_scanned_per_step_all_gpus": scanned, "ms_per_step": ms, "steps": k,
             "h2d_gbs_per_gpu": h2d / (ms / 1e3) / 1e9, "numa": numa,
             "note": "every step re-uploads all columns from pinned host memory (vgpu_segment_put_async, one DMA per column "
                     "and segment, no host wait in between), then runs the query and copies the groups back; PCIe-bound"}
