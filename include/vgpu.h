@@ -55,7 +55,7 @@
 extern "C" {
 #endif
 
-#define VGPU_ABI_VERSION 2
+#define VGPU_ABI_VERSION 3
 
 typedef enum vgpu_status {
   VGPU_OK = 0,
@@ -182,7 +182,31 @@ typedef struct vgpu_plan {
   const uint32_t *metric_cols; /* schema column indices of the selected metrics, query order */
   uint32_t need_hidden_count;  /* AVG selected without a COUNT metric selected (scan.cc:239-241) */
   uint32_t flags;              /* VGPU_PLAN_* */
+  /* ---- post-aggregation on the device (optional; replaces the HAVING test of post_agg.cc:76-83 and narrows what
+   * sort.cc:24-73 has to sort). Both only REMOVE groups from the result the host then post-aggregates as before:
+   *   HAVING   the same post-order node encoding as the row predicate, `col` = schema column of a SELECTED dimension or
+   *            metric, literals = the raw AnyNum images FilterArgsPacker emits for query->having(). A metric compares
+   *            its accumulator in the column's own type (AVG: the raw sum, Q6; BITSET: the cardinality, Q7), a
+   *            dimension its (rolled-up) key value. The caller must only ask for it when the reference applies HAVING to
+   *            every group: with a sort, or without skip / limit (without a sort the reference cuts the skip / limit
+   *            window out of the map iteration BEFORE it tests HAVING).
+   *   top-N    sort_col = schema column of the FIRST sort column, top_k = skip + limit: the result keeps every group
+   *            whose first sort key is among the top_k best (ties included), so the host's exact multi-column sort on
+   *            formatted strings (Q12) sees a superset of what it will output. Applied when the column's sort order can
+   *            be computed from raw values — integer-typed dimensions and metrics (util::StringNumCmp::SmallerInt:
+   *            length, then lexicographic, src/util/string.h:28-49), not AVG — otherwise ignored.
+   * vgpu_result_view.aggregated_recs stays the number of ALL groups (QueryStats); post_applied says what ran. */
+  uint32_t nhnodes;
+  uint32_t nhargs;
+  const vgpu_pred_node *hnodes;
+  const uint64_t *hargs;
+  uint32_t sort_col;           /* VGPU_NO_COLUMN: none */
+  uint32_t sort_descending;
+  uint64_t top_k;              /* 0: no top-N */
 } vgpu_plan;
+
+#define VGPU_NO_COLUMN 0xffffffffu
+#define VGPU_PLAN_POST 8u      /* the post-aggregation fields above are filled in (older callers leave the bit clear) */
 
 #define VGPU_PLAN_FORCE_HASH 1u  /* testing: never pick the dense group table */
 #define VGPU_PLAN_FORCE_DENSE 2u /* testing: fail instead of falling back to hashing */
@@ -217,6 +241,8 @@ typedef struct vgpu_result_view {
   uint64_t table_cells;         /* dense cells or hash capacity */
   uint32_t attempts;            /* scans run: > 1 after a hash-table or pair-region overflow (grow and scan again) */
   uint32_t distinct_paths;      /* count-distinct dedupe paths taken, VGPU_DEDUPE_* bits */
+  uint32_t post_applied;        /* bit 0: HAVING ran on the device, bit 1: top-N selection ran on the device */
+  uint32_t reserved;
 } vgpu_result_view;
 
 #define VGPU_DEDUPE_SMALL 1u    /* one global set */

@@ -369,3 +369,78 @@ def test_segment_update_ranges(built_lib):
             t.update_segment(2, 27005, {k: (val[:3] if not isinstance(val, tuple) else val[1][:3]) for k, val in grown.items()})
     finally:
         db.close()
+
+
+# ---- post-aggregation on the device: HAVING on raw accumulators, top-N on the first sort key ----
+POST_QUERIES = [
+    # (query, expect HAVING on device, expect top-N on device)
+    ({"dimensions": ["d1"], "metrics": ["count", "ls"], "having": {"op": "gt", "column": "count", "value": "3300"}}, True, False),
+    ({"dimensions": ["d1", "d0"], "metrics": ["count", "ls"], "having": {"op": "and", "filters": [
+        {"op": "gt", "column": "count", "value": "90"}, {"op": "lt", "column": "ls", "value": "0"},
+        {"op": "in", "column": "d0", "values": ["d0_3", "d0_5", "d0_8"]}]}}, True, False),
+    ({"dimensions": ["d1"], "metrics": ["count", "ls"], "sort": [{"column": "count"}, {"column": "d1", "ascending": True}], "limit": 7, "skip": 2}, False, True),
+    ({"dimensions": ["d1", "d0"], "metrics": ["ls", "is"], "sort": [{"column": "ls", "ascending": True}], "limit": 25}, False, True),     # signed: SmallerInt order
+    ({"dimensions": ["d1", "d0"], "metrics": ["ls", "is"], "sort": [{"column": "is"}], "limit": 40, "skip": 5}, False, True),              # signed, descending
+    ({"dimensions": ["i4"], "metrics": ["count"], "sort": [{"column": "i4", "ascending": True}], "limit": 30}, False, True),               # signed numeric dimension
+    ({"dimensions": ["d0", "n3"], "metrics": ["uid", "imax"], "having": {"op": "ge", "column": "uid", "value": "12"},
+      "sort": [{"column": "uid"}, {"column": "n3", "ascending": True}, {"column": "d0"}], "limit": 15}, True, True),                       # count-distinct in HAVING and sort
+    ({"dimensions": ["d0"], "metrics": ["savg", "count"], "having": {"op": "gt", "column": "savg", "value": "1000"},
+      "sort": [{"column": "savg"}], "limit": 5}, True, False),                                                                               # AVG: HAVING on the raw sum, no device top-N
+    ({"dimensions": ["d1"], "metrics": ["ds"], "sort": [{"column": "ds"}], "limit": 5}, False, False),                                       # float sort key: the host's
+    ({"dimensions": ["d0"], "metrics": ["count"], "sort": [{"column": "d0", "ascending": True}], "limit": 5}, False, False),                 # string sort key: the host's
+    ({"dimensions": ["d1"], "metrics": ["count"], "having": {"op": "gt", "column": "count", "value": "1650"}, "limit": 3}, False, False),    # window before HAVING: the host's
+    ({"dimensions": ["d2", "n3"], "metrics": ["count", "umax"], "having": {"op": "ge", "column": "umax", "value": "4294000000"},
+      "sort": [{"column": "umax"}, {"column": "d2"}, {"column": "n3"}], "limit": 100}, True, True),                                         # hashed table (1.6e5 groups)
+]
+
+
+@pytest.fixture(scope="module")
+def post_env(built_lib):
+    import viyadb_b200 as v
+    import test_gpu_parity as TP
+    segs, dicts, hidden = random_table(TP.EVENTS, 4, 50000, 1234, TP.SPEC, last_rows=12345)
+    db = v.Database({"tables": [TP.EVENTS]}, device=0)
+    upload(db.get_table("events"), segs, dicts, hidden)
+    yield v, db, segs, dicts, hidden, TP.EVENTS
+    db.close()
+
+
+@pytest.mark.parametrize("qi", range(len(POST_QUERIES)))
+def test_device_having_and_top_n(post_env, qi):
+    v, db, segs, dicts, hidden, conf = post_env
+    qd, want_having, want_topn = POST_QUERIES[qi]
+    q = dict(qd, type="aggregate", table="events")
+    want = viya_oracle.run_query(conf, segs, dicts, q, now=NOW, hidden_counts=hidden)
+    results = {}
+    for device_post in (True, False):
+        out = v.MemoryRowOutput()
+        stats = db.query(q, out, now=NOW, device_post=device_post)
+        results[device_post] = (out.rows, stats)
+        windowed = not q.get("sort") and (q.get("limit") or q.get("skip"))   # which groups fall in the window is unspecified (Q11)
+        for k in ("scanned_segments", "scanned_recs", "aggregated_recs") + (() if windowed else ("output_recs",)):
+            assert getattr(stats, k) == want["stats"][k], (device_post, k, getattr(stats, k), want["stats"][k])
+    rows, stats = results[True]
+    assert bool(stats.post_applied & 1) == want_having and bool(stats.post_applied & 2) == want_topn, stats.post_applied
+    assert results[False][1].post_applied == 0
+    if q.get("sort"):
+        # ties of the sort key are unordered in std::sort: compare the sort-key columns row by row, the rest as sets of
+        # the rows that are not tied at the cut
+        names = q["dimensions"] + q["metrics"]
+        cols = [names.index(sc["column"]) for sc in q["sort"]]
+        def same(a, b):   # double sums: the order of the additions differs (1e-12 relative, as everywhere)
+            if a == b:
+                return True
+            try:
+                x, y = float(a), float(b)
+            except ValueError:
+                return False
+            return abs(x - y) <= 1e-12 * max(abs(x), abs(y))
+        for got in (rows, results[False][0]):
+            assert len(got) == len(want["rows"])
+            for r, w in zip(got, want["rows"]):
+                assert all(same(r[c], w[c]) for c in cols), (r, w)
+    elif windowed:
+        assert len(rows) <= q["limit"] and len(results[False][0]) <= q["limit"]
+    else:
+        assert sorted(rows) == sorted(want["rows"])
+        assert sorted(results[False][0]) == sorted(want["rows"])

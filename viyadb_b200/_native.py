@@ -9,7 +9,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("VGPU_LIB_PATH") or os.path.join(_HERE, "libvgpu.so")   # override: A/B of kernel variants
 
-VGPU_ABI_VERSION = 2
+VGPU_ABI_VERSION = 3
 
 # vgpu_status
 OK, ERR_INVALID, ERR_UNSUPPORTED, ERR_CUDA, ERR_NOMEM, ERR_NCCL, ERR_STATE = 0, -1, -2, -3, -4, -5, -6
@@ -29,7 +29,8 @@ TU_YEAR, TU_MONTH, TU_WEEK, TU_DAY, TU_HOUR, TU_MINUTE, TU_SECOND, TU_NONE = ran
 NODE_RELOP, NODE_IN, NODE_AND, NODE_OR, NODE_EMPTY = range(5)
 # vgpu_relop (== query::RelOpFilter::Operator order)
 OP_EQ, OP_NE, OP_LT, OP_LE, OP_GT, OP_GE = range(6)
-PLAN_FORCE_HASH, PLAN_FORCE_DENSE, PLAN_RESULT_ON_ROOT = 1, 2, 4
+PLAN_FORCE_HASH, PLAN_FORCE_DENSE, PLAN_RESULT_ON_ROOT, PLAN_POST = 1, 2, 4, 8
+NO_COLUMN = 0xFFFFFFFF
 DEDUPE_SMALL, DEDUPE_FAST, DEDUPE_WIDE, DEDUPE_GENERAL, DEDUPE_REDONE, DEDUPE_PARTITIONED = 1, 2, 4, 8, 16, 32
 MAX_ROLLUP_RULES = 8
 
@@ -62,7 +63,10 @@ class Plan(C.Structure):
     _fields_ = [("nnodes", C.c_uint32), ("nargs", C.c_uint32), ("nodes", C.POINTER(PredNode)),
                 ("args", C.POINTER(C.c_uint64)), ("nkeys", C.c_uint32), ("nmetrics", C.c_uint32),
                 ("keys", C.POINTER(Key)), ("metric_cols", C.POINTER(C.c_uint32)),
-                ("need_hidden_count", C.c_uint32), ("flags", C.c_uint32)]
+                ("need_hidden_count", C.c_uint32), ("flags", C.c_uint32),
+                ("nhnodes", C.c_uint32), ("nhargs", C.c_uint32), ("hnodes", C.POINTER(PredNode)),
+                ("hargs", C.POINTER(C.c_uint64)), ("sort_col", C.c_uint32), ("sort_descending", C.c_uint32),
+                ("top_k", C.c_uint64)]
 
 
 class ResultView(C.Structure):
@@ -72,7 +76,8 @@ class ResultView(C.Structure):
                 ("scanned_segments", C.c_uint64), ("aggregated_recs", C.c_uint64),
                 ("passed_rows", C.c_uint64), ("gpu_ms", C.c_double), ("scan_ms", C.c_double),
                 ("launches", C.c_uint32), ("table_mode", C.c_uint32), ("table_cells", C.c_uint64),
-                ("attempts", C.c_uint32), ("distinct_paths", C.c_uint32)]
+                ("attempts", C.c_uint32), ("distinct_paths", C.c_uint32), ("post_applied", C.c_uint32),
+                ("reserved", C.c_uint32)]
 
 
 class RowsPlan(C.Structure):

@@ -858,8 +858,11 @@ struct ExtractMet {
   uint32_t stride;     // bytes between cells
   uint32_t acc_width;  // 4 or 8
   uint32_t out_width;  // 1,2,4,8 (truncation == the reference's own-type wrap-around, Q4)
+  uint32_t sext;       // signed integer type: sign-extend the truncated value (HAVING / sort key on the device)
+  uint32_t pad;
   void *out;
 };
+constexpr int kMaxPostProg = 24;
 struct ExtractParams {
   uint64_t ncells;  // dense cells, or hash capacity + 1 (last = sentinel-key cell)
   uint32_t hash_mode;
@@ -877,6 +880,17 @@ struct ExtractParams {
   uint64_t cap;                 // rows the output arrays hold: groups beyond it are counted, not written
   uint32_t *pos_out;            // optional [ncells], preset to 0xffffffff: output position of every present cell
                                 // (extract_late_kernel fills in the accumulators that were not final yet)
+  // ---- post-aggregation on the device (vgpu_plan: HAVING, top-N) ----
+  uint32_t nhprog;              // HAVING program: PInstr with cls == C_GEN, slot = source (key k, or nkeys + metric m)
+  PInstr hprog[kMaxPostProg];
+  uint32_t sort_src;            // source of the first sort column, 0xffffffff: none
+  uint32_t sort_kind;           // 0: unsigned (numeric order == SmallerInt order), 1: signed (SmallerInt string order)
+  uint32_t sort_desc;
+  uint64_t *cand_cell;          // candidates (present and passing HAVING): cell and order-preserving sort key
+  uint64_t *cand_ord;
+  unsigned long long *cand_n;   // number of candidates
+  unsigned long long *out_n;    // rows written by post_extract_kernel
+  const unsigned long long *threshold;  // post_extract_kernel: keep candidates with ord <= *threshold
 };
 
 __device__ __forceinline__ bool cell_present(const ExtractParams &E, uint64_t c, uint64_t &packed) {
@@ -899,6 +913,58 @@ __device__ __forceinline__ bool cell_present(const ExtractParams &E, uint64_t c,
   return packed != kEmptyKey;
 }
 
+// value of key k of the group in cell c, widened (two's complement for signed types, raw bits for floats)
+__device__ __forceinline__ uint64_t group_key_value(const ExtractParams &E, uint32_t k, uint64_t c, uint64_t packed) {
+  const ExtractKey &ek = E.keys[k];
+  if (E.hash_mode == 2) return E.wkeys[c * E.nkeys + k];
+  uint64_t q = packed / ek.div;
+  if (ek.mod) q %= ek.mod;
+  uint64_t v = ek.lo + q;
+  if (ek.dict) v = ek.dict[q];
+  if (ek.lut) {  // the q-th set bit
+    uint64_t x = ek.lut;
+    for (uint64_t i = 0; i < q; ++i) x &= x - 1;
+    v = (uint64_t)(__ffsll((long long)x) - 1);
+  }
+  return v;
+}
+__device__ __forceinline__ uint64_t group_acc_raw(const ExtractMet &em, uint64_t c) {
+  const uint8_t *ap = reinterpret_cast<const uint8_t *>(em.acc) + c * em.stride;
+  return em.acc_width == 4 ? (uint64_t)*reinterpret_cast<const uint32_t *>(ap) : *reinterpret_cast<const uint64_t *>(ap);
+}
+// accumulator m as the reference holds it: truncated to the column's own width (Q4), sign-extended for signed types
+__device__ __forceinline__ uint64_t group_acc_value(const ExtractMet &em, uint64_t c) {
+  uint64_t v = group_acc_raw(em, c);
+  if (em.out_width < 8) {
+    v &= (1ull << (8 * em.out_width)) - 1;
+    if (em.sext) { const uint64_t sb = 1ull << (8 * em.out_width - 1); v = (v ^ sb) - sb; }
+  }
+  return v;
+}
+// write group `c` to row `pos` of the result arrays
+__device__ __forceinline__ void extract_cell(const ExtractParams &E, uint64_t c, uint64_t packed, uint64_t pos) {
+  for (uint32_t k = 0; k < E.nkeys; ++k) {
+    const ExtractKey &ek = E.keys[k];
+    const uint64_t v = group_key_value(E, k, c, packed);
+    switch (ek.width) {
+      case 1: reinterpret_cast<uint8_t *>(ek.out)[pos] = (uint8_t)v; break;
+      case 2: reinterpret_cast<uint16_t *>(ek.out)[pos] = (uint16_t)v; break;
+      case 4: reinterpret_cast<uint32_t *>(ek.out)[pos] = (uint32_t)v; break;
+      default: reinterpret_cast<uint64_t *>(ek.out)[pos] = v; break;
+    }
+  }
+  for (uint32_t m = 0; m < E.nmets; ++m) {
+    const ExtractMet &em = E.mets[m];
+    const uint64_t v = group_acc_raw(em, c);
+    switch (em.out_width) {
+      case 1: reinterpret_cast<uint8_t *>(em.out)[pos] = (uint8_t)v; break;
+      case 2: reinterpret_cast<uint16_t *>(em.out)[pos] = (uint16_t)v; break;
+      case 4: reinterpret_cast<uint32_t *>(em.out)[pos] = (uint32_t)v; break;
+      default: reinterpret_cast<uint64_t *>(em.out)[pos] = v; break;
+    }
+  }
+}
+
 __global__ void __launch_bounds__(256)
 extract_groups_kernel(const __grid_constant__ ExtractParams E) {
   const uint32_t lane = threadIdx.x & 31;
@@ -916,41 +982,161 @@ extract_groups_kernel(const __grid_constant__ ExtractParams E) {
     uint64_t pos = base + __popc(ballot & ((1u << lane) - 1));
     if (pos >= E.cap) continue;
     if (E.pos_out) E.pos_out[c] = (uint32_t)pos;
-    for (uint32_t k = 0; k < E.nkeys; ++k) {
-      const ExtractKey &ek = E.keys[k];
-      uint64_t v;
-      if (E.hash_mode == 2) {
-        v = E.wkeys[c * E.nkeys + k];
-      } else {
-        uint64_t q = packed / ek.div;
-        if (ek.mod) q %= ek.mod;
-        v = ek.lo + q;
-        if (ek.dict) v = ek.dict[q];
-        if (ek.lut) {  // the q-th set bit
-          uint64_t x = ek.lut;
-          for (uint64_t i = 0; i < q; ++i) x &= x - 1;
-          v = (uint64_t)(__ffsll((long long)x) - 1);
-        }
-      }
-      switch (ek.width) {
-        case 1: reinterpret_cast<uint8_t *>(ek.out)[pos] = (uint8_t)v; break;
-        case 2: reinterpret_cast<uint16_t *>(ek.out)[pos] = (uint16_t)v; break;
-        case 4: reinterpret_cast<uint32_t *>(ek.out)[pos] = (uint32_t)v; break;
-        default: reinterpret_cast<uint64_t *>(ek.out)[pos] = v; break;
-      }
+    extract_cell(E, c, packed, pos);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// post-aggregation on the device: HAVING on raw accumulators, top-N selection on the first sort key
+// ---------------------------------------------------------------------------------------------
+// value of source `src` (key k, or nkeys + metric m) of the group in cell c
+__device__ __forceinline__ uint64_t group_value(const ExtractParams &E, uint32_t src, uint64_t c, uint64_t packed) {
+  return src < E.nkeys ? group_key_value(E, src, c, packed) : group_acc_value(E.mets[src - E.nkeys], c);
+}
+__device__ __forceinline__ bool post_compare(uint32_t gcls, uint32_t gop, uint64_t v, uint64_t a) {
+  switch (gcls) {
+    case G_I64: {
+      const long long x = (long long)v, y = (long long)a;
+      switch (gop) { case 0: return x == y; case 1: return x != y; case 2: return x < y; case 3: return x <= y; case 4: return x > y; default: return x >= y; }
     }
-    for (uint32_t m = 0; m < E.nmets; ++m) {
-      const ExtractMet &em = E.mets[m];
-      const uint8_t *ap = reinterpret_cast<const uint8_t *>(em.acc) + c * em.stride;
-      uint64_t v = em.acc_width == 4 ? (uint64_t)*reinterpret_cast<const uint32_t *>(ap)
-                                     : *reinterpret_cast<const uint64_t *>(ap);
-      switch (em.out_width) {
-        case 1: reinterpret_cast<uint8_t *>(em.out)[pos] = (uint8_t)v; break;
-        case 2: reinterpret_cast<uint16_t *>(em.out)[pos] = (uint16_t)v; break;
-        case 4: reinterpret_cast<uint32_t *>(em.out)[pos] = (uint32_t)v; break;
-        default: reinterpret_cast<uint64_t *>(em.out)[pos] = v; break;
-      }
+    case G_F32: {
+      const float x = __uint_as_float((uint32_t)v), y = __uint_as_float((uint32_t)a);
+      switch (gop) { case 0: return x == y; case 1: return x != y; case 2: return x < y; case 3: return x <= y; case 4: return x > y; default: return x >= y; }
     }
+    case G_F64: {
+      const double x = __longlong_as_double((long long)v), y = __longlong_as_double((long long)a);
+      switch (gop) { case 0: return x == y; case 1: return x != y; case 2: return x < y; case 3: return x <= y; case 4: return x > y; default: return x >= y; }
+    }
+    default:
+      switch (gop) { case 0: return v == a; case 1: return v != a; case 2: return v < a; case 3: return v <= a; case 4: return v > a; default: return v >= a; }
+  }
+}
+// FilterComparison over (agg key, accumulators), post_agg.cc:76-83: the same bitwise &,| tree as the row predicate
+__device__ __forceinline__ bool group_passes(const ExtractParams &E, uint64_t c, uint64_t packed) {
+  uint32_t stk = 0;  // bit i = stack entry i (depth <= kStackDepth)
+  int sp = 0;
+  for (uint32_t pc = 0; pc < E.nhprog; ++pc) {
+    const PInstr &in = E.hprog[pc];
+    if (in.kind <= P_OR_LEAF) {
+      bool m = in.cls == C_TRUE ? true : in.cls == C_FALSE ? false
+               : post_compare(in.gcls, in.gop, group_value(E, in.slot, c, packed), in.arg);
+      if (in.neg) m = !m;
+      if (in.kind == P_PUSH) { stk = (stk & ~(1u << sp)) | ((m ? 1u : 0u) << sp); ++sp; }
+      else if (in.kind == P_AND_LEAF) { if (!m) stk &= ~(1u << (sp - 1)); }
+      else { if (m) stk |= 1u << (sp - 1); }
+    } else {
+      const bool b = (stk >> (sp - 1)) & 1u, a = (stk >> (sp - 2)) & 1u;
+      const bool r = in.kind == P_AND ? (a && b) : (a || b);
+      --sp;
+      stk = (stk & ~(1u << (sp - 1))) | ((r ? 1u : 0u) << (sp - 1));
+    }
+  }
+  return sp == 0 ? true : (stk & 1u) != 0;
+}
+// Order-preserving image of an integer under util::StringNumCmp::SmallerInt (length, then lexicographic,
+// src/util/string.h:28-49): non-negative numbers order numerically; "-" sorts before every digit, so inside one string
+// length the negatives come first, by increasing magnitude. rank = number of representable values that sort before x.
+__device__ __forceinline__ uint64_t smaller_int_rank(long long x) {
+  const unsigned long long p10[20] = {1ull, 10ull, 100ull, 1000ull, 10000ull, 100000ull, 1000000ull, 10000000ull, 100000000ull,
+                                      1000000000ull, 10000000000ull, 100000000000ull, 1000000000000ull, 10000000000000ull,
+                                      100000000000000ull, 1000000000000000ull, 10000000000000000ull, 100000000000000000ull,
+                                      1000000000000000000ull, 10000000000000000000ull};
+  const unsigned long long kPos = 1ull << 63;                 // representable non-negative values
+  auto nonneg_upto = [&](int digits) { return digits <= 0 ? 0ull : (digits >= 19 ? kPos : p10[digits]); };      // with <= digits digits
+  auto neg_upto = [&](int digits) { return digits <= 0 ? 0ull : (digits >= 19 ? kPos : p10[digits] - 1ull); };  // magnitude <= digits digits
+  if (x >= 0) {
+    const unsigned long long u = (unsigned long long)x;
+    int d = 1;
+    while (d < 19 && u >= p10[d]) ++d;                        // decimal digits = string length
+    // before x: everything shorter (non-negatives with < d digits, negatives with magnitude < d - 1 digits ... of length < d),
+    // the negatives of length d (magnitude of d - 1 digits), the non-negatives of d digits below x
+    return nonneg_upto(d - 1) + neg_upto(d - 1) + (u - (d == 1 ? 0ull : p10[d - 1]));
+  }
+  const unsigned long long m = 0ull - (unsigned long long)x;  // magnitude (2^63 for INT64_MIN)
+  int e = 1;
+  while (e < 19 && m >= p10[e]) ++e;                          // digits of the magnitude; string length e + 1
+  return nonneg_upto(e) + neg_upto(e - 1) + (m - p10[e - 1]);
+}
+__device__ __forceinline__ uint64_t sort_ordinal(const ExtractParams &E, uint64_t c, uint64_t packed) {
+  const uint64_t v = group_value(E, E.sort_src, c, packed);
+  const uint64_t o = E.sort_kind == 1 ? smaller_int_rank((long long)v) : v;
+  return E.sort_desc ? ~o : o;
+}
+
+// pass 1: count the groups, keep the candidates (present and passing HAVING) with their sort key
+__global__ void __launch_bounds__(256) post_select_kernel(const __grid_constant__ ExtractParams E) {
+  const uint32_t lane = threadIdx.x & 31;
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  const uint64_t limit = (E.ncells + 31) & ~31ull;
+  for (uint64_t c = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; c < limit; c += stride) {
+    uint64_t packed = 0;
+    const bool pres = (c < E.ncells) && cell_present(E, c, packed);
+    const uint32_t ballot = __ballot_sync(0xffffffffu, pres);
+    if (ballot == 0) continue;
+    if (lane == 0) atomicAdd(E.counter, (unsigned long long)__popc(ballot));
+    const bool cand = pres && group_passes(E, c, packed);
+    const uint32_t cb = __ballot_sync(0xffffffffu, cand);
+    if (cb == 0) continue;
+    unsigned long long base = 0;
+    if (lane == 0) base = atomicAdd(E.cand_n, (unsigned long long)__popc(cb));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (!cand) continue;
+    const uint64_t pos = base + __popc(cb & ((1u << lane) - 1));
+    E.cand_cell[pos] = c;
+    E.cand_ord[pos] = E.sort_src != 0xffffffffu ? sort_ordinal(E, c, packed) : 0ull;
+  }
+}
+
+// radix select of the k-th smallest sort key among the candidates, most significant byte first: one histogram pass over
+// the keys that match the prefix found so far, one single-thread step that picks the byte. state: [0] prefix,
+// [1] remaining k (1-based), [2] resolved bits mask; after 8 rounds state[0] is the threshold.
+__global__ void __launch_bounds__(256) radix_hist_kernel(const uint64_t *ord, const unsigned long long *n_ptr, const unsigned long long *state,
+                                                         uint32_t shift, unsigned int *hist) {
+  __shared__ unsigned int s_h[256];
+  s_h[threadIdx.x] = 0;
+  __syncthreads();
+  if (state[3]) return;   // nothing to select: every candidate is kept
+  const uint64_t n = *n_ptr, prefix = state[0], mask = state[2];
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+    const uint64_t o = ord[i];
+    if ((o & mask) == prefix) atomicAdd(&s_h[(o >> shift) & 0xffu], 1u);
+  }
+  __syncthreads();
+  if (s_h[threadIdx.x]) atomicAdd(&hist[threadIdx.x], s_h[threadIdx.x]);
+}
+__global__ void radix_pick_kernel(unsigned long long *state, int shift, unsigned int *hist, const unsigned long long *n_ptr,
+                                  unsigned long long top_k) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  if (shift < 0) {                         // set-up call
+    state[0] = 0; state[2] = 0;
+    state[1] = top_k;
+    state[3] = (top_k == 0 || *n_ptr <= top_k) ? 1 : 0;   // fewer candidates than wanted: keep them all
+    if (state[3]) state[0] = ~0ull;
+    return;
+  }
+  if (state[3]) { for (int b = 0; b < 256; ++b) hist[b] = 0; return; }
+  unsigned long long k = state[1];
+  int b = 0;
+  for (; b < 255; ++b) {
+    if (hist[b] >= k) break;
+    k -= hist[b];
+  }
+  state[1] = k;
+  state[0] |= (unsigned long long)b << shift;
+  state[2] |= 0xffull << shift;
+  for (int i = 0; i < 256; ++i) hist[i] = 0;
+}
+
+// pass 2: the candidates whose sort key is <= the threshold become the result
+__global__ void __launch_bounds__(256) post_extract_kernel(const __grid_constant__ ExtractParams E) {
+  const unsigned long long n = *E.cand_n, thr = *E.threshold;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+    if (E.cand_ord[i] > thr) continue;
+    const uint64_t c = E.cand_cell[i];
+    uint64_t packed = 0;
+    cell_present(E, c, packed);
+    const unsigned long long pos = atomicAdd(E.out_n, 1ull);
+    if (pos < E.cap) extract_cell(E, c, packed, pos);
   }
 }
 

@@ -920,6 +920,30 @@ int vgpu_query_agg(vgpu_table *t, const vgpu_plan *plan, vgpu_result **out) {
       }
     }
 
+    // ---- post-aggregation on the device (vgpu_plan: HAVING, top-N) ----
+    Planner hpl(t, plan, true);
+    bool post_having = false, post_topn = false;
+    uint32_t sort_src = 0xffffffffu, sort_kind = 0;
+    if ((plan->flags & VGPU_PLAN_POST) && !(ctx->tune & (1u << 23)) && !q.active.empty()) {
+      if (plan->nhnodes > 0) {
+        hpl.build_predicate();   // throws for columns that are not selected, like the reference (query.cc:127-133)
+        post_having = hpl.P.nprog <= (uint32_t)kMaxPostProg;
+      }
+      if (plan->sort_col != VGPU_NO_COLUMN && plan->top_k > 0) {
+        const ColInfo &ci = t->cols[plan->sort_col];
+        // the column's sort order must follow from its raw value: decimal integers under SmallerInt (string.h:28-49).
+        // Strings, times (sorted as strings), booleans ("true" / "false"), floats and AVG (a quotient) stay the host's.
+        const bool is_dim = plan->sort_col < t->ndims;
+        const bool ok = !type_float(ci.type) && (is_dim ? ci.kind == VGPU_DIM_NUMERIC : (ci.bitset || (ci.agg != VGPU_AGG_AVG && ci.kind != VGPU_METRIC_HIDDEN_COUNT)));
+        if (ok) {
+          sort_src = hpl.source_of(plan->sort_col);
+          sort_kind = type_signed(ci.type) && !ci.bitset ? 1u : 0u;
+          post_topn = true;
+        }
+      }
+    }
+    const bool post = post_having || post_topn;
+
     // ---- work list ----
     uint64_t max_rows = 0;
     for (uint32_t s : q.active) max_rows = std::max(max_rows, t->segs[s].nrows);
@@ -943,8 +967,9 @@ int vgpu_query_agg(vgpu_table *t, const vgpu_plan *plan, vgpu_result **out) {
     view.nmetrics = plan->nmetrics;
 
     CUDA_CK(cudaEventRecord(sc->ev_begin, stream));
-    uint32_t launches = 0, paths = 0;
+    uint32_t launches = 0, paths = 0, paths_post = 0;
     float scan_ms_total = 0;
+    bool force_general = false;   // device post-aggregation: the fast dedupe overflowed, scan again and dedupe the general way
 
     uint64_t hash_cap = 0;
     if (q.hash_mode) {
@@ -1197,6 +1222,7 @@ int vgpu_query_agg(vgpu_table *t, const vgpu_plan *plan, vgpu_result **out) {
         if (ctx->test_pairs_cap) pin[d].expect = 0;
         if (ctx->test_expect) pin[d].expect = ctx->test_expect;
         dmode[d] = choose_dedupe_mode(ctx, t, pin[d], dnb[d]);
+        if (force_general && dmode[d] == kDedupeFast) dmode[d] = kDedupeGeneral;
       }
 
       // ---- several GPUs: one exchange ----
@@ -1308,6 +1334,7 @@ int vgpu_query_agg(vgpu_table *t, const vgpu_plan *plan, vgpu_result **out) {
         em.stride = P.mets[m].stride;
         em.acc_width = q.accs[m].acc_width;
         em.out_width = q.accs[m].out_width;
+        em.sext = q.accs[m].op != A_DISTINCT && type_signed(t->cols[q.acc_cols[m]].type) ? 1u : 0u;
         em.out = d_accs[m];
         return em;
       };
@@ -1320,7 +1347,8 @@ int vgpu_query_agg(vgpu_table *t, const vgpu_plan *plan, vgpu_result **out) {
         return false;
       }();
       const bool distinct_done = G > 1 && q.hash_mode;  // deduplicated inside the hash merge
-      const bool early = P.ndistinct > 0 && !distinct_done && acc_cells_x <= (1ull << 24) && !(ctx->tune & (1u << 20));
+      // (device post-aggregation reads every accumulator of a group at once: one extraction, after the dedupe)
+      const bool early = P.ndistinct > 0 && !distinct_done && !post && acc_cells_x <= (1ull << 24) && !(ctx->tune & (1u << 20));
       uint32_t *d_pos = nullptr;
       auto run_extract = [&](cudaStream_t s, bool with_late) {
         E.nmets = 0;
@@ -1328,9 +1356,46 @@ int vgpu_query_agg(vgpu_table *t, const vgpu_plan *plan, vgpu_result **out) {
           if (with_late || q.accs[m].op != A_DISTINCT) E.mets[E.nmets++] = extract_met(m);
         E.pos_out = with_late ? nullptr : d_pos;
         E.count_only = 0;
-        extract_groups_kernel<<<grid_for(acc_cells_x, 256, ctx->sm_count), 256, 0, s>>>(E);
+        if (!post) {
+          extract_groups_kernel<<<grid_for(acc_cells_x, 256, ctx->sm_count), 256, 0, s>>>(E);
+          CUDA_CK(cudaGetLastError());
+          ++launches;
+          return;
+        }
+        // HAVING on the raw accumulators and / or top-N on the first sort key: candidates, radix select, extraction
+        E.nhprog = post_having ? hpl.P.nprog : 0;
+        for (uint32_t i = 0; i < E.nhprog; ++i) E.hprog[i] = hpl.P.prog[i];
+        E.sort_src = post_topn ? sort_src : 0xffffffffu;
+        E.sort_kind = sort_kind;
+        E.sort_desc = plan->sort_descending ? 1u : 0u;
+        E.cand_cell = scratch.alloc<uint64_t>(rows_bound);
+        E.cand_ord = scratch.alloc<uint64_t>(rows_bound);
+        E.cand_n = sc->d_counters + kCCand;
+        E.out_n = sc->d_counters + kCOut;
+        unsigned long long *state = scratch.alloc<unsigned long long>(4);   // [0] threshold
+        unsigned int *hist = scratch.alloc<unsigned int>(256);
+        E.threshold = state;
+        post_select_kernel<<<grid_for(acc_cells_x, 256, ctx->sm_count), 256, 0, s>>>(E);
         CUDA_CK(cudaGetLastError());
         ++launches;
+        if (post_topn) {
+          CUDA_CK(cudaMemsetAsync(hist, 0, 256 * sizeof(unsigned int), s));
+          radix_pick_kernel<<<1, 32, 0, s>>>(state, -1, hist, E.cand_n, plan->top_k);   // set-up
+          CUDA_CK(cudaGetLastError());
+          for (int shift = 56; shift >= 0; shift -= 8) {
+            radix_hist_kernel<<<grid_for(rows_bound, 256, ctx->sm_count, 4), 256, 0, s>>>(E.cand_ord, E.cand_n, state, (uint32_t)shift, hist);
+            CUDA_CK(cudaGetLastError());
+            radix_pick_kernel<<<1, 32, 0, s>>>(state, shift, hist, E.cand_n, plan->top_k);
+            CUDA_CK(cudaGetLastError());
+            launches += 2;
+          }
+        } else {
+          CUDA_CK(cudaMemsetAsync(state, 0xff, 8, s));
+        }
+        post_extract_kernel<<<grid_for(rows_bound, 256, ctx->sm_count, 4), 256, 0, s>>>(E);
+        CUDA_CK(cudaGetLastError());
+        ++launches;
+        paths_post = (post_having ? 1u : 0u) | (post_topn ? 2u : 0u);
       };
       auto run_extract_late = [&](cudaStream_t s) {
         ExtractLateParams L{};
@@ -1495,8 +1560,11 @@ int vgpu_query_agg(vgpu_table *t, const vgpu_plan *plan, vgpu_result **out) {
         }
       }
       if (ngroups > rows_bound) fail(VGPU_ERR_CUDA, "group extraction overflow");
+      // device post-aggregation: the result holds the groups that survived HAVING / the top-N cut, not all of them
+      const uint64_t nout = (post && have_rows) ? (uint64_t)hc[kCOut] : ngroups;
+      if (nout > rows_bound) fail(VGPU_ERR_CUDA, "group extraction overflow");
       // several GPUs, VGPU_PLAN_RESULT_ON_ROOT: the merged groups go to rank 0's host only
-      const uint64_t out_rows = (G > 1 && (plan->flags & VGPU_PLAN_RESULT_ON_ROOT) && ctx->rank != 0) ? 0 : ngroups;
+      const uint64_t out_rows = (G > 1 && (plan->flags & VGPU_PLAN_RESULT_ON_ROOT) && ctx->rank != 0) ? 0 : nout;
       host_copy(out_rows);
       // the flags of the fast dedupe path travel behind everything on s0
       unsigned long long *hc2 = sc->h_counters + 32;
@@ -1504,6 +1572,15 @@ int vgpu_query_agg(vgpu_table *t, const vgpu_plan *plan, vgpu_result **out) {
       CUDA_CK(cudaEventRecord(sc->ev_end, stream));
       CUDA_CK(cudaStreamSynchronize(sc->s1));
       CUDA_CK(cudaStreamSynchronize(stream));   // host sync #2
+      if (post && P.ndistinct && !distinct_done && (hc2[kCBucketOver] != 0 || hc2[kCSetOver] != 0)) {
+        // HAVING / top-N already looked at incomplete distinct counts: scan again, dedupe the general way (rare)
+        force_general = true;
+        if (res->block.first) { res->pool->release(res->block); res->block = {nullptr, 0}; }
+        res->key_ptrs.clear();
+        res->acc_ptrs.clear();
+        view.hidden_count = nullptr;
+        continue;
+      }
       if (P.ndistinct && !distinct_done && (hc2[kCBucketOver] != 0 || hc2[kCSetOver] != 0)) {
         // rare: hash buckets did not fit (very uneven data or stale hints). Redo the distinct counts the general way.
         redo_distinct_general();
@@ -1556,6 +1633,7 @@ int vgpu_query_agg(vgpu_table *t, const vgpu_plan *plan, vgpu_result **out) {
       view.table_cells = q.ncells;
       view.attempts = (uint32_t)attempt + 1;
       view.distinct_paths = paths;
+      view.post_applied = have_rows ? paths_post : 0;
       break;
     }
 

@@ -41,6 +41,8 @@ enum Counter : int {
   kCError = 11,        // a rank failed before the exchange: everybody aborts
   kCGroups = 12,       // groups extracted (local)
   kCUnit = 13,         // next work unit of the scan (low 32 bits)
+  kCOut = 14,          // device post-aggregation: rows written to the result
+  kCCand = 15,         // device post-aggregation: groups that passed HAVING
   kCSumFirst = 0, kCMaxFirst = 5, kCLocalFirst = 12
 };
 

@@ -295,7 +295,7 @@ struct vgpu_ctx {
   // tightening of key domains from the predicate, bit 18 no CTA-private shared-memory copy of small dense group tables,
   // bit 19 count-distinct: never the shared-memory-set fast path, bit 20 no early group extraction on the side
   // stream, bit 21 no bucket dictionary for rolled-up time keys, bit 22 always store presence flags (never read them
-  // off a COUNT accumulator)
+  // off a COUNT accumulator), bit 23 no post-aggregation on the device (HAVING / top-N stay the host's)
   uint32_t tune = 2;
   int ctas_per_sm = VGPU_MIN_CTAS;  // resident scan CTAs per SM (compile time: with kScanThreads it fixes the register cap)
   uint32_t unit_chunks = 0;  // VGPU_UNIT_CHUNKS: 512-row chunks per dynamically scheduled work unit (0: adaptive)
@@ -725,12 +725,29 @@ struct TreeNode {
 struct Planner {
   const vgpu_table *t;
   const vgpu_plan *plan;
+  // the predicate this planner lowers: the row filter, or (having = true) the HAVING filter over selected columns
+  const vgpu_pred_node *nodes_;
+  const uint64_t *args_;
+  uint32_t nnodes_, nargs_;
+  bool having = false;
   ScanParams P{};
   std::vector<TreeNode> tree;
   int root = -1;
   int depth = 0, max_depth = 0;
 
-  Planner(const vgpu_table *table, const vgpu_plan *p) : t(table), plan(p) {}
+  Planner(const vgpu_table *table, const vgpu_plan *p)
+      : t(table), plan(p), nodes_(p->nodes), args_(p->args), nnodes_(p->nnodes), nargs_(p->nargs) {}
+  Planner(const vgpu_table *table, const vgpu_plan *p, bool having_filter)
+      : t(table), plan(p), nodes_(p->hnodes), args_(p->hargs), nnodes_(p->nhnodes), nargs_(p->nhargs), having(having_filter) {}
+
+  // HAVING: a leaf reads a selected key (source k) or a selected metric (source nkeys + m) of the group
+  uint32_t source_of(uint32_t col) const {
+    for (uint32_t k = 0; k < plan->nkeys; ++k)
+      if (plan->keys[k].col == col) return k;
+    for (uint32_t m = 0; m < plan->nmetrics; ++m)
+      if (plan->metric_cols[m] == col) return plan->nkeys + m;
+    fail(VGPU_ERR_INVALID, "HAVING on a column that is not selected");
+  }
 
   uint32_t slot_of(uint32_t col) {
     if (col >= t->cols.size()) fail(VGPU_ERR_INVALID, "column index out of range");
@@ -757,7 +774,7 @@ struct Planner {
   uint32_t slot_cols[kMaxSlots];
 
   void build_tree() {
-    if (plan->nnodes == 0) {  // no filter at all == EmptyFilter
+    if (nnodes_ == 0) {  // no filter at all == EmptyFilter
       TreeNode e{};
       e.kind = VGPU_NODE_EMPTY;
       tree.push_back(e);
@@ -765,19 +782,19 @@ struct Planner {
       return;
     }
     std::vector<int> stack;
-    for (uint32_t i = 0; i < plan->nnodes; ++i) {
-      const vgpu_pred_node &pn = plan->nodes[i];
+    for (uint32_t i = 0; i < nnodes_; ++i) {
+      const vgpu_pred_node &pn = nodes_[i];
       TreeNode tn{};
       tn.kind = pn.kind; tn.op = pn.op; tn.col = pn.col; tn.arg = pn.arg; tn.n = pn.n;
       switch (pn.kind) {
         case VGPU_NODE_RELOP:
           if (pn.op > VGPU_OP_GE) fail(VGPU_ERR_INVALID, "bad relational operator");
-          if (pn.arg >= plan->nargs) fail(VGPU_ERR_INVALID, "predicate argument out of range");
+          if (pn.arg >= nargs_) fail(VGPU_ERR_INVALID, "predicate argument out of range");
           if (pn.col >= t->cols.size()) fail(VGPU_ERR_INVALID, "predicate column out of range");
           break;
         case VGPU_NODE_IN:
           if (pn.n == 0) fail(VGPU_ERR_INVALID, "IN filter without values");
-          if ((uint64_t)pn.arg + pn.n > plan->nargs) fail(VGPU_ERR_INVALID, "predicate argument out of range");
+          if ((uint64_t)pn.arg + pn.n > nargs_) fail(VGPU_ERR_INVALID, "predicate argument out of range");
           if (pn.col >= t->cols.size()) fail(VGPU_ERR_INVALID, "predicate column out of range");
           break;
         case VGPU_NODE_AND:
@@ -837,6 +854,20 @@ struct Planner {
     const ColInfo &ci = t->cols[col];
     PInstr in{};
     in.kind = leaf_kind(mode);
+    if (having) {
+      // per group, on the device: generic compare of the widened value (post_compare, kernels.cuh)
+      if (mode == 0) push_depth();
+      in.slot = (uint8_t)source_of(col);
+      in.cls = C_GEN;
+      in.gop = (uint8_t)op;
+      if (ci.bitset) { in.gcls = G_CARD; in.arg = widen_arg(raw_arg, ci.lit_type); }
+      else {
+        in.gcls = ci.type == VGPU_F32 ? G_F32 : ci.type == VGPU_F64 ? G_F64 : type_signed(ci.type) ? G_I64 : G_U64;
+        in.arg = widen_arg(raw_arg, ci.type);
+      }
+      emit(in);
+      return;
+    }
     in.slot = (uint8_t)slot_of(col);
     if (mode == 0) push_depth();
     if (ci.bitset) {  // compares cardinality() (filter.cc:215-217)
@@ -874,6 +905,7 @@ struct Planner {
   }
 
   bool is_small_int_col(uint32_t col) const {
+    if (having) return false;  // no vector leaf classes, lookup masks or range fusion per group
     const ColInfo &ci = t->cols[col];
     return !ci.bitset && ci.width <= 4 && !type_float(ci.type);
   }
@@ -890,7 +922,7 @@ struct Planner {
         emit(in);
       } break;
       case VGPU_NODE_RELOP:
-        emit_compare(n.col, n.op, plan->args[n.arg], mode);
+        emit_compare(n.col, n.op, args_[n.arg], mode);
         break;
       case VGPU_NODE_IN: {
         // IN = OR chain of ==, NOT IN = AND chain of != (filter.cc:222-241)
@@ -901,7 +933,7 @@ struct Planner {
           uint64_t lut = 0;
           bool ok = true;
           for (uint32_t i = 0; i < n.n && ok; ++i) {
-            uint64_t a = widen_arg(plan->args[n.arg + i], ci.type);
+            uint64_t a = widen_arg(args_[n.arg + i], ci.type);
             // a literal that is missing from the dictionary decodes to UINTn_MAX: it matches no stored
             // code (dictionary.cc:46-75 hands out codes from 0 upwards), so it adds nothing to the mask
             if (ci.kind == VGPU_DIM_STRING && a == type_max_value(ci.type)) continue;
@@ -922,10 +954,10 @@ struct Planner {
         const int chain = eq ? 2 : 1;
         const uint32_t op = eq ? VGPU_OP_EQ : VGPU_OP_NE;
         if (mode == chain) {
-          for (uint32_t i = 0; i < n.n; ++i) emit_compare(n.col, op, plan->args[n.arg + i], chain);
+          for (uint32_t i = 0; i < n.n; ++i) emit_compare(n.col, op, args_[n.arg + i], chain);
         } else {
-          emit_compare(n.col, op, plan->args[n.arg], 0);
-          for (uint32_t i = 1; i < n.n; ++i) emit_compare(n.col, op, plan->args[n.arg + i], chain);
+          emit_compare(n.col, op, args_[n.arg], 0);
+          for (uint32_t i = 1; i < n.n; ++i) emit_compare(n.col, op, args_[n.arg + i], chain);
           if (mode != 0) combine(mode);
         }
       } break;
@@ -953,8 +985,8 @@ struct Planner {
               if (!((a_lo && b_hi) || (a_hi && b_lo))) continue;
               const TreeNode &lo = a_lo ? a : b, &hi = a_lo ? b : a;
               const ColInfo &ci = t->cols[a.col];
-              uint64_t lo_o = ord32(widen_arg(plan->args[lo.arg], ci.type), ci.type);
-              uint64_t hi_o = ord32(widen_arg(plan->args[hi.arg], ci.type), ci.type);
+              uint64_t lo_o = ord32(widen_arg(args_[lo.arg], ci.type), ci.type);
+              uint64_t hi_o = ord32(widen_arg(args_[hi.arg], ci.type), ci.type);
               if (lo.op == VGPU_OP_GT) lo_o += 1;
               if (hi.op == VGPU_OP_LE) hi_o += 1;  // exclusive upper bound, may be ordmax+1
               PInstr in{};
@@ -1021,7 +1053,7 @@ struct Planner {
     const TreeNode &n = tree[idx];
     switch (n.kind) {
       case VGPU_NODE_EMPTY: return true;
-      case VGPU_NODE_RELOP: return skip_leaf(sd, n.col, n.op, plan->args[n.arg]);
+      case VGPU_NODE_RELOP: return skip_leaf(sd, n.col, n.op, args_[n.arg]);
       case VGPU_NODE_IN: {
         const ColInfo &ci = t->cols[n.col];
         if (!(ci.kind == VGPU_DIM_NUMERIC || ci.kind == VGPU_DIM_TIME || ci.kind == VGPU_DIM_MICROTIME))
@@ -1029,7 +1061,7 @@ struct Planner {
         // NOT IN is pruned with the same "some value inside [min,max]" test (filter.cc:303-327
         // ignores equal()) — reproduced as is
         bool r = false;
-        for (uint32_t i = 0; i < n.n; ++i) r = r || skip_leaf(sd, n.col, VGPU_OP_EQ, plan->args[n.arg + i]);
+        for (uint32_t i = 0; i < n.n; ++i) r = r || skip_leaf(sd, n.col, VGPU_OP_EQ, args_[n.arg + i]);
         return r;
       }
       case VGPU_NODE_AND: {
@@ -1712,6 +1744,11 @@ void validate_plan(const vgpu_table *t, const vgpu_plan *plan) {
   if (plan->nargs && !plan->args) fail(VGPU_ERR_INVALID, "null predicate args");
   if (plan->nkeys && !plan->keys) fail(VGPU_ERR_INVALID, "null keys");
   if (plan->nmetrics && !plan->metric_cols) fail(VGPU_ERR_INVALID, "null metric list");
+  if (plan->flags & VGPU_PLAN_POST) {
+    if (plan->nhnodes && !plan->hnodes) fail(VGPU_ERR_INVALID, "null HAVING nodes");
+    if (plan->nhargs && !plan->hargs) fail(VGPU_ERR_INVALID, "null HAVING args");
+    if (plan->sort_col != VGPU_NO_COLUMN && plan->sort_col >= t->cols.size()) fail(VGPU_ERR_INVALID, "sort column out of range");
+  }
   if (plan->nkeys > kMaxKeys) fail(VGPU_ERR_UNSUPPORTED, "too many group-by keys");
   if (plan->nmetrics + (plan->need_hidden_count ? 1 : 0) > kMaxMetrics)
     fail(VGPU_ERR_UNSUPPORTED, "too many metrics");

@@ -396,6 +396,7 @@ class QueryStats:
         self.table_cells = 0
         self.attempts = 0
         self.distinct_paths = 0
+        self.post_applied = 0
 
 
 # ------------------------------------------------------------------------------------------------
@@ -463,12 +464,13 @@ class GpuQueryRunner:
     filter arguments exactly like the reference, lowers the query to a vgpu_plan, calls
     vgpu_query_agg and runs the host post-aggregation into the caller's RowOutput."""
 
-    def __init__(self, database, output, flags=0, now=None):
+    def __init__(self, database, output, flags=0, now=None, device_post=True):
         self.database = database
         self.output = output
         self.stats = QueryStats()
         self.flags = flags
         self.now = now
+        self.device_post = device_post   # HAVING / top-N on the device (vgpu.h VGPU_PLAN_POST); False: the host does both
         self.last_result = None
 
     # "now" for rollup boundaries: VIYA_TEST_ROLLUP_TS pins it (codegen/db/rollup.cc:47-49)
@@ -523,6 +525,25 @@ class GpuQueryRunner:
         plan.need_hidden_count = 1 if (has_avg and not has_count) else 0   # scan.cc:239-241
         plan.flags = self.flags
         plan._keep = (nodes, args, keys, mcols)
+        # ---- post-aggregation on the device (vgpu.h: HAVING, top-N); both only remove groups, post_aggregate below
+        # stays what it was. HAVING only where the reference tests every group: with a sort, or without skip / limit
+        # (without a sort it cuts the skip / limit window out of the map iteration first, post_agg.cc:26-83).
+        plan.sort_col, plan.sort_descending, plan.top_k = N.NO_COLUMN, 0, 0
+        if self.device_post:
+            plan.flags |= N.PLAN_POST
+            if query.having is not None and (query.sort_cols or (query.skip == 0 and query.limit == 0)):
+                hp = FilterArgsPacker(t).visit(query.having)
+                hnodes = (N.PredNode * max(1, len(hp.nodes)))()
+                for i, (kind, op, col, arg, n) in enumerate(hp.nodes):
+                    hnodes[i] = N.PredNode(kind, op, col, arg, n, 0)
+                hargs = (C.c_uint64 * max(1, len(hp.args)))(*hp.args)
+                plan.nhnodes, plan.nhargs, plan.hnodes, plan.hargs = len(hp.nodes), len(hp.args), hnodes, hargs
+                plan._keep += (hnodes, hargs)
+            if query.sort_cols and query.limit > 0:
+                sc = query.sort_cols[0]
+                plan.sort_col = t.schema_index(sc.col)
+                plan.sort_descending = 0 if sc.ascending else 1
+                plan.top_k = query.skip + query.limit
         return plan
 
     def run_plan(self, query, plan):
@@ -561,6 +582,7 @@ class GpuQueryRunner:
         s.gpu_ms, s.kernel_scan_ms, s.launches = view.gpu_ms, view.scan_ms, view.launches
         s.table_mode, s.table_cells = view.table_mode, view.table_cells
         s.attempts, s.distinct_paths = view.attempts, view.distinct_paths
+        s.post_applied = view.post_applied
         return {"ngroups": n, "keys": keys, "accs": accs, "hidden_count": hidden, "_owner": owner}
 
     def _predicate(self, query):
@@ -714,8 +736,11 @@ class GpuQueryRunner:
         out, stats = self.output, self.stats
         out.start()
         n = groups["ngroups"]
-        skip = min(n, query.skip)
-        limit = min(query.limit, n - skip)
+        # skip / limit are clamped by agg_map.size() (post_agg.cc:40-47) = all groups, also when HAVING / top-N already ran
+        # on the device and `groups` only holds the survivors
+        n_all = max(n, stats.aggregated_recs)
+        skip = min(n_all, query.skip)
+        limit = min(query.limit, n_all - skip)
         sorting = bool(query.sort_cols)
         lo, hi = 0, n
         if not sorting:
