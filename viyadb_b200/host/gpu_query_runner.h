@@ -743,6 +743,32 @@ public:
     plan.metric_cols = metric_cols.data();
     plan.need_hidden_count = (has_avg && !has_count) ? 1 : 0;
 
+    // 3b. post-aggregation on the device (include/vgpu.h: HAVING, top-N). Both only remove groups; PostAggregate below
+    // stays what it was. HAVING only where the reference tests every group: with a sort, or without skip / limit
+    // (without a sort it cuts the skip / limit window out of the map iteration first, post_agg.cc:26-83).
+    plan.sort_col = VGPU_NO_COLUMN;
+    std::vector<uint64_t> raw_hargs;
+    PredicateProgramBuilder hpred(table, binding);
+    if (getenv("VGPU_HOST_POST") == nullptr) {
+      plan.flags |= VGPU_PLAN_POST;
+      auto sort_columns = query->sort_cols();
+      if (query->having() != nullptr && (!sort_columns.empty() || (query->skip() == 0 && query->limit() == 0))) {
+        std::vector<db::AnyNum> hargs = having_args.args();
+        raw_hargs.resize(hargs.size());
+        for (size_t i = 0; i < hargs.size(); ++i) std::memcpy(&raw_hargs[i], &hargs[i], 8);
+        query->having()->Accept(hpred);
+        plan.nhnodes = static_cast<uint32_t>(hpred.nodes().size());
+        plan.hnodes = hpred.nodes().data();
+        plan.nhargs = static_cast<uint32_t>(raw_hargs.size());
+        plan.hargs = raw_hargs.data();
+      }
+      if (!sort_columns.empty() && query->limit() > 0) {
+        plan.sort_col = static_cast<uint32_t>(binding.schema_index(sort_columns[0].col()));
+        plan.sort_descending = sort_columns[0].ascending() ? 0 : 1;
+        plan.top_k = query->skip() + query->limit();
+      }
+    }
+
     // 4. the hot path
     vgpu_result *res = nullptr;
     check(vgpu_query_agg(binding.handle(), &plan, &res), "vgpu_query_agg");
@@ -815,8 +841,11 @@ private:
     auto &metric_cols = query->metric_cols();
     output_.Start();
     size_t n = view.ngroups;
-    size_t skip = std::min(n, query->skip());
-    size_t limit = std::min(query->limit(), n - skip);
+    // skip / limit are clamped by agg_map.size() (post_agg.cc:40-47) = ALL groups, also when HAVING / top-N already ran on
+    // the device and the view only holds the survivors
+    size_t n_all = std::max<size_t>(n, view.aggregated_recs);
+    size_t skip = std::min(n_all, query->skip());
+    size_t limit = std::min(query->limit(), n_all - skip);
     auto sort_columns = query->sort_cols();
     size_t lo = 0, hi = n;
     if (sort_columns.empty()) {
