@@ -120,3 +120,30 @@ def test_query_validation_errors(db):
         QueryFactory.create({"type": "show", "table": "events"}, db)
     with pytest.raises(KeyError):      # config.str("dimension") throws in the reference too (query.cc:141)
         QueryFactory.create({"type": "search", "table": "events"}, db)
+
+
+def test_device_post_aggregation_is_only_asked_for_where_the_reference_tests_every_group(db):
+    """vgpu_plan post fields (include/vgpu.h): HAVING travels to the device with a sort, or without skip / limit — without
+    a sort the reference cuts the skip / limit window out of the map iteration BEFORE it tests HAVING (post_agg.cc:26-83);
+    the first sort column travels with skip + limit; device_post=False leaves everything to the host."""
+    t = db.get_table("events")
+    t.dimension("country").dict.encode("US")
+
+    def plan_of(conf, **kw):
+        q = QueryFactory.create(dict(conf, type="aggregate", table="events"), db)
+        return GpuQueryRunner(db, MemoryRowOutput(), **kw).build_plan(q)
+
+    base = {"dimensions": ["country", "n"], "metrics": ["count", "avg"]}
+    having = {"op": "and", "filters": [{"op": "gt", "column": "count", "value": "5"}, {"op": "eq", "column": "country", "value": "US"}]}
+    p = plan_of(dict(base, having=having))
+    assert p.flags & N.PLAN_POST and p.nhnodes == 3 and p.nhargs == 2 and p.sort_col == N.NO_COLUMN and p.top_k == 0
+    # the HAVING leaves name schema columns of SELECTED columns, literals in FilterArgsPacker order
+    assert [p.hnodes[i].col for i in range(2)] == [t.schema_index(t.metric("count")), t.schema_index(t.dimension("country"))]
+    p = plan_of(dict(base, having=having, limit=3))                       # window before HAVING: the host's
+    assert p.nhnodes == 0 and p.top_k == 0
+    p = plan_of(dict(base, having=having, limit=3, skip=2, sort=[{"column": "count"}, {"column": "n", "ascending": True}]))
+    assert p.nhnodes == 3 and p.sort_col == t.schema_index(t.metric("count")) and p.sort_descending == 1 and p.top_k == 5
+    p = plan_of(dict(base, sort=[{"column": "n", "ascending": True}]))    # a sort without limit: nothing to cut
+    assert p.sort_col == N.NO_COLUMN and p.top_k == 0
+    p = plan_of(dict(base, having=having, sort=[{"column": "count"}], limit=3), device_post=False)
+    assert not (p.flags & N.PLAN_POST) and p.nhnodes == 0 and p.top_k == 0
