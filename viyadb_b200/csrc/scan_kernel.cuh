@@ -302,7 +302,7 @@ __device__ __noinline__ void append_csr_cell(const ScanParams &P, uint32_t *curs
 #ifndef VGPU_MIN_CTAS
 #define VGPU_MIN_CTAS 3
 #endif
-// kMinCtas CTAs per SM: caps the registers (3 -> 80, 4 -> 64); the host picks (VGPU_CTAS, default VGPU_MIN_CTAS)
+// kMinCtas CTAs per SM (VGPU_MIN_CTAS, compile time): with kScanThreads it caps the registers (256 x 3 -> 80)
 // kSmemTable: the instantiation that aggregates into a CTA-private shared-memory copy of a small dense group
 // table (ScanParams::smem_cells != 0); the other one carries none of that code.
 // kPlainKeys: no group key needs a time rollup, a bucket-dictionary lookup or the -0.0 fix (the common case: dictionary

@@ -278,7 +278,6 @@ struct vgpu_ctx {
   // the caller's stream (vgpu_set_stream): queries are ordered after what it holds when they start, and it waits
   // for them when they end, so that the caller's own events bracket a query
   cudaStream_t user_stream = nullptr;
-  cudaEvent_t ev_user = nullptr;
   // idle query scopes
   std::mutex scope_mu;
   std::vector<QueryScope *> idle_scopes;
@@ -472,12 +471,9 @@ struct ScopeLease {
       CUDA_CK(cudaMallocHost(&n->h_plan, 64 * sizeof(uint64_t)));
       sc = n.release();
     }
-    if (user) {
-      cudaEvent_t ev = nullptr;   // a private event: ctx->ev_user would race between concurrent queries
-      CUDA_CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
-      cudaEventRecord(ev, user);
-      cudaStreamWaitEvent(sc->s0, ev, 0);
-      cudaEventDestroy(ev);
+    if (user) {   // the scope's own event: concurrent queries never share one
+      cudaEventRecord(sc->ev_c, user);
+      cudaStreamWaitEvent(sc->s0, sc->ev_c, 0);
     }
   }
   ~ScopeLease() {
@@ -1182,7 +1178,6 @@ int vgpu_init(int device, vgpu_ctx **out) {
     CUDA_CK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
     CUDA_CK(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
     CUDA_CK(cudaEventCreateWithFlags(&ctx->ev_copy, cudaEventDisableTiming));
-    CUDA_CK(cudaEventCreateWithFlags(&ctx->ev_user, cudaEventDisableTiming));
     // keep freed scratch in the pool: repeated queries never go back to the driver
     cudaMemPool_t pool;
     CUDA_CK(cudaDeviceGetDefaultMemPool(&pool, device));
@@ -1243,7 +1238,6 @@ void vgpu_shutdown(vgpu_ctx *ctx) {
   for (QueryScope *sc : ctx->idle_scopes) destroy_scope(sc);
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   if (ctx->ev_copy) cudaEventDestroy(ctx->ev_copy);
-  if (ctx->ev_user) cudaEventDestroy(ctx->ev_user);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
