@@ -43,6 +43,10 @@ constexpr int kWarps = kThreads / 32;     // select / search kernels
 #endif
 constexpr int kScanThreads = VGPU_SCAN_THREADS;
 constexpr int kScanWarps = kScanThreads / 32;
+#ifndef VGPU_PF_DIST
+#define VGPU_PF_DIST 1
+#endif
+constexpr uint32_t kPrefetchDist = VGPU_PF_DIST;  // how many chunks ahead of its loads a warp prefetches into L2
 constexpr uint32_t kSmemTableBytes = 40 * 1024;  // CTA-private group table (3 CTAs/SM: 3 x (17 + 40) KB fit 227 KB)
 constexpr int kListCap = kChunkRows + 32;       // a chunk's worth of rows plus one incomplete batch
 static_assert(kVec * 32 == kSubChunk, "a lane owns kVec consecutive rows of every sub-chunk");
@@ -512,12 +516,12 @@ scan_filter_groupby_kernel(const __grid_constant__ ScanParams P) {
     // paying a DRAM round trip per column. The chunk after the last one of a unit opens the next unit.
     if (!(P.tune & 32u) && lane < P.nfilter_slots) {
       const uint8_t *a = nullptr;
-      if (ci + 1 < c_end) {
-        a = seg.slab + P.pf_off[lane] * seg.cap + (uint64_t)(chunk_row + kChunkRows) * P.pf_width[lane];
-      } else if (next_unit < nunits) {
+      if (ci + kPrefetchDist < c_end) {
+        a = seg.slab + P.pf_off[lane] * seg.cap + (uint64_t)(chunk_row + kPrefetchDist * kChunkRows) * P.pf_width[lane];
+      } else if (next_unit < nunits && ci + kPrefetchDist - c_end < P.unit_chunks) {
         const uint32_t nsi = next_unit / ups, npart = next_unit - nsi * ups;
         const SegDesc &nsd = P.segs[P.active[nsi]];
-        const uint32_t nrow = npart * P.unit_chunks * kChunkRows;
+        const uint32_t nrow = (npart * P.unit_chunks + (ci + kPrefetchDist - c_end)) * kChunkRows;
         if (nrow < (uint32_t)nsd.nrows) a = nsd.slab + P.pf_off[lane] * nsd.cap + (uint64_t)nrow * P.pf_width[lane];
       }
       if (a != nullptr)
