@@ -518,10 +518,11 @@ scan_filter_groupby_kernel(const __grid_constant__ ScanParams P) {
       const uint8_t *a = nullptr;
       if (ci + kPrefetchDist < c_end) {
         a = seg.slab + P.pf_off[lane] * seg.cap + (uint64_t)(chunk_row + kPrefetchDist * kChunkRows) * P.pf_width[lane];
-      } else if (next_unit < nunits && ci + kPrefetchDist - c_end < P.unit_chunks) {
+      } else if (next_unit < nunits && (kPrefetchDist == 1 || ci + kPrefetchDist - c_end < P.unit_chunks)) {
         const uint32_t nsi = next_unit / ups, npart = next_unit - nsi * ups;
         const SegDesc &nsd = P.segs[P.active[nsi]];
-        const uint32_t nrow = (npart * P.unit_chunks + (ci + kPrefetchDist - c_end)) * kChunkRows;
+        const uint32_t ahead = kPrefetchDist == 1 ? 0u : ci + kPrefetchDist - c_end;  // chunk of the next unit
+        const uint32_t nrow = (npart * P.unit_chunks + ahead) * kChunkRows;
         if (nrow < (uint32_t)nsd.nrows) a = nsd.slab + P.pf_off[lane] * nsd.cap + (uint64_t)nrow * P.pf_width[lane];
       }
       if (a != nullptr)
