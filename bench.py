@@ -447,6 +447,9 @@ def run_workload(args, wname, steps, torch, v, dist, rank, world, local, full):
                          "traffic": traffic, "traffic_unit": "bytes/launch (dram__bytes_read.sum + dram__bytes_write.sum)",
                          "traffic_source": traffic_src, "kernel": "scan_filter_groupby_kernel", "kernel_ms": scan_avg,
                          "algorithmic_bytes_per_row": b_alg, "algorithmic_bytes_per_launch": alg_bytes,
+                         "referenced_bytes_per_row": w["filter_bytes"] + w["payload_bytes"],   # B_full of SURVEY 8d
+                         "table_bytes_per_row": w["full_bytes"],
+                         "frac_of_datasheet_8TBs": achieved / 8000.0,
                          "peak_source": peak_src},
             "gpu_launches": launches, "gpu_ms_per_step": gpu_avg,
             "clocks": clocks, "e2e": e2e, "generate_s": t_gen,
