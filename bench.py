@@ -494,7 +494,8 @@ def main_ours(args):
                     also[wname]["post_agg"] = r["post_agg"]
                 also[wname]["config"] = r["config"]
                 also[wname]["roofline"] = {k: r["roofline"][k] for k in ("frac", "frac_query_device", "frac_step", "kernel_ms", "achieved",
-                                                                           "algorithmic_bytes_per_row")}
+                                                                           "algorithmic_bytes_per_row", "algorithmic_bytes_per_launch",
+                                                                           "traffic", "traffic_source")}
             if not args.no_check:
                 c = parity_check(v, dist, rank, world, local, wname, min(args.check_rows, 500_000))
                 if r is not None:
