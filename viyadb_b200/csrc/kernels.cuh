@@ -8,12 +8,14 @@
 //   count-distinct   src/util/bitset.h:26-67 (set union, cardinality)
 //
 // This header holds the building blocks (streaming / gather loads, UTC calendar arithmetic, accumulator
-// updates, hash cells) and every kernel but the fused scan itself (scan_kernel.cuh): count-distinct partition /
+// updates, hash cells; the pure arithmetic — calendar, rollup, hash mixers — is in device_arith.h, which also compiles
+// for the host) and every kernel but the fused scan itself (scan_kernel.cuh): count-distinct partition /
 // dedupe, multi-GPU exchange, group extraction, row-mirror build, column statistics, the synthetic generator.
 #ifndef VGPU_KERNELS_CUH_
 #define VGPU_KERNELS_CUH_
 
 #include "scan_params.h"
+#include "device_arith.h"
 #include <cuda_runtime.h>
 
 namespace vgpu {
@@ -126,102 +128,6 @@ __device__ __forceinline__ uint32_t gather_u32(const uint32_t *p) {
   return v;
 }
 
-// ---------------------------------------------------------------------------------------------
-// UTC calendar arithmetic (proleptic Gregorian, no leap seconds) == glibc gmtime_r / timegm for
-// non-negative time_t, which is all util::Time32/Time64 ever see (unsigned inputs).
-// ---------------------------------------------------------------------------------------------
-// T = uint32_t for util::Time32 (seconds fit 32 bits: every division is by a constant, i.e. a multiply-high)
-// and uint64_t for the seconds part of util::Time64.
-template <typename T>
-__device__ __forceinline__ T trunc_days_to(T days, bool to_year) {
-  // civil_from_days / days_from_civil (H. Hinnant's public-domain algorithms), days since 1970-01-01
-  T z = days + 719468;
-  T era = z / 146097;
-  T doe = z - era * 146097;
-  T yoe = (doe - doe / 1460 + doe / 36524 - doe / 146096) / 365;
-  T doy = doe - (365 * yoe + yoe / 4 - yoe / 100);  // March-based day of year
-  T mp = (5 * doy + 2) / 153;
-  T d = doy - (153 * mp + 2) / 5 + 1;
-  if (!to_year) return days - (d - 1);
-  // first of January of the civil year: March-based months 10,11 (Jan, Feb) belong to year yoe+1
-  T y = yoe + era * 400 + (mp >= 10 ? 1 : 0);
-  // days_from_civil(y, 1, 1)
-  T yy = y - 1;
-  T era2 = yy / 400;
-  T yoe2 = yy - era2 * 400;
-  T doy2 = (153 * 10 + 2) / 5;  // January 1st, March-based
-  T doe2 = yoe2 * 365 + yoe2 / 4 - yoe2 / 100 + doy2;
-  return era2 * 146097 + doe2 - 719468;
-}
-
-template <typename T>
-__device__ __forceinline__ T trunc_seconds(T t, uint32_t unit) {
-  switch (unit) {
-    case 0: return trunc_days_to(t / 86400, true) * 86400;   // YEAR
-    case 1: return trunc_days_to(t / 86400, false) * 86400;  // MONTH
-    case 3: return t - t % 86400;                            // DAY
-    case 4: return t - t % 3600;                             // HOUR
-    case 5: return t - t % 60;                               // MINUTE
-    default: return t;                                       // SECOND / NONE
-  }
-}
-
-__device__ __noinline__ uint64_t rollup_value(uint64_t v, const KeySpec &k) {
-  uint32_t unit = 7;  // VGPU_TU_NONE
-  for (uint32_t r = 0; r < k.nrules; ++r) {
-    if (v < k.rule_boundary[r]) {  // first matching rule wins (rollup.cc:77-95)
-      unit = k.rule_unit[r];
-      break;
-    }
-  }
-  // the query granularity truncates the same std::tm again (scan.cc:212-216): nested units, so the
-  // result is the coarser of the two
-  unit = min(unit, (uint32_t)k.query_unit);
-  if (k.micro) {
-    uint64_t secs = v / 1000000ull;
-    uint64_t micros = v - secs * 1000000ull;
-    if (unit != 7) micros = 0;  // Time64::trunc zeroes micros_ for every unit (time.h:129-132)
-    return trunc_seconds<uint64_t>(secs, unit) * 1000000ull + micros;
-  }
-  return (uint64_t)trunc_seconds<uint32_t>((uint32_t)v, unit);
-}
-
-// rank of a rolled-up time value among all attainable ones (TimeDict, scan_params.h): no calendar arithmetic
-__device__ __noinline__ uint64_t tdict_rank(const TimeDict &T, uint64_t v) {
-  const uint64_t x = T.micro ? v / 1000000ull : v;
-  // branch-free binary search for the last piece whose start is <= x (<= 48 pieces: 6 probes of the constant bank;
-  // the linear scan it replaces was 27 % of the C4 kernel's instructions, profiles/r2_final_scan_ncu_c4.txt)
-  uint32_t p = 0;
-  if (T.narrow) {
-    const uint32_t x32 = (uint32_t)x;
-#pragma unroll
-    for (uint32_t s = 32; s > 0; s >>= 1) {
-      const uint32_t q = p + s;
-      if (q < T.npieces && x32 >= T.start32[q]) p = q;
-    }
-  } else {
-#pragma unroll
-    for (uint32_t s = 32; s > 0; s >>= 1) {
-      const uint32_t q = p + s;
-      if (q < T.npieces && x >= T.start[q]) p = q;
-    }
-  }
-  const uint32_t d = (uint32_t)(x - T.origin[p]);   // a piece spans less than 2^32 seconds
-  uint32_t q;
-  switch (T.step[p]) {   // divisions by compile-time constants
-    case 0: q = 0; break;
-    case 60: q = d / 60u; break;
-    case 3600: q = d / 3600u; break;
-    case 86400: q = d / 86400u; break;
-    default: q = d; break;   // 1: second granularity
-  }
-  return (uint64_t)(T.base[p] + q);
-}
-
-// floating-point keys: -0.0 groups with +0.0 (KeyEqual uses ==, std::hash<float> maps both to 0; store.cc:46-85)
-__device__ __forceinline__ uint64_t fzero_fix(uint64_t val, uint32_t width) {
-  return (width == 4 ? (uint32_t)(val << 1) == 0u : (val << 1) == 0ull) ? 0ull : val;
-}
 
 // ---------------------------------------------------------------------------------------------
 // accumulator update == Metrics::Update (store.cc:131-161), on native atomics
@@ -329,14 +235,6 @@ __device__ __forceinline__ void acc_update_shared(uint32_t a, uint32_t op, uint6
   }
 }
 
-__device__ __forceinline__ uint64_t mix64(uint64_t x) {
-  x ^= x >> 33;
-  x *= 0xff51afd7ed558ccdULL;
-  x ^= x >> 33;
-  x *= 0xc4ceb9fe1a85ec53ULL;
-  x ^= x >> 33;
-  return x;
-}
 
 // Find-or-claim the cell of `key` in the open-addressing table. The all-ones key (== the EMPTY
 // marker) gets the dedicated cell `cap`. Returns ~0 on probe-limit overflow.
@@ -422,10 +320,6 @@ __device__ __forceinline__ Pair128 cas128(Pair128 *p, Pair128 cmp, Pair128 val) 
       : "memory");
   return r;
 }
-// owner rank of a pair (scan kernel, several GPUs): every copy of a pair must meet on one rank
-__device__ __forceinline__ uint32_t pair_owner(uint64_t hi, uint64_t id, uint32_t nranks) {
-  return (uint32_t)((mix64(hi * 0x9E3779B97F4A7C15ull + id) >> 33) % nranks);
-}
 
 constexpr int kBucketThreads = 1024;
 constexpr int kBucketPer = 8;          // pairs per thread and tile
@@ -441,9 +335,6 @@ struct PairsBucketParams {
   uint64_t *out;               // bucket b at b * bucket_cap
   unsigned long long *flags;   // set on bucket overflow
 };
-__device__ __forceinline__ uint32_t pair_bucket(uint64_t key, uint32_t nbuckets) {
-  return (uint32_t)(mix64(key) >> 24) & (nbuckets - 1);
-}
 
 // Tile of 8192 pairs per CTA iteration: histogram + rank of every pair in shared memory, one global atomic per
 // non-empty bucket and tile, then the scatter (the L2 write-combines the 8-byte stores of a bucket's tail).
@@ -1033,30 +924,6 @@ __device__ __forceinline__ bool group_passes(const ExtractParams &E, uint64_t c,
   }
   return sp == 0 ? true : (stk & 1u) != 0;
 }
-// Order-preserving image of an integer under util::StringNumCmp::SmallerInt (length, then lexicographic,
-// src/util/string.h:28-49): non-negative numbers order numerically; "-" sorts before every digit, so inside one string
-// length the negatives come first, by increasing magnitude. rank = number of representable values that sort before x.
-__device__ __forceinline__ uint64_t smaller_int_rank(long long x) {
-  const unsigned long long p10[20] = {1ull, 10ull, 100ull, 1000ull, 10000ull, 100000ull, 1000000ull, 10000000ull, 100000000ull,
-                                      1000000000ull, 10000000000ull, 100000000000ull, 1000000000000ull, 10000000000000ull,
-                                      100000000000000ull, 1000000000000000ull, 10000000000000000ull, 100000000000000000ull,
-                                      1000000000000000000ull, 10000000000000000000ull};
-  const unsigned long long kPos = 1ull << 63;                 // representable non-negative values
-  auto nonneg_upto = [&](int digits) { return digits <= 0 ? 0ull : (digits >= 19 ? kPos : p10[digits]); };      // with <= digits digits
-  auto neg_upto = [&](int digits) { return digits <= 0 ? 0ull : (digits >= 19 ? kPos : p10[digits] - 1ull); };  // magnitude <= digits digits
-  if (x >= 0) {
-    const unsigned long long u = (unsigned long long)x;
-    int d = 1;
-    while (d < 19 && u >= p10[d]) ++d;                        // decimal digits = string length
-    // before x: everything shorter (non-negatives with < d digits, negatives with magnitude < d - 1 digits ... of length < d),
-    // the negatives of length d (magnitude of d - 1 digits), the non-negatives of d digits below x
-    return nonneg_upto(d - 1) + neg_upto(d - 1) + (u - (d == 1 ? 0ull : p10[d - 1]));
-  }
-  const unsigned long long m = 0ull - (unsigned long long)x;  // magnitude (2^63 for INT64_MIN)
-  int e = 1;
-  while (e < 19 && m >= p10[e]) ++e;                          // digits of the magnitude; string length e + 1
-  return nonneg_upto(e) + neg_upto(e - 1) + (m - p10[e - 1]);
-}
 __device__ __forceinline__ uint64_t sort_ordinal(const ExtractParams &E, uint64_t c, uint64_t packed) {
   const uint64_t v = group_value(E, E.sort_src, c, packed);
   const uint64_t o = E.sort_kind == 1 ? smaller_int_rank((long long)v) : v;
@@ -1192,26 +1059,6 @@ __global__ void fill64_kernel(uint64_t *p, uint64_t n, uint64_t v) {
     p[i] = v;
 }
 
-// Order-preserving map of an element to uint64 (so one atomicMin/Max pair serves every type).
-__device__ __forceinline__ uint64_t to_ordered(uint64_t raw, uint32_t type) {
-  switch (type) {
-    case 4: case 5: case 6: case 7:  // signed ints (already sign-extended)
-      return raw ^ 0x8000000000000000ull;
-    case 8: {                        // f32
-      uint32_t b = (uint32_t)raw;
-      if (b == 0x80000000u) b = 0;   // -0.0 == +0.0
-      b = (b >> 31) ? ~b : (b | 0x80000000u);
-      return b;
-    }
-    case 9: {                        // f64
-      uint64_t b = raw;
-      if (b == 0x8000000000000000ull) b = 0;
-      return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
-    }
-    default:
-      return raw;
-  }
-}
 
 struct StatCol {
   uint64_t off;
@@ -1295,13 +1142,6 @@ __global__ void __launch_bounds__(256) build_rows_kernel(const __grid_constant__
   }
 }
 
-__device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
-  x += 0x9E3779B97F4A7C15ULL;
-  uint64_t z = x;
-  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
-  z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
-  return z ^ (z >> 31);
-}
 
 struct GenCol {
   uint64_t off;     // slab offset, or unused for bitset

@@ -8,6 +8,7 @@
 // point fails with VGPU_ERR_CUDA.
 #include "../../include/vgpu.h"
 #include "select_kernels.cuh"
+#include "time_dict.h"
 
 #include <algorithm>
 #include <cfloat>
