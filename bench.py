@@ -569,7 +569,9 @@ def measure_e2e(torch, v, db, t, query, runner, plan, rows, nseg, world, dist, s
     # so that the pinned host buffers of all ranks together stay modest; the table is cut down to exactly the
     # uploaded segments first, so rows scanned == rows uploaded.
     e_rows = min(rows, args.e2e_rows) if args.e2e_rows else (rows if world == 1 else min(rows, 250_000_000))
-    # pinned buffers close to the GPU: bind this process to the GPU's NUMA-local cores before allocating them
+    # pinned buffers close to the GPU: bind this process to the GPU's NUMA-local cores before allocating them (and give
+    # the cores back afterwards: the cpu_baseline leg that follows must see every core of the box)
+    saved_affinity = os.sched_getaffinity(0)
     try:
         import pynvml
         pynvml.nvmlInit()
@@ -625,6 +627,7 @@ def measure_e2e(torch, v, db, t, query, runner, plan, rows, nseg, world, dist, s
         tt = torch.tensor([ms], device="cuda", dtype=torch.float64)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         ms = tt.item()
+    os.sched_setaffinity(0, saved_affinity)
     d2h = sum(a.nbytes for a in g["keys"]) + sum(a.nbytes for a in g["accs"])
     scanned = runner.stats.scanned_recs   # all ranks (QueryStats are merged): the tables hold exactly the uploaded segments
     assert scanned == e_rows * world, (scanned, e_rows, world)
