@@ -13,6 +13,9 @@ Runs only in the authoring container (needs /root/reference and oracle/_ref buil
      benchmark configs C0-C4 and edge cases the gtests do not cover) through the real reference.
      -> tests/golden/ref_scenarios.jsonl + seg files
 
+  3. tests/golden/fuzz_scenarios.py: seeded random tables / rows / queries through the real reference
+     -> tests/golden/ref_fuzz_scenarios.jsonl + seg files (the differential pin of the numpy oracle)
+
 The fixtures are what travels to the GPU box (no /root/reference there).
 """
 import gzip
@@ -70,14 +73,22 @@ def from_gtest_capture(run=True):
           f"queries from the reference's gtests")
 
 
-def from_scenarios(which="SCENARIOS", target="ref_scenarios.jsonl"):
+def _run_job(jpath):
+    return subprocess.run([os.path.join(REF, "oracle_cli"), jpath], capture_output=True, text=True)
+
+
+def from_scenarios(which="SCENARIOS", target="ref_scenarios.jsonl", module="scenarios", workers=1, state_dir=None):
     sys.path.insert(0, HERE)
-    import scenarios
+    import importlib
+    from concurrent.futures import ThreadPoolExecutor
+    scenarios = importlib.import_module(module)
     tmp = os.path.join(REF, "scenario_tmp")
     os.makedirs(tmp, exist_ok=True)
     out = []
-    for sc in getattr(scenarios, which):
-        job = {"state_dir": os.path.join(REF, "state"), "table": sc["table"], "queries": sc["queries"],
+    all_sc = getattr(scenarios, which)
+    jobs = []
+    for sc in all_sc:
+        job = {"state_dir": state_dir or os.path.join(REF, "state"), "table": sc["table"], "queries": sc["queries"],
                "dump": os.path.join(tmp, sc["name"] + ".bin")}
         for k in ("rows", "generate", "rollup_ts"):
             if k in sc:
@@ -85,7 +96,11 @@ def from_scenarios(which="SCENARIOS", target="ref_scenarios.jsonl"):
         jpath = os.path.join(tmp, sc["name"] + ".json")
         with open(jpath, "w") as f:
             json.dump(job, f)
-        p = subprocess.run([os.path.join(REF, "oracle_cli"), jpath], capture_output=True, text=True)
+        jobs.append((job, jpath))
+    # one reference process per scenario (each distinct query is a g++ JIT compile): several at a time
+    with ThreadPoolExecutor(max_workers=workers) as ex:
+        procs = list(ex.map(_run_job, [jp for _, jp in jobs]))
+    for sc, (job, jpath), p in zip(all_sc, jobs, procs):
         if p.returncode != 0:
             raise RuntimeError(f"oracle_cli failed on {sc['name']}: {p.stdout[-500:]} {p.stderr[-500:]}")
         res = json.loads(p.stdout.strip().splitlines()[-1])
@@ -117,3 +132,7 @@ if __name__ == "__main__":
         from_scenarios("SELECT_SCENARIOS", "ref_select_scenarios.jsonl")
     if "edge" in what or not sys.argv[1:]:
         from_scenarios("EDGE_SCENARIOS", "ref_edge_scenarios.jsonl")
+    if "fuzz" in what or not sys.argv[1:]:
+        # a JIT cache of its own: these ~250 one-off .so files must not travel to the GPU box with oracle/_ref/state
+        from_scenarios("FUZZ_SCENARIOS", "ref_fuzz_scenarios.jsonl", module="fuzz_scenarios", workers=os.cpu_count() or 1,
+                       state_dir=os.path.join("/tmp", "vgpu_fuzz_state"))
