@@ -730,7 +730,9 @@ def run_search(table_conf, segments, dicts, query):
         col = seg[d.name]
         for i in passing.tolist():
             v = col[i]
-            key = v.tobytes()
+            # std::unordered_set of the column's C++ type: floating-point values compare with == (-0.0 == 0.0; the
+            # first one seen is the one that is printed)
+            key = (v + 0.0).tobytes() if d.type in ("f32", "f64") and v == 0 else v.tobytes()
             if key in codes:
                 continue
             codes.add(key)

@@ -200,3 +200,56 @@ def make_scenarios(seed=20261017, count=36, queries=6, prefix="fuzz", rows=(20, 
 
 # two batches: small tables with deep filters, then larger ones (more merged upserts, multi-id bitset cells, wrapped sums)
 FUZZ_SCENARIOS = make_scenarios() + make_scenarios(seed=77001, count=24, prefix="fuzzb", rows=(300, 1200))
+
+
+# ---- select / search: rows in (segment, tuple) order with the per-segment limit quirk; distinct values ----
+def _make_select(rng, table, gen, kinds):
+    dims = [d["name"] for d in table["dimensions"]]
+    mets = [m["name"] for m in table["metrics"]]
+    fcols = [c for c in dims + mets if _filterable(c, kinds)]
+    if rng.random() < 0.3:
+        d = rng.choice([x for x in dims if kinds[x][0] in ("str", "num", "bool") and (kinds[x][1] or "") not in ("float", "double")] or dims[:1])
+        pool = gen.get(d, ["a"])
+        term = rng.choice(["", rng.choice(pool)[:rng.randrange(1, 3)], rng.choice(pool)[-1:], "zz"])
+        q = {"type": "search", "table": "events", "dimension": d, "term": term}
+        if rng.random() < 0.5:
+            q["limit"] = rng.randrange(1, 5)
+    else:
+        q = {"type": "select", "table": "events"}
+        if rng.random() < 0.2:
+            q["select"] = [{"column": "*"}]
+        else:
+            sel_d = rng.sample(dims, rng.randrange(1, min(3, len(dims)) + 1))
+            sel_m = rng.sample(mets, rng.randrange(0, min(3, len(mets)) + 1))
+            select = []
+            for d in sel_d:
+                c = {"column": d}
+                if kinds[d][0] in ("time", "micro") and rng.random() < 0.7:
+                    c["format"] = "%Y-%m-%d %H:%M:%S"
+                select.append(c)
+            q["select"] = select + [{"column": m} for m in sel_m]
+        if rng.random() < 0.5:
+            q["limit"] = rng.randrange(1, 12)
+        if rng.random() < 0.35:
+            q["skip"] = rng.randrange(0, 9)
+    if fcols and rng.random() < 0.6:
+        q["filter"] = _filter(rng, fcols, kinds, gen, depth=1)
+    if rng.random() < 0.15:
+        q["header"] = True
+    return q
+
+
+def make_select_scenarios(seed=424242, count=20, queries=6):
+    rng = random.Random(seed)
+    out = []
+    for i in range(count):
+        table, gen, kinds = _make_table(rng, i)
+        nrows = rng.randrange(10, 160)
+        cols = [d["name"] for d in table["dimensions"]] + [m["name"] for m in table["metrics"] if m["type"] != "count"]
+        data = [[rng.choice(gen[c]) for c in cols] for _ in range(nrows)]
+        out.append({"name": f"fuzzs{i:02d}", "table": table, "rows": data, "rollup_ts": NOW,
+                    "queries": [_make_select(rng, table, gen, kinds) for _ in range(queries)]})
+    return out
+
+
+FUZZ_SELECT_SCENARIOS = make_select_scenarios()

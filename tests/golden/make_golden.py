@@ -136,3 +136,6 @@ if __name__ == "__main__":
         # a JIT cache of its own: these ~250 one-off .so files must not travel to the GPU box with oracle/_ref/state
         from_scenarios("FUZZ_SCENARIOS", "ref_fuzz_scenarios.jsonl", module="fuzz_scenarios", workers=os.cpu_count() or 1,
                        state_dir=os.path.join("/tmp", "vgpu_fuzz_state"))
+    if "fuzz_select" in what or not sys.argv[1:]:
+        from_scenarios("FUZZ_SELECT_SCENARIOS", "ref_fuzz_select_scenarios.jsonl", module="fuzz_scenarios",
+                       workers=os.cpu_count() or 1, state_dir=os.path.join("/tmp", "vgpu_fuzz_state"))

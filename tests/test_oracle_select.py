@@ -9,13 +9,14 @@ import viya_oracle
 
 GTEST = G.records("ref_gtest_select.jsonl")
 SCEN = G.records("ref_select_scenarios.jsonl")
+FUZZ = G.records("ref_fuzz_select_scenarios.jsonl")   # seeded random select / search queries (tests/golden/fuzz_scenarios.py)
 
 
 def check(rec):
     hdr, segs, dicts, hidden = viya_oracle.read_dump(G.seg_path(rec["seg"]))
     q = rec["query"]
     if "error" in rec:
-        with pytest.raises((ValueError, OverflowError, KeyError)):
+        with pytest.raises((ValueError, OverflowError, KeyError, RuntimeError)):
             if q["type"] == "select":
                 viya_oracle.run_select(rec["table"], segs, dicts, q, hidden_counts=hidden)
             else:
@@ -42,4 +43,9 @@ def test_oracle_matches_reference_gtests(rec):
 
 @pytest.mark.parametrize("rec", SCEN, ids=[G.rec_id(r) for r in SCEN])
 def test_oracle_matches_reference_scenarios(rec):
+    check(rec)
+
+
+@pytest.mark.parametrize("rec", FUZZ, ids=[G.rec_id(r) for r in FUZZ])
+def test_oracle_matches_reference_fuzz(rec):
     check(rec)
