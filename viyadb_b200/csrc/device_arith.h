@@ -189,6 +189,99 @@ VGPU_HD VGPU_INLINE uint64_t splitmix64(uint64_t x) {
   return z ^ (z >> 31);
 }
 
+// bit patterns as floating-point values (the kernel's intrinsics on the device, memcpy on the host)
+#if defined(__CUDA_ARCH__)
+VGPU_HD VGPU_INLINE float vgpu_bits_f32(uint32_t x) { return __uint_as_float(x); }
+VGPU_HD VGPU_INLINE double vgpu_bits_f64(uint64_t x) { return __longlong_as_double((long long)x); }
+#else
+VGPU_HD VGPU_INLINE float vgpu_bits_f32(uint32_t x) { float f; __builtin_memcpy(&f, &x, 4); return f; }
+VGPU_HD VGPU_INLINE double vgpu_bits_f64(uint64_t x) { double f; __builtin_memcpy(&f, &x, 8); return f; }
+#endif
+
+// ---------------------------------------------------------------------------------------------
+// predicate leaves (filter.cc:206-261): the generic per-row compare and the vectorised leaf classes
+// ---------------------------------------------------------------------------------------------
+VGPU_HD VGPU_NOINLINE bool gen_compare(uint32_t gcls, uint32_t gop, uint64_t v, uint64_t a) {
+  switch (gcls) {
+    case G_I64: {
+      long long x = (long long)v, y = (long long)a;
+      switch (gop) { case 0: return x == y; case 1: return x != y; case 2: return x < y;
+                     case 3: return x <= y; case 4: return x > y; default: return x >= y; }
+    }
+    case G_F32: {
+      float x = vgpu_bits_f32((uint32_t)v), y = vgpu_bits_f32((uint32_t)a);
+      switch (gop) { case 0: return x == y; case 1: return x != y; case 2: return x < y;
+                     case 3: return x <= y; case 4: return x > y; default: return x >= y; }
+    }
+    case G_F64: {
+      double x = vgpu_bits_f64(v), y = vgpu_bits_f64(a);
+      switch (gop) { case 0: return x == y; case 1: return x != y; case 2: return x < y;
+                     case 3: return x <= y; case 4: return x > y; default: return x >= y; }
+    }
+    default: {  // G_U64, G_CARD
+      switch (gop) { case 0: return v == a; case 1: return v != a; case 2: return v < a;
+                     case 3: return v <= a; case 4: return v > a; default: return v >= a; }
+    }
+  }
+}
+
+// mask of one vectorisable leaf over the 16 rows in v
+VGPU_HD VGPU_INLINE uint32_t leaf_mask16(const PInstr &in, const uint32_t (&v)[kRowsPerThread]) {
+  uint32_t m = 0;
+  const uint32_t cls = in.cls;
+  const uint32_t a = (uint32_t)in.arg;
+  if (cls == C_EQ32) {
+#pragma unroll
+    for (int i = 0; i < kRowsPerThread; ++i) if (v[i] == a) m |= 1u << i;
+  } else if (cls == C_LT32) {
+    const uint32_t bias = in.bias;
+#pragma unroll
+    for (int i = 0; i < kRowsPerThread; ++i) if ((v[i] ^ bias) < a) m |= 1u << i;
+  } else if (cls == C_RNG32) {
+    const uint32_t bias = in.bias, len = in.arg2;
+    if (bias == 0) {
+#pragma unroll
+      for (int i = 0; i < kRowsPerThread; ++i) if ((v[i] - a) < len) m |= 1u << i;
+    } else {
+#pragma unroll
+      for (int i = 0; i < kRowsPerThread; ++i) if (((v[i] ^ bias) - a) < len) m |= 1u << i;
+    }
+  } else {  // C_LUT64: membership in a set of codes < 64 — one shift per row whatever the list length
+    const uint64_t lut = in.arg;
+#pragma unroll
+    for (int i = 0; i < kRowsPerThread; ++i) {
+      uint64_t t;
+#if defined(__CUDA_ARCH__)
+      asm("shr.b64 %0, %1, %2;" : "=l"(t) : "l"(lut), "r"(v[i]));  // shift amounts >= 64 give 0
+#else
+      t = v[i] >= 64u ? 0ull : lut >> v[i];
+#endif
+      if (t & 1ull) m |= 1u << i;
+    }
+  }
+  return m;
+}
+
+// HAVING on the device (post_agg.cc:76-83): generic compare of widened group values (group_passes, kernels.cuh)
+VGPU_HD VGPU_INLINE bool post_compare(uint32_t gcls, uint32_t gop, uint64_t v, uint64_t a) {
+  switch (gcls) {
+    case G_I64: {
+      const long long x = (long long)v, y = (long long)a;
+      switch (gop) { case 0: return x == y; case 1: return x != y; case 2: return x < y; case 3: return x <= y; case 4: return x > y; default: return x >= y; }
+    }
+    case G_F32: {
+      const float x = vgpu_bits_f32((uint32_t)v), y = vgpu_bits_f32((uint32_t)a);
+      switch (gop) { case 0: return x == y; case 1: return x != y; case 2: return x < y; case 3: return x <= y; case 4: return x > y; default: return x >= y; }
+    }
+    case G_F64: {
+      const double x = vgpu_bits_f64(v), y = vgpu_bits_f64(a);
+      switch (gop) { case 0: return x == y; case 1: return x != y; case 2: return x < y; case 3: return x <= y; case 4: return x > y; default: return x >= y; }
+    }
+    default:
+      switch (gop) { case 0: return v == a; case 1: return v != a; case 2: return v < a; case 3: return v <= a; case 4: return v > a; default: return v >= a; }
+  }
+}
+
 }  // namespace vgpu
 
 #endif  // VGPU_DEVICE_ARITH_H_

@@ -884,24 +884,6 @@ extract_groups_kernel(const __grid_constant__ ExtractParams E) {
 __device__ __forceinline__ uint64_t group_value(const ExtractParams &E, uint32_t src, uint64_t c, uint64_t packed) {
   return src < E.nkeys ? group_key_value(E, src, c, packed) : group_acc_value(E.mets[src - E.nkeys], c);
 }
-__device__ __forceinline__ bool post_compare(uint32_t gcls, uint32_t gop, uint64_t v, uint64_t a) {
-  switch (gcls) {
-    case G_I64: {
-      const long long x = (long long)v, y = (long long)a;
-      switch (gop) { case 0: return x == y; case 1: return x != y; case 2: return x < y; case 3: return x <= y; case 4: return x > y; default: return x >= y; }
-    }
-    case G_F32: {
-      const float x = __uint_as_float((uint32_t)v), y = __uint_as_float((uint32_t)a);
-      switch (gop) { case 0: return x == y; case 1: return x != y; case 2: return x < y; case 3: return x <= y; case 4: return x > y; default: return x >= y; }
-    }
-    case G_F64: {
-      const double x = __longlong_as_double((long long)v), y = __longlong_as_double((long long)a);
-      switch (gop) { case 0: return x == y; case 1: return x != y; case 2: return x < y; case 3: return x <= y; case 4: return x > y; default: return x >= y; }
-    }
-    default:
-      switch (gop) { case 0: return v == a; case 1: return v != a; case 2: return v < a; case 3: return v <= a; case 4: return v > a; default: return v >= a; }
-  }
-}
 // FilterComparison over (agg key, accumulators), post_agg.cc:76-83: the same bitwise &,| tree as the row predicate
 __device__ __forceinline__ bool group_passes(const ExtractParams &E, uint64_t c, uint64_t packed) {
   uint32_t stk = 0;  // bit i = stack entry i (depth <= kStackDepth)

@@ -669,20 +669,7 @@ int vgpu_query_agg(vgpu_table *t, const vgpu_plan *plan, vgpu_result **out) {
         // (unsigned keys of at most 4 bytes, no rollup; leaf arguments are raw zero-extended values).
         uint64_t lut = 0;
         if (P.conj && !ks.rollup && !type_signed(ci.type) && ci.width <= 4 && !(ctx->tune & 16384u)) {
-          for (uint32_t i = 0; i < P.nprog; ++i) {
-            const PInstr &in = P.prog[i];
-            if (in.slot != ks.slot || in.neg) continue;
-            const uint64_t a = (uint32_t)in.arg;
-            if (in.cls == C_EQ32) { lo = std::max(lo, a); hi = std::min(hi, a); }
-            else if (in.cls == C_RNG32 && in.bias == 0) { lo = std::max(lo, a); hi = std::min(hi, a + in.arg2 - 1); }
-            else if (in.cls == C_LT32 && in.bias == 0 && a > 0) { hi = std::min(hi, a - 1); }
-            else if (in.cls == C_LUT64) lut = lut ? (lut & in.arg) : in.arg;
-          }
-          if (lo > hi) hi = lo;  // nothing can pass: any one-value domain will do
-          if (lut) {
-            for (uint32_t b = 0; b < 64; ++b)
-              if (b < lo || b > hi) lut &= ~(1ull << b);
-          }
+          lut = tighten_key_domain(P, ks.slot, lo, hi);   // planner.h
         }
         kr.lo = lo;
         kr.range = hi - lo + 1;  // wraps to 0 for the full 64-bit domain

@@ -86,30 +86,6 @@ __device__ __forceinline__ void load_vec16(const uint8_t *col, uint32_t width, u
   }
 }
 
-__device__ __noinline__ bool gen_compare(uint32_t gcls, uint32_t gop, uint64_t v, uint64_t a) {
-  switch (gcls) {
-    case G_I64: {
-      long long x = (long long)v, y = (long long)a;
-      switch (gop) { case 0: return x == y; case 1: return x != y; case 2: return x < y;
-                     case 3: return x <= y; case 4: return x > y; default: return x >= y; }
-    }
-    case G_F32: {
-      float x = __uint_as_float((uint32_t)v), y = __uint_as_float((uint32_t)a);
-      switch (gop) { case 0: return x == y; case 1: return x != y; case 2: return x < y;
-                     case 3: return x <= y; case 4: return x > y; default: return x >= y; }
-    }
-    case G_F64: {
-      double x = __longlong_as_double((long long)v), y = __longlong_as_double((long long)a);
-      switch (gop) { case 0: return x == y; case 1: return x != y; case 2: return x < y;
-                     case 3: return x <= y; case 4: return x > y; default: return x >= y; }
-    }
-    default: {  // G_U64, G_CARD
-      switch (gop) { case 0: return v == a; case 1: return v != a; case 2: return v < a;
-                     case 3: return v <= a; case 4: return v > a; default: return v >= a; }
-    }
-  }
-}
-
 __device__ __forceinline__ uint64_t bitset_card(const SegDesc &seg, uint32_t bidx, uint64_t row) {
   const uint32_t *off = seg.bs_offsets[bidx];
   if (off == nullptr) return 1;
@@ -122,39 +98,6 @@ struct CurSeg {
   const uint8_t *rows;
   uint32_t cap, nrows, index;
 };
-
-// mask of one vectorisable leaf over the 16 rows in v
-__device__ __forceinline__ uint32_t leaf_mask16(const PInstr &in, const uint32_t (&v)[kRowsPerThread]) {
-  uint32_t m = 0;
-  const uint32_t cls = in.cls;
-  const uint32_t a = (uint32_t)in.arg;
-  if (cls == C_EQ32) {
-#pragma unroll
-    for (int i = 0; i < kRowsPerThread; ++i) if (v[i] == a) m |= 1u << i;
-  } else if (cls == C_LT32) {
-    const uint32_t bias = in.bias;
-#pragma unroll
-    for (int i = 0; i < kRowsPerThread; ++i) if ((v[i] ^ bias) < a) m |= 1u << i;
-  } else if (cls == C_RNG32) {
-    const uint32_t bias = in.bias, len = in.arg2;
-    if (bias == 0) {
-#pragma unroll
-      for (int i = 0; i < kRowsPerThread; ++i) if ((v[i] - a) < len) m |= 1u << i;
-    } else {
-#pragma unroll
-      for (int i = 0; i < kRowsPerThread; ++i) if (((v[i] ^ bias) - a) < len) m |= 1u << i;
-    }
-  } else {  // C_LUT64: membership in a set of codes < 64 — one shift per row whatever the list length
-    const uint64_t lut = in.arg;
-#pragma unroll
-    for (int i = 0; i < kRowsPerThread; ++i) {
-      uint64_t t;
-      asm("shr.b64 %0, %1, %2;" : "=l"(t) : "l"(lut), "r"(v[i]));  // shift amounts >= 64 give 0
-      if (t & 1ull) m |= 1u << i;
-    }
-  }
-  return m;
-}
 
 // row0 = first row of the lane inside the segment (chunk_row0 + lane*4)
 // kConjOnly: the caller knows the predicate is an unrolled conjunction (P.conj): the interpreter is not compiled in
