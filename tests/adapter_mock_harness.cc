@@ -1,0 +1,211 @@
+// adapter_mock_harness.cc — TEST INFRASTRUCTURE. The C++ drop-in adapter (viyadb_b200/host/gpu_query_runner.h), UNMODIFIED
+// and whole, inside a reference process without a GPU: this file DEFINES the C ABI of include/vgpu.h as a mock device —
+// vgpu_table_create records the schema, vgpu_query_agg records the plan the adapter lowered and hands back a group table
+// from the job file (tests/test_adapter_mock.py takes it from the oracle, which is pinned to the real reference on the
+// same records) — and it is linked INSTEAD of libvgpu.so. So `query->Accept(GpuQueryRunner)` runs exactly the code a
+// ViyaDB maintainer would ship: the reference's FilterArgsPacker, the predicate program, rollup boundaries through
+// util::Duration, the post-aggregation request, then HAVING / formatting / sort / skip / limit on the returned groups.
+// The mock computes nothing: it is not a CPU path of the product and nothing under viyadb_b200/ links it.
+//
+// job = {"table": {...}, "dicts": {"<string dim>": ["__exceeded", "v1", ...]}, "rollup_ts": N, "state_dir": "...",
+//        "cases": [{"query": {...}, "ngroups": n, "keys": [[bits...] per selected dimension], "accs": [[bits...] per
+//                   selected metric], "hidden": [counts...] | null, "scanned_recs": r, "scanned_segments": s}]}
+#include "db/database.h"
+#include "db/dictionary.h"
+#include "db/table.h"
+#include "gpu_query_runner.h"
+#include "query/output.h"
+#include "query/query.h"
+#include "query/runner.h"
+#include "util/config.h"
+#include <cstring>
+#include <fstream>
+#include <iostream>
+#include <nlohmann/json.hpp>
+
+using json = nlohmann::json;
+namespace db = viya::db;
+namespace util = viya::util;
+namespace query = viya::query;
+
+// ---------------------------------------------------------------------------------------------
+// the mock device
+// ---------------------------------------------------------------------------------------------
+struct vgpu_ctx { int dummy; };
+struct vgpu_table { json schema; };
+struct vgpu_result { vgpu_result_view view; };
+struct vgpu_rows { int dummy; };
+struct vgpu_search { int dummy; };
+
+namespace {
+vgpu_ctx g_ctx;
+json g_plan;                 // the last plan vgpu_query_agg saw
+vgpu_result_view g_canned;   // what it answers
+json g_schema;
+
+json nodes_json(const vgpu_pred_node *nodes, uint32_t n) {
+  json a = json::array();
+  for (uint32_t i = 0; i < n; ++i) a.push_back({nodes[i].kind, nodes[i].op, nodes[i].col, nodes[i].arg, nodes[i].n});
+  return a;
+}
+}  // namespace
+
+extern "C" {
+const char *vgpu_last_error(void) { return "mock device"; }
+int vgpu_table_create(vgpu_ctx *, const vgpu_schema *schema, vgpu_table **out) {
+  auto *t = new vgpu_table();
+  json cols = json::array();
+  for (uint32_t c = 0; c < schema->ncols; ++c)
+    cols.push_back({schema->cols[c].kind, schema->cols[c].type, schema->cols[c].agg, schema->cols[c].lit_type});
+  t->schema = {{"ncols", schema->ncols}, {"ndims", schema->ndims}, {"segment_size", schema->segment_size}, {"cols", cols}};
+  g_schema = t->schema;
+  *out = t;
+  return VGPU_OK;
+}
+void vgpu_table_free(vgpu_table *t) { delete t; }
+int vgpu_segment_put_async(vgpu_table *, uint32_t, uint64_t, const void *const *) { return VGPU_OK; }
+int vgpu_segment_update(vgpu_table *, uint32_t, uint64_t, uint64_t, const void *const *) { return VGPU_OK; }
+int vgpu_table_sync(vgpu_table *) { return VGPU_OK; }
+int vgpu_table_invalidate(vgpu_table *, uint32_t) { return VGPU_OK; }
+int vgpu_host_pin(vgpu_ctx *, const void *, size_t) { return VGPU_OK; }
+int vgpu_host_unpin(vgpu_ctx *, const void *) { return VGPU_OK; }
+int vgpu_query_agg(vgpu_table *, const vgpu_plan *p, vgpu_result **out) {
+  json keys = json::array();
+  for (uint32_t k = 0; k < p->nkeys; ++k) {
+    const vgpu_key &key = p->keys[k];
+    json b = json::array(), g = json::array();
+    for (uint32_t r = 0; r < key.nrules; ++r) { b.push_back(key.rule_boundary[r]); g.push_back(key.rule_granularity[r]); }
+    keys.push_back({{"col", key.col}, {"nrules", key.nrules}, {"query_granularity", key.query_granularity},
+                    {"rule_boundary", b}, {"rule_granularity", g}});
+  }
+  json args = json::array(), hargs = json::array(), mcols = json::array();
+  for (uint32_t i = 0; i < p->nargs; ++i) args.push_back(p->args[i]);
+  for (uint32_t i = 0; i < p->nhargs; ++i) hargs.push_back(p->hargs[i]);
+  for (uint32_t i = 0; i < p->nmetrics; ++i) mcols.push_back(p->metric_cols[i]);
+  g_plan = {{"nodes", nodes_json(p->nodes, p->nnodes)}, {"args", args}, {"keys", keys}, {"metric_cols", mcols},
+            {"need_hidden_count", p->need_hidden_count}, {"flags", p->flags},
+            {"hnodes", nodes_json(p->hnodes, p->nhnodes)}, {"hargs", hargs},
+            {"sort_col", p->sort_col}, {"sort_descending", p->sort_descending}, {"top_k", p->top_k}};
+  auto *r = new vgpu_result();
+  r->view = g_canned;
+  *out = r;
+  return VGPU_OK;
+}
+int vgpu_result_get(const vgpu_result *r, vgpu_result_view *view) { *view = r->view; return VGPU_OK; }
+void vgpu_result_free(vgpu_result *r) { delete r; }
+// select / search: referenced by the visitor's vtable; the aggregate cases of this harness never reach them
+int vgpu_query_select(vgpu_table *, const vgpu_rows_plan *, vgpu_rows **) { return VGPU_ERR_UNSUPPORTED; }
+int vgpu_rows_get(const vgpu_rows *, vgpu_rows_view *) { return VGPU_ERR_UNSUPPORTED; }
+void vgpu_rows_free(vgpu_rows *) {}
+int vgpu_query_search(vgpu_table *, const vgpu_search_plan *, vgpu_search **) { return VGPU_ERR_UNSUPPORTED; }
+int vgpu_search_get(const vgpu_search *, vgpu_search_view *) { return VGPU_ERR_UNSUPPORTED; }
+void vgpu_search_free(vgpu_search *) {}
+}  // extern "C"
+
+// ---------------------------------------------------------------------------------------------
+int main(int argc, char **argv) {
+  if (argc < 2) {
+    std::cerr << "usage: adapter_mock_cli <job.json>\n";
+    return 2;
+  }
+  std::ifstream in(argv[1]);
+  json job;
+  in >> job;
+  if (job.count("rollup_ts")) {
+    std::string v = std::to_string(job["rollup_ts"].get<long>()) + "L";
+    setenv("VIYA_TEST_ROLLUP_TS", v.c_str(), 1);
+  }
+  json out;
+  try {
+    json dbconf;
+    dbconf["state_dir"] = job.value("state_dir", std::string("/tmp/vgpu_fuzz_state"));
+    dbconf["tables"] = json::array({job["table"]});
+    db::Database database{util::Config(dbconf)};
+    auto *table = database.GetTable(job["table"]["name"].get<std::string>());
+    // dictionaries in code order, the way the generated upsert code fills them (code = c2v.size(), both maps): code 0 is
+    // "__exceeded" already (dictionary.cc:22-25)
+    for (auto *dim : table->dimensions()) {
+      if (dim->dim_type() != db::Dimension::DimType::STRING) continue;
+      auto dict = static_cast<const db::StrDimension *>(dim)->dict();
+      auto &vals = job["dicts"][dim->name()];
+      for (size_t i = 1; i < vals.size(); ++i) {
+        const std::string v = vals[i].get<std::string>();
+        const uint64_t code = dict->c2v().size();
+        dict->c2v().push_back(v);
+        switch (dim->num_type().size()) {
+        case db::BaseNumType::_1: reinterpret_cast<db::DictImpl<uint8_t> *>(dict->v2c())->insert(std::make_pair(v, (uint8_t)code)); break;
+        case db::BaseNumType::_2: reinterpret_cast<db::DictImpl<uint16_t> *>(dict->v2c())->insert(std::make_pair(v, (uint16_t)code)); break;
+        case db::BaseNumType::_4: reinterpret_cast<db::DictImpl<uint32_t> *>(dict->v2c())->insert(std::make_pair(v, (uint32_t)code)); break;
+        default: reinterpret_cast<db::DictImpl<uint64_t> *>(dict->v2c())->insert(std::make_pair(v, (uint64_t)code)); break;
+        }
+      }
+    }
+    vgpu_host::GpuQueryRunner::Bindings bindings;
+    out["results"] = json::array();
+    for (auto &c : job["cases"]) {
+      json res;
+      try {
+        query::MemoryRowOutput output;
+        query::QueryFactory factory;
+        std::unique_ptr<query::Query> qq(factory.Create(util::Config(c["query"]), database));
+        auto *aq = dynamic_cast<query::AggregateQuery *>(qq.get());
+        if (aq == nullptr) throw std::runtime_error("not an aggregate query");
+        const uint64_t n = c["ngroups"].get<uint64_t>();
+        auto &dim_cols = aq->dimension_cols();
+        auto &metric_cols = aq->metric_cols();
+        std::vector<std::vector<char>> kbuf(dim_cols.size()), abuf(metric_cols.size());
+        std::vector<const void *> kptr(dim_cols.size()), aptr(metric_cols.size());
+        for (size_t k = 0; k < dim_cols.size(); ++k) {
+          const uint32_t w = (uint32_t)dim_cols[k].dim()->num_type().size();
+          kbuf[k].resize(n * w + 8);
+          for (uint64_t g = 0; g < n; ++g) {
+            uint64_t bits = c["keys"][k][g].get<uint64_t>();
+            std::memcpy(kbuf[k].data() + g * w, &bits, w);
+          }
+          kptr[k] = kbuf[k].data();
+        }
+        for (size_t m = 0; m < metric_cols.size(); ++m) {
+          auto metric = metric_cols[m].metric();
+          const uint32_t w = metric->agg_type() == db::Metric::AggregationType::BITSET ? 8u : (uint32_t)metric->num_type().size();
+          abuf[m].resize(n * w + 8);
+          for (uint64_t g = 0; g < n; ++g) {
+            uint64_t bits = c["accs"][m][g].get<uint64_t>();
+            std::memcpy(abuf[m].data() + g * w, &bits, w);
+          }
+          aptr[m] = abuf[m].data();
+        }
+        std::vector<uint64_t> hidden;
+        if (!c["hidden"].is_null()) hidden = c["hidden"].get<std::vector<uint64_t>>();
+        g_canned = vgpu_result_view{};
+        g_canned.ngroups = n;
+        g_canned.nkeys = (uint32_t)dim_cols.size();
+        g_canned.nmetrics = (uint32_t)metric_cols.size();
+        g_canned.keys = kptr.data();
+        g_canned.accs = aptr.data();
+        g_canned.hidden_count = hidden.empty() ? nullptr : hidden.data();
+        g_canned.aggregated_recs = n;
+        g_canned.scanned_recs = c.value("scanned_recs", (uint64_t)0);
+        g_canned.scanned_segments = c.value("scanned_segments", (uint64_t)0);
+        g_plan = json();
+        vgpu_host::GpuQueryRunner runner(database, output, &g_ctx, bindings);
+        qq->Accept(runner);
+        auto &s = runner.stats();
+        res = {{"rows", output.rows()}, {"plan", g_plan}, {"schema", g_schema},
+               {"stats", {{"scanned_segments", s.scanned_segments}, {"scanned_recs", s.scanned_recs},
+                          {"aggregated_recs", s.aggregated_recs}, {"output_recs", s.output_recs}}}};
+      } catch (const std::invalid_argument &e) {
+        res = {{"error", e.what()}, {"error_type", "invalid_argument"}};
+      } catch (const std::exception &e) {
+        res = {{"error", e.what()}, {"error_type", "exception"}};
+      }
+      out["results"].push_back(res);
+    }
+    bindings.clear();
+  } catch (const std::exception &e) {
+    out["fatal"] = e.what();
+    std::cout << out.dump() << std::endl;
+    return 1;
+  }
+  std::cout << out.dump() << std::endl;
+  return 0;
+}

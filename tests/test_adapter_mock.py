@@ -1,0 +1,198 @@
+"""The C++ drop-in adapter — whole and unmodified — on the CPU, against a mock device.
+
+viyadb_b200/host/gpu_query_runner.h is what a ViyaDB maintainer ships: a query::QueryVisitor that packs literals with the
+reference's own FilterArgsPacker, lowers the query to a vgpu_plan, calls the C ABI and post-aggregates the returned group
+table (HAVING, util::Format, the sort on formatted strings through StringNumCmp, skip / limit). tests/adapter_mock_harness.cc
+links it, inside a reference process, against a MOCK of include/vgpu.h instead of libvgpu.so: the mock records the plan
+and answers with the group table the oracle computed (the oracle is pinned to the real reference on the same records).
+For every golden record the real reference answered (gtests, scenarios, edge cases, 338 fuzz queries):
+
+  * the rows `query->Accept(GpuQueryRunner)` sends == the reference's rows, QueryStats included;
+  * the plan the C++ adapter lowered == the plan the Python mirror lowers (viyadb_b200/query.py — the host the GPU
+    parity suite drives), node for node, literal for literal (the bytes of the literal's own type: the rest of an
+    AnyNum image is uninitialised in the reference), rollup boundaries, post-aggregation request; same schema.
+
+The binary links the reference's objects: built by `make -C oracle adapter_mock` (part of __graft_entry__.build()) where
+/root/reference exists; without it the test skips. No GPU, no libvgpu.so: nothing here computes a scan."""
+import collections
+import json
+import os
+import subprocess
+import tempfile
+
+import numpy as np
+import pytest
+
+import golden_util as G
+import viya_oracle
+import viyadb_b200 as v
+from viyadb_b200 import _native as N
+from viyadb_b200 import db as vdb_mod
+from viyadb_b200.query import GpuQueryRunner, MemoryRowOutput, QueryFactory
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CLI = os.path.join(ROOT, "viyadb_b200", "host", "_build", "adapter_mock_cli")
+STATE = os.path.join(tempfile.gettempdir(), "vgpu_fuzz_state")
+RECS = [r for name in ("ref_gtest.jsonl", "ref_scenarios.jsonl", "ref_edge_scenarios.jsonl", "ref_fuzz_scenarios.jsonl")
+        for r in G.records(name) if "error" not in r and "seg" in r]
+# one process per (table, segment dump): its dictionaries are rebuilt once
+GROUPS = collections.OrderedDict()
+for r in RECS:
+    GROUPS.setdefault((json.dumps(r["table"], sort_keys=True), r["seg"], r.get("rollup_ts")), []).append(r)
+
+
+@pytest.fixture(scope="module")
+def cli():
+    if not os.path.exists(CLI):
+        ref = os.environ.get("VIYA_REFERENCE", "/root/reference")
+        if not os.path.isdir(os.path.join(ref, "src")):
+            pytest.skip("adapter_mock_cli not built and the reference's sources are not here")
+        subprocess.run(["make", "-C", os.path.join(ROOT, "oracle"), "-j8", "ref", "adapter_mock", f"REF={ref}"], check=True,
+                       stdout=subprocess.DEVNULL)
+    return CLI
+
+
+def widen(arr):
+    a = np.asarray(arr)
+    if a.dtype.kind == "f":
+        return a.view("<u4").astype("<u8") if a.dtype.itemsize == 4 else a.view("<u8")
+    return a.astype("<i8").view("<u8") if a.dtype.kind == "i" else a.astype("<u8")
+
+
+def too_big(recs):
+    return any(len(r["rows"]) > 20000 for r in recs)
+
+
+def run_group(cli, key):
+    recs = GROUPS[key]
+    hdr, _ = vdb_mod.read_dump(G.seg_path(recs[0]["seg"]))
+    _, segs, dicts, hidden = viya_oracle.read_dump(G.seg_path(recs[0]["seg"]))
+    cases = []
+    for rec in recs:
+        q = rec["query"]
+        res = viya_oracle.run_query(rec["table"], segs, dicts, q, now=rec.get("rollup_ts"), hidden_counts=hidden)
+        g = res["groups"]
+        n = res["stats"]["aggregated_recs"]
+        cases.append({"query": q, "ngroups": n,
+                      "keys": [widen(k).tolist() for k in g["keys"]], "accs": [widen(a).tolist() for a in g["accs"]],
+                      "hidden": None if g["hidden_count"] is None else np.asarray(g["hidden_count"]).astype("<u8").tolist(),
+                      "scanned_recs": res["stats"]["scanned_recs"], "scanned_segments": res["stats"]["scanned_segments"]})
+    # db::Database generates and compiles the table's Segment class when it is created, GpuTableBinding its segment
+    # accessor (one g++ run each per distinct schema, cached by source hash): a cache of its own under /tmp — these .so
+    # files must not travel with oracle/_ref/state
+    job = {"table": recs[0]["table"], "dicts": hdr["dicts"], "cases": cases, "state_dir": STATE}
+    if recs[0].get("rollup_ts") is not None:
+        job["rollup_ts"] = recs[0]["rollup_ts"]
+    with tempfile.NamedTemporaryFile("w", suffix=".json", delete=False) as f:
+        json.dump(job, f)
+        path = f.name
+    try:
+        # the reference's JIT resolves its include / library paths relative to the CWD (compiler.cc:46-54)
+        p = subprocess.run([cli, path], capture_output=True, text=True, timeout=600,
+                           cwd=os.path.join(ROOT, "oracle", "_ref", "root", "build"))
+    finally:
+        os.remove(path)
+    if p.returncode != 0 or not p.stdout.strip():
+        return {"fatal": (p.stdout[-500:], p.stderr[-500:])}
+    return json.loads(p.stdout.strip().splitlines()[-1])
+
+
+@pytest.fixture(scope="module")
+def results(cli):
+    """every (table, dump) group through one adapter process, several at a time (cold: two g++ runs per table schema)"""
+    from concurrent.futures import ThreadPoolExecutor
+    keys = [k for k in GROUPS if not too_big(GROUPS[k])]
+    os.makedirs(STATE, exist_ok=True)
+    with ThreadPoolExecutor(max_workers=os.cpu_count() or 1) as ex:
+        outs = list(ex.map(lambda k: run_group(cli, k), keys))
+    return dict(zip(keys, outs))
+
+
+# ---- the Python mirror's plan and schema, as plain data ----
+def mirror_schema(t):
+    cols = []
+    for c in t.dimensions + t.metrics:
+        btype, lit = c.type, 0
+        if c.kind == N.METRIC_BITSET and c.type in (N.U8, N.U16):
+            btype, lit = N.U32, c.type + 1
+        cols.append([c.kind, btype, c.agg, lit])
+    if t.has_hidden_count:
+        cols.append([N.METRIC_HIDDEN_COUNT, N.U64, N.AGG_COUNT, 0])
+    return cols
+
+
+def mirror_plan(rec):
+    db = v.Database({"tables": [rec["table"]]}, device=None)
+    t = db.get_table(rec["table"]["name"])
+    hdr, _ = vdb_mod.read_dump(G.seg_path(rec["seg"]))
+    for d in t.dimensions:
+        if d.kind == N.DIM_STRING:
+            c2v = hdr["dicts"][d.name]
+            d.dict.c2v = list(c2v)
+            d.dict.v2c = {s: i for i, s in enumerate(c2v)}
+    query = QueryFactory.create(rec["query"], db)
+    plan = GpuQueryRunner(db, MemoryRowOutput(), now=rec.get("rollup_ts")).build_plan(query)
+
+    def nodes(arr, n):
+        return [[arr[i].kind, arr[i].op, arr[i].col, arr[i].arg, arr[i].n] for i in range(n)]
+    keys = []
+    for k in range(plan.nkeys):
+        key = plan.keys[k]
+        keys.append({"col": key.col, "nrules": key.nrules, "query_granularity": key.query_granularity,
+                     "rule_boundary": [key.rule_boundary[r] for r in range(key.nrules)],
+                     "rule_granularity": [key.rule_granularity[r] for r in range(key.nrules)]})
+    cols = t.dimensions + t.metrics
+    widths = [N.TYPE_WIDTH[c.type] for c in cols] + [8]
+    return {"nodes": nodes(plan.nodes, plan.nnodes), "args": [plan.args[i] for i in range(plan.nargs)], "keys": keys,
+            "metric_cols": [plan.metric_cols[i] for i in range(plan.nmetrics)], "need_hidden_count": plan.need_hidden_count,
+            "flags": plan.flags, "hnodes": nodes(plan.hnodes, plan.nhnodes) if plan.nhnodes else [],
+            "hargs": [plan.hargs[i] for i in range(plan.nhargs)] if plan.nhargs else [],
+            "sort_col": plan.sort_col, "sort_descending": plan.sort_descending, "top_k": plan.top_k}, widths, mirror_schema(t)
+
+
+def masked_args(nodes, args, widths):
+    """the bytes of each literal's own type (db::AnyNum leaves the rest of its 8 bytes uninitialised, column.h:98-121)"""
+    out = list(args)
+    for kind, op, col, arg, n in nodes:
+        if kind == N.NODE_RELOP:
+            span = range(arg, arg + 1)
+        elif kind == N.NODE_IN:
+            span = range(arg, arg + n)
+        else:
+            continue
+        mask = (1 << (8 * widths[col])) - 1
+        for i in span:
+            out[i] = args[i] & mask
+    return out
+
+
+@pytest.mark.parametrize("key", list(GROUPS), ids=[GROUPS[k][0]["test"].split(".")[0] + f"[{len(GROUPS[k])}]" for k in GROUPS])
+def test_cpp_adapter_against_mock_device(results, key):
+    recs = GROUPS[key]
+    if key not in results:
+        pytest.skip("result too large for a JSON job file")
+    out = results[key]
+    assert "fatal" not in out, out.get("fatal")
+    for rec, got in zip(recs, out["results"]):
+        assert "error" not in got, (rec["test"], got.get("error"))
+        q = rec["query"]
+        # ---- rows and QueryStats == the reference's ----
+        ordered = bool(q.get("sort"))
+        if (q.get("limit") or q.get("skip")) and not ordered:
+            assert len(got["rows"]) == len(rec["rows"]), rec["test"]     # only the count is defined
+        elif ordered:
+            assert got["rows"] == rec["rows"] or sorted(got["rows"]) == sorted(rec["rows"]), rec["test"]
+        else:
+            assert sorted(got["rows"]) == sorted(rec["rows"]), rec["test"]
+        for k, val in rec["stats"].items():
+            assert got["stats"][k] == val, (rec["test"], k, got["stats"][k], val)
+        # ---- the plan the C++ adapter lowered == the Python mirror's ----
+        want, widths, schema = mirror_plan(rec)
+        plan = got["plan"]
+        assert got["schema"]["cols"] == schema, rec["test"]
+        assert plan["nodes"] == want["nodes"], rec["test"]
+        assert masked_args(plan["nodes"], plan["args"], widths) == masked_args(want["nodes"], want["args"], widths), rec["test"]
+        assert plan["hnodes"] == want["hnodes"], rec["test"]
+        assert masked_args(plan["hnodes"], plan["hargs"], widths) == masked_args(want["hnodes"], want["hargs"], widths), rec["test"]
+        for f in ("keys", "metric_cols", "need_hidden_count", "flags", "sort_col", "sort_descending", "top_k"):
+            assert plan[f] == want[f], (rec["test"], f, plan[f], want[f])
