@@ -659,6 +659,7 @@ def run_select(table_conf, segments, dicts, query, hidden_counts=None):
         raise RuntimeError("reference JIT compile error: 'struct Metrics' has no member named '_count'")
     stats = {"scanned_segments": 0, "scanned_recs": 0, "aggregated_recs": 0, "output_recs": 0}
     rows = []
+    picked = []   # (segment, tuple) of every row sent, in output order: what a device scan hands to the host
     if query.get("header"):
         rows.append([c.name for c, _, _ in sel])
     row_index = 0
@@ -698,10 +699,11 @@ def run_select(table_conf, segments, dicts, query, hidden_counts=None):
                 else:
                     row.append(_fmt_num(seg[c.name][i], c.type))
             rows.append(row)
+            picked.append((si, i))
             stats["output_recs"] += 1
             if limit > 0 and stats["output_recs"] >= limit:
                 break   # leaves the tuple loop only (scan.cc:161): the next segment is still visited
-    return {"rows": rows, "stats": stats}
+    return {"rows": rows, "stats": stats, "picked": picked}
 
 
 def run_search(table_conf, segments, dicts, query):

@@ -8,8 +8,11 @@
 // The mock computes nothing: it is not a CPU path of the product and nothing under viyadb_b200/ links it.
 //
 // job = {"table": {...}, "dicts": {"<string dim>": ["__exceeded", "v1", ...]}, "rollup_ts": N, "state_dir": "...",
-//        "cases": [{"query": {...}, "ngroups": n, "keys": [[bits...] per selected dimension], "accs": [[bits...] per
-//                   selected metric], "hidden": [counts...] | null, "scanned_recs": r, "scanned_segments": s}]}
+//        "cases": [{"query": {...}, "scanned_recs": r, "scanned_segments": s,
+//                   aggregate: "ngroups": n, "keys": [[bits...] per selected dimension], "accs": [[bits...] per selected
+//                              metric], "hidden": [counts...] | null
+//                   select:    "nrows": n, "cells": [[bits of the n rows to send] per SCHEMA column (hidden count last)]
+//                   search:    "seg_offsets": [...], "codes": [...], "first_row": [...]   (vgpu_search_view)}]}
 #include "db/database.h"
 #include "db/dictionary.h"
 #include "db/table.h"
@@ -34,14 +37,22 @@ namespace query = viya::query;
 struct vgpu_ctx { int dummy; };
 struct vgpu_table { json schema; };
 struct vgpu_result { vgpu_result_view view; };
-struct vgpu_rows { int dummy; };
-struct vgpu_search { int dummy; };
+struct vgpu_rows {
+  std::vector<std::vector<char>> bufs;
+  std::vector<const void *> ptrs;
+  vgpu_rows_view view;
+};
+struct vgpu_search { vgpu_search_view view; };
 
 namespace {
 vgpu_ctx g_ctx;
 json g_plan;                 // the last plan vgpu_query_agg saw
 vgpu_result_view g_canned;   // what it answers
 json g_schema;
+std::vector<std::vector<uint64_t>> g_sel_cells;   // select: per schema column, the widened cells of the rows to send
+uint64_t g_sel_nrows = 0;
+std::vector<uint64_t> g_srch_offsets{0}, g_srch_codes;   // search: what the device hands back
+std::vector<uint32_t> g_srch_rows;
 
 json nodes_json(const vgpu_pred_node *nodes, uint32_t n) {
   json a = json::array();
@@ -93,13 +104,54 @@ int vgpu_query_agg(vgpu_table *, const vgpu_plan *p, vgpu_result **out) {
 }
 int vgpu_result_get(const vgpu_result *r, vgpu_result_view *view) { *view = r->view; return VGPU_OK; }
 void vgpu_result_free(vgpu_result *r) { delete r; }
-// select / search: referenced by the visitor's vtable; the aggregate cases of this harness never reach them
-int vgpu_query_select(vgpu_table *, const vgpu_rows_plan *, vgpu_rows **) { return VGPU_ERR_UNSUPPORTED; }
-int vgpu_rows_get(const vgpu_rows *, vgpu_rows_view *) { return VGPU_ERR_UNSUPPORTED; }
-void vgpu_rows_free(vgpu_rows *) {}
-int vgpu_query_search(vgpu_table *, const vgpu_search_plan *, vgpu_search **) { return VGPU_ERR_UNSUPPORTED; }
-int vgpu_search_get(const vgpu_search *, vgpu_search_view *) { return VGPU_ERR_UNSUPPORTED; }
-void vgpu_search_free(vgpu_search *) {}
+// select: the rows the reference would send, as raw cells of the requested schema columns (vgpu.h: BITSET cells are
+// cardinalities, uint64; the hidden count is uint64)
+int vgpu_query_select(vgpu_table *, const vgpu_rows_plan *p, vgpu_rows **out) {
+  json args = json::array(), cols = json::array();
+  for (uint32_t i = 0; i < p->nargs; ++i) args.push_back(p->args[i]);
+  for (uint32_t i = 0; i < p->ncols; ++i) cols.push_back(p->cols[i]);
+  g_plan = {{"nodes", nodes_json(p->nodes, p->nnodes)}, {"args", args}, {"cols", cols}, {"skip", p->skip}, {"limit", p->limit}};
+  auto *r = new vgpu_rows();
+  r->bufs.resize(p->ncols);
+  r->ptrs.resize(p->ncols);
+  for (uint32_t i = 0; i < p->ncols; ++i) {
+    const uint32_t c = p->cols[i];
+    const uint32_t kind = g_schema["cols"][c][0].get<uint32_t>(), type = g_schema["cols"][c][1].get<uint32_t>();
+    static const uint32_t widths[10] = {1, 2, 4, 8, 1, 2, 4, 8, 4, 8};
+    const uint32_t w = (kind == VGPU_METRIC_BITSET || kind == VGPU_METRIC_HIDDEN_COUNT) ? 8u : widths[type];
+    r->bufs[i].resize(g_sel_nrows * w + 8);
+    for (uint64_t row = 0; row < g_sel_nrows; ++row) std::memcpy(r->bufs[i].data() + row * w, &g_sel_cells[c][row], w);
+    r->ptrs[i] = r->bufs[i].data();
+  }
+  r->view = vgpu_rows_view{};
+  r->view.nrows = g_sel_nrows;
+  r->view.ncols = p->ncols;
+  r->view.cells = r->ptrs.data();
+  r->view.scanned_recs = g_canned.scanned_recs;
+  r->view.scanned_segments = g_canned.scanned_segments;
+  *out = r;
+  return VGPU_OK;
+}
+int vgpu_rows_get(const vgpu_rows *r, vgpu_rows_view *view) { *view = r->view; return VGPU_OK; }
+void vgpu_rows_free(vgpu_rows *r) { delete r; }
+// search: per processed segment the distinct values of the dimension among the passing rows with their first rows
+int vgpu_query_search(vgpu_table *, const vgpu_search_plan *p, vgpu_search **out) {
+  json args = json::array();
+  for (uint32_t i = 0; i < p->nargs; ++i) args.push_back(p->args[i]);
+  g_plan = {{"nodes", nodes_json(p->nodes, p->nnodes)}, {"args", args}, {"col", p->col}};
+  auto *r = new vgpu_search();
+  r->view = vgpu_search_view{};
+  r->view.nsegments = (uint32_t)(g_srch_offsets.size() - 1);
+  r->view.seg_offsets = g_srch_offsets.data();
+  r->view.codes = g_srch_codes.data();
+  r->view.first_row = g_srch_rows.data();
+  r->view.scanned_recs = g_canned.scanned_recs;
+  r->view.scanned_segments = g_canned.scanned_segments;
+  *out = r;
+  return VGPU_OK;
+}
+int vgpu_search_get(const vgpu_search *r, vgpu_search_view *view) { *view = r->view; return VGPU_OK; }
+void vgpu_search_free(vgpu_search *r) { delete r; }
 }  // extern "C"
 
 // ---------------------------------------------------------------------------------------------
@@ -149,43 +201,55 @@ int main(int argc, char **argv) {
         query::QueryFactory factory;
         std::unique_ptr<query::Query> qq(factory.Create(util::Config(c["query"]), database));
         auto *aq = dynamic_cast<query::AggregateQuery *>(qq.get());
-        if (aq == nullptr) throw std::runtime_error("not an aggregate query");
-        const uint64_t n = c["ngroups"].get<uint64_t>();
-        auto &dim_cols = aq->dimension_cols();
-        auto &metric_cols = aq->metric_cols();
-        std::vector<std::vector<char>> kbuf(dim_cols.size()), abuf(metric_cols.size());
-        std::vector<const void *> kptr(dim_cols.size()), aptr(metric_cols.size());
-        for (size_t k = 0; k < dim_cols.size(); ++k) {
-          const uint32_t w = (uint32_t)dim_cols[k].dim()->num_type().size();
-          kbuf[k].resize(n * w + 8);
-          for (uint64_t g = 0; g < n; ++g) {
-            uint64_t bits = c["keys"][k][g].get<uint64_t>();
-            std::memcpy(kbuf[k].data() + g * w, &bits, w);
-          }
-          kptr[k] = kbuf[k].data();
-        }
-        for (size_t m = 0; m < metric_cols.size(); ++m) {
-          auto metric = metric_cols[m].metric();
-          const uint32_t w = metric->agg_type() == db::Metric::AggregationType::BITSET ? 8u : (uint32_t)metric->num_type().size();
-          abuf[m].resize(n * w + 8);
-          for (uint64_t g = 0; g < n; ++g) {
-            uint64_t bits = c["accs"][m][g].get<uint64_t>();
-            std::memcpy(abuf[m].data() + g * w, &bits, w);
-          }
-          aptr[m] = abuf[m].data();
-        }
+        std::vector<std::vector<char>> kbuf, abuf;
+        std::vector<const void *> kptr, aptr;
         std::vector<uint64_t> hidden;
-        if (!c["hidden"].is_null()) hidden = c["hidden"].get<std::vector<uint64_t>>();
         g_canned = vgpu_result_view{};
-        g_canned.ngroups = n;
-        g_canned.nkeys = (uint32_t)dim_cols.size();
-        g_canned.nmetrics = (uint32_t)metric_cols.size();
-        g_canned.keys = kptr.data();
-        g_canned.accs = aptr.data();
-        g_canned.hidden_count = hidden.empty() ? nullptr : hidden.data();
-        g_canned.aggregated_recs = n;
         g_canned.scanned_recs = c.value("scanned_recs", (uint64_t)0);
         g_canned.scanned_segments = c.value("scanned_segments", (uint64_t)0);
+        if (aq != nullptr) {
+          const uint64_t n = c["ngroups"].get<uint64_t>();
+          auto &dim_cols = aq->dimension_cols();
+          auto &metric_cols = aq->metric_cols();
+          kbuf.resize(dim_cols.size()); abuf.resize(metric_cols.size());
+          kptr.resize(dim_cols.size()); aptr.resize(metric_cols.size());
+          for (size_t k = 0; k < dim_cols.size(); ++k) {
+            const uint32_t w = (uint32_t)dim_cols[k].dim()->num_type().size();
+            kbuf[k].resize(n * w + 8);
+            for (uint64_t g = 0; g < n; ++g) {
+              uint64_t bits = c["keys"][k][g].get<uint64_t>();
+              std::memcpy(kbuf[k].data() + g * w, &bits, w);
+            }
+            kptr[k] = kbuf[k].data();
+          }
+          for (size_t m = 0; m < metric_cols.size(); ++m) {
+            auto metric = metric_cols[m].metric();
+            const uint32_t w = metric->agg_type() == db::Metric::AggregationType::BITSET ? 8u : (uint32_t)metric->num_type().size();
+            abuf[m].resize(n * w + 8);
+            for (uint64_t g = 0; g < n; ++g) {
+              uint64_t bits = c["accs"][m][g].get<uint64_t>();
+              std::memcpy(abuf[m].data() + g * w, &bits, w);
+            }
+            aptr[m] = abuf[m].data();
+          }
+          if (!c["hidden"].is_null()) hidden = c["hidden"].get<std::vector<uint64_t>>();
+          g_canned.ngroups = n;
+          g_canned.nkeys = (uint32_t)dim_cols.size();
+          g_canned.nmetrics = (uint32_t)metric_cols.size();
+          g_canned.keys = kptr.data();
+          g_canned.accs = aptr.data();
+          g_canned.hidden_count = hidden.empty() ? nullptr : hidden.data();
+          g_canned.aggregated_recs = n;
+        } else if (dynamic_cast<query::SelectQuery *>(qq.get()) != nullptr) {
+          g_sel_nrows = c["nrows"].get<uint64_t>();
+          g_sel_cells = c["cells"].get<std::vector<std::vector<uint64_t>>>();
+        } else if (dynamic_cast<query::SearchQuery *>(qq.get()) != nullptr) {
+          g_srch_offsets = c["seg_offsets"].get<std::vector<uint64_t>>();
+          g_srch_codes = c["codes"].get<std::vector<uint64_t>>();
+          g_srch_rows = c["first_row"].get<std::vector<uint32_t>>();
+        } else {
+          throw std::runtime_error("unsupported query type");
+        }
         g_plan = json();
         vgpu_host::GpuQueryRunner runner(database, output, &g_ctx, bindings);
         qq->Accept(runner);

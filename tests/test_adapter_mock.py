@@ -196,3 +196,138 @@ def test_cpp_adapter_against_mock_device(results, key):
         assert masked_args(plan["hnodes"], plan["hargs"], widths) == masked_args(want["hnodes"], want["hargs"], widths), rec["test"]
         for f in ("keys", "metric_cols", "need_hidden_count", "flags", "sort_col", "sort_descending", "top_k"):
             assert plan[f] == want[f], (rec["test"], f, plan[f], want[f])
+
+
+# ------------------------------------------------------------------------------------------------
+# select / search through the same mock
+# ------------------------------------------------------------------------------------------------
+SEL_RECS = [r for name in ("ref_gtest_select.jsonl", "ref_select_scenarios.jsonl", "ref_fuzz_select_scenarios.jsonl")
+            for r in G.records(name) if "error" not in r and "seg" in r]
+SEL_GROUPS = collections.OrderedDict()
+for r in SEL_RECS:
+    SEL_GROUPS.setdefault((json.dumps(r["table"], sort_keys=True), r["seg"], r.get("rollup_ts")), []).append(r)
+
+
+def float_search(rec):
+    """search on a floating-point dimension: the adapter delegates it to the stock runner (the device's first-row table
+    is keyed by integer values) — nothing to mock"""
+    q = rec["query"]
+    if q["type"] != "search":
+        return False
+    d = next(d for d in rec["table"]["dimensions"] if d["name"] == q["dimension"])
+    return d.get("type") in ("float", "double")
+
+
+def select_case(rec, segs, dicts, hidden, dims, mets):
+    q = rec["query"]
+    ocols = {c.name: c for c in dims + mets}
+    flt = viya_oracle.make_filter(q.get("filter"))
+    case = {"query": q}
+    if q["type"] == "select":
+        res = viya_oracle.run_select(rec["table"], segs, dicts, q, hidden_counts=hidden)
+        picked = res["picked"]
+        cells = []
+        for c in dims + mets:
+            col = []
+            for si, i in picked:
+                if c.is_dim or c.agg != "bitset":
+                    col.append(int(widen(np.asarray(segs[si][c.name][i:i + 1]))[0]))
+                else:
+                    offsets, values = segs[si][c.name]
+                    col.append(len(set(np.asarray(values[int(offsets[i]):int(offsets[i + 1])]).tolist())))
+            cells.append(col)
+        if hidden is not None and any(h is not None for h in hidden):
+            cells.append([int(hidden[si][i]) for si, i in picked])
+        case.update({"nrows": len(picked), "cells": cells})
+    else:
+        # what vgpu_query_search returns: per processed segment the distinct values among the passing rows with the
+        # first row that holds each, ascending by that row
+        d = ocols[q["dimension"]]
+        offsets, codes, rows = [0], [], []
+        for seg in segs:
+            n = viya_oracle._seg_rows(seg, dims + mets)
+            if not viya_oracle.process_segment(flt, seg, n, ocols, dicts):
+                continue
+            if n:
+                passing = np.nonzero(viya_oracle.eval_filter(flt, seg, n, ocols, dicts))[0]
+                vals = widen(np.asarray(seg[d.name])[passing])
+                seen = set()
+                for r_, v_ in zip(passing.tolist(), vals.tolist()):
+                    if v_ not in seen:
+                        seen.add(v_)
+                        codes.append(v_)
+                        rows.append(r_)
+            offsets.append(len(codes))
+        res = viya_oracle.run_search(rec["table"], segs, dicts, q)
+        case.update({"seg_offsets": offsets, "codes": codes, "first_row": rows})
+    case["scanned_recs"] = res["stats"]["scanned_recs"]
+    case["scanned_segments"] = res["stats"]["scanned_segments"]
+    return case
+
+
+def run_select_group(cli, key):
+    recs = [r for r in SEL_GROUPS[key] if not float_search(r)]
+    hdr, _ = vdb_mod.read_dump(G.seg_path(recs[0]["seg"]))
+    _, segs, dicts, hidden = viya_oracle.read_dump(G.seg_path(recs[0]["seg"]))
+    dims, mets = viya_oracle.parse_schema(recs[0]["table"])
+    job = {"table": recs[0]["table"], "dicts": hdr["dicts"], "state_dir": STATE,
+           "cases": [select_case(r, segs, dicts, hidden, dims, mets) for r in recs]}
+    with tempfile.NamedTemporaryFile("w", suffix=".json", delete=False) as f:
+        json.dump(job, f)
+        path = f.name
+    try:
+        p = subprocess.run([cli, path], capture_output=True, text=True, timeout=600,
+                           cwd=os.path.join(ROOT, "oracle", "_ref", "root", "build"))
+    finally:
+        os.remove(path)
+    if p.returncode != 0 or not p.stdout.strip():
+        return {"fatal": (p.stdout[-500:], p.stderr[-500:])}
+    return json.loads(p.stdout.strip().splitlines()[-1])
+
+
+@pytest.fixture(scope="module")
+def select_results(cli):
+    from concurrent.futures import ThreadPoolExecutor
+    keys = [k for k in SEL_GROUPS if any(not float_search(r) for r in SEL_GROUPS[k])]
+    os.makedirs(STATE, exist_ok=True)
+    with ThreadPoolExecutor(max_workers=os.cpu_count() or 1) as ex:
+        outs = list(ex.map(lambda k: run_select_group(cli, k), keys))
+    return dict(zip(keys, outs))
+
+
+@pytest.mark.parametrize("key", list(SEL_GROUPS), ids=[SEL_GROUPS[k][0]["test"].split(".")[0] + f"[{len(SEL_GROUPS[k])}]" for k in SEL_GROUPS])
+def test_cpp_adapter_select_search_against_mock_device(select_results, key):
+    if key not in select_results:
+        pytest.skip("only searches on floating-point dimensions: delegated to the stock runner")
+    out = select_results[key]
+    assert "fatal" not in out, out.get("fatal")
+    recs = [r for r in SEL_GROUPS[key] if not float_search(r)]
+    for rec, got in zip(recs, out["results"]):
+        assert "error" not in got, (rec["test"], got.get("error"))
+        assert got["rows"] == rec["rows"], rec["test"]          # select / search output order is defined
+        for k, val in rec["stats"].items():
+            assert got["stats"][k] == val, (rec["test"], k, got["stats"][k], val)
+        # ---- the predicate and the request the C++ adapter lowered == the Python mirror's ----
+        db = v.Database({"tables": [rec["table"]]}, device=None)
+        t = db.get_table(rec["table"]["name"])
+        hdr, _ = vdb_mod.read_dump(G.seg_path(rec["seg"]))
+        for d in t.dimensions:
+            if d.kind == N.DIM_STRING:
+                d.dict.c2v = list(hdr["dicts"][d.name])
+                d.dict.v2c = {s: i for i, s in enumerate(d.dict.c2v)}
+        query = QueryFactory.create(rec["query"], db)
+        packer, _, _ = GpuQueryRunner(db, MemoryRowOutput())._predicate(query)
+        widths = [N.TYPE_WIDTH[c.type] for c in t.dimensions + t.metrics] + [8]
+        plan = got["plan"]
+        want_nodes = [list(nd) for nd in packer.nodes]
+        assert plan["nodes"] == want_nodes, rec["test"]
+        assert masked_args(plan["nodes"], plan["args"], widths) == masked_args(want_nodes, packer.args, widths), rec["test"]
+        if rec["query"]["type"] == "select":
+            want_cols = [t.schema_index(dc.dim) for dc in query.dimension_cols] + [t.schema_index(mc.metric) for mc in query.metric_cols]
+            has_avg = any(mc.metric.agg == N.AGG_AVG for mc in query.metric_cols)
+            has_count = any(mc.metric.agg == N.AGG_COUNT for mc in query.metric_cols)
+            if has_avg and not has_count:
+                want_cols.append(t.hidden_count_index)
+            assert plan["cols"] == want_cols and plan["skip"] == query.skip and plan["limit"] == query.limit, rec["test"]
+        else:
+            assert plan["col"] == t.schema_index(query.dimension), rec["test"]
