@@ -13,10 +13,13 @@
 //                              metric], "hidden": [counts...] | null
 //                   select:    "nrows": n, "cells": [[bits of the n rows to send] per SCHEMA column (hidden count last)]
 //                   search:    "seg_offsets": [...], "codes": [...], "first_row": [...]   (vgpu_search_view)}]}
+// or     {"table": ..., "state_dir": ..., "sync": [{"rows": [[...]], "notify": "none" | "epoch" | "mark"}, ...]}: every
+//        step ingests its rows through the reference's own loader, notifies the binding and calls GpuTableBinding::Sync()
 #include "db/database.h"
 #include "db/dictionary.h"
 #include "db/table.h"
 #include "gpu_query_runner.h"
+#include "input/simple.h"
 #include "query/output.h"
 #include "query/query.h"
 #include "query/runner.h"
@@ -24,6 +27,7 @@
 #include <cstring>
 #include <fstream>
 #include <iostream>
+#include <map>
 #include <nlohmann/json.hpp>
 
 using json = nlohmann::json;
@@ -35,7 +39,19 @@ namespace query = viya::query;
 // the mock device
 // ---------------------------------------------------------------------------------------------
 struct vgpu_ctx { int dummy; };
-struct vgpu_table { json schema; };
+// the mock's "HBM": what put / update calls have written, per segment and schema column (fixed-width cells as bytes; a
+// BITSET column as CSR offsets + id bytes)
+struct ShadowSeg {
+  uint64_t nrows = 0;
+  std::vector<std::vector<uint8_t>> cols;
+  std::vector<std::vector<uint64_t>> offsets;
+};
+struct vgpu_table {
+  json schema;
+  std::vector<uint32_t> kind, width;   // per schema column
+  std::map<uint32_t, ShadowSeg> segs;
+  json calls = json::array();          // the put / update calls seen, in order
+};
 struct vgpu_result { vgpu_result_view view; };
 struct vgpu_rows {
   std::vector<std::vector<char>> bufs;
@@ -49,6 +65,7 @@ vgpu_ctx g_ctx;
 json g_plan;                 // the last plan vgpu_query_agg saw
 vgpu_result_view g_canned;   // what it answers
 json g_schema;
+vgpu_table *g_table = nullptr;   // the last table created (the sync mode looks into its shadow store)
 std::vector<std::vector<uint64_t>> g_sel_cells;   // select: per schema column, the widened cells of the rows to send
 uint64_t g_sel_nrows = 0;
 std::vector<uint64_t> g_srch_offsets{0}, g_srch_codes;   // search: what the device hands back
@@ -69,13 +86,51 @@ int vgpu_table_create(vgpu_ctx *, const vgpu_schema *schema, vgpu_table **out) {
   for (uint32_t c = 0; c < schema->ncols; ++c)
     cols.push_back({schema->cols[c].kind, schema->cols[c].type, schema->cols[c].agg, schema->cols[c].lit_type});
   t->schema = {{"ncols", schema->ncols}, {"ndims", schema->ndims}, {"segment_size", schema->segment_size}, {"cols", cols}};
+  static const uint32_t widths[10] = {1, 2, 4, 8, 1, 2, 4, 8, 4, 8};
+  for (uint32_t c = 0; c < schema->ncols; ++c) {
+    t->kind.push_back(schema->cols[c].kind);
+    t->width.push_back(widths[schema->cols[c].type]);
+  }
   g_schema = t->schema;
+  g_table = t;
   *out = t;
   return VGPU_OK;
 }
 void vgpu_table_free(vgpu_table *t) { delete t; }
-int vgpu_segment_put_async(vgpu_table *, uint32_t, uint64_t, const void *const *) { return VGPU_OK; }
-int vgpu_segment_update(vgpu_table *, uint32_t, uint64_t, uint64_t, const void *const *) { return VGPU_OK; }
+int vgpu_segment_put_async(vgpu_table *t, uint32_t seg, uint64_t nrows, const void *const *ptrs) {
+  t->calls.push_back({"put", seg, nrows});
+  ShadowSeg &sh = t->segs[seg];
+  sh = ShadowSeg();
+  sh.nrows = nrows;
+  sh.cols.resize(t->kind.size());
+  sh.offsets.resize(t->kind.size());
+  for (size_t c = 0; c < t->kind.size(); ++c) {
+    if (t->kind[c] == VGPU_METRIC_BITSET) {
+      auto *csr = static_cast<const vgpu_bitset_csr *>(ptrs[c]);
+      if (csr->offsets) sh.offsets[c].assign(csr->offsets, csr->offsets + nrows + 1);
+      const uint8_t *v = static_cast<const uint8_t *>(csr->values);
+      sh.cols[c].assign(v, v + csr->nvalues * t->width[c]);
+    } else {
+      const uint8_t *v = static_cast<const uint8_t *>(ptrs[c]);
+      sh.cols[c].assign(v, v + nrows * t->width[c]);
+    }
+  }
+  return VGPU_OK;
+}
+int vgpu_segment_update(vgpu_table *t, uint32_t seg, uint64_t row_begin, uint64_t nrows, const void *const *ptrs) {
+  t->calls.push_back({"update", seg, row_begin, nrows});
+  auto it = t->segs.find(seg);
+  if (it == t->segs.end() || row_begin > it->second.nrows) return VGPU_ERR_STATE;
+  ShadowSeg &sh = it->second;
+  for (size_t c = 0; c < t->kind.size(); ++c) {
+    if (t->kind[c] == VGPU_METRIC_BITSET) return VGPU_ERR_UNSUPPORTED;
+    const uint64_t w = t->width[c];
+    if (sh.cols[c].size() < (row_begin + nrows) * w) sh.cols[c].resize((row_begin + nrows) * w);
+    std::memcpy(sh.cols[c].data() + row_begin * w, ptrs[c], nrows * w);
+  }
+  sh.nrows = std::max(sh.nrows, row_begin + nrows);
+  return VGPU_OK;
+}
 int vgpu_table_sync(vgpu_table *) { return VGPU_OK; }
 int vgpu_table_invalidate(vgpu_table *, uint32_t) { return VGPU_OK; }
 int vgpu_host_pin(vgpu_ctx *, const void *, size_t) { return VGPU_OK; }
@@ -155,6 +210,99 @@ void vgpu_search_free(vgpu_search *r) { delete r; }
 }  // extern "C"
 
 // ---------------------------------------------------------------------------------------------
+// sync mode: GpuTableBinding::Sync() against the live store of the reference. Rows go through the
+// reference's own ingest (upserts merge into existing tuples IN PLACE, src/codegen/db/upsert.cc:386-393); after every
+// Sync() the mock's shadow of "HBM" must equal the live segments, cell for cell.
+// ---------------------------------------------------------------------------------------------
+namespace {
+void load_rows(db::Table *table, const json &rows) {
+  struct L : viya::input::SimpleLoader {
+    using viya::input::SimpleLoader::SimpleLoader;
+    void Before() { BeforeLoad(); }
+    void After() { AfterLoad(); }
+  } l(*table);
+  l.Before();
+  for (auto &r : rows) {
+    std::vector<std::string> row = r.get<std::vector<std::string>>();
+    l.Load(row);
+  }
+  l.After();
+}
+
+// cells of the live store that differ from the shadow (0 == the resident copy is current)
+json compare_with_live(db::Table *table, vgpu_host::SegmentAccess &access) {
+  uint64_t diff_cells = 0, rows = 0;
+  bool missing = false;
+  const size_t ndims = table->dimensions().size(), nmetrics = table->metrics().size();
+  auto segments = table->store()->segments_copy();
+  for (size_t si = 0; si < segments.size(); ++si) {
+    const size_t size = segments[si]->size();
+    rows += size;
+    auto it = g_table->segs.find((uint32_t)si);
+    if (it == g_table->segs.end() || it->second.nrows != size) { missing = true; continue; }
+    const ShadowSeg &sh = it->second;
+    std::vector<const void *> dims(ndims), metrics(nmetrics);
+    std::vector<uint64_t> stats(2 * ndims + 2);
+    const void *hidden = nullptr;
+    access.columns()(segments[si], dims.data(), metrics.data(), &hidden, stats.data());
+    size_t c = 0;
+    auto cmp = [&](const void *live, size_t col) {
+      const uint64_t w = g_table->width[col];
+      const uint8_t *a = static_cast<const uint8_t *>(live);
+      for (size_t r = 0; r < size; ++r)
+        if (std::memcmp(a + r * w, sh.cols[col].data() + r * w, w) != 0) ++diff_cells;
+    };
+    for (size_t d = 0; d < ndims; ++d, ++c) cmp(dims[d], c);
+    for (auto *m : table->metrics()) {
+      if (m->agg_type() != db::Metric::AggregationType::BITSET) { cmp(metrics[m->index()], c++); continue; }
+      std::vector<uint64_t> offsets(size + 1);
+      const uint64_t total = access.bitset()(segments[si], m->index(), size, offsets.data(), nullptr);
+      std::vector<uint64_t> wide(total + 1);
+      access.bitset()(segments[si], m->index(), size, offsets.data(), wide.data());
+      const uint64_t w = g_table->width[c];
+      if (sh.offsets[c] != offsets || sh.cols[c].size() != total * w) { ++diff_cells; ++c; continue; }
+      for (uint64_t i = 0; i < total; ++i) {
+        uint64_t v = 0;
+        std::memcpy(&v, sh.cols[c].data() + i * w, w);
+        if (v != wide[i]) ++diff_cells;
+      }
+      ++c;
+    }
+    if (access.has_hidden_count()) cmp(hidden, c);
+  }
+  return {{"segments", segments.size()}, {"rows", rows}, {"differing_cells", diff_cells}, {"missing_or_short_segments", missing}};
+}
+
+json run_sync(const json &job, db::Database &database, db::Table *table) {
+  json out = json::array();
+  vgpu_host::GpuTableBinding binding(&g_ctx, *table);
+  vgpu_host::SegmentAccess access(*table);
+  for (auto &step : job["sync"]) {
+    std::vector<size_t> sizes_before;
+    for (auto *sgm : table->store()->segments_copy()) sizes_before.push_back(sgm->size());
+    load_rows(table, step["rows"]);
+    const std::string notify = step.value("notify", std::string("none"));
+    if (notify == "mark") {
+      // exact notifications, as an upsert hook would give them (here: every row that existed before the batch may have
+      // been updated in place); appended rows are found by the binding itself
+      for (size_t si = 0; si < sizes_before.size(); ++si) vgpu_host::GpuTableBinding::MarkDirty(table, si, 0, sizes_before[si]);
+    } else if (notify == "epoch") {
+      vgpu_host::IngestEpoch::Bump();
+    }
+    g_table->calls = json::array();
+    const uint64_t partial_before = binding.partial_updates();
+    binding.Sync();
+    json r = compare_with_live(table, access);
+    r["calls"] = g_table->calls;
+    r["partial_updates"] = binding.partial_updates() - partial_before;
+    r["notify"] = notify;
+    out.push_back(r);
+  }
+  return out;
+}
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------
 int main(int argc, char **argv) {
   if (argc < 2) {
     std::cerr << "usage: adapter_mock_cli <job.json>\n";
@@ -179,6 +327,7 @@ int main(int argc, char **argv) {
     for (auto *dim : table->dimensions()) {
       if (dim->dim_type() != db::Dimension::DimType::STRING) continue;
       auto dict = static_cast<const db::StrDimension *>(dim)->dict();
+      if (!job.count("dicts")) break;   // sync mode: the reference's own ingest fills the dictionaries
       auto &vals = job["dicts"][dim->name()];
       for (size_t i = 1; i < vals.size(); ++i) {
         const std::string v = vals[i].get<std::string>();
@@ -191,6 +340,11 @@ int main(int argc, char **argv) {
         default: reinterpret_cast<db::DictImpl<uint64_t> *>(dict->v2c())->insert(std::make_pair(v, (uint64_t)code)); break;
         }
       }
+    }
+    if (job.count("sync")) {
+      out["sync"] = run_sync(job, database, table);
+      std::cout << out.dump() << std::endl;
+      return 0;
     }
     vgpu_host::GpuQueryRunner::Bindings bindings;
     out["results"] = json::array();

@@ -331,3 +331,80 @@ def test_cpp_adapter_select_search_against_mock_device(select_results, key):
             assert plan["cols"] == want_cols and plan["skip"] == query.skip and plan["limit"] == query.limit, rec["test"]
         else:
             assert plan["col"] == t.schema_index(query.dimension), rec["test"]
+
+
+# ------------------------------------------------------------------------------------------------
+# incremental segment sync: GpuTableBinding::Sync() against the reference's live store
+# ------------------------------------------------------------------------------------------------
+def run_sync(cli, table, steps):
+    """rows go through the reference's own ingest; after every Sync() the mock's shadow of HBM is compared with the live
+    segments cell by cell. JIT cache: oracle/_ref/state, pre-warmed for the scenario tables by __graft_entry__.build()."""
+    job = {"table": table, "state_dir": os.path.join(ROOT, "oracle", "_ref", "state"), "sync": steps}
+    with tempfile.NamedTemporaryFile("w", suffix=".json", delete=False) as f:
+        json.dump(job, f)
+        path = f.name
+    try:
+        p = subprocess.run([cli, path], capture_output=True, text=True, timeout=600,
+                           cwd=os.path.join(ROOT, "oracle", "_ref", "root", "build"))
+    finally:
+        os.remove(path)
+    assert p.returncode == 0 and p.stdout.strip(), (p.stdout[-500:], p.stderr[-500:])
+    out = json.loads(p.stdout.strip().splitlines()[-1])
+    assert "fatal" not in out, out.get("fatal")
+    return out["sync"]
+
+
+def scenario(name):
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+    import scenarios
+    return next(s for s in scenarios.SCENARIOS if s["name"] == name)
+
+
+@pytest.mark.parametrize("notify", ["epoch", "mark", "none"])
+def test_sync_follows_in_place_upserts(cli, notify):
+    """A second batch into the SAME dimension tuples updates metric cells in place (upsert.cc:386-393) and appends one new
+    tuple. With a notification (coarse epoch, or exact dirty ranges) the resident copy is current after Sync(); "mark"
+    moves only the dirty + appended rows (one vgpu_segment_update), "epoch" the whole segment. Without any notification the
+    binding only sees the appended row — the in-place updates stay stale: that is why the integration has its one line in
+    Loader::AfterLoad (INTEGRATION.md)."""
+    sc = scenario("inapp")
+    batch2 = [r[:3] + [str(float(r[3]) * 3 + 1)] for r in sc["rows"]] + [["IL", "gift", "20141114", "7.5"]]
+    first, second = run_sync(cli, sc["table"], [{"rows": sc["rows"], "notify": "none"}, {"rows": batch2, "notify": notify}])
+    n1 = first["rows"]
+    assert first["calls"] == [["put", 0, n1]] and first["differing_cells"] == 0 and not first["missing_or_short_segments"]
+    assert second["rows"] == n1 + 1 and not second["missing_or_short_segments"]
+    if notify == "epoch":
+        assert second["calls"] == [["put", 0, n1 + 1]] and second["differing_cells"] == 0
+    elif notify == "mark":
+        assert second["calls"] == [["update", 0, 0, n1 + 1]] and second["partial_updates"] == 1
+        assert second["differing_cells"] == 0
+    else:
+        assert second["calls"] == [["update", 0, n1, 1]]          # the appended row only
+        assert second["differing_cells"] > 0                       # the updated metric cells were never re-uploaded
+
+
+def test_sync_appends_across_ragged_segments(cli):
+    """segment_size 2: appended rows fill the last segment and open new ones; rows that merge into existing tuples bump
+    their count in place. Exact dirty ranges: every existing segment gets one update, new segments one put each."""
+    sc = scenario("prune_quirk")
+    batch2 = [["11", "c"], ["30", "d"], ["31", "e"], ["1", "a"]]       # two upserts into existing tuples, two new tuples
+    first, second = run_sync(cli, sc["table"], [{"rows": sc["rows"], "notify": "none"}, {"rows": batch2, "notify": "mark"}])
+    assert [c[0] for c in first["calls"]] == ["put"] * first["segments"] and first["differing_cells"] == 0
+    assert second["rows"] == first["rows"] + 2 and second["differing_cells"] == 0 and not second["missing_or_short_segments"]
+    kinds = [c[0] for c in second["calls"]]
+    assert kinds.count("update") == first["segments"] and kinds.count("put") == second["segments"] - first["segments"]
+    # a third batch with nothing new and no notification: nothing to move
+    third = run_sync(cli, sc["table"], [{"rows": sc["rows"], "notify": "none"}, {"rows": [], "notify": "none"}])[1]
+    assert third["calls"] == [] and third["differing_cells"] == 0
+
+
+def test_sync_bitset_tables_take_the_whole_segment(cli):
+    """bitset cells are flattened to CSR (their length changes when an upsert adds an id): no partial update"""
+    sc = scenario("users_bitset")
+    batch2 = [list(r) for r in sc["rows"][:3]]
+    for r in batch2:
+        r[-1] = str(int(r[-1]) + 1000)                                  # new ids into existing cells
+    first, second = run_sync(cli, sc["table"], [{"rows": sc["rows"], "notify": "none"}, {"rows": batch2, "notify": "mark"}])
+    assert first["differing_cells"] == 0 and second["differing_cells"] == 0
+    assert [c[0] for c in second["calls"]] == ["put"] * second["segments"] and second["partial_updates"] == 0
