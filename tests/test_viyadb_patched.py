@@ -1,0 +1,158 @@
+"""SURVEY 8f rank 4 (the part that can be built here): ViyaDB's own db::Database with the integration patch applied.
+
+viyadb_b200/host/viyadb_database.patch is the diff a maintainer applies to ViyaDB (src/db/database.{h,cc},
+src/input/loader.cc): `"gpu": true` in the database configuration routes Database::Query — the one entry point of /query,
+/sql and the cluster workers (src/db/database.cc:104-111) — through vgpu_host::GpuQueryRunner, and Loader::AfterLoad tells
+resident HBM copies that an ingest batch has updated cells in place. oracle/Makefile (patched_db) applies it to copies of
+the reference's files, compiles them with the reference's own flags and links them with the rest of the UNMODIFIED
+reference objects. Here the C ABI behind it is the mock of tests/mock_vgpu.h, so the wiring runs without a GPU:
+
+  * with "gpu": true every golden aggregate query sent through the REAL Database::Query produces the reference's rows
+    and QueryStats (the mock answers with the oracle's group table) — and the mock device saw a plan;
+  * without it the very same binary runs the stock g++-JIT path and never touches the device;
+  * rows ingested through the reference's loader reach the device (whole segments first, again after the next batch:
+    the patched Loader::AfterLoad bumped the ingest epoch).
+
+What cannot be built in this image is viyad itself (HTTP / SQL front-end: Boost.Asio, flex, bison are absent)."""
+import json
+import os
+import subprocess
+import sys
+import tempfile
+
+import numpy as np
+import pytest
+
+import golden_util as G
+import viya_oracle
+from viyadb_b200 import db as vdb_mod
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CLI = os.path.join(ROOT, "viyadb_b200", "host", "_build", "viyadb_patched_cli")
+STATE = os.path.join(tempfile.gettempdir(), "vgpu_fuzz_state")
+sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+
+
+@pytest.fixture(scope="module")
+def cli():
+    if not os.path.exists(CLI):
+        ref = os.environ.get("VIYA_REFERENCE", "/root/reference")
+        if not os.path.isdir(os.path.join(ref, "src")):
+            pytest.skip("viyadb_patched_cli not built and the reference's sources are not here")
+        subprocess.run(["make", "-C", os.path.join(ROOT, "oracle"), "-j8", "ref", "patched_db", f"REF={ref}"], check=True,
+                       stdout=subprocess.DEVNULL)
+    return CLI
+
+
+def run(cli, job):
+    with tempfile.NamedTemporaryFile("w", suffix=".json", delete=False) as f:
+        json.dump(job, f)
+        path = f.name
+    try:
+        p = subprocess.run([cli, path], capture_output=True, text=True, timeout=600,
+                           cwd=os.path.join(ROOT, "oracle", "_ref", "root", "build"))
+    finally:
+        os.remove(path)
+    assert p.stdout.strip(), (p.returncode, p.stderr[-800:])
+    out = json.loads(p.stdout.strip().splitlines()[-1])
+    assert "fatal" not in out, out.get("fatal")
+    return out
+
+
+def widen(arr):
+    a = np.asarray(arr)
+    if a.dtype.kind == "f":
+        return a.view("<u4").astype("<u8") if a.dtype.itemsize == 4 else a.view("<u8")
+    return a.astype("<i8").view("<u8") if a.dtype.kind == "i" else a.astype("<u8")
+
+
+def selected_names(table, q):
+    dims = [d["name"] for d in table["dimensions"]]
+    if "select" in q:
+        names = []
+        for s in q["select"]:
+            names += (dims + [m["name"] for m in table["metrics"]]) if s["column"] == "*" else [s["column"]]
+        return [n for n in names if n in dims], [n for n in names if n not in dims]
+    return list(q.get("dimensions", [])), list(q.get("metrics", []))
+
+
+def cases_for(recs):
+    _, segs, dicts, hidden = viya_oracle.read_dump(G.seg_path(recs[0]["seg"]))
+    cases = []
+    for rec in recs:
+        q = rec["query"]
+        res = viya_oracle.run_query(rec["table"], segs, dicts, q, now=rec.get("rollup_ts"), hidden_counts=hidden)
+        g = res["groups"]
+        kn, an = selected_names(rec["table"], q)
+        cases.append({"query": q, "ngroups": res["stats"]["aggregated_recs"], "key_names": kn, "acc_names": an,
+                      "keys": [widen(k).tolist() for k in g["keys"]], "accs": [widen(a).tolist() for a in g["accs"]],
+                      "hidden": None if g["hidden_count"] is None else np.asarray(g["hidden_count"]).astype("<u8").tolist(),
+                      "scanned_recs": res["stats"]["scanned_recs"], "scanned_segments": res["stats"]["scanned_segments"]})
+    return cases
+
+
+def check_rows(rec, got):
+    assert "error" not in got, (rec["test"], got.get("error"))
+    q = rec["query"]
+    ordered = bool(q.get("sort"))
+    if (q.get("limit") or q.get("skip")) and not ordered:
+        assert len(got["rows"]) == len(rec["rows"]), rec["test"]
+    elif ordered:
+        assert got["rows"] == rec["rows"] or sorted(got["rows"]) == sorted(rec["rows"]), rec["test"]
+    else:
+        assert sorted(got["rows"]) == sorted(rec["rows"]), rec["test"]
+    for k, val in rec["stats"].items():
+        assert got["stats"][k] == val, (rec["test"], k, got["stats"][k], val)
+
+
+FUZZ = [r for r in G.records("ref_fuzz_scenarios.jsonl") if "error" not in r]
+FUZZ_TABLES = sorted({r["test"].split(".")[0] for r in FUZZ})
+
+
+@pytest.mark.parametrize("name", FUZZ_TABLES[::4])
+def test_patched_database_query_runs_the_gpu_runner(cli, name):
+    """"gpu": true -> the real Database::Query goes through GpuQueryRunner (mock device) and sends the reference's rows"""
+    recs = [r for r in FUZZ if r["test"].split(".")[0] == name]
+    hdr, _ = vdb_mod.read_dump(G.seg_path(recs[0]["seg"]))
+    out = run(cli, {"table": recs[0]["table"], "dicts": hdr["dicts"], "state_dir": STATE, "gpu": True,
+                    "rollup_ts": recs[0].get("rollup_ts") or 1496570140, "cases": cases_for(recs)})
+    assert out["mock_device_used"]
+    for rec, got in zip(recs, out["results"]):
+        check_rows(rec, got)
+        assert got["plan"] is not None and got["plan"]["metric_cols"] is not None     # the device saw this query's plan
+
+
+def test_patched_database_without_the_switch_is_stock(cli):
+    """no "gpu" key: the same binary runs the stock g++-JIT runner on really ingested rows, the device is never created"""
+    import scenarios
+    sc = next(s for s in scenarios.SCENARIOS if s["name"] == "inapp")
+    want = {r["test"]: r for r in G.records("ref_scenarios.jsonl") if r["test"].startswith("inapp.")}
+    out = run(cli, {"table": sc["table"], "rows": sc["rows"], "state_dir": os.path.join(ROOT, "oracle", "_ref", "state"),
+                    "cases": [{"query": q} for q in sc["queries"]]})
+    assert not out["mock_device_used"]
+    for qi, got in enumerate(out["results"]):
+        rec = want[f"inapp.{qi}"]
+        if "error" in rec:
+            assert "error" in got
+            continue
+        check_rows(rec, got)
+        assert got["plan"] is None
+
+
+def test_patched_database_ingest_reaches_the_device(cli):
+    """rows go in through the reference's loader; the first query uploads every segment, the next batch (in-place upserts
+    + one new tuple) ends in the patched Loader::AfterLoad, so the following query uploads the table again"""
+    import scenarios
+    sc = next(s for s in scenarios.SCENARIOS if s["name"] == "inapp")
+    q = sc["queries"][1]
+    case = {"query": q, "ngroups": 0, "key_names": ["country"], "acc_names": ["count", "revenue"], "keys": [[]], "accs": [[], []],
+            "hidden": None}
+    batch2 = [r[:3] + [str(float(r[3]) * 3 + 1)] for r in sc["rows"]] + [["IL", "gift", "20141114", "7.5"]]
+    out = run(cli, {"table": sc["table"], "rows": sc["rows"], "state_dir": os.path.join(ROOT, "oracle", "_ref", "state"), "gpu": True,
+                    "cases": [case, case], "reload_rows": batch2})
+    first, again = out["results"]
+    assert first["device_calls"] == [["put", 0, len(sc["rows"])]]      # the live segment went to the device
+    assert again["device_calls"] == []                                  # nothing changed: nothing moves
+    after, after_again = out["results_after_reload"]
+    assert after["device_calls"] == [["put", 0, len(sc["rows"]) + 1]]  # the epoch moved: the stale copy is replaced
+    assert after_again["device_calls"] == []

@@ -38,6 +38,7 @@
 #include "query/query.h"
 #include "query/runner.h"
 #include "query/stats.h"
+#include "ingest_epoch.h"
 #include "segment_access.h"
 #include "util/format.h"
 #include "util/string.h"
@@ -109,23 +110,6 @@ inline uint32_t vgpu_type_of(const db::Column *col) {
   default: return VGPU_U64;
   }
 }
-
-// ---------------------------------------------------------------------------------------------
-// Ingest notifications. The reference's upsert aggregates into EXISTING tuples in place
-// (src/codegen/db/upsert.cc:386-393, `m.Update(upsert_tuple.m, tuple_idx)`): metric cells — and bitset cells — of
-// any segment may change without any SegmentBase::size() changing, so "size unchanged" does not mean "resident copy
-// still valid". Every load batch ends in input::Loader::AfterLoad() (src/input/loader.cc:39); the integration calls
-// IngestEpoch::Bump() there (the gtest drop-in binary wraps that very function), and a binding whose
-// epoch is behind re-uploads its table on the next query.
-// ---------------------------------------------------------------------------------------------
-struct IngestEpoch {
-  static std::atomic<uint64_t> &counter() {
-    static std::atomic<uint64_t> c{1};
-    return c;
-  }
-  static void Bump() { counter().fetch_add(1, std::memory_order_release); }
-  static uint64_t Load() { return counter().load(std::memory_order_acquire); }
-};
 
 // ---------------------------------------------------------------------------------------------
 // one db::Table resident in HBM
@@ -788,6 +772,9 @@ public:
 
 private:
   GpuTableBinding &Bind(db::Table &table) {
+    // `query_threads` queries may bind at once (src/db/database.cc:28-29): the map is shared by every runner of a database
+    static std::mutex bind_mu;
+    std::lock_guard<std::mutex> lk(bind_mu);
     auto it = bindings_.find(table.name());
     if (it == bindings_.end())
       it = bindings_.emplace(table.name(), std::make_unique<GpuTableBinding>(ctx_, table)).first;
@@ -971,6 +958,21 @@ private:
   query::QueryRunner stock_;
   query::QueryStats stats_;
   bool delegated_ = false;
+};
+
+// What a db::Database owns when the B200 path is selected by configuration ("gpu": true): the device context and the HBM
+// copies of its tables. viyadb_b200/host/viyadb_database.patch adds `std::unique_ptr<vgpu_host::DatabaseGpu> gpu_` to
+// db::Database and routes Database::Query through GpuQueryRunner when it is set.
+struct DatabaseGpu {
+  vgpu_ctx *ctx = nullptr;
+  GpuQueryRunner::Bindings bindings;
+  explicit DatabaseGpu(int device) { check(vgpu_init(device, &ctx), "vgpu_init"); }
+  ~DatabaseGpu() {
+    bindings.clear();   // HBM copies first, then the context they live in
+    if (ctx) vgpu_shutdown(ctx);
+  }
+  DatabaseGpu(const DatabaseGpu &) = delete;
+  DatabaseGpu &operator=(const DatabaseGpu &) = delete;
 };
 
 } // namespace vgpu_host
