@@ -43,10 +43,12 @@ for r in RECS:
 
 @pytest.fixture(scope="module")
 def cli():
+    # the reference process generates and compiles code when a table is created (its JIT: g++ against its own headers),
+    # so these tests only run where the reference's sources are — the authoring container, not the GPU box
+    ref = os.environ.get("VIYA_REFERENCE", "/root/reference")
+    if not os.path.isdir(os.path.join(ref, "src")):
+        pytest.skip("the reference's sources are not here (its JIT needs them)")
     if not os.path.exists(CLI):
-        ref = os.environ.get("VIYA_REFERENCE", "/root/reference")
-        if not os.path.isdir(os.path.join(ref, "src")):
-            pytest.skip("adapter_mock_cli not built and the reference's sources are not here")
         subprocess.run(["make", "-C", os.path.join(ROOT, "oracle"), "-j8", "ref", "adapter_mock", f"REF={ref}"], check=True,
                        stdout=subprocess.DEVNULL)
     return CLI
