@@ -158,3 +158,20 @@ def test_patched_database_ingest_reaches_the_device(cli):
     after, after_again = out["results_after_reload"]
     assert after["device_calls"] == [["put", 0, len(sc["rows"]) + 1]]  # the epoch moved: the stale copy is replaced
     assert after_again["device_calls"] == []
+
+
+def test_ingest_into_another_table_leaves_the_resident_copy_alone(cli):
+    """the ingest notification is per table (IngestEpoch::Bump(&table_) in the patched Loader::AfterLoad): a batch into
+    table B must not make the next query on table A upload A again — a large static table next to one under continuous
+    ingest would otherwise cross PCIe after every batch"""
+    import scenarios
+    sc = next(s for s in scenarios.SCENARIOS if s["name"] == "inapp")
+    other = next(s for s in scenarios.SCENARIOS if s["name"] == "prune_quirk")
+    other_table = dict(other["table"], name="other")
+    q = sc["queries"][1]
+    case = {"query": q, "ngroups": 0, "key_names": ["country"], "acc_names": ["count", "revenue"], "keys": [[]], "accs": [[], []],
+            "hidden": None}
+    out = run(cli, {"table": sc["table"], "rows": sc["rows"], "state_dir": os.path.join(ROOT, "oracle", "_ref", "state"), "gpu": True,
+                    "other_table": other_table, "cases": [case], "reload_rows": other["rows"], "reload_into": "other"})
+    assert out["results"][0]["device_calls"] == [["put", 0, len(sc["rows"])]]
+    assert out["results_after_reload"][0]["device_calls"] == []        # table "events" was not touched by the batch

@@ -9,7 +9,8 @@
 // job = {"table": {...}, "state_dir": "...", "gpu": true|false, "rows": [[...]] (optional, ingested first),
 //        "dicts": {...} (optional: fill the dictionaries directly instead of ingesting),
 //        "cases": [{"query": {...}, "ngroups": n, "keys": [...], "accs": [...], "hidden": [...] | null, ...}],
-//        "reload_rows": [[...]] (optional: a second batch, then every case again)}
+//        "reload_rows": [[...]] (optional: a second batch, then every case again), "other_table": {...} +
+//        "reload_into": "<name>" (optional: the second batch goes into another table of the same database)}
 #include "db/database.h"
 #include "db/dictionary.h"
 #include "db/table.h"
@@ -103,6 +104,7 @@ int main(int argc, char **argv) {
     json dbconf;
     dbconf["state_dir"] = job.value("state_dir", std::string("/tmp/vgpu_fuzz_state"));
     dbconf["tables"] = json::array({job["table"]});
+    if (job.count("other_table")) dbconf["tables"].push_back(job["other_table"]);   // a second table of the same database
     if (job.value("gpu", false)) dbconf["gpu"] = true;      // <- the configuration switch of the patch
     db::Database database{util::Config(dbconf)};
     auto *table = database.GetTable(job["table"]["name"].get<std::string>());
@@ -149,7 +151,9 @@ int main(int argc, char **argv) {
     };
     run_cases("results");
     if (job.count("reload_rows")) {
-      load_rows(table, job["reload_rows"]);      // ends in the patched Loader::AfterLoad -> IngestEpoch::Bump()
+      // ends in the patched Loader::AfterLoad -> IngestEpoch::Bump(&table_): the batch may go into the OTHER table
+      auto *into = job.count("reload_into") ? database.GetTable(job["reload_into"].get<std::string>()) : table;
+      load_rows(into, job["reload_rows"]);
       run_cases("results_after_reload");
     }
     out["mock_device_used"] = g_table != nullptr;

@@ -169,6 +169,7 @@ public:
       std::lock_guard<std::mutex> lk(registry_mu());
       registry().erase(&table_);
     }
+    IngestEpoch::Forget(&table_);
     vgpu_table_free(handle_);
     for (const void *p : pinned_) vgpu_host_unpin(ctx_, p);
   }
@@ -213,7 +214,7 @@ public:
   void Sync() {
     std::lock_guard<std::mutex> lk(mu_);
     // an ingest batch finished since the last upload: cells of any segment may have been updated in place
-    const uint64_t epoch = IngestEpoch::Load();
+    const uint64_t epoch = IngestEpoch::Load(&table_);
     if (epoch != epoch_seen_) {
       std::fill(uploaded_.begin(), uploaded_.end(), static_cast<size_t>(-1));
       epoch_seen_ = epoch;

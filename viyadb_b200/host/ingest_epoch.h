@@ -5,6 +5,8 @@
 
 #include <atomic>
 #include <cstdint>
+#include <map>
+#include <mutex>
 
 namespace vgpu_host {
 
@@ -13,16 +15,50 @@ namespace vgpu_host {
 // (src/codegen/db/upsert.cc:386-393, `m.Update(upsert_tuple.m, tuple_idx)`): metric cells — and bitset cells — of
 // any segment may change without any SegmentBase::size() changing, so "size unchanged" does not mean "resident copy
 // still valid". Every load batch ends in input::Loader::AfterLoad() (src/input/loader.cc:39); the integration calls
-// IngestEpoch::Bump() there (the gtest drop-in binary wraps that very function), and a binding whose
-// epoch is behind re-uploads its table on the next query.
+// IngestEpoch::Bump(&table_) there (viyadb_database.patch; the gtest drop-in binary, which wraps that function from
+// outside the class, can only call the coarse Bump()), and a binding whose epoch is behind re-uploads its table on the
+// next query.
 // ---------------------------------------------------------------------------------------------
 struct IngestEpoch {
   static std::atomic<uint64_t> &counter() {
     static std::atomic<uint64_t> c{1};
     return c;
   }
+  // coarse: some table of this process finished an ingest batch (what a hook without access to the loader's table can say)
   static void Bump() { counter().fetch_add(1, std::memory_order_release); }
   static uint64_t Load() { return counter().load(std::memory_order_acquire); }
+
+  // per table (`table` = the db::Table the batch went into, input::Loader::table_): only the resident copy of THAT table
+  // is stale — a static 30 GB table next to a table under continuous ingest is not uploaded again after every batch
+  static void Bump(const void *table) {
+    std::lock_guard<std::mutex> lk(table_mu());
+    ++table_counters()[table];
+  }
+  // what a binding of `table` compares with the value it saw at its last upload: moves when either counter moves
+  static uint64_t Load(const void *table) {
+    uint64_t own = 0;
+    {
+      std::lock_guard<std::mutex> lk(table_mu());
+      auto it = table_counters().find(table);
+      if (it != table_counters().end()) own = it->second;
+    }
+    return Load() + own;
+  }
+  // a table that goes away (Database::DropTable, ~Database): a later table at the same address starts from scratch
+  static void Forget(const void *table) {
+    std::lock_guard<std::mutex> lk(table_mu());
+    table_counters().erase(table);
+  }
+
+private:
+  static std::mutex &table_mu() {
+    static std::mutex m;
+    return m;
+  }
+  static std::map<const void *, uint64_t> &table_counters() {
+    static std::map<const void *, uint64_t> m;
+    return m;
+  }
 };
 
 } // namespace vgpu_host
