@@ -57,50 +57,6 @@ void load_rows(db::Table *table, const json &rows) {
   l.After();
 }
 
-// cells of the live store that differ from the shadow (0 == the resident copy is current)
-json compare_with_live(db::Table *table, vgpu_host::SegmentAccess &access) {
-  uint64_t diff_cells = 0, rows = 0;
-  bool missing = false;
-  const size_t ndims = table->dimensions().size(), nmetrics = table->metrics().size();
-  auto segments = table->store()->segments_copy();
-  for (size_t si = 0; si < segments.size(); ++si) {
-    const size_t size = segments[si]->size();
-    rows += size;
-    auto it = g_table->segs.find((uint32_t)si);
-    if (it == g_table->segs.end() || it->second.nrows != size) { missing = true; continue; }
-    const ShadowSeg &sh = it->second;
-    std::vector<const void *> dims(ndims), metrics(nmetrics);
-    std::vector<uint64_t> stats(2 * ndims + 2);
-    const void *hidden = nullptr;
-    access.columns()(segments[si], dims.data(), metrics.data(), &hidden, stats.data());
-    size_t c = 0;
-    auto cmp = [&](const void *live, size_t col) {
-      const uint64_t w = g_table->width[col];
-      const uint8_t *a = static_cast<const uint8_t *>(live);
-      for (size_t r = 0; r < size; ++r)
-        if (std::memcmp(a + r * w, sh.cols[col].data() + r * w, w) != 0) ++diff_cells;
-    };
-    for (size_t d = 0; d < ndims; ++d, ++c) cmp(dims[d], c);
-    for (auto *m : table->metrics()) {
-      if (m->agg_type() != db::Metric::AggregationType::BITSET) { cmp(metrics[m->index()], c++); continue; }
-      std::vector<uint64_t> offsets(size + 1);
-      const uint64_t total = access.bitset()(segments[si], m->index(), size, offsets.data(), nullptr);
-      std::vector<uint64_t> wide(total + 1);
-      access.bitset()(segments[si], m->index(), size, offsets.data(), wide.data());
-      const uint64_t w = g_table->width[c];
-      if (sh.offsets[c] != offsets || sh.cols[c].size() != total * w) { ++diff_cells; ++c; continue; }
-      for (uint64_t i = 0; i < total; ++i) {
-        uint64_t v = 0;
-        std::memcpy(&v, sh.cols[c].data() + i * w, w);
-        if (v != wide[i]) ++diff_cells;
-      }
-      ++c;
-    }
-    if (access.has_hidden_count()) cmp(hidden, c);
-  }
-  return {{"segments", segments.size()}, {"rows", rows}, {"differing_cells", diff_cells}, {"missing_or_short_segments", missing}};
-}
-
 json run_sync(const json &job, db::Database &database, db::Table *table) {
   json out = json::array();
   vgpu_host::GpuTableBinding binding(&g_ctx, *table);

@@ -2,6 +2,7 @@
 // libvgpu.so by the CPU harnesses (tests/adapter_mock_harness.cc, tests/viyadb_patched_harness.cc). It computes nothing:
 //   vgpu_table_create        records the schema
 //   vgpu_segment_put_async / vgpu_segment_update   keep a shadow of what would sit in HBM (sync tests)
+//   compare_with_live                              that shadow against the reference's live segments, cell by cell
 //   vgpu_query_agg / _select / _search             record the plan the adapter lowered and answer with the canned
 //                                                  result the harness placed in g_canned / g_sel_* / g_srch_*
 // Include it in exactly one translation unit, after gpu_query_runner.h (it needs include/vgpu.h and nlohmann::json).
@@ -190,5 +191,52 @@ int vgpu_query_search(vgpu_table *, const vgpu_search_plan *p, vgpu_search **out
 int vgpu_search_get(const vgpu_search *r, vgpu_search_view *view) { *view = r->view; return VGPU_OK; }
 void vgpu_search_free(vgpu_search *r) { delete r; }
 }  // extern "C"
+
+namespace {
+// cells of the live store that differ from the shadow (0 == the resident copy is current)
+json compare_with_live(viya::db::Table *table, vgpu_host::SegmentAccess &access) {
+  namespace db = viya::db;
+  uint64_t diff_cells = 0, rows = 0;
+  bool missing = false;
+  const size_t ndims = table->dimensions().size(), nmetrics = table->metrics().size();
+  auto segments = table->store()->segments_copy();
+  for (size_t si = 0; si < segments.size(); ++si) {
+    const size_t size = segments[si]->size();
+    rows += size;
+    auto it = g_table->segs.find((uint32_t)si);
+    if (it == g_table->segs.end() || it->second.nrows != size) { missing = true; continue; }
+    const ShadowSeg &sh = it->second;
+    std::vector<const void *> dims(ndims), metrics(nmetrics);
+    std::vector<uint64_t> stats(2 * ndims + 2);
+    const void *hidden = nullptr;
+    access.columns()(segments[si], dims.data(), metrics.data(), &hidden, stats.data());
+    size_t c = 0;
+    auto cmp = [&](const void *live, size_t col) {
+      const uint64_t w = g_table->width[col];
+      const uint8_t *a = static_cast<const uint8_t *>(live);
+      for (size_t r = 0; r < size; ++r)
+        if (std::memcmp(a + r * w, sh.cols[col].data() + r * w, w) != 0) ++diff_cells;
+    };
+    for (size_t d = 0; d < ndims; ++d, ++c) cmp(dims[d], c);
+    for (auto *m : table->metrics()) {
+      if (m->agg_type() != db::Metric::AggregationType::BITSET) { cmp(metrics[m->index()], c++); continue; }
+      std::vector<uint64_t> offsets(size + 1);
+      const uint64_t total = access.bitset()(segments[si], m->index(), size, offsets.data(), nullptr);
+      std::vector<uint64_t> wide(total + 1);
+      access.bitset()(segments[si], m->index(), size, offsets.data(), wide.data());
+      const uint64_t w = g_table->width[c];
+      if (sh.offsets[c] != offsets || sh.cols[c].size() != total * w) { ++diff_cells; ++c; continue; }
+      for (uint64_t i = 0; i < total; ++i) {
+        uint64_t v = 0;
+        std::memcpy(&v, sh.cols[c].data() + i * w, w);
+        if (v != wide[i]) ++diff_cells;
+      }
+      ++c;
+    }
+    if (access.has_hidden_count()) cmp(hidden, c);
+  }
+  return {{"segments", segments.size()}, {"rows", rows}, {"differing_cells", diff_cells}, {"missing_or_short_segments", missing}};
+}
+}  // namespace
 
 #endif  // VGPU_TESTS_MOCK_VGPU_H_

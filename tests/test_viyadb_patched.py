@@ -142,22 +142,35 @@ def test_patched_database_without_the_switch_is_stock(cli):
 
 
 def test_patched_database_ingest_reaches_the_device(cli):
-    """rows go in through the reference's loader; the first query uploads every segment, the next batch (in-place upserts
-    + one new tuple) ends in the patched Loader::AfterLoad, so the following query uploads the table again"""
+    """Rows go in through the reference's loader; the first query uploads every segment. The next batch updates existing
+    tuples IN PLACE and appends one: the patched upsert code reports the updated rows (vgpu_ingest_mark_dirty, resolved by
+    the JIT-compiled .so from the executable), the patched Loader::AfterLoad hands them to the resident copy, and the
+    following query moves exactly those rows plus the appended one — after which the device holds the live store, cell
+    for cell (the mock keeps a shadow of it)."""
     import scenarios
     sc = next(s for s in scenarios.SCENARIOS if s["name"] == "inapp")
+    n1 = len(sc["rows"])
     q = sc["queries"][1]
     case = {"query": q, "ngroups": 0, "key_names": ["country"], "acc_names": ["count", "revenue"], "keys": [[]], "accs": [[], []],
             "hidden": None}
+    job = {"table": sc["table"], "rows": sc["rows"], "state_dir": os.path.join(ROOT, "oracle", "_ref", "state"), "gpu": True,
+           "cases": [case, case]}
+    # every existing tuple again, plus a new one: rows [0, n1) updated in place, row n1 appended -> one range
     batch2 = [r[:3] + [str(float(r[3]) * 3 + 1)] for r in sc["rows"]] + [["IL", "gift", "20141114", "7.5"]]
-    out = run(cli, {"table": sc["table"], "rows": sc["rows"], "state_dir": os.path.join(ROOT, "oracle", "_ref", "state"), "gpu": True,
-                    "cases": [case, case], "reload_rows": batch2})
+    out = run(cli, dict(job, reload_rows=batch2))
     first, again = out["results"]
-    assert first["device_calls"] == [["put", 0, len(sc["rows"])]]      # the live segment went to the device
+    assert first["device_calls"] == [["put", 0, n1]] and first["shadow"]["differing_cells"] == 0
     assert again["device_calls"] == []                                  # nothing changed: nothing moves
     after, after_again = out["results_after_reload"]
-    assert after["device_calls"] == [["put", 0, len(sc["rows"]) + 1]]  # the epoch moved: the stale copy is replaced
+    assert after["device_calls"] == [["update", 0, 0, n1 + 1]]
+    assert after["shadow"]["rows"] == n1 + 1 and after["shadow"]["differing_cells"] == 0 and not after["shadow"]["missing_or_short_segments"]
     assert after_again["device_calls"] == []
+    # two of the existing tuples only (rows 2 and 5 of the segment), nothing appended: two one-row updates
+    batch3 = [sc["rows"][2][:3] + ["100.5"], sc["rows"][5][:3] + ["0.25"]]
+    out = run(cli, dict(job, reload_rows=batch3))
+    after = out["results_after_reload"][0]
+    assert after["device_calls"] == [["update", 0, 2, 1], ["update", 0, 5, 1]]
+    assert after["shadow"]["differing_cells"] == 0
 
 
 def test_ingest_into_another_table_leaves_the_resident_copy_alone(cli):

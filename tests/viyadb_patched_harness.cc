@@ -138,7 +138,13 @@ int main(int argc, char **argv) {
           if (g_table != nullptr) g_table->calls = json::array();
           query::MemoryRowOutput output;
           auto stats = database.Query(util::Config(c["query"]), output);     // the real entry point
+          json shadow;   // after the query's Sync(): is what the device holds the live store?
+          if (g_table != nullptr) {
+            vgpu_host::SegmentAccess access(*table);
+            shadow = compare_with_live(table, access);
+          }
           res = {{"rows", output.rows()}, {"plan", g_plan}, {"device_calls", g_table ? g_table->calls : json::array()},
+                 {"shadow", shadow},
                  {"stats", {{"scanned_segments", stats.scanned_segments}, {"scanned_recs", stats.scanned_recs},
                             {"aggregated_recs", stats.aggregated_recs}, {"output_recs", stats.output_recs}}}};
         } catch (const std::invalid_argument &e) {

@@ -961,6 +961,16 @@ private:
   bool delegated_ = false;
 };
 
+// End of an ingest batch into `table` (input::Loader::AfterLoad in the integration): hand the rows the generated upsert
+// code reported as updated in place (IngestDirty, ingest_epoch.h) to the table's resident copy. Rows appended by the batch
+// need no report: Sync() sees the segments grow.
+inline void FlushIngest(const db::Table *table) {
+  auto &pending = IngestDirty::pending();
+  for (auto &r : pending)
+    if (r.table == table) GpuTableBinding::MarkDirty(table, r.seg, r.lo, r.hi);
+  pending.clear();
+}
+
 // What a db::Database owns when the B200 path is selected by configuration ("gpu": true): the device context and the HBM
 // copies of its tables. viyadb_b200/host/viyadb_database.patch adds `std::unique_ptr<vgpu_host::DatabaseGpu> gpu_` to
 // db::Database and routes Database::Query through GpuQueryRunner when it is set.

@@ -5,8 +5,10 @@
 
 #include <atomic>
 #include <cstdint>
+#include <cstddef>
 #include <map>
 #include <mutex>
+#include <vector>
 
 namespace vgpu_host {
 
@@ -58,6 +60,34 @@ private:
   static std::map<const void *, uint64_t> &table_counters() {
     static std::map<const void *, uint64_t> m;
     return m;
+  }
+};
+
+// Exact notifications. viyadb_database.patch makes the generated upsert code call
+// vgpu_ingest_mark_dirty(table, segment, tuple) where it updates an existing tuple in place
+// (src/codegen/db/upsert.cc:386-393). The rows are collected per ingest thread, adjacent ones merged, and handed to the
+// table's resident copy when the batch ends (Loader::AfterLoad -> vgpu_host::FlushIngest, gpu_query_runner.h): the next
+// query then moves only those rows and the appended ones across PCIe (vgpu_segment_update) — no epoch bump needed.
+struct IngestDirty {
+  struct Range {
+    const void *table;
+    size_t seg, lo, hi;
+  };
+  static std::vector<Range> &pending() {
+    static thread_local std::vector<Range> v;   // BeforeLoad .. Load .. AfterLoad of a batch run on one thread
+    return v;
+  }
+  static void Mark(const void *table, size_t seg, size_t row) {
+    auto &v = pending();
+    if (!v.empty()) {
+      Range &b = v.back();
+      if (b.table == table && b.seg == seg && row + 1 >= b.lo && row <= b.hi) {
+        if (row < b.lo) b.lo = row;
+        if (row + 1 > b.hi) b.hi = row + 1;
+        return;
+      }
+    }
+    v.push_back(Range{table, seg, row, row + 1});
   }
 };
 
