@@ -918,7 +918,7 @@ private:
       }
     }
     if (!sort_columns.empty()) {
-      std::sort(post_agg.begin(), post_agg.end(), [&sort_columns](const Row &a, const Row &b) {
+      auto row_less = [&sort_columns](const Row &a, const Row &b) {
         size_t sc_size = sort_columns.size();
         for (size_t i = 0; i < sc_size; ++i) {
           auto &sc = sort_columns[i];
@@ -942,7 +942,15 @@ private:
           if (i < sc_size - 1 && gt) return false;
         }
         return false;
-      });
+      };
+      // The reference sorts everything and sends [skip, skip + limit) (sort.cc:32-73). Only that window has to be in
+      // order: a partial sort of its upper end is the same rows in the same order (std::sort leaves ties unspecified
+      // as well) in O(n log(skip + limit)) — what remains of a large group table when the sort key is one the device
+      // cannot rank (strings, times, floats, AVG).
+      if (limit > 0 && skip + limit < post_agg.size())
+        std::partial_sort(post_agg.begin(), post_agg.begin() + (skip + limit), post_agg.end(), row_less);
+      else
+        std::sort(post_agg.begin(), post_agg.end(), row_less);
       size_t end = limit > 0 ? std::min(post_agg.size(), skip + limit) : post_agg.size();
       for (size_t i = std::min(skip, post_agg.size()); i < end; ++i) {
         output_.Send(post_agg[i]);
