@@ -15,6 +15,7 @@
 //                   search:    "seg_offsets": [...], "codes": [...], "first_row": [...]   (vgpu_search_view)}]}
 // or     {"table": ..., "state_dir": ..., "sync": [{"rows": [[...]], "notify": "none" | "epoch" | "mark"}, ...]}: every
 //        step ingests its rows through the reference's own loader, notifies the binding and calls GpuTableBinding::Sync()
+// or     {..., "cases": [...], "concurrent": {"threads": T, "repeat": R}}: every case from T threads at once (see below)
 #include "db/database.h"
 #include "db/dictionary.h"
 #include "db/table.h"
@@ -24,7 +25,9 @@
 #include "query/query.h"
 #include "query/runner.h"
 #include "util/config.h"
+#include <atomic>
 #include <chrono>
+#include <thread>
 #include <cstring>
 #include <fstream>
 #include <iostream>
@@ -87,53 +90,8 @@ json run_sync(const json &job, db::Database &database, db::Table *table) {
 }
 }  // namespace
 
-// ---------------------------------------------------------------------------------------------
-int main(int argc, char **argv) {
-  if (argc < 2) {
-    std::cerr << "usage: adapter_mock_cli <job.json>\n";
-    return 2;
-  }
-  std::ifstream in(argv[1]);
-  json job;
-  in >> job;
-  if (job.count("rollup_ts")) {
-    std::string v = std::to_string(job["rollup_ts"].get<long>()) + "L";
-    setenv("VIYA_TEST_ROLLUP_TS", v.c_str(), 1);
-  }
-  json out;
-  try {
-    json dbconf;
-    dbconf["state_dir"] = job.value("state_dir", std::string("/tmp/vgpu_fuzz_state"));
-    dbconf["tables"] = json::array({job["table"]});
-    db::Database database{util::Config(dbconf)};
-    auto *table = database.GetTable(job["table"]["name"].get<std::string>());
-    // dictionaries in code order, the way the generated upsert code fills them (code = c2v.size(), both maps): code 0 is
-    // "__exceeded" already (dictionary.cc:22-25)
-    for (auto *dim : table->dimensions()) {
-      if (dim->dim_type() != db::Dimension::DimType::STRING) continue;
-      auto dict = static_cast<const db::StrDimension *>(dim)->dict();
-      if (!job.count("dicts")) break;   // sync mode: the reference's own ingest fills the dictionaries
-      auto &vals = job["dicts"][dim->name()];
-      for (size_t i = 1; i < vals.size(); ++i) {
-        const std::string v = vals[i].get<std::string>();
-        const uint64_t code = dict->c2v().size();
-        dict->c2v().push_back(v);
-        switch (dim->num_type().size()) {
-        case db::BaseNumType::_1: reinterpret_cast<db::DictImpl<uint8_t> *>(dict->v2c())->insert(std::make_pair(v, (uint8_t)code)); break;
-        case db::BaseNumType::_2: reinterpret_cast<db::DictImpl<uint16_t> *>(dict->v2c())->insert(std::make_pair(v, (uint16_t)code)); break;
-        case db::BaseNumType::_4: reinterpret_cast<db::DictImpl<uint32_t> *>(dict->v2c())->insert(std::make_pair(v, (uint32_t)code)); break;
-        default: reinterpret_cast<db::DictImpl<uint64_t> *>(dict->v2c())->insert(std::make_pair(v, (uint64_t)code)); break;
-        }
-      }
-    }
-    if (job.count("sync")) {
-      out["sync"] = run_sync(job, database, table);
-      std::cout << out.dump() << std::endl;
-      return 0;
-    }
-    vgpu_host::GpuQueryRunner::Bindings bindings;
-    out["results"] = json::array();
-    for (auto &c : job["cases"]) {
+// one case on the calling thread: arm the (thread-local) canned answer of the mock, run the query through the adapter
+json run_case(const json &job, const json &c, db::Database &database, vgpu_host::GpuQueryRunner::Bindings &bindings) {
       json res;
       try {
         query::MemoryRowOutput output;
@@ -207,8 +165,108 @@ int main(int argc, char **argv) {
       } catch (const std::exception &e) {
         res = {{"error", e.what()}, {"error_type", "exception"}};
       }
-      out["results"].push_back(res);
+      return res;
+}
+
+// ---------------------------------------------------------------------------------------------
+// concurrent mode: the reference runs `query_threads` queries at once next to an ingest thread (src/db/database.cc:28-33).
+// T threads run every case R times through their own GpuQueryRunner over the SHARED bindings of the database while
+// another thread keeps sending ingest notifications for the table; every answer must equal the single-threaded one.
+// Built with -fsanitize=thread (oracle/Makefile: adapter_mock_tsan) this is the data-race check of the adapter's host code.
+// ---------------------------------------------------------------------------------------------
+json run_concurrent(const json &job, db::Database &database, db::Table *table) {
+  const int threads = job["concurrent"].value("threads", 4), repeat = job["concurrent"].value("repeat", 3);
+  std::vector<json> baseline;
+  {
+    vgpu_host::GpuQueryRunner::Bindings single;
+    for (auto &c : job["cases"]) baseline.push_back(run_case(job, c, database, single)["rows"]);
+  }
+  vgpu_host::GpuQueryRunner::Bindings bindings;   // fresh: the threads race to bind the table (GpuQueryRunner::Bind)
+  std::atomic<bool> stop{false};
+  std::atomic<uint64_t> mismatches{0}, queries{0}, errors{0};
+  std::thread notifier([&] {
+    uint64_t i = 0;
+    while (!stop.load()) {
+      vgpu_host::GpuTableBinding::MarkDirty(table, 0, i % 7, i % 7 + 1);
+      if (i % 3 == 0) vgpu_host::IngestEpoch::Bump(table);
+      if (i % 11 == 0) vgpu_host::IngestEpoch::Bump();
+      vgpu_host::IngestDirty::Mark(table, 0, i % 5);
+      vgpu_host::FlushIngest(table);
+      ++i;
+      std::this_thread::yield();
     }
+  });
+  std::vector<std::thread> pool;
+  for (int t = 0; t < threads; ++t)
+    pool.emplace_back([&, t] {
+      for (int r = 0; r < repeat; ++r)
+        for (size_t i = 0; i < job["cases"].size(); ++i) {
+          const size_t k = (i + t) % job["cases"].size();   // different threads, different queries at the same time
+          json res = run_case(job, job["cases"][k], database, bindings);
+          ++queries;
+          if (res.count("error")) ++errors;
+          else if (res["rows"] != baseline[k]) ++mismatches;
+        }
+    });
+  for (auto &th : pool) th.join();
+  stop.store(true);
+  notifier.join();
+  bindings.clear();
+  return {{"threads", threads}, {"queries", queries.load()}, {"mismatches", mismatches.load()}, {"errors", errors.load()}};
+}
+
+// ---------------------------------------------------------------------------------------------
+int main(int argc, char **argv) {
+  if (argc < 2) {
+    std::cerr << "usage: adapter_mock_cli <job.json>\n";
+    return 2;
+  }
+  std::ifstream in(argv[1]);
+  json job;
+  in >> job;
+  if (job.count("rollup_ts")) {
+    std::string v = std::to_string(job["rollup_ts"].get<long>()) + "L";
+    setenv("VIYA_TEST_ROLLUP_TS", v.c_str(), 1);
+  }
+  json out;
+  try {
+    json dbconf;
+    dbconf["state_dir"] = job.value("state_dir", std::string("/tmp/vgpu_fuzz_state"));
+    dbconf["tables"] = json::array({job["table"]});
+    db::Database database{util::Config(dbconf)};
+    auto *table = database.GetTable(job["table"]["name"].get<std::string>());
+    // dictionaries in code order, the way the generated upsert code fills them (code = c2v.size(), both maps): code 0 is
+    // "__exceeded" already (dictionary.cc:22-25)
+    for (auto *dim : table->dimensions()) {
+      if (dim->dim_type() != db::Dimension::DimType::STRING) continue;
+      auto dict = static_cast<const db::StrDimension *>(dim)->dict();
+      if (!job.count("dicts")) break;   // sync mode: the reference's own ingest fills the dictionaries
+      auto &vals = job["dicts"][dim->name()];
+      for (size_t i = 1; i < vals.size(); ++i) {
+        const std::string v = vals[i].get<std::string>();
+        const uint64_t code = dict->c2v().size();
+        dict->c2v().push_back(v);
+        switch (dim->num_type().size()) {
+        case db::BaseNumType::_1: reinterpret_cast<db::DictImpl<uint8_t> *>(dict->v2c())->insert(std::make_pair(v, (uint8_t)code)); break;
+        case db::BaseNumType::_2: reinterpret_cast<db::DictImpl<uint16_t> *>(dict->v2c())->insert(std::make_pair(v, (uint16_t)code)); break;
+        case db::BaseNumType::_4: reinterpret_cast<db::DictImpl<uint32_t> *>(dict->v2c())->insert(std::make_pair(v, (uint32_t)code)); break;
+        default: reinterpret_cast<db::DictImpl<uint64_t> *>(dict->v2c())->insert(std::make_pair(v, (uint64_t)code)); break;
+        }
+      }
+    }
+    if (job.count("sync")) {
+      out["sync"] = run_sync(job, database, table);
+      std::cout << out.dump() << std::endl;
+      return 0;
+    }
+    if (job.count("concurrent")) {
+      out["concurrent"] = run_concurrent(job, database, table);
+      std::cout << out.dump() << std::endl;
+      return 0;
+    }
+    vgpu_host::GpuQueryRunner::Bindings bindings;
+    out["results"] = json::array();
+    for (auto &c : job["cases"]) out["results"].push_back(run_case(job, c, database, bindings));
     bindings.clear();
   } catch (const std::exception &e) {
     out["fatal"] = e.what();

@@ -11,6 +11,7 @@
 
 #include <cstring>
 #include <map>
+#include <mutex>
 #include <nlohmann/json.hpp>
 #include <vector>
 
@@ -43,14 +44,17 @@ struct vgpu_search { vgpu_search_view view; };
 
 namespace {
 vgpu_ctx g_ctx;
-json g_plan;                 // the last plan vgpu_query_agg saw
-vgpu_result_view g_canned;   // what it answers
+// per thread: several queries may run at once (the concurrent mode of adapter_mock_harness.cc), each with its own
+// canned answer, like `query_threads` pool threads of the server
+thread_local json g_plan;                 // the last plan vgpu_query_agg saw on this thread
+thread_local vgpu_result_view g_canned;   // what it answers
+std::mutex g_mock_mu;                     // call log + shadow store of the tables
 json g_schema;
 vgpu_table *g_table = nullptr;   // the last table created (the sync mode looks into its shadow store)
-std::vector<std::vector<uint64_t>> g_sel_cells;   // select: per schema column, the widened cells of the rows to send
-uint64_t g_sel_nrows = 0;
-std::vector<uint64_t> g_srch_offsets{0}, g_srch_codes;   // search: what the device hands back
-std::vector<uint32_t> g_srch_rows;
+thread_local std::vector<std::vector<uint64_t>> g_sel_cells;   // select: per schema column, the widened cells of the rows to send
+thread_local uint64_t g_sel_nrows = 0;
+thread_local std::vector<uint64_t> g_srch_offsets{0}, g_srch_codes;   // search: what the device hands back
+thread_local std::vector<uint32_t> g_srch_rows;
 
 json nodes_json(const vgpu_pred_node *nodes, uint32_t n) {
   json a = json::array();
@@ -81,6 +85,7 @@ int vgpu_table_create(vgpu_ctx *, const vgpu_schema *schema, vgpu_table **out) {
 }
 void vgpu_table_free(vgpu_table *t) { delete t; }
 int vgpu_segment_put_async(vgpu_table *t, uint32_t seg, uint64_t nrows, const void *const *ptrs) {
+  std::lock_guard<std::mutex> lk(g_mock_mu);
   t->calls.push_back({"put", seg, nrows});
   ShadowSeg &sh = t->segs[seg];
   sh = ShadowSeg();
@@ -101,6 +106,7 @@ int vgpu_segment_put_async(vgpu_table *t, uint32_t seg, uint64_t nrows, const vo
   return VGPU_OK;
 }
 int vgpu_segment_update(vgpu_table *t, uint32_t seg, uint64_t row_begin, uint64_t nrows, const void *const *ptrs) {
+  std::lock_guard<std::mutex> lk(g_mock_mu);
   t->calls.push_back({"update", seg, row_begin, nrows});
   auto it = t->segs.find(seg);
   if (it == t->segs.end() || row_begin > it->second.nrows) return VGPU_ERR_STATE;

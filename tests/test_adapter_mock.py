@@ -410,3 +410,69 @@ def test_sync_bitset_tables_take_the_whole_segment(cli):
     first, second = run_sync(cli, sc["table"], [{"rows": sc["rows"], "notify": "none"}, {"rows": batch2, "notify": "mark"}])
     assert first["differing_cells"] == 0 and second["differing_cells"] == 0
     assert [c[0] for c in second["calls"]] == ["put"] * second["segments"] and second["partial_updates"] == 0
+
+
+# ------------------------------------------------------------------------------------------------
+# concurrency (SURVEY 8b "Threading"): query_threads queries at once over the shared bindings, next to ingest notifications
+# ------------------------------------------------------------------------------------------------
+TSAN_CLI = os.path.join(ROOT, "viyadb_b200", "host", "_build", "adapter_mock_tsan")
+
+
+def concurrent_job(name="fuzzb01", threads=6, repeat=3):
+    recs = [r for r in RECS if r["test"].split(".")[0] == name]
+    key = (json.dumps(recs[0]["table"], sort_keys=True), recs[0]["seg"], recs[0].get("rollup_ts"))
+    hdr, _ = vdb_mod.read_dump(G.seg_path(recs[0]["seg"]))
+    _, segs, dicts, hidden = viya_oracle.read_dump(G.seg_path(recs[0]["seg"]))
+    cases = []
+    for rec in GROUPS[key]:
+        res = viya_oracle.run_query(rec["table"], segs, dicts, rec["query"], now=rec.get("rollup_ts"), hidden_counts=hidden)
+        g = res["groups"]
+        cases.append({"query": rec["query"], "ngroups": res["stats"]["aggregated_recs"],
+                      "keys": [widen(k).tolist() for k in g["keys"]], "accs": [widen(a).tolist() for a in g["accs"]],
+                      "hidden": None if g["hidden_count"] is None else np.asarray(g["hidden_count"]).astype("<u8").tolist()})
+    job = {"table": recs[0]["table"], "dicts": hdr["dicts"], "cases": cases, "state_dir": STATE,
+           "concurrent": {"threads": threads, "repeat": repeat}}
+    if recs[0].get("rollup_ts") is not None:
+        job["rollup_ts"] = recs[0]["rollup_ts"]
+    return job, len(cases)
+
+
+def run_concurrent(binary, job, env=None):
+    with tempfile.NamedTemporaryFile("w", suffix=".json", delete=False) as f:
+        json.dump(job, f)
+        path = f.name
+    try:
+        return subprocess.run([binary, path], capture_output=True, text=True, timeout=900, env=env,
+                              cwd=os.path.join(ROOT, "oracle", "_ref", "root", "build"))
+    finally:
+        os.remove(path)
+
+
+def test_concurrent_queries_through_the_adapter(cli):
+    """six threads, each running every query of a fuzz table three times through its own GpuQueryRunner over the shared
+    bindings, while another thread sends ingest notifications: every answer equals the single-threaded one"""
+    job, ncases = concurrent_job()
+    p = run_concurrent(cli, job)
+    assert p.returncode == 0 and p.stdout.strip(), (p.stdout[-500:], p.stderr[-500:])
+    out = json.loads(p.stdout.strip().splitlines()[-1])["concurrent"]
+    assert out["queries"] == 6 * 3 * ncases and out["mismatches"] == 0 and out["errors"] == 0
+
+
+def test_concurrent_queries_under_thread_sanitizer(cli):
+    """the same run in a -fsanitize=thread build of the harness (the adapter header, the reference's inline header code
+    it calls and the mock are instrumented): ThreadSanitizer must report nothing"""
+    if not os.path.exists(TSAN_CLI):
+        ref = os.environ.get("VIYA_REFERENCE", "/root/reference")
+        if not os.path.exists("/usr/bin/g++"):
+            pytest.skip("no g++ with libtsan")
+        r = subprocess.run(["make", "-C", os.path.join(ROOT, "oracle"), "-j8", "ref", "adapter_mock_tsan", f"REF={ref}"],
+                           capture_output=True, text=True)
+        if r.returncode != 0:
+            pytest.skip("ThreadSanitizer build not available: " + r.stderr[-200:])
+    job, ncases = concurrent_job(threads=8, repeat=2)
+    env = dict(os.environ, TSAN_OPTIONS="exitcode=66 halt_on_error=0")
+    p = run_concurrent(TSAN_CLI, job, env)
+    assert "ThreadSanitizer" not in p.stderr, p.stderr[-3000:]
+    assert p.returncode == 0 and p.stdout.strip(), (p.returncode, p.stdout[-300:], p.stderr[-1500:])
+    out = json.loads(p.stdout.strip().splitlines()[-1])["concurrent"]
+    assert out["queries"] == 8 * 2 * ncases and out["mismatches"] == 0 and out["errors"] == 0
