@@ -31,7 +31,7 @@ from viyadb_b200 import db as vdb_mod
 from viyadb_b200.query import GpuQueryRunner, MemoryRowOutput, QueryFactory
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-CLI = os.path.join(ROOT, "viyadb_b200", "host", "_build", "adapter_mock_cli")
+CLI = os.environ.get("VGPU_ADAPTER_CLI") or os.path.join(ROOT, "viyadb_b200", "host", "_build", "adapter_mock_cli")   # override: sanitizer builds
 STATE = os.path.join(tempfile.gettempdir(), "vgpu_fuzz_state")
 RECS = [r for name in ("ref_gtest.jsonl", "ref_scenarios.jsonl", "ref_edge_scenarios.jsonl", "ref_fuzz_scenarios.jsonl")
         for r in G.records(name) if "error" not in r and "seg" in r]

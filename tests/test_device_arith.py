@@ -25,11 +25,12 @@ U64P = C.POINTER(C.c_uint64)
 
 @pytest.fixture(scope="module")
 def lib(tmp_path_factory):
-    gxx = shutil.which("g++")
+    gxx = os.environ.get("VGPU_HARNESS_CXX") or shutil.which("g++")   # VGPU_HARNESS_CXX / _FLAGS: sanitizer builds
+    extra = os.environ.get("VGPU_HARNESS_FLAGS", "").split()
     if gxx is None:
         pytest.skip("g++ not available")
     so = str(tmp_path_factory.mktemp("arith") / "libdevice_arith.so")
-    subprocess.run([gxx, "-std=c++17", "-O2", "-shared", "-fPIC", "-Wno-unknown-pragmas", "-o", so,
+    subprocess.run([gxx, "-std=c++17", "-O2", "-shared", "-fPIC", *extra, "-Wno-unknown-pragmas", "-o", so,
                     os.path.join(ROOT, "tests", "device_arith_harness.cc")], check=True)
     return C.CDLL(so)
 
