@@ -472,6 +472,8 @@ def test_concurrent_queries_under_thread_sanitizer(cli):
     job, ncases = concurrent_job(threads=8, repeat=2)
     env = dict(os.environ, TSAN_OPTIONS="exitcode=66 halt_on_error=0")
     p = run_concurrent(TSAN_CLI, job, env)
+    if "FATAL: ThreadSanitizer" in p.stderr or "unexpected memory mapping" in p.stderr:
+        pytest.skip("the ThreadSanitizer runtime does not start on this kernel: " + p.stderr.strip().splitlines()[0][:120])
     assert "ThreadSanitizer" not in p.stderr, p.stderr[-3000:]
     assert p.returncode == 0 and p.stdout.strip(), (p.returncode, p.stdout[-300:], p.stderr[-1500:])
     out = json.loads(p.stdout.strip().splitlines()[-1])["concurrent"]
