@@ -33,17 +33,39 @@ def test_library_exports_every_declared_symbol(built_lib):
 
 
 def test_struct_layouts_match_the_header(built_lib):
-    """sizeof of the ctypes mirrors == sizeof in C (compiled from the header with gcc)."""
+    """Every public struct of include/vgpu.h against its ctypes mirror (viyadb_b200/_native.py): sizeof AND the offset of
+    every field, taken from a C program compiled from the header with gcc. A binding that drifts from the header would
+    hand the library misplaced pointers — silently."""
     import subprocess
     import tempfile
     from viyadb_b200 import _native as N
-    src = '#include "vgpu.h"\n#include <stdio.h>\nint main(){printf("%zu %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(vgpu_column), sizeof(vgpu_schema), sizeof(vgpu_bitset_csr), sizeof(vgpu_pred_node), sizeof(vgpu_key), sizeof(vgpu_plan), sizeof(vgpu_result_view), sizeof(vgpu_gen_col));return 0;}\n'
+    pairs = [("vgpu_column", N.Column), ("vgpu_schema", N.Schema), ("vgpu_bitset_csr", N.BitsetCsr), ("vgpu_pred_node", N.PredNode),
+             ("vgpu_key", N.Key), ("vgpu_plan", N.Plan), ("vgpu_result_view", N.ResultView), ("vgpu_gen_col", N.GenCol),
+             ("vgpu_rows_plan", N.RowsPlan), ("vgpu_rows_view", N.RowsView), ("vgpu_search_plan", N.SearchPlan),
+             ("vgpu_search_view", N.SearchView)]
+    lines = []
+    for cname, cls in pairs:
+        lines.append(f'printf("{cname} %zu", sizeof({cname}));')
+        for fname, _ in cls._fields_:
+            lines.append(f'printf(" {fname}:%zu", offsetof({cname}, {fname}));')
+        lines.append('printf("\\n");')
+    src = '#include "vgpu.h"\n#include <stddef.h>\n#include <stdio.h>\nint main(){' + "".join(lines) + "return 0;}\n"
     with tempfile.TemporaryDirectory() as d:
         open(os.path.join(d, "t.c"), "w").write(src)
+        # a field the binding names but the header lacks fails to compile here
         subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), "-o", os.path.join(d, "t"), os.path.join(d, "t.c")], check=True)
-        out = subprocess.run([os.path.join(d, "t")], capture_output=True, text=True, check=True).stdout.split()
-    want = [C.sizeof(x) for x in (N.Column, N.Schema, N.BitsetCsr, N.PredNode, N.Key, N.Plan, N.ResultView, N.GenCol)]
-    assert [int(x) for x in out] == want
+        out = subprocess.run([os.path.join(d, "t")], capture_output=True, text=True, check=True).stdout.strip().splitlines()
+    assert len(out) == len(pairs)
+    for line, (cname, cls) in zip(out, pairs):
+        parts = line.split()
+        assert parts[0] == cname and int(parts[1]) == C.sizeof(cls), (cname, parts[1], C.sizeof(cls))
+        got = {p.split(":")[0]: int(p.split(":")[1]) for p in parts[2:]}
+        want = {fname: getattr(cls, fname).offset for fname, _ in cls._fields_}
+        assert got == want, (cname, got, want)
+    # and the header has no struct the binding does not mirror
+    import re
+    declared = set(re.findall(r"typedef struct (vgpu_\w+) \{", open(os.path.join(ROOT, "include", "vgpu.h")).read()))
+    assert declared == {c for c, _ in pairs}, declared ^ {c for c, _ in pairs}
 
 
 def test_no_cpu_fallback_without_a_device(built_lib):
