@@ -68,6 +68,38 @@ def test_struct_layouts_match_the_header(built_lib):
     assert declared == {c for c, _ in pairs}, declared ^ {c for c, _ in pairs}
 
 
+def test_constants_match_the_header():
+    """every enumerator and flag of include/vgpu.h against the constant of the same name (without the VGPU_ prefix) in the
+    ctypes binding: an enum that drifts would send the library a different column kind or operator than the host meant"""
+    import re
+    import subprocess
+    import tempfile
+    from viyadb_b200 import _native as N
+    text = open(os.path.join(ROOT, "include", "vgpu.h")).read()
+    names = set()
+    for body in re.findall(r"typedef enum \w+ \{(.*?)\}", text, re.S):
+        names.update(re.findall(r"\b(VGPU_[A-Z0-9_]+)\s*=", body))
+    names.update(re.findall(r"#define (VGPU_[A-Z0-9_]+) +[-0-9xa-fA-Fu(]", text))
+    names.discard("VGPU_H_")
+    assert len(names) > 50
+    src = '#include "vgpu.h"\n#include <stdio.h>\nint main(){' + "".join(
+        f'printf("{n} %lld\\n", (long long)({n}));' for n in sorted(names)) + "return 0;}\n"
+    with tempfile.TemporaryDirectory() as d:
+        open(os.path.join(d, "t.c"), "w").write(src)
+        subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), "-o", os.path.join(d, "t"), os.path.join(d, "t.c")], check=True)
+        out = subprocess.run([os.path.join(d, "t")], capture_output=True, text=True, check=True).stdout.split("\n")
+    header = {l.split()[0]: int(l.split()[1]) for l in out if l.strip()}
+    checked = 0
+    for name, value in header.items():
+        py = name[len("VGPU_"):]
+        if name == "VGPU_ABI_VERSION":
+            py = "VGPU_ABI_VERSION"
+        if hasattr(N, py):
+            assert getattr(N, py) == value or getattr(N, py) == value & 0xFFFFFFFF, (name, getattr(N, py), value)
+            checked += 1
+    assert checked >= 45, checked      # the binding names (nearly) everything the header defines
+
+
 def test_no_cpu_fallback_without_a_device(built_lib):
     import torch
     if torch.cuda.is_available():
