@@ -65,6 +65,23 @@ namespace query = viya::query;
 namespace util = viya::util;
 namespace cg = viya::codegen;
 
+// The adapter casts these enums of the reference straight into their include/vgpu.h counterparts: the orders must agree.
+static_assert((int)db::Metric::AggregationType::MAX == VGPU_AGG_MAX && (int)db::Metric::AggregationType::MIN == VGPU_AGG_MIN &&
+                  (int)db::Metric::AggregationType::SUM == VGPU_AGG_SUM && (int)db::Metric::AggregationType::AVG == VGPU_AGG_AVG &&
+                  (int)db::Metric::AggregationType::COUNT == VGPU_AGG_COUNT &&
+                  (int)db::Metric::AggregationType::BITSET == VGPU_AGG_BITSET,
+              "db::Metric::AggregationType (src/db/column.h:244) vs vgpu_agg");
+static_assert((int)util::TimeUnit::YEAR == VGPU_TU_YEAR && (int)util::TimeUnit::MONTH == VGPU_TU_MONTH &&
+                  (int)util::TimeUnit::WEEK == VGPU_TU_WEEK && (int)util::TimeUnit::DAY == VGPU_TU_DAY &&
+                  (int)util::TimeUnit::HOUR == VGPU_TU_HOUR && (int)util::TimeUnit::MINUTE == VGPU_TU_MINUTE &&
+                  (int)util::TimeUnit::SECOND == VGPU_TU_SECOND,
+              "util::TimeUnit (src/util/time.h:27) vs vgpu_time_unit");
+static_assert((int)query::RelOpFilter::Operator::EQUAL == VGPU_OP_EQ && (int)query::RelOpFilter::Operator::NOT_EQUAL == VGPU_OP_NE &&
+                  (int)query::RelOpFilter::Operator::LESS == VGPU_OP_LT && (int)query::RelOpFilter::Operator::LESS_EQUAL == VGPU_OP_LE &&
+                  (int)query::RelOpFilter::Operator::GREATER == VGPU_OP_GT &&
+                  (int)query::RelOpFilter::Operator::GREATER_EQUAL == VGPU_OP_GE,
+              "query::RelOpFilter::Operator (src/query/filter.h:54-61) vs vgpu_relop");
+
 inline void check(int rc, const char *what) {
   if (rc != VGPU_OK) throw std::runtime_error(std::string(what) + ": " + vgpu_last_error());
 }
