@@ -35,7 +35,7 @@ def _num_domain(rng, typ, small):
     return [str(v) for v in vals]
 
 
-def _make_table(rng, idx):
+def _make_table(rng, idx, rich=False):
     dims, mets = [], []
     gen = {}      # column name -> list of input strings to draw from
     kinds = {}    # column name -> ("str"|"num"|"time"|"micro"|"bool"|"metric"|"bitset"|"count", numeric type)
@@ -83,13 +83,23 @@ def _make_table(rng, idx):
         if k == "count" and have_count:
             k = "value"
         if k == "count":
-            mets.append({"name": "count", "type": "count"})
+            conf = {"name": "count", "type": "count"}
+            if rich and rng.random() < 0.4:
+                conf["max"] = 10**11                      # -> a 64-bit count column (column.cc:278-284)
+            mets.append(conf)
             kinds["count"] = ("count", "uint")
             have_count = True
         elif k == "bitset":
             name = f"u{m}"
             conf = {"name": name, "type": "bitset"}
             dom = rng.choice([5, 40, 4000000000])
+            if rich:
+                # the id type follows "max" (column.cc:54-62, 398-400): ubyte / ushort / uint ids in a Roaring, ulong ids
+                # in a Roaring64Map (bitset.h:27-31); a filter literal on the metric has that type (Q7)
+                mx = rng.choice([200, 50000, None, 10**12])
+                if mx:
+                    conf["max"] = mx
+                dom = {200: rng.choice([5, 200]), 50000: rng.choice([40, 50000]), None: dom, 10**12: rng.choice([40, 10**12])}[mx]
             gen[name] = [str(rng.randrange(0, dom)) for _ in range(rng.randrange(3, 12))]
             mets.append(conf)
             kinds[name] = ("bitset", "uint")
@@ -184,11 +194,11 @@ def _make_query(rng, table, gen, kinds):
     return q
 
 
-def make_scenarios(seed=20261017, count=36, queries=6, prefix="fuzz", rows=(20, 260)):
+def make_scenarios(seed=20261017, count=36, queries=6, prefix="fuzz", rows=(20, 260), rich=False):
     rng = random.Random(seed)
     out = []
     for i in range(count):
-        table, gen, kinds = _make_table(rng, i)
+        table, gen, kinds = _make_table(rng, i, rich)
         nrows = rng.choice([0, 9, 40, 120, 300]) if i % 9 == 0 else rng.randrange(*rows)
         cols = [d["name"] for d in table["dimensions"]] + [m["name"] for m in table["metrics"] if m["type"] != "count"]
         data = [[rng.choice(gen[c]) for c in cols] for _ in range(nrows)]
@@ -199,7 +209,9 @@ def make_scenarios(seed=20261017, count=36, queries=6, prefix="fuzz", rows=(20, 
 
 
 # two batches: small tables with deep filters, then larger ones (more merged upserts, multi-id bitset cells, wrapped sums)
-FUZZ_SCENARIOS = make_scenarios() + make_scenarios(seed=77001, count=24, prefix="fuzzb", rows=(300, 1200))
+# (a third batch, "fuzzc": bitset metrics of every id width — ubyte / ushort / uint / ulong — and 64-bit count columns)
+FUZZ_SCENARIOS = (make_scenarios() + make_scenarios(seed=77001, count=24, prefix="fuzzb", rows=(300, 1200))
+                  + make_scenarios(seed=5150, count=24, prefix="fuzzc", rows=(40, 500), rich=True))
 
 
 # ---- select / search: rows in (segment, tuple) order with the per-segment limit quirk; distinct values ----

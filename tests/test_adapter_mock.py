@@ -5,7 +5,7 @@ reference's own FilterArgsPacker, lowers the query to a vgpu_plan, calls the C A
 table (HAVING, util::Format, the sort on formatted strings through StringNumCmp, skip / limit). tests/adapter_mock_harness.cc
 links it, inside a reference process, against a MOCK of include/vgpu.h instead of libvgpu.so: the mock records the plan
 and answers with the group table the oracle computed (the oracle is pinned to the real reference on the same records).
-For every golden record the real reference answered (gtests, scenarios, edge cases, 338 fuzz queries):
+For every golden record the real reference answered (gtests, scenarios, edge cases, 478 fuzz queries):
 
   * the rows `query->Accept(GpuQueryRunner)` sends == the reference's rows, QueryStats included;
   * the plan the C++ adapter lowered == the plan the Python mirror lowers (viyadb_b200/query.py — the host the GPU

@@ -96,7 +96,7 @@ FUZZ = [r for r in G.records("ref_fuzz_scenarios.jsonl") if "error" not in r]
                     reason="written after the round's GPU budget was spent: never run on a B200 yet (VGPU_FUZZ=1 runs it)")
 @pytest.mark.parametrize("flags", [0, 1], ids=["auto", "force_hash"])
 def test_reference_fuzz(vdb, flags):
-    """The 338 seeded random queries (tests/golden/fuzz_scenarios.py) the real reference answered, on its own segment
+    """The 478 seeded random queries (tests/golden/fuzz_scenarios.py) the real reference answered, on its own segment
     bytes. The oracle (test_oracle_golden.py) and the host side (test_host_fuzz.py) are pinned to them on the CPU; this
     is the device leg."""
     failures = []

@@ -1,5 +1,5 @@
 """The host side of the drop-in (viyadb_b200/query.py: QueryFactory, FilterArgsPacker, plan lowering, post-aggregation)
-on the 360 seeded random queries of tests/golden/ref_fuzz_scenarios.jsonl — WITHOUT a GPU: the group table a device scan
+on the 504 seeded random queries of tests/golden/ref_fuzz_scenarios.jsonl — WITHOUT a GPU: the group table a device scan
 would return is taken from the oracle (which tests/test_oracle_golden.py pins to the real reference on the same
 records), the host formats / filters (HAVING) / sorts / cuts it, and the rows must be the reference's rows.
 

@@ -2,7 +2,7 @@
 to the device program, segment pruning, key-domain tightening — the source vgpu.cu compiles) and csrc/device_arith.h
 (leaf_mask16, gen_compare, post_compare — the source the kernels compile) are built with plain g++
 (tests/planner_harness.cc) and run over every golden record the real reference answered — its own gtest queries, the
-scenario / edge-case runs and the 360 seeded random queries of tests/golden/fuzz_scenarios.py:
+scenario / edge-case runs and the 504 seeded random queries of tests/golden/fuzz_scenarios.py:
 
   * row predicate: program(row) == the oracle's eval_filter(row) for every row of every segment, through the unrolled
     conjunction path where the planner chooses it AND through the stack interpreter;
