@@ -29,7 +29,9 @@ from viyadb_b200 import db as vdb_mod
 from viyadb_b200.query import FilterArgsPacker, QueryFactory
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-RECS = [r for name in ("ref_gtest.jsonl", "ref_scenarios.jsonl", "ref_edge_scenarios.jsonl", "ref_fuzz_scenarios.jsonl")
+# aggregate records, and the select / search records too: they share the predicate and the pruning (scan.cc:40-73)
+RECS = [r for name in ("ref_gtest.jsonl", "ref_scenarios.jsonl", "ref_edge_scenarios.jsonl", "ref_fuzz_scenarios.jsonl",
+                       "ref_gtest_select.jsonl", "ref_select_scenarios.jsonl", "ref_fuzz_select_scenarios.jsonl")
         for r in G.records(name) if "error" not in r and "seg" in r]
 U64P = C.POINTER(C.c_uint64)
 
@@ -177,7 +179,7 @@ def test_planner_program_matches_oracle(lib, rec):
                 lib.h_planner_eval_rows(C.c_void_p(handle), C.c_uint64(n), pa, C.c_int(force), got.ctypes.data_as(C.POINTER(C.c_uint8)))
                 bad = np.nonzero(got.astype(bool) != want)[0]
                 assert len(bad) == 0, ("row predicate", si, int(bad[0]), force)
-            for dc in query.dimension_cols:
+            for dc in (query.dimension_cols if q["type"] == "aggregate" else []):
                 ci = t.schema_index(dc.dim)
                 key_lo[ci] = min(key_lo.get(ci, 2**64 - 1), int(cols[ci].min()))
                 key_hi[ci] = max(key_hi.get(ci, 0), int(cols[ci].max()))
