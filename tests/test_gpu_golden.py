@@ -1,8 +1,6 @@
 """CUDA path vs the REAL reference: every aggregate query of the reference's own gtest suite (and
 the oracle_cli scenarios), on the very segment bytes the reference scanned (golden dumps), through
 the C ABI. Integer results, keys and QueryStats bit-exact; double sums within 1e-12 relative."""
-import os
-
 import pytest
 
 import golden_util as G
@@ -88,24 +86,3 @@ def test_reference_edge_cases(vdb, rec, flags):
             pytest.skip("key wider than 64 bits")
         raise
 
-
-FUZZ = [r for r in G.records("ref_fuzz_scenarios.jsonl") if "error" not in r]
-
-
-@pytest.mark.skipif(os.environ.get("VGPU_FUZZ") != "1",
-                    reason="written after the round's GPU budget was spent: never run on a B200 yet (VGPU_FUZZ=1 runs it)")
-@pytest.mark.parametrize("flags", [0, 1], ids=["auto", "force_hash"])
-def test_reference_fuzz(vdb, flags):
-    """The 478 seeded random queries (tests/golden/fuzz_scenarios.py) the real reference answered, on its own segment
-    bytes. The oracle (test_oracle_golden.py) and the host side (test_host_fuzz.py) are pinned to them on the CPU; this
-    is the device leg."""
-    failures = []
-    for rec in FUZZ:
-        try:
-            run(vdb, rec, flags=flags)
-        except vdb.VgpuError as e:
-            if not (flags == 1 and e.code == -2):    # key wider than 64 bits under a forced hash table
-                failures.append((G.rec_id(rec), repr(e)))
-        except AssertionError as e:
-            failures.append((G.rec_id(rec), str(e)[:200]))
-    assert not failures, f"{len(failures)} of {len(FUZZ)} fuzz queries differ from the reference: {failures[:5]}"
